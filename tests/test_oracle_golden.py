@@ -1,0 +1,140 @@
+"""Pin the CPU oracle (oracle/contrad_oracle.py) against the fixtures produced by running the
+UNMODIFIED reference (tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import contrad_oracle as O
+
+
+def _unpack(packed):
+    return {k: packed[i] for i, k in enumerate(O.PARAM_FIELDS)}
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_augment_forward_backward_matches_reference(golden_dir):
+    fx = _load(golden_dir, "augment_simclr.pt")
+    assert fx["fields"] == list(O.PARAM_FIELDS)
+    orders = set()
+    for case in fx["cases"]:
+        x = case["x"].clone().requires_grad_(True)
+        y = O.augment_simclr(x, _unpack(case["params"]), case["order"])
+        (y * case["dy"]).sum().backward()
+        orders.add(case["order"])
+        assert torch.allclose(y, case["y"], atol=5e-6, rtol=0), (y - case["y"]).abs().max()
+        assert torch.allclose(x.grad, case["dx"], atol=2e-5, rtol=1e-5), (x.grad - case["dx"]).abs().max()
+    assert orders == {0, 1}
+
+
+def test_sampler_replays_reference_rng_stream(golden_dir):
+    """Same seeds -> same explicit draws as stored (and those reproduced the reference output)."""
+    fx = _load(golden_dir, "augment_simclr.pt")
+    for case in fx["cases"]:
+        b, _, h, w = case["x"].shape
+        np.random.seed(case["seed"]); torch.manual_seed(case["seed"])
+        x = torch.rand(b, 3, h, w); _ = torch.randn(b, 3, h, w)
+        assert torch.equal(x, case["x"])
+        params, order = O.sample_simclr_params(b, h, w)
+        assert order == case["order"]
+        assert torch.equal(O.pack_params(params), case["params"])
+
+
+def test_contrastive_losses_match_reference(golden_dir):
+    fx = _load(golden_dir, "contrastive.pt")
+    for case in fx["cases"]:
+        a, b, c = (case[k].clone().requires_grad_(True) for k in "abc")
+        l1 = O.nt_xent(a, b, 0.1)
+        g1 = torch.autograd.grad(l1, [a, b])
+        assert abs(float(l1) - case["nt_xent"]) < 1e-5 * max(1, abs(case["nt_xent"]))
+        for g, r in zip(g1, case["nt_xent_grads"]):
+            assert torch.allclose(g, r, atol=1e-6, rtol=1e-4)
+        l2 = O.supcon_fake(a, b, c, 0.1)
+        g2 = torch.autograd.grad(l2, [a, b, c])
+        assert abs(float(l2) - case["supcon"]) < 1e-5 * max(1, abs(case["supcon"]))
+        for g, r in zip(g2, case["supcon_grads"]):
+            assert torch.allclose(g, r, atol=1e-6, rtol=1e-4)
+        assert abs(float(O.nt_xent(a, b, 0.5)) - case["nt_xent_t05"]) < 1e-5
+
+
+def test_spectral_norm_matches_torch_hook(golden_dir):
+    fx = _load(golden_dir, "spectral_norm.pt")
+    for name, rec in fx.items():
+        w = rec["weight_orig"].clone().requires_grad_(True)
+        u, v = rec["u0"].clone(), rec["v0"].clone()
+        w_hat = O.spectral_normalize(w, u, v, training=True)
+        assert torch.allclose(u, rec["u1"], atol=1e-6) and torch.allclose(v, rec["v1"], atol=1e-6)
+        assert torch.allclose(w_hat, rec["w_hat"], atol=1e-6, rtol=1e-5)
+        if name == "conv":
+            y = F.conv2d(rec["x"], w_hat, rec["bias"], padding=1)
+        else:
+            y = F.linear(rec["x"], w_hat, rec["bias"])
+        assert torch.allclose(y, rec["y"], atol=1e-5, rtol=1e-5)
+        y.pow(2).sum().backward()
+        assert torch.allclose(w.grad, rec["grad_weight_orig"], atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("loss_kind", ["nonsat", "hinge"])
+def test_small_sndcgan_step_matches_reference(golden_dir, loss_kind):
+    fx = _load(golden_dir, "sndcgan_small.pt")[loss_kind]
+    sd_d = {k: v.clone() for k, v in fx["sd_d"].items()}
+    sd_g = {k: v.clone() for k, v in fx["sd_g"].items()}
+    n = fx["images"].shape[0]
+    O.set_requires_grad(sd_g, False); O.set_requires_grad(sd_d, True)
+    with torch.no_grad():
+        gen = O.g_sndcgan_forward(sd_g, fx["z_d"], ngf=4)
+    assert torch.allclose(gen, fx["d_step"]["gen"], atol=1e-5)
+    l_con, l_dis, ex = O.loss_d(sd_d, fx["images"], gen, _unpack(fx["aug_d"]), fx["order_d"], loss=loss_kind)
+    (l_con + l_dis).backward()
+    ref = fx["d_step"]
+    assert abs(float(l_con) - ref["l_con"]) < 1e-4 * abs(ref["l_con"])
+    assert abs(float(l_dis) - ref["l_dis"]) < 1e-4 * abs(ref["l_dis"])
+    assert abs(float(ex["d_real"]) - ref["d_real"]) < 1e-5 + 1e-3 * abs(ref["d_real"])
+    assert abs(float(ex["d_gen"]) - ref["d_gen"]) < 1e-5 + 1e-3 * abs(ref["d_gen"])
+    for k, gn in ref["grad_norms"].items():
+        mine = float(sd_d[k].grad.double().norm()) if sd_d[k].grad is not None else 0.0
+        assert abs(mine - gn) <= 1e-3 * gn + 1e-7, (k, mine, gn)
+    for k, buf in fx["uv_after_d_step"].items():
+        assert torch.allclose(sd_d[k], buf, atol=1e-5), k
+    # G step through the frozen D (second power iteration happens here as in the reference)
+    O.set_requires_grad(sd_g, True); O.set_requires_grad(sd_d, False)
+    for v in sd_d.values():
+        v.grad = None
+    gen2 = O.g_sndcgan_forward(sd_g, fx["z_g"], ngf=4)
+    l_gen = O.loss_g(sd_d, gen2, _unpack(fx["aug_g"]), fx["order_g"], loss=loss_kind)
+    l_gen.backward()
+    assert abs(float(l_gen) - fx["g_step"]["l_gen"]) < 1e-4 * abs(fx["g_step"]["l_gen"]) + 1e-7
+    for k, gn in fx["g_step"]["grad_norms"].items():
+        mine = float(sd_g[k].grad.double().norm())
+        assert abs(mine - gn) <= 2e-3 * gn + 1e-8, (k, mine, gn)
+
+
+def test_config1_two_full_steps_match_reference(golden_dir):
+    """BASELINE config 1 (SNDCGAN+ContraD, c10_b512.gin hyper-parameters, b64, CPU): two complete
+    train steps incl. Adam agree with the reference's scalars within the north_star tolerance (1e-3)."""
+    with open(os.path.join(golden_dir, "config1_scalars.json")) as f:
+        fx = json.load(f)
+    n = fx["batch"]
+    gen_w = torch.Generator().manual_seed(fx["weights_seed"])
+    sd_d = O.make_d_state(generator=gen_w)
+    sd_g = O.make_g_state(generator=gen_w)
+    opt_g = O.Adam(O.trainable(sd_g).values(), 2e-4)
+    opt_d = O.Adam(O.trainable(sd_d).values(), 2e-4)
+    np.random.seed(fx["data_seed"]); torch.manual_seed(fx["data_seed"])
+    for ref in fx["steps"]:
+        images = torch.rand(n, 3, 32, 32)
+        z_d = O.sample_latent(n)
+        aug_d = O.sample_simclr_params(3 * n, 32, 32)
+        z_g = O.sample_latent(n)
+        aug_g = O.sample_simclr_params(n, 32, 32)
+        got = O.train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=ref["step"])
+        l_con = got["l_con_pos"] + got["l_con_neg"]
+        assert abs(l_con - ref["l_con"]) < 1e-3 * abs(ref["l_con"])
+        for key in ("l_dis", "l_gen", "d_grad_norm", "g_grad_norm"):
+            assert abs(got[key] - ref[key]) < 1e-3 * abs(ref[key]), (key, got[key], ref[key])
