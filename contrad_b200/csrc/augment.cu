@@ -1,0 +1,397 @@
+// Fused SimCLR augmentation chain (random-resized-crop -> hflip -> color-jitter -> grayscale)
+// for sm_100a: ONE forward kernel and ONE backward kernel replace the ~120 ATen ops / ~25
+// full-tensor round trips of the reference chain (reference: augment/__init__.py:106-112,
+// augment/spatial.py:84-148, augment/color_jitter.py:44-104, augment/utils.py:27-63; exact
+// arithmetic restated in SURVEY.md A.1 and oracle/contrad_oracle.py).
+//
+// Roofline: HBM-bound, 8 algorithmic bytes per tensor element (4 read + 4 written, fp32).
+//
+// Small-image path (H*W <= 4096, i.e. every 32x32 / 64x64 config): one CTA owns one image.
+//   * the [3,H,W] image is staged into shared memory with coalesced, L1-bypassing float4 loads;
+//   * every thread keeps its output pixels (quads of 4 along W, 3 channels) in registers across
+//     the per-channel mean that `adjust_contrast` needs (a block reduction - the image never
+//     leaves the SM between the stages of the chain);
+//   * bilinear taps (reflection padding, align_corners=False) are gathered from shared memory;
+//     the horizontal flip is an index mirror folded into the gather (exact at power-of-two
+//     sizes);
+//   * output is written once with float4 streaming stores.
+// Per-sample parameters arrive as an SoA block [11, B] (see PARAM_FIELDS in the oracle /
+// include/contrad_b200.h); sampling them stays on the host so that the reference's numpy +
+// torch RNG interleaving is reproduced exactly.
+//
+// Backward (needed in every G step): HSV is straight-through (color_jitter.py:97-104); contrast is
+// dx = f*dy' + (1-f)*mean(dy') with dy' = dy*1[0<=u<=1]; gray/blend are linear; the crop is the
+// transposed bilinear gather, accumulated with shared-memory atomics and written out once.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace {
+
+constexpr int kMaxThreads = 256;
+
+struct SampleParams {
+    float sx, sy, bx, by, flip, cj_on, fc, fh, fs, fv, gray_on;
+};
+
+__device__ __forceinline__ SampleParams load_params(const float* __restrict__ p, int B, int b) {
+    SampleParams s;
+    s.sx = __ldg(p + 0 * B + b);
+    s.sy = __ldg(p + 1 * B + b);
+    s.bx = __ldg(p + 2 * B + b);
+    s.by = __ldg(p + 3 * B + b);
+    s.flip = __ldg(p + 4 * B + b);
+    s.cj_on = __ldg(p + 5 * B + b);
+    s.fc = __ldg(p + 6 * B + b);
+    s.fh = __ldg(p + 7 * B + b);
+    s.fs = __ldg(p + 8 * B + b);
+    s.fv = __ldg(p + 9 * B + b);
+    s.gray_on = __ldg(p + 10 * B + b);
+    return s;
+}
+
+// grid_sample(padding_mode='reflection', align_corners=False): reflect about -0.5 and size-0.5,
+// clip to [0, size-1].
+__device__ __forceinline__ float fold_coord(float coord, float size) {
+    float t = fabsf(coord + 0.5f);
+    float extra = fmodf(t, size);
+    int flips = (int)floorf(t / size);
+    float r = (flips & 1) ? (size - extra - 0.5f) : (extra - 0.5f);
+    return fminf(fmaxf(r, 0.f), size - 1.f);
+}
+
+struct Tap {
+    int i0, i1;
+    float w0, w1;
+};
+
+// Source taps of output index `o` along an axis of length n for scale s and bias b.
+__device__ __forceinline__ Tap axis_tap(int o, int n, float s, float b) {
+    float fn = (float)n;
+    float base = (2.f * (float)o + 1.f) / fn - 1.f;
+    float g = s * base + b;
+    float p = fold_coord(((g + 1.f) * fn - 1.f) * 0.5f, fn);
+    float p0 = floorf(p);
+    Tap t;
+    t.i0 = (int)p0;
+    t.w1 = p - p0;
+    t.w0 = 1.f - t.w1;
+    t.i1 = t.i0 + 1;
+    if (t.i1 > n - 1) {   // out-of-range tap contributes zero
+        t.i1 = n - 1;
+        t.w1 = 0.f;
+    }
+    return t;
+}
+
+// RandomHSVFunction.forward on one pixel (augment/color_jitter.py:83-95, augment/utils.py:27-38,55-63).
+__device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float fh, float fs, float fv) {
+    float cmax = fmaxf(r, fmaxf(g, b));
+    float cmin = fminf(r, fminf(g, b));
+    float hue = atan2f(1.7320508075688772f * (g - b), 2.f * r - g - b);
+    if (hue < 0.f) hue += 6.283185307179586f;
+    hue = hue / 6.283185307179586f;
+    float sat = 1.f - cmin / (cmax + 1e-8f);
+    float val = cmax;
+    if (!isfinite(hue)) hue = 0.f;
+    if (!isfinite(sat)) sat = 0.f;
+    if (!isfinite(val)) val = 0.f;
+    float h = hue + (fh * 255.f) / 360.f;
+    h = h - floorf(h);
+    float s = sat * fs;
+    float v = val * fv;
+    h = fminf(fmaxf(h, 0.f), 1.f);
+    s = fminf(fmaxf(s, 0.f), 1.f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    float c = v * s;
+    float h6 = h * 6.f;
+    float k, t;
+    k = 5.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = fminf(fmaxf(fminf(k, 4.f - k), 0.f), 1.f); r = v - c * t;
+    k = 3.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = fminf(fmaxf(fminf(k, 4.f - k), 0.f), 1.f); g = v - c * t;
+    k = 1.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = fminf(fmaxf(fminf(k, 4.f - k), 0.f), 1.f); b = v - c * t;
+}
+
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+// Stage one [3,H,W] image into shared memory (coalesced float4, streaming).
+__device__ __forceinline__ void stage_image(const float* __restrict__ src, float* dst, int n_elems) {
+    for (int e = threadIdx.x * 4; e < n_elems; e += blockDim.x * 4) {
+        float4 v = ldg_stream4(src + e);
+        *reinterpret_cast<float4*>(dst + e) = v;
+    }
+}
+
+// crop+flip for the quad (row i, cols j0..j0+3): out[c][k]
+__device__ __forceinline__ void gather_quad(const float* xs, int H, int W, int i, int j0, const SampleParams& sp,
+                                            float (&out)[3][4]) {
+    const int HW = H * W;
+    Tap ty = axis_tap(i, H, sp.sy, sp.by);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int j = j0 + k;
+        int jj = (sp.flip < 0.f) ? (W - 1 - j) : j;
+        Tap tx = axis_tap(jj, W, sp.sx, sp.bx);
+        float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
+        const float* r0 = xs + ty.i0 * W;
+        const float* r1 = xs + ty.i1 * W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            out[c][k] = r0[c * HW + tx.i0] * w00 + r0[c * HW + tx.i1] * w01 + r1[c * HW + tx.i0] * w10 +
+                        r1[c * HW + tx.i1] * w11;
+        }
+    }
+}
+
+template <int QPT>
+__global__ void __launch_bounds__(kMaxThreads)
+augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
+                          int B, int H, int W, int order) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                      // [3*H*W]
+    float* red = smem + 3 * H * W;         // [3*32]
+    const int b = blockIdx.x;
+    const int HW = H * W, Wq = W >> 2, nquads = HW >> 2;
+    const SampleParams sp = load_params(params, B, b);
+    stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);
+    __syncthreads();
+
+    float v[QPT][3][4];
+    bool live[QPT];
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        int quad = threadIdx.x + q * blockDim.x;
+        live[q] = quad < nquads;
+        if (live[q]) {
+            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, sp, v[q]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[q][c][k] = 0.f;
+        }
+    }
+
+    if (sp.cj_on != 0.f) {          // uniform across the CTA (one image per CTA)
+        if (order == 1) {
+#pragma unroll
+            for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], sp.fh, sp.fs, sp.fv);
+        }
+        float sums[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < QPT; ++q)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sums[c] += (v[q][c][0] + v[q][c][1]) + (v[q][c][2] + v[q][c][3]);
+        block_sum<3>(sums, red);
+        const float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float m = sums[c] * inv;
+#pragma unroll
+            for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[q][c][k] = clamp01((v[q][c][k] - m) * sp.fc + m);
+        }
+        if (order == 0) {
+#pragma unroll
+            for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], sp.fh, sp.fs, sp.fv);
+        }
+    }
+    float* yb = y + (size_t)b * 3 * HW;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        if (!live[q]) continue;
+        int quad = threadIdx.x + q * blockDim.x;
+        if (sp.gray_on != 0.f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float l = 0.299f * v[q][0][k] + 0.587f * v[q][1][k] + 0.114f * v[q][2][k];
+                v[q][0][k] = l; v[q][1][k] = l; v[q][2][k] = l;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            stg_stream4(yb + c * HW + quad * 4, make_float4(v[q][c][0], v[q][c][1], v[q][c][2], v[q][c][3]));
+    }
+}
+
+template <int QPT>
+__global__ void __launch_bounds__(kMaxThreads)
+augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                          const float* __restrict__ params, int B, int H, int W, int order) {
+    extern __shared__ __align__(16) float smem[];
+    const int HW = H * W, Wq = W >> 2, nquads = HW >> 2;
+    float* xs = smem;                  // [3*HW] forward image
+    float* gs = smem + 3 * HW;         // [3*HW] dx accumulator
+    float* red = smem + 6 * HW;        // [3*32]
+    const int b = blockIdx.x;
+    const SampleParams sp = load_params(params, B, b);
+    stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);
+    for (int e = threadIdx.x; e < 3 * HW; e += blockDim.x) gs[e] = 0.f;
+    __syncthreads();
+
+    float f[QPT][3][4];   // forward value at the contrast input (crop+flip, optionally hsv)
+    float g[QPT][3][4];   // gradient
+    bool live[QPT];
+    const float* dyb = dy + (size_t)b * 3 * HW;
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        int quad = threadIdx.x + q * blockDim.x;
+        live[q] = quad < nquads;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { f[q][c][k] = 0.f; g[q][c][k] = 0.f; }
+        if (!live[q]) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float4 t = ldg_stream4(dyb + c * HW + quad * 4);
+            g[q][c][0] = t.x; g[q][c][1] = t.y; g[q][c][2] = t.z; g[q][c][3] = t.w;
+        }
+        if (sp.gray_on != 0.f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float s = g[q][0][k] + g[q][1][k] + g[q][2][k];
+                g[q][0][k] = 0.299f * s; g[q][1][k] = 0.587f * s; g[q][2][k] = 0.114f * s;
+            }
+        }
+    }
+    if (sp.cj_on != 0.f) {
+#pragma unroll
+        for (int q = 0; q < QPT; ++q) {
+            if (!live[q]) continue;
+            int quad = threadIdx.x + q * blockDim.x;
+            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, sp, f[q]);
+            if (order == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hsv_jitter(f[q][0][k], f[q][1][k], f[q][2][k], sp.fh, sp.fs, sp.fv);
+            }
+        }
+        float sums[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < QPT; ++q)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sums[c] += (f[q][c][0] + f[q][c][1]) + (f[q][c][2] + f[q][c][3]);
+        block_sum<3>(sums, red);
+        const float inv = 1.f / (float)HW;
+        float gsum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float m = sums[c] * inv;
+#pragma unroll
+            for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float u = (f[q][c][k] - m) * sp.fc + m;
+                    float gg = (u >= 0.f && u <= 1.f) ? g[q][c][k] : 0.f;   // clamp backward (inclusive)
+                    g[q][c][k] = gg;
+                    gsum[c] += gg;
+                }
+        }
+        block_sum<3>(gsum, red);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float gm = gsum[c] * inv * (1.f - sp.fc);
+#pragma unroll
+            for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[q][c][k] = sp.fc * g[q][c][k] + gm;
+        }
+    }
+    // transposed crop: scatter into the shared accumulator
+#pragma unroll
+    for (int q = 0; q < QPT; ++q) {
+        if (!live[q]) continue;
+        int quad = threadIdx.x + q * blockDim.x;
+        int i = quad / Wq, j0 = (quad % Wq) * 4;
+        Tap ty = axis_tap(i, H, sp.sy, sp.by);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int j = j0 + k;
+            int jj = (sp.flip < 0.f) ? (W - 1 - j) : j;
+            Tap tx = axis_tap(jj, W, sp.sx, sp.bx);
+            float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float gv = g[q][c][k];
+                float* base = gs + c * HW;
+                atomicAdd(base + ty.i0 * W + tx.i0, gv * w00);
+                if (w01 != 0.f) atomicAdd(base + ty.i0 * W + tx.i1, gv * w01);
+                if (w10 != 0.f) atomicAdd(base + ty.i1 * W + tx.i0, gv * w10);
+                if (w11 != 0.f) atomicAdd(base + ty.i1 * W + tx.i1, gv * w11);
+            }
+        }
+    }
+    __syncthreads();
+    float* dxb = dx + (size_t)b * 3 * HW;
+    for (int e = threadIdx.x * 4; e < 3 * HW; e += blockDim.x * 4)
+        stg_stream4(dxb + e, *reinterpret_cast<const float4*>(gs + e));
+}
+
+struct LaunchShape {
+    int threads, qpt;
+};
+
+bool pick_shape(int H, int W, LaunchShape* s) {
+    int nquads = (H * W) / 4;
+    int threads = nquads < kMaxThreads ? ((nquads + 31) / 32) * 32 : kMaxThreads;
+    int qpt = (nquads + threads - 1) / threads;
+    if (qpt > 4) return false;
+    s->threads = threads;
+    s->qpt = qpt == 3 ? 4 : qpt;
+    return true;
+}
+
+}  // namespace
+
+extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* params, int B, int H, int W,
+                                        int order, void* stream) {
+    CB200_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (order == 0 || order == 1), "augment_fwd: bad shape/order");
+    CB200_CHECK_ARG(W % 4 == 0 && (H * W) % 4 == 0, "augment_fwd: W must be a multiple of 4 (got %d)", W);
+    CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                    "augment_fwd: x/y must be 16-byte aligned");
+    if (B == 0) return CB200_OK;
+    LaunchShape ls;
+    CB200_CHECK_ARG(pick_shape(H, W, &ls),
+                    "augment_fwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
+    size_t smem = (size_t)(3 * H * W + 96) * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LAUNCH_FWD(Q)                                                                                          \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(augment_simclr_fwd_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        augment_simclr_fwd_kernel<Q><<<B, ls.threads, smem, st>>>(x, y, params, B, H, W, order);               \
+    } while (0)
+    if (ls.qpt == 1) LAUNCH_FWD(1); else if (ls.qpt == 2) LAUNCH_FWD(2); else LAUNCH_FWD(4);
+#undef LAUNCH_FWD
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("augment_simclr_fwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_augment_simclr_bwd(const float* x, const float* dy, float* dx, const float* params, int B,
+                                        int H, int W, int order, void* stream) {
+    CB200_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (order == 0 || order == 1), "augment_bwd: bad shape/order");
+    CB200_CHECK_ARG(W % 4 == 0, "augment_bwd: W must be a multiple of 4 (got %d)", W);
+    CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
+                      reinterpret_cast<uintptr_t>(dx)) & 15) == 0, "augment_bwd: pointers must be 16-byte aligned");
+    if (B == 0) return CB200_OK;
+    LaunchShape ls;
+    CB200_CHECK_ARG(pick_shape(H, W, &ls),
+                    "augment_bwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
+    size_t smem = (size_t)(6 * H * W + 96) * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LAUNCH_BWD(Q)                                                                                          \
+    do {                                                                                                       \
+        cudaFuncSetAttribute(augment_simclr_bwd_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        augment_simclr_bwd_kernel<Q><<<B, ls.threads, smem, st>>>(x, dy, dx, params, B, H, W, order);          \
+    } while (0)
+    if (ls.qpt == 1) LAUNCH_BWD(1); else if (ls.qpt == 2) LAUNCH_BWD(2); else LAUNCH_BWD(4);
+#undef LAUNCH_BWD
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("augment_simclr_bwd");
+    return CB200_OK;
+}

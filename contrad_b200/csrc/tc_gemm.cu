@@ -1,0 +1,497 @@
+// tcgen05 / TMA "tap GEMM" for sm_100a: one warp-specialised kernel that covers every dense
+// contraction whose A operand is a (shifted) box of an NHWC tensor:
+//
+//     out[row(m), n] = epilogue( sum_{tap t} sum_{c} A[m shifted by tap t, c] * Bw[n, t*C + c] )
+//
+//   * 3x3 stride-1 convolution forward and its data-gradient            (SNDCGAN D layers 3,5,7)
+//   * 4x4 stride-2 convolution forward (space-to-depth view, no copies)  (layers 2,4,6)
+//   * 4x4 stride-2 data-gradient == ConvTranspose2d(4,2,1) forward, as 4 output-parity classes
+//     of 2x2-tap convolutions (blockIdx.z = class)                       (D dgrad, G forward)
+//   * plain C = A * B^T GEMMs (the MLP heads)                            (1 tap, 2-D A)
+//
+// Replaces the cuDNN implicit-GEMM / cuBLAS calls behind nn.Conv2d / nn.Linear of the reference
+// (models/gan/sndcgan.py:91-109, models/gan/base.py:14-35,92-101).
+//
+// Design (Blackwell-native): operands are fp32 in HBM and are fed to the tensor core as TF32
+// (kind::tf32, fp32 accumulate in TMEM).  A tile = 128 output pixels x 32 channels (one 128-byte
+// swizzle span) is fetched by ONE TMA box load per k-block; im2col never exists - the tap shift is
+// a coordinate offset of the box and zero padding is TMA out-of-bounds fill.  B tile = BN x 32 of
+// the K-major weight matrix.  Warp roles: warp0 = TMA producer, warp1 = MMA issuer (single elected
+// thread), warp2 = TMEM allocator, warps4-7 = epilogue (tcgen05.ld -> bias / LeakyReLU / lrelu'
+// mask / TF32 rounding -> global).  smem ring of kStages (full/empty mbarriers); tcgen05.commit
+// releases ring slots and signals the epilogue.
+//
+// Roofline: tensor pipe.  kind::tf32 M=128,N=BN,K=8 per instruction; algorithmic FLOPs =
+// 2*M*N*K_total per launch (DESIGN.md lists them per layer).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                       // fp32 elements = 128 bytes = one swizzle span
+constexpr int kATileBytes = kBlockM * kBlockK * 4;   // 16 KB
+constexpr int kMaxTaps = 16;
+constexpr int kThreads = 256;
+
+struct TapGemmParams {
+    CUtensorMap tmap_a;
+    CUtensorMap tmap_b;
+    int box[4];           // A box extent along spatial dims 1..4 (product == 128)
+    int tiles[4];         // tile counts along dims 1..4
+    int extent[4];        // valid extent along dims 1..4 (rows beyond are not stored)
+    long long ostride[4]; // output-row stride of each dim
+    long long cls_off[4]; // output-row offset of each class
+    int tap[4][kMaxTaps][5];   // [class][tap] -> {c_add, d1, d2, d3, d4}
+    int ntaps, cblocks;   // k-blocks = ntaps * cblocks
+    int ldo;              // floats between consecutive output rows
+    int b_rows_per_cls;   // row offset into the B map per class
+    float* out;
+    const float* bias;    // [N] or null
+    const float* dact;    // same addressing as out; multiplies by (dact > 0 ? 1 : slope); or null
+    float slope;          // LeakyReLU slope applied after bias (1.0 = identity) when dact == null
+    int round_out;        // round outputs to TF32 (they feed another tensor-core GEMM)
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int kBTileBytes = BN * kBlockK * 4;
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int cls = blockIdx.z;
+    const int n0 = blockIdx.y * BN;
+    const int num_kb = p.ntaps * p.cblocks;
+
+    // tile -> base coordinates along the 4 spatial dims
+    int base[4];
+    {
+        int t = blockIdx.x;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            base[d] = (t % p.tiles[d]) * p.box[d];
+            t /= p.tiles[d];
+        }
+    }
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&p.tmap_a);
+        tc::prefetch_tmap(&p.tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(tmem_full_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc(tmem_slot, BN);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int t = kb / p.cblocks;
+                const int cb = kb - t * p.cblocks;
+                tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * L::kStageBytes;
+                uint8_t* sb = sa + kATileBytes;
+                tc::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                const int* tp = p.tap[cls][t];
+                tc::tma_load_5d(sa, &p.tmap_a, &full_bar[stage], cb * kBlockK + tp[0], base[0] + tp[1],
+                                base[1] + tp[2], base[2] + tp[3], base[3] + tp[4]);
+                tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * kBlockK, cls * p.b_rows_per_cls + n0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = tc::idesc_tf32(kBlockM, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            tc::mbar_wait(&full_bar[stage], phase);
+            tc::fence_after_sync();
+            if (tc::elect_one()) {
+                const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
+                const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 8; ++k) {
+                    const uint64_t adesc = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                    tc::mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                }
+                tc::mma_commit(&empty_bar[stage]);
+                if (kb == num_kb - 1) tc::mma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        int r = q * 32 + lane;
+        bool valid = true;
+        long long orow = p.cls_off[cls];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int rd = r % p.box[d];
+            r /= p.box[d];
+            int x = base[d] + rd;
+            valid = valid && (x < p.extent[d]);
+            orow += (long long)x * p.ostride[d];
+        }
+        float* orow_ptr = p.out + orow * p.ldo + n0;
+        const float* drow_ptr = p.dact ? p.dact + orow * p.ldo + n0 : nullptr;
+        tc::mbar_wait(tmem_full_bar, 0);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+            tc::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[j + e]);
+                    if (p.bias) {
+                        float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                        o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+                    }
+                    if (drow_ptr) {
+                        float4 a = __ldg(reinterpret_cast<const float4*>(drow_ptr + c0 + j));
+                        o[0] *= (a.x > 0.f) ? 1.f : p.slope;
+                        o[1] *= (a.y > 0.f) ? 1.f : p.slope;
+                        o[2] *= (a.z > 0.f) ? 1.f : p.slope;
+                        o[3] *= (a.w > 0.f) ? 1.f : p.slope;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = (o[e] > 0.f) ? o[e] : o[e] * p.slope;
+                    }
+                    if (p.round_out) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
+                    }
+                    *reinterpret_cast<float4*>(orow_ptr + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// rank-5 fp32 tensor map with 128B swizzle; dims[0] is the contiguous one.
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+    auto fn = get_encode_fn();
+    if (!fn) {
+        cb200_set_error("cuTensorMapEncodeTiled driver entry point not available");
+        return CB200_ERR_TMAP;
+    }
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i];
+    }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        cb200_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu)",
+                        (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                        (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                        (unsigned long long)(rank > 4 ? dims[4] : 0));
+        return CB200_ERR_TMAP;
+    }
+    return CB200_OK;
+}
+
+int ilog2_floor(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// split 128 output rows over (w, h, b): w fastest
+void pick_spatial_box(int Wo, int Ho, int* wt, int* ht, int* bt) {
+    *wt = Wo < kBlockM ? Wo : kBlockM;
+    int rest = kBlockM / *wt;
+    *ht = Ho < rest ? Ho : rest;
+    *bt = rest / *ht;
+}
+
+struct Epilogue {
+    const float* bias;
+    const float* dact;
+    float slope;
+    int round_out;
+};
+
+template <int BN, int STAGES>
+int launch(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
+    using L = SmemLayout<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             L::kTotal);
+        if (e != cudaSuccess) {
+            cb200_set_error("%s: cudaFuncSetAttribute(smem=%d): %s", name, L::kTotal, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    dim3 grid(m_tiles, n_tiles, classes);
+    tap_gemm_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, st>>>(p);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH(name);
+    return CB200_OK;
+}
+
+int dispatch(const TapGemmParams& p, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
+    if (N % 128 == 0) return launch<128, 3>(p, m_tiles, N / 128, classes, st, name);
+    if (N % 64 == 0) return launch<64, 6>(p, m_tiles, N / 64, classes, st, name);
+    if (N % 32 == 0) return launch<32, 6>(p, m_tiles, N / 32, classes, st, name);
+    cb200_set_error("%s: N=%d must be a multiple of 32", name, N);
+    return CB200_ERR_ARG;
+}
+
+int check_ptr16(const void* p, const char* what) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) {
+        cb200_set_error("%s must be 16-byte aligned", what);
+        return CB200_ERR_ARG;
+    }
+    return CB200_OK;
+}
+
+// Common set-up for an NHWC tensor [Bn, Hs, Ws, C] traversed with unit spatial stride.
+int conv_like(const float* src, int Bn, int Hs, int Ws, int C,           // A tensor (NHWC)
+              int Wo, int Ho,                                             // positions per image along w / h
+              const float* wmat, int N, int ntaps, const int (*taps)[2],  // weight [N(*classes), ntaps*C]; taps = {dh, dw}
+              int classes, const int (*cls_taps)[4][2],                   // optional per-class taps (classes == 4)
+              float* out, int ldo, long long os_w, long long os_h, long long os_b, const long long* cls_off,
+              const Epilogue& ep, cudaStream_t st, const char* name) {
+    CB200_CHECK_ARG(C % kBlockK == 0, "%s: channel count %d must be a multiple of 32", name, C);
+    CB200_CHECK_ARG(is_pow2(Wo) && is_pow2(Ho), "%s: spatial size %dx%d must be powers of two", name, Ho, Wo);
+    if (int e = check_ptr16(src, "activation pointer")) return e;
+    if (int e = check_ptr16(wmat, "weight pointer")) return e;
+    if (int e = check_ptr16(out, "output pointer")) return e;
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    int wt, ht, bt;
+    pick_spatial_box(Wo, Ho, &wt, &ht, &bt);
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)Ws, (uint64_t)Hs, (uint64_t)Bn, 1};
+    uint64_t strides[5] = {4, (uint64_t)C * 4, (uint64_t)Ws * C * 4, (uint64_t)Hs * Ws * C * 4,
+                           (uint64_t)Bn * Hs * Ws * C * 4};
+    uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)wt, (uint32_t)ht, (uint32_t)bt, 1};
+    if (int e = encode_map(&p.tmap_a, src, 5, dims, strides, box)) return e;
+    const int Ktot = ntaps * C;
+    uint64_t bdims[2] = {(uint64_t)Ktot, (uint64_t)N * classes};
+    uint64_t bstr[2] = {4, (uint64_t)Ktot * 4};
+    const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+    uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    if (int e = encode_map(&p.tmap_b, wmat, 2, bdims, bstr, bbox)) return e;
+    p.box[0] = wt; p.box[1] = ht; p.box[2] = bt; p.box[3] = 1;
+    p.tiles[0] = (Wo + wt - 1) / wt; p.tiles[1] = (Ho + ht - 1) / ht; p.tiles[2] = (Bn + bt - 1) / bt; p.tiles[3] = 1;
+    p.extent[0] = Wo; p.extent[1] = Ho; p.extent[2] = Bn; p.extent[3] = 1;
+    p.ostride[0] = os_w; p.ostride[1] = os_h; p.ostride[2] = os_b; p.ostride[3] = 0;
+    for (int c = 0; c < classes; ++c) {
+        p.cls_off[c] = cls_off ? cls_off[c] : 0;
+        for (int t = 0; t < ntaps; ++t) {
+            const int* hw = cls_taps ? cls_taps[c][t] : taps[t];
+            p.tap[c][t][0] = 0;
+            p.tap[c][t][1] = hw[1];   // dw
+            p.tap[c][t][2] = hw[0];   // dh
+            p.tap[c][t][3] = 0;
+            p.tap[c][t][4] = 0;
+        }
+    }
+    p.ntaps = ntaps; p.cblocks = C / kBlockK;
+    p.ldo = ldo; p.b_rows_per_cls = N;
+    p.out = out; p.bias = ep.bias; p.dact = ep.dact; p.slope = ep.slope; p.round_out = ep.round_out;
+    const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2];
+    return dispatch(p, N, m_tiles, classes, st, name);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+
+// out[M, N] (row stride ldo) = lrelu_slope( A[M, K] (row stride lda) * Bw[N, K]^T + bias ), TF32 tensor cores.
+extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, const float* bias, float* out,
+                                  long long ldo, int M, int N, int K, float slope, int round_out, void* stream) {
+    CB200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_nt: empty problem");
+    CB200_CHECK_ARG(K % kBlockK == 0, "gemm_nt: K=%d must be a multiple of 32", K);
+    CB200_CHECK_ARG(lda % 4 == 0 && ldo % 4 == 0, "gemm_nt: lda/ldo must be multiples of 4 floats");
+    if (int e = check_ptr16(a, "gemm_nt: A")) return e;
+    if (int e = check_ptr16(bw, "gemm_nt: B")) return e;
+    if (int e = check_ptr16(out, "gemm_nt: out")) return e;
+    TapGemmParams p;
+    memset(&p, 0, sizeof(p));
+    uint64_t dims[5] = {(uint64_t)K, (uint64_t)M, 1, 1, 1};
+    uint64_t strides[5] = {4, (uint64_t)lda * 4, (uint64_t)lda * 4 * M, (uint64_t)lda * 4 * M, (uint64_t)lda * 4 * M};
+    uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1, 1, 1};
+    if (int e = encode_map(&p.tmap_a, a, 5, dims, strides, box)) return e;
+    uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t bstr[2] = {4, (uint64_t)K * 4};
+    const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+    uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    if (int e = encode_map(&p.tmap_b, bw, 2, bdims, bstr, bbox)) return e;
+    p.box[0] = kBlockM; p.box[1] = 1; p.box[2] = 1; p.box[3] = 1;
+    p.tiles[0] = (M + kBlockM - 1) / kBlockM; p.tiles[1] = 1; p.tiles[2] = 1; p.tiles[3] = 1;
+    p.extent[0] = M; p.extent[1] = 1; p.extent[2] = 1; p.extent[3] = 1;
+    p.ostride[0] = 1;
+    p.ntaps = 1; p.cblocks = K / kBlockK;
+    p.ldo = (int)ldo; p.b_rows_per_cls = 0;
+    p.out = out; p.bias = bias; p.dact = nullptr; p.slope = slope; p.round_out = round_out;
+    return dispatch(p, N, p.tiles[0], 1, static_cast<cudaStream_t>(stream), "gemm_nt_tf32");
+}
+
+// y[B,Ho,Wo,Cout] = lrelu(conv(x[B,H,W,Cin], w) + bias), NHWC, w as GEMM matrix [Cout, ks*ks*Cin] (tap-major).
+// Supported: (ks=3, stride=1, pad=1) and (ks=4, stride=2, pad=1).
+extern "C" int cb200_conv2d_nhwc_fwd(const float* x, const float* wmat, const float* bias, float* y, int B, int H,
+                                     int W, int Cin, int Cout, int ks, int stride, float slope, int round_out,
+                                     void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Epilogue ep{bias, nullptr, slope, round_out};
+    if (ks == 3 && stride == 1) {
+        int taps[9][2];
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) { taps[kh * 3 + kw][0] = kh - 1; taps[kh * 3 + kw][1] = kw - 1; }
+        return conv_like(x, B, H, W, Cin, W, H, wmat, Cout, 9, taps, 1, nullptr, y, Cout, 1, W, (long long)H * W,
+                         nullptr, ep, st, "conv3x3s1_fwd");
+    }
+    if (ks == 4 && stride == 2) {
+        // space-to-depth view of x: dims (2C, W/2, 2, H/2, B); tap (kh,kw) -> (dh,ph),(dw,pw)
+        CB200_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv4x4s2_fwd: H, W must be even");
+        CB200_CHECK_ARG(Cin % kBlockK == 0, "conv4x4s2_fwd: Cin=%d must be a multiple of 32", Cin);
+        const int Ho = H / 2, Wo = W / 2;
+        CB200_CHECK_ARG(is_pow2(Wo) && is_pow2(Ho), "conv4x4s2_fwd: output size must be powers of two");
+        if (int e = check_ptr16(x, "conv4x4s2_fwd: x")) return e;
+        if (int e = check_ptr16(wmat, "conv4x4s2_fwd: w")) return e;
+        if (int e = check_ptr16(y, "conv4x4s2_fwd: y")) return e;
+        TapGemmParams p;
+        memset(&p, 0, sizeof(p));
+        int wt, ht, bt;
+        pick_spatial_box(Wo, Ho, &wt, &ht, &bt);
+        uint64_t dims[5] = {(uint64_t)2 * Cin, (uint64_t)Wo, 2, (uint64_t)Ho, (uint64_t)B};
+        uint64_t strides[5] = {4, (uint64_t)2 * Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)2 * W * Cin * 4,
+                               (uint64_t)H * W * Cin * 4};
+        uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)wt, 1, (uint32_t)ht, (uint32_t)bt};
+        if (int e = encode_map(&p.tmap_a, x, 5, dims, strides, box)) return e;
+        const int Ktot = 16 * Cin;
+        uint64_t bdims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
+        uint64_t bstr[2] = {4, (uint64_t)Ktot * 4};
+        const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
+        uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+        if (int e = encode_map(&p.tmap_b, wmat, 2, bdims, bstr, bbox)) return e;
+        p.box[0] = wt; p.box[1] = 1; p.box[2] = ht; p.box[3] = bt;
+        p.tiles[0] = (Wo + wt - 1) / wt; p.tiles[1] = 1; p.tiles[2] = (Ho + ht - 1) / ht; p.tiles[3] = (B + bt - 1) / bt;
+        p.extent[0] = Wo; p.extent[1] = 1; p.extent[2] = Ho; p.extent[3] = B;
+        p.ostride[0] = 1; p.ostride[1] = 0; p.ostride[2] = Wo; p.ostride[3] = (long long)Ho * Wo;
+        static const int dpar[4][2] = {{-1, 1}, {0, 0}, {0, 1}, {1, 0}};   // k -> (delta, parity)
+        for (int kh = 0; kh < 4; ++kh)
+            for (int kw = 0; kw < 4; ++kw) {
+                int* tp = p.tap[0][kh * 4 + kw];
+                tp[0] = dpar[kw][1] * Cin;   // channel offset selects the w-parity half
+                tp[1] = dpar[kw][0];         // dw (in half-res units)
+                tp[2] = dpar[kh][1];         // h parity
+                tp[3] = dpar[kh][0];         // dh
+                tp[4] = 0;
+            }
+        p.ntaps = 16; p.cblocks = Cin / kBlockK;
+        p.ldo = Cout; p.b_rows_per_cls = 0;
+        p.out = y; p.bias = bias; p.dact = nullptr; p.slope = slope; p.round_out = round_out;
+        return dispatch(p, Cout, p.tiles[0] * p.tiles[2] * p.tiles[3], 1, st, "conv4x4s2_fwd");
+    }
+    cb200_set_error("conv2d_nhwc_fwd: unsupported kernel/stride %d/%d", ks, stride);
+    return CB200_ERR_ARG;
+}
+
+// dx[B,H,W,Cin] = dgrad(dy[B,Ho,Wo,Cout], w) (* lrelu'(act_in) if act_in != null) (+ bias_out, lrelu if given).
+//   ks=3,stride=1: wmat_t = [Cin, 3*3*Cout] with tap index (kh*3+kw) holding W[co,ci,kh,kw]
+//   ks=4,stride=2: wmat_t = [4 classes (ph*2+pw)][Cin][4 taps][Cout]  (see pack_weights in weights.cu)
+// This is also ConvTranspose2d(4,2,1) / ConvTranspose2d(3,1,1) *forward* (G_SNDCGAN) with bias_out / slope.
+extern "C" int cb200_conv2d_nhwc_dgrad(const float* dy, const float* wmat_t, const float* act_in, const float* bias_out,
+                                       float* dx, int B, int H, int W, int Cin, int Cout, int ks, int stride,
+                                       float slope, int round_out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Epilogue ep{bias_out, act_in, slope, round_out};
+    if (ks == 3 && stride == 1) {
+        int taps[9][2];
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) { taps[kh * 3 + kw][0] = 1 - kh; taps[kh * 3 + kw][1] = 1 - kw; }
+        return conv_like(dy, B, H, W, Cout, W, H, wmat_t, Cin, 9, taps, 1, nullptr, dx, Cin, 1, W, (long long)H * W,
+                         nullptr, ep, st, "conv3x3s1_dgrad");
+    }
+    if (ks == 4 && stride == 2) {
+        CB200_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "conv4x4s2_dgrad: H, W must be even");
+        const int Ho = H / 2, Wo = W / 2;
+        // output parity p: taps (k, delta on the dy grid): p=0 -> (1,0),(3,-1);  p=1 -> (0,+1),(2,0)
+        static const int dsel[2][2] = {{0, -1}, {1, 0}};   // [parity][j] -> delta
+        int cls_taps[4][4][2];
+        long long cls_off[4];
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                int c = ph * 2 + pw;
+                cls_off[c] = (long long)ph * W + pw;
+                for (int jh = 0; jh < 2; ++jh)
+                    for (int jw = 0; jw < 2; ++jw) {
+                        cls_taps[c][jh * 2 + jw][0] = dsel[ph][jh];
+                        cls_taps[c][jh * 2 + jw][1] = dsel[pw][jw];
+                    }
+            }
+        return conv_like(dy, B, Ho, Wo, Cout, Wo, Ho, wmat_t, Cin, 4, nullptr, 4, cls_taps, dx, Cin, 2, 2LL * W,
+                         (long long)H * W, cls_off, ep, st, "conv4x4s2_dgrad");
+    }
+    cb200_set_error("conv2d_nhwc_dgrad: unsupported kernel/stride %d/%d", ks, stride);
+    return CB200_ERR_ARG;
+}
