@@ -1,0 +1,203 @@
+"""Layer classes of the SimCLR chain.  Each class keeps the reference's constructor signature (they are
+bound by gin by CLASS NAME, configs/defaults/augment.gin) and can run alone; ``FusedSimCLR`` runs the
+whole chain in one kernel launch."""
+import math
+import numbers
+
+import gin
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..functional import AugmentSimCLRFn
+
+_N_FIELDS = 11   # sx, sy, bx, by, flip, cj_on, contrast, hue, sat, val, gray_on
+
+
+def _identity_block(batch, device):
+    p = torch.zeros(_N_FIELDS, batch, device=device)
+    p[0] = 1.0; p[1] = 1.0; p[4] = 1.0; p[6] = 1.0; p[8] = 1.0; p[9] = 1.0
+    return p
+
+
+@gin.configurable
+class NoAugment(nn.Module):
+    def forward(self, input):
+        return input
+
+
+@gin.configurable
+class RandomResizeCropLayer(nn.Module):
+    """Inception crop parameters (augment/spatial.py:96-148)."""
+
+    def __init__(self, scale, ratio=(3. / 4., 4. / 3.)):
+        super().__init__()
+        self.register_buffer("_eye", torch.eye(2, 3))      # kept for state_dict compatibility
+        self.scale = scale
+        self.ratio = ratio
+
+    def sample(self, inputs):
+        """numpy draws in the reference order (spatial.py:119-136). Returns float32 [4, B] on the host."""
+        n, _, width, height = inputs.shape
+        area = height * width
+        target_area = np.random.uniform(*self.scale, n * 10) * area
+        log_ratio = (math.log(self.ratio[0]), math.log(self.ratio[1]))
+        aspect = np.exp(np.random.uniform(*log_ratio, n * 10))
+        w = np.round(np.sqrt(target_area * aspect))
+        h = np.round(np.sqrt(target_area / aspect))
+        keep = (0 < w) * (w <= width) * (0 < h) * (h <= height)
+        w, h = w[keep], h[keep]
+        if len(w) > n:
+            sel = np.random.choice(len(w), n, replace=False)
+            w, h = w[sel], h[sel]
+        k = len(w)
+        bias_w = np.random.randint(w - width, width - w + 1) / width
+        bias_h = np.random.randint(h - height, height - h + 1) / height
+        block = np.zeros((4, n), dtype=np.float32)
+        block[0], block[1] = 1.0, 1.0
+        block[0, :k] = w / width
+        block[1, :k] = h / height
+        block[2, :k] = bias_w
+        block[3, :k] = bias_h
+        return torch.from_numpy(block)
+
+    def forward(self, inputs):
+        p = _identity_block(inputs.shape[0], inputs.device)
+        p[0:4] = self.sample(inputs).to(inputs.device, non_blocking=True)
+        return AugmentSimCLRFn.apply(inputs, p, 0)
+
+
+@gin.configurable
+class HorizontalFlipLayer(nn.Module):
+    """augment/spatial.py:70-93."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("_eye", torch.eye(2, 3))
+
+    def sample(self, inputs):
+        n = inputs.size(0)
+        return torch.bernoulli(torch.ones(n, device=inputs.device) * 0.5) * 2 - 1
+
+    def forward(self, inputs):
+        p = _identity_block(inputs.shape[0], inputs.device)
+        p[4] = self.sample(inputs)
+        return AugmentSimCLRFn.apply(inputs, p, 0)
+
+
+@gin.configurable
+class ColorJitterLayer(nn.Module):
+    """augment/color_jitter.py:15-78 (ranges validated like the reference's _check_input)."""
+
+    def __init__(self, brightness, contrast, saturation, hue):
+        super().__init__()
+        self.brightness = self._range(brightness, "brightness")
+        self.contrast = self._range(contrast, "contrast")
+        self.saturation = self._range(saturation, "saturation")
+        self.hue = self._range(hue, "hue", center=0, bound=(-0.5, 0.5), clip_first_on_zero=False)
+
+    @staticmethod
+    def _range(value, name, center=1, bound=(0, float("inf")), clip_first_on_zero=True):
+        if isinstance(value, numbers.Number):
+            if value < 0:
+                raise ValueError("If {} is a single number, it must be non negative.".format(name))
+            value = [center - value, center + value]
+            if clip_first_on_zero:
+                value[0] = max(value[0], 0)
+        elif isinstance(value, (tuple, list)) and len(value) == 2:
+            if not bound[0] <= value[0] <= value[1] <= bound[1]:
+                raise ValueError("{} values should be between {}".format(name, bound))
+        else:
+            raise TypeError("{} should be a single number or a list/tuple with lenght 2.".format(name))
+        if value[0] == value[1] == center:
+            value = None
+        return value
+
+    def sample(self, inputs):
+        """Returns (order, contrast, hue, sat, val) drawn like color_jitter.py:44-75."""
+        n = inputs.size(0)
+        order = 0 if np.random.rand() > 0.5 else 1
+
+        def draw_contrast():
+            if self.contrast:
+                return inputs.new_empty(n, 1, 1, 1).uniform_(*self.contrast).view(n)
+            return inputs.new_ones(n)
+
+        def draw_hsv():
+            f_h = inputs.new_zeros(n, 1, 1)
+            f_s = inputs.new_ones(n, 1, 1)
+            f_v = inputs.new_ones(n, 1, 1)
+            if self.hue:
+                f_h.uniform_(*self.hue)
+            if self.saturation:
+                f_s = f_s.uniform_(*self.saturation)
+            if self.brightness:
+                f_v = f_v.uniform_(*self.brightness)
+            return f_h.view(n), f_s.view(n), f_v.view(n)
+
+        if order == 0:
+            f_c = draw_contrast()
+            f_h, f_s, f_v = draw_hsv()
+        else:
+            f_h, f_s, f_v = draw_hsv()
+            f_c = draw_contrast()
+        return order, f_c, f_h, f_s, f_v
+
+    def forward(self, inputs):
+        p = _identity_block(inputs.shape[0], inputs.device)
+        order, p[6], p[7], p[8], p[9] = self.sample(inputs)
+        p[5] = 1.0
+        return AugmentSimCLRFn.apply(inputs, p, order)
+
+
+@gin.configurable
+class RandomColorGrayLayer(nn.Module):
+    """augment/__init__.py:81-91."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("_weight", torch.tensor([[0.299, 0.587, 0.114]]).view(1, 3, 1, 1))
+
+    def forward(self, inputs):
+        p = _identity_block(inputs.shape[0], inputs.device)
+        p[10] = 1.0
+        return AugmentSimCLRFn.apply(inputs, p, 0)
+
+
+class RandomApply(nn.Module):
+    """augment/__init__.py:94-103: per-sample Bernoulli(p) mask blending x and fn(x)."""
+
+    def __init__(self, fn, p):
+        super().__init__()
+        self.fn = fn
+        self.p = p
+
+    def sample(self, inputs):
+        return torch.bernoulli(inputs.new_full((inputs.size(0),), self.p))
+
+    def forward(self, inputs):
+        mask = self.sample(inputs).view(-1, 1, 1, 1)
+        return inputs * (1 - mask) + self.fn(inputs) * mask
+
+
+class FusedSimCLR(nn.Sequential):
+    """nn.Sequential(RRC, HFlip, RandomApply(CJ), RandomApply(Gray)) whose forward is ONE kernel.
+    The child modules hold the gin-configured hyper-parameters and draw the random numbers (in the
+    reference order); the arithmetic is cb200_augment_simclr_fwd/bwd."""
+
+    def sample_params(self, inputs):
+        rrc, flip, apply_cj, apply_gray = self[0], self[1], self[2], self[3]
+        n, dev = inputs.shape[0], inputs.device
+        p = torch.empty(_N_FIELDS, n, device=dev)
+        p[0:4] = rrc.sample(inputs).to(dev, non_blocking=True)
+        p[4] = flip.sample(inputs)
+        p[5] = apply_cj.sample(inputs)
+        order, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs)
+        p[10] = apply_gray.sample(inputs)
+        return p, order
+
+    def forward(self, inputs):
+        if inputs.dim() != 4 or inputs.shape[1] != 3:
+            raise ValueError("FusedSimCLR expects [B,3,H,W] images, got %s" % (tuple(inputs.shape),))
+        params, order = self.sample_params(inputs)
+        return AugmentSimCLRFn.apply(inputs, params, order)

@@ -1,0 +1,198 @@
+// First discriminator layer of SNDCGAN: Conv2d(3 -> 64, 3x3, stride 1, pad 1) + bias + LeakyReLU,
+// with the `x*2-1` input affine folded in (reference: models/gan/sndcgan.py:91-93,122-124).
+//
+// K = 27 makes this layer HBM/LSU-bound (AI ~ 13 FLOP/B), so it is a register-tiled
+// SIMT direct convolution rather than a tensor-core GEMM:
+//   forward : NCHW [B,3,H,W] image in -> NHWC [B,H,W,64] activation out (the layout the tcgen05
+//             kernels of the next layers consume), TF32-rounded because it feeds tcgen05.mma.
+//             CTA = 4 output rows x 32 columns of one image; thread = 8 pixels x 4 channels.
+//             Algorithmic bytes: 12 B/pixel in + 256 B/pixel out.
+//   wgrad   : dW[64,3,3,3] and db[64] from dY (NHWC, already multiplied by lrelu') and the image.
+//   dgrad   : (G step only) runs on the tensor cores through cb200_conv2d_nhwc_dgrad with the input
+//             channels padded 3 -> 32; `conv_first_dgrad_finish` extracts the 3 real channels,
+//             applies the factor 2 of the input affine and transposes NHWC -> NCHW.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kCo = 64;
+constexpr int kThreads = 256;
+constexpr int kRows = 4;        // output rows per CTA
+constexpr int kCols = 32;       // output columns per CTA
+
+// wmat: [64][27] with column ci*9 + kh*3 + kw (the OIHW weight / sigma), bias [64]
+__global__ void __launch_bounds__(kThreads)
+conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ sigma,
+                      const float* __restrict__ bias, float* __restrict__ y, int H, int W, float slope,
+                      int round_out) {
+    __shared__ float xs[3][kRows + 2][kCols + 2];
+    __shared__ __align__(16) float ws[27][kCo];
+    const int b = blockIdx.z;
+    const int h0 = blockIdx.y * kRows;
+    const int w0 = blockIdx.x * kCols;
+    const float inv_sigma = sigma ? sigma[1] : 1.f;
+    for (int i = threadIdx.x; i < 27 * kCo; i += kThreads) {
+        int co = i / 27, t = i % 27;
+        ws[t][co] = __ldg(w + i) * inv_sigma;
+    }
+    for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
+        int c = i / ((kRows + 2) * (kCols + 2));
+        int r = (i / (kCols + 2)) % (kRows + 2);
+        int cc = i % (kCols + 2);
+        int hh = h0 + r - 1, ww = w0 + cc - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * 2.f - 1.f;
+        xs[c][r][cc] = v;
+    }
+    __syncthreads();
+    const int cg = threadIdx.x & 15;          // channels 4cg .. 4cg+3
+    const int pg = threadIdx.x >> 4;          // 16 pixel groups: row = pg/4, 8-column segment = pg%4
+    const int row = pg >> 2, seg = (pg & 3) * 8;
+    float acc[8][4];
+    const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { acc[p][0] = bv.x; acc[p][1] = bv.y; acc[p][2] = bv.z; acc[p][3] = bv.w; }
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            float in[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) in[j] = xs[ci][row + kh][seg + j];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4 wv = *reinterpret_cast<const float4*>(&ws[ci * 9 + kh * 3 + kw][cg * 4]);
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    acc[p][0] += in[p + kw] * wv.x; acc[p][1] += in[p + kw] * wv.y;
+                    acc[p][2] += in[p + kw] * wv.z; acc[p][3] += in[p + kw] * wv.w;
+                }
+            }
+        }
+    }
+    const int hh = h0 + row;
+    if (hh >= H) return;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int ww = w0 + seg + p;
+        if (ww >= W) continue;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v = acc[p][e];
+            v = v > 0.f ? v : v * slope;
+            o[e] = round_out ? round_tf32(v) : v;
+        }
+        *reinterpret_cast<float4*>(y + (((size_t)b * H + hh) * W + ww) * kCo + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// dW_hat[co][ci*9+kh*3+kw] += sum_pixels dY[pix][co] * (2x-1)[ci][h+kh-1][w+kw-1];   db[co] += sum dY
+// CTA = one image row-block of 4 rows x 32 cols (same tiling as forward); threads: 16 channel groups
+// (4 channels) x 4 tap groups (7 taps; 27 = 7+7+7+6) x 4 pixel slices.
+__global__ void __launch_bounds__(kThreads)
+conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                        float* __restrict__ db, int H, int W) {
+    __shared__ float xs[3][kRows + 2][kCols + 2];
+    __shared__ __align__(16) float part[4][28][kCo];      // per pixel-slice partial dW (27 taps + 1 bias row)
+    const int b = blockIdx.z;
+    const int h0 = blockIdx.y * kRows;
+    const int w0 = blockIdx.x * kCols;
+    for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
+        int c = i / ((kRows + 2) * (kCols + 2));
+        int r = (i / (kCols + 2)) % (kRows + 2);
+        int cc = i % (kCols + 2);
+        int hh = h0 + r - 1, ww = w0 + cc - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * 2.f - 1.f;
+        xs[c][r][cc] = v;
+    }
+    __syncthreads();
+    const int cg = threadIdx.x & 15;
+    const int tg = (threadIdx.x >> 4) & 3;
+    const int ps = threadIdx.x >> 6;          // pixel slice = output row within the CTA
+    float acc[7][4];
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 7; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    const int hh = h0 + ps;
+    if (hh < H) {
+        const float* dyrow = dy + (((size_t)b * H + hh) * W + w0) * kCo + cg * 4;
+        const int ncols = min(kCols, W - w0);
+        for (int c = 0; c < ncols; ++c) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dyrow + (size_t)c * kCo));
+            if (tg == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
+#pragma unroll
+            for (int t = 0; t < 7; ++t) {
+                const int tap = tg * 7 + t;
+                if (tap < 27) {
+                    const int ci = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+                    const float xv = xs[ci][ps + kh][c + kw];
+                    acc[t][0] += g.x * xv; acc[t][1] += g.y * xv; acc[t][2] += g.z * xv; acc[t][3] += g.w * xv;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+        const int tap = tg * 7 + t;
+        if (tap < 27) *reinterpret_cast<float4*>(&part[ps][tap][cg * 4]) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    }
+    if (tg == 0) *reinterpret_cast<float4*>(&part[ps][27][cg * 4]) = make_float4(bacc[0], bacc[1], bacc[2], bacc[3]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 28 * kCo; i += kThreads) {
+        const int tap = i / kCo, co = i % kCo;
+        const float s = (part[0][tap][co] + part[1][tap][co]) + (part[2][tap][co] + part[3][tap][co]);
+        if (tap < 27) atomicAdd(dw + co * 27 + tap, s);
+        else if (db) atomicAdd(db + co, s);
+    }
+}
+
+// dx[b,c,h,w] = 2 * dpad[b,h,w,c]   (c < 3 of the 32 padded channels)
+__global__ void __launch_bounds__(kThreads)
+conv_first_dgrad_finish_kernel(const float* __restrict__ dpad, float* __restrict__ dx, int HW, int cpad,
+                               long long total) {
+    const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;   // over B*3*HW (NCHW order)
+    if (i >= total) return;
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % 3);
+    const long long b = i / (3LL * HW);
+    dx[i] = 2.f * __ldg(dpad + (b * HW + p) * cpad + c);
+}
+
+}  // namespace
+
+// y[B,H,W,64] = lrelu_slope(conv3x3(2x-1, w/sigma) + bias); x NCHW [B,3,H,W]; w = OIHW [64,3,3,3]; sigma [2] or NULL.
+extern "C" int cb200_conv_first_fwd(const float* x, const float* w, const float* sigma, const float* bias, float* y,
+                                    int B, int H, int W, float slope, int round_out, void* stream) {
+    CB200_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv_first_fwd: empty input");
+    CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv_first_fwd: y must be 16-byte aligned");
+    dim3 grid((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B);
+    conv_first_fwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, sigma, bias, y, H, W, slope,
+                                                                                    round_out);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("conv_first_fwd");
+    return CB200_OK;
+}
+
+// dw_hat[64,27] (OIHW order, gradient w.r.t. w/sigma) and db[64] are ACCUMULATED into (caller zeroes them).
+extern "C" int cb200_conv_first_wgrad(const float* x, const float* dy, float* dw_hat, float* db, int B, int H, int W,
+                                      void* stream) {
+    CB200_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv_first_wgrad: empty input");
+    dim3 grid((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B);
+    conv_first_wgrad_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dw_hat, db, H, W);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("conv_first_wgrad");
+    return CB200_OK;
+}
+
+// dx[B,3,H,W] = 2 * dpad[B,H,W,cpad][..., :3]
+extern "C" int cb200_conv_first_dgrad_finish(const float* dpad, float* dx, int B, int H, int W, int cpad, void* stream) {
+    CB200_CHECK_ARG(B > 0 && cpad >= 3, "conv_first_dgrad_finish: bad shape");
+    const long long total = (long long)B * 3 * H * W;
+    conv_first_dgrad_finish_kernel<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0,
+                                     static_cast<cudaStream_t>(stream)>>>(dpad, dx, H * W, cpad, total);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("conv_first_dgrad_finish");
+    return CB200_OK;
+}

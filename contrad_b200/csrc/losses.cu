@@ -1,0 +1,414 @@
+// Contrastive + GAN losses of ContraD for sm_100a (SIMT fp32, warp-shuffle reductions):
+//
+//   rownorm      F.normalize(x, dim=1, eps=1e-12)                      (training/gan/contrad.py:43,48)
+//   contrastive  NT-Xent  (training/criterion.py:24-45)  and  supcon-fake (training/gan/contrad.py:8-32),
+//                flash-style: the [2N,2N] / [3N,3N] similarity matrix, the -5e4 diagonal fill, the
+//                log-softmax, the positive mask of the reference (25-45 ATen ops, two R x R fp32 matrices)
+//                are never materialised - one pass computes row log-sum-exps and the loss, the
+//                backward pass recomputes the similarities and accumulates dZ directly.
+//                supcon only evaluates the N fake rows the loss keeps (the reference computes all 3N).
+//   gan_loss     nonsat / hinge / wgan / lsgan D and G losses + their gradients (contrad.py:52-64,75-80)
+//   colsum       bias gradients
+//
+// Similarities are computed in full fp32 (FFMA) on purpose: the logits are sim / tau with tau = 0.1,
+// so TF32 rounding of the operands would be amplified 10x in the softmax.  At
+// N = 512 the two losses are 0.27 + 0.20 GFLOP forward - ~1e-4 of the step's FLOPs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kD = 128;            // embedding width (d_project)
+constexpr int kWarps = 8;
+constexpr int kRowsPerWarp = 4;
+constexpr int kRowsPerCta = kWarps * kRowsPerWarp;   // 32
+constexpr int kJT = 32;            // columns per tile = one per lane
+constexpr int kZStride = kD + 4;   // padded smem row (float4-aligned, conflict-free 128-bit reads)
+
+// ------------------------------------------------------------------------------------------ rownorm
+__global__ void __launch_bounds__(256)
+rownorm_fwd_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ y, float* __restrict__ inv_norm,
+                   int rows, int d, float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (long long)row * ldx;
+    float ss = 0.f;
+    for (int k = lane; k < d; k += 32) { float v = xr[k]; ss += v * v; }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), eps);
+    for (int k = lane; k < d; k += 32) y[(long long)row * d + k] = xr[k] * inv;
+    if (lane == 0) inv_norm[row] = inv;
+}
+
+// dx = inv * (dy - y * <dy, y>)
+__global__ void __launch_bounds__(256)
+rownorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ inv_norm,
+                   float* __restrict__ dx, long long lddx, int rows, int d, int round_out) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* gr = dy + (long long)row * d;
+    const float* yr = y + (long long)row * d;
+    float dot = 0.f;
+    for (int k = lane; k < d; k += 32) dot += gr[k] * yr[k];
+    dot = warp_sum(dot);
+    const float inv = inv_norm[row];
+    for (int k = lane; k < d; k += 32) {
+        float v = inv * (gr[k] - yr[k] * dot);
+        dx[(long long)row * lddx + k] = round_out ? round_tf32(v) : v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ contrastive
+// mode 0: NT-Xent over R = 2N rows (all rows active);  mode 1: supcon-fake over R = 3N rows, active rows 2N..3N-1.
+struct RowSpec {
+    int gi;          // global row index
+    bool active;
+};
+
+__device__ __forceinline__ void load_ztile(float (*zt)[kZStride], const float* __restrict__ z, int j0, int R) {
+    // kJT rows x 128 floats, cooperative float4 loads by the whole CTA
+    for (int e = threadIdx.x; e < kJT * (kD / 4); e += kWarps * 32) {
+        const int r = e / (kD / 4), c4 = e % (kD / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j0 + r < R) v = __ldg(reinterpret_cast<const float4*>(z + (long long)(j0 + r) * kD) + c4);
+        *reinterpret_cast<float4*>(&zt[r][c4 * 4]) = v;
+    }
+}
+
+// s[r] = <z_i[r], z_j(lane)> for the warp's 4 rows
+__device__ __forceinline__ void dots4(const float (*zi)[kD], const float (*zt)[kZStride], int lane, float (&s)[kRowsPerWarp]) {
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) s[r] = 0.f;
+#pragma unroll 8
+    for (int k4 = 0; k4 < kD / 4; ++k4) {
+        const float4 b = *reinterpret_cast<const float4*>(&zt[lane][k4 * 4]);
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&zi[r][k4 * 4]);
+            s[r] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+contrastive_fwd_kernel(const float* __restrict__ z, int R, int N, int mode, float inv_tau, float* __restrict__ lse_out,
+                       float* __restrict__ row_loss) {
+    __shared__ __align__(16) float zt[kJT][kZStride];
+    __shared__ __align__(16) float zi_all[kWarps][kRowsPerWarp][kD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (mode == 1 ? 2 * N : 0) + blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;
+    float (*zi)[kD] = zi_all[warp];
+    int gi[kRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+        gi[r] = row0 + r;
+        for (int k = lane; k < kD; k += 32) zi[r][k] = (gi[r] < R) ? __ldg(z + (long long)gi[r] * kD + k) : 0.f;
+    }
+    float m[kRowsPerWarp], l[kRowsPerWarp], pos[kRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) { m[r] = -INFINITY; l[r] = 0.f; pos[r] = 0.f; }
+    for (int j0 = 0; j0 < R; j0 += kJT) {
+        __syncthreads();
+        load_ztile(zt, z, j0, R);
+        __syncthreads();
+        float s[kRowsPerWarp];
+        dots4(zi, zt, lane, s);
+        const int j = j0 + lane;
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            float v = s[r] * inv_tau;
+            if (j == gi[r]) v = -5e4f;
+            const bool in = j < R;
+            if (mode == 0) {
+                const int pj = gi[r] < N ? gi[r] + N : gi[r] - N;
+                if (in && j == pj) pos[r] += v;
+            } else {
+                if (in && j >= 2 * N && j != gi[r]) pos[r] += v;
+            }
+            const float vm = in ? v : -INFINITY;
+            const float tile_max = warp_max(vm);
+            const float new_m = fmaxf(m[r], tile_max);
+            float e = in ? __expf(v - new_m) : 0.f;
+            e = warp_sum(e);
+            l[r] = l[r] * __expf(m[r] - new_m) + e;
+            m[r] = new_m;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+        const float p = warp_sum(pos[r]);
+        if (lane == 0 && gi[r] < R) {
+            const float lse = m[r] + logf(l[r]);
+            const int local = gi[r] - (mode == 1 ? 2 * N : 0);
+            lse_out[local] = lse;
+            row_loss[local] = (mode == 0) ? -(p - lse) / (float)(2 * N) : -(p / (float)(N - 1) - lse) / (float)N;
+        }
+    }
+}
+
+// dZ[i] = gscale * inv_tau * sum_j (c_ij + c_ji) z_j,   c_ij = dL/dS_ij (see header comment of the file)
+__global__ void __launch_bounds__(kWarps * 32)
+contrastive_bwd_kernel(const float* __restrict__ z, int R, int N, int mode, float inv_tau,
+                       const float* __restrict__ lse, const float* __restrict__ gscale, float* __restrict__ dz) {
+    __shared__ __align__(16) float zt[kJT][kZStride];
+    __shared__ __align__(16) float zi_all[kWarps][kRowsPerWarp][kD];
+    __shared__ float coef_all[kWarps][kRowsPerWarp][kJT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;     // all R rows receive gradient
+    float (*zi)[kD] = zi_all[warp];
+    float (*coef)[kJT] = coef_all[warp];
+    const int first_active = (mode == 1) ? 2 * N : 0;
+    int gi[kRowsPerWarp];
+    float lse_i[kRowsPerWarp];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+        gi[r] = row0 + r;
+        for (int k = lane; k < kD; k += 32) zi[r][k] = (gi[r] < R) ? __ldg(z + (long long)gi[r] * kD + k) : 0.f;
+        lse_i[r] = (gi[r] < R && gi[r] >= first_active) ? __ldg(lse + gi[r] - first_active) : 0.f;
+    }
+    const float wpos = (mode == 0) ? 1.f / (float)(2 * N) : 1.f / (float)N;     // row weight
+    const float wsup = 1.f / (float)(N - 1);
+    float acc[kRowsPerWarp][4];
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+    for (int j0 = 0; j0 < R; j0 += kJT) {
+        __syncthreads();
+        load_ztile(zt, z, j0, R);
+        __syncthreads();
+        float s[kRowsPerWarp];
+        dots4(zi, zt, lane, s);
+        const int j = j0 + lane;
+        const bool jin = j < R;
+        const bool j_active = jin && j >= first_active;
+        const float lse_j = j_active ? __ldg(lse + j - first_active) : 0.f;
+#pragma unroll
+        for (int r = 0; r < kRowsPerWarp; ++r) {
+            const int i = gi[r];
+            float c = 0.f;
+            if (jin && i < R && j != i) {
+                const float v = s[r] * inv_tau;
+                if (i >= first_active) {          // c_ij: row i is a loss row
+                    float tgt;
+                    if (mode == 0) tgt = (j == (i < N ? i + N : i - N)) ? 1.f : 0.f;
+                    else tgt = (j >= 2 * N) ? wsup : 0.f;
+                    c += wpos * (__expf(v - lse_i[r]) - tgt);
+                }
+                if (j_active) {                   // c_ji: row j is a loss row (S symmetric)
+                    float tgt;
+                    if (mode == 0) tgt = (i == (j < N ? j + N : j - N)) ? 1.f : 0.f;
+                    else tgt = (i >= 2 * N) ? wsup : 0.f;
+                    c += wpos * (__expf(v - lse_j) - tgt);
+                }
+            }
+            coef[r][lane] = c;
+        }
+        __syncwarp();
+        // acc[r][k-slice] += sum_j coef[r][j] * z_j[k-slice];  lane owns k = 4*lane .. 4*lane+3
+#pragma unroll 4
+        for (int jj = 0; jj < kJT; ++jj) {
+            const float4 b = *reinterpret_cast<const float4*>(&zt[jj][lane * 4]);
+#pragma unroll
+            for (int r = 0; r < kRowsPerWarp; ++r) {
+                const float c = coef[r][jj];
+                acc[r][0] += c * b.x; acc[r][1] += c * b.y; acc[r][2] += c * b.z; acc[r][3] += c * b.w;
+            }
+        }
+        __syncwarp();
+    }
+    const float g = __ldg(gscale) * inv_tau;
+#pragma unroll
+    for (int r = 0; r < kRowsPerWarp; ++r) {
+        if (gi[r] < R)
+            *reinterpret_cast<float4*>(dz + (long long)gi[r] * kD + lane * 4) =
+                make_float4(acc[r][0] * g, acc[r][1] * g, acc[r][2] * g, acc[r][3] * g);
+    }
+}
+
+// out[0] = sum(v[0..n))   (single CTA, deterministic order)
+__global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float a[1] = {0.f};
+    for (int i = threadIdx.x; i < n; i += 256) a[0] += v[i];
+    block_sum<1>(a, red);
+    if (threadIdx.x == 0) out[0] = a[0];
+}
+
+// ------------------------------------------------------------------------------------------ GAN losses
+// kind: 0 nonsat, 1 hinge, 2 wgan, 3 lsgan.   d_real / d_gen: [N] with element stride `stride`.
+// out[0] = L_dis, out[1] = mean d_real, out[2] = mean d_gen;  grads (dL_dis/dd) written to g_real / g_gen.
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+gan_d_loss_kernel(const float* __restrict__ d_real, const float* __restrict__ d_gen, long long stride, int N,
+                  int kind, float* __restrict__ out, float* __restrict__ g_real, float* __restrict__ g_gen) {
+    __shared__ float red[4 * 32];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};     // loss_real, loss_gen, sum real, sum gen
+    const float invN = 1.f / (float)N;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        const float r = d_real[i * stride], g = d_gen[i * stride];
+        a[2] += r; a[3] += g;
+        float gr, gg;
+        if (kind == 0) { a[0] += softplus_f(-r); a[1] += softplus_f(g); gr = -sigmoid_f(-r); gg = sigmoid_f(g); }
+        else if (kind == 1) { a[0] += fmaxf(1.f - r, 0.f); a[1] += fmaxf(1.f + g, 0.f); gr = (1.f - r > 0.f) ? -1.f : 0.f; gg = (1.f + g > 0.f) ? 1.f : 0.f; }
+        else if (kind == 2) { a[0] += -r; a[1] += g; gr = -1.f; gg = 1.f; }
+        else { a[0] += 0.5f * (r - 1.f) * (r - 1.f); a[1] += 0.5f * g * g; gr = (r - 1.f); gg = g; }
+        g_real[i] = gr * invN;
+        g_gen[i] = gg * invN;
+    }
+    block_sum<4>(a, red);
+    if (threadIdx.x == 0) {
+        out[0] = (a[0] + a[1]) * invN;
+        out[1] = a[2] * invN;
+        out[2] = a[3] * invN;
+    }
+}
+
+// G loss: kind 0 nonsat softplus(-d).mean(); 3 lsgan 0.5*(d-1)^2.mean(); else -d.mean()
+__global__ void __launch_bounds__(256)
+gan_g_loss_kernel(const float* __restrict__ d_gen, long long stride, int N, int kind, float* __restrict__ out,
+                  float* __restrict__ g_gen) {
+    __shared__ float red[32];
+    float a[1] = {0.f};
+    const float invN = 1.f / (float)N;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        const float g = d_gen[i * stride];
+        float gg;
+        if (kind == 0) { a[0] += softplus_f(-g); gg = -sigmoid_f(-g); }
+        else if (kind == 3) { a[0] += 0.5f * (g - 1.f) * (g - 1.f); gg = g - 1.f; }
+        else { a[0] += -g; gg = -1.f; }
+        g_gen[i] = gg * invN;
+    }
+    block_sum<1>(a, red);
+    if (threadIdx.x == 0) out[0] = a[0] * invN;
+}
+
+// ------------------------------------------------------------------------------------------ column sums
+// out[n] (+)= sum_m x[m, n]   x: [M, N] with row stride ld
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long ld, int M, int N, int rows_per_cta, float* __restrict__ out) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const int m0 = blockIdx.y * rows_per_cta;
+    const int m1 = min(M, m0 + rows_per_cta);
+    float a = 0.f;
+    for (int m = m0; m < m1; ++m) a += __ldg(x + (long long)m * ld + n);
+    atomicAdd(out + n, a);
+}
+
+// out = dy * (act > 0 ? 1 : slope)   (LeakyReLU backward from the saved OUTPUT activation; slope > 0)
+__global__ void __launch_bounds__(256)
+lrelu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ act, float4* __restrict__ out, long long n4,
+                 float slope, int round_out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n4) return;
+    float4 g = dy[i];
+    const float4 a = act[i];
+    g.x *= a.x > 0.f ? 1.f : slope; g.y *= a.y > 0.f ? 1.f : slope;
+    g.z *= a.z > 0.f ? 1.f : slope; g.w *= a.w > 0.f ? 1.f : slope;
+    if (round_out) { g.x = round_tf32(g.x); g.y = round_tf32(g.y); g.z = round_tf32(g.z); g.w = round_tf32(g.w); }
+    out[i] = g;
+}
+
+}  // namespace
+
+extern "C" int cb200_lrelu_bwd(const float* dy, const float* act, float* out, long long n, float slope, int round_out,
+                               void* stream) {
+    CB200_CHECK_ARG(n > 0 && n % 4 == 0, "lrelu_bwd: element count must be a positive multiple of 4");
+    CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(act) |
+                      reinterpret_cast<uintptr_t>(out)) & 15) == 0, "lrelu_bwd: pointers must be 16-byte aligned");
+    const long long n4 = n / 4;
+    lrelu_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(act), reinterpret_cast<float4*>(out), n4,
+        slope, round_out);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("lrelu_bwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_rownorm_fwd(const float* x, long long ldx, float* y, float* inv_norm, int rows, int d, float eps,
+                                 void* stream) {
+    CB200_CHECK_ARG(rows > 0 && d > 0, "rownorm_fwd: empty input");
+    rownorm_fwd_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, y, inv_norm, rows, d, eps);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("rownorm_fwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_rownorm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, long long lddx,
+                                 int rows, int d, int round_out, void* stream) {
+    CB200_CHECK_ARG(rows > 0 && d > 0, "rownorm_bwd: empty input");
+    rownorm_bwd_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, inv_norm, dx, lddx, rows, d,
+                                                                                       round_out);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("rownorm_bwd");
+    return CB200_OK;
+}
+
+// z [R,128] L2-normalised rows; mode 0: NT-Xent (R = 2N); mode 1: supcon-fake (R = 3N, loss rows 2N..3N-1).
+// lse / row_loss: scratch of (mode ? N : 2N) floats; loss[0] <- the scalar loss.
+extern "C" int cb200_contrastive_fwd(const float* z, int N, int d, int mode, float temperature, float* lse,
+                                     float* row_loss, float* loss, void* stream) {
+    CB200_CHECK_ARG(N > 0 && (mode == 0 || mode == 1), "contrastive_fwd: bad N/mode");
+    CB200_CHECK_ARG(d == kD, "contrastive_fwd: embedding width %d != 128", d);
+    CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "contrastive_fwd: z must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int R = mode ? 3 * N : 2 * N;
+    const int active = mode ? N : 2 * N;
+    contrastive_fwd_kernel<<<(active + kRowsPerCta - 1) / kRowsPerCta, kWarps * 32, 0, st>>>(z, R, N, mode,
+                                                                                             1.f / temperature, lse,
+                                                                                             row_loss);
+    CB200_COUNT_LAUNCH();
+    sum_kernel<<<1, 256, 0, st>>>(row_loss, active, loss);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("contrastive_fwd");
+    return CB200_OK;
+}
+
+// dz [R,128] = gscale[0] * dLoss/dz  (gscale is a device scalar: the upstream gradient of the loss)
+extern "C" int cb200_contrastive_bwd(const float* z, int N, int d, int mode, float temperature, const float* lse,
+                                     const float* gscale, float* dz, void* stream) {
+    CB200_CHECK_ARG(N > 0 && (mode == 0 || mode == 1), "contrastive_bwd: bad N/mode");
+    CB200_CHECK_ARG(d == kD, "contrastive_bwd: embedding width %d != 128", d);
+    const int R = mode ? 3 * N : 2 * N;
+    contrastive_bwd_kernel<<<(R + kRowsPerCta - 1) / kRowsPerCta, kWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, R, N, mode, 1.f / temperature, lse, gscale, dz);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("contrastive_bwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_gan_d_loss(const float* d_real, const float* d_gen, long long stride, int N, int kind, float* out3,
+                                float* g_real, float* g_gen, void* stream) {
+    CB200_CHECK_ARG(N > 0 && kind >= 0 && kind <= 3, "gan_d_loss: bad N/kind");
+    gan_d_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_real, d_gen, stride, N, kind, out3, g_real, g_gen);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("gan_d_loss");
+    return CB200_OK;
+}
+
+extern "C" int cb200_gan_g_loss(const float* d_gen, long long stride, int N, int kind, float* out1, float* g_gen,
+                                void* stream) {
+    CB200_CHECK_ARG(N > 0 && kind >= 0 && kind <= 3, "gan_g_loss: bad N/kind");
+    gan_g_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_gen, stride, N, kind, out1, g_gen);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("gan_g_loss");
+    return CB200_OK;
+}
+
+// out[N] = column sums of x[M,N] (row stride ld); out is zeroed here.
+extern "C" int cb200_colsum(const float* x, long long ld, int M, int N, float* out, void* stream) {
+    CB200_CHECK_ARG(M > 0 && N > 0, "colsum: empty input");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+    if (e != cudaSuccess) { cb200_set_error("colsum: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    int row_chunks = (M + 255) / 256;
+    if (row_chunks > 1024) row_chunks = 1024;
+    const int rows_per_cta = (M + row_chunks - 1) / row_chunks;
+    dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
+    colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, rows_per_cta, out);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("colsum");
+    return CB200_OK;
+}

@@ -365,12 +365,14 @@ int conv_like(const float* src, int Bn, int Hs, int Ws, int C,           // A te
 // C ABI
 // ------------------------------------------------------------------------------------------------
 
-// out[M, N] (row stride ldo) = lrelu_slope( A[M, K] (row stride lda) * Bw[N, K]^T + bias ), TF32 tensor cores.
-extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, const float* bias, float* out,
-                                  long long ldo, int M, int N, int K, float slope, int round_out, void* stream) {
+// out[M, N] (row stride ldo) = epi( A[M, K] (row stride lda) * Bw[N, K]^T (row stride ldb) + bias ), TF32 tensor cores.
+// epi = LeakyReLU(slope) when dact == NULL, else multiply by lrelu'(dact[M,N]) (dact shares ldo with out).
+extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, long long ldb, const float* bias,
+                                  const float* dact, float* out, long long ldo, int M, int N, int K, float slope,
+                                  int round_out, void* stream) {
     CB200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_nt: empty problem");
     CB200_CHECK_ARG(K % kBlockK == 0, "gemm_nt: K=%d must be a multiple of 32", K);
-    CB200_CHECK_ARG(lda % 4 == 0 && ldo % 4 == 0, "gemm_nt: lda/ldo must be multiples of 4 floats");
+    CB200_CHECK_ARG(lda % 4 == 0 && ldo % 4 == 0 && ldb % 4 == 0, "gemm_nt: lda/ldb/ldo must be multiples of 4 floats");
     if (int e = check_ptr16(a, "gemm_nt: A")) return e;
     if (int e = check_ptr16(bw, "gemm_nt: B")) return e;
     if (int e = check_ptr16(out, "gemm_nt: out")) return e;
@@ -381,7 +383,7 @@ extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw
     uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1, 1, 1};
     if (int e = encode_map(&p.tmap_a, a, 5, dims, strides, box)) return e;
     uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
-    uint64_t bstr[2] = {4, (uint64_t)K * 4};
+    uint64_t bstr[2] = {4, (uint64_t)ldb * 4};
     const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
     uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
     if (int e = encode_map(&p.tmap_b, bw, 2, bdims, bstr, bbox)) return e;
@@ -391,7 +393,7 @@ extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw
     p.ostride[0] = 1;
     p.ntaps = 1; p.cblocks = K / kBlockK;
     p.ldo = (int)ldo; p.b_rows_per_cls = 0;
-    p.out = out; p.bias = bias; p.dact = nullptr; p.slope = slope; p.round_out = round_out;
+    p.out = out; p.bias = bias; p.dact = dact; p.slope = slope; p.round_out = round_out;
     return dispatch(p, N, p.tiles[0], 1, static_cast<cudaStream_t>(stream), "gemm_nt_tf32");
 }
 

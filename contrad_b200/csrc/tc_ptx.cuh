@@ -124,9 +124,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (64-bit): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | base_offset [49,52) | layout [61,64) (2 = SWIZZLE_128B).
-__host__ __device__ constexpr uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__host__ __device__ constexpr uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                 uint64_t layout_type) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (layout_type << 61);
+}
+// K-major operand, 128-byte swizzle with 16-byte atoms (TMA CU_TENSOR_MAP_SWIZZLE_128B).
+__host__ __device__ constexpr uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes, 2);
+}
+// MN-major 32-bit (TF32) operand: the only legal layout is SWIZZLE_128B_BASE32B = 128-byte swizzle with
+// 32-byte atoms (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in
+// 16-byte units: 32 MN elements contiguous, 4 K rows of 128 B per atom, SBO between K atoms, LBO between
+// 32-element MN chunks.
+__host__ __device__ constexpr uint64_t smem_desc_sw128_base32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc(saddr, lbo_bytes, sbo_bytes, 1);
 }
 // Instruction descriptor (32-bit) for kind::tf32, fp32 accumulate:
 // c_format=F32 (1<<4) | a_format=TF32 (2<<7) | b_format=TF32 (2<<10) | a_major<<15 | b_major<<16 |

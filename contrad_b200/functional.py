@@ -1,0 +1,370 @@
+"""torch.autograd.Functions of the ContraD hot path.  Every forward/backward is a sequence of calls
+into the C ABI (contrad_b200.kernels); there is no ATen math on the activation path and no CPU path.
+
+Layout convention inside the discriminator: activations are NHWC fp32, TF32-rounded by the producing
+epilogue; weights are consumed as packed GEMM matrices written by the spectral-norm kernels.
+"""
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# augmentation  (reference: augment/__init__.py:106-112 chain; backward = its autograd)
+# ------------------------------------------------------------------------------------------------
+class AugmentSimCLRFn(Function):
+    @staticmethod
+    def forward(ctx, x, params, order):
+        x = _c(x)
+        ctx.save_for_backward(x, params)
+        ctx.order = order
+        return K.augment_simclr_fwd(x, params, order)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, params = ctx.saved_tensors
+        dx = K.augment_simclr_bwd(x, _c(dy), params, ctx.order) if ctx.needs_input_grad[0] else None
+        return dx, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral norm + packing of every D_SNDCGAN weight  (models/gan/sndcgan.py:111-118)
+# ------------------------------------------------------------------------------------------------
+class SNLayerSpec(object):
+    """Static description of one spectrally-normalised layer of the discriminator."""
+
+    def __init__(self, name, module, kind, ks=1, stride=1):
+        self.name, self.module, self.kind, self.ks, self.stride = name, module, kind, ks, stride
+
+
+class SNPackFn(Function):
+    """(weight_orig_1 ... weight_orig_L) -> packed W/sigma matrices.
+
+    outputs (differentiable): conv packs in layer order, then Wcat (the three first-layer heads stacked,
+    columns in (h,w,c) order), then the three second-layer head packs.
+    side (python dict returned through `holder`): data-gradient packs, sigmas."""
+
+    @staticmethod
+    def forward(ctx, holder, training, *weights):
+        specs = holder["specs"]
+        dev = weights[0].device
+        sig, outs, side = [], [], {"dgrad": {}, "sigma": {}}
+        saved_uv = []
+        head1 = [s for s in specs if s.kind == "head1"]
+        wcat = wcat_t = None
+        for s, w in zip(specs, weights):
+            m = s.module
+            w = _c(w)
+            sigma = torch.empty(2, device=dev, dtype=torch.float32)
+            K.sn_power_iter(w, m.weight_u, m.weight_v, sigma, training=training)
+            sig.append(sigma)
+            saved_uv.append((m.weight_u.clone(), m.weight_v.clone()))
+            side["sigma"][s.name] = sigma
+            cout = w.shape[0]
+            if s.kind == "conv_first":
+                fwd = torch.empty(cout, 27, device=dev)
+                K.sn_pack_weights(w.view(cout, 27, 1, 1), sigma, fwd=fwd, ld_fwd=27, round_out=False)
+                dg = torch.zeros(32, 9 * cout, device=dev)
+                K.sn_pack_weights(w, sigma, dgrad=dg, dgrad_mode=1, round_out=True)
+                outs.append(fwd)
+                side["dgrad"][s.name] = dg
+            elif s.kind == "conv":
+                cin = w.shape[1]
+                fwd = torch.empty(cout, s.ks * s.ks * cin, device=dev)
+                if s.stride == 1:
+                    dg = torch.empty(cin, s.ks * s.ks * cout, device=dev)
+                    K.sn_pack_weights(w, sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=1)
+                else:
+                    dg = torch.empty(4 * cin, 4 * cout, device=dev)
+                    K.sn_pack_weights(w, sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=2)
+                outs.append(fwd)
+                side["dgrad"][s.name] = dg
+            elif s.kind == "head1":
+                nfeat = w.shape[1]
+                c_last, sh, sw = holder["feat_chw"]
+                if wcat is None:
+                    wcat = torch.empty(len(head1) * cout, nfeat, device=dev)
+                    wcat_t = torch.empty(nfeat, len(head1) * cout, device=dev)
+                idx = head1.index(s)
+                K.sn_pack_weights(w.view(cout, c_last, sh, sw), sigma, fwd=wcat[idx * cout:], ld_fwd=nfeat,
+                                  dgrad=wcat_t, dgrad_mode=3, ldt=wcat_t.shape[1], col0=idx * cout)
+                if idx == len(head1) - 1:
+                    outs.append(wcat)
+                    side["dgrad"]["wcat"] = wcat_t
+            else:   # head2: [cout, hidden]; the 1-output `linear.l2` is padded to 32 rows / 128 for wgrad
+                hid = w.shape[1]
+                rows = cout if cout % 32 == 0 else 32
+                fwd = torch.zeros(rows, hid, device=dev) if rows != cout else torch.empty(rows, hid, device=dev)
+                dg = torch.zeros(hid, rows, device=dev) if rows != cout else torch.empty(hid, rows, device=dev)
+                K.sn_pack_weights(w.view(cout, hid, 1, 1), sigma, fwd=fwd, ld_fwd=hid, dgrad=dg, dgrad_mode=3,
+                                  ldt=rows, col0=0)
+                outs.append(fwd)
+                side["dgrad"][s.name] = dg
+        holder["side"] = side
+        ctx.holder = holder
+        ctx.saved_uv = saved_uv
+        ctx.sig = sig
+        ctx.save_for_backward(*weights)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dpacks):
+        specs = ctx.holder["specs"]
+        weights = ctx.saved_tensors
+        grads = []
+        head1 = [s for s in specs if s.kind == "head1"]
+        n_conv = sum(1 for s in specs if s.kind in ("conv_first", "conv"))
+        for li, (s, w) in enumerate(zip(specs, weights)):
+            if not ctx.needs_input_grad[2 + li]:
+                grads.append(None)
+                continue
+            u, v = ctx.saved_uv[li]
+            sigma = ctx.sig[li]
+            cout = w.shape[0]
+            dw = torch.empty_like(w)
+            if s.kind == "conv_first":
+                g = dpacks[li]
+                grads.append(None if g is None else K.sn_weight_bwd(_c(g), 27, w.view(cout, 27, 1, 1), u, v, sigma, dw))
+            elif s.kind == "conv":
+                g = dpacks[li]
+                grads.append(None if g is None else K.sn_weight_bwd(_c(g), g.shape[1], w, u, v, sigma, dw))
+            elif s.kind == "head1":
+                g = dpacks[n_conv]
+                if g is None:
+                    grads.append(None)
+                    continue
+                g = _c(g)
+                idx = head1.index(s)
+                c_last, sh, sw = ctx.holder["feat_chw"]
+                grads.append(K.sn_weight_bwd(g[idx * cout:(idx + 1) * cout], g.shape[1], w.view(cout, c_last, sh, sw),
+                                             u, v, sigma, dw))
+            else:
+                pos = n_conv + 1 + [x for x in specs if x.kind == "head2"].index(s)
+                g = dpacks[pos]
+                grads.append(None if g is None else K.sn_weight_bwd(_c(g), g.shape[1], w.view(cout, w.shape[1], 1, 1),
+                                                                    u, v, sigma, dw))
+        return (None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# discriminator backbone  (models/gan/sndcgan.py:91-109,122-128)
+# ------------------------------------------------------------------------------------------------
+class SNDCGANBackboneFn(Function):
+    """x [B,3,H,W] (NCHW, in [0,1]) -> features [B, Hf*Wf*C] in (h, w, c) order (post-LeakyReLU).
+
+    args after x: for each conv layer (pack, bias); `holder` carries the data-gradient packs."""
+
+    SLOPE = 0.1
+
+    @staticmethod
+    def forward(ctx, holder, x, *wb):
+        specs = [s for s in holder["specs"] if s.kind in ("conv_first", "conv")]
+        x = _c(x)
+        acts = [K.conv_first_fwd(x, wb[0].view(-1, 3, 3, 3), None, wb[1], slope=SNDCGANBackboneFn.SLOPE, round_out=True)]
+        for li, s in enumerate(specs[1:], start=1):
+            acts.append(K.conv2d_nhwc_fwd(acts[-1], wb[2 * li], wb[2 * li + 1], s.ks, s.stride,
+                                          slope=SNDCGANBackboneFn.SLOPE, round_out=True))
+        ctx.specs = specs
+        ctx.dgrad = [holder["side"]["dgrad"][s.name] for s in specs]
+        ctx.save_for_backward(x, *acts, *[wb[2 * i] for i in range(len(specs))])
+        feat = acts[-1]
+        return feat.view(feat.shape[0], -1)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        specs = ctx.specs
+        L = len(specs)
+        saved = ctx.saved_tensors
+        x, acts = saved[0], saved[1:1 + L]
+        need_x = ctx.needs_input_grad[1]
+        need_w = [ctx.needs_input_grad[2 + 2 * i] for i in range(L)]
+        need_b = [ctx.needs_input_grad[3 + 2 * i] for i in range(L)]
+        grads_w, grads_b = [None] * L, [None] * L
+        # g = gradient w.r.t. the pre-activation of the last layer
+        g = K.lrelu_bwd(_c(dfeat).view_as(acts[-1]), acts[-1], SNDCGANBackboneFn.SLOPE, round_out=True)
+        for li in range(L - 1, 0, -1):
+            s = specs[li]
+            a_in = acts[li - 1]
+            if need_w[li]:
+                grads_w[li] = K.conv2d_nhwc_wgrad(a_in, g, s.ks, s.stride)
+            if need_b[li]:
+                grads_b[li] = K.colsum(g.view(-1, g.shape[-1]))
+            if li > 1 or need_x or need_w[0] or need_b[0]:
+                g = K.conv2d_nhwc_dgrad(g, ctx.dgrad[li], tuple(a_in.shape), s.ks, s.stride, act_in=a_in,
+                                        slope=SNDCGANBackboneFn.SLOPE, round_out=True)
+            else:
+                g = None
+        dx = None
+        if g is not None:
+            if need_w[0] or need_b[0]:
+                dw0, db0 = K.conv_first_wgrad(x, g)
+                grads_w[0] = dw0 if need_w[0] else None
+                grads_b[0] = db0 if need_b[0] else None
+            if need_x:
+                B, H, W, _ = g.shape
+                dpad = K.conv2d_nhwc_dgrad(g, ctx.dgrad[0], (B, H, W, 32), 3, 1)
+                dx = K.conv_first_dgrad_finish(dpad)
+        out = [None, dx]
+        for i in range(L):
+            out += [grads_w[i], grads_b[i]]
+        return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# heads: linear (TinyDiscriminator), projection, projection2  (models/gan/base.py:14-35,92-101,123-133)
+# ------------------------------------------------------------------------------------------------
+class HeadsFn(Function):
+    """features [B,F] -> (d [B,1], projection [B,P], projection2 [B,P]).
+
+    One GEMM computes the three hidden layers (A read once): H = lrelu(feat @ Wcat^T + bcat), Wcat [3*hid, F].
+    sg_linear: the `linear` head does not propagate into the features (features.detach(), base.py:123-126)."""
+
+    SLOPE = 0.1
+
+    @staticmethod
+    def forward(ctx, holder, sg_linear, feat, wcat, bcat, w_l2, b_l2, w_p1, b_p1, w_p2, b_p2):
+        feat = _c(feat)
+        hid = wcat.shape[0] // 3
+        H = K.gemm_nt(feat, wcat, bcat, slope=HeadsFn.SLOPE, round_out=True)
+        b_l2p = torch.zeros(w_l2.shape[0], device=feat.device)
+        b_l2p[:b_l2.numel()] = b_l2
+        d32 = K.gemm_nt(H[:, :hid], w_l2, b_l2p)
+        p1 = K.gemm_nt(H[:, hid:2 * hid], w_p1, b_p1)
+        p2 = K.gemm_nt(H[:, 2 * hid:], w_p2, b_p2)
+        side = holder["side"]["dgrad"]
+        ctx.t_cat, ctx.t_l2, ctx.t_p1, ctx.t_p2 = side["wcat"], side["linear.l2"], side["projection.2"], side["projection2.2"]
+        ctx.sg_linear, ctx.hid, ctx.n_out = sg_linear, hid, b_l2.numel()
+        ctx.save_for_backward(feat, H)
+        return d32[:, :ctx.n_out].contiguous(), p1, p2
+
+    @staticmethod
+    def backward(ctx, dd, dp1, dp2):
+        feat, H = ctx.saved_tensors
+        hid, B = ctx.hid, feat.shape[0]
+        dev = feat.device
+        ng = ctx.needs_input_grad
+        dH = torch.empty_like(H)
+        parts = ((dd, ctx.t_l2, 0, 32), (dp1, ctx.t_p1, 1, None), (dp2, ctx.t_p2, 2, None))
+        used = [False, False, False]
+        padded = [None, None, None]
+        for g, wt, idx, pad in parts:
+            sl = slice(idx * hid, (idx + 1) * hid)
+            if g is None:
+                dH[:, sl].zero_()
+                continue
+            used[idx] = True
+            g = _c(g)
+            if pad is not None and g.shape[1] != pad:
+                gp = torch.zeros(B, 128, device=dev)          # 128 columns: also reused by the wgrad below
+                gp[:, :g.shape[1]] = g
+                padded[idx] = gp
+                g = gp[:, :pad]
+            else:
+                padded[idx] = g
+            K.gemm_nt(g, wt, None, slope=HeadsFn.SLOPE, round_out=True, out=dH[:, sl], dact=H[:, sl])
+        grads = [None] * 11
+        # second-layer weight / bias gradients
+        for (g, wt, idx, pad), wpos, bpos in zip(parts, (5, 7, 9), (6, 8, 10)):
+            if g is None:
+                continue
+            sl = slice(idx * hid, (idx + 1) * hid)
+            gfull = padded[idx]
+            if ng[wpos]:
+                dw = K.gemm_tn_wgrad(gfull if gfull.shape[1] % 128 == 0 else gfull, H[:, sl])
+                rows = 32 if pad is not None else dw.shape[0]
+                grads[wpos] = dw[:rows].contiguous() if rows != dw.shape[0] else dw
+            if ng[bpos]:
+                grads[bpos] = K.colsum(_c(g))
+        if ng[3]:
+            grads[3] = K.gemm_tn_wgrad(dH, feat)
+        if ng[4]:
+            grads[4] = K.colsum(dH)
+        if ng[2]:
+            lo = hid if ctx.sg_linear else 0
+            # only heads that actually received a gradient contribute (dH of the others is zero)
+            grads[2] = K.gemm_nt(dH[:, lo:], ctx.t_cat[:, lo:], None, slope=1.0, round_out=False)
+        return tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+class RowNormalizeFn(Function):
+    """F.normalize(x, dim=1, eps=1e-12) (training/gan/contrad.py:43,48)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y, inv = K.rownorm_fwd(x if x.stride(1) == 1 else x.contiguous())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        return K.rownorm_bwd(_c(dy), y, inv)
+
+
+class ContrastiveFn(Function):
+    """mode 0: nt_xent on z = [out1; out2] (training/criterion.py:24-45);
+    mode 1: supcon_fake on z = [out1; out2; others] (training/gan/contrad.py:8-32)."""
+
+    @staticmethod
+    def forward(ctx, z, n, mode, temperature):
+        z = _c(z)
+        loss, lse = K.contrastive_fwd(z, n, mode, temperature)
+        ctx.save_for_backward(z, lse)
+        ctx.cfg = (n, mode, temperature)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, lse = ctx.saved_tensors
+        n, mode, temperature = ctx.cfg
+        return K.contrastive_bwd(z, n, mode, temperature, lse, _c(gout).float()), None, None, None
+
+
+class GanDLossFn(Function):
+    """d_all [3N,1] -> (L_dis, mean d_real, mean d_gen) with d_real = d_all[:N], d_gen = d_all[2N:]
+    (training/gan/contrad.py:52-70).  The two means are logging values (non-differentiable here)."""
+
+    @staticmethod
+    def forward(ctx, d_all, n, kind):
+        d_all = _c(d_all)
+        flat = d_all.view(-1)
+        out, g_r, g_g = K.gan_d_loss(flat[:n], flat[2 * n:3 * n], kind)
+        ctx.save_for_backward(g_r, g_g)
+        ctx.n, ctx.total = n, d_all.shape[0]
+        means = out[1:].clone()
+        ctx.mark_non_differentiable(means)
+        return out[0].clone(), means
+
+    @staticmethod
+    def backward(ctx, gl, _gm):
+        g_r, g_g = ctx.saved_tensors
+        n = ctx.n
+        gd = torch.zeros(ctx.total, 1, device=g_r.device)
+        gd[:n, 0] = g_r * gl
+        gd[2 * n:3 * n, 0] = g_g * gl
+        return gd, None, None
+
+
+class GanGLossFn(Function):
+    """training/gan/contrad.py:75-80."""
+
+    @staticmethod
+    def forward(ctx, d_gen, kind):
+        d_gen = _c(d_gen)
+        out, g = K.gan_g_loss(d_gen.view(-1), kind)
+        ctx.save_for_backward(g)
+        ctx.shape = d_gen.shape
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, gl):
+        (g,) = ctx.saved_tensors
+        return (g * gl).view(ctx.shape), None

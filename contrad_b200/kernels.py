@@ -38,18 +38,21 @@ def augment_simclr_bwd(x, dy, params, order):
 
 
 # ------------------------------------------------------------------ tensor-core GEMM / conv
-def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None):
-    """out[M,N] = lrelu_slope(a[M,K] @ bw[N,K]^T + bias).  `a` / `out` may be row-strided 2-D views."""
+def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None):
+    """out[M,N] = lrelu_slope(a[M,K] @ bw[N,K]^T + bias), or (...) * lrelu'(dact) when dact is given.
+    `a`, `bw`, `out`, `dact` may be row-strided 2-D views (dact must share out's row stride)."""
     assert a.dim() == 2 and bw.dim() == 2 and a.shape[1] == bw.shape[1]
-    assert a.stride(1) == 1 and bw.is_contiguous()
+    assert a.stride(1) == 1 and bw.stride(1) == 1
     M, K = a.shape
     N = bw.shape[0]
     if out is None:
         out = torch.empty(M, N, device=a.device, dtype=torch.float32)
     assert out.shape == (M, N) and out.stride(1) == 1
-    check(lib().cb200_gemm_nt_tf32(ptr(a), i64(a.stride(0)), ptr(bw), ptr(bias), ptr(out), i64(out.stride(0)),
-                                   i32(M), i32(N), i32(K), f32(slope), i32(1 if round_out else 0), stream_ptr()),
-          "cb200_gemm_nt_tf32")
+    if dact is not None:
+        assert dact.shape == (M, N) and dact.stride(1) == 1 and dact.stride(0) == out.stride(0)
+    check(lib().cb200_gemm_nt_tf32(ptr(a), i64(a.stride(0)), ptr(bw), i64(bw.stride(0)), ptr(bias), ptr(dact), ptr(out),
+                                   i64(out.stride(0)), i32(M), i32(N), i32(K), f32(slope), i32(1 if round_out else 0),
+                                   stream_ptr()), "cb200_gemm_nt_tf32")
     return out
 
 
@@ -77,6 +80,179 @@ def conv2d_nhwc_dgrad(dy, wmat_t, in_shape, ks, stride, act_in=None, bias_out=No
                                         i32(W), i32(Cin), i32(Cout), i32(ks), i32(stride), f32(slope),
                                         i32(1 if round_out else 0), stream_ptr()), "cb200_conv2d_nhwc_dgrad")
     return dx
+
+
+def conv2d_nhwc_wgrad(x, dy, ks, stride):
+    """x [B,H,W,Cin], dy [B,Ho,Wo,Cout] -> dW_hat [Cout, ks*ks*Cin] (forward-pack layout)."""
+    x = _f32c(x, "x")
+    dy = _f32c(dy, "dy")
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    dw = torch.empty(Cout, ks * ks * Cin, device=x.device, dtype=torch.float32)
+    check(lib().cb200_conv2d_nhwc_wgrad(ptr(x), ptr(dy), ptr(dw), i32(B), i32(H), i32(W), i32(Cin), i32(Cout),
+                                        i32(ks), i32(stride), stream_ptr()), "cb200_conv2d_nhwc_wgrad")
+    return dw
+
+
+def gemm_tn_wgrad(dy, x, out=None):
+    """dW[N,K] = dy[M,N]^T @ x[M,K]; dy / x / out may be row-strided 2-D views."""
+    assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0]
+    assert dy.stride(1) == 1 and x.stride(1) == 1
+    M, N = dy.shape
+    Kd = x.shape[1]
+    if out is None:
+        out = torch.empty(N, Kd, device=x.device, dtype=torch.float32)
+    assert out.shape == (N, Kd) and out.stride(1) == 1
+    check(lib().cb200_gemm_tn_wgrad(ptr(dy), i64(dy.stride(0)), ptr(x), i64(x.stride(0)), ptr(out), i64(out.stride(0)),
+                                    i32(M), i32(N), i32(Kd), stream_ptr()), "cb200_gemm_tn_wgrad")
+    return out
+
+
+# ------------------------------------------------------------------ spectral norm / packing
+def sn_power_iter(w, u, v, sigma, training=True, eps=1e-12):
+    """In place: u, v <- one power iteration (training) ; sigma[2] <- {sigma, 1/sigma}."""
+    Cout = w.shape[0]
+    Fdim = w.numel() // Cout
+    t = torch.empty(Fdim, device=w.device, dtype=torch.float32)
+    s = torch.empty(Cout, device=w.device, dtype=torch.float32)
+    check(lib().cb200_sn_power_iter(ptr(w), ptr(u), ptr(v), ptr(sigma), ptr(t), ptr(s), i32(Cout), i32(Fdim),
+                                    f32(eps), i32(1 if training else 0), stream_ptr()), "cb200_sn_power_iter")
+
+
+def sn_pack_weights(w4, sigma, fwd=None, ld_fwd=0, dgrad=None, dgrad_mode=0, ldt=0, col0=0, round_out=True):
+    """w4: weight viewed as [Cout, Cin, KH, KW] (contiguous)."""
+    Cout, Cin, KH, KW = w4.shape
+    check(lib().cb200_sn_pack_weights(ptr(w4), ptr(sigma), ptr(fwd), i64(ld_fwd), ptr(dgrad), i32(dgrad_mode),
+                                      i64(ldt), i32(col0), i32(Cout), i32(Cin), i32(KH), i32(KW),
+                                      i32(1 if round_out else 0), stream_ptr()), "cb200_sn_pack_weights")
+
+
+def sn_weight_bwd(dw_hat_packed, ld_fwd, w4, u, v, sigma, dw_out, accumulate=False):
+    Cout, Cin, KH, KW = w4.shape
+    acc = torch.empty(1, device=w4.device, dtype=torch.float32)
+    check(lib().cb200_sn_weight_bwd(ptr(dw_hat_packed), i64(ld_fwd), ptr(w4), ptr(u), ptr(v), ptr(sigma), ptr(acc),
+                                    ptr(dw_out), i32(1 if accumulate else 0), i32(Cout), i32(Cin), i32(KH), i32(KW),
+                                    stream_ptr()), "cb200_sn_weight_bwd")
+    return dw_out
+
+
+# ------------------------------------------------------------------ first conv layer
+def conv_first_fwd(x, w, sigma, bias, slope=0.1, round_out=True):
+    x = _f32c(x, "x")
+    B, C, H, W = x.shape
+    assert C == 3 and w.shape == (64, 3, 3, 3) and w.is_contiguous()
+    y = torch.empty(B, H, W, 64, device=x.device, dtype=torch.float32)
+    check(lib().cb200_conv_first_fwd(ptr(x), ptr(w), ptr(sigma), ptr(bias), ptr(y), i32(B), i32(H), i32(W),
+                                     f32(slope), i32(1 if round_out else 0), stream_ptr()), "cb200_conv_first_fwd")
+    return y
+
+
+def conv_first_wgrad(x, dy):
+    x = _f32c(x, "x")
+    dy = _f32c(dy, "dy")
+    B, C, H, W = x.shape
+    dw = torch.zeros(64, 27, device=x.device, dtype=torch.float32)
+    db = torch.zeros(64, device=x.device, dtype=torch.float32)
+    check(lib().cb200_conv_first_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(db), i32(B), i32(H), i32(W), stream_ptr()),
+          "cb200_conv_first_wgrad")
+    return dw, db
+
+
+def conv_first_dgrad_finish(dpad):
+    dpad = _f32c(dpad, "dpad")
+    B, H, W, cpad = dpad.shape
+    dx = torch.empty(B, 3, H, W, device=dpad.device, dtype=torch.float32)
+    check(lib().cb200_conv_first_dgrad_finish(ptr(dpad), ptr(dx), i32(B), i32(H), i32(W), i32(cpad), stream_ptr()),
+          "cb200_conv_first_dgrad_finish")
+    return dx
+
+
+# ------------------------------------------------------------------ losses
+LOSS_KINDS = {"nonsat": 0, "hinge": 1, "wgan": 2, "lsgan": 3}
+
+
+def rownorm_fwd(x, eps=1e-12):
+    """x: [rows, d] (row-strided view allowed) -> (y contiguous, inv_norm)."""
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, d = x.shape
+    y = torch.empty(rows, d, device=x.device, dtype=torch.float32)
+    inv = torch.empty(rows, device=x.device, dtype=torch.float32)
+    check(lib().cb200_rownorm_fwd(ptr(x), i64(x.stride(0)), ptr(y), ptr(inv), i32(rows), i32(d), f32(eps),
+                                  stream_ptr()), "cb200_rownorm_fwd")
+    return y, inv
+
+
+def rownorm_bwd(dy, y, inv, out=None, round_out=False):
+    dy = _f32c(dy, "dy")
+    rows, d = y.shape
+    if out is None:
+        out = torch.empty(rows, d, device=y.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    check(lib().cb200_rownorm_bwd(ptr(dy), ptr(y), ptr(inv), ptr(out), i64(out.stride(0)), i32(rows), i32(d),
+                                  i32(1 if round_out else 0), stream_ptr()), "cb200_rownorm_bwd")
+    return out
+
+
+def contrastive_fwd(z, n, mode, temperature):
+    """z: [2n or 3n, 128] normalised rows.  Returns (loss[1], lse)."""
+    z = _f32c(z, "z")
+    active = n if mode else 2 * n
+    assert z.shape == ((3 if mode else 2) * n, 128), z.shape
+    lse = torch.empty(active, device=z.device, dtype=torch.float32)
+    row_loss = torch.empty(active, device=z.device, dtype=torch.float32)
+    loss = torch.empty(1, device=z.device, dtype=torch.float32)
+    check(lib().cb200_contrastive_fwd(ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
+                                      ptr(row_loss), ptr(loss), stream_ptr()), "cb200_contrastive_fwd")
+    return loss, lse
+
+
+def contrastive_bwd(z, n, mode, temperature, lse, gscale):
+    z = _f32c(z, "z")
+    dz = torch.empty_like(z)
+    gscale = _f32c(gscale.reshape(1), "gscale")
+    check(lib().cb200_contrastive_bwd(ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
+                                      ptr(gscale), ptr(dz), stream_ptr()), "cb200_contrastive_bwd")
+    return dz
+
+
+def gan_d_loss(d_real, d_gen, kind):
+    """d_real, d_gen: 1-D views (any element stride, equal).  Returns (out3, g_real, g_gen)."""
+    n = d_real.numel()
+    assert d_real.dim() == 1 and d_gen.dim() == 1 and d_real.stride(0) == d_gen.stride(0)
+    out = torch.empty(3, device=d_real.device, dtype=torch.float32)
+    g_r = torch.empty(n, device=d_real.device, dtype=torch.float32)
+    g_g = torch.empty(n, device=d_real.device, dtype=torch.float32)
+    check(lib().cb200_gan_d_loss(ptr(d_real), ptr(d_gen), i64(d_real.stride(0)), i32(n), i32(LOSS_KINDS[kind]),
+                                 ptr(out), ptr(g_r), ptr(g_g), stream_ptr()), "cb200_gan_d_loss")
+    return out, g_r, g_g
+
+
+def gan_g_loss(d_gen, kind):
+    n = d_gen.numel()
+    assert d_gen.dim() == 1
+    out = torch.empty(1, device=d_gen.device, dtype=torch.float32)
+    g = torch.empty(n, device=d_gen.device, dtype=torch.float32)
+    k = LOSS_KINDS.get(kind, 2)
+    check(lib().cb200_gan_g_loss(ptr(d_gen), i64(d_gen.stride(0)), i32(n), i32(k), ptr(out), ptr(g), stream_ptr()),
+          "cb200_gan_g_loss")
+    return out, g
+
+
+def lrelu_bwd(dy, act, slope, round_out=False):
+    dy = _f32c(dy, "dy")
+    act = _f32c(act, "act")
+    out = torch.empty_like(act)
+    check(lib().cb200_lrelu_bwd(ptr(dy), ptr(act), ptr(out), i64(act.numel()), f32(slope), i32(1 if round_out else 0),
+                                stream_ptr()), "cb200_lrelu_bwd")
+    return out
+
+
+def colsum(x2d):
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    M, N = x2d.shape
+    out = torch.empty(N, device=x2d.device, dtype=torch.float32)
+    check(lib().cb200_colsum(ptr(x2d), i64(x2d.stride(0)), i32(M), i32(N), ptr(out), stream_ptr()), "cb200_colsum")
+    return out
 
 
 # ------------------------------------------------------------------ layout helpers (torch ops; test/reference use)

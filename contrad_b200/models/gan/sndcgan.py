@@ -1,0 +1,93 @@
+"""Mirror of models/gan/sndcgan.py: ``D_SNDCGAN`` (:69-148) on the sm_100a kernels and ``G_SNDCGAN``
+(:13-66).  state_dict keys / shapes are those of the reference, so checkpoints interchange.
+
+Discriminator data flow: NCHW image -> SIMT first layer (x*2-1 folded in) -> NHWC TF32 activations ->
+six tcgen05 implicit-GEMM convolutions with fused bias + LeakyReLU(0.1) -> features [B, 4*4*512] in
+(h,w,c) order -> one tensor-core GEMM for the three head MLPs.  Spectral norm: batched power iteration
++ packing kernels; sigma stays on the device."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ...functional import SNDCGANBackboneFn, SNLayerSpec
+from .base import BaseDiscriminator, SNConv2d
+
+
+class G_SNDCGAN(nn.Module):
+    """models/gan/sndcgan.py:13-66.  (Round 1: the generator still runs on ATen/cuDNN library kernels; it is
+    the next row to move onto the tcgen05 transposed-conv kernels - see DESIGN.md 'library stand-ins'.)"""
+
+    def __init__(self, image_size, ngf=64, nz=128):
+        super().__init__()
+        self.image_size, self.ngf, self.nz = image_size, ngf, nz
+        s_h, s_w, nc = image_size
+        self.s_hb, self.s_wb = s_h // 8, s_w // 8
+        self.linear = nn.Linear(nz, ngf * 8 * self.s_hb * self.s_wb)
+        self.norm_init = nn.BatchNorm2d(ngf * 8 * self.s_hb * self.s_wb)
+        self.main = nn.Sequential(
+            nn.ConvTranspose2d(ngf * 8, ngf * 4, 4, 2, 1), nn.BatchNorm2d(ngf * 4), nn.ReLU(inplace=True),
+            nn.ConvTranspose2d(ngf * 4, ngf * 2, 4, 2, 1), nn.BatchNorm2d(ngf * 2), nn.ReLU(inplace=True),
+            nn.ConvTranspose2d(ngf * 2, ngf, 4, 2, 1), nn.BatchNorm2d(ngf), nn.ReLU(inplace=True),
+            nn.ConvTranspose2d(ngf, nc, 3, 1, 1), nn.Tanh())
+        self.reset_parameters()
+
+    def forward(self, z):
+        h = self.linear(z)
+        h = F.relu(self.norm_init(h.view(h.size(0), h.size(1), 1, 1)), inplace=True)
+        h = h.view(-1, self.ngf * 8, self.s_hb, self.s_wb)
+        return 0.5 * self.main(h) + 0.5
+
+    def sample_latent(self, n_samples):
+        device = next(self.parameters()).device
+        return torch.empty(n_samples, self.nz).uniform_(-1, 1).to(device)
+
+    def reset_parameters(self):
+        for m in self.modules():
+            if isinstance(m, (nn.ConvTranspose2d, nn.Linear)):
+                nn.init.normal_(m.weight.data, 0.0, 0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias.data, 0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight.data, 1.0)
+                nn.init.constant_(m.bias.data, 0.0)
+
+
+class D_SNDCGAN(BaseDiscriminator):
+    def __init__(self, image_size, ndf=64, n_classes=1, normalize=False, disable_sn=False, mlp_linear=False,
+                 d_hidden=128):
+        if normalize or disable_sn:
+            raise NotImplementedError("normalize / disable_sn variants are not used by any reference config")
+        if ndf != 64:
+            raise NotImplementedError("the first-layer kernel is specialised for ndf=64 (the registry value)")
+        s_h, s_w, nc = image_size
+        if nc != 3:
+            raise NotImplementedError("RGB inputs only")
+        self.image_size, self.ndf = image_size, ndf
+        self.s_hb, self.s_wb = s_h // 8, s_w // 8
+        self.n_features = ndf * 8 * self.s_hb * self.s_wb
+        super().__init__(self.n_features, n_classes=n_classes, d_hidden=d_hidden, mlp_linear=mlp_linear)
+        self._feat_chw = (ndf * 8, self.s_hb, self.s_wb)
+        act = lambda: nn.LeakyReLU(0.1, inplace=True)     # placeholders keep the reference's `main.<2i>` indices
+        self.main = nn.Sequential(
+            SNConv2d(nc, ndf, 3, 1, 1), act(),
+            SNConv2d(ndf, ndf * 2, 4, 2, 1), act(), SNConv2d(ndf * 2, ndf * 2, 3, 1, 1), act(),
+            SNConv2d(ndf * 2, ndf * 4, 4, 2, 1), act(), SNConv2d(ndf * 4, ndf * 4, 3, 1, 1), act(),
+            SNConv2d(ndf * 4, ndf * 8, 4, 2, 1), act(), SNConv2d(ndf * 8, ndf * 8, 3, 1, 1), act())
+
+    def _sn_specs(self):
+        specs = []
+        for i in range(0, len(self.main), 2):
+            m = self.main[i]
+            specs.append(SNLayerSpec("main.%d" % i, m, "conv_first" if i == 0 else "conv", m.ks, m.stride))
+        return specs + self._head_specs()
+
+    def _backbone(self, holder, inputs, packs):
+        convs = [self.main[i] for i in range(0, len(self.main), 2)]
+        wb = []
+        for pack, m in zip(packs, convs):
+            wb += [pack, m.bias]
+        return SNDCGANBackboneFn.apply(holder, inputs, *wb)
+
+    def _to_reference_order(self, features):
+        c, h, w = self._feat_chw
+        return features.view(-1, h, w, c).permute(0, 3, 1, 2).reshape(-1, self.n_features)

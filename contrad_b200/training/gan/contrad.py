@@ -1,0 +1,64 @@
+"""Mirror of training/gan/contrad.py: ``supcon_fake``, ``loss_D_fn``, ``loss_G_fn`` with the reference
+signatures; the arithmetic runs on the sm_100a kernels (one fused contrastive kernel per loss, one
+fused GAN-loss kernel) and, when ``P.distributed``, on ONE packed all-gather of the embeddings."""
+import torch
+
+from ...functional import ContrastiveFn, GanDLossFn, GanGLossFn, RowNormalizeFn
+from ...third_party.gather_layer import GatherLayer, gather_rows
+
+_D_LOSSES = ("nonsat", "wgan", "hinge", "lsgan")
+
+
+def supcon_fake(out1, out2, others, temperature, distributed=False):
+    """training/gan/contrad.py:8-32."""
+    if distributed:
+        out1 = torch.cat(GatherLayer.apply(out1), dim=0)
+        out2 = torch.cat(GatherLayer.apply(out2), dim=0)
+        others = torch.cat(GatherLayer.apply(others), dim=0)
+    n = out1.size(0)
+    return ContrastiveFn.apply(torch.cat([out1, out2, others], dim=0), n, 1, float(temperature))
+
+
+def _rank_major(blocks, n):
+    """[world, 3n, d] gathered rows -> [out1_all; out2_all; others_all], each rank-major (the order
+    torch.cat(GatherLayer.apply(x)) produces in the reference, criterion.py:31-32)."""
+    world, _, d = blocks.shape
+    return blocks.view(world, 3, n, d).transpose(0, 1).reshape(3 * world * n, d)
+
+
+def loss_D_fn(P, D, options, images, gen_images):
+    """training/gan/contrad.py:35-70."""
+    assert images.size(0) == gen_images.size(0)
+    if options["loss"] not in _D_LOSSES:
+        raise NotImplementedError()
+    gen_images = gen_images.detach()
+    n = images.size(0)
+
+    cat_images = torch.cat([images, images, gen_images], dim=0)
+    d_all, aux = D(P.augment_fn(cat_images), sg_linear=True, projection=True, projection2=True)
+    views = RowNormalizeFn.apply(aux["projection"])
+    reals = RowNormalizeFn.apply(aux["projection2"])
+    if P.distributed:
+        both = gather_rows(torch.cat([views, reals], dim=1))          # one collective for all 5 blocks
+        d = views.shape[1]
+        views_all = _rank_major(both[:, :, :d].contiguous(), n)
+        reals_all = _rank_major(both[:, :, d:].contiguous(), n)
+        n_all = n * both.shape[0]
+        simclr_loss = ContrastiveFn.apply(views_all[:2 * n_all], n_all, 0, float(P.temp))
+        sup_loss = ContrastiveFn.apply(reals_all, n_all, 1, float(P.temp))
+    else:
+        simclr_loss = ContrastiveFn.apply(views[:2 * n], n, 0, float(P.temp))
+        sup_loss = ContrastiveFn.apply(reals, n, 1, float(P.temp))
+
+    d_loss, means = GanDLossFn.apply(d_all, n, options["loss"])
+    return simclr_loss + P.lbd_a * sup_loss, {
+        "penalty": d_loss,
+        "d_real": means[0],
+        "d_gen": means[1],
+    }
+
+
+def loss_G_fn(P, D, options, images, gen_images):
+    """training/gan/contrad.py:73-82."""
+    d_gen = D(P.augment_fn(gen_images))
+    return GanGLossFn.apply(d_gen, options["loss"])

@@ -50,21 +50,86 @@ int cb200_augment_simclr_bwd(const float* x, const float* dy, float* dx, const f
  * Replace F.linear / nn.Conv2d / nn.ConvTranspose2d behind models/gan/sndcgan.py:24-38,91-109 and
  * models/gan/base.py:14-35,92-101 (cuBLAS / cuDNN in the reference).  Activations are NHWC.
  *
- * gemm_nt:   out[M,N] = lrelu_slope(A[M,K] * Bw[N,K]^T + bias)      (slope 1 = no activation)
+ * gemm_nt:   out[M,N] = lrelu_slope(A[M,K] * Bw[N,K]^T + bias)      (slope 1 = no activation);
+ *            with dact != NULL: out = (A * Bw^T + bias) * lrelu'(dact[M,N])  (row strides lda/ldb/ldo)
  * conv fwd:  y[B,Ho,Wo,Cout] = lrelu_slope(conv(x[B,H,W,Cin]) + bias); wmat = [Cout, ks*ks*Cin],
  *            column (kh*ks+kw)*Cin+ci = W[co,ci,kh,kw]; (ks,stride) in {(3,1),(4,2)}, pad 1
  * conv dgrad: dx[B,H,W,Cin] = conv^T(dy[B,Ho,Wo,Cout]) (* lrelu'(act_in) when act_in != NULL,
  *            + bias_out then lrelu_slope otherwise); wmat_t layouts are produced by
  *            cb200_sn_pack_weights.  Also serves ConvTranspose2d forward in G_SNDCGAN.
  * round_out: round outputs to TF32 (nearest) because they feed another tensor-core GEMM. */
-int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, const float* bias, float* out,
-                       long long ldo, int M, int N, int K, float slope, int round_out, void* stream);
+int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, long long ldb, const float* bias,
+                       const float* dact, float* out, long long ldo, int M, int N, int K, float slope,
+                       int round_out, void* stream);
 int cb200_conv2d_nhwc_fwd(const float* x, const float* wmat, const float* bias, float* y, int B, int H,
                           int W, int Cin, int Cout, int ks, int stride, float slope, int round_out,
                           void* stream);
 int cb200_conv2d_nhwc_dgrad(const float* dy, const float* wmat_t, const float* act_in,
                             const float* bias_out, float* dx, int B, int H, int W, int Cin, int Cout,
                             int ks, int stride, float slope, int round_out, void* stream);
+
+/* wgrad: dw_hat[Cout, ks*ks*Cin] (forward-pack layout) = sum over pixels dy (x) shifted x; both operands are
+ * MN-major tcgen05 tiles, split-K over pixels with fp32 atomics (buffer is zeroed inside).
+ * gemm_tn_wgrad: dw[N,K] = dy[M,N]^T * x[M,K] (linear layers).  Replace autograd's cuDNN/cuBLAS wgrad. */
+int cb200_conv2d_nhwc_wgrad(const float* x, const float* dy, float* dw_hat, int B, int H, int W, int Cin,
+                            int Cout, int ks, int stride, void* stream);
+int cb200_gemm_tn_wgrad(const float* dy, long long ldy, const float* x, long long ldx, float* dw,
+                        long long ldw, int M, int N, int K, void* stream);
+
+/* ---- spectral norm + weight packing ---------------------------------------------------------
+ * Replaces torch.nn.utils.spectral_norm's pre-forward hook (call sites models/gan/sndcgan.py:111-118;
+ * arithmetic torch/nn/utils/spectral_norm.py:92-114): one power iteration in train mode (u, v updated
+ * in place), sigma = u^T W v kept on the device as sigma[2] = {sigma, 1/sigma}.
+ * sn_pack_weights writes W/sigma in the GEMM layouts the tensor-core kernels consume
+ *   fwd   [Cout][KH][KW][Cin] (row stride ld_fwd);
+ *   dgrad mode 1: [Cin][KH][KW][Cout]; mode 2: [ph][pw][Cin][jh][jw][Cout] (4x4 stride 2);
+ *         mode 3: [KH][KW][Cin] rows x ldt columns at column offset col0 (transposed linear weight).
+ * sn_weight_bwd maps dW_hat (forward-pack layout) back to dW (OIHW) including the sigma term:
+ *   dW = (dW_hat - <dW_hat, W_hat> u v^T) / sigma        (autograd of W / (u^T W v), u, v constant). */
+int cb200_sn_power_iter(const float* w, float* u, float* v, float* sigma, float* t_scratch,
+                        float* s_scratch, int Cout, int F, float eps, int training, void* stream);
+int cb200_sn_pack_weights(const float* w, const float* sigma, float* fwd, long long ld_fwd, float* dgrad,
+                          int dgrad_mode, long long ldt, int col0, int Cout, int Cin, int KH, int KW,
+                          int round_out, void* stream);
+int cb200_sn_weight_bwd(const float* dw_hat_packed, long long ld_fwd, const float* w, const float* u,
+                        const float* v, const float* sigma, float* acc_scratch, float* dw, int accumulate,
+                        int Cout, int Cin, int KH, int KW, void* stream);
+
+/* ---- first discriminator layer: Conv2d(3->64,3,1,1) + bias + LeakyReLU with x*2-1 folded in ---
+ * (models/gan/sndcgan.py:91-93,122-124).  NCHW image in, NHWC activation out (SIMT, HBM-bound).
+ * wgrad accumulates into dw_hat[64,27] (OIHW order) and db[64]; dgrad_finish extracts the 3 real
+ * channels of the 32-channel padded tensor-core data gradient, applies the factor 2, NHWC->NCHW. */
+int cb200_conv_first_fwd(const float* x, const float* w, const float* sigma, const float* bias, float* y,
+                         int B, int H, int W, float slope, int round_out, void* stream);
+int cb200_conv_first_wgrad(const float* x, const float* dy, float* dw_hat, float* db, int B, int H, int W,
+                           void* stream);
+int cb200_conv_first_dgrad_finish(const float* dpad, float* dx, int B, int H, int W, int cpad, void* stream);
+
+/* ---- contrastive + GAN losses (fp32 SIMT, flash-style: no R x R matrix is materialised) --------
+ * rownorm      = F.normalize(x, dim=1, eps)                       (training/gan/contrad.py:43,48)
+ * contrastive  mode 0 = nt_xent(out1,out2) on z=[out1;out2] (training/criterion.py:24-45)
+ *              mode 1 = supcon_fake(out1,out2,others) on z=[out1;out2;others] (training/gan/contrad.py:8-32)
+ *              z rows are L2-normalised, width 128; diagonal sentinel -5e4 after the 1/temperature scale.
+ *              fwd writes row log-sum-exps (needed by bwd) and loss[0]; bwd writes dz = gscale[0]*dL/dz.
+ * gan_d_loss   kind 0 nonsat, 1 hinge, 2 wgan, 3 lsgan (contrad.py:52-64): out3 = {L_dis, mean d_real,
+ *              mean d_gen}, g_real/g_gen = dL_dis/dd.   gan_g_loss (contrad.py:75-80): out1 = {L_gen}.
+ * colsum       out[n] = sum_m x[m,n]  (bias gradients). */
+int cb200_rownorm_fwd(const float* x, long long ldx, float* y, float* inv_norm, int rows, int d, float eps,
+                      void* stream);
+int cb200_rownorm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, long long lddx,
+                      int rows, int d, int round_out, void* stream);
+int cb200_contrastive_fwd(const float* z, int N, int d, int mode, float temperature, float* lse,
+                          float* row_loss, float* loss, void* stream);
+int cb200_contrastive_bwd(const float* z, int N, int d, int mode, float temperature, const float* lse,
+                          const float* gscale, float* dz, void* stream);
+int cb200_gan_d_loss(const float* d_real, const float* d_gen, long long stride, int N, int kind, float* out3,
+                     float* g_real, float* g_gen, void* stream);
+int cb200_gan_g_loss(const float* d_gen, long long stride, int N, int kind, float* out1, float* g_gen,
+                     void* stream);
+int cb200_colsum(const float* x, long long ld, int M, int N, float* out, void* stream);
+/* out = dy * lrelu'(act) from the saved output activation (nn.LeakyReLU backward, sndcgan.py:92-108). */
+int cb200_lrelu_bwd(const float* dy, const float* act, float* out, long long n, float slope, int round_out,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,192 @@
+"""End-to-end parity of the B200 path (contrad_b200 modules + kernels) against the CPU oracle and the
+reference-generated golden scalars.  Run with -m gpu."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import contrad_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    compat = os.path.join(repo, "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    gin.clear_config()
+    gin.parse_config("""
+ColorJitterLayer.brightness = 0.4
+ColorJitterLayer.contrast = 0.4
+ColorJitterLayer.saturation = 0.4
+ColorJitterLayer.hue = 0.1
+RandomResizeCropLayer.scale = (0.2, 1.0)
+""")
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import contrad
+    from contrad_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return SimpleNamespace(get_augment=get_augment, get_architecture=get_architecture, contrad=contrad, engine=engine)
+
+
+def _unpack(packed):
+    return {k: packed[i] for i, k in enumerate(O.PARAM_FIELDS)}
+
+
+class _FixedAugment(torch.nn.Module):
+    """Augment module fed with pre-drawn parameter blocks (so GPU and oracle see identical draws)."""
+
+    def __init__(self, blocks):
+        super().__init__()
+        self.blocks = list(blocks)
+
+    def forward(self, x):
+        from contrad_b200.functional import AugmentSimCLRFn
+        packed, order = self.blocks.pop(0)
+        return AugmentSimCLRFn.apply(x, packed.to(x.device), order)
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+@pytest.mark.parametrize("loss_kind,n", [("nonsat", 4), ("hinge", 6)])
+def test_d_and_g_losses_and_grads_vs_oracle(env, loss_kind, n):
+    """Full-width SNDCGAN D (ndf=64) at a small batch: every loss, the D outputs and every parameter
+    gradient against the fp32 CPU oracle on identical weights, latents and augmentation draws."""
+    gen_w = torch.Generator().manual_seed(99)
+    sd_d = O.make_d_state(generator=gen_w)
+    sd_g = O.make_g_state(generator=gen_w)
+    G, D = env.get_architecture("sndcgan", (32, 32, 3))
+    D.load_state_dict(sd_d); G.load_state_dict(sd_g)
+    G.cuda(); D.cuda(); G.train(); D.train()
+    np.random.seed(3); torch.manual_seed(3)
+    images = torch.rand(n, 3, 32, 32)
+    z_d = O.sample_latent(n)
+    aug_d = O.sample_simclr_params(3 * n, 32, 32)
+    z_g = O.sample_latent(n)
+    aug_g = O.sample_simclr_params(n, 32, 32)
+
+    # ---------------- oracle (CPU fp32)
+    sd_d_o = {k: v.clone() for k, v in sd_d.items()}
+    sd_g_o = {k: v.clone() for k, v in sd_g.items()}
+    O.set_requires_grad(sd_g_o, False); O.set_requires_grad(sd_d_o, True)
+    with torch.no_grad():
+        gen_o = O.g_sndcgan_forward(sd_g_o, z_d)
+    l_con_o, l_dis_o, ex = O.loss_d(sd_d_o, images, gen_o, aug_d[0], aug_d[1], loss=loss_kind)
+    (l_con_o + l_dis_o).backward()
+    grads_o = {k: v.grad.clone() for k, v in O.trainable(sd_d_o).items()}
+    uv_o = {k: v.clone() for k, v in sd_d_o.items() if k.endswith(("weight_u", "weight_v"))}
+
+    # ---------------- B200 path
+    P = SimpleNamespace(augment_fn=_FixedAugment([(O.pack_params(aug_d[0]), aug_d[1]), (O.pack_params(aug_g[0]), aug_g[1])]),
+                        temp=0.1, lbd_a=1.0, distributed=False)
+    options = {"loss": loss_kind}
+    env.engine.set_grad(G, False); env.engine.set_grad(D, True)
+    with torch.no_grad():
+        gen = G(z_d.cuda())
+    assert torch.allclose(gen.cpu(), gen_o, atol=2e-4)
+    d_loss, aux = env.contrad.loss_D_fn(P, D, options, images.cuda(), gen)
+    (d_loss + aux["penalty"]).backward()
+    assert _rel(float(d_loss), float(l_con_o)) < 1e-3, (float(d_loss), float(l_con_o))
+    assert _rel(float(aux["penalty"]), float(l_dis_o)) < 1e-3
+    assert abs(float(aux["d_real"]) - float(ex["d_real"])) < 1e-3 * max(1.0, abs(float(ex["d_real"])))
+    sd_now = D.state_dict()
+    for k, ref in uv_o.items():
+        assert torch.allclose(sd_now[k].cpu(), ref, atol=2e-5), k
+    tot_o = torch.sqrt(sum(g.double().pow(2).sum() for g in grads_o.values()))
+    tot = float(env.engine.grad_norm(D))
+    assert _rel(tot, float(tot_o)) < 1e-3, (tot, float(tot_o))
+    named = dict(D.named_parameters())
+    for k, g_o in grads_o.items():
+        g = named[k].grad
+        assert g is not None, k
+        err = (g.cpu() - g_o).norm() / g_o.norm().clamp_min(1e-12)
+        assert err < 5e-3, (k, float(err))
+
+    # ---------------- G step through the frozen D
+    O.set_requires_grad(sd_g_o, True); O.set_requires_grad(sd_d_o, False)
+    gen2_o = O.g_sndcgan_forward(sd_g_o, z_g)
+    l_gen_o = O.loss_g(sd_d_o, gen2_o, aug_g[0], aug_g[1], loss=loss_kind)
+    l_gen_o.backward()
+    env.engine.set_grad(G, True); env.engine.set_grad(D, False)
+    gen2 = G(z_g.cuda())
+    g_loss = env.contrad.loss_G_fn(P, D, options, images.cuda(), gen2)
+    g_loss.backward()
+    assert _rel(float(g_loss), float(l_gen_o)) < 1e-3 or abs(float(g_loss) - float(l_gen_o)) < 1e-6
+    gn_o = O.grad_norm(sd_g_o)
+    assert _rel(float(env.engine.grad_norm(G)), gn_o) < 2e-3, (float(env.engine.grad_norm(G)), gn_o)
+
+
+def test_config1_two_steps_vs_reference_scalars(env, golden_dir):
+    """BASELINE config 1 shape (b64, c10_b512.gin hyper-parameters): two complete train steps (Adam incl.) on
+    the B200 path reproduce the UNMODIFIED reference's scalars (tests/golden/config1_scalars.json) to 1e-3."""
+    with open(os.path.join(golden_dir, "config1_scalars.json")) as f:
+        fx = json.load(f)
+    n = fx["batch"]
+    gen_w = torch.Generator().manual_seed(fx["weights_seed"])
+    sd_d = O.make_d_state(generator=gen_w)
+    sd_g = O.make_g_state(generator=gen_w)
+    G, D = env.get_architecture("sndcgan", (32, 32, 3))
+    D.load_state_dict(sd_d); G.load_state_dict(sd_g)
+    G.cuda(); D.cuda()
+    opt_G = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    opt_D = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    options = {"loss": "nonsat", "warmup": 3000, "lr": 2e-4, "lr_d": 2e-4}
+    np.random.seed(fx["data_seed"]); torch.manual_seed(fx["data_seed"])
+    train_fn = {"D": env.contrad.loss_D_fn, "G": env.contrad.loss_G_fn}
+
+    class _G(torch.nn.Module):       # latents drawn on the CPU generator in the reference's order
+        def __init__(self, g, zs):
+            super().__init__(); self.g, self.zs = g, zs
+        def sample_latent(self, k):
+            return self.zs.pop(0).cuda()
+        def forward(self, z):
+            return self.g(z)
+        def parameters(self, recurse=True):
+            return self.g.parameters(recurse)
+        def train(self, mode=True):
+            self.g.train(mode); return self
+
+    for ref in fx["steps"]:
+        images = torch.rand(n, 3, 32, 32)
+        z_d = O.sample_latent(n)
+        aug_d = O.sample_simclr_params(3 * n, 32, 32)
+        z_g = O.sample_latent(n)
+        aug_g = O.sample_simclr_params(n, 32, 32)
+        P = SimpleNamespace(augment_fn=_FixedAugment([(O.pack_params(aug_d[0]), aug_d[1]),
+                                                      (O.pack_params(aug_g[0]), aug_g[1])]),
+                            temp=0.1, lbd_a=1.0, distributed=False)
+        got = env.engine.train_step(P, options, train_fn, (_G(G, [z_d, z_g]), D), (opt_G, opt_D), images.cuda(),
+                                    ref["step"], record_grad_norms=True)
+        for key, mine in (("l_con", "d_loss"), ("l_dis", "d_penalty"), ("l_gen", "g_loss"),
+                          ("d_grad_norm", "d_grad_norm"), ("g_grad_norm", "g_grad_norm")):
+            assert _rel(float(got[mine]), ref[key]) < 1e-3, (ref["step"], key, float(got[mine]), ref[key])
+
+
+def test_full_batch_step_runs_and_is_finite(env):
+    """BASELINE config 2 shape (N=512, D-step batch 1536): one step; losses finite and at their
+    initialisation values (L_dis ~ 2 ln 2, L_gen ~ ln 2, L_con+ ~ ln(2N-1) scale)."""
+    torch.manual_seed(0); np.random.seed(0)
+    G, D = env.get_architecture("sndcgan", (32, 32, 3))
+    G.cuda(); D.cuda()
+    opt_G = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    opt_D = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    options = {"loss": "nonsat", "warmup": 3000, "lr": 2e-4}
+    P = SimpleNamespace(augment_fn=env.get_augment("simclr").cuda(), temp=0.1, lbd_a=1.0, distributed=False)
+    train_fn = {"D": env.contrad.loss_D_fn, "G": env.contrad.loss_G_fn}
+    images = torch.rand(512, 3, 32, 32, device="cuda")
+    out = env.engine.train_step(P, options, train_fn, (G, D), (opt_G, opt_D), images, 1)
+    vals = {k: float(v) for k, v in out.items()}
+    assert all(np.isfinite(v) for v in vals.values()), vals
+    assert abs(vals["d_penalty"] - 2 * np.log(2)) < 0.05 and abs(vals["g_loss"] - np.log(2)) < 0.05, vals
+    assert 8.0 < vals["d_loss"] < 16.0, vals
