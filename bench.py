@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the ContraD per-step training hot path (BASELINE.json metric: train-step images/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
+
+Workload (BASELINE.json configs[1]/[2]): SNDCGAN + ContraD, `c10_b512.gin` hyper-parameters
+(global batch 512, nonsat loss, Adam(2e-4, (0.5,0.999)), warm-up 3000), `--aug=simclr`, synthetic
+32x32 images U[0,1), random-init weights.  One "step" = one full iteration of train_gan.py:141-179
+(D step on 3N augmented images + G step, both Adam updates).  For N GPUs the global batch is split
+(512 // N per rank, DDP + SyncBN(G) + the packed embedding all-gather) exactly like train_gan.py:247 ->
+"scaling": "strong".
+
+Prints ONE JSON line (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same through
+the public API with the per-step pinned-host -> device image copy and the reference's per-step loss
+read-backs inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.append(os.path.join(REPO, "contrad_b200", "compat"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GLOBAL_BATCH = 512
+GIN_DEFAULTS = """
+ColorJitterLayer.brightness = 0.4
+ColorJitterLayer.contrast = 0.4
+ColorJitterLayer.saturation = 0.4
+ColorJitterLayer.hue = 0.1
+RandomResizeCropLayer.scale = (0.2, 1.0)
+"""
+OPTIONS = {"loss": "nonsat", "warmup": 3000, "lr": 2e-4, "lr_d": 2e-4, "beta": (0.5, 0.999), "batch_size": GLOBAL_BATCH}
+# algorithmic FLOPs per real image per full step (D fwd+dgrad+wgrad on 3N, G fwd/bwd, D fwd+dgrad on N)
+FLOP_PER_IMAGE_STEP = 5.85e9
+WORKLOAD = "SNDCGAN+ContraD CIFAR-10 32x32 b512 --aug=simclr (c10_b512.gin), synthetic images, full D+G step"
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    parts = [x.strip() for x in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        sm.append(float(parts[1])); smax = float(parts[2])
+                    except ValueError:
+                        continue
+                    for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                        if val.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]           # upper half = samples under load
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """CPU restatement of the reference path (oracle/contrad_oracle.py, kind "port": the reference is
+    Python and cannot travel to the GPU box) on all host cores.  Each step = a bounded SAMPLE of the
+    workload: one full D+G step at batch 64 (1/8 of the b512 batch; BASELINE config 1 shape)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import contrad_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = 64
+    gen_w = torch.Generator().manual_seed(0)
+    sd_d, sd_g = O.make_d_state(generator=gen_w), O.make_g_state(generator=gen_w)
+    opt_g = O.Adam(O.trainable(sd_g).values(), 2e-4)
+    opt_d = O.Adam(O.trainable(sd_d).values(), 2e-4)
+    np.random.seed(0); torch.manual_seed(0)
+
+    def one(step):
+        images = torch.rand(n, 3, 32, 32)
+        z_d = O.sample_latent(n); aug_d = O.sample_simclr_params(3 * n, 32, 32)
+        z_g = O.sample_latent(n); aug_g = O.sample_simclr_params(n, 32, 32)
+        return O.train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=step)
+
+    for w in range(args.warmup):
+        one(w + 1)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        one(args.warmup + s + 1)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = "full D+G step at batch 64 (1/8 of the b512 workload) per timed step"
+    line = {"impl": "reference", "metric": "train_step_images_per_sec", "value": value, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline_leg(seconds_budget=25.0):
+    from oracle import contrad_oracle as O
+    cores = os.cpu_count() or 1
+    prev = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    n = 64
+    gen_w = torch.Generator().manual_seed(0)
+    sd_d, sd_g = O.make_d_state(generator=gen_w), O.make_g_state(generator=gen_w)
+    opt_g = O.Adam(O.trainable(sd_g).values(), 2e-4)
+    opt_d = O.Adam(O.trainable(sd_d).values(), 2e-4)
+    st_np, st_t = np.random.get_state(), torch.get_rng_state()
+    np.random.seed(0); torch.manual_seed(0)
+
+    def one(step):
+        images = torch.rand(n, 3, 32, 32)
+        z_d = O.sample_latent(n); aug_d = O.sample_simclr_params(3 * n, 32, 32)
+        z_g = O.sample_latent(n); aug_g = O.sample_simclr_params(n, 32, 32)
+        O.train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=step)
+
+    one(1)
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 3 or (time.perf_counter() - t0 < seconds_budget and steps < 12):
+        one(steps + 2)
+        steps += 1
+    dt = time.perf_counter() - t0
+    np.random.set_state(st_np); torch.set_rng_state(st_t)
+    torch.set_num_threads(prev)
+    return {"value": n * steps / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": "%d full D+G steps at batch 64 (1/8 of the b512 workload) on the host CPU, torch fp32" % steps}
+
+
+# ----------------------------------------------------------------------------------------------- this repo's arm
+def build_world(args):
+    import gin
+    from contrad_b200 import _capi
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import setup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+    _capi.lib()                                   # fail loudly if the CUDA library is missing
+    gin.clear_config()
+    gin.parse_config(GIN_DEFAULTS)
+    P = SimpleNamespace(mode="contrad", aug="simclr", penalty="none", temp=0.1, lbd_a=1.0, distributed=world > 1,
+                        rank=rank)
+    P = setup(P)
+    torch.manual_seed(1234 + rank); np.random.seed(1234 + rank)
+    G, D = get_architecture("sndcgan", (32, 32, 3))
+    if world > 1:
+        G = torch.nn.SyncBatchNorm.convert_sync_batchnorm(G)
+    G.cuda(); D.cuda()
+    opt_G = torch.optim.Adam(G.parameters(), lr=OPTIONS["lr"], betas=OPTIONS["beta"])
+    opt_D = torch.optim.Adam(D.parameters(), lr=OPTIONS["lr_d"], betas=OPTIONS["beta"])
+    P.augment_fn = get_augment(mode=P.aug).cuda()
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        G_w = DDP(G, device_ids=[local_rank], broadcast_buffers=False)
+        G_w.sample_latent = G.sample_latent
+        D_w = DDP(D, device_ids=[local_rank], broadcast_buffers=False)
+    else:
+        G_w, D_w = G, D
+    return SimpleNamespace(P=P, G=G_w, D=D_w, opt_G=opt_G, opt_D=opt_D, world=world, rank=rank, local_rank=local_rank)
+
+
+def run_native(args):
+    from contrad_b200 import _capi, engine, kernels as K
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback (use --impl reference)")
+    W = build_world(args)
+    world, rank = W.world, W.rank
+    n_local = GLOBAL_BATCH // world
+    dev = torch.device("cuda", W.local_rank if world > 1 else 0)
+    train_fn = W.P.train_fn
+    step_no = [0]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(images):
+        step_no[0] += 1
+        return engine.train_step(W.P, OPTIONS, train_fn, (W.G, W.D), (W.opt_G, W.opt_D), images, step_no[0])
+
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    pool = [torch.rand(n_local, 3, 32, 32, device=dev, generator=gen) for _ in range(4)]
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident arm
+    for w in range(args.warmup):
+        one_step(pool[w % len(pool)])
+    clocks = ClockSampler(W.local_rank if world > 1 else 0)
+    if rank == 0:
+        clocks.start()
+    _capi.reset_launch_count()
+    ms = timed(lambda s: one_step(pool[s % len(pool)]), args.steps)
+    launches = _capi.launch_count()
+    clk = clocks.stop() if rank == 0 else {}
+    value = GLOBAL_BATCH * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: pinned host images -> device every step + the reference's per-step loss read-backs
+    host_pool = [torch.rand(n_local, 3, 32, 32).pin_memory() for _ in range(4)]
+    d2h = [0]
+
+    def e2e_step(s):
+        images = host_pool[s % len(host_pool)].to(dev, non_blocking=True)
+        out = one_step(images)
+        vals = [out[k].item() for k in ("g_loss", "d_loss", "d_penalty", "d_real", "d_gen")]   # train_gan.py:164-167,179
+        d2h[0] = 4 * len(vals)
+        return vals
+
+    for w in range(2):
+        e2e_step(w)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        roof = roofline_legs(K, engine, W, one_step, pool, peaks) if world == 1 else None
+        cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": "train_step_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "per_gpu_batch": n_local,
+                       "parallelism": "dp%d" % world, "image": "3x32x32",
+                       "l2": "per-step working set ~1.3 GB of activations >> 126 MB L2 (no explicit flush needed)"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": n_local * 3 * 32 * 32 * 4, "d2h_bytes_per_step": d2h[0]},
+            "gpu_launches": int(launches),
+            "step_tflops": FLOP_PER_IMAGE_STEP * value / 1e12,
+        }
+        if roof:
+            line.update(roof)
+        if cpu:
+            line["cpu_baseline"] = cpu
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+def roofline_legs(K, engine, W, one_step, pool, peaks):
+    """Per-kernel-family device time measured with CUDA events around every C-ABI call during 3 extra,
+    instrumented steps (same stream); the dominant family gives `roofline`.  Plus the fused-augment HBM
+    point at a saturating size (B = 65536 images of 32x32, 805 MB in)."""
+    records = []
+    K.set_profile_hook(records)
+    for s in range(3):
+        one_step(pool[s % len(pool)])
+    torch.cuda.synchronize()
+    K.set_profile_hook(None)
+    fam = {}
+    for name, e0, e1, flops, nbytes in records:
+        d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["bytes"] += nbytes; d["launches"] += 1
+    total_ms = sum(d["ms"] for d in fam.values()) or 1.0
+    tc = {k: v for k, v in fam.items() if v["flops"] > 0}
+    out = {"kernel_time_share": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+    if tc:
+        name, d = max(tc.items(), key=lambda kv: kv[1]["ms"])
+        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        peak_tf32 = peaks["bf16_tflops_sustained"] / 2.0
+        out["roofline"] = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s",
+                           "frac": achieved / peak_tf32, "traffic": load_traffic(name),
+                           "launches_per_step": d["launches"] / 3.0, "avg_launch_ms": d["ms"] / d["launches"],
+                           "peak_note": "TF32 peak taken as %s bf16 sustained (%.1f TF/s) / 2; frac of bf16 peak = %.3f"
+                                        % (peaks["source"], peaks["bf16_tflops_sustained"], achieved / peaks["bf16_tflops_sustained"])}
+        all_flops = sum(v["flops"] for v in tc.values()); all_ms = sum(v["ms"] for v in tc.values())
+        out["tensor_kernels"] = {"achieved_tflops": all_flops / (all_ms * 1e-3) / 1e12,
+                                 "frac_of_tf32_peak": all_flops / (all_ms * 1e-3) / 1e12 / peak_tf32}
+    # fused augment at the HBM-saturating size
+    from contrad_b200.augment.layers import FusedSimCLR  # noqa: F401
+    B = 65536
+    x = torch.rand(B, 3, 32, 32, device="cuda")
+    params, order = W.P.augment_fn.sample_params(x)
+    for _ in range(3):
+        K.augment_simclr_fwd(x, params, order)
+    evs = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); K.augment_simclr_fwd(x, params, order); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    gbs = 8.0 * x.numel() / (ms * 1e-3) / 1e9
+    out["roofline_augment"] = {"kernel": "augment_simclr_fwd", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": load_traffic("augment_simclr_fwd"),
+                               "size": "B=65536 x 3x32x32 fp32 (805 MB in, 805 MB out), 8 algorithmic B/element",
+                               "peak_note": "%s copy bandwidth" % peaks["source"]}
+    return out
+
+
+def load_traffic(kernel):
+    """dram bytes per launch from the committed ncu summary (profiles/traffic.json), or None."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

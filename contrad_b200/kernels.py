@@ -8,6 +8,28 @@ from ._capi import check, f32, i32, i64, lib, ptr, stream_ptr
 PARAM_FIELDS = ("sx", "sy", "bx", "by", "flip", "cj_on", "contrast", "hue", "sat", "val", "gray_on")
 
 
+_PROFILE = None
+
+
+def set_profile_hook(records):
+    """records: a list that receives (kernel family, start event, end event, algorithmic FLOPs, bytes) for
+    every C-ABI call made while set (bench.py's instrumented steps); None disables."""
+    global _PROFILE
+    _PROFILE = records
+
+
+def _call(name, flops, nbytes, fn, *args):
+    if _PROFILE is None:
+        check(fn(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args), name)
+    e1.record()
+    _PROFILE.append((name, e0, e1, float(flops), float(nbytes)))
+
+
 def _f32c(t, name):
     if t.dtype != torch.float32:
         raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
@@ -21,8 +43,8 @@ def augment_simclr_fwd(x, params, order):
     B, C, H, W = x.shape
     assert C == 3 and params.shape == (len(PARAM_FIELDS), B), (x.shape, params.shape)
     y = torch.empty_like(x)
-    check(lib().cb200_augment_simclr_fwd(ptr(x), ptr(y), ptr(params), i32(B), i32(H), i32(W), i32(order),
-                                         stream_ptr()), "cb200_augment_simclr_fwd")
+    _call("augment_simclr_fwd", 0, 8 * x.numel(), lib().cb200_augment_simclr_fwd, ptr(x), ptr(y), ptr(params), i32(B), i32(H), i32(W), i32(order),
+                                         stream_ptr())
     return y
 
 
@@ -32,8 +54,8 @@ def augment_simclr_bwd(x, dy, params, order):
     params = _f32c(params, "params")
     B, C, H, W = x.shape
     dx = torch.empty_like(x)
-    check(lib().cb200_augment_simclr_bwd(ptr(x), ptr(dy), ptr(dx), ptr(params), i32(B), i32(H), i32(W), i32(order),
-                                         stream_ptr()), "cb200_augment_simclr_bwd")
+    _call("augment_simclr_bwd", 0, 12 * x.numel(), lib().cb200_augment_simclr_bwd, ptr(x), ptr(dy), ptr(dx), ptr(params), i32(B), i32(H), i32(W), i32(order),
+                                         stream_ptr())
     return dx
 
 
@@ -50,9 +72,9 @@ def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None):
     assert out.shape == (M, N) and out.stride(1) == 1
     if dact is not None:
         assert dact.shape == (M, N) and dact.stride(1) == 1 and dact.stride(0) == out.stride(0)
-    check(lib().cb200_gemm_nt_tf32(ptr(a), i64(a.stride(0)), ptr(bw), i64(bw.stride(0)), ptr(bias), ptr(dact), ptr(out),
+    _call("gemm_nt_tf32", 2.0 * M * N * K, 4 * (M * K + N * K + M * N), lib().cb200_gemm_nt_tf32, ptr(a), i64(a.stride(0)), ptr(bw), i64(bw.stride(0)), ptr(bias), ptr(dact), ptr(out),
                                    i64(out.stride(0)), i32(M), i32(N), i32(K), f32(slope), i32(1 if round_out else 0),
-                                   stream_ptr()), "cb200_gemm_nt_tf32")
+                                   stream_ptr())
     return out
 
 
@@ -64,9 +86,9 @@ def conv2d_nhwc_fwd(x, wmat, bias, ks, stride, slope=1.0, round_out=False):
     assert wmat.shape[1] == ks * ks * Cin and wmat.is_contiguous()
     Ho, Wo = H // stride, W // stride
     y = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=torch.float32)
-    check(lib().cb200_conv2d_nhwc_fwd(ptr(x), ptr(wmat), ptr(bias), ptr(y), i32(B), i32(H), i32(W), i32(Cin),
+    _call("conv2d_nhwc_fwd", 2.0 * B * Ho * Wo * Cout * Cin * ks * ks, 4 * (x.numel() + wmat.numel() + y.numel()), lib().cb200_conv2d_nhwc_fwd, ptr(x), ptr(wmat), ptr(bias), ptr(y), i32(B), i32(H), i32(W), i32(Cin),
                                       i32(Cout), i32(ks), i32(stride), f32(slope), i32(1 if round_out else 0),
-                                      stream_ptr()), "cb200_conv2d_nhwc_fwd")
+                                      stream_ptr())
     return y
 
 
@@ -76,9 +98,9 @@ def conv2d_nhwc_dgrad(dy, wmat_t, in_shape, ks, stride, act_in=None, bias_out=No
     B, H, W, Cin = in_shape
     Cout = dy.shape[3]
     dx = torch.empty(B, H, W, Cin, device=dy.device, dtype=torch.float32)
-    check(lib().cb200_conv2d_nhwc_dgrad(ptr(dy), ptr(wmat_t), ptr(act_in), ptr(bias_out), ptr(dx), i32(B), i32(H),
+    _call("conv2d_nhwc_dgrad", 2.0 * B * (H // stride) * (W // stride) * Cout * Cin * ks * ks, 4 * (dy.numel() + wmat_t.numel() + dx.numel()), lib().cb200_conv2d_nhwc_dgrad, ptr(dy), ptr(wmat_t), ptr(act_in), ptr(bias_out), ptr(dx), i32(B), i32(H),
                                         i32(W), i32(Cin), i32(Cout), i32(ks), i32(stride), f32(slope),
-                                        i32(1 if round_out else 0), stream_ptr()), "cb200_conv2d_nhwc_dgrad")
+                                        i32(1 if round_out else 0), stream_ptr())
     return dx
 
 
@@ -89,8 +111,8 @@ def conv2d_nhwc_wgrad(x, dy, ks, stride):
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
     dw = torch.empty(Cout, ks * ks * Cin, device=x.device, dtype=torch.float32)
-    check(lib().cb200_conv2d_nhwc_wgrad(ptr(x), ptr(dy), ptr(dw), i32(B), i32(H), i32(W), i32(Cin), i32(Cout),
-                                        i32(ks), i32(stride), stream_ptr()), "cb200_conv2d_nhwc_wgrad")
+    _call("conv2d_nhwc_wgrad", 2.0 * B * (H // stride) * (W // stride) * Cout * Cin * ks * ks, 4 * (x.numel() + dy.numel() + dw.numel()), lib().cb200_conv2d_nhwc_wgrad, ptr(x), ptr(dy), ptr(dw), i32(B), i32(H), i32(W), i32(Cin), i32(Cout),
+                                        i32(ks), i32(stride), stream_ptr())
     return dw
 
 
@@ -103,8 +125,8 @@ def gemm_tn_wgrad(dy, x, out=None):
     if out is None:
         out = torch.empty(N, Kd, device=x.device, dtype=torch.float32)
     assert out.shape == (N, Kd) and out.stride(1) == 1
-    check(lib().cb200_gemm_tn_wgrad(ptr(dy), i64(dy.stride(0)), ptr(x), i64(x.stride(0)), ptr(out), i64(out.stride(0)),
-                                    i32(M), i32(N), i32(Kd), stream_ptr()), "cb200_gemm_tn_wgrad")
+    _call("gemm_tn_wgrad", 2.0 * M * N * Kd, 4 * (M * N + M * Kd + N * Kd), lib().cb200_gemm_tn_wgrad, ptr(dy), i64(dy.stride(0)), ptr(x), i64(x.stride(0)), ptr(out), i64(out.stride(0)),
+                                    i32(M), i32(N), i32(Kd), stream_ptr())
     return out
 
 
@@ -115,24 +137,24 @@ def sn_power_iter(w, u, v, sigma, training=True, eps=1e-12):
     Fdim = w.numel() // Cout
     t = torch.empty(Fdim, device=w.device, dtype=torch.float32)
     s = torch.empty(Cout, device=w.device, dtype=torch.float32)
-    check(lib().cb200_sn_power_iter(ptr(w), ptr(u), ptr(v), ptr(sigma), ptr(t), ptr(s), i32(Cout), i32(Fdim),
-                                    f32(eps), i32(1 if training else 0), stream_ptr()), "cb200_sn_power_iter")
+    _call("sn_power_iter", 0, 0, lib().cb200_sn_power_iter, ptr(w), ptr(u), ptr(v), ptr(sigma), ptr(t), ptr(s), i32(Cout), i32(Fdim),
+                                    f32(eps), i32(1 if training else 0), stream_ptr())
 
 
 def sn_pack_weights(w4, sigma, fwd=None, ld_fwd=0, dgrad=None, dgrad_mode=0, ldt=0, col0=0, round_out=True):
     """w4: weight viewed as [Cout, Cin, KH, KW] (contiguous)."""
     Cout, Cin, KH, KW = w4.shape
-    check(lib().cb200_sn_pack_weights(ptr(w4), ptr(sigma), ptr(fwd), i64(ld_fwd), ptr(dgrad), i32(dgrad_mode),
+    _call("sn_pack_weights", 0, 0, lib().cb200_sn_pack_weights, ptr(w4), ptr(sigma), ptr(fwd), i64(ld_fwd), ptr(dgrad), i32(dgrad_mode),
                                       i64(ldt), i32(col0), i32(Cout), i32(Cin), i32(KH), i32(KW),
-                                      i32(1 if round_out else 0), stream_ptr()), "cb200_sn_pack_weights")
+                                      i32(1 if round_out else 0), stream_ptr())
 
 
 def sn_weight_bwd(dw_hat_packed, ld_fwd, w4, u, v, sigma, dw_out, accumulate=False):
     Cout, Cin, KH, KW = w4.shape
     acc = torch.empty(1, device=w4.device, dtype=torch.float32)
-    check(lib().cb200_sn_weight_bwd(ptr(dw_hat_packed), i64(ld_fwd), ptr(w4), ptr(u), ptr(v), ptr(sigma), ptr(acc),
+    _call("sn_weight_bwd", 0, 0, lib().cb200_sn_weight_bwd, ptr(dw_hat_packed), i64(ld_fwd), ptr(w4), ptr(u), ptr(v), ptr(sigma), ptr(acc),
                                     ptr(dw_out), i32(1 if accumulate else 0), i32(Cout), i32(Cin), i32(KH), i32(KW),
-                                    stream_ptr()), "cb200_sn_weight_bwd")
+                                    stream_ptr())
     return dw_out
 
 
@@ -142,8 +164,8 @@ def conv_first_fwd(x, w, sigma, bias, slope=0.1, round_out=True):
     B, C, H, W = x.shape
     assert C == 3 and w.shape == (64, 3, 3, 3) and w.is_contiguous()
     y = torch.empty(B, H, W, 64, device=x.device, dtype=torch.float32)
-    check(lib().cb200_conv_first_fwd(ptr(x), ptr(w), ptr(sigma), ptr(bias), ptr(y), i32(B), i32(H), i32(W),
-                                     f32(slope), i32(1 if round_out else 0), stream_ptr()), "cb200_conv_first_fwd")
+    _call("conv_first_fwd", 0, 0, lib().cb200_conv_first_fwd, ptr(x), ptr(w), ptr(sigma), ptr(bias), ptr(y), i32(B), i32(H), i32(W),
+                                     f32(slope), i32(1 if round_out else 0), stream_ptr())
     return y
 
 
@@ -153,8 +175,7 @@ def conv_first_wgrad(x, dy):
     B, C, H, W = x.shape
     dw = torch.zeros(64, 27, device=x.device, dtype=torch.float32)
     db = torch.zeros(64, device=x.device, dtype=torch.float32)
-    check(lib().cb200_conv_first_wgrad(ptr(x), ptr(dy), ptr(dw), ptr(db), i32(B), i32(H), i32(W), stream_ptr()),
-          "cb200_conv_first_wgrad")
+    _call("conv_first_wgrad", 0, 0, lib().cb200_conv_first_wgrad, ptr(x), ptr(dy), ptr(dw), ptr(db), i32(B), i32(H), i32(W), stream_ptr())
     return dw, db
 
 
@@ -162,8 +183,7 @@ def conv_first_dgrad_finish(dpad):
     dpad = _f32c(dpad, "dpad")
     B, H, W, cpad = dpad.shape
     dx = torch.empty(B, 3, H, W, device=dpad.device, dtype=torch.float32)
-    check(lib().cb200_conv_first_dgrad_finish(ptr(dpad), ptr(dx), i32(B), i32(H), i32(W), i32(cpad), stream_ptr()),
-          "cb200_conv_first_dgrad_finish")
+    _call("conv_first_dgrad_finish", 0, 0, lib().cb200_conv_first_dgrad_finish, ptr(dpad), ptr(dx), i32(B), i32(H), i32(W), i32(cpad), stream_ptr())
     return dx
 
 
@@ -177,8 +197,8 @@ def rownorm_fwd(x, eps=1e-12):
     rows, d = x.shape
     y = torch.empty(rows, d, device=x.device, dtype=torch.float32)
     inv = torch.empty(rows, device=x.device, dtype=torch.float32)
-    check(lib().cb200_rownorm_fwd(ptr(x), i64(x.stride(0)), ptr(y), ptr(inv), i32(rows), i32(d), f32(eps),
-                                  stream_ptr()), "cb200_rownorm_fwd")
+    _call("rownorm_fwd", 0, 0, lib().cb200_rownorm_fwd, ptr(x), i64(x.stride(0)), ptr(y), ptr(inv), i32(rows), i32(d), f32(eps),
+                                  stream_ptr())
     return y, inv
 
 
@@ -188,8 +208,8 @@ def rownorm_bwd(dy, y, inv, out=None, round_out=False):
     if out is None:
         out = torch.empty(rows, d, device=y.device, dtype=torch.float32)
     assert out.stride(1) == 1
-    check(lib().cb200_rownorm_bwd(ptr(dy), ptr(y), ptr(inv), ptr(out), i64(out.stride(0)), i32(rows), i32(d),
-                                  i32(1 if round_out else 0), stream_ptr()), "cb200_rownorm_bwd")
+    _call("rownorm_bwd", 0, 0, lib().cb200_rownorm_bwd, ptr(dy), ptr(y), ptr(inv), ptr(out), i64(out.stride(0)), i32(rows), i32(d),
+                                  i32(1 if round_out else 0), stream_ptr())
     return out
 
 
@@ -201,8 +221,8 @@ def contrastive_fwd(z, n, mode, temperature):
     lse = torch.empty(active, device=z.device, dtype=torch.float32)
     row_loss = torch.empty(active, device=z.device, dtype=torch.float32)
     loss = torch.empty(1, device=z.device, dtype=torch.float32)
-    check(lib().cb200_contrastive_fwd(ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
-                                      ptr(row_loss), ptr(loss), stream_ptr()), "cb200_contrastive_fwd")
+    _call("contrastive_fwd", 0, 0, lib().cb200_contrastive_fwd, ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
+                                      ptr(row_loss), ptr(loss), stream_ptr())
     return loss, lse
 
 
@@ -210,8 +230,8 @@ def contrastive_bwd(z, n, mode, temperature, lse, gscale):
     z = _f32c(z, "z")
     dz = torch.empty_like(z)
     gscale = _f32c(gscale.reshape(1), "gscale")
-    check(lib().cb200_contrastive_bwd(ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
-                                      ptr(gscale), ptr(dz), stream_ptr()), "cb200_contrastive_bwd")
+    _call("contrastive_bwd", 0, 0, lib().cb200_contrastive_bwd, ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
+                                      ptr(gscale), ptr(dz), stream_ptr())
     return dz
 
 
@@ -222,8 +242,8 @@ def gan_d_loss(d_real, d_gen, kind):
     out = torch.empty(3, device=d_real.device, dtype=torch.float32)
     g_r = torch.empty(n, device=d_real.device, dtype=torch.float32)
     g_g = torch.empty(n, device=d_real.device, dtype=torch.float32)
-    check(lib().cb200_gan_d_loss(ptr(d_real), ptr(d_gen), i64(d_real.stride(0)), i32(n), i32(LOSS_KINDS[kind]),
-                                 ptr(out), ptr(g_r), ptr(g_g), stream_ptr()), "cb200_gan_d_loss")
+    _call("gan_d_loss", 0, 0, lib().cb200_gan_d_loss, ptr(d_real), ptr(d_gen), i64(d_real.stride(0)), i32(n), i32(LOSS_KINDS[kind]),
+                                 ptr(out), ptr(g_r), ptr(g_g), stream_ptr())
     return out, g_r, g_g
 
 
@@ -233,8 +253,7 @@ def gan_g_loss(d_gen, kind):
     out = torch.empty(1, device=d_gen.device, dtype=torch.float32)
     g = torch.empty(n, device=d_gen.device, dtype=torch.float32)
     k = LOSS_KINDS.get(kind, 2)
-    check(lib().cb200_gan_g_loss(ptr(d_gen), i64(d_gen.stride(0)), i32(n), i32(k), ptr(out), ptr(g), stream_ptr()),
-          "cb200_gan_g_loss")
+    _call("gan_g_loss", 0, 0, lib().cb200_gan_g_loss, ptr(d_gen), i64(d_gen.stride(0)), i32(n), i32(k), ptr(out), ptr(g), stream_ptr())
     return out, g
 
 
@@ -242,8 +261,8 @@ def lrelu_bwd(dy, act, slope, round_out=False):
     dy = _f32c(dy, "dy")
     act = _f32c(act, "act")
     out = torch.empty_like(act)
-    check(lib().cb200_lrelu_bwd(ptr(dy), ptr(act), ptr(out), i64(act.numel()), f32(slope), i32(1 if round_out else 0),
-                                stream_ptr()), "cb200_lrelu_bwd")
+    _call("lrelu_bwd", 0, 0, lib().cb200_lrelu_bwd, ptr(dy), ptr(act), ptr(out), i64(act.numel()), f32(slope), i32(1 if round_out else 0),
+                                stream_ptr())
     return out
 
 
@@ -251,7 +270,7 @@ def colsum(x2d):
     assert x2d.dim() == 2 and x2d.stride(1) == 1
     M, N = x2d.shape
     out = torch.empty(N, device=x2d.device, dtype=torch.float32)
-    check(lib().cb200_colsum(ptr(x2d), i64(x2d.stride(0)), i32(M), i32(N), ptr(out), stream_ptr()), "cb200_colsum")
+    _call("colsum", 0, 0, lib().cb200_colsum, ptr(x2d), i64(x2d.stride(0)), i32(M), i32(N), ptr(out), stream_ptr())
     return out
 
 

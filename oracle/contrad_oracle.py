@@ -563,8 +563,9 @@ def train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=1,
     l_con, l_dis, ex = loss_d(sd_d, images, gen, aug_d[0], aug_d[1], temp, lbd_a, loss)
     opt_d.zero_grad()
     (l_con + l_dis).backward()
-    out.update(l_con_pos=float(ex["l_con_pos"]), l_con_neg=float(ex["l_con_neg"]), l_dis=float(l_dis),
-               d_real=float(ex["d_real"]), d_gen=float(ex["d_gen"]), d_grad_norm=grad_norm(sd_d))
+    out.update(l_con_pos=float(ex["l_con_pos"].detach()), l_con_neg=float(ex["l_con_neg"].detach()),
+               l_dis=float(l_dis.detach()), d_real=float(ex["d_real"].detach()), d_gen=float(ex["d_gen"].detach()),
+               d_grad_norm=grad_norm(sd_d))
     opt_d.step()
     # ---- G step
     set_requires_grad(sd_g, True)
@@ -573,6 +574,6 @@ def train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=1,
     l_gen = loss_g(sd_d, gen, aug_g[0], aug_g[1], loss)
     opt_g.zero_grad()
     l_gen.backward()
-    out.update(l_gen=float(l_gen), g_grad_norm=grad_norm(sd_g))
+    out.update(l_gen=float(l_gen.detach()), g_grad_norm=grad_norm(sd_g))
     opt_g.step()
     return out
