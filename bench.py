@@ -55,6 +55,23 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def usable_cores():
+    """Host threads the CPU baseline may use: scheduler affinity, capped by the cgroup CPU quota if there is one,
+    and by 32 (torch's CPU convolutions at batch 64 stop scaling - and badly oversubscribe - beyond that)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -117,7 +134,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     from oracle import contrad_oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     n = 64
     gen_w = torch.Generator().manual_seed(0)
@@ -153,7 +170,7 @@ def run_reference(args):
 
 def cpu_baseline_leg(seconds_budget=25.0):
     from oracle import contrad_oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     prev = torch.get_num_threads()
     torch.set_num_threads(cores)
     n = 64

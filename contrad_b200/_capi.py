@@ -70,6 +70,8 @@ def ptr(t):
 
 def stream_ptr():
     import torch
+    if not torch.cuda.is_available():
+        raise CB200Error("contrad_b200 kernels need a CUDA device; there is no CPU path")
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

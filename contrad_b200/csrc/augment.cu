@@ -51,10 +51,12 @@ __device__ __forceinline__ SampleParams load_params(const float* __restrict__ p,
 
 // grid_sample(padding_mode='reflection', align_corners=False): reflect about -0.5 and size-0.5,
 // clip to [0, size-1].
-__device__ __forceinline__ float fold_coord(float coord, float size) {
+// (fmod via floor: exact for power-of-two sizes; elsewhere the two branches agree at the reflection points.)
+__device__ __forceinline__ float fold_coord(float coord, float size, float inv_size) {
     float t = fabsf(coord + 0.5f);
-    float extra = fmodf(t, size);
-    int flips = (int)floorf(t / size);
+    float fl = floorf(t * inv_size);
+    float extra = fmaf(-fl, size, t);
+    int flips = (int)fl;
     float r = (flips & 1) ? (size - extra - 0.5f) : (extra - 0.5f);
     return fminf(fmaxf(r, 0.f), size - 1.f);
 }
@@ -67,9 +69,10 @@ struct Tap {
 // Source taps of output index `o` along an axis of length n for scale s and bias b.
 __device__ __forceinline__ Tap axis_tap(int o, int n, float s, float b) {
     float fn = (float)n;
-    float base = (2.f * (float)o + 1.f) / fn - 1.f;
+    float inv = 1.f / fn;
+    float base = (2.f * (float)o + 1.f) * inv - 1.f;
     float g = s * base + b;
-    float p = fold_coord(((g + 1.f) * fn - 1.f) * 0.5f, fn);
+    float p = fold_coord(((g + 1.f) * fn - 1.f) * 0.5f, fn, inv);
     float p0 = floorf(p);
     Tap t;
     t.i0 = (int)p0;
@@ -83,19 +86,41 @@ __device__ __forceinline__ Tap axis_tap(int o, int n, float s, float b) {
     return t;
 }
 
+// atan2(y, x) / (2 pi) folded into [0, 1): 8-term minimax odd polynomial on [0,1] (max abs error 1.2e-7 rad)
+// + octant fix-ups; the division is the fast reciprocal (2 ulp) - the result feeds a piecewise-linear
+// colour wheel with slope <= 6, so 1e-7 in the turn fraction is far below the fp32 noise of the chain.
+__device__ __forceinline__ float hue_turns(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float u = t * t;
+    float p = -0.004054375924170017f;
+    p = fmaf(p, u, 0.021862227469682693f);
+    p = fmaf(p, u, -0.05591120570898056f);
+    p = fmaf(p, u, 0.09642109274864197f);
+    p = fmaf(p, u, -0.13908591866493225f);
+    p = fmaf(p, u, 0.1994655728340149f);
+    p = fmaf(p, u, -0.33329859375953674f);
+    p = fmaf(p, u, 0.9999993443489075f);
+    float a = p * t;                                   // atan(mn/mx) in [0, pi/4]
+    if (ay > ax) a = 1.5707963267948966f - a;           // first quadrant
+    if (x < 0.f) a = 3.141592653589793f - a;            // upper half plane
+    if (y < 0.f) a = 6.283185307179586f - a;            // == (atan2 < 0 ? atan2 + 2 pi : atan2)
+    return a * 0.15915494309189535f;
+}
+
 // RandomHSVFunction.forward on one pixel (augment/color_jitter.py:83-95, augment/utils.py:27-38,55-63).
-__device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float fh, float fs, float fv) {
+// `hshift` = (f_h * 255) / 360 is hoisted per image.
+__device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float hshift, float fs, float fv) {
     float cmax = fmaxf(r, fmaxf(g, b));
     float cmin = fminf(r, fminf(g, b));
-    float hue = atan2f(1.7320508075688772f * (g - b), 2.f * r - g - b);
-    if (hue < 0.f) hue += 6.283185307179586f;
-    hue = hue / 6.283185307179586f;
-    float sat = 1.f - cmin / (cmax + 1e-8f);
+    float hue = hue_turns(1.7320508075688772f * (g - b), 2.f * r - g - b);
+    float sat = 1.f - __fdividef(cmin, cmax + 1e-8f);
     float val = cmax;
     if (!isfinite(hue)) hue = 0.f;
     if (!isfinite(sat)) sat = 0.f;
     if (!isfinite(val)) val = 0.f;
-    float h = hue + (fh * 255.f) / 360.f;
+    float h = hue + hshift;
     h = h - floorf(h);
     float s = sat * fs;
     float v = val * fv;
@@ -120,23 +145,56 @@ __device__ __forceinline__ void stage_image(const float* __restrict__ src, float
     }
 }
 
+// Per-image tap tables in shared memory: column taps already include the horizontal flip.
+struct TapTables {
+    int* xi0; int* xi1; float* xw0; float* xw1;     // [W]
+    int* yi0; int* yi1; float* yw0; float* yw1;     // [H]
+};
+
+__device__ __forceinline__ TapTables carve_taps(float* base, int H, int W) {
+    TapTables t;
+    t.xi0 = reinterpret_cast<int*>(base);          t.xi1 = t.xi0 + W;
+    t.xw0 = base + 2 * W;                          t.xw1 = base + 3 * W;
+    float* yb = base + 4 * W;
+    t.yi0 = reinterpret_cast<int*>(yb);            t.yi1 = t.yi0 + H;
+    t.yw0 = yb + 2 * H;                            t.yw1 = yb + 3 * H;
+    return t;
+}
+
+__device__ __forceinline__ void fill_taps(const TapTables& t, int H, int W, const SampleParams& sp) {
+    for (int e = threadIdx.x; e < W + H; e += blockDim.x) {
+        if (e < W) {
+            const int jj = (sp.flip < 0.f) ? (W - 1 - e) : e;
+            const Tap a = axis_tap(jj, W, sp.sx, sp.bx);
+            t.xi0[e] = a.i0; t.xi1[e] = a.i1; t.xw0[e] = a.w0; t.xw1[e] = a.w1;
+        } else {
+            const int i = e - W;
+            const Tap a = axis_tap(i, H, sp.sy, sp.by);
+            t.yi0[i] = a.i0; t.yi1[i] = a.i1; t.yw0[i] = a.w0; t.yw1[i] = a.w1;
+        }
+    }
+}
+
 // crop+flip for the quad (row i, cols j0..j0+3): out[c][k]
-__device__ __forceinline__ void gather_quad(const float* xs, int H, int W, int i, int j0, const SampleParams& sp,
+__device__ __forceinline__ void gather_quad(const float* xs, int H, int W, int i, int j0, const TapTables& t,
                                             float (&out)[3][4]) {
     const int HW = H * W;
-    Tap ty = axis_tap(i, H, sp.sy, sp.by);
+    const float wy0 = t.yw0[i], wy1 = t.yw1[i];
+    const float* r0 = xs + t.yi0[i] * W;
+    const float* r1 = xs + t.yi1[i] * W;
+    const int4 i0 = *reinterpret_cast<const int4*>(t.xi0 + j0);
+    const int4 i1 = *reinterpret_cast<const int4*>(t.xi1 + j0);
+    const float4 w0 = *reinterpret_cast<const float4*>(t.xw0 + j0);
+    const float4 w1 = *reinterpret_cast<const float4*>(t.xw1 + j0);
+    const int a0[4] = {i0.x, i0.y, i0.z, i0.w}, a1[4] = {i1.x, i1.y, i1.z, i1.w};
+    const float b0[4] = {w0.x, w0.y, w0.z, w0.w}, b1[4] = {w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        int j = j0 + k;
-        int jj = (sp.flip < 0.f) ? (W - 1 - j) : j;
-        Tap tx = axis_tap(jj, W, sp.sx, sp.bx);
-        float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
-        const float* r0 = xs + ty.i0 * W;
-        const float* r1 = xs + ty.i1 * W;
+        const float w00 = b0[k] * wy0, w01 = b1[k] * wy0, w10 = b0[k] * wy1, w11 = b1[k] * wy1;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            out[c][k] = r0[c * HW + tx.i0] * w00 + r0[c * HW + tx.i1] * w01 + r1[c * HW + tx.i0] * w10 +
-                        r1[c * HW + tx.i1] * w11;
+            out[c][k] = r0[c * HW + a0[k]] * w00 + r0[c * HW + a1[k]] * w01 + r1[c * HW + a0[k]] * w10 +
+                        r1[c * HW + a1[k]] * w11;
         }
     }
 }
@@ -148,10 +206,13 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                      // [3*H*W]
     float* red = smem + 3 * H * W;         // [3*32]
+    const TapTables taps = carve_taps(red + 96, H, W);
     const int b = blockIdx.x;
     const int HW = H * W, Wq = W >> 2, nquads = HW >> 2;
     const SampleParams sp = load_params(params, B, b);
+    const float hshift = (sp.fh * 255.f) / 360.f;
     stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);
+    fill_taps(taps, H, W, sp);
     __syncthreads();
 
     float v[QPT][3][4];
@@ -161,7 +222,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
         int quad = threadIdx.x + q * blockDim.x;
         live[q] = quad < nquads;
         if (live[q]) {
-            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, sp, v[q]);
+            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, taps, v[q]);
         } else {
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -176,7 +237,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
             for (int q = 0; q < QPT; ++q)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], sp.fh, sp.fs, sp.fv);
+                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], hshift, sp.fs, sp.fv);
         }
         float sums[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -198,7 +259,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
             for (int q = 0; q < QPT; ++q)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], sp.fh, sp.fs, sp.fv);
+                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], hshift, sp.fs, sp.fv);
         }
     }
     float* yb = y + (size_t)b * 3 * HW;
@@ -228,10 +289,14 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
     float* xs = smem;                  // [3*HW] forward image
     float* gs = smem + 3 * HW;         // [3*HW] dx accumulator
     float* red = smem + 6 * HW;        // [3*32]
+    const TapTables taps = carve_taps(red + 96, H, W);
     const int b = blockIdx.x;
     const SampleParams sp = load_params(params, B, b);
-    stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);
-    for (int e = threadIdx.x; e < 3 * HW; e += blockDim.x) gs[e] = 0.f;
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    if (sp.cj_on != 0.f) stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);   // x only feeds the clamp mask
+    for (int e = threadIdx.x * 4; e < 3 * HW; e += blockDim.x * 4)
+        *reinterpret_cast<float4*>(gs + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    fill_taps(taps, H, W, sp);
     __syncthreads();
 
     float f[QPT][3][4];   // forward value at the contrast input (crop+flip, optionally hsv)
@@ -265,10 +330,10 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
         for (int q = 0; q < QPT; ++q) {
             if (!live[q]) continue;
             int quad = threadIdx.x + q * blockDim.x;
-            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, sp, f[q]);
+            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, taps, f[q]);
             if (order == 1) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) hsv_jitter(f[q][0][k], f[q][1][k], f[q][2][k], sp.fh, sp.fs, sp.fv);
+                for (int k = 0; k < 4; ++k) hsv_jitter(f[q][0][k], f[q][1][k], f[q][2][k], hshift, sp.fs, sp.fv);
             }
         }
         float sums[3] = {0.f, 0.f, 0.f};
@@ -308,21 +373,22 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
         if (!live[q]) continue;
         int quad = threadIdx.x + q * blockDim.x;
         int i = quad / Wq, j0 = (quad % Wq) * 4;
-        Tap ty = axis_tap(i, H, sp.sy, sp.by);
+        const float wy0 = taps.yw0[i], wy1 = taps.yw1[i];
+        const int y0 = taps.yi0[i] * W, y1 = taps.yi1[i] * W;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            int j = j0 + k;
-            int jj = (sp.flip < 0.f) ? (W - 1 - j) : j;
-            Tap tx = axis_tap(jj, W, sp.sx, sp.bx);
-            float w00 = tx.w0 * ty.w0, w01 = tx.w1 * ty.w0, w10 = tx.w0 * ty.w1, w11 = tx.w1 * ty.w1;
+            const int j = j0 + k;
+            const int x0 = taps.xi0[j], x1 = taps.xi1[j];
+            const float wx0 = taps.xw0[j], wx1 = taps.xw1[j];
+            float w00 = wx0 * wy0, w01 = wx1 * wy0, w10 = wx0 * wy1, w11 = wx1 * wy1;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 float gv = g[q][c][k];
                 float* base = gs + c * HW;
-                atomicAdd(base + ty.i0 * W + tx.i0, gv * w00);
-                if (w01 != 0.f) atomicAdd(base + ty.i0 * W + tx.i1, gv * w01);
-                if (w10 != 0.f) atomicAdd(base + ty.i1 * W + tx.i0, gv * w10);
-                if (w11 != 0.f) atomicAdd(base + ty.i1 * W + tx.i1, gv * w11);
+                atomicAdd(base + y0 + x0, gv * w00);
+                if (w01 != 0.f) atomicAdd(base + y0 + x1, gv * w01);
+                if (w10 != 0.f) atomicAdd(base + y1 + x0, gv * w10);
+                if (w11 != 0.f) atomicAdd(base + y1 + x1, gv * w11);
             }
         }
     }
@@ -358,7 +424,7 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
     LaunchShape ls;
     CB200_CHECK_ARG(pick_shape(H, W, &ls),
                     "augment_fwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
-    size_t smem = (size_t)(3 * H * W + 96) * sizeof(float);
+    size_t smem = (size_t)(3 * H * W + 96 + 4 * W + 4 * H) * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_FWD(Q)                                                                                          \
     do {                                                                                                       \
@@ -382,7 +448,7 @@ extern "C" int cb200_augment_simclr_bwd(const float* x, const float* dy, float* 
     LaunchShape ls;
     CB200_CHECK_ARG(pick_shape(H, W, &ls),
                     "augment_bwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
-    size_t smem = (size_t)(6 * H * W + 96) * sizeof(float);
+    size_t smem = (size_t)(6 * H * W + 96 + 4 * W + 4 * H) * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_BWD(Q)                                                                                          \
     do {                                                                                                       \

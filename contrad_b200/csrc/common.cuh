@@ -64,6 +64,24 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* scratch) {
     __syncthreads();
 }
 
+// Column reductions over a row-major [M, C] matrix with few columns: the 256 threads of a CTA are arranged as
+// (256 / cc) row lanes x cc columns (cc = min(C, 256), a power of two), so all lanes stay busy when C < 256.
+// After the per-thread loop over rows, fold the row lanes: result valid in the threads with row lane 0.
+template <int NV>
+__device__ __forceinline__ void fold_row_lanes(float (&v)[NV], float* scratch /* NV * 256 floats */, int cc) {
+    const int lanes = blockDim.x / cc;
+    if (lanes <= 1) return;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[i * 256 + threadIdx.x] = v[i];
+    __syncthreads();
+    if ((int)threadIdx.x < cc) {
+        for (int r = 1; r < lanes; ++r) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] += scratch[i * 256 + r * cc + threadIdx.x];
+        }
+    }
+}
+
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -24,7 +24,7 @@ constexpr int kCols = 32;       // output columns per CTA
 __global__ void __launch_bounds__(kThreads)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ sigma,
                       const float* __restrict__ bias, float* __restrict__ y, int H, int W, float slope,
-                      int round_out) {
+                      int round_out, float in_scale, float in_shift) {
     __shared__ float xs[3][kRows + 2][kCols + 2];
     __shared__ __align__(16) float ws[27][kCo];
     const int b = blockIdx.z;
@@ -41,7 +41,8 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
         int cc = i % (kCols + 2);
         int hh = h0 + r - 1, ww = w0 + cc - 1;
         float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * 2.f - 1.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+            v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * in_scale + in_shift;
         xs[c][r][cc] = v;
     }
     __syncthreads();
@@ -88,47 +89,56 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 }
 
 // dW_hat[co][ci*9+kh*3+kw] += sum_pixels dY[pix][co] * (2x-1)[ci][h+kh-1][w+kw-1];   db[co] += sum dY
-// CTA = one image row-block of 4 rows x 32 cols (same tiling as forward); threads: 16 channel groups
-// (4 channels) x 4 tap groups (7 taps; 27 = 7+7+7+6) x 4 pixel slices.
+// Persistent CTAs: each CTA walks a strided list of (image, 4-row x 32-col) tiles and keeps its partial
+// dW in REGISTERS across tiles, so the global atomics are issued once per CTA (grid * 1792 in total)
+// instead of once per tile.  Threads: 16 channel groups (4 channels) x 4 tap groups (7 taps; 27 = 7+7+7+6)
+// x 4 pixel slices (one output row each).
 __global__ void __launch_bounds__(kThreads)
 conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                        float* __restrict__ db, int H, int W) {
+                        float* __restrict__ db, int B, int H, int W, float in_scale, float in_shift) {
     __shared__ float xs[3][kRows + 2][kCols + 2];
     __shared__ __align__(16) float part[4][28][kCo];      // per pixel-slice partial dW (27 taps + 1 bias row)
-    const int b = blockIdx.z;
-    const int h0 = blockIdx.y * kRows;
-    const int w0 = blockIdx.x * kCols;
-    for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
-        int c = i / ((kRows + 2) * (kCols + 2));
-        int r = (i / (kCols + 2)) % (kRows + 2);
-        int cc = i % (kCols + 2);
-        int hh = h0 + r - 1, ww = w0 + cc - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * 2.f - 1.f;
-        xs[c][r][cc] = v;
-    }
-    __syncthreads();
+    const int tiles_w = (W + kCols - 1) / kCols, tiles_h = (H + kRows - 1) / kRows;
+    const int ntiles = tiles_w * tiles_h * B;
     const int cg = threadIdx.x & 15;
     const int tg = (threadIdx.x >> 4) & 3;
-    const int ps = threadIdx.x >> 6;          // pixel slice = output row within the CTA
+    const int ps = threadIdx.x >> 6;          // pixel slice = output row within the tile
     float acc[7][4];
     float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < 7; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-    const int hh = h0 + ps;
-    if (hh < H) {
-        const float* dyrow = dy + (((size_t)b * H + hh) * W + w0) * kCo + cg * 4;
-        const int ncols = min(kCols, W - w0);
-        for (int c = 0; c < ncols; ++c) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(dyrow + (size_t)c * kCo));
-            if (tg == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / (tiles_w * tiles_h);
+        const int rem = tile - b * tiles_w * tiles_h;
+        const int h0 = (rem / tiles_w) * kRows, w0 = (rem % tiles_w) * kCols;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
+            int c = i / ((kRows + 2) * (kCols + 2));
+            int r = (i / (kCols + 2)) % (kRows + 2);
+            int cc = i % (kCols + 2);
+            int hh = h0 + r - 1, ww = w0 + cc - 1;
+            float v = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * in_scale + in_shift;
+            xs[c][r][cc] = v;
+        }
+        __syncthreads();
+        const int hh = h0 + ps;
+        if (hh < H) {
+            const float* dyrow = dy + (((size_t)b * H + hh) * W + w0) * kCo + cg * 4;
+            const int ncols = min(kCols, W - w0);
+#pragma unroll 4
+            for (int c = 0; c < ncols; ++c) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(dyrow + (size_t)c * kCo));
+                if (tg == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
 #pragma unroll
-            for (int t = 0; t < 7; ++t) {
-                const int tap = tg * 7 + t;
-                if (tap < 27) {
-                    const int ci = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
-                    const float xv = xs[ci][ps + kh][c + kw];
-                    acc[t][0] += g.x * xv; acc[t][1] += g.y * xv; acc[t][2] += g.z * xv; acc[t][3] += g.w * xv;
+                for (int t = 0; t < 7; ++t) {
+                    const int tap = tg * 7 + t;
+                    if (tap < 27) {
+                        const int ci = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
+                        const float xv = xs[ci][ps + kh][c + kw];
+                        acc[t][0] += g.x * xv; acc[t][1] += g.y * xv; acc[t][2] += g.z * xv; acc[t][3] += g.w * xv;
+                    }
                 }
             }
         }
@@ -162,14 +172,16 @@ conv_first_dgrad_finish_kernel(const float* __restrict__ dpad, float* __restrict
 
 }  // namespace
 
-// y[B,H,W,64] = lrelu_slope(conv3x3(2x-1, w/sigma) + bias); x NCHW [B,3,H,W]; w = OIHW [64,3,3,3]; sigma [2] or NULL.
+// y[B,H,W,64] = lrelu_slope(conv3x3(in_scale*x+in_shift, w/sigma) + bias); x NCHW [B,3,H,W]; w = OIHW [64,3,3,3];
+// sigma [2] or NULL.  D's first layer uses in_scale=2, in_shift=-1 (the folded `x*2-1`).
 extern "C" int cb200_conv_first_fwd(const float* x, const float* w, const float* sigma, const float* bias, float* y,
-                                    int B, int H, int W, float slope, int round_out, void* stream) {
+                                    int B, int H, int W, float slope, int round_out, float in_scale, float in_shift,
+                                    void* stream) {
     CB200_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv_first_fwd: empty input");
     CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv_first_fwd: y must be 16-byte aligned");
     dim3 grid((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B);
     conv_first_fwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, sigma, bias, y, H, W, slope,
-                                                                                    round_out);
+                                                                                    round_out, in_scale, in_shift);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("conv_first_fwd");
     return CB200_OK;
@@ -177,10 +189,12 @@ extern "C" int cb200_conv_first_fwd(const float* x, const float* w, const float*
 
 // dw_hat[64,27] (OIHW order, gradient w.r.t. w/sigma) and db[64] are ACCUMULATED into (caller zeroes them).
 extern "C" int cb200_conv_first_wgrad(const float* x, const float* dy, float* dw_hat, float* db, int B, int H, int W,
-                                      void* stream) {
+                                      float in_scale, float in_shift, void* stream) {
     CB200_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv_first_wgrad: empty input");
-    dim3 grid((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B);
-    conv_first_wgrad_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dw_hat, db, H, W);
+    const long long ntiles = (long long)((W + kCols - 1) / kCols) * ((H + kRows - 1) / kRows) * B;
+    const int grid = (int)(ntiles < 4 * 148 ? ntiles : 4 * 148);
+    conv_first_wgrad_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dw_hat, db, B, H, W,
+                                                                                      in_scale, in_shift);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("conv_first_wgrad");
     return CB200_OK;

@@ -1,0 +1,293 @@
+// Generator-side elementwise / reduction kernels of G_SNDCGAN for sm_100a (HBM-bound SIMT):
+// train-mode BatchNorm (+ReLU) forward / backward on NHWC activations, the final tanh stage, and a
+// TF32 rounding pass.  The dense parts of the generator (Linear, 3x ConvTranspose2d(4,2,1),
+// ConvTranspose2d(3,1,1)) run on the tcgen05 tap-GEMM / wgrad kernels (tc_gemm.cu, tc_wgrad.cu).
+//
+// Reference: models/gan/sndcgan.py:24-48 (nn.BatchNorm2d in train mode: batch statistics, biased variance
+// for normalisation, running stats updated with momentum 0.1 and the unbiased variance; nn.ReLU; nn.Tanh;
+// `0.5 * y + 0.5`).  Under DDP the reference converts BN to SyncBatchNorm (train_gan.py:268): the two-phase
+// split here (partial sums -> finalize) lets the host all-reduce the [2, C] sums between the phases.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+
+// sums[0][c] += sum_m x[m,c];  sums[1][c] += sum_m x[m,c]^2     (x: [M, C] row-major)
+// threads: (256/cc) row lanes x cc columns, cc = min(C, 256)
+__global__ void __launch_bounds__(kT)
+bn_stats_kernel(const float* __restrict__ x, int M, int C, int cc, int rows_per_cta, float* __restrict__ sums) {
+    __shared__ float scratch[2 * 256];
+    const int tx = threadIdx.x % cc, ty = threadIdx.x / cc, lanes = kT / cc;
+    const int c = blockIdx.x * cc + tx;
+    const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+    float a[2] = {0.f, 0.f};
+    if (c < C)
+        for (int m = m0 + ty; m < m1; m += lanes) {
+            const float v = __ldg(x + (long long)m * C + c);
+            a[0] += v;
+            a[1] += v * v;
+        }
+    fold_row_lanes<2>(a, scratch, cc);
+    if (ty == 0 && c < C) {
+        atomicAdd(sums + c, a[0]);
+        atomicAdd(sums + C + c, a[1]);
+    }
+}
+
+// stats[0][c] = mean, stats[1][c] = rstd; running stats updated in place (momentum, unbiased variance)
+__global__ void __launch_bounds__(kT)
+bn_finalize_kernel(const float* __restrict__ sums, float count, int C, float eps, float momentum,
+                   float* __restrict__ stats, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * kT + threadIdx.x;
+    if (c >= C) return;
+    const float mean = sums[c] / count;
+    const float var = fmaxf(sums[C + c] / count - mean * mean, 0.f);
+    stats[c] = mean;
+    stats[C + c] = rsqrtf(var + eps);
+    if (running_mean) {
+        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+}
+
+// y = relu(gamma * (x - mean) * rstd + beta), optionally TF32-rounded.
+// remap_s > 0: x is [M, C*S] with feature index c*S + s (the reference's flattened (c,h,w) order, C = channels,
+// S = h*w) and y is NHWC [M, S, C]; statistics are per FEATURE (BatchNorm2d over a 1x1 map, sndcgan.py:42-45).
+__global__ void __launch_bounds__(kT)
+bn_apply_relu_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ y, long long total, int C, int remap_s,
+                     int round_out) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;      // output index
+    if (i >= total) return;
+    int f;            // statistics / affine index
+    long long src;    // input index
+    if (remap_s > 0) {
+        const int F = C;                          // here C = number of features = channels * S
+        const int ch = F / remap_s;
+        const long long m = i / F;
+        const int r = (int)(i - m * F);           // r = s * ch + c
+        const int s = r / ch, c = r - s * ch;
+        f = c * remap_s + s;
+        src = m * F + f;
+    } else {
+        f = (int)(i % C);
+        src = i;
+    }
+    float v = (x[src] - stats[f]) * stats[C + f] * gamma[f] + beta[f];
+    v = fmaxf(v, 0.f);
+    y[i] = round_out ? round_tf32(v) : v;
+}
+
+// sums[0][f] += sum dz, sums[1][f] += sum dz * xhat, with dz = dy * 1[y > 0]   (same indexing as above)
+__global__ void __launch_bounds__(kT)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                     const float* __restrict__ stats, int M, int C, int remap_s, int cc, int rows_per_cta,
+                     float* __restrict__ sums) {
+    __shared__ float scratch[2 * 256];
+    const int tx = threadIdx.x % cc, ty = threadIdx.x / cc, lanes = kT / cc;
+    const int j = blockIdx.x * cc + tx;          // column of the OUTPUT-side tensors (dy, y)
+    int f = j;
+    if (remap_s > 0 && j < C) {
+        const int ch = C / remap_s;
+        const int s = j / ch, c = j - s * ch;
+        f = c * remap_s + s;
+    }
+    float a[2] = {0.f, 0.f};
+    if (j < C) {
+        const float mean = stats[f], rstd = stats[C + f];
+        const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
+        for (int m = m0 + ty; m < m1; m += lanes) {
+            const float g = (__ldg(y + (long long)m * C + j) > 0.f) ? __ldg(dy + (long long)m * C + j) : 0.f;
+            const float xh = (__ldg(x + (long long)m * C + f) - mean) * rstd;
+            a[0] += g;
+            a[1] += g * xh;
+        }
+    }
+    fold_row_lanes<2>(a, scratch, cc);
+    if (ty == 0 && j < C) {
+        atomicAdd(sums + f, a[0]);
+        atomicAdd(sums + C + f, a[1]);
+    }
+}
+
+// dx = gamma * rstd * (dz - sum_dz / count - xhat * sum_dz_xhat / count)    (dx in the INPUT-side layout)
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                    const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ sums,
+                    float count, float* __restrict__ dx, long long total, int C, int remap_s, int round_out) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;      // output-side index
+    if (i >= total) return;
+    int f;
+    long long src;
+    if (remap_s > 0) {
+        const int ch = C / remap_s;
+        const long long m = i / C;
+        const int r = (int)(i - m * C);
+        const int s = r / ch, c = r - s * ch;
+        f = c * remap_s + s;
+        src = m * C + f;
+    } else {
+        f = (int)(i % C);
+        src = i;
+    }
+    const float rstd = stats[C + f];
+    const float xh = (x[src] - stats[f]) * rstd;
+    const float g = (y[i] > 0.f) ? dy[i] : 0.f;
+    const float inv = 1.f / count;
+    float v = gamma[f] * rstd * (g - sums[f] * inv - xh * sums[C + f] * inv);
+    dx[src] = round_out ? round_tf32(v) : v;
+}
+
+// out[n,c,h,w] = 0.5 * tanh(pre[n,h,w,c] + bias[c]) + 0.5     (pre: NHWC with `cpad` channels, c < 3)
+__global__ void __launch_bounds__(kT)
+g_final_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ bias, float* __restrict__ out, int HW,
+                   int cpad, long long total) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;   // NCHW index over B*3*HW
+    if (i >= total) return;
+    const int p = (int)(i % HW);
+    const int c = (int)((i / HW) % 3);
+    const long long b = i / (3LL * HW);
+    const float v = __ldg(pre + (b * HW + p) * cpad + c) + (bias ? __ldg(bias + c) : 0.f);
+    out[i] = 0.5f * tanhf(v) + 0.5f;
+}
+
+// dpre[n,c,h,w] = dout * 0.5 * (1 - t^2), t = 2*out - 1;  dbias[c] += sum dpre
+__global__ void __launch_bounds__(kT)
+g_final_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dpre,
+                   float* __restrict__ dbias, int HW, long long total) {
+    __shared__ float red[3 * 32];
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    float s[3] = {0.f, 0.f, 0.f};
+    if (i < total) {
+        const float t = 2.f * out[i] - 1.f;
+        const float g = dout[i] * 0.5f * (1.f - t * t);
+        dpre[i] = g;
+        const int c = (int)((i / HW) % 3);
+        s[0] = c == 0 ? g : 0.f; s[1] = c == 1 ? g : 0.f; s[2] = c == 2 ? g : 0.f;
+    }
+    block_sum<3>(s, red);
+    if (threadIdx.x == 0 && dbias) { atomicAdd(dbias + 0, s[0]); atomicAdd(dbias + 1, s[1]); atomicAdd(dbias + 2, s[2]); }
+}
+
+__global__ void __launch_bounds__(kT)
+round_tf32_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i < n) y[i] = round_tf32(x[i]);
+}
+
+int row_chunks(int M, int* rows_per_cta) {
+    int chunks = (M + 127) / 128;
+    if (chunks > 1024) chunks = 1024;
+    *rows_per_cta = (M + chunks - 1) / chunks;
+    return (M + *rows_per_cta - 1) / *rows_per_cta;
+}
+
+int col_lanes(int C) {          // columns per CTA: smallest power of two >= C, between 32 and 256
+    int cc = 256;
+    while (cc > 32 && cc / 2 >= C) cc /= 2;
+    return cc;
+}
+
+}  // namespace
+
+// sums[2,C] (zeroed here) <- per-channel sum and sum of squares of x[M,C].
+extern "C" int cb200_bn_stats(const float* x, int M, int C, float* sums, void* stream) {
+    CB200_CHECK_ARG(M > 0 && C > 0, "bn_stats: empty input");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+    if (e != cudaSuccess) { cb200_set_error("bn_stats: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    int rpc;
+    const int chunks = row_chunks(M, &rpc);
+    const int cc = col_lanes(C);
+    bn_stats_kernel<<<dim3((C + cc - 1) / cc, chunks), kT, 0, st>>>(x, M, C, cc, rpc, sums);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("bn_stats");
+    return CB200_OK;
+}
+
+// stats[2,C] <- {mean, rstd} from (possibly all-reduced) sums over `count` samples; running stats updated when given.
+extern "C" int cb200_bn_finalize(const float* sums, float count, int C, float eps, float momentum, float* stats,
+                                 float* running_mean, float* running_var, void* stream) {
+    CB200_CHECK_ARG(C > 0 && count > 0.f, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + kT - 1) / kT, kT, 0, static_cast<cudaStream_t>(stream)>>>(sums, count, C, eps, momentum, stats,
+                                                                                        running_mean, running_var);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("bn_finalize");
+    return CB200_OK;
+}
+
+extern "C" int cb200_bn_apply_relu(const float* x, const float* stats, const float* gamma, const float* beta, float* y,
+                                   int M, int C, int remap_s, int round_out, void* stream) {
+    CB200_CHECK_ARG(M > 0 && C > 0 && (remap_s == 0 || C % remap_s == 0), "bn_apply_relu: bad shape");
+    const long long total = (long long)M * C;
+    bn_apply_relu_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, stats, gamma, beta, y, total, C, remap_s, round_out);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("bn_apply_relu");
+    return CB200_OK;
+}
+
+// sums[2,C] (zeroed here) <- {sum dz, sum dz*xhat}
+extern "C" int cb200_bn_bwd_reduce(const float* dy, const float* y, const float* x, const float* stats, int M, int C,
+                                   int remap_s, float* sums, void* stream) {
+    CB200_CHECK_ARG(M > 0 && C > 0 && (remap_s == 0 || C % remap_s == 0), "bn_bwd_reduce: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+    if (e != cudaSuccess) { cb200_set_error("bn_bwd_reduce: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    int rpc;
+    const int chunks = row_chunks(M, &rpc);
+    const int cc = col_lanes(C);
+    bn_bwd_reduce_kernel<<<dim3((C + cc - 1) / cc, chunks), kT, 0, st>>>(dy, y, x, stats, M, C, remap_s, cc, rpc, sums);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("bn_bwd_reduce");
+    return CB200_OK;
+}
+
+extern "C" int cb200_bn_bwd_apply(const float* dy, const float* y, const float* x, const float* stats, const float* gamma,
+                                  const float* sums, float count, float* dx, int M, int C, int remap_s, int round_out,
+                                  void* stream) {
+    CB200_CHECK_ARG(M > 0 && C > 0 && count > 0.f, "bn_bwd_apply: bad shape");
+    const long long total = (long long)M * C;
+    bn_bwd_apply_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+        dy, y, x, stats, gamma, sums, count, dx, total, C, remap_s, round_out);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("bn_bwd_apply");
+    return CB200_OK;
+}
+
+extern "C" int cb200_g_final_fwd(const float* pre, const float* bias, float* out, int B, int H, int W, int cpad,
+                                 void* stream) {
+    CB200_CHECK_ARG(B > 0 && cpad >= 3, "g_final_fwd: bad shape");
+    const long long total = (long long)B * 3 * H * W;
+    g_final_fwd_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(pre, bias, out, H * W,
+                                                                                                       cpad, total);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("g_final_fwd");
+    return CB200_OK;
+}
+
+// dpre[B,3,H,W], dbias[3] (zeroed here) from dout and the saved output.
+extern "C" int cb200_g_final_bwd(const float* dout, const float* out, float* dpre, float* dbias, int B, int H, int W,
+                                 void* stream) {
+    CB200_CHECK_ARG(B > 0, "g_final_bwd: bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dbias) {
+        cudaError_t e = cudaMemsetAsync(dbias, 0, sizeof(float) * 3, st);
+        if (e != cudaSuccess) { cb200_set_error("g_final_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    const long long total = (long long)B * 3 * H * W;
+    g_final_bwd_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, st>>>(dout, out, dpre, dbias, H * W, total);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("g_final_bwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_round_tf32(const float* x, float* y, long long n, void* stream) {
+    CB200_CHECK_ARG(n > 0, "round_tf32: empty input");
+    round_tf32_kernel<<<(unsigned)((n + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("round_tf32");
+    return CB200_OK;
+}

@@ -19,10 +19,11 @@ namespace {
 
 constexpr int kD = 128;            // embedding width (d_project)
 constexpr int kWarps = 8;
-constexpr int kRowsPerWarp = 4;
-constexpr int kRowsPerCta = kWarps * kRowsPerWarp;   // 32
+constexpr int kRowsPerWarp = 2;
+constexpr int kRowsPerCta = kWarps * kRowsPerWarp;   // 16
 constexpr int kJT = 32;            // columns per tile = one per lane
 constexpr int kZStride = kD + 4;   // padded smem row (float4-aligned, conflict-free 128-bit reads)
+constexpr int kMaxSplits = 16;
 
 // ------------------------------------------------------------------------------------------ rownorm
 __global__ void __launch_bounds__(256)
@@ -60,14 +61,12 @@ rownorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, co
 }
 
 // ------------------------------------------------------------------------------------------ contrastive
-// mode 0: NT-Xent over R = 2N rows (all rows active);  mode 1: supcon-fake over R = 3N rows, active rows 2N..3N-1.
-struct RowSpec {
-    int gi;          // global row index
-    bool active;
-};
+// mode 0: NT-Xent over R = 2N rows (all rows are loss rows);  mode 1: supcon-fake over R = 3N rows, loss rows
+// 2N..3N-1.  Grid = (blocks of 16 rows, column splits): every CTA streams its slice of the columns through a
+// shared-memory tile (lane-owns-column dot products against the warp's rows) so that ~2 x #SM CTAs are
+// resident even though the problem has only 1-1.5 k rows.
 
 __device__ __forceinline__ void load_ztile(float (*zt)[kZStride], const float* __restrict__ z, int j0, int R) {
-    // kJT rows x 128 floats, cooperative float4 loads by the whole CTA
     for (int e = threadIdx.x; e < kJT * (kD / 4); e += kWarps * 32) {
         const int r = e / (kD / 4), c4 = e % (kD / 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -76,8 +75,9 @@ __device__ __forceinline__ void load_ztile(float (*zt)[kZStride], const float* _
     }
 }
 
-// s[r] = <z_i[r], z_j(lane)> for the warp's 4 rows
-__device__ __forceinline__ void dots4(const float (*zi)[kD], const float (*zt)[kZStride], int lane, float (&s)[kRowsPerWarp]) {
+// s[r] = <z_i[r], z_j(lane)> for the warp's rows
+__device__ __forceinline__ void dots_rows(const float (*zi)[kD], const float (*zt)[kZStride], int lane,
+                                          float (&s)[kRowsPerWarp]) {
 #pragma unroll
     for (int r = 0; r < kRowsPerWarp; ++r) s[r] = 0.f;
 #pragma unroll 8
@@ -86,18 +86,22 @@ __device__ __forceinline__ void dots4(const float (*zi)[kD], const float (*zt)[k
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {
             const float4 a = *reinterpret_cast<const float4*>(&zi[r][k4 * 4]);
-            s[r] += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            s[r] = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s[r]))));
         }
     }
 }
 
+// partial[(local_row * splits + split) * 3 + {0,1,2}] = running max, sum of exp, positive-logit sum
 __global__ void __launch_bounds__(kWarps * 32)
-contrastive_fwd_kernel(const float* __restrict__ z, int R, int N, int mode, float inv_tau, float* __restrict__ lse_out,
-                       float* __restrict__ row_loss) {
+contrastive_fwd_kernel(const float* __restrict__ z, int R, int N, int mode, float inv_tau, int cols_per_split,
+                       float* __restrict__ partial) {
     __shared__ __align__(16) float zt[kJT][kZStride];
     __shared__ __align__(16) float zi_all[kWarps][kRowsPerWarp][kD];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = (mode == 1 ? 2 * N : 0) + blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;
+    const int first = (mode == 1 ? 2 * N : 0);
+    const int row0 = first + blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;
+    const int splits = gridDim.y, split = blockIdx.y;
+    const int jbeg = split * cols_per_split, jend = min(R, jbeg + cols_per_split);
     float (*zi)[kD] = zi_all[warp];
     int gi[kRowsPerWarp];
 #pragma unroll
@@ -108,26 +112,25 @@ contrastive_fwd_kernel(const float* __restrict__ z, int R, int N, int mode, floa
     float m[kRowsPerWarp], l[kRowsPerWarp], pos[kRowsPerWarp];
 #pragma unroll
     for (int r = 0; r < kRowsPerWarp; ++r) { m[r] = -INFINITY; l[r] = 0.f; pos[r] = 0.f; }
-    for (int j0 = 0; j0 < R; j0 += kJT) {
+    for (int j0 = jbeg; j0 < jend; j0 += kJT) {
         __syncthreads();
-        load_ztile(zt, z, j0, R);
+        load_ztile(zt, z, j0, jend);
         __syncthreads();
         float s[kRowsPerWarp];
-        dots4(zi, zt, lane, s);
+        dots_rows(zi, zt, lane, s);
         const int j = j0 + lane;
+        const bool in = j < jend;
 #pragma unroll
         for (int r = 0; r < kRowsPerWarp; ++r) {
             float v = s[r] * inv_tau;
             if (j == gi[r]) v = -5e4f;
-            const bool in = j < R;
             if (mode == 0) {
                 const int pj = gi[r] < N ? gi[r] + N : gi[r] - N;
                 if (in && j == pj) pos[r] += v;
             } else {
                 if (in && j >= 2 * N && j != gi[r]) pos[r] += v;
             }
-            const float vm = in ? v : -INFINITY;
-            const float tile_max = warp_max(vm);
+            const float tile_max = warp_max(in ? v : -INFINITY);
             const float new_m = fmaxf(m[r], tile_max);
             float e = in ? __expf(v - new_m) : 0.f;
             e = warp_sum(e);
@@ -139,23 +142,42 @@ contrastive_fwd_kernel(const float* __restrict__ z, int R, int N, int mode, floa
     for (int r = 0; r < kRowsPerWarp; ++r) {
         const float p = warp_sum(pos[r]);
         if (lane == 0 && gi[r] < R) {
-            const float lse = m[r] + logf(l[r]);
-            const int local = gi[r] - (mode == 1 ? 2 * N : 0);
-            lse_out[local] = lse;
-            row_loss[local] = (mode == 0) ? -(p - lse) / (float)(2 * N) : -(p / (float)(N - 1) - lse) / (float)N;
+            float* dst = partial + ((long long)(gi[r] - first) * splits + split) * 3;
+            dst[0] = m[r]; dst[1] = l[r]; dst[2] = p;
         }
     }
 }
 
-// dZ[i] = gscale * inv_tau * sum_j (c_ij + c_ji) z_j,   c_ij = dL/dS_ij (see header comment of the file)
+// merge the column splits: lse[row], loss[0] (single CTA, fixed order => deterministic)
+__global__ void __launch_bounds__(256)
+contrastive_finalize_kernel(const float* __restrict__ partial, int rows, int splits, int N, int mode,
+                            float* __restrict__ lse_out, float* __restrict__ loss) {
+    __shared__ float red[32];
+    float a[1] = {0.f};
+    for (int row = threadIdx.x; row < rows; row += 256) {
+        const float* p = partial + (long long)row * splits * 3;
+        float M = -INFINITY;
+        for (int s = 0; s < splits; ++s) M = fmaxf(M, p[s * 3]);
+        float L = 0.f, pos = 0.f;
+        for (int s = 0; s < splits; ++s) { L += p[s * 3 + 1] * __expf(p[s * 3] - M); pos += p[s * 3 + 2]; }
+        const float lse = M + logf(L);
+        lse_out[row] = lse;
+        a[0] += (mode == 0) ? -(pos - lse) / (float)(2 * N) : -(pos / (float)(N - 1) - lse) / (float)N;
+    }
+    block_sum<1>(a, red);
+    if (threadIdx.x == 0) loss[0] = a[0];
+}
+
+// dZ[i] += gscale * inv_tau * sum_{j in split} (c_ij + c_ji) z_j,   c_ij = dL/dS_ij
 __global__ void __launch_bounds__(kWarps * 32)
-contrastive_bwd_kernel(const float* __restrict__ z, int R, int N, int mode, float inv_tau,
+contrastive_bwd_kernel(const float* __restrict__ z, int R, int N, int mode, float inv_tau, int cols_per_split,
                        const float* __restrict__ lse, const float* __restrict__ gscale, float* __restrict__ dz) {
     __shared__ __align__(16) float zt[kJT][kZStride];
     __shared__ __align__(16) float zi_all[kWarps][kRowsPerWarp][kD];
     __shared__ float coef_all[kWarps][kRowsPerWarp][kJT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kRowsPerCta + warp * kRowsPerWarp;     // all R rows receive gradient
+    const int jbeg = blockIdx.y * cols_per_split, jend = min(R, jbeg + cols_per_split);
     float (*zi)[kD] = zi_all[warp];
     float (*coef)[kJT] = coef_all[warp];
     const int first_active = (mode == 1) ? 2 * N : 0;
@@ -172,14 +194,14 @@ contrastive_bwd_kernel(const float* __restrict__ z, int R, int N, int mode, floa
     float acc[kRowsPerWarp][4];
 #pragma unroll
     for (int r = 0; r < kRowsPerWarp; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-    for (int j0 = 0; j0 < R; j0 += kJT) {
+    for (int j0 = jbeg; j0 < jend; j0 += kJT) {
         __syncthreads();
-        load_ztile(zt, z, j0, R);
+        load_ztile(zt, z, j0, jend);
         __syncthreads();
         float s[kRowsPerWarp];
-        dots4(zi, zt, lane, s);
+        dots_rows(zi, zt, lane, s);
         const int j = j0 + lane;
-        const bool jin = j < R;
+        const bool jin = j < jend;
         const bool j_active = jin && j >= first_active;
         const float lse_j = j_active ? __ldg(lse + j - first_active) : 0.f;
 #pragma unroll
@@ -219,19 +241,29 @@ contrastive_bwd_kernel(const float* __restrict__ z, int R, int N, int mode, floa
     const float g = __ldg(gscale) * inv_tau;
 #pragma unroll
     for (int r = 0; r < kRowsPerWarp; ++r) {
-        if (gi[r] < R)
-            *reinterpret_cast<float4*>(dz + (long long)gi[r] * kD + lane * 4) =
-                make_float4(acc[r][0] * g, acc[r][1] * g, acc[r][2] * g, acc[r][3] * g);
+        if (gi[r] < R) {
+            float* dst = dz + (long long)gi[r] * kD + lane * 4;
+            if (gridDim.y == 1) {
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0] * g, acc[r][1] * g, acc[r][2] * g, acc[r][3] * g);
+            } else {
+                atomicAdd(dst + 0, acc[r][0] * g); atomicAdd(dst + 1, acc[r][1] * g);
+                atomicAdd(dst + 2, acc[r][2] * g); atomicAdd(dst + 3, acc[r][3] * g);
+            }
+        }
     }
 }
 
-// out[0] = sum(v[0..n))   (single CTA, deterministic order)
-__global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
-    __shared__ float red[32];
-    float a[1] = {0.f};
-    for (int i = threadIdx.x; i < n; i += 256) a[0] += v[i];
-    block_sum<1>(a, red);
-    if (threadIdx.x == 0) out[0] = a[0];
+// pick the number of column splits so that ~2 CTAs per SM are in flight; columns per split multiple of 32
+static int pick_splits(int row_blocks, int R, int* cols_per_split) {
+    int splits = (2 * 148 + row_blocks - 1) / row_blocks;
+    const int max_by_cols = (R + 4 * kJT - 1) / (4 * kJT);      // at least 4 tiles of columns per CTA
+    if (splits > max_by_cols) splits = max_by_cols;
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    if (splits < 1) splits = 1;
+    int cps = (R + splits - 1) / splits;
+    cps = ((cps + kJT - 1) / kJT) * kJT;
+    *cols_per_split = cps;
+    return (R + cps - 1) / cps;
 }
 
 // ------------------------------------------------------------------------------------------ GAN losses
@@ -285,16 +317,19 @@ gan_g_loss_kernel(const float* __restrict__ d_gen, long long stride, int N, int 
 }
 
 // ------------------------------------------------------------------------------------------ column sums
-// out[n] (+)= sum_m x[m, n]   x: [M, N] with row stride ld
+// out[n] (+)= sum_m x[m, n]   x: [M, N] with row stride ld.  Threads: (256/cc) row lanes x cc columns.
 __global__ void __launch_bounds__(256)
-colsum_kernel(const float* __restrict__ x, long long ld, int M, int N, int rows_per_cta, float* __restrict__ out) {
-    const int n = blockIdx.x * 256 + threadIdx.x;
-    if (n >= N) return;
+colsum_kernel(const float* __restrict__ x, long long ld, int M, int N, int cc, int rows_per_cta, float* __restrict__ out) {
+    __shared__ float scratch[256];
+    const int tx = threadIdx.x % cc, ty = threadIdx.x / cc, lanes = 256 / cc;
+    const int n = blockIdx.x * cc + tx;
     const int m0 = blockIdx.y * rows_per_cta;
     const int m1 = min(M, m0 + rows_per_cta);
-    float a = 0.f;
-    for (int m = m0; m < m1; ++m) a += __ldg(x + (long long)m * ld + n);
-    atomicAdd(out + n, a);
+    float a[1] = {0.f};
+    if (n < N)
+        for (int m = m0 + ty; m < m1; m += lanes) a[0] += __ldg(x + (long long)m * ld + n);
+    fold_row_lanes<1>(a, scratch, cc);
+    if (ty == 0 && n < N) atomicAdd(out + n, a[0]);
 }
 
 // out = dy * (act > 0 ? 1 : slope)   (LeakyReLU backward from the saved OUTPUT activation; slope > 0)
@@ -347,20 +382,21 @@ extern "C" int cb200_rownorm_bwd(const float* dy, const float* y, const float* i
 }
 
 // z [R,128] L2-normalised rows; mode 0: NT-Xent (R = 2N); mode 1: supcon-fake (R = 3N, loss rows 2N..3N-1).
-// lse / row_loss: scratch of (mode ? N : 2N) floats; loss[0] <- the scalar loss.
+// lse: (mode ? N : 2N) floats (kept for the backward); scratch: 48 * (mode ? N : 2N) floats; loss[0] <- scalar.
 extern "C" int cb200_contrastive_fwd(const float* z, int N, int d, int mode, float temperature, float* lse,
-                                     float* row_loss, float* loss, void* stream) {
+                                     float* scratch, float* loss, void* stream) {
     CB200_CHECK_ARG(N > 0 && (mode == 0 || mode == 1), "contrastive_fwd: bad N/mode");
     CB200_CHECK_ARG(d == kD, "contrastive_fwd: embedding width %d != 128", d);
     CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(z) & 15) == 0, "contrastive_fwd: z must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int R = mode ? 3 * N : 2 * N;
     const int active = mode ? N : 2 * N;
-    contrastive_fwd_kernel<<<(active + kRowsPerCta - 1) / kRowsPerCta, kWarps * 32, 0, st>>>(z, R, N, mode,
-                                                                                             1.f / temperature, lse,
-                                                                                             row_loss);
+    const int row_blocks = (active + kRowsPerCta - 1) / kRowsPerCta;
+    int cps;
+    const int splits = pick_splits(row_blocks, R, &cps);
+    contrastive_fwd_kernel<<<dim3(row_blocks, splits), kWarps * 32, 0, st>>>(z, R, N, mode, 1.f / temperature, cps, scratch);
     CB200_COUNT_LAUNCH();
-    sum_kernel<<<1, 256, 0, st>>>(row_loss, active, loss);
+    contrastive_finalize_kernel<<<1, 256, 0, st>>>(scratch, active, splits, N, mode, lse, loss);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("contrastive_fwd");
     return CB200_OK;
@@ -371,9 +407,17 @@ extern "C" int cb200_contrastive_bwd(const float* z, int N, int d, int mode, flo
                                      const float* gscale, float* dz, void* stream) {
     CB200_CHECK_ARG(N > 0 && (mode == 0 || mode == 1), "contrastive_bwd: bad N/mode");
     CB200_CHECK_ARG(d == kD, "contrastive_bwd: embedding width %d != 128", d);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int R = mode ? 3 * N : 2 * N;
-    contrastive_bwd_kernel<<<(R + kRowsPerCta - 1) / kRowsPerCta, kWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        z, R, N, mode, 1.f / temperature, lse, gscale, dz);
+    const int row_blocks = (R + kRowsPerCta - 1) / kRowsPerCta;
+    int cps;
+    const int splits = pick_splits(row_blocks, R, &cps);
+    if (splits > 1) {
+        cudaError_t e = cudaMemsetAsync(dz, 0, sizeof(float) * (size_t)R * kD, st);
+        if (e != cudaSuccess) { cb200_set_error("contrastive_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    contrastive_bwd_kernel<<<dim3(row_blocks, splits), kWarps * 32, 0, st>>>(z, R, N, mode, 1.f / temperature, cps, lse,
+                                                                           gscale, dz);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("contrastive_bwd");
     return CB200_OK;
@@ -403,11 +447,13 @@ extern "C" int cb200_colsum(const float* x, long long ld, int M, int N, float* o
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, st);
     if (e != cudaSuccess) { cb200_set_error("colsum: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    int cc = 256;
+    while (cc > 32 && cc / 2 >= N) cc /= 2;                 // smallest power of two >= N, between 32 and 256
     int row_chunks = (M + 255) / 256;
     if (row_chunks > 1024) row_chunks = 1024;
     const int rows_per_cta = (M + row_chunks - 1) / row_chunks;
-    dim3 grid((N + 255) / 256, (M + rows_per_cta - 1) / rows_per_cta);
-    colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, rows_per_cta, out);
+    dim3 grid((N + cc - 1) / cc, (M + rows_per_cta - 1) / rows_per_cta);
+    colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, cc, rows_per_cta, out);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("colsum");
     return CB200_OK;

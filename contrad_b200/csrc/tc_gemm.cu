@@ -27,6 +27,7 @@
 #include "tc_ptx.cuh"
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -63,6 +64,61 @@ struct SmemLayout {
     static constexpr int kBarOffset = STAGES * kStageBytes;
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
+
+// Epilogue of one 128-row tile: thread = one output row; TMEM -> registers -> bias / activation -> global.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
+                                              uint32_t tmem_base, uint64_t* tmem_full_bar, int warp, int lane) {
+    const int q = warp & 3;
+    int r = q * 32 + lane;
+    bool valid = true;
+    long long orow = p.cls_off[cls];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        int rd = r % p.box[d];
+        r /= p.box[d];
+        int x = base[d] + rd;
+        valid = valid && (x < p.extent[d]);
+        orow += (long long)x * p.ostride[d];
+    }
+    float* orow_ptr = p.out + orow * p.ldo + n0;
+    const float* drow_ptr = p.dact ? p.dact + orow * p.ldo + n0 : nullptr;
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tc::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[j + e]);
+                if (p.bias) {
+                    float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+                    o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+                }
+                if (drow_ptr) {
+                    float4 a = __ldg(reinterpret_cast<const float4*>(drow_ptr + c0 + j));
+                    o[0] *= (a.x > 0.f) ? 1.f : p.slope;
+                    o[1] *= (a.y > 0.f) ? 1.f : p.slope;
+                    o[2] *= (a.z > 0.f) ? 1.f : p.slope;
+                    o[3] *= (a.w > 0.f) ? 1.f : p.slope;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = (o[e] > 0.f) ? o[e] : o[e] * p.slope;
+                }
+                if (p.round_out) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
+                }
+                *reinterpret_cast<float4*>(orow_ptr + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -151,61 +207,129 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;
-        int r = q * 32 + lane;
-        bool valid = true;
-        long long orow = p.cls_off[cls];
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            int rd = r % p.box[d];
-            r /= p.box[d];
-            int x = base[d] + rd;
-            valid = valid && (x < p.extent[d]);
-            orow += (long long)x * p.ostride[d];
-        }
-        float* orow_ptr = p.out + orow * p.ldo + n0;
-        const float* drow_ptr = p.dact ? p.dact + orow * p.ldo + n0 : nullptr;
-        tc::mbar_wait(tmem_full_bar, 0);
-        tc::fence_after_sync();
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-            tc::tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[j + e]);
-                    if (p.bias) {
-                        float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                        o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
-                    }
-                    if (drow_ptr) {
-                        float4 a = __ldg(reinterpret_cast<const float4*>(drow_ptr + c0 + j));
-                        o[0] *= (a.x > 0.f) ? 1.f : p.slope;
-                        o[1] *= (a.y > 0.f) ? 1.f : p.slope;
-                        o[2] *= (a.z > 0.f) ? 1.f : p.slope;
-                        o[3] *= (a.w > 0.f) ? 1.f : p.slope;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = (o[e] > 0.f) ? o[e] : o[e] * p.slope;
-                    }
-                    if (p.round_out) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
-                    }
-                    *reinterpret_cast<float4*>(orow_ptr + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
-        }
+        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane);
     }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 2) {
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem_base, BN);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster own two consecutive 128-row M tiles and issue ONE
+// tcgen05.mma with M = 256; each CTA stages its own A tile and HALF of the B tile (BN/2 weight rows), so the
+// shared-memory / L2 operand traffic per FLOP is halved with respect to the single-CTA kernel.  The pair
+// leader (cluster rank 0) owns the `full` barriers (they collect the TMA bytes of both CTAs) and issues the
+// MMAs; tcgen05.commit is multicast to the `empty` / `tmem_full` barriers of both CTAs.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct SmemLayout2 {
+    static constexpr int kBTileBytes = (BN / 2) * kBlockK * 4;
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
+    using L = SmemLayout2<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cls = blockIdx.z;
+    const int n0 = blockIdx.y * BN;
+    const int num_kb = p.ntaps * p.cblocks;
+
+    int base[4];
+    {
+        int t = blockIdx.x;           // grid.x is padded to an even count; surplus tiles fall outside `extent`
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            base[d] = (t % p.tiles[d]) * p.box[d];
+            t /= p.tiles[d];
+        }
+        if (t > 0) base[3] = p.extent[3] + p.box[3] * t;     // beyond the last tile: loads are OOB zeros, stores masked
+    }
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&p.tmap_a);
+        tc::prefetch_tmap(&p.tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(tmem_full_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc2(tmem_slot, BN);
+    tc::fence_before_sync();
+    tc::cluster_sync_all();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int t = kb / p.cblocks;
+                const int cb = kb - t * p.cblocks;
+                tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * L::kStageBytes;
+                uint8_t* sb = sa + kATileBytes;
+                const uint32_t bar = tc::map_to_cta(tc::smem_u32(&full_bar[stage]), 0);
+                if (leader) tc::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                const int* tp = p.tap[cls][t];
+                tc::tma2_load_5d(sa, &p.tmap_a, bar, cb * kBlockK + tp[0], base[0] + tp[1], base[1] + tp[2],
+                                 base[2] + tp[3], base[3] + tp[4]);
+                tc::tma2_load_2d(sb, &p.tmap_b, bar, kb * kBlockK, cls * p.b_rows_per_cls + n0 + (int)rank * (BN / 2));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        constexpr uint32_t idesc = tc::idesc_tf32(256, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            tc::mbar_wait(&full_bar[stage], phase);
+            tc::fence_after_sync();
+            if (tc::elect_one()) {
+                const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
+                const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / 8; ++k) {
+                    const uint64_t adesc = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                    tc::mma2_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                }
+                tc::mma2_commit_multicast(&empty_bar[stage]);
+                if (kb == num_kb - 1) tc::mma2_commit_multicast(tmem_full_bar);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane);
+    }
+    tc::fence_before_sync();
+    tc::cluster_sync_all();
+    if (warp == 2) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc2(tmem_base, BN);
     }
 }
 
@@ -256,7 +380,6 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, 
     return CB200_OK;
 }
 
-int ilog2_floor(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // split 128 output rows over (w, h, b): w fastest
@@ -294,10 +417,60 @@ int launch(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaSt
     return CB200_OK;
 }
 
+template <int BN, int STAGES>
+int launch2(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
+    using L = SmemLayout2<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tap_gemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             L::kTotal);
+        if (e != cudaSuccess) {
+            cb200_set_error("%s: cudaFuncSetAttribute(smem=%d): %s", name, L::kTotal, cudaGetErrorString(e));
+            return (int)e;
+        }
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((m_tiles + 1) & ~1, n_tiles, classes);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm2_kernel<BN, STAGES>, p);
+    CB200_COUNT_LAUNCH();
+    if (e != cudaSuccess) {
+        cb200_set_error("%s: cluster launch failed: %s", name, cudaGetErrorString(e));
+        return (int)e;
+    }
+    CB200_CHECK_LAUNCH(name);
+    return CB200_OK;
+}
+
+// 0 = single-CTA tiles only, 1 = CTA pairs where the shape allows (default); env CB200_TAPGEMM_PAIR overrides.
+int pair_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CB200_TAPGEMM_PAIR");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
 int dispatch(const TapGemmParams& p, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
+    if (pair_mode() && m_tiles >= 296) {
+        if (N % 256 == 0) return launch2<256, 4>(p, m_tiles, N / 256, classes, st, name);     // 32 KB / stage / CTA
+        if (N % 128 == 0) return launch2<128, 4>(p, m_tiles, N / 128, classes, st, name);     // 24 KB / stage / CTA
+    }
     if (N % 128 == 0) return launch<128, 3>(p, m_tiles, N / 128, classes, st, name);
-    if (N % 64 == 0) return launch<64, 6>(p, m_tiles, N / 64, classes, st, name);
-    if (N % 32 == 0) return launch<32, 6>(p, m_tiles, N / 32, classes, st, name);
+    if (N % 64 == 0) return launch<64, 4>(p, m_tiles, N / 64, classes, st, name);     // 96 KB -> 2 CTAs / SM
+    if (N % 32 == 0) return launch<32, 4>(p, m_tiles, N / 32, classes, st, name);     // 80 KB -> 2 CTAs / SM
     cb200_set_error("%s: N=%d must be a multiple of 32", name, N);
     return CB200_ERR_ARG;
 }

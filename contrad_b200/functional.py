@@ -53,24 +53,24 @@ class SNPackFn(Function):
     def forward(ctx, holder, training, *weights):
         specs = holder["specs"]
         dev = weights[0].device
-        sig, outs, side = [], [], {"dgrad": {}, "sigma": {}}
-        saved_uv = []
+        weights = [_c(w) for w in weights]
+        side = {"dgrad": {}, "sigma": {}}
+        sig_all = torch.empty(len(specs), 2, device=dev, dtype=torch.float32)
+        sig = [sig_all[i] for i in range(len(specs))]
+        K.sn_power_iter_batched([(w, s.module.weight_u, s.module.weight_v, sg) for s, w, sg in zip(specs, weights, sig)],
+                                training=training)
+        saved_uv = [(s.module.weight_u.clone(), s.module.weight_v.clone()) for s in specs]
         head1 = [s for s in specs if s.kind == "head1"]
+        outs, jobs = [], []
         wcat = wcat_t = None
-        for s, w in zip(specs, weights):
-            m = s.module
-            w = _c(w)
-            sigma = torch.empty(2, device=dev, dtype=torch.float32)
-            K.sn_power_iter(w, m.weight_u, m.weight_v, sigma, training=training)
-            sig.append(sigma)
-            saved_uv.append((m.weight_u.clone(), m.weight_v.clone()))
+        for s, w, sigma in zip(specs, weights, sig):
             side["sigma"][s.name] = sigma
             cout = w.shape[0]
             if s.kind == "conv_first":
                 fwd = torch.empty(cout, 27, device=dev)
-                K.sn_pack_weights(w.view(cout, 27, 1, 1), sigma, fwd=fwd, ld_fwd=27, round_out=False)
                 dg = torch.zeros(32, 9 * cout, device=dev)
-                K.sn_pack_weights(w, sigma, dgrad=dg, dgrad_mode=1, round_out=True)
+                jobs.append(dict(w4=w.view(cout, 27, 1, 1), sigma=sigma, fwd=fwd, ld_fwd=27, round_out=False))
+                jobs.append(dict(w4=w, sigma=sigma, dgrad=dg, dgrad_mode=1, round_out=True))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
             elif s.kind == "conv":
@@ -78,10 +78,10 @@ class SNPackFn(Function):
                 fwd = torch.empty(cout, s.ks * s.ks * cin, device=dev)
                 if s.stride == 1:
                     dg = torch.empty(cin, s.ks * s.ks * cout, device=dev)
-                    K.sn_pack_weights(w, sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=1)
+                    jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=1))
                 else:
                     dg = torch.empty(4 * cin, 4 * cout, device=dev)
-                    K.sn_pack_weights(w, sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=2)
+                    jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=2))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
             elif s.kind == "head1":
@@ -91,20 +91,22 @@ class SNPackFn(Function):
                     wcat = torch.empty(len(head1) * cout, nfeat, device=dev)
                     wcat_t = torch.empty(nfeat, len(head1) * cout, device=dev)
                 idx = head1.index(s)
-                K.sn_pack_weights(w.view(cout, c_last, sh, sw), sigma, fwd=wcat[idx * cout:], ld_fwd=nfeat,
-                                  dgrad=wcat_t, dgrad_mode=3, ldt=wcat_t.shape[1], col0=idx * cout)
+                jobs.append(dict(w4=w.view(cout, c_last, sh, sw), sigma=sigma, fwd=wcat[idx * cout:], ld_fwd=nfeat,
+                                 dgrad=wcat_t, dgrad_mode=3, ldt=wcat_t.shape[1], col0=idx * cout))
                 if idx == len(head1) - 1:
                     outs.append(wcat)
                     side["dgrad"]["wcat"] = wcat_t
-            else:   # head2: [cout, hidden]; the 1-output `linear.l2` is padded to 32 rows / 128 for wgrad
+            else:   # head2: [cout, hidden]; the 1-output `linear.l2` is padded to 32 rows
                 hid = w.shape[1]
                 rows = cout if cout % 32 == 0 else 32
                 fwd = torch.zeros(rows, hid, device=dev) if rows != cout else torch.empty(rows, hid, device=dev)
                 dg = torch.zeros(hid, rows, device=dev) if rows != cout else torch.empty(hid, rows, device=dev)
-                K.sn_pack_weights(w.view(cout, hid, 1, 1), sigma, fwd=fwd, ld_fwd=hid, dgrad=dg, dgrad_mode=3,
-                                  ldt=rows, col0=0)
+                jobs.append(dict(w4=w.view(cout, hid, 1, 1), sigma=sigma, fwd=fwd, ld_fwd=hid, dgrad=dg, dgrad_mode=3,
+                                 ldt=rows, col0=0))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
+        for i in range(0, len(jobs), 16):
+            K.sn_pack_batched(jobs[i:i + 16])
         holder["side"] = side
         ctx.holder = holder
         ctx.saved_uv = saved_uv
@@ -116,38 +118,38 @@ class SNPackFn(Function):
     def backward(ctx, *dpacks):
         specs = ctx.holder["specs"]
         weights = ctx.saved_tensors
-        grads = []
+        grads = [None] * len(specs)
         head1 = [s for s in specs if s.kind == "head1"]
+        head2 = [s for s in specs if s.kind == "head2"]
         n_conv = sum(1 for s in specs if s.kind in ("conv_first", "conv"))
+        jobs = []
         for li, (s, w) in enumerate(zip(specs, weights)):
             if not ctx.needs_input_grad[2 + li]:
-                grads.append(None)
                 continue
             u, v = ctx.saved_uv[li]
-            sigma = ctx.sig[li]
             cout = w.shape[0]
-            dw = torch.empty_like(w)
             if s.kind == "conv_first":
-                g = dpacks[li]
-                grads.append(None if g is None else K.sn_weight_bwd(_c(g), 27, w.view(cout, 27, 1, 1), u, v, sigma, dw))
+                g, w4 = dpacks[li], w.view(cout, 27, 1, 1)
             elif s.kind == "conv":
-                g = dpacks[li]
-                grads.append(None if g is None else K.sn_weight_bwd(_c(g), g.shape[1], w, u, v, sigma, dw))
+                g, w4 = dpacks[li], w
             elif s.kind == "head1":
                 g = dpacks[n_conv]
-                if g is None:
-                    grads.append(None)
-                    continue
-                g = _c(g)
-                idx = head1.index(s)
                 c_last, sh, sw = ctx.holder["feat_chw"]
-                grads.append(K.sn_weight_bwd(g[idx * cout:(idx + 1) * cout], g.shape[1], w.view(cout, c_last, sh, sw),
-                                             u, v, sigma, dw))
+                w4 = w.view(cout, c_last, sh, sw)
+                if g is not None:
+                    idx = head1.index(s)
+                    g = _c(g)[idx * cout:(idx + 1) * cout]
             else:
-                pos = n_conv + 1 + [x for x in specs if x.kind == "head2"].index(s)
-                g = dpacks[pos]
-                grads.append(None if g is None else K.sn_weight_bwd(_c(g), g.shape[1], w.view(cout, w.shape[1], 1, 1),
-                                                                    u, v, sigma, dw))
+                g, w4 = dpacks[n_conv + 1 + head2.index(s)], w.view(cout, w.shape[1], 1, 1)
+            if g is None:
+                continue
+            g = g if g.stride(-1) == 1 and (g.dim() < 2 or g.stride(0) >= g.shape[1]) else _c(g)
+            dw = torch.empty_like(w)
+            grads[li] = dw
+            jobs.append(dict(dw_hat_packed=g, ld_fwd=g.stride(0) if g.dim() == 2 else g.shape[-1], w4=w4, u=u, v=v,
+                             sigma=ctx.sig[li], dw=dw))
+        for i in range(0, len(jobs), 16):
+            K.sn_weight_bwd_batched(jobs[i:i + 16])
         return (None, None) + tuple(grads)
 
 
@@ -213,6 +215,127 @@ class SNDCGANBackboneFn(Function):
         for i in range(L):
             out += [grads_w[i], grads_b[i]]
         return tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# generator  (models/gan/sndcgan.py:13-52)
+# ------------------------------------------------------------------------------------------------
+def _bn_forward(K_, x2d, bn_state, gamma, beta, remap_s, training, sync):
+    """Train-mode BN(+ReLU): returns (y, stats, count).  bn_state = (running_mean, running_var) or None."""
+    M = x2d.shape[0]
+    if training:
+        sums = K.bn_stats(x2d)
+        count = float(M)
+        if sync:
+            import torch.distributed as dist
+            dist.all_reduce(sums)
+            count *= dist.get_world_size()
+        rm, rv = bn_state if bn_state is not None else (None, None)
+        stats = K.bn_finalize(sums, count, rm, rv)
+    else:
+        rm, rv = bn_state
+        stats = torch.stack([rm, torch.rsqrt(rv + 1e-5)])
+        count = float(M)
+    return K.bn_apply_relu(x2d, stats, gamma, beta, remap_s=remap_s), stats, count
+
+
+def _bn_backward(dy2d, y2d, x2d, stats, gamma, count, remap_s, sync):
+    """Returns (dx, dgamma, dbeta); under SyncBN the sums are all-reduced for dx, the affine grads stay local
+    (DDP averages them afterwards, as torch's SyncBatchNorm does)."""
+    sums = K.bn_bwd_reduce(dy2d, y2d, x2d, stats, remap_s=remap_s)
+    dbeta, dgamma = sums[0].clone(), sums[1].clone()
+    if sync:
+        import torch.distributed as dist
+        dist.all_reduce(sums)
+    dx = K.bn_bwd_apply(dy2d, y2d, x2d, stats, gamma, sums, count, remap_s=remap_s)
+    return dx, dgamma, dbeta
+
+
+class GSNDCGANFn(Function):
+    """z [N,nz] -> images [N,3,8*s_h,8*s_w] in [0,1].
+
+    Linear and the four ConvTranspose2d layers run on the tcgen05 tap-GEMM kernels (a transposed convolution
+    is the data-gradient of the convolution with the same weight tensor); BatchNorm+ReLU, tanh are HBM-bound
+    SIMT kernels; activations are NHWC.  args: z, linear.{weight,bias}, then per block (convT.weight,
+    convT.bias) interleaved with (bn.weight, bn.bias): see G_SNDCGAN.forward."""
+
+    @staticmethod
+    def forward(ctx, holder, z, w_lin, b_lin, g0, be0, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, g3, be3, w4, b4):
+        training, sync = holder["training"], holder["sync"]
+        bn_states = holder["bn_states"]           # [(running_mean, running_var)] * 4
+        sh, sw = holder["s_hb"], holder["s_wb"]
+        dev = z.device
+        N = z.shape[0]
+        convs = [_c(w1), _c(w2), _c(w3)]
+        w4 = _c(w4)
+        w_lin = _c(w_lin)
+        # ---- packs (TF32-rounded): linear as-is; convT weights as OIHW of the underlying conv
+        wl = torch.empty_like(w_lin)
+        jobs = [dict(w4=w_lin.view(w_lin.shape[0], w_lin.shape[1], 1, 1), fwd=wl, ld_fwd=w_lin.shape[1])]
+        tpacks, fpacks = [], []
+        for w in convs:
+            o, i = w.shape[0], w.shape[1]
+            fp = torch.empty(o, 16 * i, device=dev)
+            tp = torch.empty(4 * i, 4 * o, device=dev)
+            jobs.append(dict(w4=w, fwd=fp, ld_fwd=16 * i, dgrad=tp, dgrad_mode=2))
+            tpacks.append(tp); fpacks.append(fp)
+        t4 = torch.zeros(32, 9 * w4.shape[0], device=dev)
+        jobs.append(dict(w4=w4, dgrad=t4, dgrad_mode=1))
+        K.sn_pack_batched(jobs)
+        zr = K.round_tf32_(z)
+        h0 = K.gemm_nt(zr, wl, b_lin)
+        a, st0, cnt0 = _bn_forward(K, h0, bn_states[0], g0, be0, sh * sw, training, sync)
+        xs, acts, stats, counts = [h0], [a], [st0], [cnt0]
+        hw = (sh, sw)
+        for li, (w, b, g, be) in enumerate(((convs[0], b1, g1, be1), (convs[1], b2, g2, be2), (convs[2], b3, g3, be3))):
+            o, i = w.shape[0], w.shape[1]
+            x_in = acts[-1].view(N, hw[0], hw[1], o)
+            hw = (hw[0] * 2, hw[1] * 2)
+            x = K.conv2d_nhwc_dgrad(x_in, tpacks[li], (N, hw[0], hw[1], i), 4, 2, bias_out=b, slope=1.0)
+            y, st, cnt = _bn_forward(K, x.view(-1, i), bn_states[li + 1], g, be, 0, training, sync)
+            xs.append(x); acts.append(y); stats.append(st); counts.append(cnt)
+        c_last = convs[2].shape[1]
+        pre = K.conv2d_nhwc_dgrad(acts[-1].view(N, hw[0], hw[1], c_last), t4, (N, hw[0], hw[1], 32), 3, 1)
+        out = K.g_final_fwd(pre, b4)
+        ctx.meta = (sh, sw, sync, counts, [tuple(w.shape) for w in convs])
+        ctx.save_for_backward(zr, w4, g0, g1, g2, g3, out, *xs, *acts, *stats, *fpacks)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        sh, sw, sync, counts, wshapes = ctx.meta
+        sv = ctx.saved_tensors
+        zr, w4, gammas, out = sv[0], sv[1], sv[2:6], sv[6]
+        xs, acts, stats, fpacks = sv[7:11], sv[11:15], sv[15:19], sv[19:22]
+        N = zr.shape[0]
+        grads = [None] * 20
+        dpre, db4 = K.g_final_bwd(dout, out)
+        H, W = out.shape[2], out.shape[3]
+        c_last = wshapes[2][1]
+        a3 = acts[3].view(N, H, W, c_last)
+        dw4, _ = K.conv_first_wgrad(dpre, a3, in_scale=1.0, in_shift=0.0)
+        grads[18], grads[19] = dw4.view_as(w4), db4
+        da = K.conv_first_fwd(dpre, w4, None, None, slope=1.0, round_out=False, in_scale=1.0, in_shift=0.0)
+        hw = (H, W)
+        for li in (2, 1, 0):
+            o, i = wshapes[li][0], wshapes[li][1]
+            dx, dgam, dbet = _bn_backward(da.view(-1, i), acts[li + 1], xs[li + 1].view(-1, i), stats[li + 1],
+                                          gammas[li + 1], counts[li + 1], 0, sync)
+            base = 6 + 4 * li                       # positions of (w, b, gamma, beta) of block li in forward's args
+            grads[base + 2], grads[base + 3] = dgam, dbet
+            dx4 = dx.view(N, hw[0], hw[1], i)
+            a_in = acts[li].view(N, hw[0] // 2, hw[1] // 2, o)
+            dwp = K.conv2d_nhwc_wgrad(dx4, a_in, 4, 2)                        # [o, 16*i] forward-pack layout
+            dw = torch.empty(o, i, 4, 4, device=dx.device)
+            K.sn_weight_bwd(dwp, dwp.shape[1], dw, None, None, None, dw)
+            grads[base], grads[base + 1] = dw, K.colsum(dx)
+            da = K.conv2d_nhwc_fwd(dx4, fpacks[li], None, 4, 2, slope=1.0, round_out=False)
+            hw = (hw[0] // 2, hw[1] // 2)
+        dh0, dgam, dbet = _bn_backward(da.view(N, -1), acts[0], xs[0], stats[0], gammas[0], counts[0], sh * sw, sync)
+        grads[4], grads[5] = dgam, dbet
+        grads[2] = K.gemm_tn_wgrad(dh0, zr)
+        grads[3] = K.colsum(dh0)
+        return tuple(grads)
 
 
 # ------------------------------------------------------------------------------------------------

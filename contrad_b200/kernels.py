@@ -1,5 +1,7 @@
 """Raw (non-autograd) Python bindings of the C ABI: shape checks, output allocation, stream plumbing.
 The autograd Functions in ``contrad_b200.functional`` are built on these."""
+import ctypes
+
 import torch
 
 from . import _capi
@@ -158,24 +160,91 @@ def sn_weight_bwd(dw_hat_packed, ld_fwd, w4, u, v, sigma, dw_out, accumulate=Fal
     return dw_out
 
 
+class _SnLayer(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p), ("sigma", ctypes.c_void_p),
+                ("t", ctypes.c_void_p), ("s", ctypes.c_void_p), ("cout", ctypes.c_int), ("f", ctypes.c_int)]
+
+
+class _SnPackJob(ctypes.Structure):
+    _fields_ = [("w", ctypes.c_void_p), ("sigma", ctypes.c_void_p), ("fwd", ctypes.c_void_p), ("dgrad", ctypes.c_void_p),
+                ("ld_fwd", ctypes.c_longlong), ("ldt", ctypes.c_longlong), ("cout", ctypes.c_int), ("cin", ctypes.c_int),
+                ("kh", ctypes.c_int), ("kw", ctypes.c_int), ("dgrad_mode", ctypes.c_int), ("col0", ctypes.c_int),
+                ("round_out", ctypes.c_int)]
+
+
+class _SnBwdJob(ctypes.Structure):
+    _fields_ = [("dw_hat_packed", ctypes.c_void_p), ("w", ctypes.c_void_p), ("u", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("sigma", ctypes.c_void_p), ("acc", ctypes.c_void_p), ("dw", ctypes.c_void_p),
+                ("ld_fwd", ctypes.c_longlong), ("cout", ctypes.c_int), ("cin", ctypes.c_int), ("kh", ctypes.c_int),
+                ("kw", ctypes.c_int)]
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def sn_power_iter_batched(layers, training=True, eps=1e-12):
+    """layers: list of (w, u, v, sigma[2]).  One launch per phase for all of them (u, v, sigma updated in place)."""
+    dev = layers[0][0].device
+    fs = [w.numel() // w.shape[0] for w, _, _, _ in layers]
+    couts = [w.shape[0] for w, _, _, _ in layers]
+    pad4 = lambda n: (n + 3) // 4 * 4                      # keep every layer's scratch 16-byte aligned (float4 loads)
+    t_all = torch.zeros(sum(pad4(f) for f in fs), device=dev, dtype=torch.float32) if training else torch.empty(1, device=dev)
+    s_all = torch.empty(sum(couts), device=dev, dtype=torch.float32)
+    arr = (_SnLayer * len(layers))()
+    to, so = 0, 0
+    for i, (w, u, v, sigma) in enumerate(layers):
+        assert w.is_cuda and w.is_contiguous()
+        arr[i] = _SnLayer(w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
+                          t_all.data_ptr() + 4 * to if training else 0, s_all.data_ptr() + 4 * so, couts[i], fs[i])
+        to += pad4(fs[i])
+        so += couts[i]
+    _call("sn_power_iter", 0, 0, lib().cb200_sn_power_iter_batched, arr, i32(len(layers)), f32(eps),
+          i32(1 if training else 0), stream_ptr())
+
+
+def sn_pack_batched(jobs):
+    """jobs: list of dicts(w4, sigma, fwd, ld_fwd, dgrad, dgrad_mode, ldt, col0, round_out)."""
+    arr = (_SnPackJob * len(jobs))()
+    for i, j in enumerate(jobs):
+        cout, cin, kh, kw = j["w4"].shape
+        arr[i] = _SnPackJob(j["w4"].data_ptr(), _p(j.get("sigma")), _p(j.get("fwd")), _p(j.get("dgrad")),
+                            int(j.get("ld_fwd", 0)), int(j.get("ldt", 0)), cout, cin, kh, kw, int(j.get("dgrad_mode", 0)),
+                            int(j.get("col0", 0)), 1 if j.get("round_out", True) else 0)
+    _call("sn_pack_weights", 0, 0, lib().cb200_sn_pack_batched, arr, i32(len(jobs)), stream_ptr())
+
+
+def sn_weight_bwd_batched(jobs):
+    """jobs: list of dicts(dw_hat_packed, ld_fwd, w4, u, v, sigma, dw)."""
+    dev = jobs[0]["w4"].device
+    acc = torch.zeros(len(jobs), device=dev, dtype=torch.float32)
+    arr = (_SnBwdJob * len(jobs))()
+    for i, j in enumerate(jobs):
+        cout, cin, kh, kw = j["w4"].shape
+        arr[i] = _SnBwdJob(j["dw_hat_packed"].data_ptr(), j["w4"].data_ptr(), j["u"].data_ptr(), j["v"].data_ptr(),
+                           j["sigma"].data_ptr(), acc.data_ptr() + 4 * i, j["dw"].data_ptr(), int(j["ld_fwd"]), cout, cin,
+                           kh, kw)
+    _call("sn_weight_bwd", 0, 0, lib().cb200_sn_weight_bwd_batched, arr, i32(len(jobs)), stream_ptr())
+
+
 # ------------------------------------------------------------------ first conv layer
-def conv_first_fwd(x, w, sigma, bias, slope=0.1, round_out=True):
+def conv_first_fwd(x, w, sigma, bias, slope=0.1, round_out=True, in_scale=2.0, in_shift=-1.0):
     x = _f32c(x, "x")
     B, C, H, W = x.shape
     assert C == 3 and w.shape == (64, 3, 3, 3) and w.is_contiguous()
     y = torch.empty(B, H, W, 64, device=x.device, dtype=torch.float32)
     _call("conv_first_fwd", 0, 0, lib().cb200_conv_first_fwd, ptr(x), ptr(w), ptr(sigma), ptr(bias), ptr(y), i32(B), i32(H), i32(W),
-                                     f32(slope), i32(1 if round_out else 0), stream_ptr())
+                                     f32(slope), i32(1 if round_out else 0), f32(in_scale), f32(in_shift), stream_ptr())
     return y
 
 
-def conv_first_wgrad(x, dy):
+def conv_first_wgrad(x, dy, in_scale=2.0, in_shift=-1.0):
     x = _f32c(x, "x")
     dy = _f32c(dy, "dy")
     B, C, H, W = x.shape
     dw = torch.zeros(64, 27, device=x.device, dtype=torch.float32)
     db = torch.zeros(64, device=x.device, dtype=torch.float32)
-    _call("conv_first_wgrad", 0, 0, lib().cb200_conv_first_wgrad, ptr(x), ptr(dy), ptr(dw), ptr(db), i32(B), i32(H), i32(W), stream_ptr())
+    _call("conv_first_wgrad", 0, 0, lib().cb200_conv_first_wgrad, ptr(x), ptr(dy), ptr(dw), ptr(db), i32(B), i32(H), i32(W), f32(in_scale), f32(in_shift), stream_ptr())
     return dw, db
 
 
@@ -219,7 +288,7 @@ def contrastive_fwd(z, n, mode, temperature):
     active = n if mode else 2 * n
     assert z.shape == ((3 if mode else 2) * n, 128), z.shape
     lse = torch.empty(active, device=z.device, dtype=torch.float32)
-    row_loss = torch.empty(active, device=z.device, dtype=torch.float32)
+    row_loss = torch.empty(48 * active, device=z.device, dtype=torch.float32)      # column-split partials
     loss = torch.empty(1, device=z.device, dtype=torch.float32)
     _call("contrastive_fwd", 0, 0, lib().cb200_contrastive_fwd, ptr(z), i32(n), i32(z.shape[1]), i32(mode), f32(temperature), ptr(lse),
                                       ptr(row_loss), ptr(loss), stream_ptr())
@@ -272,6 +341,72 @@ def colsum(x2d):
     out = torch.empty(N, device=x2d.device, dtype=torch.float32)
     _call("colsum", 0, 0, lib().cb200_colsum, ptr(x2d), i64(x2d.stride(0)), i32(M), i32(N), ptr(out), stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------ generator-side kernels
+def bn_stats(x2d):
+    M, C = x2d.shape
+    sums = torch.empty(2, C, device=x2d.device, dtype=torch.float32)
+    _call("bn_stats", 0, 8 * x2d.numel(), lib().cb200_bn_stats, ptr(x2d), i32(M), i32(C), ptr(sums), stream_ptr())
+    return sums
+
+
+def bn_finalize(sums, count, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    C = sums.shape[1]
+    stats = torch.empty(2, C, device=sums.device, dtype=torch.float32)
+    _call("bn_finalize", 0, 0, lib().cb200_bn_finalize, ptr(sums), f32(count), i32(C), f32(eps), f32(momentum), ptr(stats),
+          ptr(running_mean), ptr(running_var), stream_ptr())
+    return stats
+
+
+def bn_apply_relu(x2d, stats, gamma, beta, remap_s=0, round_out=True):
+    M, C = x2d.shape
+    y = torch.empty(M, C, device=x2d.device, dtype=torch.float32)
+    _call("bn_apply_relu", 0, 8 * x2d.numel(), lib().cb200_bn_apply_relu, ptr(x2d), ptr(stats), ptr(gamma), ptr(beta), ptr(y),
+          i32(M), i32(C), i32(remap_s), i32(1 if round_out else 0), stream_ptr())
+    return y
+
+
+def bn_bwd_reduce(dy2d, y2d, x2d, stats, remap_s=0):
+    M, C = x2d.shape
+    sums = torch.empty(2, C, device=x2d.device, dtype=torch.float32)
+    _call("bn_bwd_reduce", 0, 12 * x2d.numel(), lib().cb200_bn_bwd_reduce, ptr(dy2d), ptr(y2d), ptr(x2d), ptr(stats), i32(M),
+          i32(C), i32(remap_s), ptr(sums), stream_ptr())
+    return sums
+
+
+def bn_bwd_apply(dy2d, y2d, x2d, stats, gamma, sums, count, remap_s=0, round_out=True):
+    M, C = x2d.shape
+    dx = torch.empty(M, C, device=x2d.device, dtype=torch.float32)
+    _call("bn_bwd_apply", 0, 16 * x2d.numel(), lib().cb200_bn_bwd_apply, ptr(dy2d), ptr(y2d), ptr(x2d), ptr(stats), ptr(gamma),
+          ptr(sums), f32(count), ptr(dx), i32(M), i32(C), i32(remap_s), i32(1 if round_out else 0), stream_ptr())
+    return dx
+
+
+def g_final_fwd(pre_nhwc, bias):
+    B, H, W, cpad = pre_nhwc.shape
+    out = torch.empty(B, 3, H, W, device=pre_nhwc.device, dtype=torch.float32)
+    _call("g_final_fwd", 0, 0, lib().cb200_g_final_fwd, ptr(pre_nhwc), ptr(bias), ptr(out), i32(B), i32(H), i32(W), i32(cpad),
+          stream_ptr())
+    return out
+
+
+def g_final_bwd(dout, out, need_bias=True):
+    dout = _f32c(dout, "dout")
+    B, _, H, W = out.shape
+    dpre = torch.empty_like(out)
+    dbias = torch.empty(3, device=out.device, dtype=torch.float32) if need_bias else None
+    _call("g_final_bwd", 0, 0, lib().cb200_g_final_bwd, ptr(dout), ptr(out), ptr(dpre), ptr(dbias), i32(B), i32(H), i32(W),
+          stream_ptr())
+    return dpre, dbias
+
+
+def round_tf32_(x):
+    """Device-side RNA rounding to TF32 into a new tensor (kernel, not the torch bit trick below)."""
+    x = _f32c(x, "x")
+    y = torch.empty_like(x)
+    _call("round_tf32", 0, 0, lib().cb200_round_tf32, ptr(x), ptr(y), i64(x.numel()), stream_ptr())
+    return y
 
 
 # ------------------------------------------------------------------ layout helpers (torch ops; test/reference use)

@@ -9,18 +9,21 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ...functional import SNDCGANBackboneFn, SNLayerSpec
+from ...functional import GSNDCGANFn, SNDCGANBackboneFn, SNLayerSpec
 from .base import BaseDiscriminator, SNConv2d
 
 
 class G_SNDCGAN(nn.Module):
-    """models/gan/sndcgan.py:13-66.  (Round 1: the generator still runs on ATen/cuDNN library kernels; it is
-    the next row to move onto the tcgen05 transposed-conv kernels - see DESIGN.md 'library stand-ins'.)"""
+    """models/gan/sndcgan.py:13-66.  The torch modules below are parameter / buffer containers (same names,
+    shapes and initialisation as the reference, so state_dicts interchange and
+    nn.SyncBatchNorm.convert_sync_batchnorm works); the arithmetic is contrad_b200.functional.GSNDCGANFn."""
 
     def __init__(self, image_size, ngf=64, nz=128):
         super().__init__()
         self.image_size, self.ngf, self.nz = image_size, ngf, nz
         s_h, s_w, nc = image_size
+        if nc != 3:
+            raise NotImplementedError("RGB outputs only")
         self.s_hb, self.s_wb = s_h // 8, s_w // 8
         self.linear = nn.Linear(nz, ngf * 8 * self.s_hb * self.s_wb)
         self.norm_init = nn.BatchNorm2d(ngf * 8 * self.s_hb * self.s_wb)
@@ -31,11 +34,26 @@ class G_SNDCGAN(nn.Module):
             nn.ConvTranspose2d(ngf, nc, 3, 1, 1), nn.Tanh())
         self.reset_parameters()
 
+    def _bns(self):
+        return [self.norm_init, self.main[1], self.main[4], self.main[7]]
+
     def forward(self, z):
-        h = self.linear(z)
-        h = F.relu(self.norm_init(h.view(h.size(0), h.size(1), 1, 1)), inplace=True)
-        h = h.view(-1, self.ngf * 8, self.s_hb, self.s_wb)
-        return 0.5 * self.main(h) + 0.5
+        bns = self._bns()
+        holder = {"training": self.training,
+                  "sync": self.training and any(isinstance(b, nn.SyncBatchNorm) for b in bns)
+                  and torch.distributed.is_available() and torch.distributed.is_initialized()
+                  and torch.distributed.get_world_size() > 1,
+                  "bn_states": [(b.running_mean, b.running_var) for b in bns],
+                  "s_hb": self.s_hb, "s_wb": self.s_wb}
+        if self.training:
+            for b in bns:
+                b.num_batches_tracked += 1
+        c = self.main
+        return GSNDCGANFn.apply(holder, z, self.linear.weight, self.linear.bias, bns[0].weight, bns[0].bias,
+                                c[0].weight, c[0].bias, bns[1].weight, bns[1].bias,
+                                c[3].weight, c[3].bias, bns[2].weight, bns[2].bias,
+                                c[6].weight, c[6].bias, bns[3].weight, bns[3].bias,
+                                c[9].weight, c[9].bias)
 
     def sample_latent(self, n_samples):
         device = next(self.parameters()).device

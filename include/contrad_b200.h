@@ -95,14 +95,34 @@ int cb200_sn_weight_bwd(const float* dw_hat_packed, long long ld_fwd, const floa
                         const float* v, const float* sigma, float* acc_scratch, float* dw, int accumulate,
                         int Cout, int Cin, int KH, int KW, void* stream);
 
+/* Batched forms: all spectrally-normalised layers of D in one launch per phase (descriptor arrays live in
+ * HOST memory; n <= 16).  power_iter_batched expects every layer's `t` scratch zeroed by the caller,
+ * weight_bwd_batched every job's `acc` scalar zeroed. */
+struct cb200_sn_layer {
+    const float* w; float* u; float* v; float* sigma; float* t; float* s;
+    int cout, f;
+};
+struct cb200_sn_pack_job {
+    const float* w; const float* sigma; float* fwd; float* dgrad; long long ld_fwd, ldt;
+    int cout, cin, kh, kw, dgrad_mode, col0, round_out;
+};
+struct cb200_sn_bwd_job {
+    const float* dw_hat_packed; const float* w; const float* u; const float* v; const float* sigma; float* acc; float* dw;
+    long long ld_fwd; int cout, cin, kh, kw;
+};
+int cb200_sn_power_iter_batched(const struct cb200_sn_layer* layers, int n, float eps, int training, void* stream);
+int cb200_sn_pack_batched(const struct cb200_sn_pack_job* jobs, int n, void* stream);
+int cb200_sn_weight_bwd_batched(const struct cb200_sn_bwd_job* jobs, int n, void* stream);
+
 /* ---- first discriminator layer: Conv2d(3->64,3,1,1) + bias + LeakyReLU with x*2-1 folded in ---
  * (models/gan/sndcgan.py:91-93,122-124).  NCHW image in, NHWC activation out (SIMT, HBM-bound).
  * wgrad accumulates into dw_hat[64,27] (OIHW order) and db[64]; dgrad_finish extracts the 3 real
  * channels of the 32-channel padded tensor-core data gradient, applies the factor 2, NHWC->NCHW. */
 int cb200_conv_first_fwd(const float* x, const float* w, const float* sigma, const float* bias, float* y,
-                         int B, int H, int W, float slope, int round_out, void* stream);
+                         int B, int H, int W, float slope, int round_out, float in_scale, float in_shift,
+                         void* stream);
 int cb200_conv_first_wgrad(const float* x, const float* dy, float* dw_hat, float* db, int B, int H, int W,
-                           void* stream);
+                           float in_scale, float in_shift, void* stream);
 int cb200_conv_first_dgrad_finish(const float* dpad, float* dx, int B, int H, int W, int cpad, void* stream);
 
 /* ---- contrastive + GAN losses (fp32 SIMT, flash-style: no R x R matrix is materialised) --------
@@ -119,7 +139,7 @@ int cb200_rownorm_fwd(const float* x, long long ldx, float* y, float* inv_norm, 
 int cb200_rownorm_bwd(const float* dy, const float* y, const float* inv_norm, float* dx, long long lddx,
                       int rows, int d, int round_out, void* stream);
 int cb200_contrastive_fwd(const float* z, int N, int d, int mode, float temperature, float* lse,
-                          float* row_loss, float* loss, void* stream);
+                          float* scratch /* 48 floats per loss row */, float* loss, void* stream);
 int cb200_contrastive_bwd(const float* z, int N, int d, int mode, float temperature, const float* lse,
                           const float* gscale, float* dz, void* stream);
 int cb200_gan_d_loss(const float* d_real, const float* d_gen, long long stride, int N, int kind, float* out3,
@@ -130,6 +150,33 @@ int cb200_colsum(const float* x, long long ld, int M, int N, float* out, void* s
 /* out = dy * lrelu'(act) from the saved output activation (nn.LeakyReLU backward, sndcgan.py:92-108). */
 int cb200_lrelu_bwd(const float* dy, const float* act, float* out, long long n, float slope, int round_out,
                     void* stream);
+
+/* ---- generator-side kernels (G_SNDCGAN, models/gan/sndcgan.py:24-48) ------------------------------
+ * Train-mode BatchNorm2d(+ReLU) on NHWC activations x[M,C] (M = batch*H*W), split so the host can
+ * all-reduce the partial sums (SyncBatchNorm under DDP, train_gan.py:268):
+ *   bn_stats      sums[2,C] = {sum x, sum x^2}
+ *   bn_finalize   stats[2,C] = {mean, rstd}; running_mean/var updated (momentum, unbiased variance)
+ *   bn_apply_relu y = relu(gamma*(x-mean)*rstd + beta); remap_s > 0: x is [M, C] with feature index
+ *                 c*S+s ((c,h,w) flattening of norm_init, sndcgan.py:42-45) and y is NHWC [M, S, C/S]
+ *   bn_bwd_reduce sums[2,C] = {sum dz, sum dz*xhat}, dz = dy*1[y>0]
+ *   bn_bwd_apply  dx = gamma*rstd*(dz - sum_dz/count - xhat*sum_dz_xhat/count)
+ * g_final_fwd: out[B,3,H,W] = 0.5*tanh(pre[B,H,W,cpad][..., :3] + bias) + 0.5 (nn.Tanh + `0.5*y+0.5`);
+ * g_final_bwd: its backward from the saved output (+ bias gradient).  round_tf32: y = rna_tf32(x). */
+int cb200_bn_stats(const float* x, int M, int C, float* sums, void* stream);
+int cb200_bn_finalize(const float* sums, float count, int C, float eps, float momentum, float* stats,
+                      float* running_mean, float* running_var, void* stream);
+int cb200_bn_apply_relu(const float* x, const float* stats, const float* gamma, const float* beta, float* y,
+                        int M, int C, int remap_s, int round_out, void* stream);
+int cb200_bn_bwd_reduce(const float* dy, const float* y, const float* x, const float* stats, int M, int C,
+                        int remap_s, float* sums, void* stream);
+int cb200_bn_bwd_apply(const float* dy, const float* y, const float* x, const float* stats, const float* gamma,
+                       const float* sums, float count, float* dx, int M, int C, int remap_s, int round_out,
+                       void* stream);
+int cb200_g_final_fwd(const float* pre, const float* bias, float* out, int B, int H, int W, int cpad,
+                      void* stream);
+int cb200_g_final_bwd(const float* dout, const float* out, float* dpre, float* dbias, int B, int H, int W,
+                      void* stream);
+int cb200_round_tf32(const float* x, float* y, long long n, void* stream);
 
 #ifdef __cplusplus
 }

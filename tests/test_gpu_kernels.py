@@ -303,3 +303,38 @@ def test_rownorm_and_gan_losses(K):
         assert abs(float(out[0]) - float(ref)) < 1e-5 and torch.allclose(g, dr.grad[:, 0], atol=1e-6)
     x = torch.randn(5000, 192, device="cuda")
     assert torch.allclose(K.colsum(x), x.sum(0), atol=1e-3, rtol=1e-4)
+
+
+def test_sn_batched_equals_single(K):
+    """The batched power-iteration / pack / backward launches give the single-layer results."""
+    torch.manual_seed(0)
+    shapes = [(64, 3, 3, 3), (128, 64, 4, 4), (512, 512, 3, 3), (512, 8192), (1, 512), (128, 512)]
+    ws = [torch.randn(*s, device="cuda") * 0.05 for s in shapes]
+    us = [F.normalize(torch.randn(s[0], device="cuda"), dim=0) for s in shapes]
+    vs = [F.normalize(torch.randn(w.numel() // w.shape[0], device="cuda"), dim=0) for w in ws]
+    u1, v1 = [u.clone() for u in us], [v.clone() for v in vs]
+    u2, v2 = [u.clone() for u in us], [v.clone() for v in vs]
+    s1 = [torch.zeros(2, device="cuda") for _ in ws]
+    s2 = [torch.zeros(2, device="cuda") for _ in ws]
+    for w, u, v, s in zip(ws, u1, v1, s1):
+        K.sn_power_iter(w, u, v, s, training=True)
+    K.sn_power_iter_batched(list(zip(ws, u2, v2, s2)), training=True)
+    for a, b in zip(u1 + v1 + s1, u2 + v2 + s2):
+        assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+    # eval-mode sigma from the stored vectors
+    s3 = [torch.zeros(2, device="cuda") for _ in ws]
+    K.sn_power_iter_batched(list(zip(ws, u2, v2, s3)), training=False)
+    for a, b in zip(s2, s3):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+    # pack + backward on the 4x4 stride-2 layer and the big linear layer
+    w = ws[1]
+    fwd_a = torch.empty(128, 16 * 64, device="cuda"); dg_a = torch.empty(4 * 64, 4 * 128, device="cuda")
+    fwd_b = torch.empty_like(fwd_a); dg_b = torch.empty_like(dg_a)
+    K.sn_pack_weights(w, s1[1], fwd=fwd_a, ld_fwd=1024, dgrad=dg_a, dgrad_mode=2)
+    K.sn_pack_batched([dict(w4=w, sigma=s1[1], fwd=fwd_b, ld_fwd=1024, dgrad=dg_b, dgrad_mode=2)])
+    assert torch.equal(fwd_a, fwd_b) and torch.equal(dg_a, dg_b)
+    g = torch.randn_like(fwd_a)
+    dw_a = torch.empty_like(w); dw_b = torch.empty_like(w)
+    K.sn_weight_bwd(g, 1024, w, u1[1], v1[1], s1[1], dw_a)
+    K.sn_weight_bwd_batched([dict(dw_hat_packed=g, ld_fwd=1024, w4=w, u=u1[1], v=v1[1], sigma=s1[1], dw=dw_b)])
+    assert torch.allclose(dw_a, dw_b, atol=1e-6, rtol=1e-4)

@@ -1,0 +1,41 @@
+"""Small driver for `ncu --set full`: runs one hot kernel of the D-step a few times.
+usage: python tools/profile_target.py {conv3x3|conv4x4|dgrad|wgrad|augment|heads}"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from contrad_b200 import kernels as K
+which = sys.argv[1] if len(sys.argv) > 1 else "conv3x3"
+B = 1536
+torch.manual_seed(0)
+if which in ("conv3x3", "dgrad", "wgrad"):
+    H, Cin, Cout, ks, st = 16, 128, 128, 3, 1
+elif which == "conv4x4":
+    H, Cin, Cout, ks, st = 16, 128, 256, 4, 2
+if which in ("conv3x3", "conv4x4", "dgrad", "wgrad"):
+    x = K.round_tf32(torch.randn(B, H, H, Cin, device="cuda"))
+    w = K.round_tf32(torch.randn(Cout, Cin, ks, ks, device="cuda") * 0.02)
+    bias = torch.zeros(Cout, device="cuda")
+    wm, wt = K.pack_fwd_weight(w), K.pack_dgrad_weight(w, st)
+    dy = K.round_tf32(torch.randn(B, H // st, H // st, Cout, device="cuda"))
+    for _ in range(4):
+        if which in ("conv3x3", "conv4x4"):
+            K.conv2d_nhwc_fwd(x, wm, bias, ks, st, slope=0.1, round_out=True)
+        elif which == "dgrad":
+            K.conv2d_nhwc_dgrad(dy, wt, (B, H, H, Cin), ks, st, act_in=x, slope=0.1, round_out=True)
+        else:
+            K.conv2d_nhwc_wgrad(x, dy, ks, st)
+elif which == "heads":
+    a = K.round_tf32(torch.randn(B, 8192, device="cuda")); b = K.round_tf32(torch.randn(1536, 8192, device="cuda") * 0.02)
+    for _ in range(4):
+        K.gemm_nt(a, b, None, slope=0.1, round_out=True)
+elif which == "augment":
+    from oracle import contrad_oracle as O
+    np.random.seed(0)
+    Bn = 65536
+    params, order = O.sample_simclr_params(Bn, 32, 32)
+    p = O.pack_params(params).cuda()
+    xx = torch.rand(Bn, 3, 32, 32, device="cuda")
+    for _ in range(4):
+        K.augment_simclr_fwd(xx, p, order)
+torch.cuda.synchronize()
+print("done", which)
