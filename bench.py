@@ -227,8 +227,9 @@ def build_world(args):
     if world > 1:
         G = torch.nn.SyncBatchNorm.convert_sync_batchnorm(G)
     G.cuda(); D.cuda()
-    opt_G = torch.optim.Adam(G.parameters(), lr=OPTIONS["lr"], betas=OPTIONS["beta"])
-    opt_D = torch.optim.Adam(D.parameters(), lr=OPTIONS["lr_d"], betas=OPTIONS["beta"])
+    from contrad_b200.optim import FusedAdam      # same update rule / state as torch.optim.Adam (train_gan.py:273-274)
+    opt_G = FusedAdam(G.parameters(), lr=OPTIONS["lr"], betas=OPTIONS["beta"])
+    opt_D = FusedAdam(D.parameters(), lr=OPTIONS["lr_d"], betas=OPTIONS["beta"])
     P.augment_fn = get_augment(mode=P.aug).cuda()
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP

@@ -114,28 +114,24 @@ __device__ __forceinline__ float hue_turns(float y, float x) {
 __device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float hshift, float fs, float fv) {
     float cmax = fmaxf(r, fmaxf(g, b));
     float cmin = fminf(r, fminf(g, b));
-    float hue = hue_turns(1.7320508075688772f * (g - b), 2.f * r - g - b);
+    float hue = hue_turns(1.7320508075688772f * (g - b), 2.f * r - g - b);     // finite for finite inputs
     float sat = 1.f - __fdividef(cmin, cmax + 1e-8f);
-    float val = cmax;
-    if (!isfinite(hue)) hue = 0.f;
-    if (!isfinite(sat)) sat = 0.f;
-    if (!isfinite(val)) val = 0.f;
+    if (!isfinite(sat)) sat = 0.f;           // the reference zeroes non-finite hsv entries (utils.py:37)
+    float val = isfinite(cmax) ? cmax : 0.f;
     float h = hue + hshift;
     h = h - floorf(h);
-    float s = sat * fs;
-    float v = val * fv;
-    h = fminf(fmaxf(h, 0.f), 1.f);
-    s = fminf(fmaxf(s, 0.f), 1.f);
-    v = fminf(fmaxf(v, 0.f), 1.f);
-    float c = v * s;
-    float h6 = h * 6.f;
+    const float s = __saturatef(sat * fs);
+    const float v = __saturatef(val * fv);
+    h = __saturatef(h);
+    const float c = v * s;
+    const float h6 = h * 6.f;
     float k, t;
-    k = 5.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = fminf(fmaxf(fminf(k, 4.f - k), 0.f), 1.f); r = v - c * t;
-    k = 3.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = fminf(fmaxf(fminf(k, 4.f - k), 0.f), 1.f); g = v - c * t;
-    k = 1.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = fminf(fmaxf(fminf(k, 4.f - k), 0.f), 1.f); b = v - c * t;
+    k = 5.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = __saturatef(fminf(k, 4.f - k)); r = fmaf(-c, t, v);
+    k = 3.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = __saturatef(fminf(k, 4.f - k)); g = fmaf(-c, t, v);
+    k = 1.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = __saturatef(fminf(k, 4.f - k)); b = fmaf(-c, t, v);
 }
 
-__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+__device__ __forceinline__ float clamp01(float x) { return __saturatef(x); }   // one FADD.SAT; NaN -> 0 like fmin(fmax())
 
 // Stage one [3,H,W] image into shared memory (coalesced float4, streaming).
 __device__ __forceinline__ void stage_image(const float* __restrict__ src, float* dst, int n_elems) {

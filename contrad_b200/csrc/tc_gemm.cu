@@ -463,6 +463,16 @@ int pair_mode() {
     return mode;
 }
 
+// Rows of the weight matrix one CTA stages per k-block for an (N, m_tiles) problem - the B tensor map's box must
+// be encoded with exactly this many rows.  Mirrors the kernel choice made in dispatch().
+int b_box_rows(int N, int m_tiles) {
+    if (pair_mode() && m_tiles >= 296) {
+        if (N % 256 == 0) return 128;      // pair, BN = 256: half per CTA
+        if (N % 128 == 0) return 64;       // pair, BN = 128
+    }
+    return (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
+}
+
 int dispatch(const TapGemmParams& p, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
     if (pair_mode() && m_tiles >= 296) {
         if (N % 256 == 0) return launch2<256, 4>(p, m_tiles, N / 256, classes, st, name);     // 32 KB / stage / CTA
@@ -504,14 +514,15 @@ int conv_like(const float* src, int Bn, int Hs, int Ws, int C,           // A te
                            (uint64_t)Bn * Hs * Ws * C * 4};
     uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)wt, (uint32_t)ht, (uint32_t)bt, 1};
     if (int e = encode_map(&p.tmap_a, src, 5, dims, strides, box)) return e;
-    const int Ktot = ntaps * C;
-    uint64_t bdims[2] = {(uint64_t)Ktot, (uint64_t)N * classes};
-    uint64_t bstr[2] = {4, (uint64_t)Ktot * 4};
-    const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
-    uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
-    if (int e = encode_map(&p.tmap_b, wmat, 2, bdims, bstr, bbox)) return e;
     p.box[0] = wt; p.box[1] = ht; p.box[2] = bt; p.box[3] = 1;
     p.tiles[0] = (Wo + wt - 1) / wt; p.tiles[1] = (Ho + ht - 1) / ht; p.tiles[2] = (Bn + bt - 1) / bt; p.tiles[3] = 1;
+    {
+        const int Ktot = ntaps * C;
+        uint64_t bdims[2] = {(uint64_t)Ktot, (uint64_t)N * classes};
+        uint64_t bstr[2] = {4, (uint64_t)Ktot * 4};
+        uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)b_box_rows(N, p.tiles[0] * p.tiles[1] * p.tiles[2])};
+        if (int e = encode_map(&p.tmap_b, wmat, 2, bdims, bstr, bbox)) return e;
+    }
     p.extent[0] = Wo; p.extent[1] = Ho; p.extent[2] = Bn; p.extent[3] = 1;
     p.ostride[0] = os_w; p.ostride[1] = os_h; p.ostride[2] = os_b; p.ostride[3] = 0;
     for (int c = 0; c < classes; ++c) {
@@ -557,8 +568,7 @@ extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw
     if (int e = encode_map(&p.tmap_a, a, 5, dims, strides, box)) return e;
     uint64_t bdims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t bstr[2] = {4, (uint64_t)ldb * 4};
-    const int BN = (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
-    uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+    uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)b_box_rows(N, (M + kBlockM - 1) / kBlockM)};
     if (int e = encode_map(&p.tmap_b, bw, 2, bdims, bstr, bbox)) return e;
     p.box[0] = kBlockM; p.box[1] = 1; p.box[2] = 1; p.box[3] = 1;
     p.tiles[0] = (M + kBlockM - 1) / kBlockM; p.tiles[1] = 1; p.tiles[2] = 1; p.tiles[3] = 1;
@@ -605,8 +615,8 @@ extern "C" int cb200_conv2d_nhwc_fwd(const float* x, const float* wmat, const fl
         const int Ktot = 16 * Cin;
         uint64_t bdims[2] = {(uint64_t)Ktot, (uint64_t)Cout};
         uint64_t bstr[2] = {4, (uint64_t)Ktot * 4};
-        const int BN = (Cout % 128 == 0) ? 128 : (Cout % 64 == 0 ? 64 : 32);
-        uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)BN};
+        const int mt = ((Wo + wt - 1) / wt) * ((Ho + ht - 1) / ht) * ((B + bt - 1) / bt);
+        uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)b_box_rows(Cout, mt)};
         if (int e = encode_map(&p.tmap_b, wmat, 2, bdims, bstr, bbox)) return e;
         p.box[0] = wt; p.box[1] = 1; p.box[2] = ht; p.box[3] = bt;
         p.tiles[0] = (Wo + wt - 1) / wt; p.tiles[1] = 1; p.tiles[2] = (Ho + ht - 1) / ht; p.tiles[3] = (B + bt - 1) / bt;

@@ -409,6 +409,24 @@ def round_tf32_(x):
     return y
 
 
+# ------------------------------------------------------------------ fused Adam
+class _AdamTensor(ctypes.Structure):
+    _fields_ = [("p", ctypes.c_void_p), ("g", ctypes.c_void_p), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("numel", ctypes.c_longlong)]
+
+
+def adam_step(entries, lr, beta1, beta2, eps, step):
+    """entries: list of (param, grad, exp_avg, exp_avg_sq) contiguous fp32 CUDA tensors; in-place update."""
+    arr = (_AdamTensor * len(entries))()
+    nbytes = 0
+    for i, (p, g, m, v) in enumerate(entries):
+        assert p.is_cuda and p.is_contiguous() and g.is_contiguous()
+        arr[i] = _AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+        nbytes += 28 * p.numel()
+    _call("adam_step", 0, nbytes, lib().cb200_adam_step, arr, i32(len(entries)), f32(lr), f32(beta1), f32(beta2), f32(eps),
+          i32(step), stream_ptr())
+
+
 # ------------------------------------------------------------------ layout helpers (torch ops; test/reference use)
 def pack_fwd_weight(w):
     """OIHW -> [Cout, kh*kw*Cin] (tap-major, channel-minor)."""

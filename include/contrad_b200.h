@@ -178,6 +178,14 @@ int cb200_g_final_bwd(const float* dout, const float* out, float* dpre, float* d
                       void* stream);
 int cb200_round_tf32(const float* x, float* y, long long n, void* stream);
 
+/* ---- fused multi-tensor Adam (torch.optim.Adam of train_gan.py:273-274: no weight decay / amsgrad) ----
+ * One launch per 48 tensors; `step` is the 1-based step count used for the bias corrections. */
+struct cb200_adam_tensor {
+    float* p; const float* g; float* m; float* v; long long numel;
+};
+int cb200_adam_step(const struct cb200_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
+                    int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

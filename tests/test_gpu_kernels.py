@@ -86,7 +86,7 @@ def test_augment_full_size_properties(K):
 
 # ---------------------------------------------------------------------------------- tensor-core GEMM
 @pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (256, 128, 64), (384, 64, 96), (1000, 32, 512),
-                                    (1536, 1536, 8192), (77, 128, 128)])
+                                    (1536, 1536, 8192), (77, 128, 128), (40000, 256, 64), (37900, 128, 96)])
 def test_gemm_nt_tf32(K, M, N, K_):
     torch.manual_seed(M + N + K_)
     a = K.round_tf32(torch.randn(M, K_, device="cuda"))
@@ -111,9 +111,10 @@ def test_gemm_nt_strided_views(K):
 
 
 CONV_CASES = [
-    # B, H, Cin, Cout, ks, stride
+    # B, H, Cin, Cout, ks, stride   (the last four have >= 296 M tiles: CTA-pair / cta_group::2 kernels)
     (8, 32, 64, 128, 4, 2), (8, 16, 128, 128, 3, 1), (8, 16, 128, 256, 4, 2), (6, 8, 256, 256, 3, 1),
     (16, 8, 256, 512, 4, 2), (16, 4, 512, 512, 3, 1), (3, 4, 64, 64, 3, 1), (5, 8, 32, 32, 4, 2),
+    (301, 16, 128, 128, 3, 1), (600, 16, 128, 256, 4, 2), (1201, 8, 256, 256, 3, 1), (1200, 32, 64, 128, 4, 2),
 ]
 
 
@@ -338,3 +339,26 @@ def test_sn_batched_equals_single(K):
     K.sn_weight_bwd(g, 1024, w, u1[1], v1[1], s1[1], dw_a)
     K.sn_weight_bwd_batched([dict(dw_hat_packed=g, ld_fwd=1024, w4=w, u=u1[1], v=v1[1], sigma=s1[1], dw=dw_b)])
     assert torch.allclose(dw_a, dw_b, atol=1e-6, rtol=1e-4)
+
+
+def test_fused_adam_matches_torch_adam(K):
+    from contrad_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(512, 8192), (64, 3, 3, 3), (1, 512), (77,), (128, 64, 4, 4)]
+    pa = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdam(pa, lr=2e-4, betas=(0.5, 0.999))
+    ob = torch.optim.Adam(pb, lr=2e-4, betas=(0.5, 0.999))
+    for step in range(3):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a) * (step + 1)
+            a.grad = g.clone(); b.grad = g.clone()
+        for o in (oa, ob):
+            for grp in o.param_groups:
+                grp["lr"] = 2e-4 * (step + 1) / 3
+        oa.step(); ob.step()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, atol=1e-7, rtol=1e-5)
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert set(sa["state"][0].keys()) == set(sb["state"][0].keys())
+    ob.load_state_dict(sa)          # checkpoints interchange
