@@ -22,12 +22,24 @@ bn_stats_kernel(const float* __restrict__ x, int M, int C, int cc, int rows_per_
     const int c = blockIdx.x * cc + tx;
     const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
     float a[2] = {0.f, 0.f};
-    if (c < C)
-        for (int m = m0 + ty; m < m1; m += lanes) {
+    if (c < C) {
+        float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f, s3 = 0.f, q3 = 0.f;
+        int m = m0 + ty;
+        for (; m + 3 * lanes < m1; m += 4 * lanes) {          // 4 independent loads in flight
+            const float v0 = __ldg(x + (long long)m * C + c);
+            const float v1 = __ldg(x + (long long)(m + lanes) * C + c);
+            const float v2 = __ldg(x + (long long)(m + 2 * lanes) * C + c);
+            const float v3 = __ldg(x + (long long)(m + 3 * lanes) * C + c);
+            a[0] += v0; a[1] += v0 * v0; s1 += v1; q1 += v1 * v1; s2 += v2; q2 += v2 * v2; s3 += v3; q3 += v3 * v3;
+        }
+        for (; m < m1; m += lanes) {
             const float v = __ldg(x + (long long)m * C + c);
             a[0] += v;
             a[1] += v * v;
         }
+        a[0] += (s1 + s2) + s3;
+        a[1] += (q1 + q2) + q3;
+    }
     fold_row_lanes<2>(a, scratch, cc);
     if (ty == 0 && c < C) {
         atomicAdd(sums + c, a[0]);
@@ -98,12 +110,25 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, 
     if (j < C) {
         const float mean = stats[f], rstd = stats[C + f];
         const int m0 = blockIdx.y * rows_per_cta, m1 = min(M, m0 + rows_per_cta);
-        for (int m = m0 + ty; m < m1; m += lanes) {
+        float b0 = 0.f, b1 = 0.f;
+        int m = m0 + ty;
+        for (; m + lanes < m1; m += 2 * lanes) {               // 2 x 3 independent loads in flight
+            const long long r0 = (long long)m * C, r1 = (long long)(m + lanes) * C;
+            const float y0 = __ldg(y + r0 + j), y1 = __ldg(y + r1 + j);
+            const float d0 = __ldg(dy + r0 + j), d1 = __ldg(dy + r1 + j);
+            const float x0 = __ldg(x + r0 + f), x1 = __ldg(x + r1 + f);
+            const float g0 = y0 > 0.f ? d0 : 0.f, g1 = y1 > 0.f ? d1 : 0.f;
+            a[0] += g0; a[1] += g0 * ((x0 - mean) * rstd);
+            b0 += g1; b1 += g1 * ((x1 - mean) * rstd);
+        }
+        for (; m < m1; m += lanes) {
             const float g = (__ldg(y + (long long)m * C + j) > 0.f) ? __ldg(dy + (long long)m * C + j) : 0.f;
             const float xh = (__ldg(x + (long long)m * C + f) - mean) * rstd;
             a[0] += g;
             a[1] += g * xh;
         }
+        a[0] += b0;
+        a[1] += b1;
     }
     fold_row_lanes<2>(a, scratch, cc);
     if (ty == 0 && j < C) {

@@ -326,8 +326,18 @@ colsum_kernel(const float* __restrict__ x, long long ld, int M, int N, int cc, i
     const int m0 = blockIdx.y * rows_per_cta;
     const int m1 = min(M, m0 + rows_per_cta);
     float a[1] = {0.f};
-    if (n < N)
-        for (int m = m0 + ty; m < m1; m += lanes) a[0] += __ldg(x + (long long)m * ld + n);
+    if (n < N) {
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int m = m0 + ty;
+        for (; m + 3 * lanes < m1; m += 4 * lanes) {          // 4 independent loads in flight
+            a[0] += __ldg(x + (long long)m * ld + n);
+            a1 += __ldg(x + (long long)(m + lanes) * ld + n);
+            a2 += __ldg(x + (long long)(m + 2 * lanes) * ld + n);
+            a3 += __ldg(x + (long long)(m + 3 * lanes) * ld + n);
+        }
+        for (; m < m1; m += lanes) a[0] += __ldg(x + (long long)m * ld + n);
+        a[0] += (a1 + a2) + a3;
+    }
     fold_row_lanes<1>(a, scratch, cc);
     if (ty == 0 && n < N) atomicAdd(out + n, a[0]);
 }

@@ -55,6 +55,7 @@ struct TapGemmParams {
     const float* dact;    // same addressing as out; multiplies by (dact > 0 ? 1 : slope); or null
     float slope;          // LeakyReLU slope applied after bias (1.0 = identity) when dact == null
     int round_out;        // round outputs to TF32 (they feed another tensor-core GEMM)
+    int debug;            // profiling experiments only (env CB200_TAPGEMM_DEBUG): 1 no stores, 2 no MMA, 4 no A loads, 8 no B loads
 };
 
 template <int BN, int STAGES>
@@ -65,11 +66,19 @@ struct SmemLayout {
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
 };
 
-// Epilogue of one 128-row tile: thread = one output row; TMEM -> registers -> bias / activation -> global.
+// Epilogue of one 128-row tile.  tcgen05.ld hands every thread one accumulator ROW (32 columns at a time); writing
+// rows straight to global memory would make each warp store touch 32 different lines (measured: ~30 % of the
+// kernel).  Instead each epilogue warp transposes its 32x32 block through shared memory (the pipeline's stage-0
+// buffer, free once tmem_full has fired) so that 8 lanes cover one contiguous 128-byte row segment: bias /
+// LeakyReLU / lrelu' mask / TF32 rounding are applied in the coalesced domain, loads of `dact` included.
+constexpr int kEpiStride = 36;                        // floats per staged row: 16-byte aligned, conflict-free float4
+constexpr int kEpiWarpFloats = 32 * kEpiStride;       // 4.5 KB per epilogue warp
+
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
-                                              uint32_t tmem_base, uint64_t* tmem_full_bar, int warp, int lane) {
+__device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
+                                                     uint32_t tmem_base, int warp, int lane, float* stage_buf) {
     const int q = warp & 3;
+    float* st = stage_buf + q * kEpiWarpFloats;
     int r = q * 32 + lane;
     bool valid = true;
     long long orow = p.cls_off[cls];
@@ -81,43 +90,61 @@ __device__ __forceinline__ void epilogue_rows(const TapGemmParams& p, const int 
         valid = valid && (x < p.extent[d]);
         orow += (long long)x * p.ostride[d];
     }
-    float* orow_ptr = p.out + orow * p.ldo + n0;
-    const float* drow_ptr = p.dact ? p.dact + orow * p.ldo + n0 : nullptr;
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::fence_after_sync();
+    const long long my_off = valid ? orow * p.ldo : -1;        // element offset of this lane's row, -1 = masked
+    const int sub = lane >> 3;                                  // row within a group of 4
+    const int col4 = (lane & 7) * 4;                            // first of this lane's 4 columns within the chunk
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
         tc::tmem_ld_wait();
-        if (valid) {
+        if (p.debug & 1) continue;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float o[4];
+        for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(st + lane * kEpiStride + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + col4));
+        long long offs[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[j + e]);
-                if (p.bias) {
-                    float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-                    o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
-                }
-                if (drow_ptr) {
-                    float4 a = __ldg(reinterpret_cast<const float4*>(drow_ptr + c0 + j));
-                    o[0] *= (a.x > 0.f) ? 1.f : p.slope;
-                    o[1] *= (a.y > 0.f) ? 1.f : p.slope;
-                    o[2] *= (a.z > 0.f) ? 1.f : p.slope;
-                    o[3] *= (a.w > 0.f) ? 1.f : p.slope;
+        for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + sub);
+        float4 act[8];
+        if (p.dact) {                      // all eight independent loads in flight before the first store
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                act[it] = (offs[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(p.dact + offs[it] + n0 + c0 + col4))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int row = it * 4 + sub;
+            float4 o = *reinterpret_cast<const float4*>(st + row * kEpiStride + col4);
+            if (offs[it] >= 0) {
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                if (p.dact) {
+                    const float4 a = act[it];
+                    o.x *= (a.x > 0.f) ? 1.f : p.slope; o.y *= (a.y > 0.f) ? 1.f : p.slope;
+                    o.z *= (a.z > 0.f) ? 1.f : p.slope; o.w *= (a.w > 0.f) ? 1.f : p.slope;
                 } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = (o[e] > 0.f) ? o[e] : o[e] * p.slope;
+                    o.x = (o.x > 0.f) ? o.x : o.x * p.slope; o.y = (o.y > 0.f) ? o.y : o.y * p.slope;
+                    o.z = (o.z > 0.f) ? o.z : o.z * p.slope; o.w = (o.w > 0.f) ? o.w : o.w * p.slope;
                 }
-                if (p.round_out) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
-                }
-                *reinterpret_cast<float4*>(orow_ptr + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *reinterpret_cast<float4*>(p.out + offs[it] + n0 + c0 + col4) = o;
             }
         }
+        __syncwarp();
     }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
+                                              uint32_t tmem_base, uint64_t* tmem_full_bar, int warp, int lane,
+                                              float* stage_buf) {
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+    epilogue_rows_nowait<BN>(p, base, cls, n0, tmem_base, warp, lane, stage_buf);
 }
 
 template <int BN, int STAGES>
@@ -176,11 +203,13 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
                 tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * L::kStageBytes;
                 uint8_t* sb = sa + kATileBytes;
-                tc::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                tc::mbar_expect_tx(&full_bar[stage], ((p.debug & 4) ? 0 : kATileBytes) + ((p.debug & 8) ? 0 : L::kBTileBytes));
                 const int* tp = p.tap[cls][t];
-                tc::tma_load_5d(sa, &p.tmap_a, &full_bar[stage], cb * kBlockK + tp[0], base[0] + tp[1],
-                                base[1] + tp[2], base[2] + tp[3], base[3] + tp[4]);
-                tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * kBlockK, cls * p.b_rows_per_cls + n0);
+                if (!(p.debug & 4))
+                    tc::tma_load_5d(sa, &p.tmap_a, &full_bar[stage], cb * kBlockK + tp[0], base[0] + tp[1],
+                                    base[1] + tp[2], base[2] + tp[3], base[3] + tp[4]);
+                if (!(p.debug & 8))
+                    tc::tma_load_2d(sb, &p.tmap_b, &full_bar[stage], kb * kBlockK, cls * p.b_rows_per_cls + n0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -194,20 +223,25 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
             if (tc::elect_one()) {
                 const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
                 const uint32_t sb = sa + kATileBytes;
+                if (!(p.debug & 2)) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 8; ++k) {
-                    const uint64_t adesc = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-                    tc::mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < kBlockK / 8; ++k) {
+                        const uint64_t adesc = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                        tc::mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    tc::mma_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) tc::mma_commit(tmem_full_bar);
+                } else {
+                    tc::mbar_arrive(&empty_bar[stage]);
+                    if (kb == num_kb - 1) tc::mbar_arrive(tmem_full_bar);
                 }
-                tc::mma_commit(&empty_bar[stage]);
-                if (kb == num_kb - 1) tc::mma_commit(tmem_full_bar);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
-        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane);
+        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem));
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -323,13 +357,192 @@ tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
-        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane);
+        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem));
     }
     tc::fence_before_sync();
     tc::cluster_sync_all();
     if (warp == 2) {
         tc::fence_after_sync();
         tc::tmem_dealloc2(tmem_base, BN);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent CTA-pair variant: one cluster of two CTAs per SM pair walks a strided list of output super-tiles.
+//   * super-tile = 2*MT consecutive 128-row M tiles (MT per CTA) x BN columns; every k-block stages MT A boxes and
+//     BN/2 weight rows per CTA -> (MT*16 KB + BN*64 B) per (MT x 128 x BN x 32) MACs: 2.0x (BN=256, MT=1) resp.
+//     1.6x (BN=128, MT=2) fewer shared-memory bytes per FLOP than the 128x128 single-CTA tile, which is what the
+//     measured ~77 B/clk/SM of L2->SM ingest requires for TF32 operands;
+//   * the smem ring runs continuously across tiles (no pipeline drain between tiles);
+//   * TMEM holds TWO accumulator sets (2 * MT * BN = 512 columns): the epilogue of tile i (TMEM -> smem transpose
+//     -> coalesced stores) overlaps the MMAs of tile i+1 (tmem_full / tmem_empty barriers, the latter collecting
+//     the arrivals of the epilogue warps of BOTH CTAs at the pair leader).
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MT, int STAGES>
+struct SmemLayoutP {
+    static constexpr int kATile = MT * kATileBytes;
+    static constexpr int kBTile = (BN / 2) * kBlockK * 4;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kEpiOffset = STAGES * kStageBytes;
+    static constexpr int kBarOffset = kEpiOffset + 4 * kEpiWarpFloats * 4;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+struct PersistSched {
+    int m_tiles;          // 128-row tiles per class
+    int n_tiles;          // N / BN
+    int classes;
+    int super_per_class;  // ceil(m_tiles / (2*MT))
+    int total_units;      // super_per_class * n_tiles * classes
+    int num_pairs;        // gridDim.x / 2
+};
+
+template <int BN, int MT, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+tap_gemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_constant__ PersistSched sc) {
+    using L = SmemLayoutP<BN, MT, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* epi_buf = reinterpret_cast<float*>(smem + L::kEpiOffset);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] (used on the leader)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1;
+    const int num_kb = p.ntaps * p.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&p.tmap_a);
+        tc::prefetch_tmap(&p.tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&tmem_full_bar[b], 1);
+            tc::mbar_init(&tmem_empty_bar[b], 8);       // 4 epilogue warps x 2 CTAs
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tc::tmem_alloc2(tmem_slot, 2 * MT * BN);
+    tc::fence_before_sync();
+    tc::cluster_sync_all();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work unit -> (class, n tile, first m tile of this CTA)
+    auto decode = [&](int unit, int& cls, int& n0, int& mt0) {
+        const int nt = unit % sc.n_tiles;
+        const int rest = unit / sc.n_tiles;
+        const int sup = rest % sc.super_per_class;
+        cls = rest / sc.super_per_class;
+        n0 = nt * BN;
+        mt0 = (sup * 2 + (int)rank) * MT;
+    };
+    auto tile_base = [&](int mtile, int (&base)[4]) {
+        int t = mtile;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            base[d] = (t % p.tiles[d]) * p.box[d];
+            t /= p.tiles[d];
+        }
+        if (mtile >= sc.m_tiles) base[3] = p.extent[3] + p.box[3] * (1 + t);   // surplus tile: OOB loads, masked stores
+    };
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = pair_id; unit < sc.total_units; unit += sc.num_pairs) {
+                int cls, n0, mt0;
+                decode(unit, cls, n0, mt0);
+                int base[MT][4];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) tile_base(mt0 + m, base[m]);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int t = kb / p.cblocks;
+                    const int cb = kb - t * p.cblocks;
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::kStageBytes;
+                    uint8_t* sb = sa + L::kATile;
+                    const uint32_t bar = tc::map_to_cta(tc::smem_u32(&full_bar[stage]), 0);
+                    if (leader) tc::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+                    const int* tp = p.tap[cls][t];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tc::tma2_load_5d(sa + m * kATileBytes, &p.tmap_a, bar, cb * kBlockK + tp[0], base[m][0] + tp[1],
+                                         base[m][1] + tp[2], base[m][2] + tp[3], base[m][3] + tp[4]);
+                    tc::tma2_load_2d(sb, &p.tmap_b, bar, kb * kBlockK, cls * p.b_rows_per_cls + n0 + (int)rank * (BN / 2));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        constexpr uint32_t idesc = tc::idesc_tf32(256, BN, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int unit = pair_id; unit < sc.total_units; unit += sc.num_pairs, ++it) {
+            const int ab = it & 1;
+            const uint32_t use = (uint32_t)(it >> 1);
+            tc::mbar_wait_cluster(&tmem_empty_bar[ab], (use & 1) ^ 1);     // epilogues of both CTAs drained this set
+            tc::fence_after_sync();
+            for (int kb = 0; kb < num_kb; ++kb) {
+                tc::mbar_wait(&full_bar[stage], phase);
+                tc::fence_after_sync();
+                if (tc::elect_one()) {
+                    const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sb = sa + L::kATile;
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 8; ++k) {
+                            const uint64_t adesc = tc::smem_desc_sw128(sa + m * kATileBytes + k * 32, 16, 1024);
+                            const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                            tc::mma2_tf32(tmem_base + (uint32_t)((ab * MT + m) * BN), adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    tc::mma2_commit_multicast(&empty_bar[stage]);
+                    if (kb == num_kb - 1) tc::mma2_commit_multicast(&tmem_full_bar[ab]);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        int it = 0;
+        for (int unit = pair_id; unit < sc.total_units; unit += sc.num_pairs, ++it) {
+            const int ab = it & 1;
+            const uint32_t use = (uint32_t)(it >> 1);
+            int cls, n0, mt0;
+            decode(unit, cls, n0, mt0);
+            tc::mbar_wait(&tmem_full_bar[ab], use & 1);
+            tc::fence_after_sync();
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                int base[4];
+                tile_base(mt0 + m, base);
+                epilogue_rows_nowait<BN>(p, base, cls, n0, tmem_base + (uint32_t)((ab * MT + m) * BN), warp, lane, epi_buf);
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(&tmem_empty_bar[ab], 0);
+        }
+    }
+    tc::fence_before_sync();
+    tc::cluster_sync_all();
+    if (warp == 2) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc2(tmem_base, 2 * MT * BN);
     }
 }
 
@@ -453,6 +666,62 @@ int launch2(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaS
     return CB200_OK;
 }
 
+template <int BN, int MT, int STAGES>
+int launch_persist(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
+    using L = SmemLayoutP<BN, MT, STAGES>;
+    static bool configured = false;
+    static int sms = 0;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tap_gemm_persist_kernel<BN, MT, STAGES>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+        if (e != cudaSuccess) {
+            cb200_set_error("%s: cudaFuncSetAttribute(smem=%d): %s", name, L::kTotal, cudaGetErrorString(e));
+            return (int)e;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+        configured = true;
+    }
+    PersistSched sc;
+    sc.m_tiles = m_tiles; sc.n_tiles = n_tiles; sc.classes = classes;
+    sc.super_per_class = (m_tiles + 2 * MT - 1) / (2 * MT);
+    sc.total_units = sc.super_per_class * n_tiles * classes;
+    sc.num_pairs = sms / 2 < sc.total_units ? sms / 2 : sc.total_units;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * sc.num_pairs, 1, 1);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tap_gemm_persist_kernel<BN, MT, STAGES>, p, sc);
+    CB200_COUNT_LAUNCH();
+    if (e != cudaSuccess) {
+        cb200_set_error("%s: persistent cluster launch failed: %s", name, cudaGetErrorString(e));
+        return (int)e;
+    }
+    CB200_CHECK_LAUNCH(name);
+    return CB200_OK;
+}
+
+// 0 = off, 1 = persistent CTA-pair kernels where the shape allows (env CB200_TAPGEMM_PERSIST)
+int persist_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CB200_TAPGEMM_PERSIST");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
 // 0 = single-CTA tiles only, 1 = CTA pairs where the shape allows (default); env CB200_TAPGEMM_PAIR overrides.
 int pair_mode() {
     static int mode = -1;
@@ -466,6 +735,7 @@ int pair_mode() {
 // Rows of the weight matrix one CTA stages per k-block for an (N, m_tiles) problem - the B tensor map's box must
 // be encoded with exactly this many rows.  Mirrors the kernel choice made in dispatch().
 int b_box_rows(int N, int m_tiles) {
+    if (persist_mode() && m_tiles >= 64 && N % 64 == 0) return (N % 256 == 0) ? 128 : (N % 128 == 0 ? 64 : 32);
     if (pair_mode() && m_tiles >= 296) {
         if (N % 256 == 0) return 128;      // pair, BN = 256: half per CTA
         if (N % 128 == 0) return 64;       // pair, BN = 128
@@ -473,7 +743,23 @@ int b_box_rows(int N, int m_tiles) {
     return (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
 }
 
-int dispatch(const TapGemmParams& p, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
+int debug_flags() {
+    static int flags = -1;
+    if (flags < 0) {
+        const char* e = getenv("CB200_TAPGEMM_DEBUG");
+        flags = e ? atoi(e) : 0;
+    }
+    return flags;
+}
+
+int dispatch(const TapGemmParams& p_in, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
+    TapGemmParams p = p_in;
+    p.debug = debug_flags();
+    if (persist_mode() && m_tiles >= 64 && N % 64 == 0) {
+        if (N % 256 == 0) return launch_persist<256, 1, 5>(p, m_tiles, N / 256, classes, st, name);   // 5 x 32 KB stages
+        if (N % 128 == 0) return launch_persist<128, 2, 4>(p, m_tiles, N / 128, classes, st, name);   // 4 x 40 KB stages
+        return launch_persist<64, 4, 3>(p, m_tiles, N / 64, classes, st, name);                        // 3 x 68 KB stages
+    }
     if (pair_mode() && m_tiles >= 296) {
         if (N % 256 == 0) return launch2<256, 4>(p, m_tiles, N / 256, classes, st, name);     // 32 KB / stage / CTA
         if (N % 128 == 0) return launch2<128, 4>(p, m_tiles, N / 128, classes, st, name);     // 24 KB / stage / CTA

@@ -140,9 +140,13 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         } else if (warp >= 4) {
+            // Each thread receives one accumulator ROW (co) from TMEM; the 32x32 block of a warp is transposed through
+            // shared memory (stage-0 buffer, idle once tmem_full fired) so that 8 lanes issue one contiguous 128-byte
+            // vector reduction (red.global.add.v4.f32) instead of 32 scattered scalar atomics per row.
             const int q = warp & 3;
-            const int co = co0 + q * 32 + lane;
-            float* drow = p.dw + (long long)co * p.ldw + (long long)tap_id * (p.cin_tiles * BN) + ci0;
+            float* st = reinterpret_cast<float*>(smem) + q * (32 * 36);
+            const int sub = lane >> 3, col4 = (lane & 7) * 4;
+            float* dbase = p.dw + (long long)(co0 + q * 32) * p.ldw + (long long)tap_id * (p.cin_tiles * BN) + ci0;
             tc::mbar_wait(tmem_full_bar, 0);
             tc::fence_after_sync();
 #pragma unroll 1
@@ -151,7 +155,18 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
                 tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(st + lane * 36 + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = it * 4 + sub;
+                    const float4 o = *reinterpret_cast<const float4*>(st + row * 36 + col4);
+                    atomicAdd(reinterpret_cast<float4*>(dbase + (long long)row * p.ldw + c0 + col4), o);
+                }
+                __syncwarp();
             }
         }
     }

