@@ -68,11 +68,19 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = None
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (raw C accessor: ~1 us instead of ~18 us)."""
+    global _raw_stream
     import torch
-    if not torch.cuda.is_available():
-        raise CB200Error("contrad_b200 kernels need a CUDA device; there is no CPU path")
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if _raw_stream is None:
+        if not torch.cuda.is_available():
+            raise CB200Error("contrad_b200 kernels need a CUDA device; there is no CPU path")
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (
+            lambda dev: torch.cuda.current_stream(dev).cuda_stream)
+    return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
 
 
 def i32(v):

@@ -14,6 +14,29 @@ from ..functional import AugmentSimCLRFn
 _N_FIELDS = 11   # sx, sy, bx, by, flip, cj_on, contrast, hue, sat, val, gray_on
 
 
+class _PinnedRing(object):
+    """Small ring of pinned host buffers so that per-step host->device parameter copies are truly asynchronous
+    (a pageable `.to(device)` blocks the host until the stream drains - measured 2.4 ms/step)."""
+
+    def __init__(self, slots=8):
+        self.slots, self.bufs, self.i = slots, {}, 0
+
+    def stage(self, cpu_tensor, device):
+        if device.type != "cuda":
+            return cpu_tensor.to(device)
+        key = (tuple(cpu_tensor.shape), cpu_tensor.dtype)
+        ring = self.bufs.get(key)
+        if ring is None:
+            ring = self.bufs[key] = [torch.empty(cpu_tensor.shape, dtype=cpu_tensor.dtype).pin_memory() for _ in range(self.slots)]
+        self.i = (self.i + 1) % self.slots
+        buf = ring[self.i]
+        buf.copy_(cpu_tensor)
+        return buf.to(device, non_blocking=True)
+
+
+_RING = _PinnedRing()
+
+
 def _identity_block(batch, device):
     p = torch.zeros(_N_FIELDS, batch, device=device)
     p[0] = 1.0; p[1] = 1.0; p[4] = 1.0; p[6] = 1.0; p[8] = 1.0; p[9] = 1.0
@@ -63,7 +86,7 @@ class RandomResizeCropLayer(nn.Module):
 
     def forward(self, inputs):
         p = _identity_block(inputs.shape[0], inputs.device)
-        p[0:4] = self.sample(inputs).to(inputs.device, non_blocking=True)
+        p[0:4] = _RING.stage(self.sample(inputs), inputs.device)
         return AugmentSimCLRFn.apply(inputs, p, 0)
 
 
@@ -189,7 +212,7 @@ class FusedSimCLR(nn.Sequential):
         rrc, flip, apply_cj, apply_gray = self[0], self[1], self[2], self[3]
         n, dev = inputs.shape[0], inputs.device
         p = torch.empty(_N_FIELDS, n, device=dev)
-        p[0:4] = rrc.sample(inputs).to(dev, non_blocking=True)
+        p[0:4] = _RING.stage(rrc.sample(inputs), dev)
         p[4] = flip.sample(inputs)
         p[5] = apply_cj.sample(inputs)
         order, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs)

@@ -22,36 +22,43 @@
 namespace {
 
 constexpr int kTileM = 128;     // Cout rows per CTA
-constexpr int kKP = 64;         // pixels per pipeline stage (8 MMAs of K = 8)
-constexpr int kChunkBytes = kKP * 128;   // one [KP x 32 fp32] box
 constexpr int kThreads = 256;
 constexpr int kMaxTaps = 16;
 
 struct WgradParams {
     CUtensorMap tmap_dy;      // (Cout, d1..d4)
     CUtensorMap tmap_x;       // (C,    d1..d4)
-    int box[4];               // pixel box along dims 1..4 (product == kKP)
+    int box[4];               // pixel box along dims 1..4 (product == KP)
     int tiles[4];             // pixel-tile counts along dims 1..4
     int tap[kMaxTaps][5];     // {c_add, d1, d2, d3, d4} offsets applied to the X box
     int ntaps;
     int cin_tiles;            // Cin / BN
+    int total_btiles;         // ntaps * cin_tiles  ("B tiles": one (tap, Cin tile) each)
     int total_ptiles;         // product of tiles[]
     int ptiles_per_split;
     int ldw;                  // floats per dW_hat row (= ntaps * Cin for convs)
     float* dw;
 };
 
-template <int BN, int STAGES>
+// One pipeline stage = the dY box (128 channels x KP pixels) + NB X boxes (BN channels x KP pixels) that SHARE it:
+// NB (tap, Cin-tile) products accumulate into NB*BN TMEM columns, so the dY bytes are amortised over NB MMAs.
+template <int BN, int NB, int KP, int STAGES>
 struct WgSmem {
-    static constexpr int kStageBytes = (kTileM / 32 + BN / 32) * kChunkBytes;
+    static constexpr int kChunkBytes = KP * 128;                      // one [KP x 32 fp32] box
+    static constexpr int kABytes = (kTileM / 32) * kChunkBytes;
+    static constexpr int kBBytes = (BN / 32) * kChunkBytes;
+    static constexpr int kStageBytes = kABytes + NB * kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static constexpr int kTmemCols = (NB * BN <= 32) ? 32 : (NB * BN <= 64) ? 64 : (NB * BN <= 128) ? 128 : (NB * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, int STAGES>
+template <int BN, int NB, int KP, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ WgradParams p) {
-    using L = WgSmem<BN, STAGES>;
+    using L = WgSmem<BN, NB, KP, STAGES>;
+    static_assert(NB * BN <= 512, "accumulators exceed TMEM");
+    static_assert(L::kStageBytes >= 4 * 32 * 36 * 4, "stage 0 doubles as the epilogue staging buffer");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -62,8 +69,8 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int split = blockIdx.x;
-    const int tap_id = blockIdx.y / p.cin_tiles;
-    const int ci0 = (blockIdx.y % p.cin_tiles) * BN;
+    const int bt0 = blockIdx.y * NB;                       // first B tile of this CTA
+    const int nb = min(NB, p.total_btiles - bt0);          // valid B tiles (>= 1)
     const int co0 = blockIdx.z * kTileM;
     const int pt_begin = split * p.ptiles_per_split;
     const int pt_end = min(p.total_ptiles, pt_begin + p.ptiles_per_split);
@@ -81,7 +88,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         tc::mbar_init(tmem_full_bar, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 2) tc::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    if (warp == 2) tc::tmem_alloc(tmem_slot, L::kTmemCols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -92,7 +99,6 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
             if (tc::elect_one()) {
                 int stage = 0;
                 uint32_t phase = 0;
-                const int* tp = p.tap[tap_id];
                 for (int kb = 0; kb < num_kb; ++kb) {
                     int t = pt_begin + kb;
                     int c[4];
@@ -103,16 +109,26 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
                     }
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::kStageBytes;
-                    uint8_t* sb = sa + (kTileM / 32) * kChunkBytes;
-                    tc::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+                    tc::mbar_expect_tx(&full_bar[stage], L::kABytes + nb * L::kBBytes);
 #pragma unroll
                     for (int j = 0; j < kTileM / 32; ++j)
-                        tc::tma_load_5d(sa + j * kChunkBytes, &p.tmap_dy, &full_bar[stage], co0 + j * 32, c[0], c[1],
+                        tc::tma_load_5d(sa + j * L::kChunkBytes, &p.tmap_dy, &full_bar[stage], co0 + j * 32, c[0], c[1],
                                         c[2], c[3]);
 #pragma unroll
-                    for (int j = 0; j < BN / 32; ++j)
-                        tc::tma_load_5d(sb + j * kChunkBytes, &p.tmap_x, &full_bar[stage], ci0 + j * 32 + tp[0],
-                                        c[0] + tp[1], c[1] + tp[2], c[2] + tp[3], c[3] + tp[4]);
+                    for (int b = 0; b < NB; ++b) {
+                        if (b < nb) {
+                            const int bt = bt0 + b;
+                            const int tap_id = bt / p.cin_tiles;
+                            const int ci0 = (bt - tap_id * p.cin_tiles) * BN;
+                            const int* tp = p.tap[tap_id];
+                            uint8_t* sb = sa + L::kABytes + b * L::kBBytes;
+#pragma unroll
+                            for (int j = 0; j < BN / 32; ++j)
+                                tc::tma_load_5d(sb + j * L::kChunkBytes, &p.tmap_x, &full_bar[stage],
+                                                ci0 + j * 32 + tp[0], c[0] + tp[1], c[1] + tp[2], c[2] + tp[3],
+                                                c[3] + tp[4]);
+                        }
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -125,13 +141,18 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
                 tc::fence_after_sync();
                 if (tc::elect_one()) {
                     const uint32_t sa = tc::smem_u32(smem + stage * L::kStageBytes);
-                    const uint32_t sb = sa + (kTileM / 32) * kChunkBytes;
 #pragma unroll
-                    for (int g = 0; g < kKP / 8; ++g) {
-                        // MN-major TF32: LBO = stride between 32-element MN chunks, SBO = stride between 4-row K atoms
-                        const uint64_t adesc = tc::smem_desc_sw128_base32(sa + g * 1024, kChunkBytes, 512);
-                        const uint64_t bdesc = tc::smem_desc_sw128_base32(sb + g * 1024, kChunkBytes, 512);
-                        tc::mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | g) ? 1u : 0u);
+                    for (int b = 0; b < NB; ++b) {
+                        if (b < nb) {
+                            const uint32_t sb = sa + L::kABytes + b * L::kBBytes;
+#pragma unroll
+                            for (int g = 0; g < KP / 8; ++g) {
+                                // MN-major TF32: LBO = stride between 32-element MN chunks, SBO = between 4-row K atoms
+                                const uint64_t adesc = tc::smem_desc_sw128_base32(sa + g * 1024, L::kChunkBytes, 512);
+                                const uint64_t bdesc = tc::smem_desc_sw128_base32(sb + g * 1024, L::kChunkBytes, 512);
+                                tc::mma_tf32(tmem_base + b * BN, adesc, bdesc, idesc, (kb | g) ? 1u : 0u);
+                            }
+                        }
                     }
                     tc::mma_commit(&empty_bar[stage]);
                     if (kb == num_kb - 1) tc::mma_commit(tmem_full_bar);
@@ -146,27 +167,33 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
             const int q = warp & 3;
             float* st = reinterpret_cast<float*>(smem) + q * (32 * 36);
             const int sub = lane >> 3, col4 = (lane & 7) * 4;
-            float* dbase = p.dw + (long long)(co0 + q * 32) * p.ldw + (long long)tap_id * (p.cin_tiles * BN) + ci0;
             tc::mbar_wait(tmem_full_bar, 0);
             tc::fence_after_sync();
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-                tc::tmem_ld_wait();
+            for (int b = 0; b < nb; ++b) {
+                const int bt = bt0 + b;
+                const int tap_id = bt / p.cin_tiles;
+                const int ci0 = (bt - tap_id * p.cin_tiles) * BN;
+                float* dbase = p.dw + (long long)(co0 + q * 32) * p.ldw + (long long)tap_id * (p.cin_tiles * BN) + ci0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + c0, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(st + lane * 36 + j) =
-                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                    __uint_as_float(v[j + 3]));
-                __syncwarp();
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(st + lane * 36 + j) =
+                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                        __uint_as_float(v[j + 3]));
+                    __syncwarp();
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int row = it * 4 + sub;
-                    const float4 o = *reinterpret_cast<const float4*>(st + row * 36 + col4);
-                    atomicAdd(reinterpret_cast<float4*>(dbase + (long long)row * p.ldw + c0 + col4), o);
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + sub;
+                        const float4 o = *reinterpret_cast<const float4*>(st + row * 36 + col4);
+                        atomicAdd(reinterpret_cast<float4*>(dbase + (long long)row * p.ldw + c0 + col4), o);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     }
@@ -174,7 +201,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     __syncthreads();
     if (warp == 2) {
         tc::fence_after_sync();
-        tc::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+        tc::tmem_dealloc(tmem_base, L::kTmemCols);
     }
 }
 
@@ -215,21 +242,20 @@ int encode5(CUtensorMap* m, const void* ptr, const uint64_t* dims, const uint64_
     return CB200_OK;
 }
 
-// split kKP pixels over (w, h, b), w fastest
-void pick_pixel_box(int Wo, int Ho, int* wt, int* ht, int* bt) {
-    *wt = Wo < kKP ? Wo : kKP;
-    int rest = kKP / *wt;
+// split KP pixels over (w, h, b), w fastest
+void pick_pixel_box(int KP, int Wo, int Ho, int* wt, int* ht, int* bt) {
+    *wt = Wo < KP ? Wo : KP;
+    int rest = KP / *wt;
     *ht = Ho < rest ? Ho : rest;
     *bt = rest / *ht;
 }
 
-template <int BN>
-int launch_wgrad(WgradParams& p, int Cout, int Cin, int sm_count, cudaStream_t st, const char* name) {
-    constexpr int STAGES = (BN == 128) ? 3 : 4;
-    using L = WgSmem<BN, STAGES>;
+template <int BN, int NB, int KP, int STAGES>
+int launch_wgrad(WgradParams& p, int Cout, int sm_count, cudaStream_t st, const char* name) {
+    using L = WgSmem<BN, NB, KP, STAGES>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, NB, KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::kTotal);
         if (e != cudaSuccess) {
             cb200_set_error("%s: cudaFuncSetAttribute(smem=%d): %s", name, L::kTotal, cudaGetErrorString(e));
@@ -237,17 +263,19 @@ int launch_wgrad(WgradParams& p, int Cout, int Cin, int sm_count, cudaStream_t s
         }
         configured = true;
     }
-    p.cin_tiles = Cin / BN;
-    const int out_tiles = (Cout / kTileM) * p.ntaps * p.cin_tiles;
-    int splits = (2 * sm_count + out_tiles - 1) / out_tiles;
+    const int groups = (p.total_btiles + NB - 1) / NB;
+    const int out_tiles = (Cout / kTileM) * groups;
+    // split the pixel range so that the grid is (a little under) a whole number of waves of one CTA per SM
+    int waves = (out_tiles + sm_count - 1) / sm_count;
+    int splits = (waves * sm_count) / out_tiles;
     int max_splits = (p.total_ptiles + 7) / 8;          // at least 8 pipeline stages of work per CTA
     if (max_splits < 1) max_splits = 1;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.ptiles_per_split = (p.total_ptiles + splits - 1) / splits;
     splits = (p.total_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
-    dim3 grid(splits, p.ntaps * p.cin_tiles, Cout / kTileM);
-    wgrad_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, st>>>(p);
+    dim3 grid(splits, groups, Cout / kTileM);
+    wgrad_kernel<BN, NB, KP, STAGES><<<grid, kThreads, L::kTotal, st>>>(p);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH(name);
     return CB200_OK;
@@ -281,7 +309,8 @@ extern "C" int cb200_conv2d_nhwc_wgrad(const float* x, const float* dy, float* d
     WgradParams p;
     memset(&p, 0, sizeof(p));
     int wt, ht, bt;
-    pick_pixel_box(Wo, Ho, &wt, &ht, &bt);
+    constexpr int KP = 32;                     // pixels per pipeline stage (4 MMAs of K = 8 per B tile)
+    pick_pixel_box(KP, Wo, Ho, &wt, &ht, &bt);
     const int ntaps = ks * ks;
     {
         uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B, 1};
@@ -333,9 +362,18 @@ extern "C" int cb200_conv2d_nhwc_wgrad(const float* x, const float* dy, float* d
     cudaError_t e = cudaMemsetAsync(dw_hat, 0, sizeof(float) * (size_t)Cout * ntaps * Cin, st);
     if (e != cudaSuccess) { cb200_set_error("conv2d_nhwc_wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
     const int sms = sm_count_cached();
-    if (Cin % 128 == 0) return launch_wgrad<128>(p, Cout, Cin, sms, st, "conv2d_nhwc_wgrad");
-    if (Cin % 64 == 0) return launch_wgrad<64>(p, Cout, Cin, sms, st, "conv2d_nhwc_wgrad");
-    return launch_wgrad<32>(p, Cout, Cin, sms, st, "conv2d_nhwc_wgrad");
+    const char* name = "conv2d_nhwc_wgrad";
+    if (Cin % 128 == 0) {
+        p.cin_tiles = Cin / 128; p.total_btiles = ntaps * p.cin_tiles;
+        if (ks == 3) return launch_wgrad<128, 3, KP, 3>(p, Cout, sms, st, name);     // 64 KB / stage: dY shared by 3 taps
+        return launch_wgrad<128, 2, KP, 4>(p, Cout, sms, st, name);                   // 48 KB / stage
+    }
+    if (Cin % 64 == 0) {
+        p.cin_tiles = Cin / 64; p.total_btiles = ntaps * p.cin_tiles;
+        return launch_wgrad<64, 4, KP, 4>(p, Cout, sms, st, name);                    // 48 KB / stage
+    }
+    p.cin_tiles = Cin / 32; p.total_btiles = ntaps * p.cin_tiles;
+    return launch_wgrad<32, 4, KP, 4>(p, Cout, sms, st, name);
 }
 
 // dw[N, K] (row stride ldw) = dy[M, N]^T (row stride ldy) * x[M, K] (row stride ldx)   -- linear-layer weight gradient.
@@ -350,6 +388,7 @@ extern "C" int cb200_gemm_tn_wgrad(const float* dy, long long ldy, const float* 
                       reinterpret_cast<uintptr_t>(dw)) & 15) == 0, "gemm_tn_wgrad: pointers must be 16-byte aligned");
     WgradParams p;
     memset(&p, 0, sizeof(p));
+    constexpr int kKP = 32;
     {
         uint64_t dims[5] = {(uint64_t)N, (uint64_t)M, 1, 1, 1};
         uint64_t str[5] = {4, (uint64_t)ldy * 4, (uint64_t)ldy * 4 * M, (uint64_t)ldy * 4 * M, (uint64_t)ldy * 4 * M};
@@ -371,7 +410,15 @@ extern "C" int cb200_gemm_tn_wgrad(const float* dy, long long ldy, const float* 
     cudaError_t e = cudaMemset2DAsync(dw, sizeof(float) * ldw, 0, sizeof(float) * K, N, st);
     if (e != cudaSuccess) { cb200_set_error("gemm_tn_wgrad: memset: %s", cudaGetErrorString(e)); return (int)e; }
     const int sms = sm_count_cached();
-    if (K % 128 == 0) return launch_wgrad<128>(p, N, K, sms, st, "gemm_tn_wgrad");
-    if (K % 64 == 0) return launch_wgrad<64>(p, N, K, sms, st, "gemm_tn_wgrad");
-    return launch_wgrad<32>(p, N, K, sms, st, "gemm_tn_wgrad");
+    const char* name = "gemm_tn_wgrad";
+    if (K % 128 == 0) {
+        p.cin_tiles = K / 128; p.total_btiles = p.cin_tiles;
+        return launch_wgrad<128, 3, kKP, 3>(p, N, sms, st, name);
+    }
+    if (K % 64 == 0) {
+        p.cin_tiles = K / 64; p.total_btiles = p.cin_tiles;
+        return launch_wgrad<64, 4, kKP, 4>(p, N, sms, st, name);
+    }
+    p.cin_tiles = K / 32; p.total_btiles = p.cin_tiles;
+    return launch_wgrad<32, 4, kKP, 4>(p, N, sms, st, name);
 }

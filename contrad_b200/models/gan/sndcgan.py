@@ -56,8 +56,18 @@ class G_SNDCGAN(nn.Module):
                                 c[9].weight, c[9].bias)
 
     def sample_latent(self, n_samples):
+        """models/gan/sndcgan.py:50-52: U(-1,1) drawn on the CPU generator (same stream as the reference), staged
+        through a ring of pinned buffers so the host->device copy does not block the host."""
         device = next(self.parameters()).device
-        return torch.empty(n_samples, self.nz).uniform_(-1, 1).to(device)
+        if device.type != "cuda":
+            return torch.empty(n_samples, self.nz).uniform_(-1, 1).to(device)
+        ring = self.__dict__.setdefault("_latent_ring", {})
+        key = (n_samples, self.nz)
+        if key not in ring:
+            ring[key] = [[torch.empty(n_samples, self.nz).pin_memory() for _ in range(8)], 0]
+        bufs, i = ring[key]
+        ring[key][1] = (i + 1) % len(bufs)
+        return bufs[i].uniform_(-1, 1).to(device, non_blocking=True)
 
     def reset_parameters(self):
         for m in self.modules():

@@ -58,6 +58,9 @@ for (B, H, Cin, Cout, ks, st) in layers:
     med, best = timeit(lambda: K.conv2d_nhwc_dgrad(dy, wt, (B, H, H, Cin), ks, st, act_in=x, slope=0.1, round_out=True))
     print("conv dgrad B=%d %dx%d %d->%d k%d s%d: %.3f ms  %.1f TFLOP/s" % (B, H, H, Cin, Cout, ks, st, med, flops / med / 1e9))
     out["conv_dgrad_%d_%d_%d" % (H, Cin, Cout)] = {"ms": med, "tflops": flops / med / 1e9}
+    med, best = timeit(lambda: K.conv2d_nhwc_wgrad(x, dy, ks, st))
+    print("conv wgrad B=%d %dx%d %d->%d k%d s%d: %.3f ms  %.1f TFLOP/s" % (B, H, H, Cin, Cout, ks, st, med, flops / med / 1e9))
+    out["conv_wgrad_%d_%d_%d" % (H, Cin, Cout)] = {"ms": med, "tflops": flops / med / 1e9}
     # cuDNN TF32 reference timing
     torch.backends.cudnn.allow_tf32 = True
     xc = x.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
@@ -68,5 +71,8 @@ for (B, H, Cin, Cout, ks, st) in layers:
 a = K.round_tf32(torch.randn(1536, 8192, device="cuda")); b = K.round_tf32(torch.randn(1536, 8192, device="cuda") * 0.02)
 med, _ = timeit(lambda: K.gemm_nt(a, b, None, slope=0.1))
 print("heads gemm 1536x1536x8192: %.3f ms %.1f TFLOP/s" % (med, 2 * 1536 * 1536 * 8192 / med / 1e9))
+dh = K.round_tf32(torch.randn(1536, 1536, device="cuda"))
+med, _ = timeit(lambda: K.gemm_tn_wgrad(dh, a))
+print("heads wgrad 1536x1536x8192: %.3f ms %.1f TFLOP/s" % (med, 2 * 1536 * 1536 * 8192 / med / 1e9))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/probe_r1a.json", "w"), indent=1)
