@@ -133,14 +133,6 @@ __device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float h
 
 __device__ __forceinline__ float clamp01(float x) { return __saturatef(x); }   // one FADD.SAT; NaN -> 0 like fmin(fmax())
 
-// Stage one [3,H,W] image into shared memory (coalesced float4, streaming).
-__device__ __forceinline__ void stage_image(const float* __restrict__ src, float* dst, int n_elems) {
-    for (int e = threadIdx.x * 4; e < n_elems; e += blockDim.x * 4) {
-        float4 v = ldg_stream4(src + e);
-        *reinterpret_cast<float4*>(dst + e) = v;
-    }
-}
-
 // Per-image tap tables in shared memory: column taps already include the horizontal flip.
 struct TapTables {
     int* xi0; int* xi1; float* xw0; float* xw1;     // [W]
@@ -195,84 +187,138 @@ __device__ __forceinline__ void gather_quad(const float* xs, int H, int W, int i
     }
 }
 
-template <int QPT>
+// ---- async staging: one cp.async.bulk (TMA bulk copy) moves a whole [3,H,W] image into shared memory ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; spin < (1u << 26) && !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+    if (!ok) __trap();
+}
+
+// Forward: PERSISTENT CTAs (grid = resident CTAs) walk the batch with a two-deep prefetch ring: while image i is
+// being processed, image i + gridDim.x is already in flight into the other shared-memory buffer (cp.async.bulk +
+// mbarrier), so global-load latency never sits on the critical path (it was 25 % of the stall samples of the
+// non-pipelined version, profiles/prof_r1_augment.md).  S != 0 bakes the image size into the code.
+template <int QPT, int S>
 __global__ void __launch_bounds__(kMaxThreads)
 augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
-                          int B, int H, int W, int order) {
-    extern __shared__ __align__(16) float smem[];
-    float* xs = smem;                      // [3*H*W]
-    float* red = smem + 3 * H * W;         // [3*32]
-    const TapTables taps = carve_taps(red + 96, H, W);
-    const int b = blockIdx.x;
+                          int B, int H_, int W_, int order) {
+    extern __shared__ __align__(128) float smem[];
+    const int H = S ? S : H_, W = S ? S : W_;
     const int HW = H * W, Wq = W >> 2, nquads = HW >> 2;
-    const SampleParams sp = load_params(params, B, b);
-    const float hshift = (sp.fh * 255.f) / 360.f;
-    stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);
-    fill_taps(taps, H, W, sp);
+    float* red = smem + 6 * HW;            // [3*32]
+    const TapTables taps = carve_taps(red + 96, H, W);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 96 + 4 * W + 4 * H);
+    const uint32_t img_bytes = (uint32_t)(3 * HW * sizeof(float));
+
+    if (threadIdx.x == 0) {
+        bar_init(&bars[0], 1);
+        bar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-
-    float v[QPT][3][4];
-    bool live[QPT];
-#pragma unroll
-    for (int q = 0; q < QPT; ++q) {
-        int quad = threadIdx.x + q * blockDim.x;
-        live[q] = quad < nquads;
-        if (live[q]) {
-            gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, taps, v[q]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[q][c][k] = 0.f;
-        }
+    int b = blockIdx.x;
+    if (threadIdx.x == 0 && b < B) {
+        bar_expect_tx(&bars[0], img_bytes);
+        bulk_load(smem, x + (size_t)b * 3 * HW, img_bytes, &bars[0]);
     }
+    for (int it = 0; b < B; b += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int nb = b + gridDim.x;
+        if (threadIdx.x == 0 && nb < B) {          // prefetch the next image of this CTA into the other buffer
+            bar_expect_tx(&bars[buf ^ 1], img_bytes);
+            bulk_load(smem + (buf ^ 1) * 3 * HW, x + (size_t)nb * 3 * HW, img_bytes, &bars[buf ^ 1]);
+        }
+        const SampleParams sp = load_params(params, B, b);
+        const float hshift = (sp.fh * 255.f) / 360.f;
+        fill_taps(taps, H, W, sp);
+        bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
+        __syncthreads();
+        const float* xs = smem + buf * 3 * HW;
 
-    if (sp.cj_on != 0.f) {          // uniform across the CTA (one image per CTA)
-        if (order == 1) {
+        float v[QPT][3][4];
+        bool live[QPT];
 #pragma unroll
-            for (int q = 0; q < QPT; ++q)
+        for (int q = 0; q < QPT; ++q) {
+            int quad = threadIdx.x + q * blockDim.x;
+            live[q] = quad < nquads;
+            if (live[q]) {
+                gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, taps, v[q]);
+            } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], hshift, sp.fs, sp.fv);
-        }
-        float sums[3] = {0.f, 0.f, 0.f};
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int q = 0; q < QPT; ++q)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sums[c] += (v[q][c][0] + v[q][c][1]) + (v[q][c][2] + v[q][c][3]);
-        block_sum<3>(sums, red);
-        const float inv = 1.f / (float)HW;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float m = sums[c] * inv;
-#pragma unroll
-            for (int q = 0; q < QPT; ++q)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) v[q][c][k] = clamp01((v[q][c][k] - m) * sp.fc + m);
-        }
-        if (order == 0) {
-#pragma unroll
-            for (int q = 0; q < QPT; ++q)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], hshift, sp.fs, sp.fv);
-        }
-    }
-    float* yb = y + (size_t)b * 3 * HW;
-#pragma unroll
-    for (int q = 0; q < QPT; ++q) {
-        if (!live[q]) continue;
-        int quad = threadIdx.x + q * blockDim.x;
-        if (sp.gray_on != 0.f) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float l = 0.299f * v[q][0][k] + 0.587f * v[q][1][k] + 0.114f * v[q][2][k];
-                v[q][0][k] = l; v[q][1][k] = l; v[q][2][k] = l;
+                    for (int k = 0; k < 4; ++k) v[q][c][k] = 0.f;
             }
         }
+
+        if (sp.cj_on != 0.f) {          // uniform across the CTA (one image per CTA iteration)
+            if (order == 1) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-            stg_stream4(yb + c * HW + quad * 4, make_float4(v[q][c][0], v[q][c][1], v[q][c][2], v[q][c][3]));
+                for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], hshift, sp.fs, sp.fv);
+            }
+            float sums[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sums[c] += (v[q][c][0] + v[q][c][1]) + (v[q][c][2] + v[q][c][3]);
+            block_sum<3>(sums, red);
+            const float inv = 1.f / (float)HW;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float m = sums[c] * inv;
+#pragma unroll
+                for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[q][c][k] = clamp01((v[q][c][k] - m) * sp.fc + m);
+            }
+            if (order == 0) {
+#pragma unroll
+                for (int q = 0; q < QPT; ++q)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (live[q]) hsv_jitter(v[q][0][k], v[q][1][k], v[q][2][k], hshift, sp.fs, sp.fv);
+            }
+        }
+        float* yb = y + (size_t)b * 3 * HW;
+#pragma unroll
+        for (int q = 0; q < QPT; ++q) {
+            if (!live[q]) continue;
+            int quad = threadIdx.x + q * blockDim.x;
+            if (sp.gray_on != 0.f) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float l = 0.299f * v[q][0][k] + 0.587f * v[q][1][k] + 0.114f * v[q][2][k];
+                    v[q][0][k] = l; v[q][1][k] = l; v[q][2][k] = l;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                stg_stream4(yb + c * HW + quad * 4, make_float4(v[q][c][0], v[q][c][1], v[q][c][2], v[q][c][3]));
+        }
+        __syncthreads();      // tap tables / reduction scratch / this image buffer are reused by the next iteration
     }
 }
 
@@ -280,16 +326,22 @@ template <int QPT>
 __global__ void __launch_bounds__(kMaxThreads)
 augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
                           const float* __restrict__ params, int B, int H, int W, int order) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int HW = H * W, Wq = W >> 2, nquads = HW >> 2;
     float* xs = smem;                  // [3*HW] forward image
     float* gs = smem + 3 * HW;         // [3*HW] dx accumulator
     float* red = smem + 6 * HW;        // [3*32]
     const TapTables taps = carve_taps(red + 96, H, W);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 96 + 4 * W + 4 * H);
     const int b = blockIdx.x;
     const SampleParams sp = load_params(params, B, b);
     const float hshift = (sp.fh * 255.f) / 360.f;
-    if (sp.cj_on != 0.f) stage_image(x + (size_t)b * 3 * HW, xs, 3 * HW);   // x only feeds the clamp mask
+    if (sp.cj_on != 0.f && threadIdx.x == 0) {     // x only feeds the clamp mask; one async bulk copy stages it
+        bar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        bar_expect_tx(bar, (uint32_t)(3 * HW * sizeof(float)));
+        bulk_load(xs, x + (size_t)b * 3 * HW, (uint32_t)(3 * HW * sizeof(float)), bar);
+    }
     for (int e = threadIdx.x * 4; e < 3 * HW; e += blockDim.x * 4)
         *reinterpret_cast<float4*>(gs + e) = make_float4(0.f, 0.f, 0.f, 0.f);
     fill_taps(taps, H, W, sp);
@@ -322,6 +374,7 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
         }
     }
     if (sp.cj_on != 0.f) {
+        bar_wait(bar, 0);     // barrier init by thread 0 is ordered before this by the __syncthreads above
 #pragma unroll
         for (int q = 0; q < QPT; ++q) {
             if (!live[q]) continue;
@@ -420,14 +473,26 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
     LaunchShape ls;
     CB200_CHECK_ARG(pick_shape(H, W, &ls),
                     "augment_fwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
-    size_t smem = (size_t)(3 * H * W + 96 + 4 * W + 4 * H) * sizeof(float);
+    size_t smem = (size_t)(6 * H * W + 96 + 4 * W + 4 * H) * sizeof(float) + 2 * sizeof(uint64_t);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define LAUNCH_FWD(Q)                                                                                          \
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    int per_sm = (int)((200 * 1024) / smem);           // resident CTAs per SM by shared memory (<= 8 by threads)
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = B < sm_count * per_sm ? B : sm_count * per_sm;
+#define LAUNCH_FWD(Q, SZ)                                                                                      \
     do {                                                                                                       \
-        cudaFuncSetAttribute(augment_simclr_fwd_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        augment_simclr_fwd_kernel<Q><<<B, ls.threads, smem, st>>>(x, y, params, B, H, W, order);               \
+        cudaFuncSetAttribute(augment_simclr_fwd_kernel<Q, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        augment_simclr_fwd_kernel<Q, SZ><<<grid, ls.threads, smem, st>>>(x, y, params, B, H, W, order);        \
     } while (0)
-    if (ls.qpt == 1) LAUNCH_FWD(1); else if (ls.qpt == 2) LAUNCH_FWD(2); else LAUNCH_FWD(4);
+    if (H == 32 && W == 32) LAUNCH_FWD(1, 32);
+    else if (ls.qpt == 1) LAUNCH_FWD(1, 0); else if (ls.qpt == 2) LAUNCH_FWD(2, 0); else LAUNCH_FWD(4, 0);
 #undef LAUNCH_FWD
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("augment_simclr_fwd");
@@ -444,7 +509,7 @@ extern "C" int cb200_augment_simclr_bwd(const float* x, const float* dy, float* 
     LaunchShape ls;
     CB200_CHECK_ARG(pick_shape(H, W, &ls),
                     "augment_bwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
-    size_t smem = (size_t)(6 * H * W + 96 + 4 * W + 4 * H) * sizeof(float);
+    size_t smem = (size_t)(6 * H * W + 96 + 4 * W + 4 * H) * sizeof(float) + 2 * sizeof(uint64_t);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LAUNCH_BWD(Q)                                                                                          \
     do {                                                                                                       \

@@ -92,6 +92,48 @@ bn_apply_relu_kernel(const float* __restrict__ x, const float* __restrict__ stat
     y[i] = round_out ? round_tf32(v) : v;
 }
 
+// float4 fast path of bn_apply_relu for the plain NHWC case (C % 4 == 0, no remap): 4 channels per thread.
+__global__ void __launch_bounds__(kT)
+bn_apply_relu_vec4_kernel(const float4* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float4* __restrict__ y, long long total4, int C, int round_out) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i >= total4) return;
+    const int f = (int)((i * 4) % C);
+    const float4 v = x[i];
+    const float4 mu = *reinterpret_cast<const float4*>(stats + f);
+    const float4 rs = *reinterpret_cast<const float4*>(stats + C + f);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + f);
+    const float4 b = *reinterpret_cast<const float4*>(beta + f);
+    float4 o;
+    o.x = fmaxf((v.x - mu.x) * rs.x * g.x + b.x, 0.f); o.y = fmaxf((v.y - mu.y) * rs.y * g.y + b.y, 0.f);
+    o.z = fmaxf((v.z - mu.z) * rs.z * g.z + b.z, 0.f); o.w = fmaxf((v.w - mu.w) * rs.w * g.w + b.w, 0.f);
+    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    y[i] = o;
+}
+
+// float4 fast path of bn_bwd_apply (C % 4 == 0, no remap)
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_vec4_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, const float4* __restrict__ x,
+                         const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ sums,
+                         float inv_count, float4* __restrict__ dx, long long total4, int C, int round_out) {
+    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
+    if (i >= total4) return;
+    const int f = (int)((i * 4) % C);
+    const float4 gy = dy[i], yy = y[i], xx = x[i];
+    const float4 mu = *reinterpret_cast<const float4*>(stats + f);
+    const float4 rs = *reinterpret_cast<const float4*>(stats + C + f);
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + f);
+    const float4 s0 = *reinterpret_cast<const float4*>(sums + f);
+    const float4 s1 = *reinterpret_cast<const float4*>(sums + C + f);
+    float4 o;
+    o.x = gm.x * rs.x * ((yy.x > 0.f ? gy.x : 0.f) - s0.x * inv_count - (xx.x - mu.x) * rs.x * s1.x * inv_count);
+    o.y = gm.y * rs.y * ((yy.y > 0.f ? gy.y : 0.f) - s0.y * inv_count - (xx.y - mu.y) * rs.y * s1.y * inv_count);
+    o.z = gm.z * rs.z * ((yy.z > 0.f ? gy.z : 0.f) - s0.z * inv_count - (xx.z - mu.z) * rs.z * s1.z * inv_count);
+    o.w = gm.w * rs.w * ((yy.w > 0.f ? gy.w : 0.f) - s0.w * inv_count - (xx.w - mu.w) * rs.w * s1.w * inv_count);
+    if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    dx[i] = o;
+}
+
 // sums[0][f] += sum dz, sums[1][f] += sum dz * xhat, with dz = dy * 1[y > 0]   (same indexing as above)
 __global__ void __launch_bounds__(kT)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
@@ -247,8 +289,15 @@ extern "C" int cb200_bn_apply_relu(const float* x, const float* stats, const flo
                                    int M, int C, int remap_s, int round_out, void* stream) {
     CB200_CHECK_ARG(M > 0 && C > 0 && (remap_s == 0 || C % remap_s == 0), "bn_apply_relu: bad shape");
     const long long total = (long long)M * C;
-    bn_apply_relu_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, stats, gamma, beta, y, total, C, remap_s, round_out);
+    const bool vec = remap_s == 0 && C % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(stats) |
+                       reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    if (vec)
+        bn_apply_relu_vec4_kernel<<<(unsigned)((total / 4 + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(x), stats, gamma, beta, reinterpret_cast<float4*>(y), total / 4, C, round_out);
+    else
+        bn_apply_relu_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, stats, gamma, beta, y, total, C, remap_s, round_out);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("bn_apply_relu");
     return CB200_OK;
@@ -275,8 +324,17 @@ extern "C" int cb200_bn_bwd_apply(const float* dy, const float* y, const float* 
                                   void* stream) {
     CB200_CHECK_ARG(M > 0 && C > 0 && count > 0.f, "bn_bwd_apply: bad shape");
     const long long total = (long long)M * C;
-    bn_bwd_apply_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
-        dy, y, x, stats, gamma, sums, count, dx, total, C, remap_s, round_out);
+    const bool vec = remap_s == 0 && C % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) |
+                       reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(stats) | reinterpret_cast<uintptr_t>(gamma) |
+                       reinterpret_cast<uintptr_t>(sums)) & 15) == 0;
+    if (vec)
+        bn_bwd_apply_vec4_kernel<<<(unsigned)((total / 4 + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x),
+            stats, gamma, sums, 1.f / count, reinterpret_cast<float4*>(dx), total / 4, C, round_out);
+    else
+        bn_bwd_apply_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            dy, y, x, stats, gamma, sums, count, dx, total, C, remap_s, round_out);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("bn_bwd_apply");
     return CB200_OK;

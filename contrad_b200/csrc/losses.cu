@@ -14,6 +14,7 @@
 // so TF32 rounding of the operands would be amplified 10x in the softmax.  At
 // N = 512 the two losses are 0.27 + 0.20 GFLOP forward - ~1e-4 of the step's FLOPs.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -317,29 +318,60 @@ gan_g_loss_kernel(const float* __restrict__ d_gen, long long stride, int N, int 
 }
 
 // ------------------------------------------------------------------------------------------ column sums
-// out[n] (+)= sum_m x[m, n]   x: [M, N] with row stride ld.  Threads: (256/cc) row lanes x cc columns.
+// out[n] (+)= sum_m x[m, n]   x: [M, N] with row stride ld.  Threads: (256/cc) row lanes x cc column-slots;
+// VEC = 4: every slot is a float4 (N and ld multiples of 4, 16-byte aligned base) -> 128-bit loads, 4 rows in flight.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, long long ld, int M, int N, int cc, int rows_per_cta, float* __restrict__ out) {
-    __shared__ float scratch[256];
+    __shared__ float scratch[VEC * 256];
     const int tx = threadIdx.x % cc, ty = threadIdx.x / cc, lanes = 256 / cc;
-    const int n = blockIdx.x * cc + tx;
+    const int n = (blockIdx.x * cc + tx) * VEC;
     const int m0 = blockIdx.y * rows_per_cta;
     const int m1 = min(M, m0 + rows_per_cta);
-    float a[1] = {0.f};
+    float a[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a[e] = 0.f;
     if (n < N) {
-        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float b1[VEC], b2[VEC], b3[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { b1[e] = 0.f; b2[e] = 0.f; b3[e] = 0.f; }
+        auto load = [&](int m, float (&acc)[VEC]) {
+            if (VEC == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(x + (long long)m * ld + n));
+                acc[0] += v.x; acc[1 % VEC] += v.y; acc[2 % VEC] += v.z; acc[3 % VEC] += v.w;
+            } else {
+                acc[0] += __ldg(x + (long long)m * ld + n);
+            }
+        };
         int m = m0 + ty;
         for (; m + 3 * lanes < m1; m += 4 * lanes) {          // 4 independent loads in flight
-            a[0] += __ldg(x + (long long)m * ld + n);
-            a1 += __ldg(x + (long long)(m + lanes) * ld + n);
-            a2 += __ldg(x + (long long)(m + 2 * lanes) * ld + n);
-            a3 += __ldg(x + (long long)(m + 3 * lanes) * ld + n);
+            load(m, a); load(m + lanes, b1); load(m + 2 * lanes, b2); load(m + 3 * lanes, b3);
         }
-        for (; m < m1; m += lanes) a[0] += __ldg(x + (long long)m * ld + n);
-        a[0] += (a1 + a2) + a3;
+        for (; m < m1; m += lanes) load(m, a);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] += (b1[e] + b2[e]) + b3[e];
     }
-    fold_row_lanes<1>(a, scratch, cc);
-    if (ty == 0 && n < N) atomicAdd(out + n, a[0]);
+    // fold the row lanes: inside a warp by shuffles (cc < 32), across warps through shared memory (<= 8 terms)
+    for (int o = 16; o >= cc; o >>= 1) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
+    }
+    const int span = cc < 32 ? 32 : cc, groups = 256 / span;      // one partial per (warp-group, column slot)
+    if (groups > 1) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) scratch[e * 256 + threadIdx.x] = a[e];
+        __syncthreads();
+        if ((int)threadIdx.x < cc) {
+            for (int r = 1; r < groups; ++r) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) a[e] += scratch[e * 256 + r * span + threadIdx.x];
+            }
+        }
+    }
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) atomicAdd(out + n + e, a[e]);
+    }
 }
 
 // out = dy * (act > 0 ? 1 : slope)   (LeakyReLU backward from the saved OUTPUT activation; slope > 0)
@@ -457,13 +489,24 @@ extern "C" int cb200_colsum(const float* x, long long ld, int M, int N, float* o
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, st);
     if (e != cudaSuccess) { cb200_set_error("colsum: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    static const bool vec_ok = []() { const char* e = getenv("CB200_COLSUM_VEC"); return !(e && e[0] == '0'); }();
+    const bool vec = vec_ok && (N % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int slots = vec ? N / 4 : N;
     int cc = 256;
-    while (cc > 32 && cc / 2 >= N) cc /= 2;                 // smallest power of two >= N, between 32 and 256
-    int row_chunks = (M + 255) / 256;
-    if (row_chunks > 1024) row_chunks = 1024;
+    while (cc > 8 && cc / 2 >= slots) cc /= 2;              // smallest power of two >= #slots, between 8 and 256
+    // rows per CTA: <= 512 for tall matrices; short-and-wide ones (heads, G linear) are cut finer so that the grid
+    // still fills the machine (~4 CTAs per SM) instead of a handful of CTAs walking all rows serially.
+    const int col_ctas = (slots + cc - 1) / cc;
+    int row_chunks = (M + 511) / 512;
+    const int want = (592 + col_ctas - 1) / col_ctas;
+    if (row_chunks < want) row_chunks = want;
+    const int min_rows = 256 / cc;                            // at least one row per row lane
+    if (row_chunks > (M + min_rows - 1) / min_rows) row_chunks = (M + min_rows - 1) / min_rows;
+    if (row_chunks > 2048) row_chunks = 2048;
     const int rows_per_cta = (M + row_chunks - 1) / row_chunks;
-    dim3 grid((N + cc - 1) / cc, (M + rows_per_cta - 1) / rows_per_cta);
-    colsum_kernel<<<grid, 256, 0, st>>>(x, ld, M, N, cc, rows_per_cta, out);
+    dim3 grid(col_ctas, (M + rows_per_cta - 1) / rows_per_cta);
+    if (vec) colsum_kernel<4><<<grid, 256, 0, st>>>(x, ld, M, N, cc, rows_per_cta, out);
+    else colsum_kernel<1><<<grid, 256, 0, st>>>(x, ld, M, N, cc, rows_per_cta, out);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("colsum");
     return CB200_OK;
