@@ -23,6 +23,7 @@
 // dx = f*dy' + (1-f)*mean(dy') with dy' = dy*1[0<=u<=1]; gray/blend are linear; the crop is the
 // transposed bilinear gather, accumulated with shared-memory atomics and written out once.
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 
 namespace {
@@ -322,6 +323,112 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
     }
 }
 
+// Forward, square S x S images with S a multiple of 32 (the CIFAR / 64x64 cases): COLUMN mapping.  Lane = output
+// column, each thread walks NPX = S*S/256 consecutive output rows.  The bilinear gather then reads, per warp
+// instruction, 32 (almost always distinct) columns of ONE source row: no shared-memory bank conflicts, where the
+// quad mapping above put four source rows - all hitting the same banks, row stride S floats = 0 mod 32 - into
+// each warp instruction (4-way conflicts on every gather; profiles/prof_r1_augment.md: l1tex 81 %, mio_throttle).
+// Column taps are loaded once per thread, row taps are one broadcast LDS.128 per row; stores are 128 B per warp.
+template <int S>
+__global__ void __launch_bounds__(kMaxThreads)
+augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
+                               int B, int order) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int HW = S * S, NPX = HW / kMaxThreads;
+    float* red = smem + 6 * HW;                                   // [3*32]
+    float4* xtap = reinterpret_cast<float4*>(red + 96);           // [S] {i0, i1 (int bits), w0, w1}, flip folded in
+    float4* ytap = xtap + S;                                      // [S] {i0*S, i1*S (int bits), w0, w1}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ytap + S);
+    constexpr uint32_t img_bytes = (uint32_t)(3 * HW * sizeof(float));
+    const int j = threadIdx.x % S, i_first = (threadIdx.x / S) * NPX;
+
+    if (threadIdx.x == 0) {
+        bar_init(&bars[0], 1);
+        bar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int b = blockIdx.x;
+    if (threadIdx.x == 0 && b < B) {
+        bar_expect_tx(&bars[0], img_bytes);
+        bulk_load(smem, x + (size_t)b * 3 * HW, img_bytes, &bars[0]);
+    }
+    for (int it = 0; b < B; b += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int nb = b + gridDim.x;
+        if (threadIdx.x == 0 && nb < B) {
+            bar_expect_tx(&bars[buf ^ 1], img_bytes);
+            bulk_load(smem + (buf ^ 1) * 3 * HW, x + (size_t)nb * 3 * HW, img_bytes, &bars[buf ^ 1]);
+        }
+        const SampleParams sp = load_params(params, B, b);
+        const float hshift = (sp.fh * 255.f) / 360.f;
+        if (threadIdx.x < 2 * S) {
+            const int e = threadIdx.x;
+            if (e < S) {
+                const Tap a = axis_tap((sp.flip < 0.f) ? (S - 1 - e) : e, S, sp.sx, sp.bx);
+                xtap[e] = make_float4(__int_as_float(a.i0), __int_as_float(a.i1), a.w0, a.w1);
+            } else {
+                const Tap a = axis_tap(e - S, S, sp.sy, sp.by);
+                ytap[e - S] = make_float4(__int_as_float(a.i0 * S), __int_as_float(a.i1 * S), a.w0, a.w1);
+            }
+        }
+        bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
+        __syncthreads();
+        const float* xs = smem + buf * 3 * HW;
+
+        float v[NPX][3];
+        {
+            const float4 tx = xtap[j];
+            const int x0 = __float_as_int(tx.x), x1 = __float_as_int(tx.y);
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float4 ty = ytap[i_first + m];
+                const float* r0 = xs + __float_as_int(ty.x);
+                const float* r1 = xs + __float_as_int(ty.y);
+                const float w00 = tx.z * ty.z, w01 = tx.w * ty.z, w10 = tx.z * ty.w, w11 = tx.w * ty.w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v[m][c] = r0[c * HW + x0] * w00 + r0[c * HW + x1] * w01 + r1[c * HW + x0] * w10 +
+                              r1[c * HW + x1] * w11;
+            }
+        }
+        if (sp.cj_on != 0.f) {          // uniform across the CTA
+            if (order == 1) {
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
+            }
+            float sums[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int m = 0; m < NPX; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sums[c] += v[m][c];
+            block_sum<3>(sums, red);
+            constexpr float inv = 1.f / (float)HW;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float mean = sums[c] * inv;
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) v[m][c] = clamp01((v[m][c] - mean) * sp.fc + mean);
+            }
+            if (order == 0) {
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
+            }
+        }
+        float* yb = y + (size_t)b * 3 * HW + i_first * S + j;
+#pragma unroll
+        for (int m = 0; m < NPX; ++m) {
+            if (sp.gray_on != 0.f) {
+                const float l = 0.299f * v[m][0] + 0.587f * v[m][1] + 0.114f * v[m][2];
+                v[m][0] = l; v[m][1] = l; v[m][2] = l;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, v[m][c]);
+        }
+        __syncthreads();      // tap tables / reduction scratch / this image buffer are reused by the next iteration
+    }
+}
+
 template <int QPT>
 __global__ void __launch_bounds__(kMaxThreads)
 augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
@@ -491,7 +598,16 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
         cudaFuncSetAttribute(augment_simclr_fwd_kernel<Q, SZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         augment_simclr_fwd_kernel<Q, SZ><<<grid, ls.threads, smem, st>>>(x, y, params, B, H, W, order);        \
     } while (0)
-    if (H == 32 && W == 32) LAUNCH_FWD(1, 32);
+    static const bool cols_ok = []() { const char* e = getenv("CB200_AUGMENT_COLS"); return !(e && e[0] == '0'); }();
+    if (cols_ok && H == W && (H == 32 || H == 64)) {
+        if (H == 32) {
+            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_cols_kernel<32><<<grid, kMaxThreads, smem, st>>>(x, y, params, B, order);
+        } else {
+            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_cols_kernel<64><<<grid, kMaxThreads, smem, st>>>(x, y, params, B, order);
+        }
+    } else if (H == 32 && W == 32) LAUNCH_FWD(1, 32);
     else if (ls.qpt == 1) LAUNCH_FWD(1, 0); else if (ls.qpt == 2) LAUNCH_FWD(2, 0); else LAUNCH_FWD(4, 0);
 #undef LAUNCH_FWD
     CB200_COUNT_LAUNCH();
