@@ -231,18 +231,30 @@ def build_world(args):
     opt_G = FusedAdam(G.parameters(), lr=OPTIONS["lr"], betas=OPTIONS["beta"])
     opt_D = FusedAdam(D.parameters(), lr=OPTIONS["lr_d"], betas=OPTIONS["beta"])
     P.augment_fn = get_augment(mode=P.aug).cuda()
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
+    if world > 1 and getattr(args, "no_graph", False):
+        from torch.nn.parallel import DistributedDataParallel as DDP          # the reference's wrapping (train_gan.py:311-313)
         G_w = DDP(G, device_ids=[local_rank], broadcast_buffers=False)
         G_w.sample_latent = G.sample_latent
         D_w = DDP(D, device_ids=[local_rank], broadcast_buffers=False)
     else:
+        if world > 1:       # graphed step: bare modules, DDP's start-up broadcast + gradient averaging done by the engine
+            from contrad_b200 import engine
+            engine.broadcast_parameters(G); engine.broadcast_parameters(D)
         G_w, D_w = G, D
     return SimpleNamespace(P=P, G=G_w, D=D_w, opt_G=opt_G, opt_D=opt_D, world=world, rank=rank, local_rank=local_rank)
 
 
+def _log(msg):
+    """Progress marker on stderr (rank-tagged): locates a hang without touching the JSON line on stdout."""
+    sys.stderr.write("[bench rank %s] %s\n" % (os.environ.get("RANK", "0"), msg))
+    sys.stderr.flush()
+
+
 def run_native(args):
+    import faulthandler
     from contrad_b200 import _capi, engine, kernels as K
+    # a hung collective / capture must not burn the whole time limit: dump every thread's stack and exit
+    faulthandler.dump_traceback_later(int(os.environ.get("CB200_BENCH_WATCHDOG", "900")), exit=True)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback (use --impl reference)")
     W = build_world(args)
@@ -258,9 +270,19 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(images):
+    def eager_step(images):
         step_no[0] += 1
         return engine.train_step(W.P, OPTIONS, train_fn, (W.G, W.D), (W.opt_G, W.opt_D), images, step_no[0])
+
+    if args.no_graph:
+        one_step = eager_step
+    else:
+        # the public fast loop: the same train_step captured once into a CUDA graph and replayed (engine.py)
+        graphed = engine.GraphedTrainStep(W.P, OPTIONS, train_fn, (W.G, W.D), (W.opt_G, W.opt_D))
+
+        def one_step(images):
+            step_no[0] += 1
+            return graphed(images, step_no[0])
 
     gen = torch.Generator(device=dev).manual_seed(rank)
     pool = [torch.rand(n_local, 3, 32, 32, device=dev, generator=gen) for _ in range(4)]
@@ -280,8 +302,16 @@ def run_native(args):
         return float(ms)
 
     # ---- device-resident arm
+    _log("world built; set-up steps")
+    if not args.no_graph:                         # untimed set-up: eager allocator warm-up steps + the capture
+        for w in range(graphed.eager_steps + 1):
+            one_step(pool[w % len(pool)])
+    torch.cuda.synchronize()
+    _log("set-up done (graph captured: %s); warm-up" % (not args.no_graph))
     for w in range(args.warmup):
         one_step(pool[w % len(pool)])
+    torch.cuda.synchronize()
+    _log("timed region")
     clocks = ClockSampler(W.local_rank if world > 1 else 0)
     if rank == 0:
         clocks.start()
@@ -291,6 +321,7 @@ def run_native(args):
     clk = clocks.stop() if rank == 0 else {}
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
 
+    _log("device-resident arm done: %.3f ms/step" % (ms / args.steps))
     # ---- end-to-end arm: pinned host images -> device every step + the reference's per-step loss read-backs
     host_pool = [torch.rand(n_local, 3, 32, 32).pin_memory() for _ in range(4)]
     d2h = [0]
@@ -307,10 +338,12 @@ def run_native(args):
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
 
+    _log("e2e arm done: %.3f ms/step" % (ms_e2e / args.steps))
+    faulthandler.cancel_dump_traceback_later()
     line = None
     if rank == 0:
         peaks = load_peaks()
-        roof = roofline_legs(K, engine, W, one_step, pool, peaks) if world == 1 else None
+        roof = roofline_legs(K, engine, W, eager_step, pool, peaks) if world == 1 else None
         cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": "train_step_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
@@ -318,6 +351,7 @@ def run_native(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "per_gpu_batch": n_local,
                        "parallelism": "dp%d" % world, "image": "3x32x32",
+                       "launch": "eager" if args.no_graph else "cuda-graph replay of the whole D+G step",
                        "l2": "per-step working set ~1.3 GB of activations >> 126 MB L2 (no explicit flush needed)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
@@ -329,12 +363,17 @@ def run_native(args):
             line.update(roof)
         if cpu:
             line["cpu_baseline"] = cpu
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    _log("teardown")
+    if not args.no_graph:
+        graphed.release()                          # graphs holding NCCL kernels must go before the communicator
+    torch.cuda.synchronize()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line))
+    _log("done")
     return 0
 
 
@@ -408,6 +447,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (and DDP wrappers for N > 1) instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -38,6 +38,8 @@ def lib():
         _lib.cb200_last_error.restype = ctypes.c_char_p
         _lib.cb200_launch_count.restype = ctypes.c_ulonglong
         _lib.cb200_reset_launch_count.restype = None
+        _lib.cb200_add_launch_count.restype = None
+        _lib.cb200_add_launch_count.argtypes = [ctypes.c_longlong]
     return _lib
 
 
@@ -57,6 +59,10 @@ def launch_count():
 
 def reset_launch_count():
     lib().cb200_reset_launch_count()
+
+
+def add_launch_count(n):
+    lib().cb200_add_launch_count(int(n))
 
 
 def ptr(t):

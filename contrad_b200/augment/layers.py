@@ -9,32 +9,18 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import staging
 from ..functional import AugmentSimCLRFn
 
 _N_FIELDS = 11   # sx, sy, bx, by, flip, cj_on, contrast, hue, sat, val, gray_on
 
 
-class _PinnedRing(object):
-    """Small ring of pinned host buffers so that per-step host->device parameter copies are truly asynchronous
-    (a pageable `.to(device)` blocks the host until the stream drains - measured 2.4 ms/step)."""
+class _ShapeOnly(object):
+    """Stand-in for a tensor where only `.shape` is consulted (host samplers captured by the staging recorder
+    must not keep a device tensor alive)."""
 
-    def __init__(self, slots=8):
-        self.slots, self.bufs, self.i = slots, {}, 0
-
-    def stage(self, cpu_tensor, device):
-        if device.type != "cuda":
-            return cpu_tensor.to(device)
-        key = (tuple(cpu_tensor.shape), cpu_tensor.dtype)
-        ring = self.bufs.get(key)
-        if ring is None:
-            ring = self.bufs[key] = [torch.empty(cpu_tensor.shape, dtype=cpu_tensor.dtype).pin_memory() for _ in range(self.slots)]
-        self.i = (self.i + 1) % self.slots
-        buf = ring[self.i]
-        buf.copy_(cpu_tensor)
-        return buf.to(device, non_blocking=True)
-
-
-_RING = _PinnedRing()
+    def __init__(self, shape):
+        self.shape = tuple(shape)
 
 
 def _identity_block(batch, device):
@@ -86,7 +72,8 @@ class RandomResizeCropLayer(nn.Module):
 
     def forward(self, inputs):
         p = _identity_block(inputs.shape[0], inputs.device)
-        p[0:4] = _RING.stage(self.sample(inputs), inputs.device)
+        shape = _ShapeOnly(inputs.shape)
+        p[0:4] = staging.stage(lambda: self.sample(shape), inputs.device)
         return AugmentSimCLRFn.apply(inputs, p, 0)
 
 
@@ -136,10 +123,16 @@ class ColorJitterLayer(nn.Module):
             value = None
         return value
 
-    def sample(self, inputs):
+    @staticmethod
+    def draw_order():
+        """color_jitter.py:65-70: one host draw per call decides [contrast, hsv] (0) or [hsv, contrast] (1)."""
+        return 0 if np.random.rand() > 0.5 else 1
+
+    def sample(self, inputs, order=None):
         """Returns (order, contrast, hue, sat, val) drawn like color_jitter.py:44-75."""
         n = inputs.size(0)
-        order = 0 if np.random.rand() > 0.5 else 1
+        if order is None:
+            order = self.draw_order()
 
         def draw_contrast():
             if self.contrast:
@@ -211,11 +204,21 @@ class FusedSimCLR(nn.Sequential):
     def sample_params(self, inputs):
         rrc, flip, apply_cj, apply_gray = self[0], self[1], self[2], self[3]
         n, dev = inputs.shape[0], inputs.device
-        p = torch.empty(_N_FIELDS, n, device=dev)
-        p[0:4] = _RING.stage(rrc.sample(inputs), dev)
+        shape = _ShapeOnly(inputs.shape)
+        recording = staging.recording()
+        p = torch.empty(_N_FIELDS + (1 if recording else 0), n, device=dev)
+        p[0:4] = staging.stage(lambda: rrc.sample(shape), dev, shape=(4, n))
         p[4] = flip.sample(inputs)
         p[5] = apply_cj.sample(inputs)
-        order, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs)
+        if recording:
+            # CUDA-graph capture: the jitter order must not be baked into the launch.  It is staged as a device
+            # scalar (row 11, kernel order = -1); the device draws keep the sequence of order 0 (i.i.d. draws, so
+            # the distribution is the reference's; only the pairing of draws to factors differs when order = 1).
+            p[11] = staging.stage(lambda: torch.tensor([float(apply_cj.fn.draw_order())]), dev, shape=(1,))
+            _, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs, order=0)
+            order = -1
+        else:
+            order, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs)
         p[10] = apply_gray.sample(inputs)
         return p, order
 

@@ -21,6 +21,7 @@ struct AdamBatch {
     int cta_begin[kMaxTensors + 1];
     int n;
     float lr, beta1, beta2, eps, bc1, bc2_sqrt;
+    const float* hyper;     // optional device-resident {lr, 1-b1^t, sqrt(1-b2^t)} overriding lr/bc1/bc2_sqrt
 };
 
 __global__ void __launch_bounds__(kT) adam_kernel(const __grid_constant__ AdamBatch a) {
@@ -33,7 +34,10 @@ __global__ void __launch_bounds__(kT) adam_kernel(const __grid_constant__ AdamBa
     const float* __restrict__ g = a.g[l];
     float* __restrict__ m = a.m[l];
     float* __restrict__ v = a.v[l];
-    const float step = a.lr / a.bc1;
+    const float lr = a.hyper ? __ldg(a.hyper + 0) : a.lr;
+    const float bc1 = a.hyper ? __ldg(a.hyper + 1) : a.bc1;
+    const float bc2_sqrt = a.hyper ? __ldg(a.hyper + 2) : a.bc2_sqrt;
+    const float step = lr / bc1;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const long long i = base + ((long long)it * kT + threadIdx.x) * 4;
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(kT) adam_kernel(const __grid_constant__ AdamBa
         for (int e = 0; e < 4; ++e) {
             mv[e] = a.beta1 * mv[e] + (1.f - a.beta1) * gv[e];
             vv[e] = a.beta2 * vv[e] + (1.f - a.beta2) * gv[e] * gv[e];
-            const float denom = sqrtf(vv[e]) / a.bc2_sqrt + a.eps;
+            const float denom = sqrtf(vv[e]) / bc2_sqrt + a.eps;
             pv[e] -= step * (mv[e] / denom);
         }
         if (vec) {
@@ -77,17 +81,14 @@ struct cb200_adam_tensor {
 };
 }
 
-// One Adam step (step count t >= 1 shared by all tensors) on n tensors; processed in chunks of 48 per launch.
-extern "C" int cb200_adam_step(const cb200_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
-                               int step, void* stream) {
-    CB200_CHECK_ARG(n > 0 && step >= 1, "adam_step: bad arguments");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float bc1 = 1.f - powf(beta1, (float)step);
-    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+namespace {
+int adam_launch(const cb200_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps, float bc1,
+                float bc2_sqrt, const float* hyper, cudaStream_t st) {
     for (int begin = 0; begin < n; begin += kMaxTensors) {
         AdamBatch a;
         a.n = (n - begin < kMaxTensors) ? (n - begin) : kMaxTensors;
         a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.bc1 = bc1; a.bc2_sqrt = bc2_sqrt;
+        a.hyper = hyper;
         int total = 0;
         for (int l = 0; l < a.n; ++l) {
             const cb200_adam_tensor& t = tensors[begin + l];
@@ -105,4 +106,22 @@ extern "C" int cb200_adam_step(const cb200_adam_tensor* tensors, int n, float lr
     }
     CB200_CHECK_LAUNCH("adam_step");
     return CB200_OK;
+}
+}  // namespace
+
+// One Adam step (step count t >= 1 shared by all tensors) on n tensors; processed in chunks of 48 per launch.
+extern "C" int cb200_adam_step(const cb200_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
+                               int step, void* stream) {
+    CB200_CHECK_ARG(n > 0 && step >= 1, "adam_step: bad arguments");
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    return adam_launch(tensors, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+// Same update with the step-dependent scalars {lr, 1 - beta1^t, sqrt(1 - beta2^t)} read from DEVICE memory
+// (`hyper`, 3 floats): nothing step-dependent is baked into the launch, so the call can live in a CUDA graph.
+extern "C" int cb200_adam_step_dev(const cb200_adam_tensor* tensors, int n, const float* hyper, float beta1,
+                                   float beta2, float eps, void* stream) {
+    CB200_CHECK_ARG(n > 0 && hyper != nullptr, "adam_step_dev: bad arguments");
+    return adam_launch(tensors, n, 0.f, beta1, beta2, eps, 1.f, 1.f, hyper, static_cast<cudaStream_t>(stream));
 }

@@ -50,6 +50,13 @@ __device__ __forceinline__ SampleParams load_params(const float* __restrict__ p,
     return s;
 }
 
+// Colour-jitter order (0: contrast then hsv, 1: hsv then contrast).  `order` >= 0 is the launch-wide value;
+// order < 0 reads it per image from row 11 of the parameter block (device-resident, so that a CUDA graph of the
+// train step can be replayed with a freshly drawn order).
+__device__ __forceinline__ int resolve_order(const float* __restrict__ p, int B, int b, int order) {
+    return order >= 0 ? order : (__ldg(p + 11 * B + b) != 0.f ? 1 : 0);
+}
+
 // grid_sample(padding_mode='reflection', align_corners=False): reflect about -0.5 and size-0.5,
 // clip to [0, size-1].
 // (fmod via floor: exact for power-of-two sizes; elsewhere the two branches agree at the reflection points.)
@@ -250,6 +257,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
             bulk_load(smem + (buf ^ 1) * 3 * HW, x + (size_t)nb * 3 * HW, img_bytes, &bars[buf ^ 1]);
         }
         const SampleParams sp = load_params(params, B, b);
+        const int ord = resolve_order(params, B, b, order);
         const float hshift = (sp.fh * 255.f) / 360.f;
         fill_taps(taps, H, W, sp);
         bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
@@ -273,7 +281,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
         }
 
         if (sp.cj_on != 0.f) {          // uniform across the CTA (one image per CTA iteration)
-            if (order == 1) {
+            if (ord == 1) {
 #pragma unroll
                 for (int q = 0; q < QPT; ++q)
 #pragma unroll
@@ -295,7 +303,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[q][c][k] = clamp01((v[q][c][k] - m) * sp.fc + m);
             }
-            if (order == 0) {
+            if (ord == 0) {
 #pragma unroll
                 for (int q = 0; q < QPT; ++q)
 #pragma unroll
@@ -361,6 +369,7 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
             bulk_load(smem + (buf ^ 1) * 3 * HW, x + (size_t)nb * 3 * HW, img_bytes, &bars[buf ^ 1]);
         }
         const SampleParams sp = load_params(params, B, b);
+        const int ord = resolve_order(params, B, b, order);
         const float hshift = (sp.fh * 255.f) / 360.f;
         if (threadIdx.x < 2 * S) {
             const int e = threadIdx.x;
@@ -393,7 +402,7 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
             }
         }
         if (sp.cj_on != 0.f) {          // uniform across the CTA
-            if (order == 1) {
+            if (ord == 1) {
 #pragma unroll
                 for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
             }
@@ -410,7 +419,7 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
 #pragma unroll
                 for (int m = 0; m < NPX; ++m) v[m][c] = clamp01((v[m][c] - mean) * sp.fc + mean);
             }
-            if (order == 0) {
+            if (ord == 0) {
 #pragma unroll
                 for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
             }
@@ -442,6 +451,7 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + 96 + 4 * W + 4 * H);
     const int b = blockIdx.x;
     const SampleParams sp = load_params(params, B, b);
+    const int ord = resolve_order(params, B, b, order);
     const float hshift = (sp.fh * 255.f) / 360.f;
     if (sp.cj_on != 0.f && threadIdx.x == 0) {     // x only feeds the clamp mask; one async bulk copy stages it
         bar_init(bar, 1);
@@ -487,7 +497,7 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
             if (!live[q]) continue;
             int quad = threadIdx.x + q * blockDim.x;
             gather_quad(xs, H, W, quad / Wq, (quad % Wq) * 4, taps, f[q]);
-            if (order == 1) {
+            if (ord == 1) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) hsv_jitter(f[q][0][k], f[q][1][k], f[q][2][k], hshift, sp.fs, sp.fv);
             }
@@ -572,7 +582,7 @@ bool pick_shape(int H, int W, LaunchShape* s) {
 
 extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* params, int B, int H, int W,
                                         int order, void* stream) {
-    CB200_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (order == 0 || order == 1), "augment_fwd: bad shape/order");
+    CB200_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (order >= -1 && order <= 1), "augment_fwd: bad shape/order");
     CB200_CHECK_ARG(W % 4 == 0 && (H * W) % 4 == 0, "augment_fwd: W must be a multiple of 4 (got %d)", W);
     CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
                     "augment_fwd: x/y must be 16-byte aligned");
@@ -617,7 +627,7 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
 
 extern "C" int cb200_augment_simclr_bwd(const float* x, const float* dy, float* dx, const float* params, int B,
                                         int H, int W, int order, void* stream) {
-    CB200_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (order == 0 || order == 1), "augment_bwd: bad shape/order");
+    CB200_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (order >= -1 && order <= 1), "augment_bwd: bad shape/order");
     CB200_CHECK_ARG(W % 4 == 0, "augment_bwd: W must be a multiple of 4 (got %d)", W);
     CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
                       reinterpret_cast<uintptr_t>(dx)) & 15) == 0, "augment_bwd: pointers must be 16-byte aligned");

@@ -23,6 +23,8 @@ extern "C" unsigned long long cb200_launch_count(void) { return g_cb200_launches
 
 extern "C" void cb200_reset_launch_count(void) { g_cb200_launches = 0; }
 
+extern "C" void cb200_add_launch_count(long long n) { g_cb200_launches += (unsigned long long)n; }
+
 extern "C" int cb200_device_arch(int device, int* major, int* minor) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);

@@ -1,8 +1,14 @@
 """Host-side mirror of one iteration of the reference training loop (train_gan.py:141-179):
 warm-up LR, `set_grad` toggling, D step (G forward without grad, loss_D_fn, backward, Adam), G step
 (G forward, loss_G_fn through the frozen D, backward, Adam).  Used by bench.py, smoke() and the parity
-tests; the reference's own `train_gan.py` drives the same plug-ins through contrad_b200.dropin."""
+tests; the reference's own `train_gan.py` drives the same plug-ins through contrad_b200.dropin.
+
+``GraphedTrainStep`` replays the same step as ONE CUDA graph (about 240 kernel launches and their Python dispatch
+collapse into a single cudaGraphLaunch), which is what keeps the GPU busy when the per-GPU batch gets small
+(DDP b512 over 8 GPUs = 64 images per rank)."""
 import torch
+
+from . import staging
 
 
 def update_warmup(optimizer, cur_step, warmup, lr):
@@ -31,9 +37,41 @@ def grad_norm(model):
     return torch.stack(sq).sum().sqrt() if sq else torch.zeros((), dtype=torch.float64)
 
 
+def _is_ddp(model):
+    return isinstance(model, torch.nn.parallel.DistributedDataParallel)
+
+
+def broadcast_parameters(model, src=0):
+    """What DistributedDataParallel does at construction (train_gan.py:311-313): every rank starts from rank
+    `src`'s parameters and buffers.  For models that are NOT wrapped in DDP (see `allreduce_gradients`)."""
+    import torch.distributed as dist
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t, src)
+
+
+def allreduce_gradients(model):
+    """DDP's gradient averaging as ONE flat all-reduce (capturable in a CUDA graph, no bucket hooks): used when
+    `P.distributed` and the model is not DDP-wrapped."""
+    import torch.distributed as dist
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat.div_(dist.get_world_size())
+    views, off = [], 0
+    for g in grads:
+        views.append(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    torch._foreach_copy_(grads, views)
+
+
 def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=True, record_grad_norms=False):
     """One step (n_critic = 1).  Returns a dict of 0-dim tensors (no host sync inside)."""
     generator, discriminator = models
+    sync_d = getattr(P, "distributed", False) and not _is_ddp(discriminator)
+    sync_g = getattr(P, "distributed", False) and not _is_ddp(generator)
     opt_G, opt_D = optimizers
     generator.train()
     discriminator.train()
@@ -48,6 +86,8 @@ def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=Tr
     loss = d_loss + aux["penalty"]
     opt_D.zero_grad()
     loss.backward()
+    if sync_d:
+        allreduce_gradients(discriminator)
     if record_grad_norms:
         out["d_grad_norm"] = grad_norm(discriminator)
     opt_D.step()
@@ -60,8 +100,110 @@ def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=Tr
     g_loss = train_fn["G"](P, discriminator, opt, images, gen_images)
     opt_G.zero_grad()
     g_loss.backward()
+    if sync_g:
+        allreduce_gradients(generator)
     if record_grad_norms:
         out["g_grad_norm"] = grad_norm(generator)
     opt_G.step()
     out["g_loss"] = g_loss.detach()
     return out
+
+
+class GraphedTrainStep(object):
+    """``train_step`` captured once into a CUDA graph and replayed.
+
+    usage:  step_fn = GraphedTrainStep(P, opt, train_fn, (G, D), (opt_G, opt_D));  out = step_fn(images, step)
+
+    * the first ``eager_steps`` calls run the ordinary eager step on a side stream (allocator warm-up, optimiser
+      state, lazily created buffers), the next call captures, every later call replays;
+    * per-step HOST inputs (crop boxes, jitter order, latents, Adam scalars) are not baked in: the capture runs under
+      ``staging.Recorder``; each call re-draws them in the eager order and refreshes the static device buffers
+      before the replay, so the host RNG streams advance exactly as in the eager loop;
+    * device RNG draws (flip / jitter factors / apply masks) are torch CUDA-generator ops, which torch's graph
+      support re-seeds per replay;
+    * optimisers must be ``contrad_b200.optim.FusedAdam`` (device-resident step scalars); the models must not be
+      DDP-wrapped - with ``P.distributed`` the gradients are averaged by one captured NCCL all-reduce;
+    * the returned dict holds STATIC tensors that the next call overwrites;
+    * the host RNG draws of step s+1 are made right after the replay of step s is launched, so that the host
+      sampling (~2 ms) overlaps the GPU (same draw order as the eager loop; one set of draws is left unused when
+      the loop ends).
+    """
+
+    def __init__(self, P, opt, train_fn, models, optimizers, use_warmup=True, eager_steps=3):
+        from .optim import FusedAdam
+        for o in optimizers:
+            if not isinstance(o, FusedAdam):
+                raise TypeError("GraphedTrainStep needs contrad_b200.optim.FusedAdam optimisers")
+        for m in models:
+            if _is_ddp(m):
+                raise TypeError("GraphedTrainStep: pass the bare modules (gradient averaging is captured in the graph)")
+        self.P, self.opt, self.train_fn, self.models, self.optimizers = P, opt, train_fn, models, optimizers
+        self.use_warmup, self.eager_steps = use_warmup, max(1, int(eager_steps))
+        self.calls, self.graph, self.recorder = 0, None, None
+        self.static_images, self.static_out = None, None
+        self.launches_per_replay = 0
+        self.side = None
+        self.prefetched = False           # the next step's host draws already sit in pinned memory
+
+    def _eager(self, images, step, plan=False):
+        if self.side is None:
+            self.side = torch.cuda.Stream()
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            if plan:        # the last eager step also lays out the static input buffers (staging.Recorder.plan)
+                self.recorder = staging.Recorder()
+                with self.recorder.plan():
+                    out = train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers, images, step,
+                                     use_warmup=self.use_warmup)
+            else:
+                out = train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers, images, step,
+                                 use_warmup=self.use_warmup)
+        torch.cuda.current_stream().wait_stream(self.side)
+        images.record_stream(self.side)
+        return out
+
+    def _host_schedule(self, step):
+        if self.use_warmup:
+            opt_G, opt_D = self.optimizers
+            update_warmup(opt_G, step, self.opt["warmup"], self.opt["lr"])
+            update_warmup(opt_D, step, self.opt["warmup"], self.opt.get("lr_d", self.opt["lr"]))
+
+    def _capture(self, images, step):
+        from . import _capi
+        torch.cuda.synchronize()
+        self.static_images = images.clone()
+        self.graph = torch.cuda.CUDAGraph()
+        before = _capi.launch_count()
+        with self.recorder.capture():
+            # capture on the stream the eager warm-up steps ran on: the parameters' AccumulateGrad nodes stay bound
+            # to the stream of their first backward, and a mismatch would fork the capture across streams
+            with torch.cuda.graph(self.graph, stream=self.side):
+                self.static_out = train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers,
+                                             self.static_images, step, use_warmup=False)
+        self.launches_per_replay = _capi.launch_count() - before
+
+    def release(self):
+        """Drop the captured graph and its static tensors (required before torch.distributed.destroy_process_group
+        when the graph holds NCCL kernels).  The object falls back to capturing again on the next call."""
+        torch.cuda.synchronize()
+        self.graph, self.static_out, self.static_images = None, None, None
+        self.prefetched = False
+
+    def __call__(self, images, step):
+        from . import _capi
+        self.calls += 1
+        if self.calls <= self.eager_steps:
+            return self._eager(images, step, plan=(self.calls == self.eager_steps))
+        if self.graph is None:
+            self._capture(images, step)          # records the launches, executes nothing
+            _capi.add_launch_count(-self.launches_per_replay)
+        self._host_schedule(step)                # Adam's scalars are staged `late`: they see this step's lr
+        if not self.prefetched:
+            self.recorder.produce()
+        self.static_images.copy_(images, non_blocking=True)
+        self.recorder.upload()
+        self.graph.replay()
+        _capi.add_launch_count(self.launches_per_replay)
+        self.recorder.produce()                  # the NEXT step's host draws, while the GPU is busy with this one
+        self.prefetched = True
+        return self.static_out

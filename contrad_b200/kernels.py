@@ -43,7 +43,8 @@ def augment_simclr_fwd(x, params, order):
     x = _f32c(x, "x")
     params = _f32c(params, "params")
     B, C, H, W = x.shape
-    assert C == 3 and params.shape == (len(PARAM_FIELDS), B), (x.shape, params.shape)
+    # order -1: per-image order in an extra row 11 (CUDA-graph replay, include/contrad_b200.h)
+    assert C == 3 and params.shape == (len(PARAM_FIELDS) + (1 if order < 0 else 0), B), (x.shape, params.shape, order)
     y = torch.empty_like(x)
     _call("augment_simclr_fwd", 0, 8 * x.numel(), lib().cb200_augment_simclr_fwd, ptr(x), ptr(y), ptr(params), i32(B), i32(H), i32(W), i32(order),
                                          stream_ptr())
@@ -423,6 +424,12 @@ def adam_step(entries, lr, beta1, beta2, eps, step):
         assert p.is_cuda and p.is_contiguous() and g.is_contiguous()
         arr[i] = _AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
         nbytes += 28 * p.numel()
+    if isinstance(lr, torch.Tensor):
+        # device-resident {lr, 1-b1^t, sqrt(1-b2^t)} (CUDA-graph replay); `step` is ignored
+        assert lr.is_cuda and lr.dtype == torch.float32 and lr.numel() >= 3 and lr.is_contiguous()
+        _call("adam_step", 0, nbytes, lib().cb200_adam_step_dev, arr, i32(len(entries)), ptr(lr), f32(beta1), f32(beta2),
+              f32(eps), stream_ptr())
+        return
     _call("adam_step", 0, nbytes, lib().cb200_adam_step, arr, i32(len(entries)), f32(lr), f32(beta1), f32(beta2), f32(eps),
           i32(step), stream_ptr())
 

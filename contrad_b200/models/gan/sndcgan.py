@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ... import staging
 from ...functional import GSNDCGANFn, SNDCGANBackboneFn, SNLayerSpec
 from .base import BaseDiscriminator, SNConv2d
 
@@ -59,15 +60,8 @@ class G_SNDCGAN(nn.Module):
         """models/gan/sndcgan.py:50-52: U(-1,1) drawn on the CPU generator (same stream as the reference), staged
         through a ring of pinned buffers so the host->device copy does not block the host."""
         device = next(self.parameters()).device
-        if device.type != "cuda":
-            return torch.empty(n_samples, self.nz).uniform_(-1, 1).to(device)
-        ring = self.__dict__.setdefault("_latent_ring", {})
-        key = (n_samples, self.nz)
-        if key not in ring:
-            ring[key] = [[torch.empty(n_samples, self.nz).pin_memory() for _ in range(8)], 0]
-        bufs, i = ring[key]
-        ring[key][1] = (i + 1) % len(bufs)
-        return bufs[i].uniform_(-1, 1).to(device, non_blocking=True)
+        nz = self.nz
+        return staging.stage(lambda out: out.uniform_(-1, 1), device, shape=(n_samples, nz), fill=True)
 
     def reset_parameters(self):
         for m in self.modules():

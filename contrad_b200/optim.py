@@ -1,9 +1,16 @@
 """Fused Adam on the sm_100a kernels (SURVEY "next" row f2).  API- and state_dict-compatible with
 ``torch.optim.Adam`` as the reference configures it (train_gan.py:273-274: lr, betas, eps=1e-8, no weight decay,
-no amsgrad), so ``optim.pt`` checkpoints interchange.  One kernel launch per ``step()``."""
+no amsgrad), so ``optim.pt`` checkpoints interchange.  One kernel launch per ``step()``.
+
+Under ``staging.Recorder`` (CUDA-graph capture of the train step) the step-dependent scalars - learning rate and
+the two bias corrections - are staged as a 3-float device tensor, so the captured launch stays valid for every
+later step; the host-side ``state['step']`` counters still advance once per replay (inside the staged producer)."""
+import math
+
 import torch
 
 from . import kernels as K
+from . import staging
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -13,6 +20,35 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
                                       foreach=None, capturable=False, differentiable=False, fused=None))
 
+    def _init_state(self, p):
+        state = self.state[p]
+        if len(state) == 0:
+            state["step"] = torch.tensor(0.0)
+            state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return state
+
+    def _step_recording(self, group):
+        """Capture-safe variant: one launch for the group, scalars from a staged device tensor."""
+        params = [p for p in group["params"] if p.grad is not None]
+        if not params:
+            return
+        states = [self._init_state(p) for p in params]
+        if len({int(s["step"]) for s in states}) != 1:
+            raise RuntimeError("FusedAdam: graph capture needs all tensors of a group at the same step count")
+
+        def hyper():
+            for s in states:
+                s["step"] += 1
+            t = int(states[0]["step"])
+            b1, b2 = group["betas"]
+            return torch.tensor([group["lr"], 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t)], dtype=torch.float32)
+
+        dev_hyper = staging.stage(hyper, params[0].device, shape=(3,), late=True)
+        entries = [(p, p.grad if p.grad.is_contiguous() else p.grad.contiguous(), s["exp_avg"], s["exp_avg_sq"])
+                   for p, s in zip(params, states)]
+        K.adam_step(entries, dev_hyper, group["betas"][0], group["betas"][1], group["eps"], 0)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -20,15 +56,14 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         for group in self.param_groups:
+            if staging.recording():
+                self._step_recording(group)
+                continue
             entries, step_no = [], None
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                state = self.state[p]
-                if len(state) == 0:
-                    state["step"] = torch.tensor(0.0)
-                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                state = self._init_state(p)
                 state["step"] += 1
                 s = int(state["step"])
                 if step_no is None:

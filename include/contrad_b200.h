@@ -29,6 +29,9 @@ int cb200_version(void);
 const char* cb200_last_error(void);
 unsigned long long cb200_launch_count(void);     /* kernels launched by this library so far */
 void cb200_reset_launch_count(void);
+/* Launches recorded while a CUDA graph is being captured did not run, and a replay bypasses the counter: the host
+ * corrects it by a signed delta. */
+void cb200_add_launch_count(long long n);
 int cb200_device_arch(int device, int* major, int* minor);
 
 /* ---- fused SimCLR augmentation ------------------------------------------------------------
@@ -40,6 +43,8 @@ int cb200_device_arch(int device, int* major, int* minor);
  *           contrast, hue, sat, val factors, gray_on (0/1)   -- drawn on the host in the
  *           reference's numpy/torch RNG order
  *   order   0: [contrast, hsv]   1: [hsv, contrast]   (color_jitter.py:65-70, one draw per batch)
+ *           -1: read per image from an extra row 11 of `params` ([12, B]; != 0 means 1) - keeps the launch free of
+ *               step-dependent host scalars so it can be replayed inside a CUDA graph
  * Backward = autograd of the reference chain (HSV straight-through, color_jitter.py:97-104). */
 int cb200_augment_simclr_fwd(const float* x, float* y, const float* params, int B, int H, int W,
                              int order, void* stream);
@@ -185,6 +190,9 @@ struct cb200_adam_tensor {
 };
 int cb200_adam_step(const struct cb200_adam_tensor* tensors, int n, float lr, float beta1, float beta2, float eps,
                     int step, void* stream);
+/* Same update; {lr, 1 - beta1^t, sqrt(1 - beta2^t)} are read from 3 floats in DEVICE memory (CUDA-graph replay). */
+int cb200_adam_step_dev(const struct cb200_adam_tensor* tensors, int n, const float* hyper, float beta1, float beta2,
+                        float eps, void* stream);
 
 #ifdef __cplusplus
 }

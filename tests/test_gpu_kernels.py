@@ -58,6 +58,29 @@ def test_augment_matches_oracle_random(K, B, size, seed):
     assert bad < 2e-3, bad
 
 
+def test_augment_per_image_order_row(K):
+    """order = -1: the jitter order comes per image from row 11 of the parameter block (CUDA-graph replay path);
+    forward and backward equal the launch-wide order applied image by image."""
+    import numpy as np
+    np.random.seed(8); torch.manual_seed(8)
+    B = 40
+    x = torch.rand(B, 3, 32, 32).cuda()
+    dy = torch.randn(B, 3, 32, 32).cuda()
+    params, _ = O.sample_simclr_params(B, 32, 32)
+    packed = O.pack_params(params)
+    packed[5] = 1.0                                   # colour jitter on everywhere, so the order matters
+    orders = (torch.arange(B) % 3 == 0).float()
+    p12 = torch.cat([packed, orders.view(1, B)]).cuda()
+    y = K.augment_simclr_fwd(x, p12, -1)
+    dx = K.augment_simclr_bwd(x, dy, p12, -1)
+    ys = [K.augment_simclr_fwd(x, packed.cuda(), o) for o in (0, 1)]
+    dxs = [K.augment_simclr_bwd(x, dy, packed.cuda(), o) for o in (0, 1)]
+    sel = orders.bool().cuda().view(B, 1, 1, 1)
+    assert torch.equal(y, torch.where(sel, ys[1], ys[0]))
+    assert torch.allclose(dx, torch.where(sel, dxs[1], dxs[0]), atol=1e-5, rtol=1e-5)   # smem atomics reorder
+    assert not torch.equal(ys[0], ys[1])
+
+
 def test_augment_full_size_properties(K):
     """BASELINE config-2 size (B=1536): identity parameters reproduce the input bit-exactly; a pure
     flip is the exact mirror; gray output has equal channels; range stays in [0,1]."""

@@ -280,3 +280,72 @@ def test_full_batch_step_runs_and_is_finite(env):
     assert all(np.isfinite(v) for v in vals.values()), vals
     assert abs(vals["d_penalty"] - 2 * np.log(2)) < 0.05 and abs(vals["g_loss"] - np.log(2)) < 0.05, vals
     assert 8.0 < vals["d_loss"] < 16.0, vals
+
+
+class _HostDrawnAugment(torch.nn.Module):
+    """SimCLR parameters drawn entirely on the host (the oracle's sampler, numpy RNG) and staged to the device:
+    deterministic for a seed in BOTH the eager loop and the CUDA-graph loop, and exercises the per-image jitter
+    order (kernel order = -1, row 11)."""
+
+    def forward(self, x):
+        from contrad_b200 import staging
+        from contrad_b200.functional import AugmentSimCLRFn
+        n = x.shape[0]
+
+        def draw():
+            params, order = O.sample_simclr_params(n, 32, 32)
+            return torch.cat([O.pack_params(params), torch.full((1, n), float(order))])
+
+        return AugmentSimCLRFn.apply(x, staging.stage(draw, x.device, shape=(12, n)), -1)
+
+
+def test_cuda_graph_step_matches_eager_step(env):
+    """engine.GraphedTrainStep (3 eager steps, capture, replays) against the plain eager loop: same seeds -> same
+    host draws -> the same losses, the same Adam step counters and the same weight UPDATES after 7 steps.
+    The learning rate is tiny on purpose: early Adam steps are sign-like (m/sqrt(v) = +-1), so fp32-atomic
+    reordering of near-zero gradients flips O(lr) updates and, at the reference lr, two EAGER runs already differ by
+    0.3 % in the loss after four steps."""
+    from contrad_b200.optim import FusedAdam
+    n, steps, lr = 32, 7, 2e-6
+    options = {"loss": "nonsat", "warmup": 5, "lr": lr, "lr_d": lr}
+    train_fn = {"D": env.contrad.loss_D_fn, "G": env.contrad.loss_G_fn}
+    runs = []
+    for graphed in (False, True):
+        gen_w = torch.Generator().manual_seed(77)
+        G, D = env.get_architecture("sndcgan", (32, 32, 3))
+        D.load_state_dict(O.make_d_state(generator=gen_w)); G.load_state_dict(O.make_g_state(generator=gen_w))
+        G.cuda(); D.cuda()
+        params = [p for p in D.parameters()] + [p for p in G.parameters()]
+        w0 = [p.detach().clone() for p in params]
+        opt_G = FusedAdam(G.parameters(), lr=lr, betas=(0.5, 0.999))
+        opt_D = FusedAdam(D.parameters(), lr=lr, betas=(0.5, 0.999))
+        P = SimpleNamespace(augment_fn=_HostDrawnAugment(), temp=0.1, lbd_a=1.0, distributed=False)
+        np.random.seed(21); torch.manual_seed(21)
+        data = torch.rand(steps, n, 3, 32, 32).cuda()
+        step_fn = (env.engine.GraphedTrainStep(P, options, train_fn, (G, D), (opt_G, opt_D)) if graphed else
+                   (lambda im, s: env.engine.train_step(P, options, train_fn, (G, D), (opt_G, opt_D), im, s)))
+        log = []
+        for s in range(steps):
+            out = step_fn(data[s], s + 1)
+            log.append({k: float(v) for k, v in out.items()})
+        torch.cuda.synchronize()
+        if graphed:
+            assert step_fn.graph is not None and step_fn.launches_per_replay > 100
+        runs.append((log, [p.detach() - a for p, a in zip(params, w0)],
+                     [float(opt_D.state[p]["step"]) for p in D.parameters()]))
+    (log_e, d_e, t_e), (log_g, d_g, t_g) = runs
+    assert t_e == t_g == [float(steps)] * len(t_e)
+    for s, (a, b) in enumerate(zip(log_e, log_g)):
+        for k in a:
+            assert _rel(b[k], a[k]) < 1e-3 or abs(a[k] - b[k]) < 1e-4, (s, k, a[k], b[k])
+    num = torch.stack([(a - b).norm() for a, b in zip(d_e, d_g)]).norm()
+    den = torch.stack([a.norm() for a in d_e]).norm()
+    print("relative difference of the 7-step weight updates, graph vs eager: %.3g" % float(num / den))
+    assert float(num / den) < 5e-2
+    # every tensor moved, and moved alike - except the four G biases that feed a BatchNorm (exactly zero true
+    # gradient: their Adam updates are rounding noise in both runs)
+    odd = [i for i, (a, b) in enumerate(zip(d_e, d_g))
+           if not (float(a.norm()) > 0 and float((a - b).norm()) < 0.25 * float(a.norm()) + 1e-9)]
+    assert len(odd) <= 4, odd
+
+

@@ -152,3 +152,143 @@ def test_distributed_loss_equals_single_process_oracle():
     got = _rank_major(torch.stack(per_rank), n)
     want = torch.cat([torch.cat([p[i * n:(i + 1) * n] for p in per_rank]) for i in range(3)])
     assert torch.equal(got, want)
+
+
+def test_staging_eager_and_recorder_on_cpu():
+    """staging.stage: eager = the producer's value on the device; Recorder.plan() = an eager step that lays out
+    static buffers; Recorder.capture() hands the same buffers out again without calling the producers; refresh()
+    refills them by calling the producers in the recorded order (host RNG advances like the eager loop)."""
+    from contrad_b200 import staging
+    calls = []
+
+    def producer_a():
+        calls.append("a")
+        return torch.full((2, 3), float(len(calls)))
+
+    def producer_b():
+        calls.append("b")
+        return torch.full((1,), -float(len(calls)))
+
+    def filler_c(out):
+        calls.append("c")
+        out.fill_(100.0 + len(calls))
+
+    assert torch.equal(staging.stage(producer_a, "cpu"), torch.full((2, 3), 1.0)) and calls == ["a"]
+    assert float(staging.stage(filler_c, "cpu", shape=(2,), fill=True)[0]) == 102.0 and calls == ["a", "c"]
+    del calls[:]
+    rec = staging.Recorder(slots=2)
+    with rec.plan():
+        assert staging.recording()
+        buf_a = staging.stage(producer_a, "cpu", shape=(2, 3))
+        buf_b = staging.stage(producer_b, "cpu")
+        buf_c = staging.stage(filler_c, "cpu", shape=(2,), fill=True)
+    # the planned step is a real step: every producer ran exactly once and its value is in the static buffer
+    assert not staging.recording() and calls == ["a", "b", "c"]
+    assert float(buf_a[0, 0]) == 1.0 and float(buf_b[0]) == -2.0 and float(buf_c[0]) == 103.0
+    with rec.capture():
+        assert staging.stage(producer_a, "cpu", shape=(2, 3)) is buf_a
+        assert staging.stage(producer_b, "cpu") is buf_b
+        assert staging.stage(filler_c, "cpu", shape=(2,), fill=True) is buf_c
+    assert calls == ["a", "b", "c"]                                 # capture draws nothing
+    for k in range(3):                                              # more refreshes than pinned slots
+        rec.refresh()
+        assert calls[-3:] == ["a", "b", "c"]
+        assert float(buf_a[0, 0]) == len(calls) - 2 and float(buf_b[0]) == -(len(calls) - 1)
+        assert float(buf_c[1]) == 100.0 + len(calls)
+    n = len(calls)
+    rec.produce()                                                   # host half only: buffers unchanged until upload()
+    assert len(calls) == n + 3 and float(buf_a[0, 0]) == n - 2
+    rec.upload()
+    assert float(buf_a[0, 0]) == n + 1
+    with pytest.raises(RuntimeError):                               # a captured step that stages fewer inputs
+        with rec.capture():
+            staging.stage(producer_a, "cpu", shape=(2, 3))
+    with pytest.raises(RuntimeError):
+        with rec.capture():
+            staging.stage(producer_a, "cpu", shape=(5, 3))
+
+
+def test_fused_simclr_host_draw_order_matches_reference_in_recording_mode():
+    """Under a Recorder the numpy draws (crop boxes, then the jitter order) happen in the eager order, so a graphed
+    loop consumes the host RNG stream exactly like the reference loop."""
+    _gin_defaults()
+    from contrad_b200 import staging
+    from contrad_b200.augment.layers import ColorJitterLayer, RandomResizeCropLayer, _ShapeOnly
+    rrc, cj = RandomResizeCropLayer(scale=(0.2, 1.0)), ColorJitterLayer(0.4, 0.4, 0.4, 0.1)
+    shape = _ShapeOnly((6, 3, 32, 32))
+    np.random.seed(11)
+    want = [(rrc.sample(shape), cj.draw_order()) for _ in range(4)]
+    np.random.seed(11)
+    rec = staging.Recorder()
+
+    def one_step():
+        box = staging.stage(lambda: rrc.sample(shape), "cpu", shape=(4, 6))
+        order = staging.stage(lambda: torch.tensor([float(cj.draw_order())]), "cpu", shape=(1,))
+        return box, order
+
+    with rec.plan():
+        box, order = one_step()
+    assert torch.equal(box, want[0][0]) and float(order) == want[0][1]
+    with rec.capture():
+        box2, order2 = one_step()
+    assert box2 is box and order2 is order
+    for w_box, w_order in want[1:]:
+        rec.refresh()
+        assert torch.equal(box, w_box) and float(order) == w_order
+
+
+def _grad_sync_worker(rank, world, port, results):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from contrad_b200 import engine
+    torch.manual_seed(rank)                      # different init per rank -> broadcast must fix it
+    model = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3), torch.nn.Linear(3, 1, bias=False))
+    engine.broadcast_parameters(model, src=0)
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3), torch.nn.Linear(3, 1, bias=False))
+    ok = all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), ref.state_dict().values()))
+    torch.manual_seed(5)
+    data = torch.randn(world, 8, 4)
+    model.eval()
+    model(data[rank]).sum().backward()
+    engine.allreduce_gradients(model)
+    ref.eval()
+    (sum(ref(data[r]).sum() for r in range(world)) / world).backward()
+    ok = ok and all(torch.allclose(a.grad, b.grad, atol=1e-6) for a, b in zip(model.parameters(), ref.parameters()))
+    results[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_engine_gradient_sync_gloo_world2():
+    """engine.broadcast_parameters + engine.allreduce_gradients = what DDP does around backward
+    (train_gan.py:311-313): same start everywhere, gradients averaged over ranks."""
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_grad_sync_worker, args=(world, 29613, results), nprocs=world, join=True)
+    assert all(results.get(r) for r in range(world)), dict(results)
+
+
+def test_staging_late_entries_are_produced_at_upload_time():
+    """late=True (Adam's step scalars): produce() - which runs one step AHEAD, overlapping the GPU - must not touch
+    them; upload() draws them right before the replay."""
+    from contrad_b200 import staging
+    state = {"t": 0}
+
+    def hyper():
+        state["t"] += 1
+        return torch.tensor([float(state["t"])])
+
+    rec = staging.Recorder()
+    with rec.plan():
+        buf = staging.stage(hyper, "cpu", shape=(1,), late=True)
+    assert state["t"] == 1 and float(buf) == 1.0
+    with rec.capture():
+        staging.stage(hyper, "cpu", shape=(1,), late=True)
+    rec.produce()
+    assert state["t"] == 1
+    rec.upload()
+    assert state["t"] == 2 and float(buf) == 2.0

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from types import SimpleNamespace
-args = SimpleNamespace(gpus=1, steps=10, warmup=3, no_cpu_baseline=True)
+args = SimpleNamespace(gpus=1, steps=10, warmup=3, no_cpu_baseline=True, no_graph=True)
 from contrad_b200 import engine
 W = bench.build_world(args)
 pool = [torch.rand(512, 3, 32, 32, device="cuda") for _ in range(2)]
