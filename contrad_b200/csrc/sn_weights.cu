@@ -13,6 +13,7 @@
 //   sn_bwd   : dW = (dW_hat - <dW_hat, W_hat> u v^T) / sigma, un-packing the wgrad layout
 // sigma never leaves the device.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -396,6 +397,191 @@ __global__ void __launch_bounds__(kT) sn_bwd_apply_batched_kernel(const __grid_c
     p.dw[l][idx] = (g - p.acc[l][0] * inv * p.u[l][co] * p.v[l][f]) * inv;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled variants of the pack / backward kernels.  A CTA owns a 32 (Cout) x CT (Cin) x KK (taps) block of one layer
+// and moves it through shared memory, so that BOTH sides of every layout change are coalesced:
+//   OIHW weight   w[co][ci][kk]            - contiguous along (ci, kk) for a fixed co
+//   forward pack  fwd[co][kk][ci]          - contiguous along ci
+//   dgrad packs   dg[g(ci, kk)][co]        - contiguous along co (all three modes)
+// The element-indexed kernels above issue one 4-byte scattered store (a 32-byte sector read-modify-write) per
+// element on two of the three layouts; on the 17 M head weights that was 0.75 ms per step.
+// Shared layout: tile[co_l][kk * (CT + 1) + ci_l], row stride RS odd - conflict-free for the ci-major and the
+// co-major accesses, 2-way for the OIHW-ordered one.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileCo = 32;
+
+struct TileGeom {
+    int co0, ci0, n_co, n_ci, KK, CT, RS;
+};
+
+__device__ __forceinline__ TileGeom tile_geom(int local_cta, int Cout, int Cin, int KK) {
+    TileGeom g;
+    g.KK = KK;
+    g.CT = (KK == 1) ? 256 : 32;
+    const int ci_tiles = (Cin + g.CT - 1) / g.CT;
+    g.co0 = (local_cta / ci_tiles) * kTileCo;
+    g.ci0 = (local_cta % ci_tiles) * g.CT;
+    g.n_co = min(kTileCo, Cout - g.co0);
+    g.n_ci = min(g.CT, Cin - g.ci0);
+    g.RS = (KK * (g.CT + 1)) | 1;
+    return g;
+}
+
+__host__ __device__ __forceinline__ int tiles_of(int Cout, int Cin, int KK) {
+    const int CT = (KK == 1) ? 256 : 32;
+    return ((Cout + kTileCo - 1) / kTileCo) * ((Cin + CT - 1) / CT);
+}
+
+constexpr size_t kTileSmemBytes = (size_t)kTileCo * ((16 * 33) | 1) * sizeof(float);     // KK <= 16
+
+// KKc > 0: the tap count as a compile-time constant (the divisions by it become multiplies); 0 = generic.
+template <int KKc>
+__device__ __forceinline__ void pack_tile_body(const SnPackBatch& p, int l, const TileGeom& g, float* tile) {
+    const int Cout = p.cout[l], Cin = p.cin[l], KW = p.kw[l], KK = KKc ? KKc : g.KK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long F = (long long)Cin * KK;
+    const float inv = p.sigma[l] ? p.sigma[l][1] : 1.f;
+    const float* __restrict__ w = p.w[l];
+    const int ncols = g.n_ci * KK;
+    const bool rnd = p.do_round[l] != 0;
+    for (int r = warp; r < g.n_co; r += kT / 32) {
+        const float* src = w + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
+        float* row = tile + r * g.RS;
+#pragma unroll 4
+        for (int t = lane; t < ncols; t += 32) {
+            float val = __ldg(src + t) * inv;
+            if (rnd) val = round_tf32(val);
+            row[(t % KK) * (g.CT + 1) + t / KK] = val;
+        }
+    }
+    __syncthreads();
+    float* __restrict__ fwd = p.fwd[l];
+    if (fwd) {
+        for (int r = warp; r < g.n_co; r += kT / 32) {
+            float* dst = fwd + (long long)(g.co0 + r) * p.ld_fwd[l] + g.ci0;
+            const float* row = tile + r * g.RS;
+            for (int kk = 0; kk < KK; ++kk)
+#pragma unroll 4
+                for (int ci = lane; ci < g.n_ci; ci += 32) dst[(long long)kk * Cin + ci] = row[kk * (g.CT + 1) + ci];
+        }
+    }
+    float* __restrict__ dg = p.dg[l];
+    if (dg && lane < g.n_co) {
+        const int mode = p.dg_mode[l];
+        const float* col = tile + lane * g.RS;
+        for (int ci_l = warp; ci_l < g.n_ci; ci_l += kT / 32) {
+            const int ci = g.ci0 + ci_l;
+#pragma unroll 4
+            for (int kk = 0; kk < KK; ++kk) {
+                long long row;
+                if (mode == 1) {
+                    row = ((long long)ci * KK + kk) * Cout;
+                } else if (mode == 2) {
+                    const int kh = kk / KW, kw = kk % KW;
+                    const int ph = (kh & 1) ? 0 : 1, jh = (kh <= 1) ? 0 : 1;
+                    const int pw = (kw & 1) ? 0 : 1, jw = (kw <= 1) ? 0 : 1;
+                    row = ((((long long)(ph * 2 + pw) * Cin + ci) * 2 + jh) * 2 + jw) * Cout;
+                } else {
+                    row = ((long long)kk * Cin + ci) * p.ldt[l] + p.col0[l];
+                }
+                dg[row + g.co0 + lane] = col[kk * (g.CT + 1) + ci_l];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kT) sn_pack_tiled_kernel(const __grid_constant__ SnPackBatch p) {
+    extern __shared__ float tile[];
+    const int l = find_layer(p.cta_begin, p.n, blockIdx.x);
+    const int KK = p.kh[l] * p.kw[l];
+    const TileGeom g = tile_geom(blockIdx.x - p.cta_begin[l], p.cout[l], p.cin[l], KK);
+    if (KK == 1) pack_tile_body<1>(p, l, g, tile);
+    else if (KK == 9) pack_tile_body<9>(p, l, g, tile);
+    else if (KK == 16) pack_tile_body<16>(p, l, g, tile);
+    else pack_tile_body<0>(p, l, g, tile);
+}
+
+// Stage dW_hat (forward-pack order) of one tile into shared memory: coalesced along ci.
+__device__ __forceinline__ void load_dwp_tile(const float* __restrict__ dwp, long long ld, int Cin, const TileGeom& g,
+                                              float* tile) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < g.n_co; r += kT / 32) {
+        const float* src = dwp + (long long)(g.co0 + r) * ld + g.ci0;
+        float* row = tile + r * g.RS;
+        for (int kk = 0; kk < g.KK; ++kk)
+#pragma unroll 4
+            for (int ci = lane; ci < g.n_ci; ci += 32) row[kk * (g.CT + 1) + ci] = __ldg(src + (long long)kk * Cin + ci);
+    }
+    __syncthreads();
+}
+
+template <int KKc>
+__device__ __forceinline__ float dot_tile_body(const SnBwdBatch& p, int l, const TileGeom& g, const float* tile) {
+    const int KK = KKc ? KKc : g.KK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long F = (long long)p.cin[l] * KK;
+    const int ncols = g.n_ci * KK;
+    float a = 0.f;
+    for (int r = warp; r < g.n_co; r += kT / 32) {
+        const float* src = p.w[l] + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
+        const float* row = tile + r * g.RS;
+#pragma unroll 4
+        for (int t = lane; t < ncols; t += 32) a += __ldg(src + t) * row[(t % KK) * (g.CT + 1) + t / KK];
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(kT) sn_bwd_dot_tiled_kernel(const __grid_constant__ SnBwdBatch p) {
+    extern __shared__ float tile[];
+    __shared__ float red[32];
+    const int l = find_layer(p.cta_begin, p.n, blockIdx.x);
+    const int Cin = p.cin[l], KK = p.kh[l] * p.kw[l];
+    const TileGeom g = tile_geom(blockIdx.x - p.cta_begin[l], p.cout[l], Cin, KK);
+    load_dwp_tile(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    float a[1];
+    if (KK == 1) a[0] = dot_tile_body<1>(p, l, g, tile);
+    else if (KK == 9) a[0] = dot_tile_body<9>(p, l, g, tile);
+    else if (KK == 16) a[0] = dot_tile_body<16>(p, l, g, tile);
+    else a[0] = dot_tile_body<0>(p, l, g, tile);
+    block_sum<1>(a, red);
+    if (threadIdx.x == 0) atomicAdd(p.acc[l], a[0]);
+}
+
+template <int KKc>
+__device__ __forceinline__ void apply_tile_body(const SnBwdBatch& p, int l, const TileGeom& g, const float* tile) {
+    const int KK = KKc ? KKc : g.KK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long F = (long long)p.cin[l] * KK;
+    const int ncols = g.n_ci * KK;
+    const float inv = p.sigma[l][1];
+    const float scale = p.acc[l][0] * inv;
+    const float* __restrict__ v = p.v[l] + (long long)g.ci0 * KK;
+    for (int r = warp; r < g.n_co; r += kT / 32) {
+        const float su = scale * p.u[l][g.co0 + r];
+        float* dst = p.dw[l] + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
+        const float* row = tile + r * g.RS;
+#pragma unroll 4
+        for (int t = lane; t < ncols; t += 32) dst[t] = (row[(t % KK) * (g.CT + 1) + t / KK] - su * __ldg(v + t)) * inv;
+    }
+}
+
+__global__ void __launch_bounds__(kT) sn_bwd_apply_tiled_kernel(const __grid_constant__ SnBwdBatch p) {
+    extern __shared__ float tile[];
+    const int l = find_layer(p.cta_begin, p.n, blockIdx.x);
+    const int Cin = p.cin[l], KK = p.kh[l] * p.kw[l];
+    const TileGeom g = tile_geom(blockIdx.x - p.cta_begin[l], p.cout[l], Cin, KK);
+    load_dwp_tile(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    if (KK == 1) apply_tile_body<1>(p, l, g, tile);
+    else if (KK == 9) apply_tile_body<9>(p, l, g, tile);
+    else if (KK == 16) apply_tile_body<16>(p, l, g, tile);
+    else apply_tile_body<0>(p, l, g, tile);
+}
+
+bool sn_tiled_enabled() {
+    static const bool on = []() { const char* e = getenv("CB200_SN_TILED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 }  // namespace
 
 // One power iteration (training != 0) or sigma from the stored u, v (training == 0).
@@ -516,6 +702,7 @@ extern "C" int cb200_sn_power_iter_batched(const cb200_sn_layer* layers, int n, 
 
 extern "C" int cb200_sn_pack_batched(const cb200_sn_pack_job* jobs, int n, void* stream) {
     CB200_CHECK_ARG(n > 0 && n <= kMaxLayers, "sn_pack_batched: 1..16 jobs");
+    const bool tiled = sn_tiled_enabled();
     SnPackBatch p;
     p.n = n;
     int total = 0;
@@ -526,11 +713,21 @@ extern "C" int cb200_sn_pack_batched(const cb200_sn_pack_job* jobs, int n, void*
         p.cout[l] = j.cout; p.cin[l] = j.cin; p.kh[l] = j.kh; p.kw[l] = j.kw;
         p.dg_mode[l] = j.dgrad_mode; p.col0[l] = j.col0; p.do_round[l] = j.round_out;
         p.cta_begin[l] = total;
-        const long long elems = (long long)j.cout * j.cin * j.kh * j.kw;
-        total += (int)((elems + kT * 4 - 1) / (kT * 4));
+        if (tiled) {
+            CB200_CHECK_ARG(j.kh * j.kw <= 16, "sn_pack_batched: at most 16 taps");
+            total += tiles_of(j.cout, j.cin, j.kh * j.kw);
+        } else {
+            const long long elems = (long long)j.cout * j.cin * j.kh * j.kw;
+            total += (int)((elems + kT * 4 - 1) / (kT * 4));
+        }
     }
     p.cta_begin[n] = total;
-    sn_pack_batched_kernel<<<total, kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (tiled) {
+        cudaFuncSetAttribute(sn_pack_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+        sn_pack_tiled_kernel<<<total, kT, kTileSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    } else {
+        sn_pack_batched_kernel<<<total, kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("sn_pack_batched");
     return CB200_OK;
@@ -543,6 +740,25 @@ extern "C" int cb200_sn_weight_bwd_batched(const cb200_sn_bwd_job* jobs, int n, 
     SnBwdBatch p;
     p.n = n;
     int total = 0;
+    if (sn_tiled_enabled()) {
+        for (int l = 0; l < n; ++l) {
+            const cb200_sn_bwd_job& j = jobs[l];
+            CB200_CHECK_ARG(j.kh * j.kw <= 16, "sn_weight_bwd_batched: at most 16 taps");
+            p.dwp[l] = j.dw_hat_packed; p.w[l] = j.w; p.u[l] = j.u; p.v[l] = j.v; p.sigma[l] = j.sigma; p.acc[l] = j.acc;
+            p.dw[l] = j.dw; p.ld_fwd[l] = j.ld_fwd; p.cout[l] = j.cout; p.cin[l] = j.cin; p.kh[l] = j.kh; p.kw[l] = j.kw;
+            p.cta_begin[l] = total;
+            total += tiles_of(j.cout, j.cin, j.kh * j.kw);
+        }
+        p.cta_begin[n] = total;
+        cudaFuncSetAttribute(sn_bwd_dot_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+        cudaFuncSetAttribute(sn_bwd_apply_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+        sn_bwd_dot_tiled_kernel<<<total, kT, kTileSmemBytes, st>>>(p);
+        CB200_COUNT_LAUNCH();
+        sn_bwd_apply_tiled_kernel<<<total, kT, kTileSmemBytes, st>>>(p);
+        CB200_COUNT_LAUNCH();
+        CB200_CHECK_LAUNCH("sn_weight_bwd_batched");
+        return CB200_OK;
+    }
     for (int l = 0; l < n; ++l) {
         const cb200_sn_bwd_job& j = jobs[l];
         p.dwp[l] = j.dw_hat_packed; p.w[l] = j.w; p.u[l] = j.u; p.v[l] = j.v; p.sigma[l] = j.sigma; p.acc[l] = j.acc;
