@@ -55,6 +55,8 @@ struct TapGemmParams {
     const float* dact;    // same addressing as out; multiplies by (dact > 0 ? 1 : slope); or null
     float slope;          // LeakyReLU slope applied after bias (1.0 = identity) when dact == null
     int round_out;        // round outputs to TF32 (they feed another tensor-core GEMM)
+    float* colsum;        // [N] or null: += column sums of the stored outputs (bias gradient of the producing layer)
+    int n_total;          // N (columns of the whole problem)
     int debug;            // profiling experiments only (env CB200_TAPGEMM_DEBUG): 1 no stores, 2 no MMA, 4 no A loads, 8 no B loads
 };
 
@@ -76,7 +78,8 @@ constexpr int kEpiWarpFloats = 32 * kEpiStride;       // 4.5 KB per epilogue war
 
 template <int BN>
 __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
-                                                     uint32_t tmem_base, int warp, int lane, float* stage_buf) {
+                                                     uint32_t tmem_base, int warp, int lane, float* stage_buf,
+                                                     float* cs_smem = nullptr) {
     const int q = warp & 3;
     float* st = stage_buf + q * kEpiWarpFloats;
     int r = q * 32 + lane;
@@ -109,6 +112,7 @@ __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, con
         long long offs[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + sub);
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);       // column sums of this lane's 4 columns over its 8 rows
         float4 act[8];
         if (p.dact) {                      // all eight independent loads in flight before the first store
 #pragma unroll
@@ -132,6 +136,25 @@ __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, con
                 }
                 if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
                 *reinterpret_cast<float4*>(p.out + offs[it] + n0 + c0 + col4) = o;
+                cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+            }
+        }
+        if (p.colsum) {
+            // fold the four row groups of the warp (lane bits 3, 4); lanes 0..7 then hold 32-row sums of 4 columns
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8);  cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8);  cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+            if (sub == 0) {
+                if (cs_smem) {          // persistent kernel: this WARP's private partial sums, flushed once at the end
+                    float4* dst = reinterpret_cast<float4*>(cs_smem + n0 + c0 + col4);
+                    float4 t = *dst;
+                    t.x += cs.x; t.y += cs.y; t.z += cs.z; t.w += cs.w;
+                    *dst = t;
+                } else {
+                    float* dst = p.colsum + n0 + c0 + col4;
+                    atomicAdd(dst + 0, cs.x); atomicAdd(dst + 1, cs.y); atomicAdd(dst + 2, cs.z); atomicAdd(dst + 3, cs.w);
+                }
             }
         }
         __syncwarp();
@@ -379,13 +402,17 @@ tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
 //     -> coalesced stores) overlaps the MMAs of tile i+1 (tmem_full / tmem_empty barriers, the latter collecting
 //     the arrivals of the epilogue warps of BOTH CTAs at the pair leader).
 // ------------------------------------------------------------------------------------------------
+constexpr int kColsumMax = 512;     // widest N whose fused column sums are kept per CTA in shared memory
+
 template <int BN, int MT, int STAGES>
 struct SmemLayoutP {
     static constexpr int kATile = MT * kATileBytes;
     static constexpr int kBTile = (BN / 2) * kBlockK * 4;
     static constexpr int kStageBytes = kATile + kBTile;
     static constexpr int kEpiOffset = STAGES * kStageBytes;
-    static constexpr int kBarOffset = kEpiOffset + 4 * kEpiWarpFloats * 4;
+    static constexpr int kCsCols = (BN == 64) ? 64 : kColsumMax;                    // columns kept per epilogue warp
+    static constexpr int kColsumOffset = kEpiOffset + 4 * kEpiWarpFloats * 4;       // [4 warps][kCsCols] floats
+    static constexpr int kBarOffset = kColsumOffset + 4 * kCsCols * 4;
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
@@ -405,6 +432,8 @@ tap_gemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* epi_buf = reinterpret_cast<float*>(smem + L::kEpiOffset);
+    // fused column sums: one private [kCsCols] slice per epilogue warp (plain read-modify-write, no atomics)
+    float* cs_smem = (p.colsum && p.n_total <= L::kCsCols) ? reinterpret_cast<float*>(smem + L::kColsumOffset) : nullptr;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
@@ -434,6 +463,8 @@ tap_gemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_co
         tc::fence_barrier_init();
     }
     if (warp == 2) tc::tmem_alloc2(tmem_slot, 2 * MT * BN);
+    if (cs_smem)
+        for (int i = threadIdx.x; i < 4 * L::kCsCols; i += kThreads) cs_smem[i] = 0.f;
     tc::fence_before_sync();
     tc::cluster_sync_all();
     tc::fence_after_sync();
@@ -531,11 +562,19 @@ tap_gemm_persist_kernel(const __grid_constant__ TapGemmParams p, const __grid_co
             for (int m = 0; m < MT; ++m) {
                 int base[4];
                 tile_base(mt0 + m, base);
-                epilogue_rows_nowait<BN>(p, base, cls, n0, tmem_base + (uint32_t)((ab * MT + m) * BN), warp, lane, epi_buf);
+                epilogue_rows_nowait<BN>(p, base, cls, n0, tmem_base + (uint32_t)((ab * MT + m) * BN), warp, lane, epi_buf,
+                                         cs_smem ? cs_smem + (warp & 3) * L::kCsCols : nullptr);
             }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive_cluster(&tmem_empty_bar[ab], 0);
+        }
+        if (cs_smem) {          // flush this CTA's partial column sums: one global atomic per column
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+            for (int i = (int)threadIdx.x - 128; i < p.n_total; i += 128) {
+                const float v = (cs_smem[i] + cs_smem[L::kCsCols + i]) + (cs_smem[2 * L::kCsCols + i] + cs_smem[3 * L::kCsCols + i]);
+                if (v != 0.f) atomicAdd(p.colsum + i, v);
+            }
         }
     }
     tc::fence_before_sync();
@@ -608,6 +647,7 @@ struct Epilogue {
     const float* dact;
     float slope;
     int round_out;
+    float* colsum = nullptr;
 };
 
 template <int BN, int STAGES>
@@ -755,6 +795,11 @@ int debug_flags() {
 int dispatch(const TapGemmParams& p_in, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
     TapGemmParams p = p_in;
     p.debug = debug_flags();
+    p.n_total = N;
+    if (p.colsum) {
+        cudaError_t e = cudaMemsetAsync(p.colsum, 0, sizeof(float) * (size_t)N, st);
+        if (e != cudaSuccess) { cb200_set_error("%s: colsum memset: %s", name, cudaGetErrorString(e)); return (int)e; }
+    }
     if (persist_mode() && m_tiles >= 64 && N % 64 == 0) {
         if (N % 256 == 0) return launch_persist<256, 1, 5>(p, m_tiles, N / 256, classes, st, name);   // 5 x 32 KB stages
         if (N % 128 == 0) return launch_persist<128, 2, 4>(p, m_tiles, N / 128, classes, st, name);   // 4 x 40 KB stages
@@ -825,6 +870,7 @@ int conv_like(const float* src, int Bn, int Hs, int Ws, int C,           // A te
     p.ntaps = ntaps; p.cblocks = C / kBlockK;
     p.ldo = ldo; p.b_rows_per_cls = N;
     p.out = out; p.bias = ep.bias; p.dact = ep.dact; p.slope = ep.slope; p.round_out = ep.round_out;
+    p.colsum = ep.colsum;
     const int m_tiles = p.tiles[0] * p.tiles[1] * p.tiles[2];
     return dispatch(p, N, m_tiles, classes, st, name);
 }
@@ -839,7 +885,7 @@ int conv_like(const float* src, int Bn, int Hs, int Ws, int C,           // A te
 // epi = LeakyReLU(slope) when dact == NULL, else multiply by lrelu'(dact[M,N]) (dact shares ldo with out).
 extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, long long ldb, const float* bias,
                                   const float* dact, float* out, long long ldo, int M, int N, int K, float slope,
-                                  int round_out, void* stream) {
+                                  int round_out, float* colsum, void* stream) {
     CB200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_nt: empty problem");
     CB200_CHECK_ARG(K % kBlockK == 0, "gemm_nt: K=%d must be a multiple of 32", K);
     CB200_CHECK_ARG(lda % 4 == 0 && ldo % 4 == 0 && ldb % 4 == 0, "gemm_nt: lda/ldb/ldo must be multiples of 4 floats");
@@ -863,6 +909,7 @@ extern "C" int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw
     p.ntaps = 1; p.cblocks = K / kBlockK;
     p.ldo = (int)ldo; p.b_rows_per_cls = 0;
     p.out = out; p.bias = bias; p.dact = dact; p.slope = slope; p.round_out = round_out;
+    p.colsum = colsum;
     return dispatch(p, N, p.tiles[0], 1, static_cast<cudaStream_t>(stream), "gemm_nt_tf32");
 }
 
@@ -933,9 +980,9 @@ extern "C" int cb200_conv2d_nhwc_fwd(const float* x, const float* wmat, const fl
 // This is also ConvTranspose2d(4,2,1) / ConvTranspose2d(3,1,1) *forward* (G_SNDCGAN) with bias_out / slope.
 extern "C" int cb200_conv2d_nhwc_dgrad(const float* dy, const float* wmat_t, const float* act_in, const float* bias_out,
                                        float* dx, int B, int H, int W, int Cin, int Cout, int ks, int stride,
-                                       float slope, int round_out, void* stream) {
+                                       float slope, int round_out, float* colsum, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    Epilogue ep{bias_out, act_in, slope, round_out};
+    Epilogue ep{bias_out, act_in, slope, round_out, colsum};
     if (ks == 3 && stride == 1) {
         int taps[9][2];
         for (int kh = 0; kh < 3; ++kh)

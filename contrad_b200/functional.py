@@ -4,10 +4,16 @@ into the C ABI (contrad_b200.kernels); there is no ATen math on the activation p
 Layout convention inside the discriminator: activations are NHWC fp32, TF32-rounded by the producing
 epilogue; weights are consumed as packed GEMM matrices written by the spectral-norm kernels.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
 from . import kernels as K
+
+
+# bias gradients as column sums fused into the producing GEMM epilogue (CB200_FUSED_COLSUM=0: separate kernel)
+_FUSE_COLSUM = os.environ.get("CB200_FUSED_COLSUM", "1") != "0"
 
 
 def _c(t):
@@ -189,16 +195,24 @@ class SNDCGANBackboneFn(Function):
         grads_w, grads_b = [None] * L, [None] * L
         # g = gradient w.r.t. the pre-activation of the last layer
         g = K.lrelu_bwd(_c(dfeat).view_as(acts[-1]), acts[-1], SNDCGANBackboneFn.SLOPE, round_out=True)
+        if need_b[L - 1]:
+            grads_b[L - 1] = K.colsum(g.view(-1, g.shape[-1]))
         for li in range(L - 1, 0, -1):
             s = specs[li]
             a_in = acts[li - 1]
             if need_w[li]:
                 grads_w[li] = K.conv2d_nhwc_wgrad(a_in, g, s.ks, s.stride)
-            if need_b[li]:
-                grads_b[li] = K.colsum(g.view(-1, g.shape[-1]))
             if li > 1 or need_x or need_w[0] or need_b[0]:
+                # the data gradient (x lrelu') IS dL/d(pre-activation) of layer li-1: its column sum, fused into the
+                # GEMM epilogue, is that layer's bias gradient (layer 0 gets its own from conv_first_wgrad)
+                db_prev = None
+                if li > 1 and need_b[li - 1] and _FUSE_COLSUM:
+                    db_prev = torch.empty(a_in.shape[-1], device=a_in.device, dtype=torch.float32)
                 g = K.conv2d_nhwc_dgrad(g, ctx.dgrad[li], tuple(a_in.shape), s.ks, s.stride, act_in=a_in,
-                                        slope=SNDCGANBackboneFn.SLOPE, round_out=True)
+                                        slope=SNDCGANBackboneFn.SLOPE, round_out=True, colsum=db_prev)
+                if li > 1 and need_b[li - 1] and db_prev is None:
+                    db_prev = K.colsum(g.view(-1, g.shape[-1]))
+                grads_b[li - 1] = db_prev
             else:
                 g = None
         dx = None
@@ -372,6 +386,7 @@ class HeadsFn(Function):
         dev = feat.device
         ng = ctx.needs_input_grad
         dH = torch.empty_like(H)
+        db_cat = torch.empty(3 * hid, device=dev, dtype=torch.float32) if (ng[4] and _FUSE_COLSUM) else None    # = colsum(dH)
         parts = ((dd, ctx.t_l2, 0, 32), (dp1, ctx.t_p1, 1, None), (dp2, ctx.t_p2, 2, None))
         used = [False, False, False]
         padded = [None, None, None]
@@ -379,6 +394,8 @@ class HeadsFn(Function):
             sl = slice(idx * hid, (idx + 1) * hid)
             if g is None:
                 dH[:, sl].zero_()
+                if db_cat is not None:
+                    db_cat[sl].zero_()
                 continue
             used[idx] = True
             g = _c(g)
@@ -389,7 +406,8 @@ class HeadsFn(Function):
                 g = gp[:, :pad]
             else:
                 padded[idx] = g
-            K.gemm_nt(g, wt, None, slope=HeadsFn.SLOPE, round_out=True, out=dH[:, sl], dact=H[:, sl])
+            K.gemm_nt(g, wt, None, slope=HeadsFn.SLOPE, round_out=True, out=dH[:, sl], dact=H[:, sl],
+                      colsum=None if db_cat is None else db_cat[sl])
         grads = [None] * 11
         # second-layer weight / bias gradients
         for (g, wt, idx, pad), wpos, bpos in zip(parts, (5, 7, 9), (6, 8, 10)):
@@ -406,7 +424,7 @@ class HeadsFn(Function):
         if ng[3]:
             grads[3] = K.gemm_tn_wgrad(dH, feat)
         if ng[4]:
-            grads[4] = K.colsum(dH)
+            grads[4] = db_cat if db_cat is not None else K.colsum(dH)
         if ng[2]:
             lo = hid if ctx.sg_linear else 0
             # only heads that actually received a gradient contribute (dH of the others is zero)

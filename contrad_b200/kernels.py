@@ -63,9 +63,16 @@ def augment_simclr_bwd(x, dy, params, order):
 
 
 # ------------------------------------------------------------------ tensor-core GEMM / conv
-def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None):
+def _colsum_buf(colsum, n):
+    if colsum is not None:
+        assert colsum.is_cuda and colsum.dtype == torch.float32 and colsum.is_contiguous() and colsum.numel() == n
+    return colsum
+
+
+def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None, colsum=None):
     """out[M,N] = lrelu_slope(a[M,K] @ bw[N,K]^T + bias), or (...) * lrelu'(dact) when dact is given.
-    `a`, `bw`, `out`, `dact` may be row-strided 2-D views (dact must share out's row stride)."""
+    `a`, `bw`, `out`, `dact` may be row-strided 2-D views (dact must share out's row stride).
+    colsum: optional contiguous [N] tensor that receives the column sums of `out` (fused into the epilogue)."""
     assert a.dim() == 2 and bw.dim() == 2 and a.shape[1] == bw.shape[1]
     assert a.stride(1) == 1 and bw.stride(1) == 1
     M, K = a.shape
@@ -77,7 +84,7 @@ def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None):
         assert dact.shape == (M, N) and dact.stride(1) == 1 and dact.stride(0) == out.stride(0)
     _call("gemm_nt_tf32", 2.0 * M * N * K, 4 * (M * K + N * K + M * N), lib().cb200_gemm_nt_tf32, ptr(a), i64(a.stride(0)), ptr(bw), i64(bw.stride(0)), ptr(bias), ptr(dact), ptr(out),
                                    i64(out.stride(0)), i32(M), i32(N), i32(K), f32(slope), i32(1 if round_out else 0),
-                                   stream_ptr())
+                                   ptr(_colsum_buf(colsum, N)), stream_ptr())
     return out
 
 
@@ -95,15 +102,18 @@ def conv2d_nhwc_fwd(x, wmat, bias, ks, stride, slope=1.0, round_out=False):
     return y
 
 
-def conv2d_nhwc_dgrad(dy, wmat_t, in_shape, ks, stride, act_in=None, bias_out=None, slope=1.0, round_out=False):
-    """dy [B,Ho,Wo,Cout] -> dx [B,H,W,Cin] (in_shape).  wmat_t: see pack_dgrad_weight."""
+def conv2d_nhwc_dgrad(dy, wmat_t, in_shape, ks, stride, act_in=None, bias_out=None, slope=1.0, round_out=False,
+                      colsum=None):
+    """dy [B,Ho,Wo,Cout] -> dx [B,H,W,Cin] (in_shape).  wmat_t: see pack_dgrad_weight.
+    colsum: optional contiguous [Cin] tensor that receives sum over pixels of dx (= the bias gradient of the layer
+    that produced the activation `act_in`)."""
     dy = _f32c(dy, "dy")
     B, H, W, Cin = in_shape
     Cout = dy.shape[3]
     dx = torch.empty(B, H, W, Cin, device=dy.device, dtype=torch.float32)
     _call("conv2d_nhwc_dgrad", 2.0 * B * (H // stride) * (W // stride) * Cout * Cin * ks * ks, 4 * (dy.numel() + wmat_t.numel() + dx.numel()), lib().cb200_conv2d_nhwc_dgrad, ptr(dy), ptr(wmat_t), ptr(act_in), ptr(bias_out), ptr(dx), i32(B), i32(H),
                                         i32(W), i32(Cin), i32(Cout), i32(ks), i32(stride), f32(slope),
-                                        i32(1 if round_out else 0), stream_ptr())
+                                        i32(1 if round_out else 0), ptr(_colsum_buf(colsum, Cin)), stream_ptr())
     return dx
 
 

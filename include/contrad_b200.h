@@ -62,16 +62,20 @@ int cb200_augment_simclr_bwd(const float* x, const float* dy, float* dx, const f
  * conv dgrad: dx[B,H,W,Cin] = conv^T(dy[B,Ho,Wo,Cout]) (* lrelu'(act_in) when act_in != NULL,
  *            + bias_out then lrelu_slope otherwise); wmat_t layouts are produced by
  *            cb200_sn_pack_weights.  Also serves ConvTranspose2d forward in G_SNDCGAN.
- * round_out: round outputs to TF32 (nearest) because they feed another tensor-core GEMM. */
+ * round_out: round outputs to TF32 (nearest) because they feed another tensor-core GEMM.
+ * colsum   : optional [N] / [Cin] buffer (zeroed inside) that receives the column sums of the STORED outputs.  In the
+ *            backward pass the output of a data-gradient GEMM is dL/d(pre-activation) of the previous layer, whose
+ *            column sum is that layer's bias gradient (autograd of `nn.Conv2d` / `nn.Linear` bias): fusing it into
+ *            the epilogue saves one full read of the gradient tensor per layer. */
 int cb200_gemm_nt_tf32(const float* a, long long lda, const float* bw, long long ldb, const float* bias,
                        const float* dact, float* out, long long ldo, int M, int N, int K, float slope,
-                       int round_out, void* stream);
+                       int round_out, float* colsum, void* stream);
 int cb200_conv2d_nhwc_fwd(const float* x, const float* wmat, const float* bias, float* y, int B, int H,
                           int W, int Cin, int Cout, int ks, int stride, float slope, int round_out,
                           void* stream);
 int cb200_conv2d_nhwc_dgrad(const float* dy, const float* wmat_t, const float* act_in,
                             const float* bias_out, float* dx, int B, int H, int W, int Cin, int Cout,
-                            int ks, int stride, float slope, int round_out, void* stream);
+                            int ks, int stride, float slope, int round_out, float* colsum, void* stream);
 
 /* wgrad: dw_hat[Cout, ks*ks*Cin] (forward-pack layout) = sum over pixels dy (x) shifted x; both operands are
  * MN-major tcgen05 tiles, split-K over pixels with fp32 atomics (buffer is zeroed inside).

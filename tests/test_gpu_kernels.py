@@ -116,10 +116,13 @@ def test_gemm_nt_tf32(K, M, N, K_):
     a = K.round_tf32(torch.randn(M, K_, device="cuda"))
     b = K.round_tf32(torch.randn(N, K_, device="cuda") * 0.05)
     bias = torch.randn(N, device="cuda")
-    out = K.gemm_nt(a, b, bias, slope=0.1)
+    colsum = torch.full((N,), float("nan"), device="cuda")
+    out = K.gemm_nt(a, b, bias, slope=0.1, colsum=colsum)
     ref = F.leaky_relu(a.double() @ b.double().t() + bias.double(), 0.1).float()
     err = (out - ref).abs().max() / ref.abs().max()
     assert err < 5e-5, err
+    want = out.double().sum(0)
+    assert ((colsum.double() - want).abs().max() / out.double().abs().sum(0).max()) < 1e-6
 
 
 def test_gemm_nt_strided_views(K):
@@ -157,12 +160,17 @@ def test_conv_fwd_and_dgrad(K, B, H, Cin, Cout, ks, stride):
     # data gradient, fused with lrelu'(input activation)
     dy = K.round_tf32(torch.randn(B, Cout, H // stride, H // stride, device="cuda"))
     act = torch.randn(B, H, H, Cin, device="cuda")
+    colsum = torch.full((Cin,), float("nan"), device="cuda")            # zeroed inside the call
     dx = K.conv2d_nhwc_dgrad(dy.permute(0, 2, 3, 1).contiguous(), K.pack_dgrad_weight(w, stride),
-                             (B, H, H, Cin), ks, stride, act_in=act, slope=0.1)
+                             (B, H, H, Cin), ks, stride, act_in=act, slope=0.1, colsum=colsum)
     ref_dx = torch.nn.grad.conv2d_input((B, Cin, H, H), w.double(), dy.double(), stride=stride, padding=1)
     ref_dx = (ref_dx.permute(0, 2, 3, 1) * torch.where(act > 0, 1.0, 0.1).double()).float()
     err = (dx - ref_dx).abs().max() / ref_dx.abs().max()
     assert err < 2e-5, ("dgrad", err)
+    # fused column sums (= bias gradient of the producing layer) are the sums of the values actually stored
+    want = dx.double().sum(dim=(0, 1, 2))
+    scale = dx.double().abs().sum(dim=(0, 1, 2)).max()
+    assert ((colsum.double() - want).abs().max() / scale) < 1e-6, ("colsum", (colsum.double() - want).abs().max(), scale)
 
 
 @pytest.mark.parametrize("B,H,Cin,Cout,ks,stride", CONV_CASES[:6] + [(4, 8, 128, 128, 3, 1), (130, 4, 64, 128, 4, 2)])

@@ -37,5 +37,15 @@ elif which == "augment":
     xx = torch.rand(Bn, 3, 32, 32, device="cuda")
     for _ in range(4):
         K.augment_simclr_fwd(xx, p, order)
+elif which in ("conv_first_wgrad", "conv_first_fwd"):
+    xx = torch.rand(B, 3, 32, 32, device="cuda")
+    w = torch.randn(64, 3, 3, 3, device="cuda") * 0.1
+    bias = torch.zeros(64, device="cuda")
+    dy = K.round_tf32(torch.randn(B, 32, 32, 64, device="cuda"))
+    for _ in range(4):
+        if which == "conv_first_fwd":
+            K.conv_first_fwd(xx, w, None, bias)
+        else:
+            K.conv_first_wgrad(xx, dy)
 torch.cuda.synchronize()
 print("done", which)
