@@ -31,9 +31,9 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     const int h0 = blockIdx.y * kRows;
     const int w0 = blockIdx.x * kCols;
     const float inv_sigma = sigma ? sigma[1] : 1.f;
-    for (int i = threadIdx.x; i < 27 * kCo; i += kThreads) {
-        int co = i / 27, t = i % 27;
-        ws[t][co] = __ldg(w + i) * inv_sigma;
+    for (int i = threadIdx.x; i < 27 * kCo; i += kThreads) {        // lanes along co: conflict-free shared stores
+        int t = i / kCo, co = i % kCo;
+        ws[t][co] = __ldg(w + co * 27 + t) * inv_sigma;
     }
     for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
         int c = i / ((kRows + 2) * (kCols + 2));
@@ -89,60 +89,158 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 }
 
 // dW_hat[co][ci*9+kh*3+kw] += sum_pixels dY[pix][co] * (2x-1)[ci][h+kh-1][w+kw-1];   db[co] += sum dY
-// Persistent CTAs: each CTA walks a strided list of (image, 4-row x 32-col) tiles and keeps its partial
-// dW in REGISTERS across tiles, so the global atomics are issued once per CTA (grid * 1792 in total)
-// instead of once per tile.  Threads: 16 channel groups (4 channels) x 4 tap groups (7 taps; 27 = 7+7+7+6)
-// x 4 pixel slices (one output row each).
-__global__ void __launch_bounds__(kThreads)
+// ---- async staging helpers (cp.async.bulk + mbarrier, as in augment.cu) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; spin < (1u << 26) && !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+    if (!ok) __trap();
+}
+
+constexpr int kXsElems = 3 * (kRows + 2) * (kCols + 2);            // 612 image values (+halo) per tile
+constexpr int kXsPerThread = (kXsElems + kThreads - 1) / kThreads;  // 3
+constexpr int kDyTileFloats = kRows * kCols * kCo;                  // 8192 floats = 32 KB
+constexpr size_t kWgradSmemBytes = (size_t)(2 * kDyTileFloats + 2 * kXsElems) * sizeof(float) + 2 * sizeof(uint64_t);
+
+// Persistent CTAs: each CTA walks a strided list of (image, 4-row x 32-col) tiles and keeps its partial dW in
+// REGISTERS across tiles, so the global atomics are issued once per CTA.  Threads: 16 channel groups (4 channels)
+// x 4 tap groups (7 taps; 27 = 7+7+7+6) x 4 pixel slices (one output row each).
+// The dY tile of the NEXT iteration (4 rows x 32 px x 64 ch = 32 KB, contiguous per row) is fetched by
+// cp.async.bulk into the other half of a shared-memory ring while the current one is consumed, and the image halo
+// tile of the next iteration is loaded into registers before the FMA loop and parked in shared memory after it:
+// the first version read dY straight from global memory and sat in long-scoreboard stalls 7.8 of every 8 issue
+// slots (profiles/prof_r1_conv_first_wgrad.md).
+__global__ void __launch_bounds__(kThreads, 3)
 conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                         float* __restrict__ db, int B, int H, int W, float in_scale, float in_shift) {
-    __shared__ float xs[3][kRows + 2][kCols + 2];
-    __shared__ __align__(16) float part[4][28][kCo];      // per pixel-slice partial dW (27 taps + 1 bias row)
+    extern __shared__ __align__(128) float wsm[];
+    float* dys = wsm;                                   // [2][kRows][kCols][kCo]
+    float* xsb = wsm + 2 * kDyTileFloats;               // [2][3][kRows+2][kCols+2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xsb + 2 * kXsElems);
     const int tiles_w = (W + kCols - 1) / kCols, tiles_h = (H + kRows - 1) / kRows;
     const int ntiles = tiles_w * tiles_h * B;
     const int cg = threadIdx.x & 15;
     const int tg = (threadIdx.x >> 4) & 3;
     const int ps = threadIdx.x >> 6;          // pixel slice = output row within the tile
+
+    // this thread's slots of the image halo tile (tile independent)
+    int xs_c[kXsPerThread], xs_r[kXsPerThread], xs_cc[kXsPerThread];
+#pragma unroll
+    for (int k = 0; k < kXsPerThread; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        xs_c[k] = i / ((kRows + 2) * (kCols + 2));
+        xs_r[k] = (i / (kCols + 2)) % (kRows + 2);
+        xs_cc[k] = i % (kCols + 2);
+    }
+    // this thread's taps: offset of tap t inside the halo tile
+    int tap_off[7];
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+        const int tap = min(tg * 7 + t, 26);
+        tap_off[t] = ((tap / 9) * (kRows + 2) + (tap % 9) / 3) * (kCols + 2) + tap % 3;
+    }
+    auto tile_origin = [&](int tile, int& b, int& h0, int& w0) {
+        b = tile / (tiles_w * tiles_h);
+        const int rem = tile - b * tiles_w * tiles_h;
+        h0 = (rem / tiles_w) * kRows;
+        w0 = (rem % tiles_w) * kCols;
+    };
+    auto load_x = [&](int tile, float (&v)[kXsPerThread]) {
+        int b, h0, w0;
+        tile_origin(tile, b, h0, w0);
+#pragma unroll
+        for (int k = 0; k < kXsPerThread; ++k) {
+            const int hh = h0 + xs_r[k] - 1, ww = w0 + xs_cc[k] - 1;
+            v[k] = 0.f;
+            if (threadIdx.x + k * kThreads < kXsElems && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                v[k] = __ldg(x + ((size_t)(b * 3 + xs_c[k]) * H + hh) * W + ww) * in_scale + in_shift;
+        }
+    };
+    auto park_x = [&](int buf, const float (&v)[kXsPerThread]) {
+#pragma unroll
+        for (int k = 0; k < kXsPerThread; ++k)
+            if (threadIdx.x + k * kThreads < kXsElems) xsb[buf * kXsElems + threadIdx.x + k * kThreads] = v[k];
+    };
+    auto fetch_dy = [&](int tile, int buf) {              // one elected thread
+        int b, h0, w0;
+        tile_origin(tile, b, h0, w0);
+        const int rows = min(kRows, H - h0), ncols = min(kCols, W - w0);
+        const uint32_t row_bytes = (uint32_t)ncols * kCo * sizeof(float);
+        bar_expect_tx(&bars[buf], row_bytes * rows);
+        for (int r = 0; r < rows; ++r)
+            bulk_load(dys + buf * kDyTileFloats + r * kCols * kCo, dy + (((size_t)b * H + h0 + r) * W + w0) * kCo, row_bytes,
+                      &bars[buf]);
+    };
+
     float acc[7][4];
     float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int t = 0; t < 7; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = tile / (tiles_w * tiles_h);
-        const int rem = tile - b * tiles_w * tiles_h;
-        const int h0 = (rem / tiles_w) * kRows, w0 = (rem % tiles_w) * kCols;
-        __syncthreads();
-        for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
-            int c = i / ((kRows + 2) * (kCols + 2));
-            int r = (i / (kCols + 2)) % (kRows + 2);
-            int cc = i % (kCols + 2);
-            int hh = h0 + r - 1, ww = w0 + cc - 1;
-            float v = 0.f;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * in_scale + in_shift;
-            xs[c][r][cc] = v;
+
+    if (threadIdx.x == 0) {
+        bar_init(&bars[0], 1);
+        bar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+        if (threadIdx.x == 0) fetch_dy(tile, 0);
+        float v[kXsPerThread];
+        load_x(tile, v);
+        park_x(0, v);
+    }
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int next = tile + gridDim.x;
+        float vnext[kXsPerThread];
+        if (next < ntiles) {
+            if (threadIdx.x == 0) fetch_dy(next, buf ^ 1);
+            load_x(next, vnext);                      // in flight during the FMA loop below
         }
-        __syncthreads();
-        const int hh = h0 + ps;
-        if (hh < H) {
-            const float* dyrow = dy + (((size_t)b * H + hh) * W + w0) * kCo + cg * 4;
+        bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
+        __syncthreads();                               // halo tile `buf` parked by everybody
+        int b, h0, w0;
+        tile_origin(tile, b, h0, w0);
+        if (h0 + ps < H) {
+            const float* grow = dys + buf * kDyTileFloats + (ps * kCols) * kCo + cg * 4;
+            const float* xrow = xsb + buf * kXsElems + ps * (kCols + 2);
             const int ncols = min(kCols, W - w0);
 #pragma unroll 4
             for (int c = 0; c < ncols; ++c) {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(dyrow + (size_t)c * kCo));
+                const float4 g = *reinterpret_cast<const float4*>(grow + c * kCo);
                 if (tg == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
 #pragma unroll
                 for (int t = 0; t < 7; ++t) {
-                    const int tap = tg * 7 + t;
-                    if (tap < 27) {
-                        const int ci = tap / 9, kh = (tap % 9) / 3, kw = tap % 3;
-                        const float xv = xs[ci][ps + kh][c + kw];
-                        acc[t][0] += g.x * xv; acc[t][1] += g.y * xv; acc[t][2] += g.z * xv; acc[t][3] += g.w * xv;
-                    }
+                    const float xv = xrow[tap_off[t] + c];
+                    acc[t][0] += g.x * xv; acc[t][1] += g.y * xv; acc[t][2] += g.z * xv; acc[t][3] += g.w * xv;
                 }
             }
         }
+        if (next < ntiles) park_x(buf ^ 1, vnext);
+        __syncthreads();                               // buffer `buf` is free for the prefetch of iteration it+1
     }
+    // reduce the four pixel slices through shared memory (the dY ring is dead now), then one atomic per element
+    float (*part)[28][kCo] = reinterpret_cast<float (*)[28][kCo]>(dys);
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
         const int tap = tg * 7 + t;
@@ -192,9 +290,11 @@ extern "C" int cb200_conv_first_wgrad(const float* x, const float* dy, float* dw
                                       float in_scale, float in_shift, void* stream) {
     CB200_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv_first_wgrad: empty input");
     const long long ntiles = (long long)((W + kCols - 1) / kCols) * ((H + kRows - 1) / kRows) * B;
-    const int grid = (int)(ntiles < 4 * 148 ? ntiles : 4 * 148);
-    conv_first_wgrad_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dw_hat, db, B, H, W,
-                                                                                      in_scale, in_shift);
+    CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "conv_first_wgrad: dy must be 16-byte aligned");
+    const int grid = (int)(ntiles < 3 * 148 ? ntiles : 3 * 148);           // 3 resident CTAs per SM (69 KB smem each)
+    cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes);
+    conv_first_wgrad_kernel<<<grid, kThreads, kWgradSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+        x, dy, dw_hat, db, B, H, W, in_scale, in_shift);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("conv_first_wgrad");
     return CB200_OK;

@@ -410,7 +410,7 @@ struct SmemLayoutP {
     static constexpr int kBTile = (BN / 2) * kBlockK * 4;
     static constexpr int kStageBytes = kATile + kBTile;
     static constexpr int kEpiOffset = STAGES * kStageBytes;
-    static constexpr int kCsCols = (BN == 64) ? 64 : kColsumMax;                    // columns kept per epilogue warp
+    static constexpr int kCsCols = (BN <= 64) ? 64 : kColsumMax;                    // columns kept per epilogue warp
     static constexpr int kColsumOffset = kEpiOffset + 4 * kEpiWarpFloats * 4;       // [4 warps][kCsCols] floats
     static constexpr int kBarOffset = kColsumOffset + 4 * kCsCols * 4;
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;
@@ -776,6 +776,7 @@ int pair_mode() {
 // be encoded with exactly this many rows.  Mirrors the kernel choice made in dispatch().
 int b_box_rows(int N, int m_tiles) {
     if (persist_mode() && m_tiles >= 64 && N % 64 == 0) return (N % 256 == 0) ? 128 : (N % 128 == 0 ? 64 : 32);
+    if (persist_mode() && m_tiles >= 64 && N == 32) return 16;
     if (pair_mode() && m_tiles >= 296) {
         if (N % 256 == 0) return 128;      // pair, BN = 256: half per CTA
         if (N % 128 == 0) return 64;       // pair, BN = 128
@@ -804,6 +805,9 @@ int dispatch(const TapGemmParams& p_in, int N, int m_tiles, int classes, cudaStr
         if (N % 256 == 0) return launch_persist<256, 1, 5>(p, m_tiles, N / 256, classes, st, name);   // 5 x 32 KB stages
         if (N % 128 == 0) return launch_persist<128, 2, 4>(p, m_tiles, N / 128, classes, st, name);   // 4 x 40 KB stages
         return launch_persist<64, 4, 3>(p, m_tiles, N / 64, classes, st, name);                        // 3 x 68 KB stages
+    }
+    if (persist_mode() && m_tiles >= 64 && N == 32) {     // thin outputs (3 image channels padded to 32): A-supply bound
+        return launch_persist<32, 4, 3>(p, m_tiles, 1, classes, st, name);                             // 3 x 66 KB stages
     }
     if (pair_mode() && m_tiles >= 296) {
         if (N % 256 == 0) return launch2<256, 4>(p, m_tiles, N / 256, classes, st, name);     // 32 KB / stage / CTA

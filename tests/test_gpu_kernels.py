@@ -142,6 +142,8 @@ CONV_CASES = [
     (8, 32, 64, 128, 4, 2), (8, 16, 128, 128, 3, 1), (8, 16, 128, 256, 4, 2), (6, 8, 256, 256, 3, 1),
     (16, 8, 256, 512, 4, 2), (16, 4, 512, 512, 3, 1), (3, 4, 64, 64, 3, 1), (5, 8, 32, 32, 4, 2),
     (301, 16, 128, 128, 3, 1), (600, 16, 128, 256, 4, 2), (1201, 8, 256, 256, 3, 1), (1200, 32, 64, 128, 4, 2),
+    # thin data gradients (N = Cin = 32: the 3 image channels padded to 32) on the persistent BN = 32 variant
+    (700, 16, 32, 64, 3, 1), (300, 32, 32, 64, 4, 2),
 ]
 
 
