@@ -109,6 +109,58 @@ def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=Tr
     return out
 
 
+def train_step_stylegan2(P, opt, GD, g_ema, optimizers, images, step, record_grad_norms=False):
+    """One iteration of train_stylegan2_contraD.py:195-236 (n_critic = 1): LR schedule, EMA `accumulate`, G step
+    through the frozen D, D step (contrastive losses + nonsat L_dis + lazy R1 every `P.d_reg_every` steps).
+    GD is `training.gan.stylegan2.G_D(G, D, augment_fn)`; P carries use_warmup, halflife_lr, ema_start_k, accum,
+    d_reg_every, lbd_r1, style_mix, temp, lbd_a, distributed.  Returns a dict of 0-dim tensors (no host sync)."""
+    from .training.gan import stylegan2 as T
+    generator, discriminator = GD.G, GD.D
+    opt_G, opt_D = optimizers
+    d_regularize = (step % P.d_reg_every == 0) and (P.lbd_r1 > 0)
+    if P.use_warmup:
+        update_warmup(opt_G, step, opt["warmup"], opt["lr"])
+        update_warmup(opt_D, step, opt["warmup"], opt["lr_d"])
+    if (not P.use_warmup) or step > opt["warmup"]:
+        T.update_lr(opt_G, step, opt["batch_size"], P.halflife_lr, opt["lr"])
+        T.update_lr(opt_D, step, opt["batch_size"], P.halflife_lr, opt["lr_d"])
+    if g_ema is not None:
+        do_ema = (step * opt["batch_size"]) > (P.ema_start_k * 1000)
+        T.accumulate(g_ema, generator, P.accum if do_ema else 0)
+    generator.train()
+    discriminator.train()
+    out = {}
+
+    set_grad(generator, True)
+    set_grad(discriminator, False)
+    d_gen = GD(P, images, style_mix=P.style_mix, train_G=True)
+    g_loss = T.loss_G_fn(d_gen)
+    opt_G.zero_grad()
+    g_loss.backward()
+    if record_grad_norms:
+        out["g_grad_norm"] = grad_norm(generator)
+    opt_G.step()
+    out["g_loss"] = g_loss.detach()
+
+    set_grad(generator, False)
+    set_grad(discriminator, True)
+    d_all, view_r, view_f = GD(P, images, style_mix=P.style_mix)
+    d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+    loss = d_loss + aux["penalty"]
+    if d_regularize:
+        r1 = GD(P, images, return_r1_loss=True).mean()
+        loss = loss + (0.5 * P.lbd_r1) * r1 * P.d_reg_every
+        out["d_r1"] = r1.detach()
+    opt_D.zero_grad()
+    loss.backward()
+    if record_grad_norms:
+        out["d_grad_norm"] = grad_norm(discriminator)
+    opt_D.step()
+    out.update(d_loss=d_loss.detach(), d_penalty=aux["penalty"].detach(), d_real=aux["d_real"].detach(),
+               d_gen=aux["d_gen"].detach())
+    return out
+
+
 class GraphedTrainStep(object):
     """``train_step`` captured once into a CUDA graph and replayed.
 

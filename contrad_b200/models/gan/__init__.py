@@ -7,8 +7,22 @@ def get_architecture(architecture, image_size, P=None):
         generator = G_SNDCGAN(image_size=image_size)
         discriminator = D_SNDCGAN(image_size=image_size, mlp_linear=True, d_hidden=512)
         return generator, discriminator
-    if architecture in ("snresnet18", "stylegan2", "stylegan2_512"):
+    if architecture == "stylegan2":
+        from .stylegan2.discriminator import ResidualDiscriminatorP
+        from .stylegan2.generator import Generator
+        resolution = image_size[0]
+        generator = Generator(size=resolution, n_mlp=8, small32=True)
+        discriminator = ResidualDiscriminatorP(size=resolution, small32=True, mlp_linear=True, d_hidden=512)
+        return generator, discriminator
+    if architecture == "stylegan2_512":
+        from .stylegan2.discriminator import ResidualDiscriminatorP
+        from .stylegan2.generator import Generator
+        resolution = image_size[0]
+        generator = Generator(size=resolution, n_mlp=8, channel_multiplier=1.0)
+        discriminator = ResidualDiscriminatorP(size=resolution, channel_multiplier=1.0, mlp_linear=True, d_hidden=512)
+        return generator, discriminator
+    if architecture == "snresnet18":
         raise NotImplementedError(
-            "architecture %r is a later row of the hot-path scope table (SURVEY 8a a18-a22 / 8f f4); "
-            "round 1 of contrad_b200 builds 'sndcgan'" % architecture)
+            "architecture %r is a later row of the hot-path scope table (SURVEY 8f f4); "
+            "contrad_b200 builds 'sndcgan', 'stylegan2' and 'stylegan2_512'" % architecture)
     raise NotImplementedError()

@@ -198,6 +198,70 @@ int cb200_adam_step(const struct cb200_adam_tensor* tensors, int n, float lr, fl
 int cb200_adam_step_dev(const struct cb200_adam_tensor* tensors, int n, const float* hyper, float beta1, float beta2,
                         float eps, void* stream);
 
+/* ---- StyleGAN2 side of the path (models/gan/stylegan2/*) ---------------------------
+ * All activations NHWC fp32 unless strides are given.  The dense contractions of ResidualDiscriminatorP and
+ * Generator run on the tensor-core entry points above (3x3 stride-1 convolutions: cb200_conv2d_nhwc_*; every
+ * 1x1 convolution, linear layer, the blurred 3x3 stride-2 convolution and the stride-2 transposed convolution:
+ * cb200_gemm_nt_tf32 / cb200_gemm_tn_wgrad on the patch matrices written by cb200_patch_s2_*).
+ *
+ * upfirdn2d      replaces op/upfirdn2d.py:145-200 + upfirdn2d_kernel.cu (`upfirdn2d(input, kernel, up, down, pad)`):
+ *                out = decimate_down(FIR(pad(zero_stuff_up(x)))); strides are {n, c, h, w} in elements, so the same
+ *                kernel serves the reference's NCHW op and the NHWC activations; negative pads crop; flip = 1 uses the
+ *                kernel as given (the backward pass, upfirdn2d.py:113), flip = 0 flips it like the reference forward;
+ *                c_fast = 1 makes the channel the fastest thread index (NHWC outputs).
+ * patch_s2       u[B,Ho,Wo,9,C] <-> x[B,2Ho+1,2Wo+1,C]: gather = im2col of `F.conv2d(stride=2, padding=0)` with a 3x3
+ *                kernel (layers.py:174-198 after Blur), scatter = its transpose = `F.conv_transpose2d(stride=2)`
+ *                (generator.py:66-72).
+ * bias_act       mode 0: y = lrelu_slope(x + bias[c]) * gain (+ res)  (op/fused_act.py:86-94, `(out+skip)/sqrt2` of
+ *                discriminator.py:70-76 folded in); mode 1: y = x * ((ref + bias[c]) > 0 ? gain : gain*slope), the
+ *                backward AND the backward-of-backward of mode 0 (op/fused_act.py:18-52).
+ * modulate       y[b,p,c] = x[b,p,c] * s[b,c] * alpha (generator.py:55-56 moved from the weights to the activations;
+ *                x_batch_stride 0 broadcasts ConstantInput); mul_reduce: out[b,c] = sum_p a[b,p,c] * w[b,p,c].
+ * mod_epilogue   y = lrelu(x * demod[b,c] + noise[b,p] * noise_weight[0] + bias[c]) * gain
+ *                (demodulation generator.py:58-60, NoiseInjection :85-94, FusedLeakyReLU); noise_grad: its weight grad.
+ * stddev_*       _minibatch_stddev_layer (discriminator.py:22-33): fwd -> std[B/G]; concat appends it as channel C of a
+ *                Cp-channel tensor (zero padded so that Cp % 32 == 0); split / bwd / bwd_bwd are the backward passes
+ *                (bwd_bwd: the R1 double backward).
+ * rgb_to_nhwc    y[b,h,w,c<3] = x[b,c,h,w]*scale + shift, other channels 0 (`input * 2. - 1.` discriminator.py:229);
+ *                nhwc_to_rgb: out[b,c,h,w] = src[b,h,w,c]*scale (+ res), the ToRGB skip sum (generator.py:133-143).
+ * pixelnorm      layers.py:15-20.  row_sqsum / row_scale: `grad.pow(2).reshape(B,-1).sum(1)` of r1_loss
+ *                (train_stylegan2.py:106-113) and its backward.  axpby: out = alpha*a + beta*b + gamma.
+ * ema_lerp       utils.py:130-143 `accumulate`: dst = decay*dst + (1-decay)*src for a table of tensors (host memory). */
+int cb200_upfirdn2d(const float* x, const long long* x_strides, float* y, const long long* y_strides, const float* fir,
+                    int N, int C, int Hi, int Wi, int Ho, int Wo, int up, int down, int pad_x0, int pad_y0, int kh, int kw,
+                    int flip, float gain, int c_fast, int round_out, void* stream);
+int cb200_patch_s2_gather(const float* x, float* u, int B, int Ho, int Wo, int C, int round_out, void* stream);
+int cb200_patch_s2_scatter(const float* u, float* x, int B, int Ho, int Wo, int C, int round_out, void* stream);
+int cb200_bias_act(const float* x, const float* bias, const float* ref, const float* res, float* y, long long n, int C,
+                   int mode, float slope, float gain, int round_out, void* stream);
+int cb200_modulate(const float* x, long long x_batch_stride, const float* s, float* y, int B, long long P, int C, float alpha,
+                   int round_out, void* stream);
+int cb200_mul_reduce(const float* a, const float* w, long long w_batch_stride, float* out, int B, long long P, int C,
+                     void* stream);
+int cb200_mod_epilogue(const float* x, const float* demod, const float* noise, const float* noise_weight, const float* bias,
+                       float* y, int B, long long P, int C, float slope, float gain, int round_out, void* stream);
+int cb200_noise_grad(const float* g, const float* noise, float* out1, long long rows, int C, void* stream);
+int cb200_stddev_fwd(const float* x, float* std, int B, long long F, void* stream);
+int cb200_stddev_bwd(const float* dstd, const float* x, float* dx, int B, long long F, void* stream);
+int cb200_stddev_bwd_bwd(const float* gg, const float* dstd, const float* x, float* d_dstd, float* d_x, int B, long long F,
+                         void* stream);
+int cb200_stddev_concat(const float* x, const float* std, float* y, int B, long long P, int C, int Cp, int round_out,
+                        void* stream);
+int cb200_stddev_split(const float* dy, float* dx, float* dstd, int B, long long P, int C, int Cp, void* stream);
+int cb200_rgb_to_nhwc(const float* x, float* y, int B, int H, int W, int cpad, float scale, float shift, int round_out,
+                      void* stream);
+int cb200_nhwc_to_rgb(const float* src, const float* res, float* out, int B, int H, int W, int cpad, float scale,
+                      void* stream);
+int cb200_pixelnorm(const float* x, float* y, int rows, int d, int round_out, void* stream);
+int cb200_row_sqsum(const float* x, float* out, int B, long long n, void* stream);
+int cb200_row_scale(const float* x, const float* s, float* y, int B, long long n, float alpha, void* stream);
+int cb200_axpby(const float* a, const float* b, float* out, long long n, float alpha, float beta, float gamma, int round_out,
+                void* stream);
+struct cb200_ema_tensor {
+    float* dst; const float* src; long long numel;
+};
+int cb200_ema_lerp(const struct cb200_ema_tensor* tensors, int n, float decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,371 @@
+"""GPU parity tests of the StyleGAN2 side of the path, through the C ABI.
+
+  * every kernel of csrc/sg2_ops.cu against its torch stand-in (tests/cpu_kernels.py; fp32, 1e-5);
+  * the tensor-core backed autograd families (MmNT/MmNN/MmTN, Conv3x3/Dgrad/Wgrad) incl. their double backward on
+    TF32-exact inputs (1e-4);
+  * ResidualDiscriminatorP, the R1 double backward, Generator (style mixing, explicit noise) and the D-step losses of
+    train_stylegan2_contraD.py against the fixtures produced by the unmodified reference (stylegan2_small.pt).
+    Tolerances here are TF32 tolerances (fp32 storage, TF32 multiply, fp32 accumulate - the reference's own GPU
+    arithmetic): 1e-2 of the tensor's max for activations / gradients, 5e-3 on loss scalars; the measured errors are
+    written to gpurun_out/sg2_parity.json.
+  * one full train_step_stylegan2 iteration (G step, D step with R1, EMA) runs and updates every parameter."""
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from tests import cpu_kernels as CK
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REPORT = {}
+
+
+@pytest.fixture(scope="module")
+def S():
+    from contrad_b200 import sg2_kernels
+    return sg2_kernels
+
+
+@pytest.fixture(scope="module")
+def K():
+    from contrad_b200 import kernels
+    return kernels
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _chk(name, a, b, tol):
+    err = _rel(a, b)
+    REPORT[name] = err
+    assert err < tol, "%s: rel err %.3e (tol %.1e)" % (name, err, tol)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("nhwc", [True, False])
+@pytest.mark.parametrize("H,W,k,up,down,pad", [(9, 7, (1, 3, 3, 1), 1, 1, (2, 2, 2, 2)), (8, 8, (1, 3, 3, 1), 1, 2, (1, 1, 1, 1)),
+                                               (5, 6, (1, 3, 3, 1), 2, 1, (2, 1, 2, 1)), (6, 5, (1, 2, 1), 2, 3, (0, 3, 0, 3)),
+                                               (8, 8, (1, 3, 3, 1), 1, 1, (-1, 2, -1, 2)), (33, 33, (1, 3, 3, 1), 1, 1, (1, 1, 1, 1)),
+                                               (16, 16, (1, 3, 3, 1), 2, 1, (2, 1, 2, 1))])
+def test_upfirdn2d(S, nhwc, H, W, k, up, down, pad):
+    torch.manual_seed(H * 100 + W + up + down)
+    C = 5 if not nhwc else 36
+    x = torch.randn(3, H, W, C) if nhwc else torch.randn(3, C, H, W)
+    fir = torch.tensor(k, dtype=torch.float32)
+    fir = fir[None] * fir[:, None]
+    fir = fir / fir.sum() * up * up
+    fir[0, 1] += 0.01                                       # break the symmetry so that flipping is observable
+    for flip in (False, True):
+        got = S.upfirdn2d(x.cuda(), fir.cuda(), up, down, pad, nhwc=nhwc, flip=flip, gain=1.5)
+        want = CK.upfirdn2d(x, fir, up, down, pad, nhwc=nhwc, flip=flip, gain=1.5)
+        assert got.shape == want.shape
+        assert _rel(got, want) < 1e-5
+    # explicit output size (the backward pass asks for the forward input size)
+    oh = (H * up + pad[2] + pad[3] - fir.shape[0]) // down + 2
+    got = S.upfirdn2d(x.cuda(), fir.cuda(), up, down, pad, out_hw=(oh, oh), nhwc=nhwc)
+    want = CK.upfirdn2d(x, fir, up, down, pad, out_hw=(oh, oh), nhwc=nhwc)
+    assert _rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("B,Ho,C", [(2, 4, 32), (3, 16, 128), (5, 1, 8)])
+def test_patch_s2(S, B, Ho, C):
+    torch.manual_seed(B + Ho)
+    x = torch.randn(B, 2 * Ho + 1, 2 * Ho + 1, C)
+    assert torch.equal(S.patch_s2_gather(x.cuda()).cpu(), CK.patch_s2_gather(x))
+    u = torch.randn(B, Ho, Ho, 9, C)
+    assert _rel(S.patch_s2_scatter(u.cuda()), CK.patch_s2_scatter(u)) < 1e-6
+    # gather / scatter are transposes of each other
+    lhs = (S.patch_s2_gather(x.cuda()) * u.cuda()).sum()
+    rhs = (x.cuda() * S.patch_s2_scatter(u.cuda())).sum()
+    assert abs(float(lhs - rhs)) < 1e-3 * abs(float(lhs)) + 1e-3
+
+
+def test_bias_act_modulate_epilogue(S):
+    torch.manual_seed(0)
+    B, H, C = 6, 8, 48
+    x, res, bias = torch.randn(B, H, H, C), torch.randn(B, H, H, C), torch.randn(C)
+    assert _rel(S.bias_act(x.cuda(), bias.cuda(), 0.2, 1.4, res=res.cuda()), CK.bias_act(x, bias, 0.2, 1.4, res=res)) < 1e-6
+    assert _rel(S.bias_act(x.cuda(), None, 0.1, 1.0), CK.bias_act(x, None, 0.1, 1.0)) < 1e-6
+    g = torch.randn(B, H, H, C)
+    assert _rel(S.bias_act_grad(g.cuda(), x.cuda(), bias.cuda(), 0.2, 1.4), CK.bias_act_grad(g, x, bias, 0.2, 1.4)) < 1e-6
+    # TF32 rounding of the outputs is a <= 2^-11 relative perturbation
+    assert _rel(S.bias_act(x.cuda(), bias.cuda(), 0.2, 1.4, round_out=True), CK.bias_act(x, bias, 0.2, 1.4)) < 6e-4
+    s = torch.randn(B, C)
+    assert _rel(S.modulate(x.cuda(), s.cuda()), CK.modulate(x, s)) < 1e-6
+    const = torch.randn(1, H, H, C)
+    assert _rel(S.modulate(const.cuda(), s.cuda()), CK.modulate(const, s)) < 1e-6
+    assert _rel(S.mul_reduce(x.cuda(), res.cuda()), CK.mul_reduce(x, res)) < 1e-5
+    assert _rel(S.mul_reduce(x.cuda(), const.cuda()), CK.mul_reduce(x, const.expand(B, -1, -1, -1))) < 1e-5
+    noise, nw, d = torch.randn(B, 1, H, H), torch.randn(1), torch.rand(B, C) + 0.5
+    assert _rel(S.mod_epilogue(x.cuda(), d.cuda(), noise.cuda(), nw.cuda(), bias.cuda()),
+                CK.mod_epilogue(x, d, noise, nw, bias)) < 1e-6
+    assert _rel(S.mod_epilogue(x.cuda(), None, noise.cuda(), nw.cuda(), bias.cuda()),
+                CK.mod_epilogue(x, None, noise, nw, bias)) < 1e-6
+    assert _rel(S.noise_grad(g.cuda(), noise.cuda()), CK.noise_grad(g, noise)) < 1e-4
+    big = torch.randn(2, 64, 64, 40)                                   # P > 512: the split-P path of mul_reduce
+    big2 = torch.randn(2, 64, 64, 40)
+    assert _rel(S.mul_reduce(big.cuda(), big2.cuda()), CK.mul_reduce(big, big2)) < 1e-4
+
+
+@pytest.mark.parametrize("B", [4, 8, 3, 12])
+def test_minibatch_stddev(S, B):
+    torch.manual_seed(B)
+    C, H = 40, 4
+    x = torch.randn(B, H, H, C)
+    std = CK.stddev_fwd(x)
+    assert _rel(S.stddev_fwd(x.cuda()), std) < 1e-5
+    dstd = torch.randn_like(std)
+    assert _rel(S.stddev_bwd(dstd.cuda(), x.cuda()), CK.stddev_bwd(dstd, x)) < 1e-5
+    gg = torch.randn_like(x)
+    got = S.stddev_bwd_bwd(gg.cuda(), dstd.cuda(), x.cuda())
+    want = CK.stddev_bwd_bwd(gg, dstd, x)
+    assert _rel(got[0], want[0]) < 1e-4 and _rel(got[1], want[1]) < 1e-4
+    assert torch.equal(S.stddev_concat(x.cuda(), std.cuda(), 64).cpu(), CK.stddev_concat(x, std, 64))
+    dy = torch.randn(B, H, H, 64)
+    got = S.stddev_split(dy.cuda(), C)
+    want = CK.stddev_split(dy, C)
+    assert torch.equal(got[0].cpu(), want[0]) and _rel(got[1], want[1]) < 1e-5
+
+
+def test_layout_and_misc_kernels(S):
+    torch.manual_seed(5)
+    x = torch.rand(5, 3, 16, 16)
+    assert _rel(S.rgb_to_nhwc(x.cuda(), 32, 2.0, -1.0), CK.rgb_to_nhwc(x, 32, 2.0, -1.0)) < 1e-6
+    src, res = torch.randn(5, 16, 16, 32), torch.randn(5, 3, 16, 16)
+    assert _rel(S.nhwc_to_rgb(src.cuda(), res.cuda(), 0.5), CK.nhwc_to_rgb(src, res, 0.5)) < 1e-6
+    assert _rel(S.nhwc_to_rgb(src.cuda(), None, 2.0), CK.nhwc_to_rgb(src, None, 2.0)) < 1e-6
+    z = torch.randn(7, 512)
+    assert _rel(S.pixelnorm(z.cuda()), CK.pixelnorm(z)) < 1e-5
+    g = torch.randn(6, 3, 32, 32)
+    assert _rel(S.row_sqsum(g.cuda()), CK.row_sqsum(g)) < 1e-5
+    s = torch.randn(6)
+    assert _rel(S.row_scale(g.cuda(), s.cuda(), 2.0), CK.row_scale(g, s, 2.0)) < 1e-6
+    a, b = torch.randn(1000), torch.randn(1000)
+    assert _rel(S.axpby(a.cuda(), b.cuda(), 0.5, -2.0, 0.25), CK.axpby(a, b, 0.5, -2.0, 0.25)) < 1e-6
+    assert _rel(S.axpby(a.cuda(), None, 0.5, 0.0, 0.5), CK.axpby(a, None, 0.5, 0.0, 0.5)) < 1e-6
+    dst = [torch.randn(n) for n in (5, 4096, 70001)] * 30                  # 90 tensors: two launches
+    src_ = [torch.randn_like(t) for t in dst]
+    d_gpu = [t.cuda() for t in dst]
+    S.ema_lerp([(d, s_.cuda()) for d, s_ in zip(d_gpu, src_)], 0.75)
+    CK.ema_lerp(list(zip(dst, src_)), 0.75)
+    assert max(_rel(a_, b_) for a_, b_ in zip(d_gpu, dst)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core families
+def _tf32(t, K):
+    return K.round_tf32(t)
+
+
+def test_mm_family_double_backward(K):
+    from contrad_b200 import sg2_functional as SF
+    torch.manual_seed(1)
+    for (M, N, Kd) in ((70, 128, 64), (256, 32, 128), (33, 4608, 64), (512, 64, 32)):
+        a = _tf32(torch.randn(M, Kd), K).cuda().requires_grad_(True)
+        w = _tf32(torch.randn(N, Kd) * 0.1, K).cuda().requires_grad_(True)
+        bias = torch.randn(N).cuda().requires_grad_(True)
+        gy = _tf32(torch.randn(M, N), K).cuda().requires_grad_(True)
+        y = SF.MmNT.apply(a, w, bias)
+        ref = a.double() @ w.double().t() + bias.double()
+        assert _rel(y, ref) < 1e-4
+        da, dw, db = torch.autograd.grad(y, [a, w, bias], gy, create_graph=True)
+        assert _rel(da, gy.double() @ w.double()) < 1e-4
+        assert _rel(dw, gy.double().t() @ a.double()) < 1e-4
+        assert _rel(db, gy.double().sum(0)) < 1e-4
+        # second order: d/d(gy), d/dw of <da, v>
+        v = _tf32(torch.randn(M, Kd), K).cuda()
+        d_gy, d_w = torch.autograd.grad(da, [gy, w], v)
+        assert _rel(d_gy, v.double() @ w.double().t()) < 1e-4
+        assert _rel(d_w, gy.double().t() @ v.double()) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(4, 4, 544, 512), (6, 8, 128, 128), (3, 32, 128, 128)])
+def test_conv3x3_family_double_backward(K, B, H, Cin, Cout):
+    from contrad_b200 import sg2_functional as SF
+    import torch.nn.functional as F
+    torch.manual_seed(B + H)
+    x = _tf32(torch.randn(B, H, H, Cin), K).cuda().requires_grad_(True)
+    w = _tf32(torch.randn(Cout, Cin, 3, 3) * 0.05, K).cuda().requires_grad_(True)
+    gy = _tf32(torch.randn(B, H, H, Cout), K).cuda().requires_grad_(True)
+    y = SF.Conv3x3.apply(x, w)
+    xd, wd, gd = (t.detach().double() for t in (x, w, gy))
+    ref = F.conv2d(xd.permute(0, 3, 1, 2), wd, padding=1).permute(0, 2, 3, 1)
+    assert _rel(y, ref) < 1e-4
+    dx, dw = torch.autograd.grad(y, [x, w], gy, create_graph=True)
+    ref_dx = torch.nn.grad.conv2d_input((B, Cin, H, H), wd, gd.permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    ref_dw = torch.nn.grad.conv2d_weight(xd.permute(0, 3, 1, 2), (Cout, Cin, 3, 3), gd.permute(0, 3, 1, 2), padding=1)
+    assert _rel(dx, ref_dx) < 1e-4 and _rel(dw, ref_dw) < 1e-4
+    v = _tf32(torch.randn(B, H, H, Cin), K).cuda()
+    d_gy, d_w = torch.autograd.grad(dx, [gy, w], v)
+    vd = v.double()
+    assert _rel(d_gy, F.conv2d(vd.permute(0, 3, 1, 2), wd, padding=1).permute(0, 2, 3, 1)) < 1e-4
+    assert _rel(d_w, torch.nn.grad.conv2d_weight(vd.permute(0, 3, 1, 2), (Cout, Cin, 3, 3), gd.permute(0, 3, 1, 2), padding=1)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ models vs the reference
+@pytest.fixture(scope="module")
+def fx():
+    return torch.load(os.path.join(GOLDEN, "stylegan2_small.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def models(fx):
+    from oracle import stylegan2_oracle as SO
+    from contrad_b200.models.gan import get_architecture
+    sd_d = SO.make_d_state(fx["size"], small32=True, d_hidden=512, generator=torch.Generator().manual_seed(fx["w_seed_d"]))
+    sd_g = SO.make_g_state(fx["size"], small32=True, generator=torch.Generator().manual_seed(fx["w_seed_g"]))
+    gen = torch.Generator().manual_seed(fx["bias_seed"])
+    for sd in (sd_d, sd_g):
+        for k in sd:
+            if k.endswith(".bias") and sd[k].abs().sum() == 0:
+                sd[k] = 0.1 * torch.randn(sd[k].shape, generator=gen)
+            if k.endswith("noise.weight"):
+                sd[k] = 0.1 * torch.randn(1, generator=gen)
+    G, D = get_architecture("stylegan2", (fx["size"], fx["size"], 3))
+    D.load_state_dict(sd_d, strict=True)
+    G.load_state_dict(sd_g, strict=True)
+    return G.cuda().train(), D.cuda().train()
+
+
+def _norm_errs(named_params, want, prefix):
+    worst = 0.0
+    for k, n in want.items():
+        if n <= 0:
+            continue
+        g = dict(named_params)[k].grad
+        assert g is not None, "no gradient for %s" % k
+        worst = max(worst, abs(float(g.norm()) - n) / n)
+    REPORT[prefix + "_worst_grad_norm_rel"] = worst
+    return worst
+
+
+def test_discriminator_matches_reference(fx, models):
+    G, D = models
+    c = fx["d_case"]
+    D.zero_grad()
+    x = c["x"].cuda().requires_grad_(True)
+    d, aux = D(x, projection=True, projection2=True, penultimate=True)
+    _chk("D.d", d, c["d"], 1e-2)
+    _chk("D.projection", aux["projection"], c["projection"], 1e-2)
+    _chk("D.projection2", aux["projection2"], c["projection2"], 1e-2)
+    _chk("D.penultimate", aux["penultimate"], c["penultimate"], 1e-2)
+    ((d * c["c_d"].cuda()).sum() + (aux["projection"] * c["c1"].cuda()).sum() + (aux["projection2"] * c["c2"].cuda()).sum()).backward()
+    _chk("D.dx", x.grad, c["dx"], 2e-2)
+    _chk("D.grad_from_rgb", D.layers[0][0].weight.grad, c["grad_from_rgb"], 2e-2)
+    _chk("D.grad_last_bias", D.last_conv[1].bias.grad, c["grad_last_bias"], 2e-2)
+    assert _norm_errs(D.named_parameters(), c["grad_norms"], "D") < 2e-2
+
+
+def test_r1_double_backward_matches_reference(fx, models):
+    from contrad_b200.training.gan import stylegan2 as T
+    G, D = models
+    c = fx["r1_case"]
+    D.zero_grad()
+    per_sample = T.r1_per_sample(D, c["x"].cuda(), lambda t: t)
+    _chk("R1.per_sample", per_sample, c["per_sample"], 2e-2)
+    per_sample.mean().backward()
+    _chk("R1.grad_from_rgb", D.layers[0][0].weight.grad, c["grad_from_rgb"], 3e-2)
+    _chk("R1.grad_conv1_bias", D.layers[1].conv1[1].bias.grad, c["grad_conv1_bias"], 3e-2)
+    assert _norm_errs(D.named_parameters(), c["grad_norms"], "R1") < 3e-2
+
+
+def test_generator_matches_reference(fx, models):
+    G, D = models
+    c = fx["g_case"]
+    G.zero_grad()
+    noises = [n.cuda() for n in c["noises"]]
+    z_mix = c["z_mix"].cuda()
+    orig = G.sample_latent
+    G.sample_latent = lambda n: z_mix                       # the device generator differs from the CPU reference run
+    try:
+        torch.set_rng_state(c["rng_state_after_zmix"])      # CPU draws of the mixing mask (generator.py:257-258)
+        img, latents = G(c["z"].cuda(), return_latents=True, style_mix=0.9, noise=noises)
+    finally:
+        G.sample_latent = orig
+    _chk("G.latents", latents, c["latents"], 1e-2)
+    _chk("G.image", img, c["image"], 1e-2)
+    (img * c["c_img"].cuda()).sum().backward()
+    _chk("G.grad_const", G.input.const.grad, c["grad_const"], 2e-2)
+    nw = torch.stack([G.conv1.noise.weight.grad] + [l.noise.weight.grad for l in G.layers])
+    _chk("G.grad_noise_w", nw, c["grad_noise_w"], 2e-2)
+    _chk("G.grad_rgb_bias", G.to_rgbs[-1].bias.grad, c["grad_rgb_bias"], 2e-2)
+    assert _norm_errs(G.named_parameters(), c["grad_norms"], "G") < 2e-2
+    _chk("G.image_nomix", G(c["z"].cuda(), style_mix=0.0, noise=noises), c["image_nomix"], 1e-2)
+
+
+def test_dstep_losses_match_reference(fx, models):
+    from contrad_b200.training.gan import stylegan2 as T
+    G, D = models
+    c = fx["dstep_case"]
+    D.zero_grad()
+    d_all, view_r, view_f = T.discriminate(D, c["real_aug2"].cuda(), c["fake_aug"].cuda())
+    P = SimpleNamespace(temp=0.1, lbd_a=1.0, distributed=False)
+    d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+    for name, got, want in (("d_loss", d_loss, c["d_loss"]), ("penalty", aux["penalty"], c["penalty"]),
+                            ("d_real", aux["d_real"], c["d_real"]), ("d_gen", aux["d_gen"], c["d_gen"])):
+        err = abs(float(got) - want) / max(abs(want), 1.0 if name.startswith("d_r") or name.startswith("d_g") else 1e-12)
+        REPORT["dstep." + name] = err
+        assert err < 5e-3, (name, float(got), want)
+    (d_loss + aux["penalty"]).backward()
+    assert _norm_errs(D.named_parameters(), c["grad_norms"], "dstep") < 2e-2
+    g_l = T.loss_G_fn(T.discriminate(D, None, c["fake_aug"].cuda(), train_G=True))
+    assert abs(float(g_l) - c["g_loss"]) < 5e-3 * abs(c["g_loss"])
+
+
+def test_full_stylegan2_step_runs():
+    """train_step_stylegan2: G step, D step with R1 (step % d_reg_every == 0) and EMA, on the fused augmentation."""
+    import copy
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    from contrad_b200 import _capi, engine
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.optim import FusedAdam
+    from contrad_b200.training.gan import stylegan2 as T
+    gin.clear_config()
+    gin.parse_config("RandomResizeCropLayer.scale = (0.2, 1.0)\nColorJitterLayer.brightness = 0.4\n"
+                     "ColorJitterLayer.contrast = 0.4\nColorJitterLayer.saturation = 0.4\nColorJitterLayer.hue = 0.1\n")
+    torch.manual_seed(0); np.random.seed(0)
+    G, D = get_architecture("stylegan2", (32, 32, 3))
+    G.cuda(); D.cuda()
+    g_ema = copy.deepcopy(G)
+    aug = get_augment(mode="simclr").cuda()
+    GD = T.G_D(G, D, aug)
+    P = SimpleNamespace(use_warmup=True, halflife_lr=0, ema_start_k=0, accum=0.5 ** (64 / 20000.0), d_reg_every=1,
+                        lbd_r1=0.1, style_mix=0.9, temp=0.1, lbd_a=1.0, distributed=False)
+    opt = {"warmup": 3000, "lr": 2e-3, "lr_d": 2e-3, "batch_size": 8}
+    opt_G = FusedAdam(G.parameters(), lr=2e-3, betas=(0.0, 0.99))
+    opt_D = FusedAdam(D.parameters(), lr=2e-3, betas=(0.0, 0.99))
+    before_d = {k: v.detach().clone() for k, v in D.named_parameters()}
+    ema_before = g_ema.input.const.detach().clone()
+    launches = _capi.launch_count()
+    for step in (1, 2):
+        out = engine.train_step_stylegan2(P, opt, GD, g_ema, (opt_G, opt_D), torch.rand(8, 3, 32, 32, device="cuda"), step,
+                                          record_grad_norms=True)
+    torch.cuda.synchronize()
+    for k, v in out.items():
+        assert torch.isfinite(v).all(), (k, v)
+    assert "d_r1" in out and float(out["d_r1"]) > 0
+    assert _capi.launch_count() - launches > 100
+    changed = [k for k, v in D.named_parameters() if not torch.equal(v.detach(), before_d[k])]
+    assert len(changed) >= 0.9 * len(before_d), set(before_d) - set(changed)
+    REPORT["step.unchanged_params"] = sorted(set(before_d) - set(changed))
+    assert not torch.equal(g_ema.input.const, ema_before)
+    REPORT["step.values"] = {k: float(v) for k, v in out.items()}
+
+
+def test_zz_write_report():
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", "sg2_parity.json"), "w") as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

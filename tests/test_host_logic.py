@@ -102,7 +102,14 @@ def test_module_surfaces_match_reference():
     with pytest.raises(NotImplementedError):
         setup(SimpleNamespace(mode="std", aug="none", penalty="none", temp=0.1, lbd_a=1.0))
     with pytest.raises(NotImplementedError):
-        get_architecture("stylegan2", (32, 32, 3))
+        get_architecture("snresnet18", (32, 32, 3))
+    # the StyleGAN2 networks also run on the kernels only (no CPU fallback)
+    G2, D2 = get_architecture("stylegan2", (32, 32, 3))
+    from contrad_b200._capi import CB200Error as _E
+    with pytest.raises(_E):
+        D2(torch.rand(4, 3, 32, 32))
+    with pytest.raises(_E):
+        G2(torch.randn(4, 512))
     # the generator runs on the sm_100a kernels only: on CPU tensors it must fail loudly, not fall back
     from contrad_b200._capi import CB200Error
     with pytest.raises(CB200Error):

@@ -1,0 +1,222 @@
+"""CPU tests of the StyleGAN2 side of the path.
+
+1. The oracle (oracle/stylegan2_oracle.py) replays the fixtures produced by the unmodified reference
+   (tests/golden/make_golden_sg2.py -> stylegan2_small.pt): forward values, first-order gradients, the R1
+   double backward, the generator with style mixing and the D-step losses of train_stylegan2_contraD.py.
+2. The product's HOST logic - the autograd Functions of contrad_b200.sg2_functional and the module mirrors under
+   contrad_b200/models/gan/stylegan2 - is run with the kernel bindings replaced by the torch stand-ins of
+   tests/cpu_kernels.py and must reproduce the same fixtures (operator wiring, weight re-layouts, NHWC/NCHW
+   boundaries, double-backward structure).  The CUDA kernels themselves are checked against the same stand-ins by
+   the `-m gpu` tests."""
+import json
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import stylegan2_oracle as SO
+from tests import cpu_kernels as CK
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return torch.load(os.path.join(GOLDEN, "stylegan2_small.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def states(fx):
+    sd_d = SO.make_d_state(fx["size"], small32=True, d_hidden=512, generator=torch.Generator().manual_seed(fx["w_seed_d"]))
+    sd_g = SO.make_g_state(fx["size"], small32=True, generator=torch.Generator().manual_seed(fx["w_seed_g"]))
+    gen = torch.Generator().manual_seed(fx["bias_seed"])
+    for sd in (sd_d, sd_g):
+        for k in sd:
+            if k.endswith(".bias") and sd[k].abs().sum() == 0:
+                sd[k] = 0.1 * torch.randn(sd[k].shape, generator=gen)
+            if k.endswith("noise.weight"):
+                sd[k] = 0.1 * torch.randn(1, generator=gen)
+    return sd_d, sd_g
+
+
+def _close(a, b, rel=1e-4, what=""):
+    a, b = torch.as_tensor(a, dtype=torch.float32), torch.as_tensor(b, dtype=torch.float32)
+    err = float((a - b).abs().max())
+    ref = float(b.abs().max())
+    assert err <= rel * max(ref, 1e-6), "%s: max err %.3e vs scale %.3e" % (what, err, ref)
+
+
+def _leafs(sd):
+    return {k: (v.clone().requires_grad_(True) if not k.endswith(".kernel") else v) for k, v in sd.items()}
+
+
+def _check_norms(named_grads, want, rel, what):
+    for k, n in want.items():
+        g = named_grads[k]
+        assert g is not None, "%s: no gradient for %s" % (what, k)
+        got = float(g.norm())
+        assert abs(got - n) <= rel * max(n, 1e-6), "%s: |grad %s| = %.6e, reference %.6e" % (what, k, got, n)
+
+
+# ------------------------------------------------------------------------------------------------ 1. oracle vs reference
+def test_oracle_upfirdn2d(fx):
+    for c in fx["upfirdn2d"]:
+        x = c["x"].clone().requires_grad_(True)
+        y = SO.upfirdn2d(x, c["kernel"], up=c["up"], down=c["down"], pad=c["pad"])
+        _close(y, c["y"], 1e-6, "upfirdn2d fwd")
+        (dx,) = torch.autograd.grad(y, x, c["dy"])
+        _close(dx, c["dx"], 1e-6, "upfirdn2d bwd")
+
+
+def test_oracle_discriminator(fx, states):
+    sd = _leafs(states[0])
+    c = fx["d_case"]
+    x = c["x"].clone().requires_grad_(True)
+    d, p1, p2 = SO.d_forward(sd, x, fx["size"])
+    _close(d, c["d"], 1e-4, "d"); _close(p1, c["projection"], 1e-4, "projection"); _close(p2, c["projection2"], 1e-4, "projection2")
+    _close(SO.d_penultimate(sd, x, fx["size"]), c["penultimate"], 1e-4, "penultimate")
+    ((d * c["c_d"]).sum() + (p1 * c["c1"]).sum() + (p2 * c["c2"]).sum()).backward()
+    _close(x.grad, c["dx"], 1e-3, "dx")
+    _check_norms({k: v.grad for k, v in sd.items() if v.requires_grad}, c["grad_norms"], 1e-3, "oracle D")
+
+
+def test_oracle_r1(fx, states):
+    sd = _leafs(states[0])
+    c = fx["r1_case"]
+    r1 = SO.r1_penalty(sd, c["x"], fx["size"])
+    _close(r1, c["per_sample"], 1e-3, "r1 per sample")
+    r1.mean().backward()
+    _check_norms({k: v.grad for k, v in sd.items() if v.requires_grad},
+                 {k: n for k, n in c["grad_norms"].items() if n > 0}, 2e-3, "oracle R1")
+    _close(sd["layers.0.0.weight"].grad, c["grad_from_rgb"], 2e-3, "r1 grad FromRGB")
+
+
+def test_oracle_generator(fx, states):
+    sd = _leafs(states[1])
+    c = fx["g_case"]
+    img = SO.g_forward(sd, c["z"], fx["size"], c["noises"], z_mix=c["z_mix"], mix_layer=c["mix_layer"])
+    _close(img, c["image"], 1e-4, "image")
+    (img * c["c_img"]).sum().backward()
+    _check_norms({k: v.grad for k, v in sd.items() if v.requires_grad}, c["grad_norms"], 1e-3, "oracle G")
+    _close(sd["input.const"].grad, c["grad_const"], 1e-3, "grad const")
+    _close(SO.g_forward(states[1], c["z"], fx["size"], c["noises"]), c["image_nomix"], 1e-4, "image (no mixing)")
+
+
+def test_oracle_dstep_losses(fx, states):
+    sd = _leafs(states[0])
+    c = fx["dstep_case"]
+    d_loss, penalty, d_real, d_gen = SO.gd_losses(sd, fx["size"], c["real_aug2"], c["fake_aug"])
+    assert abs(float(d_loss) - c["d_loss"]) < 1e-4 * abs(c["d_loss"])
+    assert abs(float(penalty) - c["penalty"]) < 1e-4 * abs(c["penalty"])
+    assert abs(float(d_real) - c["d_real"]) < 1e-4 * max(1.0, abs(c["d_real"]))
+    assert abs(float(d_gen) - c["d_gen"]) < 1e-4 * max(1.0, abs(c["d_gen"]))
+    (d_loss + penalty).backward()
+    _check_norms({k: v.grad for k, v in sd.items() if v.requires_grad}, c["grad_norms"], 2e-3, "oracle D-step")
+    assert abs(float(SO.g_loss(states[0], fx["size"], c["fake_aug"])) - c["g_loss"]) < 1e-4 * abs(c["g_loss"])
+
+
+# ------------------------------------------------------------------------------------------------ 2. product host logic
+def _product_models(states, size):
+    from contrad_b200.models.gan import get_architecture
+    G, D = get_architecture("stylegan2", (size, size, 3))
+    D.load_state_dict(states[0], strict=True)
+    G.load_state_dict(states[1], strict=True)
+    return G.train(), D.train()
+
+
+def test_state_dict_layout_matches_reference():
+    from contrad_b200.models.gan import get_architecture
+    with open(os.path.join(GOLDEN, "stylegan2_keys.json")) as f:
+        keys = json.load(f)
+    for arch, size, suffix in (("stylegan2", 32, ""), ("stylegan2_512", 512, "512")):
+        G, D = get_architecture(arch, (size, size, 3))
+        assert {k: list(v.shape) for k, v in D.state_dict().items()} == keys["D" + suffix]
+        assert {k: list(v.shape) for k, v in G.state_dict().items()} == keys["G" + suffix]
+
+
+def test_cpu_standins_upfirdn2d(fx):
+    """The stand-in used as the kernel reference reproduces the reference op, incl. its backward via UpFirDn."""
+    from contrad_b200.models.gan.stylegan2.op import upfirdn2d
+    with CK.patched():
+        for c in fx["upfirdn2d"]:
+            x = c["x"].clone().requires_grad_(True)
+            y = upfirdn2d(x, c["kernel"], up=c["up"], down=c["down"], pad=c["pad"])
+            _close(y, c["y"], 1e-6, "upfirdn2d fwd")
+            dy = c["dy"].clone().requires_grad_(True)
+            (dx,) = torch.autograd.grad(y, x, dy, create_graph=True)
+            _close(dx, c["dx"], 1e-6, "upfirdn2d bwd")
+            # the backward of the backward (w.r.t. the cotangent) is the forward operator again
+            (ddy,) = torch.autograd.grad(dx, dy, c["x"])
+            _close(ddy, c["y"], 1e-6, "upfirdn2d bwd-of-bwd")
+
+
+def test_product_discriminator_host_logic(fx, states):
+    with CK.patched():
+        G, D = _product_models(states, fx["size"])
+        c = fx["d_case"]
+        x = c["x"].clone().requires_grad_(True)
+        d, aux = D(x, projection=True, projection2=True, penultimate=True)
+        _close(d, c["d"], 1e-4, "d"); _close(aux["projection"], c["projection"], 1e-4, "projection")
+        _close(aux["projection2"], c["projection2"], 1e-4, "projection2")
+        _close(aux["penultimate"], c["penultimate"], 1e-4, "penultimate")
+        ((d * c["c_d"]).sum() + (aux["projection"] * c["c1"]).sum() + (aux["projection2"] * c["c2"]).sum()).backward()
+        _close(x.grad, c["dx"], 1e-3, "dx")
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 1e-3, "product D")
+        _close(D.layers[0][0].weight.grad, c["grad_from_rgb"], 1e-3, "FromRGB grad")
+        _close(D.last_conv[1].bias.grad, c["grad_last_bias"], 1e-3, "last bias grad")
+        # sg_linear detaches the `linear` head from the backbone (models/gan/base.py:123-126)
+        D.zero_grad()
+        d = D(c["x"], sg_linear=True)
+        (d * c["c_d"]).sum().backward()
+        assert D.layers[0][0].weight.grad is None or float(D.layers[0][0].weight.grad.abs().sum()) == 0.0
+        assert float(D.linear.l1.weight.grad.abs().sum()) > 0
+
+
+def test_product_r1_double_backward(fx, states):
+    from contrad_b200.training.gan import stylegan2 as T
+    with CK.patched():
+        G, D = _product_models(states, fx["size"])
+        c = fx["r1_case"]
+        per_sample = T.r1_per_sample(D, c["x"], lambda t: t)
+        _close(per_sample, c["per_sample"], 1e-3, "r1 per sample")
+        per_sample.mean().backward()
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, {k: n for k, n in c["grad_norms"].items() if n > 0},
+                     2e-3, "product R1")
+        _close(D.layers[0][0].weight.grad, c["grad_from_rgb"], 2e-3, "r1 grad FromRGB")
+        _close(D.layers[1].conv1[1].bias.grad, c["grad_conv1_bias"], 2e-3, "r1 grad conv1 bias")
+
+
+def test_product_generator_host_logic(fx, states):
+    with CK.patched():
+        G, D = _product_models(states, fx["size"])
+        c = fx["g_case"]
+        torch.manual_seed(c["mix_seed"])
+        img, latents = G(c["z"], return_latents=True, style_mix=0.9, noise=c["noises"])
+        _close(latents, c["latents"], 1e-4, "latents")
+        _close(img, c["image"], 1e-4, "image")
+        (img * c["c_img"]).sum().backward()
+        _check_norms({k: p.grad for k, p in G.named_parameters()}, c["grad_norms"], 1e-3, "product G")
+        _close(G.input.const.grad, c["grad_const"], 1e-3, "grad const")
+        nw = torch.stack([G.conv1.noise.weight.grad] + [l.noise.weight.grad for l in G.layers])
+        _close(nw, c["grad_noise_w"], 1e-3, "noise weight grads")
+        _close(G.to_rgbs[-1].bias.grad, c["grad_rgb_bias"], 1e-3, "ToRGB bias grad")
+        _close(G(c["z"], style_mix=0.0, noise=c["noises"]), c["image_nomix"], 1e-4, "image (no mixing)")
+
+
+def test_product_dstep_losses(fx, states):
+    from contrad_b200.training.gan import stylegan2 as T
+    import tests.cpu_loss_standins as LS
+    with CK.patched(), LS.patched():
+        G, D = _product_models(states, fx["size"])
+        c = fx["dstep_case"]
+        d_all, view_r, view_f = T.discriminate(D, c["real_aug2"], c["fake_aug"])
+        P = type("P", (), {"temp": 0.1, "lbd_a": 1.0, "distributed": False})()
+        d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+        assert abs(float(d_loss) - c["d_loss"]) < 1e-4 * abs(c["d_loss"])
+        assert abs(float(aux["penalty"]) - c["penalty"]) < 1e-4 * abs(c["penalty"])
+        assert abs(float(aux["d_real"]) - c["d_real"]) < 1e-4 * max(1.0, abs(c["d_real"]))
+        assert abs(float(aux["d_gen"]) - c["d_gen"]) < 1e-4 * max(1.0, abs(c["d_gen"]))
+        (d_loss + aux["penalty"]).backward()
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 2e-3, "product D-step")
