@@ -31,6 +31,21 @@ def _rw(w):
     return K.round_tf32(_c(w.detach()))
 
 
+class RoundTF32(Function):
+    """Round an activation-shaped GEMM operand to TF32 (nearest); identity gradient.  Forward activations are rounded
+    by the kernels that produce them; cotangents arriving from autograd (sums of branches, loss gradients) are not,
+    and the tensor core would TRUNCATE them - a systematic shrink of ~2^-11 per GEMM that adds up along the backward
+    pass - so every backward closure rounds its incoming cotangent once."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.round_tf32_(_c(x))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 # ------------------------------------------------------------------------------------------------ GEMM family
 class MmNT(Function):
     """out[M,N] = a[M,K] @ w[N,K]^T (+ bias[N])          N, K multiples of 32."""
@@ -45,7 +60,7 @@ class MmNT(Function):
     @staticmethod
     def backward(ctx, dy):
         a, w = ctx.saved_tensors
-        dy = _c(dy)
+        dy = RoundTF32.apply(dy)
         da = MmNN.apply(dy, w) if ctx.needs_input_grad[0] else None
         dw = MmTN.apply(dy, a) if ctx.needs_input_grad[1] else None
         db = ColSum.apply(dy) if ctx.has_bias and ctx.needs_input_grad[2] else None
@@ -64,7 +79,7 @@ class MmNN(Function):
     @staticmethod
     def backward(ctx, gg):
         g, w = ctx.saved_tensors
-        gg = _c(gg)
+        gg = RoundTF32.apply(gg)
         d_g = MmNT.apply(gg, w) if ctx.needs_input_grad[0] else None
         d_w = MmTN.apply(g, gg) if ctx.needs_input_grad[1] else None
         return d_g, d_w
@@ -121,7 +136,7 @@ class Conv3x3(Function):
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dy = _c(dy)
+        dy = RoundTF32.apply(dy)
         dx = Conv3x3Dgrad.apply(dy, w) if ctx.needs_input_grad[0] else None
         dw = Conv3x3Wgrad.apply(x, dy) if ctx.needs_input_grad[1] else None
         return dx, dw
@@ -140,7 +155,7 @@ class Conv3x3Dgrad(Function):
     @staticmethod
     def backward(ctx, g):
         dy, w = ctx.saved_tensors
-        g = _c(g)
+        g = RoundTF32.apply(g)
         d_dy = Conv3x3.apply(g, w) if ctx.needs_input_grad[0] else None
         d_w = Conv3x3Wgrad.apply(g, dy) if ctx.needs_input_grad[1] else None
         return d_dy, d_w

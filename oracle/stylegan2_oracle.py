@@ -193,7 +193,7 @@ def g_forward(sd, z, size, noises, z_mix=None, mix_layer=None):
     latents = latent.unsqueeze(1).repeat(1, n_latent, 1)
     if z_mix is not None:
         latent_mix = g_mapping(sd, z_mix).unsqueeze(1)
-        mask = (torch.arange(n_latent)[None] < mix_layer.unsqueeze(1)).float().unsqueeze(-1)
+        mask = (torch.arange(n_latent)[None] < mix_layer.cpu().unsqueeze(1)).float().unsqueeze(-1).to(latents.device)
         latents = latents * mask + latent_mix * (1 - mask)
     b = z.shape[0]
     out = sd["input.const"].repeat(b, 1, 1, 1)

@@ -57,6 +57,10 @@ def colsum(x2d):
     return x2d.sum(0)
 
 
+def round_tf32_(x):
+    return x.clone()
+
+
 # ------------------------------------------------------------------ contrad_b200.sg2_kernels stand-ins
 def upfirdn_out_size(in_size, ksize, up, down, pad0, pad1):
     return (in_size * up + pad0 + pad1 - ksize) // down + 1
@@ -225,7 +229,7 @@ def ema_lerp(pairs, decay):
         d.mul_(decay).add_(s, alpha=1 - decay)
 
 
-K_NAMES = ("gemm_nt", "gemm_tn_wgrad", "conv2d_nhwc_fwd", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "colsum")
+K_NAMES = ("gemm_nt", "gemm_tn_wgrad", "conv2d_nhwc_fwd", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "colsum", "round_tf32_")
 S_NAMES = ("upfirdn2d", "patch_s2_gather", "patch_s2_scatter", "bias_act", "bias_act_grad", "modulate", "mul_reduce",
            "mod_epilogue", "noise_grad", "stddev_fwd", "stddev_bwd", "stddev_bwd_bwd", "stddev_concat", "stddev_split",
            "rgb_to_nhwc", "nhwc_to_rgb", "pixelnorm", "row_sqsum", "row_scale", "axpby", "ema_lerp")

@@ -171,6 +171,28 @@ def main():
     g_l = F.softplus(-D(fake_aug)).mean()
     out["dstep_case"]["g_loss"] = float(g_l)
 
+    # ---- the same D-step at n = 16 (inputs + scalars + gradient norms only): more samples per parameter gradient
+    torch.manual_seed(51)
+    n = 16
+    fake_aug = torch.rand(n, 3, SIZE, SIZE).half().float()          # stored as fp16: quantise before use
+    real_aug2 = torch.rand(2 * n, 3, SIZE, SIZE).half().float()
+    D.zero_grad()
+    d_gen, aux_f = D(fake_aug, sg_linear=True, projection=True, projection2=True)
+    d_rs, aux_r = D(real_aug2, sg_linear=True, projection=True, projection2=True)
+    views_r, reals = F.normalize(aux_r["projection"]), F.normalize(aux_r["projection2"])
+    others, fakes = F.normalize(aux_f["projection"]), F.normalize(aux_f["projection2"])
+    simclr = nt_xent(views_r[:n], views_r[n:], temperature=0.1)
+    sup = supcon_fake(reals[:n], reals[n:], fakes, temperature=0.1)
+    d_real = d_rs[:n]
+    penalty = F.softplus(d_gen).mean() + F.softplus(-d_real).mean()
+    r1 = r1_loss(D, real_aug2[:n], _Id())
+    (simclr + sup + penalty + 0.05 * r1).backward()
+    total = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in D.parameters() if p.grad is not None))
+    out["dstep16_case"] = {"fake_aug": fake_aug.half(), "real_aug2": real_aug2.half(), "d_loss": float(simclr + sup),
+                           "penalty": float(penalty), "r1": float(r1), "d_real": float(d_real.mean()),
+                           "d_gen": float(d_gen.mean()), "grad_norms": grad_norms(D.named_parameters()),
+                           "total_grad_norm": total}
+
     torch.save(out, os.path.join(HERE, "stylegan2_small.pt"))
     print("wrote stylegan2_small.pt (%.1f KB)" % (os.path.getsize(os.path.join(HERE, "stylegan2_small.pt")) / 1024))
 

@@ -349,3 +349,67 @@ def test_cuda_graph_step_matches_eager_step(env):
     assert len(odd) <= 4, odd
 
 
+
+
+def test_zz_eager_gpu_yardstick_sndcgan(env):
+    """Not a parity check: the denominator of north_star's ">= 10x the reference single-GPU PyTorch-eager images/sec".
+    The reference cannot travel to the GPU box, so its per-step arithmetic is executed through the oracle's torch ops ON
+    THE GPU (cuDNN / cuBLAS with TF32 allowed, torch.optim.Adam, the reference's 5 `.item()` reads per step,
+    host-drawn augmentation parameters): BASELINE config 2, b512.  Written to gpurun_out/eager_gpu_sndcgan.json."""
+    import json
+    n, steps, warm = 512, 6, 3
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        np.random.seed(0); torch.manual_seed(0)
+        sd_d = {k: v.cuda() for k, v in O.make_d_state().items()}
+        sd_g = {k: v.cuda() for k, v in O.make_g_state().items()}
+        for sd in (sd_d, sd_g):
+            O.set_requires_grad(sd, True)
+        opt_d = torch.optim.Adam(list(O.trainable(sd_d).values()), lr=2e-4, betas=(0.5, 0.999))
+        opt_g = torch.optim.Adam(list(O.trainable(sd_g).values()), lr=2e-4, betas=(0.5, 0.999))
+        images = torch.rand(n, 3, 32, 32, device="cuda")
+
+        def step():
+            O.set_requires_grad(sd_g, False); O.set_requires_grad(sd_d, True)
+            with torch.no_grad():
+                gen = O.g_sndcgan_forward(sd_g, O.sample_latent(n).cuda())
+            p, order = O.sample_simclr_params(3 * n, 32, 32, device="cuda")
+            l_con, l_dis, ex = O.loss_d(sd_d, images, gen, p, order)
+            opt_d.zero_grad()
+            (l_con + l_dis).backward()
+            opt_d.step()
+            reads = [l_con.item(), l_dis.item(), ex["d_real"].item(), ex["d_gen"].item()]
+            O.set_requires_grad(sd_g, True); O.set_requires_grad(sd_d, False)
+            gen = O.g_sndcgan_forward(sd_g, O.sample_latent(n).cuda())
+            p, order = O.sample_simclr_params(n, 32, 32, device="cuda")
+            l_gen = O.loss_g(sd_d, gen, p, order)
+            opt_g.zero_grad()
+            l_gen.backward()
+            opt_g.step()
+            reads.append(l_gen.item())
+            return reads
+
+        for _ in range(warm):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            reads = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert all(np.isfinite(r) for r in reads)
+    res = {"workload": "SNDCGAN+ContraD b512 32x32, oracle torch ops on the GPU (cuDNN/cuBLAS TF32, torch.optim.Adam)",
+           "ms_per_step": ms, "images_per_s": n / ms * 1e3}
+    print(res)
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", "eager_gpu_sndcgan.json"), "w") as f:
+            json.dump(res, f)
+    except OSError:
+        pass

@@ -220,3 +220,30 @@ def test_product_dstep_losses(fx, states):
         assert abs(float(aux["d_gen"]) - c["d_gen"]) < 1e-4 * max(1.0, abs(c["d_gen"]))
         (d_loss + aux["penalty"]).backward()
         _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 2e-3, "product D-step")
+
+
+def test_dstep16_oracle_and_product(fx, states):
+    """The full D-step objective (contrastive + L_dis + 0.05 * R1) at n = 16: scalars, per-parameter gradient norms and
+    the total gradient norm, oracle and product host logic against the reference."""
+    from contrad_b200.training.gan import stylegan2 as T
+    import tests.cpu_loss_standins as LS
+    c = fx["dstep16_case"]
+    real2, fake = c["real_aug2"].float(), c["fake_aug"].float()
+    n = fake.shape[0]
+    sd = _leafs(states[0])
+    d_loss, penalty, _, _ = SO.gd_losses(sd, fx["size"], real2, fake)
+    r1 = SO.r1_penalty(sd, real2[:n], fx["size"]).mean()
+    assert abs(float(d_loss) - c["d_loss"]) < 1e-4 * abs(c["d_loss"]) and abs(float(r1) - c["r1"]) < 1e-3 * abs(c["r1"])
+    (d_loss + penalty + 0.05 * r1).backward()
+    _check_norms({k: v.grad for k, v in sd.items() if v.requires_grad}, c["grad_norms"], 2e-3, "oracle D-step n=16")
+    with CK.patched(), LS.patched():
+        G, D = _product_models(states, fx["size"])
+        d_all, view_r, view_f = T.discriminate(D, real2, fake)
+        P = type("P", (), {"temp": 0.1, "lbd_a": 1.0, "distributed": False})()
+        d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+        r1 = T.r1_loss(D, real2[:n], lambda t: t)
+        assert abs(float(d_loss) - c["d_loss"]) < 1e-4 * abs(c["d_loss"]) and abs(float(r1) - c["r1"]) < 1e-3 * abs(c["r1"])
+        (d_loss + aux["penalty"] + 0.05 * r1).backward()
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 2e-3, "product D-step n=16")
+        total = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in D.parameters()))
+        assert abs(total - c["total_grad_norm"]) < 1e-3 * c["total_grad_norm"]

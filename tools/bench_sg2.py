@@ -1,0 +1,71 @@
+"""Side measurement for SURVEY config 4 (StyleGAN2 small32 + ContraD, c10_style64.gin: batch 64, --no_lazy R1 every
+step, --aug=simclr) on one B200: images/s of the full step (engine.train_step_stylegan2, eager launches).  The torch-eager yardstick for the same arithmetic is timed
+by tests/test_gpu_sg2.py::test_eager_gpu_yardstick_timing (only tests may run the oracle).
+Not the headline bench (bench.py keeps BASELINE.json's config 2); prints one JSON line."""
+import argparse
+import copy
+import json
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+sys.path.append(os.path.join(REPO, "contrad_b200", "compat"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--d-reg-every", type=int, default=1)
+    args = ap.parse_args()
+    import gin
+    from contrad_b200 import _capi, engine
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.optim import FusedAdam
+    from contrad_b200.training.gan import stylegan2 as T
+    gin.clear_config()
+    gin.parse_config("RandomResizeCropLayer.scale = (0.2, 1.0)\nColorJitterLayer.brightness = 0.4\n"
+                     "ColorJitterLayer.contrast = 0.4\nColorJitterLayer.saturation = 0.4\nColorJitterLayer.hue = 0.1\n")
+    torch.manual_seed(0); np.random.seed(0)
+    n = args.batch
+    G, D = get_architecture("stylegan2", (32, 32, 3))
+    G.cuda(); D.cuda()
+    g_ema = copy.deepcopy(G)
+    GD = T.G_D(G, D, get_augment(mode="simclr").cuda())
+    P = SimpleNamespace(use_warmup=True, halflife_lr=0, ema_start_k=0, accum=0.5 ** (n / 1000000.0), d_reg_every=args.d_reg_every,
+                        lbd_r1=0.1, style_mix=0.9, temp=0.1, lbd_a=1.0, distributed=False)
+    opt = {"warmup": 3000, "lr": 2e-3, "lr_d": 2e-3, "batch_size": n}
+    opts = (FusedAdam(G.parameters(), lr=2e-3, betas=(0.0, 0.99)), FusedAdam(D.parameters(), lr=2e-3, betas=(0.0, 0.99)))
+    images = [torch.rand(n, 3, 32, 32, device="cuda") for _ in range(4)]
+
+    def run(k, first):
+        for s in range(first, first + k):
+            out = engine.train_step_stylegan2(P, opt, GD, g_ema, opts, images[s % 4], s)
+        return out
+
+    run(args.warmup, 1)
+    torch.cuda.synchronize()
+    l0 = _capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = run(args.steps, 1 + args.warmup)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    res = {"workload": "StyleGAN2(small32)+ContraD 32x32 b%d, R1 every %d step(s), eager" % (n, args.d_reg_every),
+           "ms_per_step": ms, "images_per_s": n / ms * 1e3, "launches_per_step": (_capi.launch_count() - l0) / args.steps,
+           "losses": {k: float(v) for k, v in out.items()}}
+
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
