@@ -73,6 +73,49 @@ __global__ void __launch_bounds__(kT) upfirdn2d_kernel(const __grid_constant__ U
     }
 }
 
+// Contiguous NHWC, C % 4 == 0: one thread = one output pixel x 4 channels (float4, channel fastest -> coalesced); the
+// taps that hit the zero-stuffed grid are enumerated with stride `up` (no modulo in the loops); neighbouring pixels
+// re-read the same inputs from L1/L2, HBM sees each input and output once.
+__global__ void __launch_bounds__(kT) upfirdn2d_nhwc4_kernel(const __grid_constant__ UpfirdnParams p) {
+    __shared__ float ks[64];
+    for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+        const int ky = i / p.kw, kx = i % p.kw;
+        const int src = p.flip ? i : (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx);
+        ks[i] = __ldg(p.k + src) * p.gain;
+    }
+    __syncthreads();
+    const int C4 = p.C >> 2;
+    const long long total = (long long)p.N * p.Ho * p.Wo * C4;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(p.x);
+    float4* __restrict__ y4 = reinterpret_cast<float4*>(p.y);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long t = idx;
+        const int c = (int)(t % C4); t /= C4;
+        const int ox = (int)(t % p.Wo); t /= p.Wo;
+        const int oy = (int)(t % p.Ho);
+        const int n = (int)(t / p.Ho);
+        const int py_base = oy * p.down - p.py0, px_base = ox * p.down - p.px0;
+        const int ky0 = ((-py_base) % p.up + p.up) % p.up, kx0 = ((-px_base) % p.up + p.up) % p.up;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ky = ky0; ky < p.kh; ky += p.up) {
+            const int iy = (py_base + ky) / p.up;
+            if (iy < 0) continue;
+            if (iy >= p.Hi) break;
+            const float4* row = x4 + ((long long)n * p.Hi + iy) * p.Wi * C4 + c;
+            for (int kx = kx0; kx < p.kw; kx += p.up) {
+                const int ix = (px_base + kx) / p.up;
+                if (ix < 0) continue;
+                if (ix >= p.Wi) break;
+                const float4 v = __ldg(row + (long long)ix * C4);
+                const float w = ks[ky * p.kw + kx];
+                acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+            }
+        }
+        if (p.round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
+        y4[idx] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ 3x3 stride-2 patches
 // gather : u[b, oh, ow, kh*3+kw, c] = x[b, 2*oh+kh, 2*ow+kw, c]          (x is [B, 2*Ho+1, 2*Wo+1, C])
 // scatter: x[b, r, q, c] = sum over (oh,kh),(ow,kw) with 2*oh+kh = r, 2*ow+kw = q of u[b, oh, ow, kh*3+kw, c]
@@ -449,7 +492,14 @@ extern "C" int cb200_upfirdn2d(const float* x, const long long* x_strides, float
     p.ys_n = y_strides[0]; p.ys_c = y_strides[1]; p.ys_h = y_strides[2]; p.ys_w = y_strides[3];
     p.N = N; p.C = C; p.Hi = Hi; p.Wi = Wi; p.Ho = Ho; p.Wo = Wo; p.up = up; p.down = down; p.px0 = pad_x0; p.py0 = pad_y0;
     p.kh = kh; p.kw = kw; p.flip = flip; p.c_fast = c_fast; p.round_out = round_out; p.gain = gain;
-    upfirdn2d_kernel<<<grid_for((long long)N * C * Ho * Wo), kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    const bool nhwc_contig = c_fast && C % 4 == 0 && p.xs_c == 1 && p.ys_c == 1 && p.xs_w == C && p.ys_w == C &&
+                             p.xs_h == (long long)Wi * C && p.ys_h == (long long)Wo * C && p.xs_n == (long long)Hi * Wi * C &&
+                             p.ys_n == (long long)Ho * Wo * C &&
+                             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (nhwc_contig)
+        upfirdn2d_nhwc4_kernel<<<grid_for((long long)N * Ho * Wo * (C / 4)), kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    else
+        upfirdn2d_kernel<<<grid_for((long long)N * C * Ho * Wo), kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("upfirdn2d");
     return CB200_OK;

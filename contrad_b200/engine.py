@@ -109,7 +109,24 @@ def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=Tr
     return out
 
 
-def train_step_stylegan2(P, opt, GD, g_ema, optimizers, images, step, record_grad_norms=False):
+def stylegan2_schedule(P, opt, optimizers, step):
+    """Host-side LR schedule of train_stylegan2_contraD.py:198-205."""
+    from .training.gan import stylegan2 as T
+    opt_G, opt_D = optimizers
+    if P.use_warmup:
+        update_warmup(opt_G, step, opt["warmup"], opt["lr"])
+        update_warmup(opt_D, step, opt["warmup"], opt["lr_d"])
+    if (not P.use_warmup) or step > opt["warmup"]:
+        T.update_lr(opt_G, step, opt["batch_size"], P.halflife_lr, opt["lr"])
+        T.update_lr(opt_D, step, opt["batch_size"], P.halflife_lr, opt["lr_d"])
+
+
+def stylegan2_ema_decay(P, opt, step):
+    """train_stylegan2_contraD.py:207-208."""
+    return P.accum if (step * opt["batch_size"]) > (P.ema_start_k * 1000) else 0
+
+
+def train_step_stylegan2(P, opt, GD, g_ema, optimizers, images, step, record_grad_norms=False, schedule=True):
     """One iteration of train_stylegan2_contraD.py:195-236 (n_critic = 1): LR schedule, EMA `accumulate`, G step
     through the frozen D, D step (contrastive losses + nonsat L_dis + lazy R1 every `P.d_reg_every` steps).
     GD is `training.gan.stylegan2.G_D(G, D, augment_fn)`; P carries use_warmup, halflife_lr, ema_start_k, accum,
@@ -118,15 +135,10 @@ def train_step_stylegan2(P, opt, GD, g_ema, optimizers, images, step, record_gra
     generator, discriminator = GD.G, GD.D
     opt_G, opt_D = optimizers
     d_regularize = (step % P.d_reg_every == 0) and (P.lbd_r1 > 0)
-    if P.use_warmup:
-        update_warmup(opt_G, step, opt["warmup"], opt["lr"])
-        update_warmup(opt_D, step, opt["warmup"], opt["lr_d"])
-    if (not P.use_warmup) or step > opt["warmup"]:
-        T.update_lr(opt_G, step, opt["batch_size"], P.halflife_lr, opt["lr"])
-        T.update_lr(opt_D, step, opt["batch_size"], P.halflife_lr, opt["lr_d"])
+    if schedule:
+        stylegan2_schedule(P, opt, optimizers, step)
     if g_ema is not None:
-        do_ema = (step * opt["batch_size"]) > (P.ema_start_k * 1000)
-        T.accumulate(g_ema, generator, P.accum if do_ema else 0)
+        T.accumulate(g_ema, generator, stylegan2_ema_decay(P, opt, step))
     generator.train()
     discriminator.train()
     out = {}
@@ -197,6 +209,11 @@ class GraphedTrainStep(object):
         self.side = None
         self.prefetched = False           # the next step's host draws already sit in pinned memory
 
+    def _step(self, images, step, schedule):
+        """The step body that is warmed up, captured and replayed; `schedule` = also run the host-side LR schedule."""
+        return train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers, images, step,
+                          use_warmup=self.use_warmup and schedule)
+
     def _eager(self, images, step, plan=False):
         if self.side is None:
             self.side = torch.cuda.Stream()
@@ -205,11 +222,9 @@ class GraphedTrainStep(object):
             if plan:        # the last eager step also lays out the static input buffers (staging.Recorder.plan)
                 self.recorder = staging.Recorder()
                 with self.recorder.plan():
-                    out = train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers, images, step,
-                                     use_warmup=self.use_warmup)
+                    out = self._step(images, step, True)
             else:
-                out = train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers, images, step,
-                                 use_warmup=self.use_warmup)
+                out = self._step(images, step, True)
         torch.cuda.current_stream().wait_stream(self.side)
         images.record_stream(self.side)
         return out
@@ -230,8 +245,7 @@ class GraphedTrainStep(object):
             # capture on the stream the eager warm-up steps ran on: the parameters' AccumulateGrad nodes stay bound
             # to the stream of their first backward, and a mismatch would fork the capture across streams
             with torch.cuda.graph(self.graph, stream=self.side):
-                self.static_out = train_step(self.P, self.opt, self.train_fn, self.models, self.optimizers,
-                                             self.static_images, step, use_warmup=False)
+                self.static_out = self._step(self.static_images, step, False)
         self.launches_per_replay = _capi.launch_count() - before
 
     def release(self):
@@ -259,3 +273,64 @@ class GraphedTrainStep(object):
         self.recorder.produce()                  # the NEXT step's host draws, while the GPU is busy with this one
         self.prefetched = True
         return self.static_out
+
+
+class _GraphedSG2Variant(GraphedTrainStep):
+    """One CUDA graph of train_step_stylegan2 for a fixed structure (with or without the R1 term) and EMA decay."""
+
+    def __init__(self, owner, eager_steps):
+        self.owner = owner
+        self.P, self.opt, self.optimizers = owner.P, owner.opt, owner.optimizers
+        self.models = (owner.GD.G, owner.GD.D)
+        self.use_warmup, self.eager_steps = True, max(1, int(eager_steps))
+        self.calls, self.graph, self.recorder = 0, None, None
+        self.static_images, self.static_out = None, None
+        self.launches_per_replay = 0
+        self.side = owner.side
+        self.prefetched = False
+
+    def _step(self, images, step, schedule):
+        o = self.owner
+        return train_step_stylegan2(o.P, o.opt, o.GD, o.g_ema, o.optimizers, images, step, schedule=schedule)
+
+    def _host_schedule(self, step):
+        stylegan2_schedule(self.P, self.opt, self.optimizers, step)
+
+
+class GraphedStyleGAN2Step(object):
+    """``train_step_stylegan2`` replayed as CUDA graphs (same mechanics as GraphedTrainStep: eager warm-up steps on a
+    side stream, a planned step that lays out the staged host inputs - crop boxes, jitter order, the style-mixing
+    layer indices, Adam's scalars - then capture and replay).
+
+    The step's STRUCTURE depends on two host decisions, so one graph is kept per value: whether the lazy R1 term is
+    added this step (`step % P.d_reg_every == 0`, train_stylegan2_contraD.py:196) and the EMA decay (0 before
+    `ema_start_k`, `P.accum` after; it is a by-value kernel argument).  With `--no_lazy` (config 4) and after the EMA
+    start there is exactly one graph."""
+
+    def __init__(self, P, opt, GD, g_ema, optimizers, eager_steps=3):
+        from .optim import FusedAdam
+        for o in optimizers:
+            if not isinstance(o, FusedAdam):
+                raise TypeError("GraphedStyleGAN2Step needs contrad_b200.optim.FusedAdam optimisers")
+        if getattr(P, "distributed", False):
+            raise NotImplementedError("GraphedStyleGAN2Step: single-process replicas only (SURVEY 8e, config 5 = DataParallel)")
+        self.P, self.opt, self.GD, self.g_ema, self.optimizers = P, opt, GD, g_ema, optimizers
+        self.eager_steps = eager_steps
+        self.side = torch.cuda.Stream()
+        self.variants = {}
+
+    def __call__(self, images, step):
+        key = (bool((step % self.P.d_reg_every == 0) and (self.P.lbd_r1 > 0)),
+               float(stylegan2_ema_decay(self.P, self.opt, step)) if self.g_ema is not None else None)
+        v = self.variants.get(key)
+        if v is None:
+            v = self.variants[key] = _GraphedSG2Variant(self, self.eager_steps)
+        return v(images, step)
+
+    @property
+    def launches_per_replay(self):
+        return max([v.launches_per_replay for v in self.variants.values()] or [0])
+
+    def release(self):
+        for v in self.variants.values():
+            v.release()

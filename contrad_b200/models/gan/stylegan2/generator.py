@@ -17,6 +17,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .... import sg2_functional as SF
+from .... import staging
 from .layers import Blur, EqualLinear, PixelNorm, Upsample
 from .op import FusedLeakyReLU
 
@@ -206,21 +207,25 @@ class Generator(nn.Module):
             per_layer = [latent[:, i] for i in range(self.n_latent)]
         if self.training and (style_mix > 0):
             latent_mix = self.style(self.sample_latent(batch))
-            nomix_mask = torch.rand(batch) >= style_mix                  # CPU generator, as in the reference
-            mix_layer = torch.randint(self.n_latent, (batch,))
-            mix_layer = mix_layer.masked_fill(nomix_mask, self.n_latent)
+            n_latent = self.n_latent
+
+            def draw():
+                """generator.py:257-264 on the CPU generator, as in the reference: row l holds, per sample, the row of
+                cat([latents_l, latent_mix]) that layer l uses (mask = layer_idx < mix_layer keeps `latents`)."""
+                nomix_mask = torch.rand(batch) >= style_mix
+                mix_layer = torch.randint(n_latent, (batch,))
+                mix_layer = mix_layer.masked_fill(nomix_mask, n_latent)
+                use_mix = torch.arange(n_latent)[:, None] >= mix_layer[None, :]
+                return torch.arange(batch)[None, :] + batch * use_mix.long()
+
+            # staged: under CUDA-graph capture the indices live in a static buffer that is refreshed per replay
+            idx_all = staging.stage(draw, latent_mix.device, shape=(n_latent, batch), dtype=torch.int64)
             base = per_layer
+            shared = torch.cat([latent, latent_mix], 0) if base is None else None
             per_layer = []
-            ar = torch.arange(batch)
-            for i in range(self.n_latent):
-                first = base[i] if base is not None else latent
-                use_mix = (i >= mix_layer)                               # mask = layer_idx < mix_layer keeps `latents`
-                if not bool(use_mix.any()):
-                    per_layer.append(first)
-                    continue
-                both = torch.cat([first, latent_mix], 0)
-                idx = (ar + batch * use_mix.long()).to(both.device)
-                per_layer.append(both.index_select(0, idx))
+            for i in range(n_latent):
+                both = shared if shared is not None else torch.cat([base[i], latent_mix], 0)
+                per_layer.append(both.index_select(0, idx_all[i]))
         lat = (lambda i: latent) if per_layer is None else (lambda i: per_layer[i])
 
         out = self.input(latent)

@@ -26,9 +26,37 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _cached(w, key, make):
+    """Per-tensor memo of derived weight layouts: the forward GEMM, the data-gradient GEMM and the second-order passes
+    of one layer all receive the SAME (scaled) weight tensor, so each re-layout is computed once per forward.  The memo
+    lives on the tensor object and is dropped with it (or when the tensor is modified in place)."""
+    memo = getattr(w, "_cb200_memo", None)
+    if memo is None or memo[0] != w._version:
+        memo = (w._version, {})
+        try:
+            w._cb200_memo = memo
+        except AttributeError:
+            return make()
+    if key not in memo[1]:
+        memo[1][key] = make()
+    return memo[1][key]
+
+
 def _rw(w):
     """Weight-shaped operand of a tensor-core GEMM: contiguous and rounded to TF32 (nearest)."""
-    return K.round_tf32(_c(w.detach()))
+    return _cached(w, "rw", lambda: K.round_tf32(_c(w.detach())))
+
+
+def _rw_t(w):
+    return _cached(w, "rw_t", lambda: K.round_tf32(_c(w.detach().t())))
+
+
+def _pack_fwd(w):
+    return _cached(w, "pack_fwd", lambda: K.pack_fwd_weight(_rw(w)))
+
+
+def _pack_dgrad(w):
+    return _cached(w, "pack_dgrad", lambda: K.pack_dgrad_weight(_rw(w), 1))
 
 
 class RoundTF32(Function):
@@ -74,7 +102,7 @@ class MmNN(Function):
     def forward(ctx, g, w):
         g = _c(g)
         ctx.save_for_backward(g, w)
-        return K.gemm_nt(g, _rw(w.t()))
+        return K.gemm_nt(g, _rw_t(w))
 
     @staticmethod
     def backward(ctx, gg):
@@ -131,7 +159,7 @@ class Conv3x3(Function):
     def forward(ctx, x, w):
         x = _c(x)
         ctx.save_for_backward(x, w)
-        return K.conv2d_nhwc_fwd(x, K.pack_fwd_weight(_rw(w)), None, 3, 1)
+        return K.conv2d_nhwc_fwd(x, _pack_fwd(w), None, 3, 1)
 
     @staticmethod
     def backward(ctx, dy):
@@ -150,7 +178,7 @@ class Conv3x3Dgrad(Function):
         dy = _c(dy)
         ctx.save_for_backward(dy, w)
         B, H, W, _ = dy.shape
-        return K.conv2d_nhwc_dgrad(dy, K.pack_dgrad_weight(_rw(w), 1), (B, H, W, w.shape[1]), 3, 1)
+        return K.conv2d_nhwc_dgrad(dy, _pack_dgrad(w), (B, H, W, w.shape[1]), 3, 1)
 
     @staticmethod
     def backward(ctx, g):

@@ -555,6 +555,55 @@ def test_full_stylegan2_step_runs():
     REPORT["step.values"] = {k: float(v) for k, v in out.items()}
 
 
+def test_graphed_stylegan2_step():
+    """GraphedStyleGAN2Step: 3 eager steps, capture, replays.  The replays must keep training (parameters move, losses
+    stay finite and in the range of the eager steps) and consume fresh host draws (staged style-mixing indices)."""
+    import copy
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    from contrad_b200 import engine
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.optim import FusedAdam
+    from contrad_b200.training.gan import stylegan2 as T
+    gin.clear_config()
+    gin.parse_config("RandomResizeCropLayer.scale = (0.2, 1.0)\nColorJitterLayer.brightness = 0.4\n"
+                     "ColorJitterLayer.contrast = 0.4\nColorJitterLayer.saturation = 0.4\nColorJitterLayer.hue = 0.1\n")
+    torch.manual_seed(1); np.random.seed(1)
+    n = 16
+    G, D = get_architecture("stylegan2", (32, 32, 3))
+    G.cuda(); D.cuda()
+    g_ema = copy.deepcopy(G)
+    GD = T.G_D(G, D, get_augment(mode="simclr").cuda())
+    P = SimpleNamespace(use_warmup=True, halflife_lr=0, ema_start_k=0, accum=0.99, d_reg_every=1, lbd_r1=0.1, style_mix=0.9,
+                        temp=0.1, lbd_a=1.0, distributed=False)
+    opt = {"warmup": 3000, "lr": 2e-3, "lr_d": 2e-3, "batch_size": n}
+    opts = (FusedAdam(G.parameters(), lr=2e-3, betas=(0.0, 0.99)), FusedAdam(D.parameters(), lr=2e-3, betas=(0.0, 0.99)))
+    step_fn = engine.GraphedStyleGAN2Step(P, opt, GD, g_ema, opts)
+    logs, snaps = [], []
+    for s in range(1, 8):
+        out = step_fn(torch.rand(n, 3, 32, 32, device="cuda"), s)
+        torch.cuda.synchronize()
+        logs.append({k: float(v) for k, v in out.items()})
+        snaps.append((D.last_conv[0].weight.detach().clone(), G.input.const.detach().clone(), g_ema.input.const.detach().clone()))
+    (variant,) = step_fn.variants.values()
+    assert variant.graph is not None and variant.launches_per_replay > 300
+    for log in logs:
+        assert all(np.isfinite(v) for v in log.values()), log
+    # steps 5..7 are replays: every one of them moved D, G and the EMA copy
+    for a, b in zip(snaps[3:-1], snaps[4:]):
+        assert all(not torch.equal(x, y) for x, y in zip(a, b))
+    eager_d = [l["d_loss"] for l in logs[:3]]
+    assert all(0.3 * min(eager_d) < l["d_loss"] < 3 * max(eager_d) for l in logs[3:]), logs
+    assert int(opts[1].state[D.last_conv[0].weight]["step"]) == 7
+    REPORT["graphed.launches_per_replay"] = variant.launches_per_replay
+    REPORT["graphed.logs"] = logs
+    step_fn.release()
+
+
 def test_zz_write_report():
     try:
         os.makedirs("gpurun_out", exist_ok=True)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--d-reg-every", type=int, default=1)
+    ap.add_argument("--graph", action="store_true", help="replay the step as a CUDA graph (engine.GraphedStyleGAN2Step)")
     args = ap.parse_args()
     import gin
     from contrad_b200 import _capi, engine
@@ -46,21 +47,26 @@ def main():
     opts = (FusedAdam(G.parameters(), lr=2e-3, betas=(0.0, 0.99)), FusedAdam(D.parameters(), lr=2e-3, betas=(0.0, 0.99)))
     images = [torch.rand(n, 3, 32, 32, device="cuda") for _ in range(4)]
 
+    graphed = engine.GraphedStyleGAN2Step(P, opt, GD, g_ema, opts) if args.graph else None
+
     def run(k, first):
         for s in range(first, first + k):
-            out = engine.train_step_stylegan2(P, opt, GD, g_ema, opts, images[s % 4], s)
+            if graphed is not None:
+                out = graphed(images[s % 4], s)
+            else:
+                out = engine.train_step_stylegan2(P, opt, GD, g_ema, opts, images[s % 4], s)
         return out
 
-    run(args.warmup, 1)
+    run(args.warmup + (5 if args.graph else 0), 1)
     torch.cuda.synchronize()
     l0 = _capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out = run(args.steps, 1 + args.warmup)
+    out = run(args.steps, 1 + args.warmup + (5 if args.graph else 0))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
-    res = {"workload": "StyleGAN2(small32)+ContraD 32x32 b%d, R1 every %d step(s), eager" % (n, args.d_reg_every),
+    res = {"workload": "StyleGAN2(small32)+ContraD 32x32 b%d, R1 every %d step(s), %s" % (n, args.d_reg_every, "cuda-graph replay" if args.graph else "eager"),
            "ms_per_step": ms, "images_per_s": n / ms * 1e3, "launches_per_step": (_capi.launch_count() - l0) / args.steps,
            "losses": {k: float(v) for k, v in out.items()}}
 
