@@ -564,6 +564,186 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
         stg_stream4(dxb + e, *reinterpret_cast<const float4*>(gs + e));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large-image path (H*W > 4096: the 512x512 StyleGAN2 configs).  The image no longer fits one CTA's shared memory, so
+// the chain runs from global memory, one thread per output pixel, and the two per-image reductions the chain contains
+// (the per-channel mean of `adjust_contrast` and, in the backward pass, the mean of the masked gradient) become
+// separate reduction launches that write [B,3] scalars:
+//     fwd: mean kernel (skipped per image when colour jitter is off) -> apply kernel
+//     bwd: masked-gradient-sum kernel -> scatter kernel (transposed bilinear crop with global fp32 atomics)
+// The crop / hsv arithmetic is recomputed in each pass instead of being stored: x is read through L2 (the 4 bilinear
+// taps of neighbouring pixels overlap), y / dy / dx move once.
+struct PixelTaps {
+    int o00, o01, o10, o11;
+    float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ PixelTaps pixel_taps(int i, int j, int H, int W, const SampleParams& sp) {
+    const Tap ty = axis_tap(i, H, sp.sy, sp.by);
+    const Tap tx = axis_tap((sp.flip < 0.f) ? (W - 1 - j) : j, W, sp.sx, sp.bx);
+    PixelTaps t;
+    t.o00 = ty.i0 * W + tx.i0; t.o01 = ty.i0 * W + tx.i1; t.o10 = ty.i1 * W + tx.i0; t.o11 = ty.i1 * W + tx.i1;
+    t.w00 = tx.w0 * ty.w0; t.w01 = tx.w1 * ty.w0; t.w10 = tx.w0 * ty.w1; t.w11 = tx.w1 * ty.w1;
+    return t;
+}
+
+__device__ __forceinline__ void gather_pixel(const float* __restrict__ xb, int HW, const PixelTaps& t, float (&v)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* xc = xb + (size_t)c * HW;
+        v[c] = __ldg(xc + t.o00) * t.w00 + __ldg(xc + t.o01) * t.w01 + __ldg(xc + t.o10) * t.w10 + __ldg(xc + t.o11) * t.w11;
+    }
+}
+
+// means[b,3] += per-channel mean of the contrast input (crop+flip, then hsv when the order is [hsv, contrast])
+__global__ void __launch_bounds__(kMaxThreads)
+augment_large_mean_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ means, int B,
+                          int H, int W, int order) {
+    __shared__ float red[96];
+    const int b = blockIdx.y;
+    const SampleParams sp = load_params(params, B, b);
+    if (sp.cj_on == 0.f) return;                                   // uniform per CTA
+    const int ord = resolve_order(params, B, b, order);
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    const int HW = H * W;
+    const float* xb = x + (size_t)b * 3 * HW;
+    float sums[3] = {0.f, 0.f, 0.f};
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float v[3];
+        gather_pixel(xb, HW, pixel_taps(pix / W, pix % W, H, W, sp), v);
+        if (ord == 1) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
+        sums[0] += v[0]; sums[1] += v[1]; sums[2] += v[2];
+    }
+    block_sum<3>(sums, red);
+    if (threadIdx.x == 0) {
+        const float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(means + b * 3 + c, sums[c] * inv);
+    }
+}
+
+__global__ void __launch_bounds__(kMaxThreads)
+augment_large_apply_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
+                           const float* __restrict__ means, int B, int H, int W, int order) {
+    const int b = blockIdx.y;
+    const SampleParams sp = load_params(params, B, b);
+    const int ord = resolve_order(params, B, b, order);
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    const int HW = H * W;
+    const float* xb = x + (size_t)b * 3 * HW;
+    float* yb = y + (size_t)b * 3 * HW;
+    float m[3] = {0.f, 0.f, 0.f};
+    if (sp.cj_on != 0.f) { m[0] = __ldg(means + b * 3); m[1] = __ldg(means + b * 3 + 1); m[2] = __ldg(means + b * 3 + 2); }
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float v[3];
+        gather_pixel(xb, HW, pixel_taps(pix / W, pix % W, H, W, sp), v);
+        if (sp.cj_on != 0.f) {
+            if (ord == 1) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = clamp01((v[c] - m[c]) * sp.fc + m[c]);
+            if (ord == 0) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
+        }
+        if (sp.gray_on != 0.f) {
+            const float l = 0.299f * v[0] + 0.587f * v[1] + 0.114f * v[2];
+            v[0] = l; v[1] = l; v[2] = l;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) __stcs(yb + (size_t)c * HW + pix, v[c]);
+    }
+}
+
+// Gradient at the contrast OUTPUT for one pixel: gray backward, hsv straight-through, clamp mask (needs the forward
+// value at the contrast input, recomputed here).  Returns false when the image has no colour jitter.
+__device__ __forceinline__ void masked_grad(const float* __restrict__ xb, const float* __restrict__ dyb, int HW, int pix,
+                                            const PixelTaps& t, const SampleParams& sp, int ord, float hshift,
+                                            const float* m, float (&g)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = __ldcs(dyb + (size_t)c * HW + pix);
+    if (sp.gray_on != 0.f) {
+        const float s = g[0] + g[1] + g[2];
+        g[0] = 0.299f * s; g[1] = 0.587f * s; g[2] = 0.114f * s;
+    }
+    if (sp.cj_on != 0.f) {
+        float f[3];
+        gather_pixel(xb, HW, t, f);
+        if (ord == 1) hsv_jitter(f[0], f[1], f[2], hshift, sp.fs, sp.fv);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float u = (f[c] - m[c]) * sp.fc + m[c];
+            if (!(u >= 0.f && u <= 1.f)) g[c] = 0.f;               // clamp backward (inclusive)
+        }
+    }
+}
+
+// gsums[b,3] += sum over pixels of the masked gradient (only images with colour jitter)
+__global__ void __launch_bounds__(kMaxThreads)
+augment_large_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ params,
+                                const float* __restrict__ means, float* __restrict__ gsums, int B, int H, int W, int order) {
+    __shared__ float red[96];
+    const int b = blockIdx.y;
+    const SampleParams sp = load_params(params, B, b);
+    if (sp.cj_on == 0.f) return;
+    const int ord = resolve_order(params, B, b, order);
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    const int HW = H * W;
+    const float* xb = x + (size_t)b * 3 * HW;
+    const float* dyb = dy + (size_t)b * 3 * HW;
+    const float m[3] = {__ldg(means + b * 3), __ldg(means + b * 3 + 1), __ldg(means + b * 3 + 2)};
+    float sums[3] = {0.f, 0.f, 0.f};
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float g[3];
+        masked_grad(xb, dyb, HW, pix, pixel_taps(pix / W, pix % W, H, W, sp), sp, ord, hshift, m, g);
+        sums[0] += g[0]; sums[1] += g[1]; sums[2] += g[2];
+    }
+    block_sum<3>(sums, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(gsums + b * 3 + c, sums[c]);
+    }
+}
+
+// dx (zeroed by the host) += transposed crop of the gradient at the crop output
+__global__ void __launch_bounds__(kMaxThreads)
+augment_large_bwd_scatter_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx,
+                                 const float* __restrict__ params, const float* __restrict__ means,
+                                 const float* __restrict__ gsums, int B, int H, int W, int order) {
+    const int b = blockIdx.y;
+    const SampleParams sp = load_params(params, B, b);
+    const int ord = resolve_order(params, B, b, order);
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    const int HW = H * W;
+    const float* xb = x + (size_t)b * 3 * HW;
+    const float* dyb = dy + (size_t)b * 3 * HW;
+    float* dxb = dx + (size_t)b * 3 * HW;
+    float m[3] = {0.f, 0.f, 0.f}, gm[3] = {0.f, 0.f, 0.f};
+    if (sp.cj_on != 0.f) {
+        const float inv = (1.f - sp.fc) / (float)HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { m[c] = __ldg(means + b * 3 + c); gm[c] = __ldg(gsums + b * 3 + c) * inv; }
+    }
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        const PixelTaps t = pixel_taps(pix / W, pix % W, H, W, sp);
+        float g[3];
+        masked_grad(xb, dyb, HW, pix, t, sp, ord, hshift, m, g);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float gv = (sp.cj_on != 0.f) ? fmaf(sp.fc, g[c], gm[c]) : g[c];
+            float* base = dxb + (size_t)c * HW;
+            atomicAdd(base + t.o00, gv * t.w00);
+            if (t.w01 != 0.f) atomicAdd(base + t.o01, gv * t.w01);
+            if (t.w10 != 0.f) atomicAdd(base + t.o10, gv * t.w10);
+            if (t.w11 != 0.f) atomicAdd(base + t.o11, gv * t.w11);
+        }
+    }
+}
+
+inline dim3 large_grid(int B, int H, int W) {
+    long long blocks = ((long long)H * W + kMaxThreads - 1) / kMaxThreads;
+    const long long cap = (148LL * 16 + B - 1) / B;                // about 16 resident CTAs per SM over the whole batch
+    if (blocks > cap) blocks = cap < 1 ? 1 : cap;
+    return dim3((unsigned)blocks, (unsigned)B);
+}
+
 struct LaunchShape {
     int threads, qpt;
 };
@@ -646,5 +826,41 @@ extern "C" int cb200_augment_simclr_bwd(const float* x, const float* dy, float* 
 #undef LAUNCH_BWD
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("augment_simclr_bwd");
+    return CB200_OK;
+}
+
+// Any image size (used for H*W > 4096).  `means` [B,3] is written by the forward pass and must be handed to the
+// backward pass unchanged; `gsums` [B,3] is backward scratch.  Both are caller-allocated.
+extern "C" int cb200_augment_simclr_large_fwd(const float* x, float* y, const float* params, float* means, int B, int H,
+                                              int W, int order, void* stream) {
+    CB200_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && (order >= -1 && order <= 1), "augment_large_fwd: bad shape/order");
+    if (B == 0) return CB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(means, 0, sizeof(float) * 3 * (size_t)B, st);
+    if (e != cudaSuccess) { cb200_set_error("augment_large_fwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    const dim3 grid = large_grid(B, H, W);
+    augment_large_mean_kernel<<<grid, kMaxThreads, 0, st>>>(x, params, means, B, H, W, order);
+    CB200_COUNT_LAUNCH();
+    augment_large_apply_kernel<<<grid, kMaxThreads, 0, st>>>(x, y, params, means, B, H, W, order);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("augment_simclr_large_fwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_augment_simclr_large_bwd(const float* x, const float* dy, float* dx, const float* params,
+                                              const float* means, float* gsums, int B, int H, int W, int order,
+                                              void* stream) {
+    CB200_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && (order >= -1 && order <= 1), "augment_large_bwd: bad shape/order");
+    if (B == 0) return CB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(gsums, 0, sizeof(float) * 3 * (size_t)B, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * (size_t)B * H * W, st);
+    if (e != cudaSuccess) { cb200_set_error("augment_large_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    const dim3 grid = large_grid(B, H, W);
+    augment_large_bwd_reduce_kernel<<<grid, kMaxThreads, 0, st>>>(x, dy, params, means, gsums, B, H, W, order);
+    CB200_COUNT_LAUNCH();
+    augment_large_bwd_scatter_kernel<<<grid, kMaxThreads, 0, st>>>(x, dy, dx, params, means, gsums, B, H, W, order);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("augment_simclr_large_bwd");
     return CB200_OK;
 }

@@ -32,6 +32,13 @@ void cb200_set_error(const char* fmt, ...);
 extern unsigned long long g_cb200_launches;
 #define CB200_COUNT_LAUNCH() (++g_cb200_launches)
 
+// Once-per-device flags for cudaFuncSetAttribute (nn.DataParallel drives several devices from one process).
+inline bool& cb200_device_flag(bool (&flags)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return flags[dev & 63];
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -452,6 +452,20 @@ __global__ void __launch_bounds__(kT) axpby_kernel(const float* __restrict__ a, 
     }
 }
 
+// y[row, 0:C] = x[row, :], y[row, C:Cp] = 0   (zero-extends the channel dimension: the tensor-core weight-gradient kernels
+// tile the output channels by 128, layers with 32 / 64 channels present their dY zero-padded)
+__global__ void __launch_bounds__(kT) pad_channels_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows,
+                                                          int C4, int Cp4) {
+    const long long total = rows * Cp4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp4);
+        const long long r = i / Cp4;
+        y4[i] = c < C4 ? __ldg(x4 + r * C4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ EMA of G
 constexpr int kMaxEma = 64;
 constexpr int kEmaElemsPerCta = kT * 16;
@@ -706,6 +720,15 @@ extern "C" int cb200_axpby(const float* a, const float* b, float* out, long long
     axpby_kernel<<<grid_for(n), kT, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, alpha, beta, gamma, round_out);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("axpby");
+    return CB200_OK;
+}
+
+extern "C" int cb200_pad_channels(const float* x, float* y, long long rows, int C, int Cp, void* stream) {
+    CB200_CHECK_ARG(rows > 0 && C > 0 && Cp >= C && C % 4 == 0 && Cp % 4 == 0, "pad_channels: C, Cp must be multiples of 4, Cp >= C");
+    CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "pad_channels: 16-byte alignment");
+    pad_channels_kernel<<<grid_for(rows * (Cp / 4)), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, C / 4, Cp / 4);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("pad_channels");
     return CB200_OK;
 }
 

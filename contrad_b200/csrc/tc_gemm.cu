@@ -653,7 +653,8 @@ struct Epilogue {
 template <int BN, int STAGES>
 int launch(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
     using L = SmemLayout<BN, STAGES>;
-    static bool configured = false;
+    static bool configured_dev[64] = {};          // per device: the attribute belongs to the device's context
+    bool& configured = cb200_device_flag(configured_dev);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::kTotal);
@@ -673,7 +674,8 @@ int launch(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaSt
 template <int BN, int STAGES>
 int launch2(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
     using L = SmemLayout2<BN, STAGES>;
-    static bool configured = false;
+    static bool configured_dev[64] = {};          // per device: the attribute belongs to the device's context
+    bool& configured = cb200_device_flag(configured_dev);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::kTotal);
@@ -709,7 +711,8 @@ int launch2(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaS
 template <int BN, int MT, int STAGES>
 int launch_persist(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
     using L = SmemLayoutP<BN, MT, STAGES>;
-    static bool configured = false;
+    static bool configured_dev[64] = {};          // per device: the attribute belongs to the device's context
+    bool& configured = cb200_device_flag(configured_dev);
     static int sms = 0;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tap_gemm_persist_kernel<BN, MT, STAGES>,

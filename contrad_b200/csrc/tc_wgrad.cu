@@ -253,7 +253,8 @@ void pick_pixel_box(int KP, int Wo, int Ho, int* wt, int* ht, int* bt) {
 template <int BN, int NB, int KP, int STAGES>
 int launch_wgrad(WgradParams& p, int Cout, int sm_count, cudaStream_t st, const char* name) {
     using L = WgSmem<BN, NB, KP, STAGES>;
-    static bool configured = false;
+    static bool configured_dev[64] = {};          // per device: the attribute belongs to the device's context
+    bool& configured = cb200_device_flag(configured_dev);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, NB, KP, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::kTotal);

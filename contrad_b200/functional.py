@@ -24,18 +24,33 @@ def _c(t):
 # augmentation  (reference: augment/__init__.py:106-112 chain; backward = its autograd)
 # ------------------------------------------------------------------------------------------------
 class AugmentSimCLRFn(Function):
+    """Images up to 64x64 take the one-image-per-CTA kernels; larger ones (the 512x512 StyleGAN2 configs) the
+    global-memory kernels, which also hand the per-image contrast means from the forward to the backward pass.
+    `force_large` selects the second path for any size (parity tests)."""
+
     @staticmethod
-    def forward(ctx, x, params, order):
+    def forward(ctx, x, params, order, force_large=False):
         x = _c(x)
-        ctx.save_for_backward(x, params)
         ctx.order = order
+        ctx.large = bool(force_large) or K.augment_needs_large_path(x.shape[2], x.shape[3])
+        if ctx.large:
+            y, means = K.augment_simclr_large_fwd(x, params, order)
+            ctx.save_for_backward(x, params, means)
+            return y
+        ctx.save_for_backward(x, params)
         return K.augment_simclr_fwd(x, params, order)
 
     @staticmethod
     def backward(ctx, dy):
-        x, params = ctx.saved_tensors
-        dx = K.augment_simclr_bwd(x, _c(dy), params, ctx.order) if ctx.needs_input_grad[0] else None
-        return dx, None, None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.large:
+                x, params, means = ctx.saved_tensors
+                dx = K.augment_simclr_large_bwd(x, _c(dy), params, ctx.order, means)
+            else:
+                x, params = ctx.saved_tensors
+                dx = K.augment_simclr_bwd(x, _c(dy), params, ctx.order)
+        return dx, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

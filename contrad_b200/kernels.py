@@ -62,6 +62,36 @@ def augment_simclr_bwd(x, dy, params, order):
     return dx
 
 
+def augment_needs_large_path(H, W):
+    """The one-image-per-CTA kernels hold H*W <= 4096 pixels in shared memory; beyond that the global-memory path."""
+    return H * W > 4096 or W % 4 != 0
+
+
+def augment_simclr_large_fwd(x, params, order):
+    """Any image size.  Returns (y, means[B,3]); `means` must be passed to augment_simclr_large_bwd."""
+    x = _f32c(x, "x")
+    params = _f32c(params, "params")
+    B, C, H, W = x.shape
+    assert C == 3 and params.shape == (len(PARAM_FIELDS) + (1 if order < 0 else 0), B), (x.shape, params.shape, order)
+    y = torch.empty_like(x)
+    means = torch.empty(B, 3, device=x.device, dtype=torch.float32)
+    _call("augment_simclr_fwd", 0, 12 * x.numel(), lib().cb200_augment_simclr_large_fwd, ptr(x), ptr(y), ptr(params), ptr(means),
+          i32(B), i32(H), i32(W), i32(order), stream_ptr())
+    return y, means
+
+
+def augment_simclr_large_bwd(x, dy, params, order, means):
+    x = _f32c(x, "x")
+    dy = _f32c(dy, "dy")
+    params = _f32c(params, "params")
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    gsums = torch.empty(B, 3, device=x.device, dtype=torch.float32)
+    _call("augment_simclr_bwd", 0, 20 * x.numel(), lib().cb200_augment_simclr_large_bwd, ptr(x), ptr(dy), ptr(dx), ptr(params),
+          ptr(means), ptr(gsums), i32(B), i32(H), i32(W), i32(order), stream_ptr())
+    return dx
+
+
 # ------------------------------------------------------------------ tensor-core GEMM / conv
 def _colsum_buf(colsum, n):
     if colsum is not None:

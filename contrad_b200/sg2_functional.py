@@ -125,9 +125,8 @@ class MmTN(Function):
             return K.gemm_tn_wgrad(g, a)
         if k % 128 == 0:                               # the kernel wants 128 | rows of the result: compute the transpose
             return K.gemm_tn_wgrad(a, g).t().contiguous()
-        gp = torch.zeros(g.shape[0], (n + 127) // 128 * 128, device=g.device, dtype=g.dtype)
-        gp[:, :n] = g
-        return K.gemm_tn_wgrad(gp, a)[:n].contiguous()
+        # thin layers on both sides (e.g. 32 -> 64 channels at 512x512): zero-extend the cotangent to 128 columns
+        return K.gemm_tn_wgrad(S.pad_channels(g, (n + 127) // 128 * 128), a)[:n].contiguous()
 
     @staticmethod
     def backward(ctx, gw):
@@ -197,7 +196,11 @@ class Conv3x3Wgrad(Function):
         x, dy = _c(x), _c(dy)
         ctx.save_for_backward(x, dy)
         cout, cin = dy.shape[3], x.shape[3]
-        return K.conv2d_nhwc_wgrad(x, dy, 3, 1).view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
+        if cout % 128:          # the kernel tiles Cout by 128: 32- / 64-channel layers present dY zero-extended
+            dwp = K.conv2d_nhwc_wgrad(x, S.pad_channels(dy, (cout + 127) // 128 * 128), 3, 1)[:cout]
+        else:
+            dwp = K.conv2d_nhwc_wgrad(x, dy, 3, 1)
+        return dwp.view(cout, 3, 3, cin).permute(0, 3, 1, 2).contiguous()
 
     @staticmethod
     def backward(ctx, gw):

@@ -258,6 +258,17 @@ def axpby(a, b=None, alpha=1.0, beta=1.0, gamma=0.0, round_out=False):
     return out
 
 
+def pad_channels(x, cp):
+    """x [..., C] -> [..., cp] zero-extended in the last dimension."""
+    x = _f32c(x, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty(tuple(x.shape[:-1]) + (cp,), device=x.device, dtype=torch.float32)
+    _call("pad_channels", 0, 4 * (x.numel() + y.numel()), lib().cb200_pad_channels, ptr(x), ptr(y), i64(rows), i32(C), i32(cp),
+          stream_ptr())
+    return y
+
+
 class _EmaTensor(ctypes.Structure):
     _fields_ = [("dst", ctypes.c_void_p), ("src", ctypes.c_void_p), ("numel", ctypes.c_longlong)]
 

@@ -10,6 +10,8 @@ latents, Adam's step-dependent scalars) reaches the GPU through ``stage(producer
   again in the recorded order - i.e. the host RNG streams advance exactly as in the eager loop - and refreshes the
   static buffers through pinned slots, outside the graph.
 """
+import threading
+
 import torch
 
 _SLOTS = 8
@@ -29,7 +31,18 @@ class _PinnedRing(object):
         return ring[self.i]
 
 
-_RING = _PinnedRing()
+class _ThreadLocalRing(threading.local):
+    """One pinned ring per host thread: nn.DataParallel drives one replica per thread, and two replicas must never be
+    handed the same pinned slot."""
+
+    def __init__(self):
+        self.ring = _PinnedRing()
+
+    def next(self, shape, dtype):
+        return self.ring.next(shape, dtype)
+
+
+_RING = _ThreadLocalRing()
 
 
 def recording():

@@ -51,6 +51,14 @@ int cb200_augment_simclr_fwd(const float* x, float* y, const float* params, int 
 int cb200_augment_simclr_bwd(const float* x, const float* dy, float* dx, const float* params,
                              int B, int H, int W, int order, void* stream);
 
+/* Same chain for images of any size (the entry points above keep one image per CTA in shared memory: H*W <= 4096;
+ * these run from global memory and are what the 512x512 StyleGAN2 configs use).  means [B,3] (per-channel mean at the
+ * contrast input, written by fwd, read by bwd) and gsums [B,3] (bwd scratch) are caller-allocated. */
+int cb200_augment_simclr_large_fwd(const float* x, float* y, const float* params, float* means, int B, int H, int W,
+                                   int order, void* stream);
+int cb200_augment_simclr_large_bwd(const float* x, const float* dy, float* dx, const float* params, const float* means,
+                                   float* gsums, int B, int H, int W, int order, void* stream);
+
 /* ---- tcgen05 tensor-core GEMM / implicit-GEMM convolutions (TF32 in, FP32 accumulate) --------
  * Replace F.linear / nn.Conv2d / nn.ConvTranspose2d behind models/gan/sndcgan.py:24-38,91-109 and
  * models/gan/base.py:14-35,92-101 (cuBLAS / cuDNN in the reference).  Activations are NHWC.
@@ -257,6 +265,8 @@ int cb200_row_sqsum(const float* x, float* out, int B, long long n, void* stream
 int cb200_row_scale(const float* x, const float* s, float* y, int B, long long n, float alpha, void* stream);
 int cb200_axpby(const float* a, const float* b, float* out, long long n, float alpha, float beta, float gamma, int round_out,
                 void* stream);
+/* y[rows, Cp] = [x[rows, C], 0]: zero-extension of the channel dimension (operands of the weight-gradient kernels). */
+int cb200_pad_channels(const float* x, float* y, long long rows, int C, int Cp, void* stream);
 struct cb200_ema_tensor {
     float* dst; const float* src; long long numel;
 };

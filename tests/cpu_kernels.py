@@ -224,6 +224,10 @@ def axpby(a, b=None, alpha=1.0, beta=1.0, gamma=0.0, round_out=False):
     return y if b is None else y + beta * b
 
 
+def pad_channels(x, cp):
+    return F.pad(x, (0, cp - x.shape[-1]))
+
+
 def ema_lerp(pairs, decay):
     for d, s in pairs:
         d.mul_(decay).add_(s, alpha=1 - decay)
@@ -232,7 +236,7 @@ def ema_lerp(pairs, decay):
 K_NAMES = ("gemm_nt", "gemm_tn_wgrad", "conv2d_nhwc_fwd", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "colsum", "round_tf32_")
 S_NAMES = ("upfirdn2d", "patch_s2_gather", "patch_s2_scatter", "bias_act", "bias_act_grad", "modulate", "mul_reduce",
            "mod_epilogue", "noise_grad", "stddev_fwd", "stddev_bwd", "stddev_bwd_bwd", "stddev_concat", "stddev_split",
-           "rgb_to_nhwc", "nhwc_to_rgb", "pixelnorm", "row_sqsum", "row_scale", "axpby", "ema_lerp")
+           "rgb_to_nhwc", "nhwc_to_rgb", "pixelnorm", "row_sqsum", "row_scale", "axpby", "ema_lerp", "pad_channels")
 
 
 @contextlib.contextmanager

@@ -58,6 +58,38 @@ def test_augment_matches_oracle_random(K, B, size, seed):
     assert bad < 2e-3, bad
 
 
+def test_augment_large_path_matches_reference_golden(K, golden_dir):
+    """The global-memory kernels (images > 64x64) forced onto the reference-generated small fixtures."""
+    fx = _load(golden_dir, "augment_simclr.pt")
+    for case in fx["cases"]:
+        x, dy, params = case["x"].cuda(), case["dy"].cuda(), case["params"].cuda()
+        y, means = K.augment_simclr_large_fwd(x, params, case["order"])
+        dx = K.augment_simclr_large_bwd(x, dy, params, case["order"], means)
+        assert torch.allclose(y.cpu(), case["y"], atol=2e-5, rtol=0), (y.cpu() - case["y"]).abs().max()
+        assert torch.allclose(dx.cpu(), case["dx"], atol=1e-4, rtol=1e-4), (dx.cpu() - case["dx"]).abs().max()
+
+
+@pytest.mark.parametrize("B,H,W,seed", [(3, 128, 128, 0), (2, 96, 80, 1), (5, 256, 256, 2), (2, 512, 512, 3)])
+def test_augment_large_path_matches_oracle(K, B, H, W, seed):
+    """Large images (up to the 512x512 of BASELINE config 5) against the CPU oracle, forward and backward, through the
+    autograd Function (which picks the large path by size)."""
+    import numpy as np
+    from contrad_b200.functional import AugmentSimCLRFn
+    np.random.seed(seed); torch.manual_seed(seed)
+    x = torch.rand(B, 3, H, W)
+    dy = torch.randn(B, 3, H, W)
+    params, order = O.sample_simclr_params(B, H, W)
+    xr = x.clone().requires_grad_(True)
+    yr = O.augment_simclr(xr, params, order)
+    (yr * dy).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    y = AugmentSimCLRFn.apply(xg, O.pack_params(params).cuda(), order)
+    (y * dy.cuda()).sum().backward()
+    assert torch.allclose(y.detach().cpu(), yr.detach(), atol=3e-5, rtol=0), (y.detach().cpu() - yr.detach()).abs().max()
+    bad = ((xg.grad.cpu() - xr.grad).abs() > 2e-4 + 2e-4 * xr.grad.abs()).float().mean()
+    assert bad < 2e-3, bad
+
+
 def test_augment_per_image_order_row(K):
     """order = -1: the jitter order comes per image from row 11 of the parameter block (CUDA-graph replay path);
     forward and backward equal the launch-wide order applied image by image."""

@@ -555,6 +555,119 @@ def test_full_stylegan2_step_runs():
     REPORT["step.values"] = {k: float(v) for k, v in out.items()}
 
 
+def test_stylegan2_512_matches_oracle():
+    """BASELINE config 5 architecture (`stylegan2_512`, channel_multiplier 1.0, 512x512): thin 32/64-channel layers at
+    512^2 / 256^2 (zero-extended weight-gradient operands, BN=32/64 tap-GEMM tiles), 7 ResBlocks, 15 style layers.
+    D (B=4) and G (B=2) forward + backward against the fp32 CPU oracle; the R1 double backward and the large-image
+    augmentation run on the same inputs."""
+    from oracle import stylegan2_oracle as SO
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import stylegan2 as T
+    size = 512
+    sd_d = SO.make_d_state(size, small32=False, channel_multiplier=1.0, d_hidden=512, generator=torch.Generator().manual_seed(7))
+    sd_g = SO.make_g_state(size, small32=False, channel_multiplier=1.0, generator=torch.Generator().manual_seed(8))
+    gen = torch.Generator().manual_seed(9)
+    for sd in (sd_d, sd_g):
+        for k in sd:
+            if k.endswith(".bias") and sd[k].abs().sum() == 0:
+                sd[k] = 0.1 * torch.randn(sd[k].shape, generator=gen)
+            if k.endswith("noise.weight"):
+                sd[k] = 0.1 * torch.randn(1, generator=gen)
+    G, D = get_architecture("stylegan2_512", (size, size, 3))
+    D.load_state_dict(sd_d, strict=True); G.load_state_dict(sd_g, strict=True)
+    G.cuda().train(); D.cuda().train()
+    ck = _Checks("sg2_512")
+    # ---- discriminator
+    torch.manual_seed(3)
+    x = torch.rand(4, 3, size, size)
+    c1 = torch.randn(4, 128)
+    leaf = {k: (v.clone().requires_grad_(True) if not k.endswith(".kernel") else v) for k, v in sd_d.items()}
+    d_o, p1_o, _ = SO.d_forward(leaf, x, size)
+    (d_o.sum() + (p1_o * c1).sum()).backward()
+    d, aux = D(x.cuda(), projection=True)
+    (d.sum() + (aux["projection"] * c1.cuda()).sum()).backward()
+    ck.add("D.d", _rel(d, d_o), 1e-2)
+    ck.add("D.projection", _rel(aux["projection"], p1_o), 1e-2)
+    ck.add("D.norms", _norm_errs({k: p.grad for k, p in D.named_parameters()},
+                                 {k: float(v.grad.norm()) for k, v in leaf.items() if v.requires_grad and v.grad is not None},
+                                 "sg2_512.D"), 5e-2)
+    # ---- R1 at 512x512 (double backward through every operator) and the large-image augmentation in front of it
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    from contrad_b200.augment import get_augment
+    gin.clear_config()
+    gin.parse_config("RandomResizeCropLayer.scale = (0.08, 1.0)\nColorJitterLayer.brightness = 0.8\n"
+                     "ColorJitterLayer.contrast = 0.8\nColorJitterLayer.saturation = 0.8\nColorJitterLayer.hue = 0.2\n")
+    D.zero_grad()
+    r1 = T.r1_per_sample(D, x.cuda(), get_augment(mode="simclr").cuda())
+    r1.mean().backward()
+    assert torch.isfinite(r1).all() and float(r1.min()) > 0
+    assert all(torch.isfinite(p.grad).all() for p in D.parameters() if p.grad is not None)
+    assert float(D.layers[1].conv1[0].weight.grad.abs().sum()) > 0
+    REPORT["sg2_512.r1"] = [float(v) for v in r1]
+    # ---- generator
+    torch.manual_seed(4)
+    z = torch.randn(2, 512)
+    noises = [torch.randn(*s_) for s_ in SO.noise_shapes(size, 2)]
+    c_img = torch.randn(2, 3, size, size)
+    leaf = {k: (v.clone().requires_grad_(True) if not k.endswith(".kernel") else v) for k, v in sd_g.items()}
+    img_o = SO.g_forward(leaf, z, size, noises)
+    (img_o * c_img).sum().backward()
+    img = G(z.cuda(), style_mix=0.0, noise=[n_.cuda() for n_ in noises])
+    (img * c_img.cuda()).sum().backward()
+    ck.add("G.image", _rel(img, img_o), 1e-2)
+    ck.add("G.norms", _norm_errs({k: p.grad for k, p in G.named_parameters()},
+                                 _no_noise({k: float(v.grad.norm()) for k, v in leaf.items() if v.requires_grad and v.grad is not None}),
+                                 "sg2_512.G"), 5e-2)
+    ck.finish()
+
+
+def test_gd_under_data_parallel():
+    """BASELINE config 5 drives G_D through nn.DataParallel (train_stylegan2_contraD.py:300-306): one host thread per
+    GPU in ONE process.  Needs >= 2 GPUs (`gpurun --gpus 2`); checks that the replicas run concurrently on their own
+    devices / streams and that the gathered outputs back-propagate into the master parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import stylegan2 as T
+    from contrad_b200 import engine
+    gin.clear_config()
+    gin.parse_config("RandomResizeCropLayer.scale = (0.2, 1.0)\nColorJitterLayer.brightness = 0.4\n"
+                     "ColorJitterLayer.contrast = 0.4\nColorJitterLayer.saturation = 0.4\nColorJitterLayer.hue = 0.1\n")
+    torch.manual_seed(0); np.random.seed(0)
+    G, D = get_architecture("stylegan2", (32, 32, 3))
+    G.cuda(0); D.cuda(0)
+    GD = torch.nn.DataParallel(T.G_D(G, D, get_augment(mode="simclr").cuda(0)), device_ids=[0, 1])
+    P = SimpleNamespace(temp=0.1, lbd_a=1.0, distributed=False)
+    images = torch.rand(16, 3, 32, 32, device="cuda:0")
+    # G step
+    engine.set_grad(G, True); engine.set_grad(D, False)
+    d_gen = GD(P, images, train_G=True)
+    assert d_gen.shape == (16, 1) and d_gen.device.index == 0
+    T.loss_G_fn(d_gen).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in G.parameters())
+    assert float(G.input.const.grad.abs().sum()) > 0
+    # D step + R1
+    engine.set_grad(G, False); engine.set_grad(D, True)
+    d_all, view_r, view_f = GD(P, images)
+    assert d_all[0].shape == (16, 1) and view_r[0].shape == (16, 128) and view_f[2].shape == (16, 128)
+    d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+    r1 = GD(P, images, return_r1_loss=True)
+    assert r1.shape == (16,)
+    (d_loss + aux["penalty"] + 0.05 * r1.mean()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in D.parameters())
+    REPORT["dp2.values"] = {"d_loss": float(d_loss.detach()), "penalty": float(aux["penalty"].detach()), "r1": float(r1.mean().detach())}
+
+
 def test_graphed_stylegan2_step():
     """GraphedStyleGAN2Step: 3 eager steps, capture, replays.  The replays must keep training (parameters move, losses
     stay finite and in the range of the eager steps) and consume fresh host draws (staged style-mixing indices)."""
