@@ -33,6 +33,13 @@ _ALIASES = {
     "models.gan": "contrad_b200.models.gan",
     "models.gan.base": "contrad_b200.models.gan.base",
     "models.gan.sndcgan": "contrad_b200.models.gan.sndcgan",
+    "models.gan.stylegan2": "contrad_b200.models.gan.stylegan2",
+    "models.gan.stylegan2.layers": "contrad_b200.models.gan.stylegan2.layers",
+    "models.gan.stylegan2.generator": "contrad_b200.models.gan.stylegan2.generator",
+    "models.gan.stylegan2.discriminator": "contrad_b200.models.gan.stylegan2.discriminator",
+    "models.gan.stylegan2.op": "contrad_b200.models.gan.stylegan2.op",
+    "models.gan.stylegan2.op.fused_act": "contrad_b200.models.gan.stylegan2.op.fused_act",
+    "models.gan.stylegan2.op.upfirdn2d": "contrad_b200.models.gan.stylegan2.op.upfirdn2d",
     "penalty": "contrad_b200.penalty",
 }
 
