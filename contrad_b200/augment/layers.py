@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import staging
-from ..functional import AugmentSimCLRFn
+from ..functional import AugmentSimCLRFn, CutOutFn, GaussianBlurFn
 
 _N_FIELDS = 11   # sx, sy, bx, by, flip, cj_on, contrast, hue, sat, val, gray_on
 
@@ -227,3 +227,77 @@ class FusedSimCLR(nn.Sequential):
             raise ValueError("FusedSimCLR expects [B,3,H,W] images, got %s" % (tuple(inputs.shape),))
         params, order = self.sample_params(inputs)
         return AugmentSimCLRFn.apply(inputs, params, order)
+
+
+def gaussian_taps(kernel_size, sigma):
+    """The normalised 1-D Gaussian whose outer product is kornia's `get_gaussian_kernel2d((k, k), (sigma, sigma))`."""
+    x = torch.arange(kernel_size, dtype=torch.float32) - kernel_size // 2
+    g = torch.exp(-x.pow(2.0) / (2.0 * float(sigma) ** 2))
+    return g / g.sum()
+
+
+@gin.configurable
+class GaussianBlur(nn.Module):
+    """augment/__init__.py:52-78: kernel size 2*floor((H/10)/2)+1, ONE sigma ~ U(sigma_range) per call (numpy), dense
+    outer-product Gaussian with 'reflect' padding - evaluated separably by cb200_gaussian_blur."""
+
+    def __init__(self, sigma_range):
+        super().__init__()
+        self.sigma_range = sigma_range
+
+    @staticmethod
+    def kernel_size(height):
+        return int((height // 10) / 2) * 2 + 1
+
+    def taps(self, inputs):
+        k = self.kernel_size(inputs.shape[2])
+        lo, hi = self.sigma_range
+        return staging.stage(lambda: gaussian_taps(k, np.random.uniform(lo, hi)), inputs.device, shape=(k,))
+
+    def forward(self, inputs, on=None):
+        if on is None:
+            on = inputs.new_ones(inputs.shape[0])
+        return GaussianBlurFn.apply(inputs, self.taps(inputs), on)
+
+
+@gin.configurable
+class CutOut(nn.Module):
+    """augment/spatial.py:151-181."""
+
+    def __init__(self, length):
+        super().__init__()
+        if length % 2 == 0:
+            raise ValueError("Currently CutOut only accepts odd lengths: length % 2 == 1")
+        self.length = length
+        self.register_buffer("_weight", torch.ones(1, 1, self.length))     # state_dict compatibility
+        self._padding = (length - 1) // 2
+
+    def sample(self, inputs):
+        n, _, h, w = inputs.shape
+        h_center = torch.randint(h, (n, 1), device=inputs.device)
+        w_center = torch.randint(w, (n, 1), device=inputs.device)
+        return h_center.view(n).float(), w_center.view(n).float()
+
+    def forward(self, inputs, on=None):
+        n = inputs.shape[0]
+        params = torch.empty(3, n, device=inputs.device)
+        params[0] = 1.0 if on is None else on
+        params[1], params[2] = self.sample(inputs)
+        return CutOutFn.apply(inputs, params, self.length)
+
+
+class FusedSimCLRHQ(FusedSimCLR):
+    """`simclr_hq` / `simclr_hq_cutout` (augment/__init__.py:115-133): the four fused stages, then
+    RandomApply(GaussianBlur, .5) and optionally RandomApply(CutOut, .5).  Random draws in the reference order:
+    ... gray mask, blur mask (device), sigma (numpy), cutout mask (device), centres (device)."""
+
+    def forward(self, inputs):
+        out = FusedSimCLR.forward(self, inputs)
+        apply_blur = self[4]
+        on = apply_blur.sample(inputs)
+        out = apply_blur.fn(out, on=on)
+        if len(self) > 5:
+            apply_cut = self[5]
+            on = apply_cut.sample(inputs)
+            out = apply_cut.fn(out, on=on)
+        return out

@@ -53,6 +53,35 @@ class AugmentSimCLRFn(Function):
         return dx, None, None, None
 
 
+class GaussianBlurFn(Function):
+    """RandomApply(GaussianBlur) (augment/__init__.py:52-78,100-103): y = on ? blur(x) : x."""
+
+    @staticmethod
+    def forward(ctx, x, taps, on):
+        ctx.save_for_backward(taps, on)
+        return K.gaussian_blur(_c(x), taps, on)
+
+    @staticmethod
+    def backward(ctx, dy):
+        taps, on = ctx.saved_tensors
+        return K.gaussian_blur(_c(dy), taps, on, adjoint=True), None, None
+
+
+class CutOutFn(Function):
+    """RandomApply(CutOut) (augment/spatial.py:151-181): a masking, so the backward is the same masking."""
+
+    @staticmethod
+    def forward(ctx, x, params, length):
+        ctx.save_for_backward(params)
+        ctx.length = length
+        return K.cutout(_c(x), params, length)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (params,) = ctx.saved_tensors
+        return K.cutout(_c(dy), params, ctx.length), None, None
+
+
 # ------------------------------------------------------------------------------------------------
 # spectral norm + packing of every D_SNDCGAN weight  (models/gan/sndcgan.py:111-118)
 # ------------------------------------------------------------------------------------------------

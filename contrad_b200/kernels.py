@@ -92,6 +92,32 @@ def augment_simclr_large_bwd(x, dy, params, order, means):
     return dx
 
 
+def gaussian_blur(x, taps, on, adjoint=False):
+    """x [B,C,H,W]; taps [k] normalised 1-D Gaussian (device); on [B] 0/1 mask.  y = on ? blur(x) : x (or its adjoint)."""
+    x = _f32c(x, "x")
+    taps = _f32c(taps, "taps")
+    on = _f32c(on, "on")
+    B, C, H, W = x.shape
+    assert on.numel() == B
+    tmp = torch.empty_like(x)
+    y = torch.empty_like(x)
+    _call("gaussian_blur", 0, 16 * x.numel(), lib().cb200_gaussian_blur, ptr(x), ptr(tmp), ptr(y), ptr(taps), ptr(on), i32(B), i32(C),
+          i32(H), i32(W), i32(taps.numel()), i32(1 if adjoint else 0), stream_ptr())
+    return y
+
+
+def cutout(x, params, length):
+    """x [B,C,H,W]; params [3,B] = {on, h centre, w centre}; zeroes the clipped length x length square."""
+    x = _f32c(x, "x")
+    params = _f32c(params, "params")
+    B, C, H, W = x.shape
+    assert params.shape == (3, B)
+    y = torch.empty_like(x)
+    _call("cutout", 0, 8 * x.numel(), lib().cb200_cutout, ptr(x), ptr(y), ptr(params), i32(B), i32(C), i32(H), i32(W), i32(length),
+          stream_ptr())
+    return y
+
+
 # ------------------------------------------------------------------ tensor-core GEMM / conv
 def _colsum_buf(colsum, n):
     if colsum is not None:

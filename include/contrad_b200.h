@@ -59,6 +59,16 @@ int cb200_augment_simclr_large_fwd(const float* x, float* y, const float* params
 int cb200_augment_simclr_large_bwd(const float* x, const float* dy, float* dx, const float* params, const float* means,
                                    float* gsums, int B, int H, int W, int order, void* stream);
 
+/* Tail of `simclr_hq` / `simclr_hq_cutout` (augment/__init__.py:52-78,115-133; augment/spatial.py:151-181):
+ * gaussian_blur: y[b] = on[b] ? blur(x[b]) : x[b]; `taps` = the k normalised 1-D Gaussian weights (device memory; the
+ *                reference's dense k x k outer-product kernel with 'reflect' padding, applied separably); `tmp` scratch
+ *                of x's size; adjoint = 1 applies the transpose (backward).  P = planes per image (3).
+ * cutout:        params [3, B] = {on, h centre, w centre}; zeroes the clipped (length x length) square; the backward
+ *                pass is the same call on the gradient. */
+int cb200_gaussian_blur(const float* x, float* tmp, float* y, const float* taps, const float* on, int B, int P, int H,
+                        int W, int k, int adjoint, void* stream);
+int cb200_cutout(const float* x, float* y, const float* params, int B, int P, int H, int W, int length, void* stream);
+
 /* ---- tcgen05 tensor-core GEMM / implicit-GEMM convolutions (TF32 in, FP32 accumulate) --------
  * Replace F.linear / nn.Conv2d / nn.ConvTranspose2d behind models/gan/sndcgan.py:24-38,91-109 and
  * models/gan/base.py:14-35,92-101 (cuBLAS / cuDNN in the reference).  Activations are NHWC.

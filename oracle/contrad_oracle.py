@@ -261,6 +261,59 @@ def augment_simclr(x, params, order):
     return x
 
 
+def sample_hq_params(batch, height, width, device="cpu", sigma_range=(0.1, 2.0), p_blur=0.5, p_cut=0.5, cutout=False):
+    """The draws `simclr_hq` / `simclr_hq_cutout` make AFTER those of `simclr` (call sample_simclr_params first):
+      Apply blur  augment/__init__.py:101-102  torch bernoulli(0.5)[B]
+      sigma       augment/__init__.py:73       np uniform(*sigma_range), once per batch
+      Apply cut   augment/__init__.py:101-102  torch bernoulli(0.5)[B]                     (simclr_hq_cutout only)
+      centres     augment/spatial.py:169-170   torch randint(h, (B,1)), randint(w, (B,1))
+    Returns a dict with blur_on [B], sigma (float) and, with cutout, cut_on / h_center / w_center [B]."""
+    dev = torch.device(device)
+    out = {"blur_on": torch.bernoulli(torch.full((batch,), p_blur, device=dev)),
+           "sigma": float(np.random.uniform(*sigma_range))}
+    if cutout:
+        out["cut_on"] = torch.bernoulli(torch.full((batch,), p_cut, device=dev))
+        out["h_center"] = torch.randint(height, (batch, 1), device=dev).view(batch)
+        out["w_center"] = torch.randint(width, (batch, 1), device=dev).view(batch)
+    return out
+
+
+def gaussian_blur(x, sigma):
+    """GaussianBlur.forward (augment/__init__.py:64-78) with kornia's two entry points restated (kornia is unpinned
+    in the reference and absent here - parity unpinned, SURVEY 8c): k = 2*int((H//10)/2)+1, the DENSE k x k kernel
+    outer(g, g) of the normalised 1-D Gaussian g, 'reflect' padding, depthwise correlation."""
+    b, c, h, w = x.shape
+    k = int((h // 10) / 2) * 2 + 1
+    t = torch.arange(k, dtype=torch.float32, device=x.device) - k // 2
+    g = torch.exp(-t.pow(2.0) / (2.0 * float(sigma) ** 2))
+    g = g / g.sum()
+    kern = torch.outer(g, g)
+    r = k // 2
+    xp = F.pad(x, (r, r, r, r), mode="reflect") if r > 0 else x
+    return F.conv2d(xp, kern.expand(c, 1, k, k).contiguous(), groups=c)
+
+
+def cutout(x, h_center, w_center, length):
+    """CutOut.forward (augment/spatial.py:163-181): 1 - outer(box_h, box_w) with boxes of `length` around the centres."""
+    b, _, h, w = x.shape
+    half = (length - 1) // 2
+    rows = torch.arange(h, device=x.device)[None, :]
+    cols = torch.arange(w, device=x.device)[None, :]
+    mh = ((rows - h_center.view(b, 1).long()).abs() <= half).float()
+    mw = ((cols - w_center.view(b, 1).long()).abs() <= half).float()
+    mask = 1.0 - mh[:, None, :, None] * mw[:, None, None, :]
+    return x * mask
+
+
+def augment_simclr_hq(x, params, order, hq, cutout_length=None):
+    """`simclr_hq` (augment/__init__.py:115-122) / `simclr_hq_cutout` (:125-133) on explicit parameters."""
+    x = augment_simclr(x, params, order)
+    x = _blend(x, gaussian_blur(x, hq["sigma"]), hq["blur_on"])
+    if "cut_on" in hq:
+        x = _blend(x, cutout(x, hq["h_center"], hq["w_center"], cutout_length), hq["cut_on"])
+    return x
+
+
 # --------------------------------------------------------------------------------------
 # 2. Spectral norm + SNDCGAN discriminator / generator on explicit parameter dicts
 # --------------------------------------------------------------------------------------

@@ -224,15 +224,42 @@ def gen_spectral_norm():
     print("spectral norm fixtures written")
 
 
+def gen_augment_hq():
+    """`simclr_hq` / `simclr_hq_cutout` (augment/__init__.py:115-133) through the reference chain; kornia is absent, its
+    two entry points come from contrad_b200/compat/kornia (parity unpinned for the blur)."""
+    from augment import get_augment
+    cases = []
+    for (batch, size, seed, mode) in ((6, 32, 1, "simclr_hq"), (5, 32, 2, "simclr_hq_cutout"), (2, 64, 3, "simclr_hq_cutout")):
+        seed_all(seed)
+        x = torch.rand(batch, 3, size, size)
+        dy = torch.randn(batch, 3, size, size)
+        params, order = O.sample_simclr_params(batch, size, size)
+        hq = O.sample_hq_params(batch, size, size, cutout=mode.endswith("cutout"))
+        aug = get_augment(mode=mode)
+        seed_all(seed)
+        x_ref = torch.rand(batch, 3, size, size)
+        _ = torch.randn(batch, 3, size, size)
+        assert torch.equal(x, x_ref)
+        x_ref.requires_grad_(True)
+        y_ref = aug(x_ref)
+        (y_ref * dy).sum().backward()
+        cases.append({"mode": mode, "seed": seed, "x": t2l(x), "dy": t2l(dy), "order": order, "params": O.pack_params(params),
+                      "hq": hq, "length": 15, "y": t2l(y_ref), "dx": t2l(x_ref.grad)})
+        print("augment_hq case %s B=%d size=%d seed=%d" % (mode, batch, size, seed))
+    torch.save({"cases": cases}, os.path.join(HERE, "augment_hq.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gin = ref_import.activate()
-    todo = args.only.split(",") if args.only else ["augment", "contrastive", "sn", "small", "config1"]
+    todo = args.only.split(",") if args.only else ["augment", "augment_hq", "contrastive", "sn", "small", "config1"]
     if "augment" in todo:
         gen_augment(gin)
+    if "augment_hq" in todo:
+        gen_augment_hq()
     if "contrastive" in todo:
         gen_contrastive()
     if "sn" in todo:

@@ -12,6 +12,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def K():
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)          # `gin` shim for contrad_b200.augment
     from contrad_b200 import kernels
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -88,6 +92,83 @@ def test_augment_large_path_matches_oracle(K, B, H, W, seed):
     assert torch.allclose(y.detach().cpu(), yr.detach(), atol=3e-5, rtol=0), (y.detach().cpu() - yr.detach()).abs().max()
     bad = ((xg.grad.cpu() - xr.grad).abs() > 2e-4 + 2e-4 * xr.grad.abs()).float().mean()
     assert bad < 2e-3, bad
+
+
+def _unpack_hq(case):
+    hq = case["hq"]
+    on = hq["blur_on"].cuda()
+    cut = None
+    if "cut_on" in hq:
+        cut = torch.stack([hq["cut_on"], hq["h_center"].float(), hq["w_center"].float()]).cuda()
+    return on, cut
+
+
+def test_augment_hq_matches_reference_golden(K, golden_dir):
+    """simclr_hq / simclr_hq_cutout: fused chain -> separable Gaussian blur -> CutOut against the reference chain
+    (dense kornia-style blur), forward and backward through the autograd Functions."""
+    from contrad_b200.augment.layers import GaussianBlur, gaussian_taps
+    from contrad_b200.functional import AugmentSimCLRFn, CutOutFn, GaussianBlurFn
+    fx = _load(golden_dir, "augment_hq.pt")
+    for case in fx["cases"]:
+        x = case["x"].cuda().requires_grad_(True)
+        on, cut = _unpack_hq(case)
+        taps = gaussian_taps(GaussianBlur.kernel_size(x.shape[2]), case["hq"]["sigma"]).cuda()
+        y = AugmentSimCLRFn.apply(x, case["params"].cuda(), case["order"])
+        y = GaussianBlurFn.apply(y, taps, on)
+        if cut is not None:
+            y = CutOutFn.apply(y, cut, case["length"])
+        (y * case["dy"].cuda()).sum().backward()
+        assert torch.allclose(y.detach().cpu(), case["y"], atol=2e-5, rtol=0), (y.detach().cpu() - case["y"]).abs().max()
+        assert torch.allclose(x.grad.cpu(), case["dx"], atol=1e-4, rtol=1e-4), (x.grad.cpu() - case["dx"]).abs().max()
+
+
+@pytest.mark.parametrize("B,H,W,seed", [(4, 512, 512, 0), (3, 96, 80, 1), (7, 32, 32, 2)])
+def test_gaussian_blur_and_cutout_vs_oracle(K, B, H, W, seed):
+    """The 51-tap blur of the 512x512 configs (and odd shapes): separable kernel vs the oracle's dense k x k reflect
+    correlation, its adjoint vs autograd, CutOut(255) vs the oracle mask."""
+    from contrad_b200.augment.layers import GaussianBlur, gaussian_taps
+    torch.manual_seed(seed)
+    x, dy = torch.rand(B, 3, H, W), torch.randn(B, 3, H, W)
+    sigma = 0.1 + 1.9 * float(torch.rand(()))
+    on = (torch.rand(B) > 0.4).float()
+    on[0] = 1.0
+    xr = x.clone().requires_grad_(True)
+    ref = O._blend(xr, O.gaussian_blur(xr, sigma), on)
+    (ref * dy).sum().backward()
+    taps = gaussian_taps(GaussianBlur.kernel_size(H), sigma).cuda()
+    got = K.gaussian_blur(x.cuda(), taps, on.cuda())
+    got_dx = K.gaussian_blur(dy.cuda(), taps, on.cuda(), adjoint=True)
+    assert torch.allclose(got.cpu(), ref.detach(), atol=3e-6, rtol=0), (got.cpu() - ref.detach()).abs().max()
+    assert torch.allclose(got_dx.cpu(), xr.grad, atol=2e-5, rtol=1e-5), (got_dx.cpu() - xr.grad).abs().max()
+    length = 255 if H >= 512 else 15
+    hc, wc = torch.randint(H, (B,)), torch.randint(W, (B,))
+    params = torch.stack([on, hc.float(), wc.float()]).cuda()
+    want = O._blend(x, O.cutout(x, hc, wc, length), on)
+    assert torch.equal(K.cutout(x.cuda(), params, length).cpu(), want)
+
+
+def test_augment_hq_modules_run(K):
+    """get_augment('simclr_hq_cutout') end to end (gin-bound constructor arguments, device draws, staging)."""
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    import numpy as np
+    from contrad_b200.augment import get_augment
+    gin.clear_config()
+    gin.parse_config("RandomResizeCropLayer.scale = (0.08, 1.0)\nColorJitterLayer.brightness = 0.8\n"
+                     "ColorJitterLayer.contrast = 0.8\nColorJitterLayer.saturation = 0.8\nColorJitterLayer.hue = 0.2\n"
+                     "GaussianBlur.sigma_range = (0.1, 2.0)\nCutOut.length = 15\n")
+    np.random.seed(0); torch.manual_seed(0)
+    for mode in ("simclr_hq", "simclr_hq_cutout"):
+        aug = get_augment(mode=mode).cuda()
+        x = torch.rand(64, 3, 64, 64, device="cuda", requires_grad=True)
+        y = aug(x)
+        y.sum().backward()
+        assert y.shape == x.shape and torch.isfinite(y).all() and float(y.min()) >= 0 and float(y.max()) <= 1
+        assert torch.isfinite(x.grad).all() and float(x.grad.abs().sum()) > 0
+    gin.clear_config()
 
 
 def test_augment_per_image_order_row(K):

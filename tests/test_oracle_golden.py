@@ -138,3 +138,22 @@ def test_config1_two_full_steps_match_reference(golden_dir):
         assert abs(l_con - ref["l_con"]) < 1e-3 * abs(ref["l_con"])
         for key in ("l_dis", "l_gen", "d_grad_norm", "g_grad_norm"):
             assert abs(got[key] - ref[key]) < 1e-3 * abs(ref[key]), (key, got[key], ref[key])
+
+
+def test_oracle_augment_hq_matches_reference(golden_dir):
+    """simclr_hq / simclr_hq_cutout: the oracle's sampler + arithmetic reproduce the reference chain (forward 5e-6,
+    backward through autograd 1e-5)."""
+    fx = torch.load(os.path.join(golden_dir, "augment_hq.pt"), weights_only=False)
+    for c in fx["cases"]:
+        np.random.seed(c["seed"]); torch.manual_seed(c["seed"])
+        b, _, h, w = c["x"].shape
+        x = torch.rand(b, 3, h, w); _ = torch.randn(b, 3, h, w)
+        params, order = O.sample_simclr_params(b, h, w)
+        hq = O.sample_hq_params(b, h, w, cutout=c["mode"].endswith("cutout"))
+        assert torch.equal(x, c["x"]) and order == c["order"] and torch.equal(O.pack_params(params), c["params"])
+        assert hq["sigma"] == c["hq"]["sigma"] and torch.equal(hq["blur_on"], c["hq"]["blur_on"])
+        xr = x.clone().requires_grad_(True)
+        y = O.augment_simclr_hq(xr, params, order, hq, cutout_length=c["length"])
+        assert (y.detach() - c["y"]).abs().max() < 5e-6
+        (y * c["dy"]).sum().backward()
+        assert (xr.grad - c["dx"]).abs().max() < 1e-5 * max(1.0, float(c["dx"].abs().max()))
