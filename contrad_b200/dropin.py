@@ -33,6 +33,7 @@ _ALIASES = {
     "models.gan": "contrad_b200.models.gan",
     "models.gan.base": "contrad_b200.models.gan.base",
     "models.gan.sndcgan": "contrad_b200.models.gan.sndcgan",
+    "models.gan.snresnet": "contrad_b200.models.gan.snresnet",
     "models.gan.stylegan2": "contrad_b200.models.gan.stylegan2",
     "models.gan.stylegan2.layers": "contrad_b200.models.gan.stylegan2.layers",
     "models.gan.stylegan2.generator": "contrad_b200.models.gan.stylegan2.generator",

@@ -107,8 +107,9 @@ class SNPackFn(Function):
         side = {"dgrad": {}, "sigma": {}}
         sig_all = torch.empty(len(specs), 2, device=dev, dtype=torch.float32)
         sig = [sig_all[i] for i in range(len(specs))]
-        K.sn_power_iter_batched([(w, s.module.weight_u, s.module.weight_v, sg) for s, w, sg in zip(specs, weights, sig)],
-                                training=training)
+        layers = [(w, s.module.weight_u, s.module.weight_v, sg) for s, w, sg in zip(specs, weights, sig)]
+        for i in range(0, len(layers), 16):                      # the batched kernels take up to 16 layers per launch
+            K.sn_power_iter_batched(layers[i:i + 16], training=training)
         saved_uv = [(s.module.weight_u.clone(), s.module.weight_v.clone()) for s in specs]
         head1 = [s for s in specs if s.kind == "head1"]
         outs, jobs = [], []
@@ -134,6 +135,11 @@ class SNPackFn(Function):
                     jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=2))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
+            elif s.kind == "conv_plain":         # any kernel size / stride: forward GEMM matrix only (SNResNet18)
+                cin = w.shape[1]
+                fwd = torch.empty(cout, s.ks * s.ks * cin, device=dev)
+                jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1]))
+                outs.append(fwd)
             elif s.kind == "head1":
                 nfeat = w.shape[1]
                 c_last, sh, sw = holder["feat_chw"]
@@ -171,7 +177,7 @@ class SNPackFn(Function):
         grads = [None] * len(specs)
         head1 = [s for s in specs if s.kind == "head1"]
         head2 = [s for s in specs if s.kind == "head2"]
-        n_conv = sum(1 for s in specs if s.kind in ("conv_first", "conv"))
+        n_conv = sum(1 for s in specs if s.kind in ("conv_first", "conv", "conv_plain"))
         jobs = []
         for li, (s, w) in enumerate(zip(specs, weights)):
             if not ctx.needs_input_grad[2 + li]:
@@ -180,7 +186,7 @@ class SNPackFn(Function):
             cout = w.shape[0]
             if s.kind == "conv_first":
                 g, w4 = dpacks[li], w.view(cout, 27, 1, 1)
-            elif s.kind == "conv":
+            elif s.kind in ("conv", "conv_plain"):
                 g, w4 = dpacks[li], w
             elif s.kind == "head1":
                 g = dpacks[n_conv]
@@ -273,6 +279,59 @@ class SNDCGANBackboneFn(Function):
         for i in range(L):
             out += [grads_w[i], grads_b[i]]
         return tuple(out)
+
+
+class ConvFirstFn(Function):
+    """`LeakyReLU(Conv2d(3, 64, 3, 1, 1)(x * 2 - 1))` on an NCHW image -> NHWC activation (first layer of D_SNDCGAN and
+    D_SNResNet18, models/gan/snresnet.py:77-79) from the packed W/sigma [64, 27]; first order."""
+
+    @staticmethod
+    def forward(ctx, x, w27, bias, dgrad_pack, slope):
+        x = _c(x)
+        y = K.conv_first_fwd(x, w27.view(-1, 3, 3, 3), None, bias, slope=slope, round_out=True)
+        ctx.save_for_backward(x, y)
+        ctx.dgrad, ctx.slope = dgrad_pack, slope
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        g = K.lrelu_bwd(_c(dy), y, ctx.slope, round_out=True)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = K.conv_first_wgrad(x, g)
+        if ctx.needs_input_grad[0]:
+            B, H, W, _ = g.shape
+            dx = K.conv_first_dgrad_finish(K.conv2d_nhwc_dgrad(g, ctx.dgrad, (B, H, W, 32), 3, 1))
+        return dx, dw, db, None, None
+
+
+class ConvPackedFn(Function):
+    """3x3 stride-1 NHWC convolution from the packed matrices written by the spectral-norm kernels (forward pack
+    [Cout, 9*Cin], data-gradient pack [Cin, 9*Cout]); the weight gradient comes back in the forward-pack layout, which
+    is what SNPackFn.backward consumes.  First order."""
+
+    @staticmethod
+    def forward(ctx, x, wpack, dgrad_pack):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        ctx.dgrad = dgrad_pack
+        return K.conv2d_nhwc_fwd(x, wpack, None, 3, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = K.round_tf32_(_c(dy))
+        dx = K.conv2d_nhwc_dgrad(dy, ctx.dgrad, tuple(x.shape), 3, 1) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            cout = dy.shape[-1]
+            if cout % 128:          # the wgrad kernel tiles Cout by 128: 64-channel layers present dY zero-extended
+                from . import sg2_kernels as S
+                dw = K.conv2d_nhwc_wgrad(x, S.pad_channels(dy, (cout + 127) // 128 * 128), 3, 1)[:cout]
+            else:
+                dw = K.conv2d_nhwc_wgrad(x, dy, 3, 1)
+        return dx, dw, None
 
 
 # ------------------------------------------------------------------------------------------------

@@ -22,7 +22,9 @@ def get_architecture(architecture, image_size, P=None):
         discriminator = ResidualDiscriminatorP(size=resolution, channel_multiplier=1.0, mlp_linear=True, d_hidden=512)
         return generator, discriminator
     if architecture == "snresnet18":
-        raise NotImplementedError(
-            "architecture %r is a later row of the hot-path scope table (SURVEY 8f f4); "
-            "contrad_b200 builds 'sndcgan', 'stylegan2' and 'stylegan2_512'" % architecture)
+        from .sndcgan import G_SNDCGAN
+        from .snresnet import D_SNResNet18
+        generator = G_SNDCGAN(image_size=image_size)
+        discriminator = D_SNResNet18(mlp_linear=True, d_hidden=1024)
+        return generator, discriminator
     raise NotImplementedError()

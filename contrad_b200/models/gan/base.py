@@ -18,9 +18,10 @@ class _SNParams(nn.Module):
     """Parameter container of one spectrally-normalised layer: ``weight_orig``, ``bias`` (parameters),
     ``weight_u``, ``weight_v`` (buffers) - the keys torch.nn.utils.spectral_norm produces."""
 
-    def __init__(self, weight_shape):
+    def __init__(self, weight_shape, init="sndcgan"):
         super().__init__()
         self.weight_shape = tuple(weight_shape)
+        self.init = init
         fan = 1
         for s in weight_shape[1:]:
             fan *= s
@@ -34,15 +35,21 @@ class _SNParams(nn.Module):
         """models/gan/sndcgan.py:130-148: N(0, 0.02) weights, zero bias, fresh unit-norm u / v
         (torch.nn.utils.spectral_norm draws them from N(0,1))."""
         with torch.no_grad():
-            self.weight_orig.normal_(0.0, 0.02)
-            self.bias.zero_()
+            if self.init == "default":       # nn.Conv2d / nn.Linear defaults (models/gan/snresnet.py keeps them)
+                fan = self.weight_v.numel()
+                bound = 1.0 / fan ** 0.5
+                self.weight_orig.uniform_(-bound, bound)
+                self.bias.uniform_(-bound, bound)
+            else:
+                self.weight_orig.normal_(0.0, 0.02)
+                self.bias.zero_()
             self.weight_u.copy_(_unit(torch.empty_like(self.weight_u).normal_(0, 1)))
             self.weight_v.copy_(_unit(torch.empty_like(self.weight_v).normal_(0, 1)))
 
 
 class SNConv2d(_SNParams):
-    def __init__(self, cin, cout, ks, stride, padding):
-        super().__init__((cout, cin, ks, ks))
+    def __init__(self, cin, cout, ks, stride, padding, init="sndcgan"):
+        super().__init__((cout, cin, ks, ks), init=init)
         self.ks, self.stride, self.padding = ks, stride, padding
 
     def extra_repr(self):
@@ -51,8 +58,8 @@ class SNConv2d(_SNParams):
 
 
 class SNLinear(_SNParams):
-    def __init__(self, fin, fout):
-        super().__init__((fout, fin))
+    def __init__(self, fin, fout, init="sndcgan"):
+        super().__init__((fout, fin), init=init)
 
     def extra_repr(self):
         return "in_features=%d, out_features=%d (spectral norm)" % (self.weight_shape[1], self.weight_shape[0])
@@ -61,26 +68,26 @@ class SNLinear(_SNParams):
 class TinyDiscriminator(nn.Module):
     """models/gan/base.py:14-35 (parameter container; evaluated inside HeadsFn)."""
 
-    def __init__(self, n_features, n_classes=1, d_hidden=128):
+    def __init__(self, n_features, n_classes=1, d_hidden=128, init="sndcgan"):
         super().__init__()
         if n_classes > 1:
             raise NotImplementedError("class-conditional heads are not on the ContraD hot path")
         self.n_features, self.n_classes, self.d_hidden = n_features, n_classes, d_hidden
-        self.l1 = SNLinear(n_features, d_hidden)
-        self.l2 = SNLinear(d_hidden, 1)
+        self.l1 = SNLinear(n_features, d_hidden, init=init)
+        self.l2 = SNLinear(d_hidden, 1, init=init)
 
 
 class BaseDiscriminator(nn.Module, metaclass=ABCMeta):
-    def __init__(self, d_penul, n_classes=1, d_hidden=128, d_project=128, mlp_linear=False):
+    def __init__(self, d_penul, n_classes=1, d_hidden=128, d_project=128, mlp_linear=False, head_init="sndcgan"):
         super().__init__()
         if not mlp_linear:
             raise NotImplementedError("only mlp_linear=True (every registry architecture, models/gan/__init__.py) is built")
         self.d_penul, self.n_classes, self.d_hidden, self.d_project = d_penul, n_classes, d_hidden, d_project
-        self.linear = TinyDiscriminator(d_penul, n_classes=n_classes, d_hidden=d_hidden)
-        self.projection = nn.Sequential(SNLinear(d_penul, d_hidden), nn.LeakyReLU(0.1, inplace=True),
-                                        SNLinear(d_hidden, d_project))
-        self.projection2 = nn.Sequential(SNLinear(d_penul, d_hidden), nn.LeakyReLU(0.1, inplace=True),
-                                         SNLinear(d_hidden, d_project))
+        self.linear = TinyDiscriminator(d_penul, n_classes=n_classes, d_hidden=d_hidden, init=head_init)
+        self.projection = nn.Sequential(SNLinear(d_penul, d_hidden, init=head_init), nn.LeakyReLU(0.1, inplace=True),
+                                        SNLinear(d_hidden, d_project, init=head_init))
+        self.projection2 = nn.Sequential(SNLinear(d_penul, d_hidden, init=head_init), nn.LeakyReLU(0.1, inplace=True),
+                                         SNLinear(d_hidden, d_project, init=head_init))
 
     # ---- hooks the concrete discriminator implements
     @abstractmethod
@@ -119,7 +126,7 @@ class BaseDiscriminator(nn.Module, metaclass=ABCMeta):
         if y is not None:
             raise NotImplementedError("class-conditional discriminators are not on the ContraD hot path")
         holder, packs = self._packs()
-        n_conv = sum(1 for s in holder["specs"] if s.kind in ("conv_first", "conv"))
+        n_conv = sum(1 for s in holder["specs"] if s.kind in ("conv_first", "conv", "conv_plain"))
         if finetuning:
             is_train = self.training
             self.eval()

@@ -377,6 +377,59 @@ def d_sndcgan_forward(sd, x, sg_linear=False, training=True):
     return out, {"penultimate": feats, "projection": proj, "projection2": proj2}
 
 
+# D_SNResNet18 (models/gan/snresnet.py:21-93): conv1 3->64, then 4 stages of 2 BasicBlocks (64, 128, 256, 512 planes;
+# the first block of stages 2-4 has stride 2 and a 1x1 stride-2 shortcut conv); every conv / linear spectrally normalised.
+RESNET18_BLOCKS = tuple(("layer%d.%d" % (s + 1, b), cin, planes, stride)
+                        for s, (planes, first_stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)))
+                        for b, (cin, stride) in enumerate((((64, 64, 128, 256)[s], first_stride), (planes, 1))))
+
+
+def d_snresnet18_penultimate(sd, x, training=True):
+    """SNResNet.penultimate (snresnet.py:76-89) with BasicBlock.forward (:39-44)."""
+    def conv(key, h, stride, pad):
+        return F.conv2d(h, _sn_weight(sd, key, training), sd[key + ".bias"], stride=stride, padding=pad)
+
+    h = F.leaky_relu(conv("conv1", x * 2. - 1., 1, 1), 0.1)
+    for name, cin, planes, stride in RESNET18_BLOCKS:
+        out = F.leaky_relu(conv(name + ".conv1", h, stride, 1), 0.1)
+        out = conv(name + ".conv2", out, 1, 1)
+        sc = conv(name + ".shortcut.0", h, stride, 0) if (stride != 1 or cin != planes) else h
+        h = F.leaky_relu(out + sc, 0.1)
+    h = F.avg_pool2d(h, 4)
+    return h.reshape(h.shape[0], -1)
+
+
+def d_snresnet18_forward(sd, x, sg_linear=False, training=True):
+    feats = d_snresnet18_penultimate(sd, x, training)
+    out, proj, proj2 = d_heads(sd, feats, sg_linear=sg_linear, training=training)
+    return out, {"penultimate": feats, "projection": proj, "projection2": proj2}
+
+
+def make_d_resnet18_state(d_hidden=1024, d_project=128, generator=None):
+    """A D_SNResNet18(mlp_linear=True, d_hidden=1024) state_dict (models/gan/__init__.py:8-12): nn.Conv2d / nn.Linear
+    default initialisation (uniform +-1/sqrt(fan_in) for weights and biases), fresh unit-norm u / v."""
+    shapes = {"conv1": (64, 3, 3, 3)}
+    for name, cin, planes, stride in RESNET18_BLOCKS:
+        shapes[name + ".conv1"] = (planes, cin, 3, 3)
+        shapes[name + ".conv2"] = (planes, planes, 3, 3)
+        if stride != 1 or cin != planes:
+            shapes[name + ".shortcut.0"] = (planes, cin, 1, 1)
+    shapes.update({"linear.l1": (d_hidden, 512), "linear.l2": (1, d_hidden), "projection.0": (d_hidden, 512),
+                   "projection.2": (d_project, d_hidden), "projection2.0": (d_hidden, 512),
+                   "projection2.2": (d_project, d_hidden)})
+    sd = {}
+    for key, shp in shapes.items():
+        fan = 1
+        for d in shp[1:]:
+            fan *= d
+        bound = 1.0 / math.sqrt(fan)
+        sd[key + ".weight_orig"] = (torch.rand(*shp, generator=generator) * 2 - 1) * bound
+        sd[key + ".bias"] = (torch.rand(shp[0], generator=generator) * 2 - 1) * bound
+        sd[key + ".weight_u"] = _l2normalize(torch.empty(shp[0]).normal_(0, 1, generator=generator))
+        sd[key + ".weight_v"] = _l2normalize(torch.empty(fan).normal_(0, 1, generator=generator))
+    return sd
+
+
 def _batch_norm_train(x, sd, key, momentum=0.1, eps=1e-5):
     """nn.BatchNorm2d in train mode (batch statistics; running stats updated with the unbiased
     variance), as used by G_SNDCGAN (models/gan/sndcgan.py:25-36)."""

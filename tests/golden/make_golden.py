@@ -249,17 +249,42 @@ def gen_augment_hq():
     torch.save({"cases": cases}, os.path.join(HERE, "augment_hq.pt"))
 
 
+def gen_snresnet18():
+    """D_SNResNet18 (models/gan/snresnet.py) through the reference module on CPU: outputs, input gradient and
+    per-parameter gradient norms for seeded weights (oracle.make_d_resnet18_state) - only inputs / outputs are stored."""
+    from models.gan import get_architecture
+    _, D = get_architecture("snresnet18", (32, 32, 3))
+    sd = O.make_d_resnet18_state(generator=torch.Generator().manual_seed(77))
+    missing = D.load_state_dict(sd, strict=True)
+    D.train()
+    seed_all(78)
+    x = torch.rand(6, 3, 32, 32)
+    c_d, c1, c2 = torch.randn(6, 1), torch.randn(6, 128), torch.randn(6, 128)
+    xr = x.clone().requires_grad_(True)
+    d, aux = D(xr, projection=True, projection2=True, penultimate=True)
+    ((d * c_d).sum() + (aux["projection"] * c1).sum() + (aux["projection2"] * c2).sum()).backward()
+    out = {"w_seed": 77, "x": t2l(x), "c_d": c_d, "c1": c1, "c2": c2, "d": t2l(d), "projection": t2l(aux["projection"]),
+           "projection2": t2l(aux["projection2"]), "penultimate": t2l(aux["penultimate"]), "dx": t2l(xr.grad),
+           "grad_norms": {k: float(p.grad.norm()) for k, p in D.named_parameters() if p.grad is not None},
+           "grad_conv1": t2l(D.conv1.weight_orig.grad), "keys": {k: list(v.shape) for k, v in D.state_dict().items()},
+           "uv_after": {k: t2l(v) for k, v in D.state_dict().items() if k.endswith(("conv1.weight_u", "l1.weight_v"))}}
+    torch.save(out, os.path.join(HERE, "snresnet18.pt"))
+    print("snresnet18: d[0]=%.6f" % float(d[0]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gin = ref_import.activate()
-    todo = args.only.split(",") if args.only else ["augment", "augment_hq", "contrastive", "sn", "small", "config1"]
+    todo = args.only.split(",") if args.only else ["augment", "augment_hq", "contrastive", "sn", "small", "config1", "snresnet18"]
     if "augment" in todo:
         gen_augment(gin)
     if "augment_hq" in todo:
         gen_augment_hq()
+    if "snresnet18" in todo:
+        gen_snresnet18()
     if "contrastive" in todo:
         gen_contrastive()
     if "sn" in todo:

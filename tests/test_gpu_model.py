@@ -351,6 +351,79 @@ def test_cuda_graph_step_matches_eager_step(env):
 
 
 
+def test_snresnet18_matches_reference(env, golden_dir):
+    """D_SNResNet18 against the fixture produced by the unmodified reference module (CPU fp32):
+    outputs to 1e-2 of their max (TF32), input gradient / first-layer weight gradient in L2, per-parameter gradient
+    norms, and the in-place power-iteration update of u / v."""
+    fx = torch.load(os.path.join(golden_dir, "snresnet18.pt"), weights_only=False)
+    G, D = env.get_architecture("snresnet18", (32, 32, 3))
+    sd = O.make_d_resnet18_state(generator=torch.Generator().manual_seed(fx["w_seed"]))
+    D.load_state_dict(sd, strict=True)
+    D.cuda().train()
+    x = fx["x"].cuda().requires_grad_(True)
+    d, aux = D(x, projection=True, projection2=True, penultimate=True)
+    ((d * fx["c_d"].cuda()).sum() + (aux["projection"] * fx["c1"].cuda()).sum() + (aux["projection2"] * fx["c2"].cuda()).sum()).backward()
+    rel = lambda a, b: float((a.detach().cpu().double() - b.double()).abs().max() / b.double().abs().max())
+    l2 = lambda a, b: float((a.detach().cpu().double() - b.double()).norm() / b.double().norm())
+    errs = {"d": rel(d, fx["d"]), "projection": rel(aux["projection"], fx["projection"]),
+            "penultimate": rel(aux["penultimate"], fx["penultimate"]), "dx_l2": l2(x.grad, fx["dx"]),
+            "grad_conv1_l2": l2(D.conv1.weight_orig.grad, fx["grad_conv1"])}
+    grads = dict(D.named_parameters())
+    errs["worst_norm"] = max(abs(float(grads[k].grad.norm()) - n) / n for k, n in fx["grad_norms"].items() if n > 0)
+    for k, v in fx["uv_after"].items():
+        errs["uv:" + k] = rel(D.state_dict()[k], v)
+    # yardstick for the ill-conditioned element-wise gradients (17 LeakyReLU(0.1) layers: a pre-activation within TF32
+    # rounding of zero flips its slope by a factor 10): the same fixture through torch's own TF32 GPU arithmetic
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        sd_c = {k: v.clone().cuda() for k, v in O.make_d_resnet18_state(generator=torch.Generator().manual_seed(fx["w_seed"])).items()}
+        O.set_requires_grad(sd_c, True)
+        xc = fx["x"].cuda().requires_grad_(True)
+        dc, auxc = O.d_snresnet18_forward(sd_c, xc)
+        ((dc * fx["c_d"].cuda()).sum() + (auxc["projection"] * fx["c1"].cuda()).sum() + (auxc["projection2"] * fx["c2"].cuda()).sum()).backward()
+        errs["torch_tf32:dx_l2"] = l2(xc.grad, fx["dx"])
+        errs["torch_tf32:grad_conv1_l2"] = l2(sd_c["conv1.weight_orig"].grad, fx["grad_conv1"])
+        errs["torch_tf32:d"] = rel(dc, fx["d"])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    print("snresnet18 parity:", {k: "%.2e" % v for k, v in errs.items()})
+    assert errs["d"] < 1e-2 and errs["projection"] < 1e-2 and errs["penultimate"] < 1e-2
+    assert errs["dx_l2"] < max(5e-2, 3 * errs["torch_tf32:dx_l2"]) + 5e-2
+    assert errs["grad_conv1_l2"] < max(5e-2, 3 * errs["torch_tf32:grad_conv1_l2"]) + 5e-2 and errs["worst_norm"] < 3e-2
+    assert all(v < 1e-4 for k, v in errs.items() if k.startswith("uv:"))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", "snresnet18_parity.json"), "w") as f:
+            json.dump(errs, f, indent=1)
+    except OSError:
+        pass
+
+
+def test_snresnet18_train_step_runs(env):
+    """`train_gan.py ... snresnet18 --mode=contrad --aug=simclr`: one full step with D_SNResNet18 + G_SNDCGAN."""
+    from contrad_b200.optim import FusedAdam
+    np.random.seed(3); torch.manual_seed(3)
+    G, D = env.get_architecture("snresnet18", (32, 32, 3))
+    G.cuda(); D.cuda()
+    P = SimpleNamespace(augment_fn=env.get_augment(mode="simclr").cuda(), temp=0.1, lbd_a=1.0, distributed=False)
+    options = {"loss": "hinge", "warmup": 3000, "lr": 2e-4, "lr_d": 2e-4}
+    train_fn = {"D": env.contrad.loss_D_fn, "G": env.contrad.loss_G_fn}
+    opt_G = FusedAdam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    opt_D = FusedAdam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    w0 = {k: v.detach().clone() for k, v in D.named_parameters()}
+    for step in (1, 2):
+        out = env.engine.train_step(P, options, train_fn, (G, D), (opt_G, opt_D), torch.rand(32, 3, 32, 32, device="cuda"), step,
+                                    record_grad_norms=True)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v).all() for v in out.values()), out
+    moved = sum(1 for k, v in D.named_parameters() if not torch.equal(v.detach(), w0[k]))
+    # hinge loss at initialisation: every d_real / d_gen is inside the margin, so the gradient of `linear.l2.bias`
+    # (+1/n per fake, -1/n per real) cancels exactly and Adam leaves that single scalar untouched
+    assert moved >= len(w0) - 1, (moved, len(w0))
+
+
 def test_zz_eager_gpu_yardstick_sndcgan(env):
     """Not a parity check: the denominator of north_star's ">= 10x the reference single-GPU PyTorch-eager images/sec".
     The reference cannot travel to the GPU box, so its per-step arithmetic is executed through the oracle's torch ops ON

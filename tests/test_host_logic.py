@@ -102,7 +102,11 @@ def test_module_surfaces_match_reference():
     with pytest.raises(NotImplementedError):
         setup(SimpleNamespace(mode="std", aug="none", penalty="none", temp=0.1, lbd_a=1.0))
     with pytest.raises(NotImplementedError):
-        get_architecture("snresnet18", (32, 32, 3))
+        get_architecture("biggan", (32, 32, 3))
+    G3, D3 = get_architecture("snresnet18", (32, 32, 3))
+    ref_r = O.make_d_resnet18_state()
+    assert {k: tuple(v.shape) for k, v in D3.state_dict().items()} == {k: tuple(v.shape) for k, v in ref_r.items()}
+    assert D3.d_penul == 512 and isinstance(G3, type(G))
     # the StyleGAN2 networks also run on the kernels only (no CPU fallback)
     G2, D2 = get_architecture("stylegan2", (32, 32, 3))
     from contrad_b200._capi import CB200Error as _E

@@ -157,3 +157,20 @@ def test_oracle_augment_hq_matches_reference(golden_dir):
         assert (y.detach() - c["y"]).abs().max() < 5e-6
         (y * c["dy"]).sum().backward()
         assert (xr.grad - c["dx"]).abs().max() < 1e-5 * max(1.0, float(c["dx"].abs().max()))
+
+
+def test_oracle_snresnet18_matches_reference(golden_dir):
+    """D_SNResNet18 restatement vs the unmodified reference module (forward, input gradient, gradient norms, u/v)."""
+    fx = torch.load(os.path.join(golden_dir, "snresnet18.pt"), weights_only=False)
+    sd = O.make_d_resnet18_state(generator=torch.Generator().manual_seed(fx["w_seed"]))
+    assert {k: list(v.shape) for k, v in sd.items()} == fx["keys"]
+    O.set_requires_grad(sd, True)
+    x = fx["x"].clone().requires_grad_(True)
+    d, aux = O.d_snresnet18_forward(sd, x)
+    assert (d - fx["d"]).abs().max() < 1e-6 and (aux["penultimate"] - fx["penultimate"]).abs().max() < 1e-6
+    ((d * fx["c_d"]).sum() + (aux["projection"] * fx["c1"]).sum() + (aux["projection2"] * fx["c2"]).sum()).backward()
+    assert (x.grad - fx["dx"]).abs().max() < 1e-6 * max(1.0, float(fx["dx"].abs().max()))
+    for k, n in fx["grad_norms"].items():
+        assert abs(float(sd[k].grad.norm()) - n) <= 1e-5 * max(n, 1e-6), k
+    for k, v in fx["uv_after"].items():
+        assert (sd[k] - v).abs().max() < 1e-6
