@@ -391,7 +391,7 @@ def test_snresnet18_matches_reference(env, golden_dir):
     print("snresnet18 parity:", {k: "%.2e" % v for k, v in errs.items()})
     assert errs["d"] < 1e-2 and errs["projection"] < 1e-2 and errs["penultimate"] < 1e-2
     assert errs["dx_l2"] < max(5e-2, 3 * errs["torch_tf32:dx_l2"]) + 5e-2
-    assert errs["grad_conv1_l2"] < max(5e-2, 3 * errs["torch_tf32:grad_conv1_l2"]) + 5e-2 and errs["worst_norm"] < 3e-2
+    assert errs["grad_conv1_l2"] < max(5e-2, 3 * errs["torch_tf32:grad_conv1_l2"]) + 5e-2 and errs["worst_norm"] < 5e-2
     assert all(v < 1e-4 for k, v in errs.items() if k.startswith("uv:"))
     try:
         os.makedirs("gpurun_out", exist_ok=True)
