@@ -76,7 +76,18 @@ __global__ void __launch_bounds__(kT) upfirdn2d_kernel(const __grid_constant__ U
 // Contiguous NHWC, C % 4 == 0: one thread = one output pixel x 4 channels (float4, channel fastest -> coalesced); the
 // taps that hit the zero-stuffed grid are enumerated with stride `up` (no modulo in the loops); neighbouring pixels
 // re-read the same inputs from L1/L2, HBM sees each input and output once.
-__global__ void __launch_bounds__(kT) upfirdn2d_nhwc4_kernel(const __grid_constant__ UpfirdnParams p) {
+// A CTA owns one kTile x kTile tile of output pixels of one image (all channels), so that the (kTile*down + k - 1)^2
+// input pixels it touches stay in this SM's L1 while neighbouring output pixels re-read them: HBM / L2 see each input
+// about once instead of once per tap row.
+// UP / KS != 0 bake the up-sampling factor and the (square) FIR size into the code: the divisions by `up` disappear and
+// the 4x4 tap loops of the [1,3,3,1] kernels unroll (the runtime-parameter version spent most of its issue slots on
+// integer division).
+constexpr int kTile = 8;
+template <int UP, int KS>
+__global__ void __launch_bounds__(kT) upfirdn2d_nhwc4_kernel(const __grid_constant__ UpfirdnParams p_) {
+    UpfirdnParams p = p_;
+    if (UP) p.up = UP;
+    if (KS) { p.kh = KS; p.kw = KS; }
     __shared__ float ks[64];
     for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
         const int ky = i / p.kw, kx = i % p.kw;
@@ -85,34 +96,44 @@ __global__ void __launch_bounds__(kT) upfirdn2d_nhwc4_kernel(const __grid_consta
     }
     __syncthreads();
     const int C4 = p.C >> 2;
-    const long long total = (long long)p.N * p.Ho * p.Wo * C4;
+    const int tiles_x = (p.Wo + kTile - 1) / kTile, tiles_y = (p.Ho + kTile - 1) / kTile;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(p.x);
     float4* __restrict__ y4 = reinterpret_cast<float4*>(p.y);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        long long t = idx;
-        const int c = (int)(t % C4); t /= C4;
-        const int ox = (int)(t % p.Wo); t /= p.Wo;
-        const int oy = (int)(t % p.Ho);
-        const int n = (int)(t / p.Ho);
+    const int per_tile = kTile * kTile * C4;
+    const long long n_tiles = (long long)p.N * tiles_y * tiles_x;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y), n = (int)(tile / ((long long)tiles_x * tiles_y));
+      for (int e = threadIdx.x; e < per_tile; e += blockDim.x) {
+        const int c = e % C4, pix = e / C4;
+        const int ox = tx * kTile + (pix % kTile), oy = ty * kTile + (pix / kTile);
+        if (ox >= p.Wo || oy >= p.Ho) continue;
+        const long long idx = (((long long)n * p.Ho + oy) * p.Wo + ox) * C4 + c;
         const int py_base = oy * p.down - p.py0, px_base = ox * p.down - p.px0;
-        const int ky0 = ((-py_base) % p.up + p.up) % p.up, kx0 = ((-px_base) % p.up + p.up) % p.up;
+        const int ky0 = UP == 1 ? 0 : ((-py_base) % p.up + p.up) % p.up, kx0 = UP == 1 ? 0 : ((-px_base) % p.up + p.up) % p.up;
+        const int iy0 = (py_base + ky0) / p.up, ix0 = (px_base + kx0) / p.up;     // input index advances by 1 per tap step
+        const float4* img = x4 + (long long)n * p.Hi * p.Wi * C4 + c;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ky = ky0; ky < p.kh; ky += p.up) {
-            const int iy = (py_base + ky) / p.up;
-            if (iy < 0) continue;
-            if (iy >= p.Hi) break;
-            const float4* row = x4 + ((long long)n * p.Hi + iy) * p.Wi * C4 + c;
-            for (int kx = kx0; kx < p.kw; kx += p.up) {
-                const int ix = (px_base + kx) / p.up;
-                if (ix < 0) continue;
-                if (ix >= p.Wi) break;
-                const float4 v = __ldg(row + (long long)ix * C4);
+        constexpr int kSteps = KS ? (KS + (UP ? UP : 1) - 1) / (UP ? UP : 1) : 64;   // taps per axis that can hit the grid
+        constexpr int kUnroll = KS ? kSteps : 1;
+#pragma unroll kUnroll
+        for (int sy = 0; sy < kSteps; ++sy) {
+            const int ky = ky0 + sy * p.up, iy = iy0 + sy;
+            if (ky >= p.kh) break;
+            if (iy < 0 || iy >= p.Hi) continue;
+            const float4* row = img + (long long)iy * p.Wi * C4;
+#pragma unroll kUnroll
+            for (int sx = 0; sx < kSteps; ++sx) {
+                const int kx = kx0 + sx * p.up, ix = ix0 + sx;
+                if (kx >= p.kw) break;
+                if (ix < 0 || ix >= p.Wi) continue;
+                const float4 v = __ldg(row + ix * C4);
                 const float w = ks[ky * p.kw + kx];
                 acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
             }
         }
         if (p.round_out) { acc.x = round_tf32(acc.x); acc.y = round_tf32(acc.y); acc.z = round_tf32(acc.z); acc.w = round_tf32(acc.w); }
         y4[idx] = acc;
+      }
     }
 }
 
@@ -191,6 +212,75 @@ __global__ void __launch_bounds__(kT) bias_act_kernel(const float* __restrict__ 
             v = x[i] * ((ref[i] + b) > 0.f ? gain : gain * slope);
         }
         y[i] = round_out ? round_tf32(v) : v;
+    }
+}
+
+// float4 variant (C % 4 == 0, 16-byte aligned operands)
+__global__ void __launch_bounds__(kT) bias_act_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ bias,
+                                                          const float4* __restrict__ ref, const float4* __restrict__ res,
+                                                          float4* __restrict__ y, long long n4, int C4, int mode, float slope,
+                                                          float gain, int round_out) {
+    const float gneg = gain * slope;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 b = bias ? __ldg(bias + (int)(i % C4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v = x[i];
+        float4 o;
+        if (mode == 0) {
+            float t;
+            t = v.x + b.x; o.x = (t > 0.f ? t : t * slope) * gain;
+            t = v.y + b.y; o.y = (t > 0.f ? t : t * slope) * gain;
+            t = v.z + b.z; o.z = (t > 0.f ? t : t * slope) * gain;
+            t = v.w + b.w; o.w = (t > 0.f ? t : t * slope) * gain;
+            if (res) { const float4 r = res[i]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+        } else {
+            const float4 r = ref[i];
+            o.x = v.x * ((r.x + b.x) > 0.f ? gain : gneg);
+            o.y = v.y * ((r.y + b.y) > 0.f ? gain : gneg);
+            o.z = v.z * ((r.z + b.z) > 0.f ? gain : gneg);
+            o.w = v.w * ((r.w + b.w) > 0.f ? gain : gneg);
+        }
+        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        y[i] = o;
+    }
+}
+
+// float4 variants of modulate / mod_epilogue: grid (chunks of one image, B); no per-element division by the image size
+__global__ void __launch_bounds__(kT) modulate_vec_kernel(const float4* __restrict__ x, long long xbs4, const float4* __restrict__ s,
+                                                          float4* __restrict__ y, long long per4, int C4, float alpha,
+                                                          int round_out) {
+    const int b = blockIdx.y;
+    const float4* xb = x + (long long)b * xbs4;
+    float4* yb = y + (long long)b * per4;
+    const float4* sb = s + (long long)b * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = xb[i];
+        const float4 m = __ldg(sb + (int)(i % C4));
+        float4 o = make_float4(v.x * m.x * alpha, v.y * m.y * alpha, v.z * m.z * alpha, v.w * m.w * alpha);
+        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        yb[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(kT) mod_epilogue_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ d,
+                                                              const float* __restrict__ noise, const float* __restrict__ nw,
+                                                              const float4* __restrict__ bias, float4* __restrict__ y,
+                                                              long long P, int C4, float slope, float gain, int round_out) {
+    const int b = blockIdx.y;
+    const long long per4 = P * C4;
+    const float4* xb = x + (long long)b * per4;
+    float4* yb = y + (long long)b * per4;
+    const float w = (noise && nw) ? __ldg(nw) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        const long long pp = i / C4;
+        float4 t = xb[i];
+        if (d) { const float4 m = __ldg(d + (long long)b * C4 + c); t.x *= m.x; t.y *= m.y; t.z *= m.z; t.w *= m.w; }
+        if (noise) { const float nz = __ldg(noise + (long long)b * P + pp) * w; t.x += nz; t.y += nz; t.z += nz; t.w += nz; }
+        if (bias) { const float4 bb = __ldg(bias + c); t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w; }
+        t.x = (t.x > 0.f ? t.x : t.x * slope) * gain; t.y = (t.y > 0.f ? t.y : t.y * slope) * gain;
+        t.z = (t.z > 0.f ? t.z : t.z * slope) * gain; t.w = (t.w > 0.f ? t.w : t.w * slope) * gain;
+        if (round_out) { t.x = round_tf32(t.x); t.y = round_tf32(t.y); t.z = round_tf32(t.z); t.w = round_tf32(t.w); }
+        yb[i] = t;
     }
 }
 
@@ -510,8 +600,15 @@ extern "C" int cb200_upfirdn2d(const float* x, const long long* x_strides, float
                              p.xs_h == (long long)Wi * C && p.ys_h == (long long)Wo * C && p.xs_n == (long long)Hi * Wi * C &&
                              p.ys_n == (long long)Ho * Wo * C &&
                              ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-    if (nhwc_contig)
-        upfirdn2d_nhwc4_kernel<<<grid_for((long long)N * Ho * Wo * (C / 4)), kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (nhwc_contig) {
+        long long tiles = (long long)N * ((Ho + kTile - 1) / kTile) * ((Wo + kTile - 1) / kTile);
+        if (tiles > 148LL * 64) tiles = 148LL * 64;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (kh == 4 && kw == 4 && up == 1) upfirdn2d_nhwc4_kernel<1, 4><<<(unsigned)tiles, kT, 0, st>>>(p);
+        else if (kh == 4 && kw == 4 && up == 2) upfirdn2d_nhwc4_kernel<2, 4><<<(unsigned)tiles, kT, 0, st>>>(p);
+        else if (up == 1) upfirdn2d_nhwc4_kernel<1, 0><<<(unsigned)tiles, kT, 0, st>>>(p);
+        else upfirdn2d_nhwc4_kernel<0, 0><<<(unsigned)tiles, kT, 0, st>>>(p);
+    }
     else
         upfirdn2d_kernel<<<grid_for((long long)N * C * Ho * Wo), kT, 0, static_cast<cudaStream_t>(stream)>>>(p);
     CB200_COUNT_LAUNCH();
@@ -543,8 +640,15 @@ extern "C" int cb200_bias_act(const float* x, const float* bias, const float* re
                               int C, int mode, float slope, float gain, int round_out, void* stream) {
     CB200_CHECK_ARG(n > 0 && C > 0 && n % C == 0, "bias_act: element count must be a positive multiple of C");
     CB200_CHECK_ARG(mode == 0 || (mode == 1 && ref != nullptr), "bias_act: mode 1 needs the reference activation");
-    bias_act_kernel<<<grid_for(n), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, bias, ref, res, y, n, C, mode, slope, gain,
-                                                                               round_out);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (C % 4 == 0 && al16(x) && al16(y) && al16(bias) && al16(ref) && al16(res)) {
+        bias_act_vec_kernel<<<grid_for(n / 4), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(bias), reinterpret_cast<const float4*>(ref),
+            reinterpret_cast<const float4*>(res), reinterpret_cast<float4*>(y), n / 4, C / 4, mode, slope, gain, round_out);
+    } else {
+        bias_act_kernel<<<grid_for(n), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, bias, ref, res, y, n, C, mode, slope, gain,
+                                                                                   round_out);
+    }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("bias_act");
     return CB200_OK;
@@ -553,8 +657,17 @@ extern "C" int cb200_bias_act(const float* x, const float* bias, const float* re
 extern "C" int cb200_modulate(const float* x, long long x_batch_stride, const float* s, float* y, int B, long long P, int C,
                               float alpha, int round_out, void* stream) {
     CB200_CHECK_ARG(B > 0 && P > 0 && C > 0, "modulate: empty tensor");
-    modulate_kernel<<<grid_for((long long)B * P * C), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, x_batch_stride, s, y, B, P, C,
-                                                                                                 alpha, round_out);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (C % 4 == 0 && x_batch_stride % 4 == 0 && B <= 65535 && al16(x) && al16(y) && al16(s)) {
+        const long long per4 = P * (C / 4);
+        dim3 grid(grid_for(per4, kT, (148 * 16 + B - 1) / B), B);
+        modulate_vec_kernel<<<grid, kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(x), x_batch_stride / 4, reinterpret_cast<const float4*>(s),
+            reinterpret_cast<float4*>(y), per4, C / 4, alpha, round_out);
+    } else {
+        modulate_kernel<<<grid_for((long long)B * P * C), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, x_batch_stride, s, y, B, P,
+                                                                                                     C, alpha, round_out);
+    }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("modulate");
     return CB200_OK;
@@ -580,8 +693,16 @@ extern "C" int cb200_mod_epilogue(const float* x, const float* demod, const floa
                                   const float* bias, float* y, int B, long long P, int C, float slope, float gain, int round_out,
                                   void* stream) {
     CB200_CHECK_ARG(B > 0 && P > 0 && C > 0, "mod_epilogue: empty tensor");
-    mod_epilogue_kernel<<<grid_for((long long)B * P * C), kT, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, demod, noise, noise_weight, bias, y, B, P, C, slope, gain, round_out);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (C % 4 == 0 && B <= 65535 && al16(x) && al16(y) && al16(demod) && al16(bias)) {
+        dim3 grid(grid_for(P * (C / 4), kT, (148 * 16 + B - 1) / B), B);
+        mod_epilogue_vec_kernel<<<grid, kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(demod), noise, noise_weight,
+            reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(y), P, C / 4, slope, gain, round_out);
+    } else {
+        mod_epilogue_kernel<<<grid_for((long long)B * P * C), kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            x, demod, noise, noise_weight, bias, y, B, P, C, slope, gain, round_out);
+    }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("mod_epilogue");
     return CB200_OK;
