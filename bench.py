@@ -345,6 +345,7 @@ def run_native(args):
         peaks = load_peaks()
         roof = roofline_legs(K, engine, W, eager_step, pool, peaks) if world == 1 else None
         cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
+        side = side_workloads() if world == 1 and not args.no_side_workloads else None
         line = {
             "metric": "train_step_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -363,6 +364,8 @@ def run_native(args):
             line.update(roof)
         if cpu:
             line["cpu_baseline"] = cpu
+        if side:
+            line["other_workloads"] = side
     if line is not None:
         print(json.dumps(line), flush=True)
     _log("teardown")
@@ -375,6 +378,20 @@ def run_native(args):
         dist.destroy_process_group()
     _log("done")
     return 0
+
+
+def side_workloads():
+    """Not part of the headline metric: BASELINE config 4 (StyleGAN2 small32 + ContraD, c10_style64.gin: b64, R1 every
+    step) through engine.GraphedStyleGAN2Step on the same GPU, so that the StyleGAN2 rows of the hot path (SURVEY 8a
+    a18-a22) carry a measured images/s in the same artefact.  Failures are reported, never raised."""
+    try:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import bench_sg2
+        res = bench_sg2.measure(batch=64, steps=12, warmup=3, d_reg_every=1, graph=True)
+        res.pop("losses", None)
+        return {"stylegan2_config4": res}
+    except Exception as e:                                    # noqa: BLE001
+        return {"stylegan2_config4": {"error": "%s: %s" % (type(e).__name__, e)}}
 
 
 def roofline_legs(K, engine, W, one_step, pool, peaks):
@@ -480,6 +497,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-workloads", action="store_true", help="skip the StyleGAN2 config-4 side measurement")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (and DDP wrappers for N > 1) instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.impl == "reference":

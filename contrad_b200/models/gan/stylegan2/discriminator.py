@@ -49,12 +49,6 @@ class TinyDiscriminator(nn.Module):
         self.l2 = nn.Linear(d_hidden, 1)
 
 
-def _pad_rows(w, b, rows):
-    if w.shape[0] == rows:
-        return w, b
-    return (torch.nn.functional.pad(w, (0, 0, 0, rows - w.shape[0])), torch.nn.functional.pad(b, (0, rows - b.shape[0])))
-
-
 class ResidualDiscriminatorP(nn.Module):
     """discriminator.py:191-235 + models/gan/base.py:79-150."""
 
@@ -107,13 +101,22 @@ class ResidualDiscriminatorP(nn.Module):
 
     # ---- heads
     def _hwc_weight(self, w):
+        """first-layer head weight with its columns re-ordered from (c,h,w) to (h,w,c); once per optimiser step"""
         c, h, ww = self._feat_chw
-        return w.view(w.shape[0], c, h, ww).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+        n = w.shape[0]
+        return SF.weight_memo(w, "hwc", lambda: SF.LinearMap.apply(
+            w, lambda t: t.view(n, c, h, ww).permute(0, 2, 3, 1).reshape(n, -1),
+            lambda g: g.reshape(n, h, ww, c).permute(0, 3, 1, 2).reshape(n, -1)))
 
     def _mlp(self, feat, l1, l2):
         hid = SF.BiasAct.apply(SF.MmNT.apply(feat, self._hwc_weight(l1.weight)), l1.bias, None, 0.1, 1.0, True)
         n_out = l2.weight.shape[0]
-        w2, b2 = _pad_rows(l2.weight, l2.bias, (n_out + 31) // 32 * 32)
+        rows = (n_out + 31) // 32 * 32
+        pad = rows - n_out
+        w2 = SF.weight_memo(l2.weight, "rows", lambda: SF.LinearMap.apply(
+            l2.weight, lambda t: torch.nn.functional.pad(t, (0, 0, 0, pad)), lambda g: g[:n_out]))
+        b2 = SF.weight_memo(l2.bias, "rows", lambda: SF.LinearMap.apply(
+            l2.bias, lambda t: torch.nn.functional.pad(t, (0, pad)), lambda g: g[:n_out]))
         out = SF.MmNT.apply(hid, w2, b2)
         return out if out.shape[1] == n_out else out[:, :n_out]
 

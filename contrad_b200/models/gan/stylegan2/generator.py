@@ -57,24 +57,31 @@ class ModulatedConv2d(nn.Module):
         The demodulation is applied by the caller's epilogue (ModEpilogue) together with noise / bias / activation;
         `bias` (1x1 kernels only: ToRGB) is added in the GEMM epilogue."""
         s = self.modulation(style)                                       # [B, Cin]
-        w = self.weight[0] * self.scale                                  # [Cout, Cin, k, k]
+        scale = self.scale
+        w = SF.weight_memo(self.weight, "scaled", lambda: SF.LinearMap.apply(        # [Cout, Cin, k, k]
+            self.weight, lambda t: t[0] * scale, lambda g: (g * scale).unsqueeze(0)))
         cout, cin = w.shape[0], w.shape[1]
         demod = None
         if self.demodulate:
+            # not memoised: `pow` keeps its input for the backward pass, and memo entries must survive a second
+            # backward in the same optimiser step (weight_memo only holds scale / pad / permute results)
             wsq = w.pow(2).sum([2, 3])                                   # [Cout, Cin]
             demod = torch.rsqrt(SF.MmNT.apply(s * s, wsq) + self.eps)    # generator.py:58-60
         xm = SF.Modulate.apply(input, s, True)
         B, H, W, _ = xm.shape
         if self.kernel_size == 1:
             rows = (cout + 31) // 32 * 32
-            w2 = w.view(cout, cin)
-            b2 = None if bias is None else bias.reshape(-1)
-            if rows != cout:
-                w2 = F.pad(w2, (0, 0, 0, rows - cout))
-                b2 = None if b2 is None else F.pad(b2, (0, rows - cout))
+            w2 = SF.weight_memo(self.weight, "rows", lambda: SF.LinearMap.apply(
+                self.weight, lambda t: F.pad(t[0].reshape(cout, cin) * scale, (0, 0, 0, rows - cout)),
+                lambda g: (g[:cout] * scale).reshape(1, cout, cin, 1, 1)))
+            b2 = None if bias is None else SF.weight_memo(bias, "rows", lambda: SF.LinearMap.apply(
+                bias, lambda t: F.pad(t.reshape(-1), (0, rows - cout)), lambda g: g[:cout].reshape(bias.shape)))
             out = SF.MmNT.apply(xm.view(-1, cin), w2, b2).view(B, H, W, rows)
         elif self.upsample:
-            wt = w.permute(2, 3, 0, 1).reshape(9 * cout, cin)            # rows (kh, kw, co): conv_transpose2d taps
+            # rows (kh, kw, co): conv_transpose2d taps
+            wt = SF.weight_memo(self.weight, "taps", lambda: SF.LinearMap.apply(
+                self.weight, lambda t: (t[0] * scale).permute(2, 3, 0, 1).reshape(9 * cout, cin),
+                lambda g: (g.reshape(3, 3, cout, cin).permute(2, 3, 0, 1) * scale).unsqueeze(0)))
             v = SF.MmNT.apply(xm.view(-1, cin), wt).view(B, H, W, 9, cout)
             out = SF.PatchS2T.apply(v, False)                            # [B, 2H+1, 2W+1, Cout]
             out = self.blur(out, round_out=False)                        # [B, 2H, 2W, Cout]

@@ -91,11 +91,25 @@ class EqualConv2d(nn.Module):
         self.padding = padding
         self.bias = nn.Parameter(torch.zeros(out_channel)) if bias else None
 
-    def scaled_weight(self, cin_pad=None, mul=1.0):
-        w = self.weight * (self.scale * mul)
-        if cin_pad is not None and cin_pad > w.shape[1]:
-            w = F.pad(w, (0, 0, 0, 0, 0, cin_pad - w.shape[1]))     # zero weights for zero-padded input channels
-        return w
+    def scaled_weight(self, cin_pad=None, mul=1.0, gemm=False):
+        """weight * scale (* mul), input channels zero-padded to cin_pad; gemm=True: as the [Cout, k*k*Cin] matrix of the
+        patch / 1x1 GEMMs.  Memoised per optimiser step (sg2_functional.weight_memo)."""
+        cout, cin, k, _ = self.weight.shape
+        alpha = self.scale * mul
+        cp = cin if cin_pad is None else max(cin, cin_pad)
+
+        def fwd(w):
+            w = w * alpha
+            if cp > cin:
+                w = F.pad(w, (0, 0, 0, 0, 0, cp - cin))                  # zero weights for zero-padded input channels
+            return w.permute(0, 2, 3, 1).reshape(cout, -1) if gemm else w
+
+        def bwd(g):
+            if gemm:
+                g = g.reshape(cout, k, k, cp).permute(0, 3, 1, 2)
+            return g[:, :cin] * alpha
+
+        return SF.weight_memo(self.weight, ("scaled", cp, mul, gemm), lambda: SF.LinearMap.apply(self.weight, fwd, bwd))
 
     def __repr__(self):
         return (f"{self.__class__.__name__}({self.weight.shape[1]}, {self.weight.shape[0]},"
@@ -115,8 +129,11 @@ class EqualLinear(nn.Module):
         self.bias_init = bias_init
 
     def forward(self, input):
-        bias = self.bias * self.lr_mul + self.bias_init
-        w = self.weight * self.scale
+        lr_mul, b0, scale = self.lr_mul, self.bias_init, self.scale
+        bias = SF.weight_memo(self.bias, "scaled", lambda: SF.LinearMap.apply(
+            self.bias, lambda b: b * lr_mul + b0, lambda g: g * lr_mul))
+        w = SF.weight_memo(self.weight, "scaled", lambda: SF.LinearMap.apply(
+            self.weight, lambda t: t * scale, lambda g: g * scale))
         if self.activation:
             return SF.BiasAct.apply(SF.MmNT.apply(input, w), bias, None, 0.2, 2 ** 0.5, True)
         return SF.MmNT.apply(input, w, bias)
@@ -158,17 +175,18 @@ class ConvLayer(nn.Sequential):
         act = self[len(self) - 1] if self.activate else None
         B, H, W, C = x.shape
         cout = conv.weight.shape[0]
-        w = conv.scaled_weight(cin_pad=C, mul=1.0 if act is not None else mul)
+        wmul = 1.0 if act is not None else mul
         if self.kernel_size == 3 and not self.downsample:
-            y = SF.Conv3x3.apply(x, w)
+            y = SF.Conv3x3.apply(x, conv.scaled_weight(cin_pad=C, mul=wmul))
         elif self.kernel_size == 3:
             t = blur(x)                                            # [B, H+1, W+1, C]
             u = SF.PatchS2.apply(t, False)                         # [B, H/2, W/2, 9, C]
-            y = SF.MmNT.apply(u.view(-1, 9 * C), w.permute(0, 2, 3, 1).reshape(cout, 9 * C))
+            y = SF.MmNT.apply(u.view(-1, 9 * C), conv.scaled_weight(cin_pad=C, mul=wmul, gemm=True))
             y = y.view(B, u.shape[1], u.shape[2], cout)
         else:
             t = blur(x, down=2) if self.downsample else x
-            y = SF.MmNT.apply(t.reshape(-1, C), w.view(cout, C)).view(t.shape[0], t.shape[1], t.shape[2], cout)
+            y = SF.MmNT.apply(t.reshape(-1, C), conv.scaled_weight(cin_pad=C, mul=wmul, gemm=True))
+            y = y.view(t.shape[0], t.shape[1], t.shape[2], cout)
         if act is not None:
             return SF.BiasAct.apply(y, act.bias, res, act.negative_slope, act.scale * mul, True)
         if res is not None:

@@ -55,6 +55,8 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from . import sg2_functional
+        sg2_functional.bump_weight_epoch()         # the kernel writes the parameters behind torch's version counters
         for group in self.param_groups:
             if staging.recording():
                 self._step_recording(group)

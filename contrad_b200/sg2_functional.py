@@ -42,6 +42,48 @@ def _cached(w, key, make):
     return memo[1][key]
 
 
+_WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    """Called by optimisers / EMA updates that write parameters through the C ABI (raw pointers: torch's version
+    counters do not see them), so that `weight_memo` entries derived from the old values are dropped."""
+    _WEIGHT_EPOCH[0] += 1
+
+
+def weight_memo(param, key, make):
+    """Per-parameter memo of tensors derived from it (runtime-scaled weight, zero-padded / permuted variants ...),
+    valid until the parameter changes (version counter or `bump_weight_epoch`) or the autograd mode differs.  A training
+    step evaluates D up to four times with the same weights (fakes, reals, the R1 pass, the G step): the derived
+    tensors - and, through `_cached`, their GEMM re-layouts - are then built once per optimiser step instead of once per
+    forward.  The entries keep their autograd history, so gradients of all the forwards flow into the parameter; only
+    results of scale / pad / permute / reshape chains may be stored (their backward nodes hold no tensors, so they can
+    be back-propagated through any number of times, e.g. under gradient accumulation)."""
+    tag = (param._version, _WEIGHT_EPOCH[0], param.requires_grad, torch.is_grad_enabled())
+    memo = getattr(param, "_cb200_wmemo", None)
+    if memo is None or memo[0] != tag:
+        memo = (tag, {})
+        param._cb200_wmemo = memo
+    if key not in memo[1]:
+        memo[1][key] = make()
+    return memo[1][key]
+
+
+class LinearMap(Function):
+    """y = fwd(w) for a LINEAR map given with its adjoint `bwd` (two callables closing over Python scalars / shapes
+    only): weight scaling, zero-padding, re-layout.  The node saves no tensors, so a memoised result can be
+    back-propagated through repeatedly; `bwd` runs ordinary torch ops, so higher-order differentiation works."""
+
+    @staticmethod
+    def forward(ctx, w, fwd, bwd):
+        ctx.bwd = bwd
+        return fwd(w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.bwd(g), None, None
+
+
 def _rw(w):
     """Weight-shaped operand of a tensor-core GEMM: contiguous and rounded to TF32 (nearest)."""
     return _cached(w, "rw", lambda: K.round_tf32(_c(w.detach())))

@@ -34,6 +34,7 @@ def accumulate(model_dst, model_src, decay=0.999):
     pairs = [(p.data, src[k].data) for k, p in model_dst.named_parameters()]
     if pairs:
         S.ema_lerp(pairs, decay)
+        SF.bump_weight_epoch()
     buf_src = dict(model_src.named_buffers())
     for k, b in model_dst.named_buffers():
         b.data.copy_(buf_src[k].data)
