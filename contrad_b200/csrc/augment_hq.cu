@@ -59,7 +59,14 @@ __global__ void __launch_bounds__(kT) blur_axis_kernel(const float* __restrict__
         const int i = axis == 0 ? row : col;
         const float* line = x + (idx - (long long)i * stride);        // element 0 of this row / column
         float acc = 0.f;
-        if (!adjoint) {
+        if (adjoint ? (i - r > 0 && i + r < n - 1) : (i - r >= 0 && i + r < n)) {
+            // interior: no reflection involved (for the adjoint the reflected halo folds back onto 1..r and
+            // n-2-r..n-2, hence the stricter test); the adjoint reads the taps mirrored: x[i - d] = x[i + r - t]
+            const float* pt = line + (long long)(adjoint ? i + r : i - r) * stride;
+            const long long step = adjoint ? -(long long)stride : (long long)stride;
+#pragma unroll 4
+            for (int t = 0; t < k; ++t) acc = fmaf(w[t], pt[t * step], acc);
+        } else if (!adjoint) {
             for (int t = 0; t < k; ++t) acc = fmaf(w[t], line[(long long)reflect_index(i + t - r, n) * stride], acc);
         } else {
             for (int t = 0; t < k; ++t) {
@@ -75,6 +82,30 @@ __global__ void __launch_bounds__(kT) blur_axis_kernel(const float* __restrict__
             }
         }
         y[idx] = acc;
+    }
+}
+
+// float4 along W (W % 4 == 0): params as below
+__global__ void __launch_bounds__(kT) cutout_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y,
+                                                        const float* __restrict__ params, int B, int P, int H, int W4, int half) {
+    const int b = blockIdx.y;
+    const long long per4 = (long long)P * H * W4;
+    const float4* xb = x + (long long)b * per4;
+    float4* yb = y + (long long)b * per4;
+    const bool on = __ldg(params + b) != 0.f;
+    const int hc = (int)__ldg(params + B + b), wc = (int)__ldg(params + 2 * B + b);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = xb[i];
+        if (on) {
+            const int col = (int)(i % W4) * 4, row = (int)((i / W4) % H);
+            if (abs(row - hc) <= half) {
+                if (abs(col - wc) <= half) v.x = 0.f;
+                if (abs(col + 1 - wc) <= half) v.y = 0.f;
+                if (abs(col + 2 - wc) <= half) v.z = 0.f;
+                if (abs(col + 3 - wc) <= half) v.w = 0.f;
+            }
+        }
+        yb[i] = v;
     }
 }
 
@@ -118,8 +149,14 @@ extern "C" int cb200_cutout(const float* x, float* y, const float* params, int B
                             void* stream) {
     CB200_CHECK_ARG(B > 0 && P > 0 && H > 0 && W > 0, "cutout: empty tensor");
     CB200_CHECK_ARG(length >= 1 && (length & 1), "cutout: length %d must be odd (augment/spatial.py:155-156)", length);
-    cutout_kernel<<<grid_for((long long)B * P * H * W), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, y, params, B, P, H, W,
-                                                                                                    (length - 1) / 2);
+    if (W % 4 == 0 && B <= 65535 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        dim3 grid(grid_for((long long)P * H * (W / 4), kT, (148 * 16 + B - 1) / B), B);
+        cutout_vec_kernel<<<grid, kT, 0, static_cast<cudaStream_t>(stream)>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), params, B, P, H, W / 4, (length - 1) / 2);
+    } else {
+        cutout_kernel<<<grid_for((long long)B * P * H * W), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, y, params, B, P, H, W,
+                                                                                                        (length - 1) / 2);
+    }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("cutout");
     return CB200_OK;

@@ -47,5 +47,24 @@ elif which in ("conv_first_wgrad", "conv_first_fwd"):
             K.conv_first_fwd(xx, w, None, bias)
         else:
             K.conv_first_wgrad(xx, dy)
+elif which == "upfirdn":
+    from contrad_b200 import sg2_kernels as S
+    fir = torch.tensor([1., 3., 3., 1.]); fir = (fir[None] * fir[:, None] / 64).cuda()
+    xs = [torch.randn(192, 32, 32, 128, device="cuda") for _ in range(3)]
+    for i in range(4):
+        S.upfirdn2d(xs[i % 3], fir, 1, 1, (2, 2, 2, 2), round_out=True)
+elif which == "bias_act":
+    from contrad_b200 import sg2_kernels as S
+    xs = [torch.randn(192, 32, 32, 128, device="cuda") for _ in range(3)]
+    bias = torch.randn(128, device="cuda")
+    for i in range(4):
+        S.bias_act(xs[i % 3], bias, 0.2, 2 ** 0.5, round_out=True)
+elif which == "augment_large":
+    prm = torch.zeros(11, 48, device="cuda")
+    prm[0] = 0.7; prm[1] = 0.8; prm[2] = 0.1; prm[3] = -0.1; prm[4] = 1.0; prm[5] = 1.0; prm[6] = 1.2; prm[7] = 0.05
+    prm[8] = 1.1; prm[9] = 0.9
+    xs = [torch.rand(48, 3, 512, 512, device="cuda") for _ in range(3)]
+    for i in range(4):
+        K.augment_simclr_large_fwd(xs[i % 3], prm, 0)
 torch.cuda.synchronize()
 print("done", which)
