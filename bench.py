@@ -500,6 +500,12 @@ def main():
     ap.add_argument("--no-side-workloads", action="store_true", help="skip the StyleGAN2 config-4 side measurement")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (and DDP wrappers for N > 1) instead of the CUDA-graph step")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 behind Python's back (NCCL prints
+    # "NCCL version ..." there when NCCL_DEBUG is set in the environment) are routed to stderr for the whole run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
