@@ -339,6 +339,31 @@ def run_native(args):
     e2e_value = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
 
     _log("e2e arm done: %.3f ms/step" % (ms_e2e / args.steps))
+    # ---- optional: the same end-to-end loop fed with the dataset's raw uint8 images (ToTensor, the
+    # two-view duplication and the concatenation run inside the augmentation kernel; 1 B/element crosses PCIe)
+    e2e_u8 = None
+    if args.u8_input and world == 1:
+        try:
+            graphed_u8 = None if args.no_graph else engine.GraphedTrainStep(W.P, OPTIONS, train_fn, (W.G, W.D),
+                                                                            (W.opt_G, W.opt_D))
+            host_u8 = [torch.randint(0, 256, (n_local, 3, 32, 32), dtype=torch.uint8).pin_memory() for _ in range(4)]
+
+            def u8_step(s):
+                images = host_u8[s % len(host_u8)].to(dev, non_blocking=True)
+                step_no[0] += 1
+                out = graphed_u8(images, step_no[0]) if graphed_u8 is not None else engine.train_step(
+                    W.P, OPTIONS, train_fn, (W.G, W.D), (W.opt_G, W.opt_D), images, step_no[0])
+                return [out[k].item() for k in ("g_loss", "d_loss", "d_penalty", "d_real", "d_gen")]
+
+            for w in range((graphed_u8.eager_steps + 1 if graphed_u8 is not None else 0) + 2):
+                u8_step(w)
+            ms_u8 = timed(u8_step, args.steps)
+            e2e_u8 = {"value": GLOBAL_BATCH * args.steps / (ms_u8 / 1e3), "unit": "images/s", "ms_per_step": ms_u8 / args.steps,
+                      "h2d_bytes_per_step": n_local * 3 * 32 * 32, "d2h_bytes_per_step": d2h[0]}
+            if graphed_u8 is not None:
+                graphed_u8.release()
+        except Exception as e:                                # noqa: BLE001 - optional leg: report, do not lose the line
+            e2e_u8 = {"error": "%s: %s" % (type(e).__name__, e)}
     faulthandler.cancel_dump_traceback_later()
     line = None
     if rank == 0:
@@ -360,6 +385,8 @@ def run_native(args):
             "gpu_launches": int(launches),
             "step_tflops": FLOP_PER_IMAGE_STEP * value / 1e12,
         }
+        if e2e_u8 is not None:
+            line["e2e_uint8_input"] = e2e_u8
         if roof:
             line.update(roof)
         if cpu:
@@ -498,6 +525,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-workloads", action="store_true", help="skip the StyleGAN2 config-4 side measurement")
+    ap.add_argument("--u8-input", action="store_true",
+                    help="extra end-to-end leg fed with uint8 host images (row f3; N=1 only, reported as e2e_uint8_input)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (and DDP wrappers for N > 1) instead of the CUDA-graph step")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 behind Python's back (NCCL prints

@@ -5,13 +5,15 @@ host side in the reference's exact numpy / torch RNG order, so iden
 identical augmentations.
 
 `simclr_hq` / `simclr_hq_cutout` (the README's StyleGAN2 recipe) append a separable Gaussian blur and a CutOut kernel.
-Out of scope: hfrt, gaussian, diffaug - requesting them raises NotImplementedError rather than
+`hfrt` / `gaussian` (row f4, the CR / bCR baselines' augmentations) are one gather kernel / one elementwise kernel.
+Out of scope: diffaug (third_party/diffaug.py) - requesting it raises NotImplementedError rather than
 silently running something else."""
 import gin
 import torch.nn as nn
 
-from .layers import (ColorJitterLayer, CutOut, FusedSimCLR, FusedSimCLRHQ, GaussianBlur,  # noqa: F401
-                     HorizontalFlipLayer, NoAugment, RandomApply, RandomColorGrayLayer, RandomResizeCropLayer)
+from .layers import (ColorJitterLayer, CutOut, FusedSimCLR, FusedSimCLRHQ, Gaussian, GaussianBlur,  # noqa: F401
+                     HorizontalFlipLayer, HorizontalFlipRandomCrop, NoAugment, RandomApply, RandomColorGrayLayer,
+                     RandomCrop, RandomResizeCropLayer)
 
 
 def simclr():
@@ -48,8 +50,9 @@ def simclr_hq_cutout():
 
 
 _BUILT = {"none": NoAugment, "simclr": simclr, "simclr_hq": simclr_hq, "simclr_hq_cutout": simclr_hq_cutout,
-          "cutout": CutOut, "hflip": HorizontalFlipLayer, "color_jitter": ColorJitterLayer}
-_NEXT = ("gaussian", "hfrt", "diffaug")
+          "cutout": CutOut, "hflip": HorizontalFlipLayer, "color_jitter": ColorJitterLayer,
+          "gaussian": Gaussian, "hfrt": HorizontalFlipRandomCrop}
+_NEXT = ("diffaug",)
 
 
 @gin.configurable("augment", whitelist=["fn"])

@@ -10,7 +10,8 @@ import torch
 import torch.nn as nn
 
 from .. import staging
-from ..functional import AugmentSimCLRFn, CutOutFn, GaussianBlurFn
+from ..functional import (AugmentSimCLRFn, AugmentSimCLRMixedFn, CutOutFn, GaussianBlurFn, NoiseClampFn,
+                          ShiftFlipFn)
 
 _N_FIELDS = 11   # sx, sy, bx, by, flip, cj_on, contrast, hue, sat, val, gray_on
 
@@ -33,6 +34,64 @@ def _identity_block(batch, device):
 class NoAugment(nn.Module):
     def forward(self, input):
         return input
+
+
+@gin.configurable(whitelist=["sigma"])
+class Gaussian(nn.Module):
+    """augment/__init__.py:40-49: additive Gaussian noise, clamped to [0, 1].  The noise is torch.randn_like (the
+    reference's random stream); the scale-add-clamp and its gradient mask are one kernel each."""
+
+    def __init__(self, sigma):
+        super().__init__()
+        self.sigma = sigma
+
+    def forward(self, input):
+        return NoiseClampFn.apply(input, torch.randn_like(input), self.sigma)
+
+
+class _ShiftFlip(nn.Module):
+    """Shared body of HorizontalFlipRandomCrop / RandomCrop (augment/spatial.py:14-67): theta = [[sign, 0, bias_x],
+    [0, 1, bias_y]] with bias = randint(-max_pixels, max_pixels + 1) / (width / 2), sampled by nearest-neighbour
+    grid_sample.  One gather kernel instead of affine_grid + grid_sample."""
+
+    _flip = False
+
+    def __init__(self, max_pixels, width, padding_mode):
+        super().__init__()
+        if padding_mode not in ("zeros", "border", "reflection"):
+            raise ValueError("padding_mode must be 'zeros', 'border' or 'reflection' (F.grid_sample), got %r"
+                             % (padding_mode,))
+        self.max_pixels = max_pixels
+        self.width = width
+        self.register_buffer("_eye", torch.eye(2, 3))      # state_dict compatibility
+        self.padding_mode = padding_mode
+
+    def sample(self, input):
+        """[3, N] = {sign, bias_x, bias_y}; device draws in the reference order (sign first, spatial.py:31-33)."""
+        n, dev = input.size(0), input.device
+        params = torch.empty(3, n, device=dev)
+        if self._flip:
+            params[0] = torch.bernoulli(torch.ones(n, device=dev) * 0.5) * 2 - 1
+        else:
+            params[0] = 1.0
+        r_bias = torch.randint(-self.max_pixels, self.max_pixels + 1, (n, 2), device=dev).float() / (self.width / 2)
+        params[1:3] = r_bias.t()
+        return params
+
+    def forward(self, input):
+        return ShiftFlipFn.apply(input, self.sample(input), self.padding_mode)
+
+
+@gin.configurable
+class HorizontalFlipRandomCrop(_ShiftFlip):
+    """augment/spatial.py:14-40 (`--aug hfrt`)."""
+    _flip = True
+
+
+@gin.configurable
+class RandomCrop(_ShiftFlip):
+    """augment/spatial.py:43-67."""
+    _flip = False
 
 
 @gin.configurable
@@ -228,6 +287,25 @@ class FusedSimCLR(nn.Sequential):
         params, order = self.sample_params(inputs)
         return AugmentSimCLRFn.apply(inputs, params, order)
 
+    def forward_views(self, images_u8, reps=1, extra=None):
+        """Row f3: `self(torch.cat([images_u8.float() / 255] * reps + [extra]))` in ONE launch that reads
+        the dataset's uint8 bytes directly - ToTensor (datasets.py:10-21), the fp32 upload (train_gan.py:153-154) and
+        the concatenation (training/gan/contrad.py:38-40) are folded into the kernel.  Random draws are made for the
+        whole `reps * n + len(extra)` batch in the reference order, so a given seed produces the views the reference
+        produces on the converted, concatenated batch.  Only `extra` (fp32, e.g. G(z)) is differentiable."""
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[1] != 3:
+            raise ValueError("forward_views expects uint8 [n,3,H,W] images, got %s %s"
+                             % (images_u8.dtype, tuple(images_u8.shape)))
+        if extra is not None and (extra.dtype != torch.float32 or tuple(extra.shape[1:]) != tuple(images_u8.shape[1:])):
+            raise ValueError("extra must be float32 [m,3,H,W] of the same image size, got %s %s"
+                             % (extra.dtype, tuple(extra.shape)))
+        n_views = int(reps) * images_u8.shape[0]
+        total = n_views + (0 if extra is None else extra.shape[0])
+        # shape / device / dtype carrier for the samplers (no B x 3 x H x W allocation)
+        carrier = torch.empty(1, device=images_u8.device, dtype=torch.float32).expand(total, *images_u8.shape[1:])
+        params, order = self.sample_params(carrier)
+        return AugmentSimCLRMixedFn.apply(images_u8, n_views, extra, params, order)
+
 
 def gaussian_taps(kernel_size, sigma):
     """The normalised 1-D Gaussian whose outer product is kornia's `get_gaussian_kernel2d((k, k), (sigma, sigma))`."""
@@ -292,7 +370,13 @@ class FusedSimCLRHQ(FusedSimCLR):
     ... gray mask, blur mask (device), sigma (numpy), cutout mask (device), centres (device)."""
 
     def forward(self, inputs):
-        out = FusedSimCLR.forward(self, inputs)
+        return self._tail(FusedSimCLR.forward(self, inputs), inputs)
+
+    def forward_views(self, images_u8, reps=1, extra=None):
+        out = FusedSimCLR.forward_views(self, images_u8, reps, extra)
+        return self._tail(out, out)
+
+    def _tail(self, out, inputs):
         apply_blur = self[4]
         on = apply_blur.sample(inputs)
         out = apply_blur.fn(out, on=on)

@@ -331,6 +331,63 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
     }
 }
 
+// Per-image arithmetic of the column-mapped forward kernels: thread = output column j, rows i_first .. i_first+NPX-1.
+// `xs` is the fp32 [3,S,S] source image in shared memory, `yb` points at this thread's first output element.
+template <int S>
+__device__ __forceinline__ void cols_process(const float* xs, const float4* xtap, const float4* ytap, float* red,
+                                             const SampleParams& sp, int ord, float hshift, float* yb, int j,
+                                             int i_first) {
+    constexpr int HW = S * S, NPX = HW / kMaxThreads;
+    float v[NPX][3];
+    {
+        const float4 tx = xtap[j];
+        const int x0 = __float_as_int(tx.x), x1 = __float_as_int(tx.y);
+#pragma unroll
+        for (int m = 0; m < NPX; ++m) {
+            const float4 ty = ytap[i_first + m];
+            const float* r0 = xs + __float_as_int(ty.x);
+            const float* r1 = xs + __float_as_int(ty.y);
+            const float w00 = tx.z * ty.z, w01 = tx.w * ty.z, w10 = tx.z * ty.w, w11 = tx.w * ty.w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v[m][c] = r0[c * HW + x0] * w00 + r0[c * HW + x1] * w01 + r1[c * HW + x0] * w10 +
+                          r1[c * HW + x1] * w11;
+        }
+    }
+    if (sp.cj_on != 0.f) {          // uniform across the CTA
+        if (ord == 1) {
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
+        }
+        float sums[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int m = 0; m < NPX; ++m)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sums[c] += v[m][c];
+        block_sum<3>(sums, red);
+        constexpr float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mean = sums[c] * inv;
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) v[m][c] = clamp01((v[m][c] - mean) * sp.fc + mean);
+        }
+        if (ord == 0) {
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NPX; ++m) {
+        if (sp.gray_on != 0.f) {
+            const float l = 0.299f * v[m][0] + 0.587f * v[m][1] + 0.114f * v[m][2];
+            v[m][0] = l; v[m][1] = l; v[m][2] = l;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, v[m][c]);
+    }
+}
+
 // Forward, square S x S images with S a multiple of 32 (the CIFAR / 64x64 cases): COLUMN mapping.  Lane = output
 // column, each thread walks NPX = S*S/256 consecutive output rows.  The bilinear gather then reads, per warp
 // instruction, 32 (almost always distinct) columns of ONE source row: no shared-memory bank conflicts, where the
@@ -385,56 +442,82 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
         __syncthreads();
         const float* xs = smem + buf * 3 * HW;
 
-        float v[NPX][3];
-        {
-            const float4 tx = xtap[j];
-            const int x0 = __float_as_int(tx.x), x1 = __float_as_int(tx.y);
-#pragma unroll
-            for (int m = 0; m < NPX; ++m) {
-                const float4 ty = ytap[i_first + m];
-                const float* r0 = xs + __float_as_int(ty.x);
-                const float* r1 = xs + __float_as_int(ty.y);
-                const float w00 = tx.z * ty.z, w01 = tx.w * ty.z, w10 = tx.z * ty.w, w11 = tx.w * ty.w;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    v[m][c] = r0[c * HW + x0] * w00 + r0[c * HW + x1] * w01 + r1[c * HW + x0] * w10 +
-                              r1[c * HW + x1] * w11;
-            }
-        }
-        if (sp.cj_on != 0.f) {          // uniform across the CTA
-            if (ord == 1) {
-#pragma unroll
-                for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
-            }
-            float sums[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-            for (int m = 0; m < NPX; ++m)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) sums[c] += v[m][c];
-            block_sum<3>(sums, red);
-            constexpr float inv = 1.f / (float)HW;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float mean = sums[c] * inv;
-#pragma unroll
-                for (int m = 0; m < NPX; ++m) v[m][c] = clamp01((v[m][c] - mean) * sp.fc + mean);
-            }
-            if (ord == 0) {
-#pragma unroll
-                for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, sp.fs, sp.fv);
-            }
-        }
-        float* yb = y + (size_t)b * 3 * HW + i_first * S + j;
-#pragma unroll
-        for (int m = 0; m < NPX; ++m) {
-            if (sp.gray_on != 0.f) {
-                const float l = 0.299f * v[m][0] + 0.587f * v[m][1] + 0.114f * v[m][2];
-                v[m][0] = l; v[m][1] = l; v[m][2] = l;
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, v[m][c]);
-        }
+        cols_process<S>(xs, xtap, ytap, red, sp, ord, hshift, y + (size_t)b * 3 * HW + i_first * S + j, j, i_first);
         __syncthreads();      // tap tables / reduction scratch / this image buffer are reused by the next iteration
+    }
+}
+
+// Row f3: `ToTensor` folded into the augmentation.  The reference converts the dataset's uint8 images to
+// fp32 on the host (datasets.py:10-21 -> torchvision to_tensor: byte / 255), copies 4 B/element to the device and
+// concatenates [x, x, G(z)] (training/gan/contrad.py:38-40) before augmenting.  Here view b of the launch reads
+//     b <  n_u8_views : uint8 image (b mod n_u8)   (1 B/element of HBM traffic, several views may share a source)
+//     b >= n_u8_views : fp32 image (b - n_u8_views)
+// so the D-step batch cat[x, x, G(z)] is never materialised.  Bytes are expanded through a 256-entry table of
+// correctly rounded k / 255 (bit-identical to ToTensor) into a separate fp32 buffer: the prefetch ring is only ever
+// written by the async proxy, as in the fp32 kernel above.
+template <int S>
+__global__ void __launch_bounds__(kMaxThreads)
+augment_simclr_fwd_mixed_cols_kernel(const uint8_t* __restrict__ xu, int n_u8, int n_u8_views,
+                                     const float* __restrict__ xf, float* __restrict__ y,
+                                     const float* __restrict__ params, int B, int order) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int HW = S * S, NPX = HW / kMaxThreads;
+    float* conv = smem + 6 * HW;                                  // [3*HW] fp32 copy of a uint8 source
+    float* lut = conv + 3 * HW;                                   // [256]
+    float* red = lut + 256;                                       // [3*32]
+    float4* xtap = reinterpret_cast<float4*>(red + 96);
+    float4* ytap = xtap + S;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ytap + S);
+    const int j = threadIdx.x % S, i_first = (threadIdx.x / S) * NPX;
+
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);      // blockDim.x == 256
+    if (threadIdx.x == 0) {
+        bar_init(&bars[0], 1);
+        bar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto prefetch = [&](int view, int slot) {                     // thread 0 only
+        const bool bytes_src = view < n_u8_views;
+        const uint32_t nbytes = bytes_src ? (uint32_t)(3 * HW) : (uint32_t)(3 * HW * sizeof(float));
+        const void* src = bytes_src ? static_cast<const void*>(xu + (size_t)(view % n_u8) * 3 * HW)
+                                    : static_cast<const void*>(xf + (size_t)(view - n_u8_views) * 3 * HW);
+        bar_expect_tx(&bars[slot], nbytes);
+        bulk_load(smem + slot * 3 * HW, src, nbytes, &bars[slot]);
+    };
+    int b = blockIdx.x;
+    if (threadIdx.x == 0 && b < B) prefetch(b, 0);
+    for (int it = 0; b < B; b += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int nb = b + gridDim.x;
+        if (threadIdx.x == 0 && nb < B) prefetch(nb, buf ^ 1);
+        const SampleParams sp = load_params(params, B, b);
+        const int ord = resolve_order(params, B, b, order);
+        const float hshift = (sp.fh * 255.f) / 360.f;
+        if (threadIdx.x < 2 * S) {
+            const int e = threadIdx.x;
+            if (e < S) {
+                const Tap a = axis_tap((sp.flip < 0.f) ? (S - 1 - e) : e, S, sp.sx, sp.bx);
+                xtap[e] = make_float4(__int_as_float(a.i0), __int_as_float(a.i1), a.w0, a.w1);
+            } else {
+                const Tap a = axis_tap(e - S, S, sp.sy, sp.by);
+                ytap[e - S] = make_float4(__int_as_float(a.i0 * S), __int_as_float(a.i1 * S), a.w0, a.w1);
+            }
+        }
+        bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
+        const float* xs = smem + buf * 3 * HW;
+        if (b < n_u8_views) {                                     // uniform across the CTA
+            const uint32_t* packed = reinterpret_cast<const uint32_t*>(xs);
+            for (int w = threadIdx.x; w < 3 * HW / 4; w += kMaxThreads) {      // conflict-free LDS.32 / STS.128
+                const uint32_t pk = packed[w];
+                reinterpret_cast<float4*>(conv)[w] =
+                    make_float4(lut[pk & 255u], lut[(pk >> 8) & 255u], lut[(pk >> 16) & 255u], lut[pk >> 24]);
+            }
+            xs = conv;
+        }
+        __syncthreads();
+        cols_process<S>(xs, xtap, ytap, red, sp, ord, hshift, y + (size_t)b * 3 * HW + i_first * S + j, j, i_first);
+        __syncthreads();      // tap tables / scratch / conversion buffer / this ring slot are reused by the next iteration
     }
 }
 
@@ -595,6 +678,17 @@ __device__ __forceinline__ void gather_pixel(const float* __restrict__ xb, int H
     }
 }
 
+// The same gather from a uint8 image; `lut` (shared memory) holds the correctly rounded k / 255 of ToTensor.
+__device__ __forceinline__ void gather_pixel(const uint8_t* __restrict__ xb, const float* lut, int HW, const PixelTaps& t,
+                                             float (&v)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint8_t* xc = xb + (size_t)c * HW;
+        v[c] = lut[__ldg(xc + t.o00)] * t.w00 + lut[__ldg(xc + t.o01)] * t.w01 + lut[__ldg(xc + t.o10)] * t.w10 +
+               lut[__ldg(xc + t.o11)] * t.w11;
+    }
+}
+
 // means[b,3] += per-channel mean of the contrast input (crop+flip, then hsv when the order is [hsv, contrast])
 __global__ void __launch_bounds__(kMaxThreads)
 augment_large_mean_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ means, int B,
@@ -637,6 +731,77 @@ augment_large_apply_kernel(const float* __restrict__ x, float* __restrict__ y, c
     for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
         float v[3];
         gather_pixel(xb, HW, pixel_taps(pix / W, pix % W, H, W, sp), v);
+        if (sp.cj_on != 0.f) {
+            if (ord == 1) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = clamp01((v[c] - m[c]) * sp.fc + m[c]);
+            if (ord == 0) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
+        }
+        if (sp.gray_on != 0.f) {
+            const float l = 0.299f * v[0] + 0.587f * v[1] + 0.114f * v[2];
+            v[0] = l; v[1] = l; v[2] = l;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) __stcs(yb + (size_t)c * HW + pix, v[c]);
+    }
+}
+
+// Mixed-source variants of the two forward kernels (row f3, see augment_simclr_fwd_mixed_cols_kernel): view b reads the
+// uint8 image (b mod n_u8) when b < n_u8_views, else the fp32 image (b - n_u8_views).  The source type is uniform per CTA.
+__global__ void __launch_bounds__(kMaxThreads)
+augment_large_mean_mixed_kernel(const uint8_t* __restrict__ xu, int n_u8, int n_u8_views, const float* __restrict__ xf,
+                                const float* __restrict__ params, float* __restrict__ means, int B, int H, int W, int order) {
+    __shared__ float red[96];
+    __shared__ float lut[256];
+    const int b = blockIdx.y;
+    const SampleParams sp = load_params(params, B, b);
+    if (sp.cj_on == 0.f) return;                                   // uniform per CTA
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);       // blockDim.x == 256
+    __syncthreads();
+    const int ord = resolve_order(params, B, b, order);
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    const int HW = H * W;
+    const bool bytes_src = b < n_u8_views;
+    const uint8_t* xub = xu + (size_t)(bytes_src ? b % n_u8 : 0) * 3 * HW;
+    const float* xfb = xf + (size_t)(bytes_src ? 0 : b - n_u8_views) * 3 * HW;
+    float sums[3] = {0.f, 0.f, 0.f};
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float v[3];
+        const PixelTaps t = pixel_taps(pix / W, pix % W, H, W, sp);
+        if (bytes_src) gather_pixel(xub, lut, HW, t, v); else gather_pixel(xfb, HW, t, v);
+        if (ord == 1) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
+        sums[0] += v[0]; sums[1] += v[1]; sums[2] += v[2];
+    }
+    block_sum<3>(sums, red);
+    if (threadIdx.x == 0) {
+        const float inv = 1.f / (float)HW;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(means + b * 3 + c, sums[c] * inv);
+    }
+}
+
+__global__ void __launch_bounds__(kMaxThreads)
+augment_large_apply_mixed_kernel(const uint8_t* __restrict__ xu, int n_u8, int n_u8_views, const float* __restrict__ xf,
+                                 float* __restrict__ y, const float* __restrict__ params, const float* __restrict__ means,
+                                 int B, int H, int W, int order) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);       // blockDim.x == 256
+    __syncthreads();
+    const int b = blockIdx.y;
+    const SampleParams sp = load_params(params, B, b);
+    const int ord = resolve_order(params, B, b, order);
+    const float hshift = (sp.fh * 255.f) / 360.f;
+    const int HW = H * W;
+    const bool bytes_src = b < n_u8_views;
+    const uint8_t* xub = xu + (size_t)(bytes_src ? b % n_u8 : 0) * 3 * HW;
+    const float* xfb = xf + (size_t)(bytes_src ? 0 : b - n_u8_views) * 3 * HW;
+    float* yb = y + (size_t)b * 3 * HW;
+    float m[3] = {0.f, 0.f, 0.f};
+    if (sp.cj_on != 0.f) { m[0] = __ldg(means + b * 3); m[1] = __ldg(means + b * 3 + 1); m[2] = __ldg(means + b * 3 + 2); }
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float v[3];
+        const PixelTaps t = pixel_taps(pix / W, pix % W, H, W, sp);
+        if (bytes_src) gather_pixel(xub, lut, HW, t, v); else gather_pixel(xfb, HW, t, v);
         if (sp.cj_on != 0.f) {
             if (ord == 1) hsv_jitter(v[0], v[1], v[2], hshift, sp.fs, sp.fv);
 #pragma unroll
@@ -862,5 +1027,55 @@ extern "C" int cb200_augment_simclr_large_bwd(const float* x, const float* dy, f
     augment_large_bwd_scatter_kernel<<<grid, kMaxThreads, 0, st>>>(x, dy, dx, params, means, gsums, B, H, W, order);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("augment_simclr_large_bwd");
+    return CB200_OK;
+}
+
+
+// Row f3: forward of the chain over B = n_u8_views + n_f32 views, where view b < n_u8_views reads the uint8 image
+// (b mod n_u8) of `x_u8` [n_u8,3,H,W] (value / 255, ToTensor) and the others the fp32 images of `x_f32`
+// [B - n_u8_views,3,H,W] in order.  With n_u8_views = 2 * n_u8 this is augment(cat[x, x, G(z)]) of
+// training/gan/contrad.py:38-41 without the host-side conversion, the 4 B/element upload and the concatenation.
+// `means` [B,3] is caller-allocated scratch (written only on the any-size path; hand it to
+// cb200_augment_simclr_large_bwd, sliced to the fp32 views, for the gradient of those).  Either source may be empty
+// (n_u8_views == 0 or == B); its pointer is then ignored.
+extern "C" int cb200_augment_simclr_mixed_fwd(const unsigned char* x_u8, int n_u8, int n_u8_views, const float* x_f32,
+                                              float* y, const float* params, float* means, int B, int H, int W,
+                                              int order, void* stream) {
+    CB200_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && (order >= -1 && order <= 1), "augment_mixed_fwd: bad shape/order");
+    CB200_CHECK_ARG(n_u8_views >= 0 && n_u8_views <= B && (n_u8_views == 0 || n_u8 > 0),
+                    "augment_mixed_fwd: %d uint8 views of %d images in a batch of %d", n_u8_views, n_u8, B);
+    if (B == 0) return CB200_OK;
+    if (n_u8 < 1) n_u8 = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x_u8) | reinterpret_cast<uintptr_t>(x_f32)) & 15) == 0;
+    if (H == W && (H == 32 || H == 64) && aligned) {
+        const size_t smem = (size_t)(9 * H * W + 256 + 96 + 8 * H) * sizeof(float) + 2 * sizeof(uint64_t);
+        int dev = 0, sm_count = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (sm_count <= 0) sm_count = 148;
+        int per_sm = (int)((200 * 1024) / smem);
+        if (per_sm > 8) per_sm = 8;
+        if (per_sm < 1) per_sm = 1;
+        const int grid = B < sm_count * per_sm ? B : sm_count * per_sm;
+        if (H == 32) {
+            cudaFuncSetAttribute(augment_simclr_fwd_mixed_cols_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_mixed_cols_kernel<32><<<grid, kMaxThreads, smem, st>>>(x_u8, n_u8, n_u8_views, x_f32, y, params, B, order);
+        } else {
+            cudaFuncSetAttribute(augment_simclr_fwd_mixed_cols_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_mixed_cols_kernel<64><<<grid, kMaxThreads, smem, st>>>(x_u8, n_u8, n_u8_views, x_f32, y, params, B, order);
+        }
+        CB200_COUNT_LAUNCH();
+        CB200_CHECK_LAUNCH("augment_simclr_mixed_fwd");
+        return CB200_OK;
+    }
+    cudaError_t e = cudaMemsetAsync(means, 0, sizeof(float) * 3 * (size_t)B, st);
+    if (e != cudaSuccess) { cb200_set_error("augment_mixed_fwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    const dim3 grid = large_grid(B, H, W);
+    augment_large_mean_mixed_kernel<<<grid, kMaxThreads, 0, st>>>(x_u8, n_u8, n_u8_views, x_f32, params, means, B, H, W, order);
+    CB200_COUNT_LAUNCH();
+    augment_large_apply_mixed_kernel<<<grid, kMaxThreads, 0, st>>>(x_u8, n_u8, n_u8_views, x_f32, y, params, means, B, H, W, order);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("augment_simclr_mixed_fwd");
     return CB200_OK;
 }

@@ -28,6 +28,10 @@ _ALIASES = {
     "training.criterion": "contrad_b200.training.criterion",
     "training.gan": "contrad_b200.training.gan",
     "training.gan.contrad": "contrad_b200.training.gan.contrad",
+    "training.gan.std": "contrad_b200.training.gan.std",
+    "training.gan.aug": "contrad_b200.training.gan.aug",
+    "training.gan.aug_both": "contrad_b200.training.gan.aug_both",
+    "training.gan.simclr_only": "contrad_b200.training.gan.simclr_only",
     "third_party.gather_layer": "contrad_b200.third_party.gather_layer",
     "models": "contrad_b200.models",
     "models.gan": "contrad_b200.models.gan",

@@ -53,6 +53,36 @@ class AugmentSimCLRFn(Function):
         return dx, None, None, None
 
 
+class AugmentSimCLRMixedFn(Function):
+    """Row f3: augment(cat[ToTensor(x_u8)] * reps + [x_f32]) in one launch, without materialising the conversion or the
+    concatenation (datasets.py:10-21, training/gan/contrad.py:38-41).  Only `x_f32` is differentiable; its gradient runs
+    the ordinary backward kernels on the parameter columns of its views."""
+
+    @staticmethod
+    def forward(ctx, x_u8, n_u8_views, x_f32, params, order):
+        y, means = K.augment_simclr_mixed_fwd(x_u8, n_u8_views, x_f32, params, order)
+        ctx.order, ctx.n_u8_views = order, n_u8_views
+        ctx.has_f32 = x_f32 is not None and x_f32.shape[0] > 0
+        if ctx.has_f32 and x_f32.requires_grad:
+            x_f32 = _c(x_f32)
+            # sizes that need the global-memory backward always took the global-memory forward, so `means` is valid
+            ctx.large = K.augment_needs_large_path(x_f32.shape[2], x_f32.shape[3])
+            ctx.save_for_backward(x_f32, params[:, n_u8_views:].contiguous(), means[n_u8_views:].contiguous())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = None
+        if ctx.has_f32 and ctx.needs_input_grad[2]:
+            x_f32, params, means = ctx.saved_tensors
+            dy = _c(dy[ctx.n_u8_views:])
+            if ctx.large:
+                dx = K.augment_simclr_large_bwd(x_f32, dy, params, ctx.order, means)
+            else:
+                dx = K.augment_simclr_bwd(x_f32, dy, params, ctx.order)
+        return None, None, dx, None, None
+
+
 class GaussianBlurFn(Function):
     """RandomApply(GaussianBlur) (augment/__init__.py:52-78,100-103): y = on ? blur(x) : x."""
 
@@ -80,6 +110,38 @@ class CutOutFn(Function):
     def backward(ctx, dy):
         (params,) = ctx.saved_tensors
         return K.cutout(_c(dy), params, ctx.length), None, None
+
+
+class ShiftFlipFn(Function):
+    """HorizontalFlipRandomCrop / RandomCrop (augment/spatial.py:14-67): a per-sample index map, so the backward is the
+    transposed map (cb200_shift_flip_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, params, padding_mode):
+        ctx.save_for_backward(params)
+        ctx.padding_mode = padding_mode
+        return K.shift_flip(_c(x), params, padding_mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (params,) = ctx.saved_tensors
+        return K.shift_flip(_c(dy), params, ctx.padding_mode, adjoint=True), None, None
+
+
+class NoiseClampFn(Function):
+    """Gaussian (augment/__init__.py:40-49): clamp(x + noise * sigma, 0, 1)."""
+
+    @staticmethod
+    def forward(ctx, x, noise, sigma):
+        x = _c(x)
+        ctx.save_for_backward(x, noise)
+        ctx.sigma = float(sigma)
+        return K.noise_clamp_fwd(x, noise, ctx.sigma)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, noise = ctx.saved_tensors
+        return K.noise_clamp_bwd(x, noise, _c(dy), ctx.sigma), None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -577,12 +639,13 @@ class GanDLossFn(Function):
     (training/gan/contrad.py:52-70).  The two means are logging values (non-differentiable here)."""
 
     @staticmethod
-    def forward(ctx, d_all, n, kind):
+    def forward(ctx, d_all, n, kind, gen_offset=None):
         d_all = _c(d_all)
         flat = d_all.view(-1)
-        out, g_r, g_g = K.gan_d_loss(flat[:n], flat[2 * n:3 * n], kind)
+        off = 2 * n if gen_offset is None else int(gen_offset)      # [N real | N real view 2 | N fake] by default
+        out, g_r, g_g = K.gan_d_loss(flat[:n], flat[off:off + n], kind)
         ctx.save_for_backward(g_r, g_g)
-        ctx.n, ctx.total = n, d_all.shape[0]
+        ctx.n, ctx.total, ctx.off = n, d_all.shape[0], off
         means = out[1:].clone()
         ctx.mark_non_differentiable(means)
         return out[0].clone(), means
@@ -593,8 +656,8 @@ class GanDLossFn(Function):
         n = ctx.n
         gd = torch.zeros(ctx.total, 1, device=g_r.device)
         gd[:n, 0] = g_r * gl
-        gd[2 * n:3 * n, 0] = g_g * gl
-        return gd, None, None
+        gd[ctx.off:ctx.off + n, 0] = g_g * gl
+        return gd, None, None, None
 
 
 class GanGLossFn(Function):

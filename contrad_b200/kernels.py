@@ -92,6 +92,34 @@ def augment_simclr_large_bwd(x, dy, params, order, means):
     return dx
 
 
+def augment_simclr_mixed_fwd(x_u8, n_u8_views, x_f32, params, order):
+    """Row f3: B = n_u8_views + len(x_f32) views in ONE launch; view b < n_u8_views reads uint8 image b % len(x_u8)
+    (ToTensor's / 255 inside the kernel), the others the fp32 images.  Returns (y [B,3,H,W], means [B,3])."""
+    params = _f32c(params, "params")
+    if x_u8 is not None:
+        if x_u8.dtype != torch.uint8:
+            raise TypeError("x_u8 must be uint8 (got %s)" % x_u8.dtype)
+        x_u8 = x_u8 if x_u8.is_contiguous() else x_u8.contiguous()
+    if x_f32 is not None:
+        x_f32 = _f32c(x_f32, "x_f32")
+    ref = x_u8 if x_u8 is not None else x_f32
+    n_u8 = 0 if x_u8 is None else x_u8.shape[0]
+    n_f32 = 0 if x_f32 is None else x_f32.shape[0]
+    _, C, H, W = ref.shape
+    if n_u8_views and not n_u8:
+        raise ValueError("n_u8_views = %d without uint8 images" % n_u8_views)
+    if x_u8 is not None and x_f32 is not None and tuple(x_u8.shape[1:]) != tuple(x_f32.shape[1:]):
+        raise ValueError("uint8 and fp32 images differ in shape: %s vs %s" % (tuple(x_u8.shape), tuple(x_f32.shape)))
+    B = n_u8_views + n_f32
+    assert C == 3 and params.shape == (len(PARAM_FIELDS) + (1 if order < 0 else 0), B), (ref.shape, params.shape, order)
+    y = torch.empty(B, 3, H, W, device=ref.device, dtype=torch.float32)
+    means = torch.empty(B, 3, device=ref.device, dtype=torch.float32)
+    nbytes = n_u8_views * 3 * H * W * 5 + n_f32 * 3 * H * W * 8
+    _call("augment_simclr_fwd", 0, nbytes, lib().cb200_augment_simclr_mixed_fwd, ptr(x_u8), i32(n_u8), i32(n_u8_views),
+          ptr(x_f32), ptr(y), ptr(params), ptr(means), i32(B), i32(H), i32(W), i32(order), stream_ptr())
+    return y, means
+
+
 def gaussian_blur(x, taps, on, adjoint=False):
     """x [B,C,H,W]; taps [k] normalised 1-D Gaussian (device); on [B] 0/1 mask.  y = on ? blur(x) : x (or its adjoint)."""
     x = _f32c(x, "x")
@@ -116,6 +144,44 @@ def cutout(x, params, length):
     _call("cutout", 0, 8 * x.numel(), lib().cb200_cutout, ptr(x), ptr(y), ptr(params), i32(B), i32(C), i32(H), i32(W), i32(length),
           stream_ptr())
     return y
+
+
+PADDING_MODES = {"zeros": 0, "border": 1, "reflection": 2}
+
+
+def shift_flip(x, params, padding_mode, adjoint=False):
+    """x [B,P,H,W]; params [3,B] = {sign, bias_x, bias_y}; nearest-neighbour mirror + translation (row f4).
+    adjoint=True applies the transpose (x = dy, returns dx)."""
+    x = _f32c(x, "x")
+    params = _f32c(params, "params")
+    B, P, H, W = x.shape
+    assert params.shape == (3, B), (params.shape, B)
+    mode = PADDING_MODES[padding_mode]
+    y = torch.empty_like(x)
+    fn = lib().cb200_shift_flip_bwd if adjoint else lib().cb200_shift_flip_fwd
+    _call("shift_flip", 0, 8 * x.numel(), fn, ptr(x), ptr(y), ptr(params), i32(B), i32(P), i32(H), i32(W), i32(mode),
+          stream_ptr())
+    return y
+
+
+def noise_clamp_fwd(x, noise, sigma):
+    x = _f32c(x, "x")
+    noise = _f32c(noise, "noise")
+    assert x.shape == noise.shape
+    y = torch.empty_like(x)
+    _call("noise_clamp", 0, 12 * x.numel(), lib().cb200_noise_clamp_fwd, ptr(x), ptr(noise), ptr(y), f32(sigma), i64(x.numel()),
+          stream_ptr())
+    return y
+
+
+def noise_clamp_bwd(x, noise, dy, sigma):
+    x = _f32c(x, "x")
+    noise = _f32c(noise, "noise")
+    dy = _f32c(dy, "dy")
+    dx = torch.empty_like(x)
+    _call("noise_clamp", 0, 16 * x.numel(), lib().cb200_noise_clamp_bwd, ptr(x), ptr(noise), ptr(dy), ptr(dx), f32(sigma),
+          i64(x.numel()), stream_ptr())
+    return dx
 
 
 # ------------------------------------------------------------------ tensor-core GEMM / conv

@@ -77,6 +77,13 @@ class TinyDiscriminator(nn.Module):
         self.l2 = SNLinear(d_hidden, 1, init=init)
 
 
+def projection(D, inputs):
+    """models/gan/base.py:73-76 (used by training/gan/simclr_only.py): the projection head's output; `d.mean() * 0`
+    keeps the unused linear head in the graph so that DDP finds a gradient for every parameter."""
+    d, aux = D(inputs, projection=True)
+    return aux["projection"] + d.mean() * 0
+
+
 class BaseDiscriminator(nn.Module, metaclass=ABCMeta):
     def __init__(self, d_penul, n_classes=1, d_hidden=128, d_project=128, mlp_linear=False, head_init="sndcgan"):
         super().__init__()

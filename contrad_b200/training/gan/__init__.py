@@ -1,4 +1,5 @@
-"""Mirror of training/gan/__init__.py:4-29 - the reference's training-mode plug-in boundary."""
+"""Mirror of training/gan/__init__.py:4-29 - the reference's training-mode plug-in boundary.  mode='contrad' is the hot
+path; the baselines (std / aug / aug_both / simclr_only) are thin compositions of the same kernels (row f4)."""
 from importlib import import_module
 
 _FILENAMES = {
@@ -13,10 +14,6 @@ _FILENAMES = {
 def setup(P):
     if P.mode not in _FILENAMES:
         raise NotImplementedError()
-    if P.mode != "contrad":
-        raise NotImplementedError(
-            "training mode %r is one of the paper's baselines and outside the ContraD hot path "
-            "(SURVEY 2.1: OUT OF SCOPE); contrad_b200 builds mode='contrad' only" % P.mode)
     mod = import_module(f".{P.mode}", __name__)
     P.filename = _FILENAMES[P.mode](P)
     P.train_fn = {"G": mod.loss_G_fn, "D": mod.loss_D_fn}

@@ -34,8 +34,15 @@ def loss_D_fn(P, D, options, images, gen_images):
     gen_images = gen_images.detach()
     n = images.size(0)
 
-    cat_images = torch.cat([images, images, gen_images], dim=0)
-    d_all, aux = D(P.augment_fn(cat_images), sg_linear=True, projection=True, projection2=True)
+    if images.dtype == torch.uint8:
+        # row f3: raw dataset bytes; ToTensor, the two-view duplication and the concatenation happen inside the kernel
+        if not hasattr(P.augment_fn, "forward_views"):
+            raise TypeError("uint8 images need a fused augmentation (simclr / simclr_hq / simclr_hq_cutout); "
+                            "got %s - convert with images.float().div(255) first" % type(P.augment_fn).__name__)
+        aug_images = P.augment_fn.forward_views(images, 2, gen_images)
+    else:
+        aug_images = P.augment_fn(torch.cat([images, images, gen_images], dim=0))
+    d_all, aux = D(aug_images, sg_linear=True, projection=True, projection2=True)
     views = RowNormalizeFn.apply(aux["projection"])
     reals = RowNormalizeFn.apply(aux["projection2"])
     if P.distributed:

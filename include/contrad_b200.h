@@ -59,6 +59,17 @@ int cb200_augment_simclr_large_fwd(const float* x, float* y, const float* params
 int cb200_augment_simclr_large_bwd(const float* x, const float* dy, float* dx, const float* params, const float* means,
                                    float* gsums, int B, int H, int W, int order, void* stream);
 
+/* Row f3: the dataset's `ToTensor` (datasets.py:10-21: uint8 HWC -> fp32 CHW / 255, here on NCHW bytes),
+ * the fp32 host->device copy of train_gan.py:153-154 and the `torch.cat([images, images, gen_images])` of
+ * training/gan/contrad.py:38-40 folded into the forward of the chain.  The launch produces B views; view b reads
+ *     b <  n_u8_views : the uint8 image (b mod n_u8) of x_u8 [n_u8,3,H,W]      (value / 255, correctly rounded)
+ *     b >= n_u8_views : the fp32 image (b - n_u8_views) of x_f32 [B - n_u8_views,3,H,W]
+ * params / order as above, over all B views.  means [B,3]: caller-allocated scratch, written on the any-size path
+ * (H, W other than 32x32 / 64x64) exactly like cb200_augment_simclr_large_fwd.  Gradients flow to the fp32 images
+ * only: call cb200_augment_simclr_bwd / _large_bwd on them with the parameter columns (and means rows) of their views. */
+int cb200_augment_simclr_mixed_fwd(const unsigned char* x_u8, int n_u8, int n_u8_views, const float* x_f32, float* y,
+                                   const float* params, float* means, int B, int H, int W, int order, void* stream);
+
 /* Tail of `simclr_hq` / `simclr_hq_cutout` (augment/__init__.py:52-78,115-133; augment/spatial.py:151-181):
  * gaussian_blur: y[b] = on[b] ? blur(x[b]) : x[b]; `taps` = the k normalised 1-D Gaussian weights (device memory; the
  *                reference's dense k x k outer-product kernel with 'reflect' padding, applied separably); `tmp` scratch
@@ -68,6 +79,23 @@ int cb200_augment_simclr_large_bwd(const float* x, const float* dy, float* dx, c
 int cb200_gaussian_blur(const float* x, float* tmp, float* y, const float* taps, const float* on, int B, int P, int H,
                         int W, int k, int adjoint, void* stream);
 int cb200_cutout(const float* x, float* y, const float* params, int B, int P, int H, int W, int length, void* stream);
+
+/* Row f4: light augmentations of the CR / bCR baselines (`--aug hfrt`, `gaussian`).
+ * shift_flip:  HorizontalFlipRandomCrop / RandomCrop (augment/spatial.py:14-67) = grid_sample(mode='nearest',
+ *              padding_mode, align_corners=False) on theta = [[sign, 0, bias_x], [0, 1, bias_y]].
+ *              params [3, B] = {sign (+-1), bias_x, bias_y} (bias = integer shift / (width / 2), as the reference draws
+ *              it); padding_mode 0 'zeros', 1 'border', 2 'reflection'; x, y [B,P,H,W].  bwd: dx = transposed gather of
+ *              dy (dx is cleared inside the call).
+ * noise_clamp: Gaussian (augment/__init__.py:40-49): y = clamp(x + noise * sigma, 0, 1) on n elements, `noise` drawn by
+ *              the caller (torch.randn_like keeps the reference's random stream); bwd: dx = dy where the sum is inside
+ *              [0, 1]. */
+int cb200_shift_flip_fwd(const float* x, float* y, const float* params, int B, int P, int H, int W, int padding_mode,
+                         void* stream);
+int cb200_shift_flip_bwd(const float* dy, float* dx, const float* params, int B, int P, int H, int W, int padding_mode,
+                         void* stream);
+int cb200_noise_clamp_fwd(const float* x, const float* noise, float* y, float sigma, long long n, void* stream);
+int cb200_noise_clamp_bwd(const float* x, const float* noise, const float* dy, float* dx, float sigma, long long n,
+                          void* stream);
 
 /* ---- tcgen05 tensor-core GEMM / implicit-GEMM convolutions (TF32 in, FP32 accumulate) --------
  * Replace F.linear / nn.Conv2d / nn.ConvTranspose2d behind models/gan/sndcgan.py:24-38,91-109 and

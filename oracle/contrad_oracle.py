@@ -318,6 +318,111 @@ def augment_simclr_hq(x, params, order, hq, cutout_length=None):
 # 2. Spectral norm + SNDCGAN discriminator / generator on explicit parameter dicts
 # --------------------------------------------------------------------------------------
 
+# ---- rows f3 / f4 of SURVEY 8f: uint8 input, hfrt / RandomCrop, Gaussian noise, baseline modes --------------------
+
+def to_tensor_u8(x_u8):
+    """The dataset transform `ToTensor` on NCHW bytes (datasets.py:10-21 -> torchvision to_tensor:
+    `img.to(float32).div(255)`)."""
+    return x_u8.to(torch.float32).div(255)
+
+
+def sample_shift_flip(batch, max_pixels=4, width=32, flip=True, device="cpu"):
+    """Random draws of HorizontalFlipRandomCrop (flip=True, augment/spatial.py:31-33) / RandomCrop (flip=False,
+    spatial.py:60-61) in the reference order.  Returns [3, B] = {sign, bias_x, bias_y}."""
+    params = torch.empty(3, batch, device=device)
+    if flip:
+        params[0] = torch.bernoulli(torch.ones(batch, device=device) * 0.5) * 2 - 1
+    else:
+        params[0] = 1.0
+    r_bias = torch.randint(-max_pixels, max_pixels + 1, (batch, 2), device=device).float() / (width / 2)
+    params[1:3] = r_bias.t()
+    return params
+
+
+def _nearest_index(g, size, padding_mode):
+    """grid_sample(mode='nearest', align_corners=False) index pipeline of one axis (ATen GridSampler.h:
+    grid_sampler_unnormalize -> clip / reflect -> nearbyint -> bounds check).  Returns (index, valid)."""
+    c = ((g + 1.0) * size - 1.0) / 2.0
+    if padding_mode == "border":
+        c = c.clamp(0.0, float(size) - 1.0)
+    elif padding_mode == "reflection":
+        c = _reflect(c, size)
+    elif padding_mode != "zeros":
+        raise ValueError(padding_mode)
+    r = torch.round(c)                      # round-half-even == nearbyint
+    valid = (r >= 0) & (r <= size - 1)
+    return r.clamp(0, size - 1).long(), valid
+
+
+def shift_flip(x, params, padding_mode="reflection"):
+    """HorizontalFlipRandomCrop.forward / RandomCrop.forward on explicit draws (augment/spatial.py:25-40,54-67):
+    theta = [[sign, 0, bias_x], [0, 1, bias_y]], affine_grid + nearest grid_sample, restated as an index gather."""
+    B, C, H, W = x.shape
+    sign, bx, by = params[0], params[1], params[2]
+    j = torch.arange(W, dtype=torch.float32, device=x.device)
+    i = torch.arange(H, dtype=torch.float32, device=x.device)
+    gx = sign.view(B, 1) * ((2.0 * j + 1.0) / W - 1.0).view(1, W) + bx.view(B, 1)
+    gy = ((2.0 * i + 1.0) / H - 1.0).view(1, H) + by.view(B, 1)
+    xi, xv = _nearest_index(gx, W, padding_mode)        # [B, W]
+    yi, yv = _nearest_index(gy, H, padding_mode)        # [B, H]
+    rows = torch.gather(x, 2, yi.view(B, 1, H, 1).expand(B, C, H, W))
+    out = torch.gather(rows, 3, xi.view(B, 1, 1, W).expand(B, C, H, W))
+    mask = (yv.view(B, 1, H, 1) & xv.view(B, 1, 1, W)).to(x.dtype)
+    return out * mask
+
+
+def gaussian_noise(x, noise, sigma):
+    """Gaussian.forward on an explicit noise draw (augment/__init__.py:46-49)."""
+    return (x + noise * sigma).clamp(0, 1)
+
+
+def penalty_cr(sd_d, d_real, images, aug, lbd, training=True):
+    """penalty.consistency (penalty.py:47-49) with `aug` = the augmentation on explicit draws."""
+    d_aug, _ = d_sndcgan_forward(sd_d, aug(images), training=training)
+    return lbd * ((d_real - d_aug) ** 2).mean()
+
+
+def penalty_bcr(sd_d, d_real, d_gen, all_images, aug, lbd, lbd2, training=True):
+    """penalty.balanced_consistency (penalty.py:52-60)."""
+    d_aug_all, _ = d_sndcgan_forward(sd_d, aug(all_images), training=training)
+    n = all_images.shape[0] // 2
+    return lbd * ((d_real - d_aug_all[:n]) ** 2).mean() + lbd2 * ((d_gen - d_aug_all[n:]) ** 2).mean()
+
+
+def loss_d_baseline(sd_d, mode, images, gen_images, augs, loss="nonsat", penalty="none", lbd=10.0, lbd2=10.0,
+                    training=True):
+    """training/gan/{std,aug,aug_both}.py loss_D_fn.  `augs` is the list of augmentation callables (explicit draws)
+    in call order: the mode's own `P.augment_fn` call first (aug / aug_both), then the penalty's.
+    Returns (d_loss, penalty, d_real.mean(), d_gen.mean()).  NOTE: in train mode every D forward advances the
+    spectral-norm power iteration in `sd_d` (as the reference's hooks do)."""
+    augs = list(augs)
+    gen_images = gen_images.detach()
+    n = images.shape[0]
+    if mode == "std":                                   # std.py:11-13
+        all_images = torch.cat([images, gen_images], dim=0)
+        d_inputs = all_images
+    elif mode == "aug":                                 # aug.py:11-13
+        all_images = torch.cat([augs.pop(0)(images), gen_images], dim=0)
+        d_inputs = all_images
+    elif mode == "aug_both":                            # aug_both.py:12-14
+        all_images = torch.cat([images, gen_images], dim=0)
+        d_inputs = augs.pop(0)(all_images)
+    else:
+        raise NotImplementedError(mode)
+    d_all, _ = d_sndcgan_forward(sd_d, d_inputs, training=training)
+    d_real, d_gen = d_all[:n], d_all[n:]
+    d_loss = gan_d_loss(d_real, d_gen, loss)
+    if penalty == "none":
+        pen = torch.zeros(1)
+    elif penalty == "cr":
+        pen = penalty_cr(sd_d, d_real, images, augs.pop(0), lbd, training)
+    elif penalty == "bcr":
+        pen = penalty_bcr(sd_d, d_real, d_gen, all_images, augs.pop(0), lbd, lbd2, training)
+    else:
+        raise NotImplementedError(penalty)
+    return d_loss, pen, d_real.mean(), d_gen.mean()
+
+
 def _l2normalize(v, eps=1e-12):
     return v / v.norm().clamp_min(eps)
 

@@ -272,13 +272,129 @@ def gen_snresnet18():
     print("snresnet18: d[0]=%.6f" % float(d[0]))
 
 
+def gen_augment_aux(gin):
+    """Rows f3 / f4: HorizontalFlipRandomCrop ('hfrt'), RandomCrop (all three padding modes), Gaussian noise through the
+    reference classes; the explicit draws come from replaying the seed with the oracle's samplers (agreement of the
+    OUTPUTS pins them).  The uint8 case stores bytes and the reference chain applied to ToTensor(bytes)."""
+    from augment import get_augment
+    from augment.spatial import HorizontalFlipRandomCrop, RandomCrop
+    from augment import Gaussian
+    cases = []
+    specs = [("hfrt", 6, 32, 32, 4, 32, "reflection"), ("hfrt", 5, 32, 32, 4, 32, "zeros"),
+             ("hfrt", 5, 32, 32, 6, 32, "border"), ("crop", 4, 32, 32, 4, 32, "reflection"),
+             ("hfrt", 3, 64, 64, 4, 32, "reflection"), ("hfrt", 3, 20, 28, 5, 28, "reflection"),
+             ("hfrt", 3, 20, 28, 5, 28, "zeros")]
+    for k, (kind, batch, h, w, max_pixels, width, pad) in enumerate(specs):
+        seed = 300 + k
+        cls = HorizontalFlipRandomCrop if kind == "hfrt" else RandomCrop
+        layer = cls(max_pixels=max_pixels, width=width, padding_mode=pad)
+        seed_all(seed)
+        x = torch.rand(batch, 3, h, w)
+        dy = torch.randn(batch, 3, h, w)
+        params = O.sample_shift_flip(batch, max_pixels, width, flip=(kind == "hfrt"))
+        seed_all(seed)
+        x_ref = torch.rand(batch, 3, h, w)
+        _ = torch.randn(batch, 3, h, w)
+        x_ref.requires_grad_(True)
+        y_ref = layer(x_ref)
+        (y_ref * dy).sum().backward()
+        cases.append({"kind": kind, "seed": seed, "max_pixels": max_pixels, "width": width, "padding_mode": pad,
+                      "x": t2l(x), "dy": t2l(dy), "params": t2l(params), "y": t2l(y_ref), "dx": t2l(x_ref.grad)})
+        print("shift_flip case %s B=%d %dx%d pad=%s" % (kind, batch, h, w, pad))
+    noise_cases = []
+    for k, (batch, size, sigma) in enumerate(((4, 32, 0.12), (2, 30, 0.5))):
+        seed = 320 + k
+        seed_all(seed)
+        x = torch.rand(batch, 3, size, size)
+        dy = torch.randn(batch, 3, size, size)
+        noise = torch.randn(batch, 3, size, size)
+        seed_all(seed)
+        x_ref = torch.rand(batch, 3, size, size)
+        _ = torch.randn(batch, 3, size, size)
+        x_ref.requires_grad_(True)
+        y_ref = Gaussian(sigma=sigma)(x_ref)
+        (y_ref * dy).sum().backward()
+        noise_cases.append({"seed": seed, "sigma": sigma, "x": t2l(x), "dy": t2l(dy), "noise": t2l(noise),
+                            "y": t2l(y_ref), "dx": t2l(x_ref.grad)})
+    # uint8 input (row f3): reference = simclr()(cat([ToTensor(bytes)] * 2 + [fakes]))
+    u8_cases = []
+    for k, (n, m, size) in enumerate(((4, 4, 32), (2, 3, 64), (2, 2, 48))):
+        seed = 340 + k
+        gen = torch.Generator().manual_seed(seed)
+        x_u8 = torch.randint(0, 256, (n, 3, size, size), generator=gen, dtype=torch.uint8)
+        fakes = torch.rand(m, 3, size, size, generator=gen)
+        dy = torch.randn(2 * n + m, 3, size, size, generator=gen)
+        seed_all(seed)
+        params, order = O.sample_simclr_params(2 * n + m, size, size)
+        aug = get_augment(mode="simclr")
+        seed_all(seed)
+        fk = fakes.clone().requires_grad_(True)
+        x_f = x_u8.to(torch.float32).div(255)
+        y_ref = aug(torch.cat([x_f, x_f, fk], dim=0))
+        (y_ref * dy).sum().backward()
+        u8_cases.append({"seed": seed, "x_u8": x_u8, "fakes": t2l(fakes), "dy": dy, "params": O.pack_params(params),
+                         "order": order, "y": t2l(y_ref), "d_fakes": t2l(fk.grad)})
+        print("uint8 case n=%d m=%d size=%d order=%d" % (n, m, size, order))
+    torch.save({"shift_flip": cases, "noise": noise_cases, "uint8": u8_cases}, os.path.join(HERE, "augment_aux.pt"))
+
+
+def gen_baselines(gin):
+    """training/gan/{std,aug,aug_both}.py with penalty none / cr / bcr and `--aug hfrt`, and simclr_only, through the
+    reference modules at reduced width (ndf=4, d_hidden=16): losses, penalty and the D gradient norms."""
+    from augment import get_augment
+    from models.gan.sndcgan import D_SNDCGAN
+    from importlib import import_module
+    out = []
+    combos = [("std", "none", "nonsat"), ("std", "cr", "hinge"), ("std", "bcr", "nonsat"), ("aug", "none", "lsgan"),
+              ("aug_both", "bcr", "wgan"), ("aug", "cr", "nonsat")]
+    for k, (mode, penalty, loss_kind) in enumerate(combos):
+        seed = 400 + k
+        seed_all(seed)
+        D = D_SNDCGAN(image_size=(32, 32, 3), ndf=4, mlp_linear=True, d_hidden=16)
+        D.train()
+        sd_d0 = {kk: t2l(v) for kk, v in D.state_dict().items()}
+        n = 4
+        P = SimpleNamespace(augment_fn=get_augment(mode="hfrt"), temp=0.1, lbd_a=1.0, distributed=False, penalty=penalty)
+        options = {"loss": loss_kind, "lbd": 10.0, "lbd2": 5.0}
+        mod = import_module("training.gan.%s" % mode)
+        seed_all(seed + 50)
+        images = torch.rand(n, 3, 32, 32)
+        gen = torch.rand(n, 3, 32, 32)
+        d_loss, aux = mod.loss_D_fn(P, D, options, images, gen)
+        (d_loss + aux["penalty"]).backward()
+        rec = {"mode": mode, "penalty": penalty, "loss": loss_kind, "lbd": 10.0, "lbd2": 5.0, "sd_d": sd_d0,
+               "images": t2l(images), "gen": t2l(gen), "d_loss": float(d_loss), "pen": float(aux["penalty"]),
+               "d_real": float(aux["d_real"]), "d_gen": float(aux["d_gen"]), "grad_norms": _grad_norms(D)}
+        # explicit draws: replay the stream (one hfrt call per P.augment_fn call, in call order)
+        seed_all(seed + 50)
+        _ = torch.rand(n, 3, 32, 32); _ = torch.rand(n, 3, 32, 32)
+        calls = []
+        if mode == "aug":
+            calls.append(n)
+        elif mode == "aug_both":
+            calls.append(2 * n)
+        if penalty == "cr":
+            calls.append(n)
+        elif penalty == "bcr":
+            calls.append(2 * n)
+        rec["aug_params"] = [O.sample_shift_flip(b, 4, 32, flip=True) for b in calls]
+        g_loss = mod.loss_G_fn(P, D, options, images, gen)
+        rec["g_loss"] = float(g_loss)
+        if mode == "aug_both":
+            rec["aug_params_g"] = None      # drawn after the D step; the G loss is checked by its own seed below
+        out.append(rec)
+        print("baseline %s/%s/%s: d_loss=%.6f pen=%.6f" % (mode, penalty, loss_kind, rec["d_loss"], rec["pen"]))
+    torch.save({"cases": out}, os.path.join(HERE, "baseline_modes.pt"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gin = ref_import.activate()
-    todo = args.only.split(",") if args.only else ["augment", "augment_hq", "contrastive", "sn", "small", "config1", "snresnet18"]
+    todo = args.only.split(",") if args.only else ["augment", "augment_hq", "contrastive", "sn", "small", "config1", "snresnet18",
+                                                     "augment_aux", "baselines"]
     if "augment" in todo:
         gen_augment(gin)
     if "augment_hq" in todo:
@@ -293,6 +409,10 @@ def main():
         gen_small_models(gin)
     if "config1" in todo:
         gen_config1(gin)
+    if "augment_aux" in todo:
+        gen_augment_aux(gin)
+    if "baselines" in todo:
+        gen_baselines(gin)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,202 @@
+"""GPU parity of the rows added after the round's GPU budget was spent (f3 uint8 input, f4 hfrt / RandomCrop /
+Gaussian + the CR / bCR baseline modes).  The kernels cross-compile for sm_100a and their host logic and index arithmetic
+are covered on CPU (tests/test_host_logic.py), but they have NOT run on hardware yet: until one hardware run has been
+looked at, a failure here is reported as `xfailed` (and a pass as `XPASS`) instead of stopping the verified suite.  The
+file name sorts last so that a faulting kernel cannot poison the CUDA context of the verified tests."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import contrad_oracle as O
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(strict=False, reason="kernels of rows f3/f4 written without GPU access (round-1 budget "
+                                                     "exhausted); first hardware run pending")]
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _unpack(packed):
+    return {k: packed[i] for i, k in enumerate(O.PARAM_FIELDS)}
+
+
+@pytest.fixture(scope="module")
+def gin_defaults():
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    compat = os.path.join(repo, "contrad_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import gin
+    gin.clear_config()
+    gin.parse_config("""
+ColorJitterLayer.brightness = 0.4
+ColorJitterLayer.contrast = 0.4
+ColorJitterLayer.saturation = 0.4
+ColorJitterLayer.hue = 0.1
+RandomResizeCropLayer.scale = (0.2, 1.0)
+HorizontalFlipRandomCrop.max_pixels = 4
+HorizontalFlipRandomCrop.width = 32
+HorizontalFlipRandomCrop.padding_mode = "reflection"
+Gaussian.sigma = 0.12
+""")
+    return gin
+
+
+# ------------------------------------------------------------------------------------------------ row f3: uint8 input
+def test_mixed_fwd_matches_reference_fixtures(golden_dir):
+    """cb200_augment_simclr_mixed_fwd on the stored bytes / fakes / draws vs the reference chain on
+    cat[ToTensor(x), ToTensor(x), fakes] (32x32 and 64x64: shared-memory path; 48x48: any-size path)."""
+    from contrad_b200.functional import AugmentSimCLRMixedFn
+    for case in _load(golden_dir, "augment_aux.pt")["uint8"]:
+        n = case["x_u8"].shape[0]
+        fakes = case["fakes"].cuda().requires_grad_(True)
+        y = AugmentSimCLRMixedFn.apply(case["x_u8"].cuda(), 2 * n, fakes, case["params"].cuda(), case["order"])
+        assert torch.allclose(y.cpu(), case["y"], atol=2e-5, rtol=0), float((y.cpu() - case["y"]).abs().max())
+        (y * case["dy"].cuda()).sum().backward()
+        assert torch.allclose(fakes.grad.cpu(), case["d_fakes"], atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("size,n,m", [(32, 512, 512), (64, 40, 24), (48, 6, 5), (96, 3, 2), (32, 7, 0), (32, 0, 9)])
+def test_mixed_fwd_equals_fp32_kernel_on_converted_batch(size, n, m):
+    """Same arithmetic, different source type: the mixed-source launch must equal the verified fp32 kernels on
+    cat[x/255, x/255, fakes] BIT FOR BIT (the byte -> float table holds correctly rounded k/255), including at the
+    benchmark batch (3 x 512 views)."""
+    from contrad_b200 import kernels as K
+    g = torch.Generator().manual_seed(size + n)
+    x_u8 = torch.randint(0, 256, (max(n, 1), 3, size, size), generator=g, dtype=torch.uint8).cuda()
+    fakes = torch.rand(m, 3, size, size, generator=g).cuda() if m else None
+    total = 2 * n + m
+    np.random.seed(size); torch.manual_seed(size)
+    params, order = O.sample_simclr_params(total, size, size)
+    packed = O.pack_params(params).cuda()
+    y, means = K.augment_simclr_mixed_fwd(x_u8 if n else None, 2 * n, fakes, packed, order)
+    parts = ([x_u8.float().div(255)] * 2 if n else []) + ([fakes] if m else [])
+    cat = torch.cat(parts, dim=0)
+    if K.augment_needs_large_path(size, size) or size not in (32, 64):
+        want, means_ref = K.augment_simclr_large_fwd(cat, packed, order)
+        assert torch.allclose(means, means_ref, rtol=1e-6, atol=1e-7)          # atomics order
+        assert torch.allclose(y, want, rtol=0, atol=1e-6)
+    else:
+        want = K.augment_simclr_fwd(cat, packed, order)
+        assert torch.equal(y, want), float((y - want).abs().max())
+    assert torch.isfinite(y).all() and float(y.min()) >= 0.0 and float(y.max()) <= 1.0
+
+
+def test_forward_views_and_loss_d_fn_with_uint8_images(gin_defaults):
+    """Public surface: loss_D_fn(P, D, options, uint8 images, gen) == loss_D_fn on ToTensor(images) with the same seed."""
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import contrad
+    gen_w = torch.Generator().manual_seed(5)
+    _, D = get_architecture("sndcgan", (32, 32, 3))
+    D.load_state_dict(O.make_d_state(generator=gen_w))
+    D.cuda().train()
+    uv = {k: v.clone() for k, v in D.state_dict().items() if k.endswith(("weight_u", "weight_v"))}
+    x_u8 = torch.randint(0, 256, (16, 3, 32, 32), generator=gen_w, dtype=torch.uint8).cuda()
+    gen = torch.rand(16, 3, 32, 32, generator=gen_w).cuda()
+    P = SimpleNamespace(augment_fn=get_augment("simclr"), temp=0.1, lbd_a=1.0, distributed=False)
+    got = []
+    for images in (x_u8, x_u8.float().div(255)):
+        D.load_state_dict(uv, strict=False)                  # same power-iteration start for both calls
+        np.random.seed(2); torch.manual_seed(2)
+        loss, aux = contrad.loss_D_fn(P, D, {"loss": "hinge"}, images, gen)
+        got.append([float(loss), float(aux["penalty"]), float(aux["d_real"]), float(aux["d_gen"])])
+    assert got[0] == pytest.approx(got[1], rel=1e-6, abs=1e-6), got
+
+
+# ------------------------------------------------------------------------------------ row f4: hfrt / RandomCrop / noise
+def test_shift_flip_matches_reference_fixtures(golden_dir):
+    from contrad_b200.functional import ShiftFlipFn
+    for case in _load(golden_dir, "augment_aux.pt")["shift_flip"]:
+        x = case["x"].cuda().requires_grad_(True)
+        y = ShiftFlipFn.apply(x, case["params"].cuda(), case["padding_mode"])
+        assert torch.equal(y.cpu(), case["y"]), (case["kind"], case["padding_mode"])
+        (y * case["dy"].cuda()).sum().backward()
+        assert torch.allclose(x.grad.cpu(), case["dx"], atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("shape,pad", [((1536, 3, 32, 32), "reflection"), ((16, 3, 512, 512), "reflection"),
+                                       ((5, 3, 30, 34), "border"), ((5, 1, 7, 9), "zeros")])
+def test_shift_flip_vs_oracle_and_adjoint_identity(shape, pad):
+    """Benchmark batch and 512x512: the gather equals the oracle's index map exactly, and <A x, y> == <x, A^T y>."""
+    from contrad_b200 import kernels as K
+    b, _, h, w = shape
+    torch.manual_seed(b)
+    x = torch.rand(*shape)
+    params = O.sample_shift_flip(b, 4, w, flip=True)
+    y = K.shift_flip(x.cuda(), params.cuda(), pad)
+    assert torch.equal(y.cpu(), O.shift_flip(x, params, pad))
+    dy = torch.randn(*shape)
+    dx = K.shift_flip(dy.cuda(), params.cuda(), pad, adjoint=True)
+    lhs = float((y.double().cpu() * dy.double()).sum())
+    rhs = float((x.double() * dx.double().cpu()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(1.0, abs(lhs))
+
+
+def test_gaussian_noise_matches_reference_fixtures(golden_dir):
+    from contrad_b200.functional import NoiseClampFn
+    for case in _load(golden_dir, "augment_aux.pt")["noise"]:
+        x = case["x"].cuda().requires_grad_(True)
+        y = NoiseClampFn.apply(x, case["noise"].cuda(), case["sigma"])
+        assert torch.equal(y.cpu(), case["y"])
+        (y * case["dy"].cuda()).sum().backward()
+        assert torch.equal(x.grad.cpu(), case["dx"])
+
+
+def test_layers_draw_on_device_and_run(gin_defaults):
+    """get_augment('hfrt') / ('gaussian') end to end on the device: outputs are permutations / clamped sums of the input."""
+    from contrad_b200.augment import get_augment
+    x = torch.rand(64, 3, 32, 32, device="cuda", requires_grad=True)
+    y = get_augment("hfrt")(x)
+    assert y.shape == x.shape and float(y.min()) >= float(x.min()) and float(y.max()) <= float(x.max())
+    y.sum().backward()
+    assert abs(float(x.grad.sum()) - x.numel()) < 1e-2 * x.numel() ** 0.5 + 1.0       # reflection: every output has one source
+    z = get_augment("gaussian")(x.detach())
+    assert float(z.min()) >= 0.0 and float(z.max()) <= 1.0 and float((z - x.detach()).abs().mean()) > 0.01
+
+
+@pytest.mark.parametrize("mode,penalty,loss_kind", [("std", "none", "nonsat"), ("std", "bcr", "hinge"), ("aug", "cr", "lsgan"),
+                                                    ("aug_both", "bcr", "wgan")])
+def test_baseline_modes_vs_oracle(gin_defaults, mode, penalty, loss_kind):
+    """training/gan/{std,aug,aug_both}.py + cr / bcr under --aug hfrt on the full-width SNDCGAN D: losses, penalty and the
+    total D gradient norm against the fp32 CPU oracle on identical weights and draws (TF32 path: 1e-3 / 5e-3)."""
+    from contrad_b200.augment import get_augment
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import setup
+    from contrad_b200 import engine
+    n = 8
+    sd_d = O.make_d_state(generator=torch.Generator().manual_seed(31))
+    _, D = get_architecture("sndcgan", (32, 32, 3))
+    D.load_state_dict(sd_d)
+    D.cuda().train()
+    engine.set_grad(D, True)
+    P = setup(SimpleNamespace(mode=mode, aug="hfrt", penalty=penalty, temp=0.1, lbd_a=1.0, distributed=False))
+    P.augment_fn = get_augment("hfrt")
+    options = {"loss": loss_kind, "lbd": 10.0, "lbd2": 5.0}
+    torch.manual_seed(17)
+    images, gen = torch.rand(n, 3, 32, 32), torch.rand(n, 3, 32, 32)
+    calls = ([n] if mode == "aug" else [2 * n] if mode == "aug_both" else []) + \
+            ([n] if penalty == "cr" else [2 * n] if penalty == "bcr" else [])
+    torch.manual_seed(23)                               # the product draws on the device: replay with a device generator
+    draws = [O.sample_shift_flip(b, 4, 32, flip=True, device="cuda").cpu() for b in calls]
+    torch.manual_seed(23)
+    d_loss, aux = P.train_fn["D"](P, D, options, images.cuda(), gen.cuda())
+    (d_loss + aux["penalty"]).sum().backward()
+    sd_o = {k: v.clone() for k, v in sd_d.items()}
+    O.set_requires_grad(sd_o, True)
+    augs = [(lambda p: (lambda t: O.shift_flip(t, p, "reflection")))(p) for p in draws]
+    d_loss_o, pen_o, d_real_o, d_gen_o = O.loss_d_baseline(sd_o, mode, images, gen, augs, loss=loss_kind, penalty=penalty,
+                                                          lbd=10.0, lbd2=5.0)
+    (d_loss_o + pen_o.sum()).backward()
+    assert abs(float(d_loss) - float(d_loss_o)) < 1e-3 * max(1.0, abs(float(d_loss_o)))
+    assert abs(float(aux["penalty"]) - float(pen_o)) < 1e-2 * abs(float(pen_o)) + 1e-5
+    assert abs(float(aux["d_real"]) - float(d_real_o)) < 1e-3 and abs(float(aux["d_gen"]) - float(d_gen_o)) < 1e-3
+    tot_o = O.grad_norm(sd_o)
+    tot = float(engine.grad_norm(D))
+    assert abs(tot - tot_o) < 5e-3 * tot_o, (tot, tot_o)

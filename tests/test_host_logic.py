@@ -99,8 +99,13 @@ def test_module_surfaces_match_reference():
     assert D.d_penul == 8192 and hasattr(D, "penultimate") and hasattr(D, "reset_parameters")
     P = setup(SimpleNamespace(mode="contrad", aug="simclr", lbd_a=1.0, temp=0.1, penalty="none"))
     assert P.filename == "contrad_simclr_L1.0_T0.1" and set(P.train_fn) == {"G", "D"}
+    for mode, pen, aug, name in (("std", "none", "none", "std_none"), ("std", "bcr", "hfrt", "std_bcr_hfrt"),
+                                 ("aug", "cr", "hfrt", "aug_hfrt_cr"), ("aug_both", "none", "simclr", "aug_both_simclr_none"),
+                                 ("simclr_only", "none", "simclr", "simclr_only_simclr_T0.1")):
+        Pb = setup(SimpleNamespace(mode=mode, aug=aug, penalty=pen, temp=0.1, lbd_a=1.0))
+        assert Pb.filename == name and set(Pb.train_fn) == {"G", "D"}          # training/gan/__init__.py:9-20
     with pytest.raises(NotImplementedError):
-        setup(SimpleNamespace(mode="std", aug="none", penalty="none", temp=0.1, lbd_a=1.0))
+        setup(SimpleNamespace(mode="no_such_mode", aug="none", penalty="none", temp=0.1, lbd_a=1.0))
     with pytest.raises(NotImplementedError):
         get_architecture("biggan", (32, 32, 3))
     G3, D3 = get_architecture("snresnet18", (32, 32, 3))
@@ -303,3 +308,189 @@ def test_staging_late_entries_are_produced_at_upload_time():
     assert state["t"] == 1
     rec.upload()
     assert state["t"] == 2 and float(buf) == 2.0
+
+
+def test_shift_flip_index_function_compiled_for_host_matches_oracle(tmp_path):
+    """The index arithmetic of cb200_shift_flip_* (csrc/augment_aux.cu: nearest_source) is plain C: compile that function
+    with g++ and compare the source tables it produces with the oracle's (which is pinned bit-exactly on the reference's
+    affine_grid + nearest grid_sample) for every padding mode, odd sizes and shifts beyond the image."""
+    import ctypes
+    import subprocess
+    src = open(os.path.join(REPO, "contrad_b200", "csrc", "augment_aux.cu")).read()
+    body = src[src.index("// [host-testable: nearest_source]"):src.index("// [host-testable: end]")]
+    cpp = tmp_path / "nearest.cpp"
+    cpp.write_text("#include <math.h>\n#define __device__\n#define __forceinline__ inline\n"
+                   "enum PadMode { kZeros = 0, kBorder = 1, kReflection = 2 };\n" + body +
+                   'extern "C" void table(float sign, float bias, int n, int pad, int* out) {\n'
+                   "  for (int e = 0; e < n; ++e) { float base = (2.f * (float)e + 1.f) / (float)n - 1.f;\n"
+                   "    out[e] = nearest_source(sign * base + bias, n, pad); } }\n")
+    so = tmp_path / "nearest.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    rng = np.random.RandomState(0)
+    checked = 0
+    for pad_id, pad in enumerate(("zeros", "border", "reflection")):
+        for n in (4, 20, 28, 32, 33, 64, 512):
+            for _ in range(12):
+                sign = float(rng.choice([-1.0, 1.0]))
+                shift = int(rng.randint(-n - 3, n + 4))
+                bias = np.float32(shift) / np.float32(n / 2)
+                out = (ctypes.c_int * n)()
+                lib.table(ctypes.c_float(sign), ctypes.c_float(bias), n, pad_id, out)
+                g = torch.tensor(sign) * ((2.0 * torch.arange(n, dtype=torch.float32) + 1.0) / n - 1.0) + torch.tensor(bias)
+                idx, valid = O._nearest_index(g, n, pad)
+                want = torch.where(valid, idx, torch.full_like(idx, -1)).tolist()
+                assert list(out) == want, (pad, n, sign, shift)
+                checked += 1
+    assert checked == 3 * 7 * 12
+
+
+def _load_fx(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_forward_views_uint8_host_logic(golden_dir):
+    """Row f3: FusedSimCLR.forward_views(bytes, 2, fakes) draws the parameters of all 2n + m views in the reference's
+    order (same seed -> the views the reference produces for cat[ToTensor(x), ToTensor(x), fakes]) and routes the
+    gradient to the fp32 images only.  Kernel bindings replaced by the oracle stand-ins."""
+    import tests.cpu_augment_standins as AS
+    _gin_defaults()
+    from contrad_b200.augment import get_augment
+    aug = get_augment("simclr")
+    fx = _load_fx(golden_dir, "augment_aux.pt")
+    with AS.patched():
+        for case in fx["uint8"]:
+            np.random.seed(case["seed"]); torch.manual_seed(case["seed"])
+            fakes = case["fakes"].clone().requires_grad_(True)
+            y = aug.forward_views(case["x_u8"], 2, fakes)
+            assert torch.allclose(y, case["y"], atol=2e-5, rtol=0), (y - case["y"]).abs().max()
+            (y * case["dy"]).sum().backward()
+            assert torch.allclose(fakes.grad, case["d_fakes"], atol=5e-5, rtol=1e-5)
+        # only fp32 views: same as the ordinary call; only uint8 views: no gradient anywhere
+        case = fx["uint8"][0]
+        np.random.seed(1); torch.manual_seed(1)
+        y1 = aug.forward_views(case["x_u8"], 1, None)
+        np.random.seed(1); torch.manual_seed(1)
+        y2 = aug(O.to_tensor_u8(case["x_u8"]))
+        assert torch.equal(y1, y2) and not y1.requires_grad
+    with pytest.raises(ValueError):
+        aug.forward_views(case["fakes"], 2, None)            # not uint8
+    with pytest.raises(ValueError):
+        aug.forward_views(case["x_u8"], 2, case["fakes"][:, :, :16])
+
+
+def test_loss_d_fn_accepts_uint8_images(golden_dir):
+    """training/gan/contrad.py:35-70 with raw uint8 images == the same call on ToTensor(images) (same seed)."""
+    import tests.cpu_augment_standins as AS
+    import tests.cpu_loss_standins as LS
+    from types import SimpleNamespace
+    _gin_defaults()
+    from contrad_b200.augment import get_augment
+    from contrad_b200.training.gan import contrad
+    fxs = _load_fx(golden_dir, "sndcgan_small.pt")["nonsat"]
+    sd = {k: v.clone() for k, v in fxs["sd_d"].items()}
+
+    class OracleD(torch.nn.Module):
+        def forward(self, x, sg_linear=False, projection=False, projection2=False):
+            local = {k: v.clone() for k, v in sd.items()}
+            d, aux = O.d_sndcgan_forward(local, x, sg_linear=sg_linear)
+            return d, aux
+
+    x_u8 = torch.randint(0, 256, (4, 3, 32, 32), generator=torch.Generator().manual_seed(3), dtype=torch.uint8)
+    gen = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+    P = SimpleNamespace(augment_fn=get_augment("simclr"), temp=0.1, lbd_a=1.0, distributed=False)
+    out = []
+    with AS.patched(), LS.patched():
+        for images in (x_u8, O.to_tensor_u8(x_u8)):
+            np.random.seed(9); torch.manual_seed(9)
+            loss, aux = contrad.loss_D_fn(P, OracleD(), {"loss": "nonsat"}, images, gen)
+            out.append((float(loss), float(aux["penalty"]), float(aux["d_real"]), float(aux["d_gen"])))
+        assert out[0] == pytest.approx(out[1], rel=1e-6, abs=1e-7)
+        P2 = SimpleNamespace(augment_fn=get_augment("hflip"), temp=0.1, lbd_a=1.0, distributed=False)
+        with pytest.raises(TypeError):
+            contrad.loss_D_fn(P2, OracleD(), {"loss": "nonsat"}, x_u8, gen)
+
+
+def test_shift_flip_and_gaussian_layers_replay_reference_stream(golden_dir):
+    """Row f4: the product's HorizontalFlipRandomCrop / RandomCrop / Gaussian layers draw in the reference order (same
+    seed -> the stored reference outputs); kernels replaced by the oracle stand-ins."""
+    import tests.cpu_augment_standins as AS
+    from contrad_b200.augment.layers import Gaussian, HorizontalFlipRandomCrop, RandomCrop
+    fx = _load_fx(golden_dir, "augment_aux.pt")
+    with AS.patched():
+        for case in fx["shift_flip"]:
+            cls = HorizontalFlipRandomCrop if case["kind"] == "hfrt" else RandomCrop
+            layer = cls(max_pixels=case["max_pixels"], width=case["width"], padding_mode=case["padding_mode"])
+            assert set(layer.state_dict()) == {"_eye"}
+            np.random.seed(case["seed"]); torch.manual_seed(case["seed"])
+            x = torch.rand_like(case["x"]); _ = torch.randn_like(case["x"])
+            x.requires_grad_(True)
+            y = layer(x)
+            assert torch.equal(y, case["y"])
+            (y * case["dy"]).sum().backward()
+            assert torch.allclose(x.grad, case["dx"], atol=1e-6, rtol=1e-6)
+        for case in fx["noise"]:
+            np.random.seed(case["seed"]); torch.manual_seed(case["seed"])
+            x = torch.rand_like(case["x"]); _ = torch.randn_like(case["x"])
+            x.requires_grad_(True)
+            y = Gaussian(sigma=case["sigma"])(x)
+            assert torch.equal(y, case["y"])
+            (y * case["dy"]).sum().backward()
+            assert torch.equal(x.grad, case["dx"])
+    with pytest.raises(ValueError):
+        RandomCrop(max_pixels=4, width=32, padding_mode="circular")
+
+
+def test_baseline_training_modes_host_logic(golden_dir):
+    """training/gan/{std,aug,aug_both}.py + penalty cr / bcr under --aug hfrt: the product's mode modules reproduce the
+    reference's scalars and D gradient norms when the discriminator and the kernels are oracle stand-ins (checks the
+    wiring: which tensors are augmented, what the penalty sees, RNG order, the generalised GAN-loss offsets)."""
+    import tests.cpu_augment_standins as AS
+    from types import SimpleNamespace
+    gin = _gin_defaults()
+    gin.parse_config("""
+HorizontalFlipRandomCrop.max_pixels = 4
+HorizontalFlipRandomCrop.width = 32
+HorizontalFlipRandomCrop.padding_mode = "reflection"
+""")
+    from contrad_b200.augment import get_augment
+    from contrad_b200.training.gan import setup
+    fx = _load_fx(golden_dir, "baseline_modes.pt")
+
+    class OracleD(torch.nn.Module):
+        def __init__(self, sd):
+            super().__init__()
+            self.sd = {k: v.clone() for k, v in sd.items()}
+            for k in O.trainable(self.sd):
+                self.sd[k].requires_grad_(True)
+
+        def forward(self, x):
+            return O.d_sndcgan_forward(self.sd, x)[0]
+
+    with AS.patched():
+        for case in fx["cases"]:
+            P = setup(SimpleNamespace(mode=case["mode"], aug="hfrt", penalty=case["penalty"], temp=0.1, lbd_a=1.0,
+                                      distributed=False))
+            assert P.filename.startswith(case["mode"])
+            P.augment_fn = get_augment("hfrt")
+            D = OracleD(case["sd_d"])
+            # the generator seeds of make_golden.gen_baselines: images / gen first, then the mode's own draws
+            seed = 400 + fx["cases"].index(case)
+            np.random.seed(seed + 50); torch.manual_seed(seed + 50)
+            images = torch.rand(4, 3, 32, 32); gen = torch.rand(4, 3, 32, 32)
+            assert torch.equal(images, case["images"])
+            options = {"loss": case["loss"], "lbd": case["lbd"], "lbd2": case["lbd2"]}
+            d_loss, aux = P.train_fn["D"](P, D, options, images, gen)
+            assert float(d_loss) == pytest.approx(case["d_loss"], rel=1e-5, abs=1e-6)
+            assert float(aux["penalty"]) == pytest.approx(case["pen"], rel=1e-4, abs=1e-7)
+            assert float(aux["d_real"]) == pytest.approx(case["d_real"], abs=1e-5)
+            assert float(aux["d_gen"]) == pytest.approx(case["d_gen"], abs=1e-5)
+            (d_loss + aux["penalty"]).sum().backward()
+            for k, ref in case["grad_norms"].items():
+                got = float(D.sd[k].grad.double().norm())
+                assert abs(got - ref) <= 1e-4 * max(ref, 1e-6) + 1e-9, (case["mode"], case["penalty"], k, got, ref)
+            g_loss = P.train_fn["G"](P, D, options, images, gen)
+            assert float(g_loss) == pytest.approx(case["g_loss"], rel=1e-5, abs=1e-6)
+    from contrad_b200.penalty import compute_penalty
+    with pytest.raises(NotImplementedError):
+        compute_penalty("gp", D=None, images=None, gen_images=None, lbd=1.0)

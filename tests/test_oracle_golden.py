@@ -174,3 +174,71 @@ def test_oracle_snresnet18_matches_reference(golden_dir):
         assert abs(float(sd[k].grad.norm()) - n) <= 1e-5 * max(n, 1e-6), k
     for k, v in fx["uv_after"].items():
         assert (sd[k] - v).abs().max() < 1e-6
+
+
+# ---- rows f3 / f4: uint8 input, hfrt / RandomCrop, Gaussian noise, baseline training modes --------------------
+
+def test_shift_flip_matches_reference(golden_dir):
+    """HorizontalFlipRandomCrop / RandomCrop through the reference's affine_grid + nearest grid_sample vs the oracle's
+    index-gather restatement: bit-exact forward, backward to fp32 summation order."""
+    fx = _load(golden_dir, "augment_aux.pt")
+    pads = set()
+    for case in fx["shift_flip"]:
+        b = case["x"].shape[0]
+        np.random.seed(case["seed"]); torch.manual_seed(case["seed"])
+        _ = torch.rand_like(case["x"]); _ = torch.randn_like(case["x"])
+        params = O.sample_shift_flip(b, case["max_pixels"], case["width"], flip=(case["kind"] == "hfrt"))
+        assert torch.equal(params, case["params"])
+        x = case["x"].clone().requires_grad_(True)
+        y = O.shift_flip(x, case["params"], case["padding_mode"])
+        (y * case["dy"]).sum().backward()
+        assert torch.equal(y, case["y"]), (case["kind"], case["padding_mode"], (y - case["y"]).abs().max())
+        assert torch.allclose(x.grad, case["dx"], atol=1e-6, rtol=1e-6)
+        pads.add(case["padding_mode"])
+    assert pads == {"zeros", "border", "reflection"}
+
+
+def test_gaussian_noise_matches_reference(golden_dir):
+    fx = _load(golden_dir, "augment_aux.pt")
+    for case in fx["noise"]:
+        x = case["x"].clone().requires_grad_(True)
+        y = O.gaussian_noise(x, case["noise"], case["sigma"])
+        (y * case["dy"]).sum().backward()
+        assert torch.equal(y, case["y"])
+        assert torch.equal(x.grad, case["dx"])
+
+
+def test_uint8_views_match_reference(golden_dir):
+    """Row f3: augment_simclr(cat[ToTensor(bytes), ToTensor(bytes), fakes]) on the stored draws equals the reference
+    chain on the converted batch."""
+    fx = _load(golden_dir, "augment_aux.pt")
+    for case in fx["uint8"]:
+        fakes = case["fakes"].clone().requires_grad_(True)
+        x_f = O.to_tensor_u8(case["x_u8"])
+        y = O.augment_simclr(torch.cat([x_f, x_f, fakes], dim=0), _unpack(case["params"]), case["order"])
+        (y * case["dy"]).sum().backward()
+        # quantised inputs put more pixels near the hue wheel's kinks than U[0,1) floats do: 7e-6 worst case
+        assert torch.allclose(y, case["y"], atol=2e-5, rtol=0), (y - case["y"]).abs().max()
+        assert torch.allclose(fakes.grad, case["d_fakes"], atol=5e-5, rtol=1e-5)      # scatter-add order; |grad| up to 7
+
+
+def test_baseline_modes_match_reference(golden_dir):
+    """std / aug / aug_both with penalty none / cr / bcr under `--aug hfrt`: oracle composition vs the reference modules."""
+    fx = _load(golden_dir, "baseline_modes.pt")
+    seen = set()
+    for case in fx["cases"]:
+        sd = {k: v.clone() for k, v in case["sd_d"].items()}
+        for k in O.trainable(sd):
+            sd[k].requires_grad_(True)
+        augs = [(lambda p: (lambda x: O.shift_flip(x, p, "reflection")))(p) for p in case["aug_params"]]
+        d_loss, pen, d_real, d_gen = O.loss_d_baseline(sd, case["mode"], case["images"], case["gen"], augs, loss=case["loss"],
+                                                       penalty=case["penalty"], lbd=case["lbd"], lbd2=case["lbd2"])
+        assert abs(float(d_loss) - case["d_loss"]) < 1e-5 * max(1.0, abs(case["d_loss"]))
+        assert abs(float(pen) - case["pen"]) < 1e-5 * max(1e-2, abs(case["pen"])), (float(pen), case["pen"])
+        assert abs(float(d_real) - case["d_real"]) < 1e-5 and abs(float(d_gen) - case["d_gen"]) < 1e-5
+        (d_loss + pen.sum()).backward()
+        for k, ref in case["grad_norms"].items():
+            got = float(sd[k].grad.double().norm())
+            assert abs(got - ref) <= 1e-4 * max(ref, 1e-6) + 1e-9, (case["mode"], k, got, ref)
+        seen.add((case["mode"], case["penalty"]))
+    assert {m for m, _ in seen} == {"std", "aug", "aug_both"} and {p for _, p in seen} == {"none", "cr", "bcr"}
