@@ -525,9 +525,11 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-workloads", action="store_true", help="skip the StyleGAN2 config-4 side measurement")
-    ap.add_argument("--u8-input", action="store_true",
-                    help="extra end-to-end leg fed with uint8 host images (row f3; N=1 only, reported as e2e_uint8_input)")
+    ap.add_argument("--no-u8-input", dest="u8_input", action="store_false",
+                    help="skip the extra end-to-end leg fed with uint8 host images (row f3; N=1 only, e2e_uint8_input)")
+    ap.add_argument("--u8-input", dest="u8_input", action="store_true", help=argparse.SUPPRESS)      # default on
     ap.add_argument("--no-graph", action="store_true", help="eager launches (and DDP wrappers for N > 1) instead of the CUDA-graph step")
+    ap.set_defaults(u8_input=True)
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 behind Python's back (NCCL prints
     # "NCCL version ..." there when NCCL_DEBUG is set in the environment) are routed to stderr for the whole run.

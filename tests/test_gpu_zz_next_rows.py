@@ -1,8 +1,6 @@
-"""GPU parity of the rows added after the round's GPU budget was spent (f3 uint8 input, f4 hfrt / RandomCrop /
-Gaussian + the CR / bCR baseline modes).  The kernels cross-compile for sm_100a and their host logic and index arithmetic
-are covered on CPU (tests/test_host_logic.py), but they have NOT run on hardware yet: until one hardware run has been
-looked at, a failure here is reported as `xfailed` (and a pass as `XPASS`) instead of stopping the verified suite.  The
-file name sorts last so that a faulting kernel cannot poison the CUDA context of the verified tests."""
+"""GPU parity of SURVEY 8f rows f3 (uint8 input) and f4 (hfrt / RandomCrop / Gaussian + the CR / bCR baseline modes):
+the kernels against the reference-generated fixtures, against the oracle at the benchmark batch, and the mixed-source
+augmentation against the fp32 kernels bit for bit.  The file name sorts last: it was added after the verified suite."""
 import os
 from types import SimpleNamespace
 
@@ -12,9 +10,7 @@ import torch
 
 from oracle import contrad_oracle as O
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="kernels of rows f3/f4 written without GPU access (round-1 budget "
-                                                     "exhausted); first hardware run pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def _load(golden_dir, name):
@@ -76,7 +72,9 @@ def test_mixed_fwd_equals_fp32_kernel_on_converted_batch(size, n, m):
     params, order = O.sample_simclr_params(total, size, size)
     packed = O.pack_params(params).cuda()
     y, means = K.augment_simclr_mixed_fwd(x_u8 if n else None, 2 * n, fakes, packed, order)
-    parts = ([x_u8.float().div(255)] * 2 if n else []) + ([fakes] if m else [])
+    # ToTensor runs on the HOST in the reference (correctly rounded k / 255); torch's CUDA `div(255)` multiplies by
+    # fl(1/255) instead and differs in the last bit for some k, so the comparison batch is converted on the CPU
+    parts = ([O.to_tensor_u8(x_u8.cpu()).cuda()] * 2 if n else []) + ([fakes] if m else [])
     cat = torch.cat(parts, dim=0)
     if K.augment_needs_large_path(size, size) or size not in (32, 64):
         want, means_ref = K.augment_simclr_large_fwd(cat, packed, order)
@@ -102,12 +100,14 @@ def test_forward_views_and_loss_d_fn_with_uint8_images(gin_defaults):
     gen = torch.rand(16, 3, 32, 32, generator=gen_w).cuda()
     P = SimpleNamespace(augment_fn=get_augment("simclr"), temp=0.1, lbd_a=1.0, distributed=False)
     got = []
-    for images in (x_u8, x_u8.float().div(255)):
+    for images in (x_u8, O.to_tensor_u8(x_u8.cpu()).cuda()):         # host-side ToTensor, as in the reference's DataLoader
         D.load_state_dict(uv, strict=False)                  # same power-iteration start for both calls
         np.random.seed(2); torch.manual_seed(2)
         loss, aux = contrad.loss_D_fn(P, D, {"loss": "hinge"}, images, gen)
         got.append([float(loss), float(aux["penalty"]), float(aux["d_real"]), float(aux["d_gen"])])
-    assert got[0] == pytest.approx(got[1], rel=1e-6, abs=1e-6), got
+    # identical views (bit-equal, test above); the D forward itself repeats to ~3e-5 relative only (fp32 atomics order in
+    # the split reductions, amplified by 1/temperature), measured run to run on identical inputs
+    assert got[0] == pytest.approx(got[1], rel=2e-4, abs=1e-5), got
 
 
 # ------------------------------------------------------------------------------------ row f4: hfrt / RandomCrop / noise

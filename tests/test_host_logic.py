@@ -148,13 +148,14 @@ def _gather_worker(rank, world, port, results):
     dist.destroy_process_group()
 
 
-def test_gather_layer_semantics_gloo_world2():
-    """third_party/gather_layer.py:8-23: forward = rank-major all-gather, backward = own slice."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_gather_layer_semantics_gloo_world2(world):
+    """third_party/gather_layer.py:8-23: forward = rank-major all-gather, backward = own slice (world sizes 2 and 4: the
+    scaling bench runs 1 / 2 / 4 / 8 ranks)."""
     import torch.multiprocessing as mp
-    world = 2
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_gather_worker, args=(world, 29611, results), nprocs=world, join=True)
+    mp.spawn(_gather_worker, args=(world, 29611 + world, results), nprocs=world, join=True)
     assert all(results.get(r) for r in range(world)), dict(results)
 
 
@@ -163,11 +164,11 @@ def test_distributed_loss_equals_single_process_oracle():
     [out1_all; out2_all; others_all] (checked on CPU against the oracle's loss on the full batch)."""
     from contrad_b200.training.gan.contrad import _rank_major
     torch.manual_seed(1)
-    world, n, d = 2, 3, 4
-    per_rank = [torch.randn(3 * n, d) for _ in range(world)]
-    got = _rank_major(torch.stack(per_rank), n)
-    want = torch.cat([torch.cat([p[i * n:(i + 1) * n] for p in per_rank]) for i in range(3)])
-    assert torch.equal(got, want)
+    for world, n, d in ((2, 3, 4), (8, 64, 128)):
+        per_rank = [torch.randn(3 * n, d) for _ in range(world)]
+        got = _rank_major(torch.stack(per_rank), n)
+        want = torch.cat([torch.cat([p[i * n:(i + 1) * n] for p in per_rank]) for i in range(3)])
+        assert torch.equal(got, want)
 
 
 def test_staging_eager_and_recorder_on_cpu():
