@@ -5,13 +5,13 @@ host side in the reference's exact numpy / torch RNG order, so iden
 identical augmentations.
 
 `simclr_hq` / `simclr_hq_cutout` (the README's StyleGAN2 recipe) append a separable Gaussian blur and a CutOut kernel.
-`hfrt` / `gaussian` (row f4, the CR / bCR baselines' augmentations) are one gather kernel / one elementwise kernel.
-Out of scope: diffaug (third_party/diffaug.py) - requesting it raises NotImplementedError rather than
-silently running something else."""
+`hfrt` / `gaussian` (row f4, the CR / bCR baselines' augmentations) are one gather kernel / one elementwise kernel,
+`diffaug` (third_party/diffaug.py, policy 'color,cutout') a reduction + a pointwise launch.  Every mode of the reference's
+registry (augment/__init__.py:14-25) is built; an unknown mode raises KeyError as in the reference."""
 import gin
 import torch.nn as nn
 
-from .layers import (ColorJitterLayer, CutOut, FusedSimCLR, FusedSimCLRHQ, Gaussian, GaussianBlur,  # noqa: F401
+from .layers import (ColorJitterLayer, CutOut, DiffAugLayer, FusedSimCLR, FusedSimCLRHQ, Gaussian, GaussianBlur,  # noqa: F401
                      HorizontalFlipLayer, HorizontalFlipRandomCrop, NoAugment, RandomApply, RandomColorGrayLayer,
                      RandomCrop, RandomResizeCropLayer)
 
@@ -49,17 +49,16 @@ def simclr_hq_cutout():
     )
 
 
+def diffaug():
+    """augment/__init__.py:144-145."""
+    return DiffAugLayer(policy="color,cutout")
+
+
 _BUILT = {"none": NoAugment, "simclr": simclr, "simclr_hq": simclr_hq, "simclr_hq_cutout": simclr_hq_cutout,
           "cutout": CutOut, "hflip": HorizontalFlipLayer, "color_jitter": ColorJitterLayer,
-          "gaussian": Gaussian, "hfrt": HorizontalFlipRandomCrop}
-_NEXT = ("diffaug",)
+          "gaussian": Gaussian, "hfrt": HorizontalFlipRandomCrop, "diffaug": diffaug}
 
 
 @gin.configurable("augment", whitelist=["fn"])
 def get_augment(mode="none", **kwargs):
-    if mode in _BUILT:
-        return _BUILT[mode]()
-    if mode in _NEXT:
-        raise NotImplementedError(
-            "augment mode %r is outside the hot path of contrad_b200 (SURVEY 8f); built: %s" % (mode, sorted(_BUILT)))
-    raise KeyError(mode)
+    return _BUILT[mode]()

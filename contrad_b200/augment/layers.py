@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import staging
-from ..functional import (AugmentSimCLRFn, AugmentSimCLRMixedFn, CutOutFn, GaussianBlurFn, NoiseClampFn,
+from ..functional import (AugmentSimCLRFn, AugmentSimCLRMixedFn, CutOutFn, DiffAugFn, GaussianBlurFn, NoiseClampFn,
                           ShiftFlipFn)
 
 _N_FIELDS = 11   # sx, sy, bx, by, flip, cj_on, contrast, hue, sat, val, gray_on
@@ -385,3 +385,51 @@ class FusedSimCLRHQ(FusedSimCLR):
             on = apply_cut.sample(inputs)
             out = apply_cut.fn(out, on=on)
         return out
+
+
+class DiffAugLayer(nn.Module):
+    """augment/__init__.py:136-142 + third_party/diffaug.py: DiffAugment(inputs, policy) with policy a comma-separated
+    subset of 'color', 'translation', 'cutout'.  The per-sample draws are made on the device in the reference order
+    (brightness, saturation, contrast; shift along H, along W; cutout offset along H, along W); the arithmetic is two
+    launches (cb200_diffaug_fwd).  The stages must be listed in the canonical order (the only policy the reference uses is
+    'color,cutout'); any other order raises."""
+
+    _ORDER = ("color", "translation", "cutout")
+
+    def __init__(self, policy=""):
+        super().__init__()
+        self.policy = policy
+        stages = [p for p in policy.split(",")] if policy else []
+        for p in stages:
+            if p not in self._ORDER:
+                raise KeyError(p)                                   # AUGMENT_FNS[p] in the reference
+        if stages != [p for p in self._ORDER if p in stages]:
+            raise NotImplementedError("DiffAugLayer: stages must be a subset of %s in that order (got %r)"
+                                      % (",".join(self._ORDER), policy))
+        self.stages = stages
+
+    def sample(self, x):
+        """[7, B] draws in the reference's torch RNG order (third_party/diffaug.py:24-76); unused rows stay zero."""
+        n, _, h, w = x.shape
+        dev = x.device
+        p = torch.zeros(7, n, device=dev)
+        if "color" in self.stages:
+            for row in range(3):                                    # rand_brightness, rand_saturation, rand_contrast
+                p[row] = torch.rand(n, 1, 1, 1, dtype=x.dtype, device=dev).view(n)
+        if "translation" in self.stages:
+            sh, sw = int(h * 0.125 + 0.5), int(w * 0.125 + 0.5)
+            p[3] = torch.randint(-sh, sh + 1, size=[n, 1, 1], device=dev).view(n).float()
+            p[4] = torch.randint(-sw, sw + 1, size=[n, 1, 1], device=dev).view(n).float()
+        if "cutout" in self.stages:
+            ch, cw = int(h * 0.5 + 0.5), int(w * 0.5 + 0.5)
+            p[5] = torch.randint(0, h + (1 - ch % 2), size=[n, 1, 1], device=dev).view(n).float()
+            p[6] = torch.randint(0, w + (1 - cw % 2), size=[n, 1, 1], device=dev).view(n).float()
+        return p
+
+    def forward(self, inputs):
+        if not self.stages:
+            return inputs                                           # DiffAugment with an empty policy is the identity
+        if inputs.dim() != 4 or inputs.shape[1] != 3:
+            raise ValueError("DiffAugLayer expects [B,3,H,W] images, got %s" % (tuple(inputs.shape),))
+        flags = sum({"color": 1, "translation": 2, "cutout": 4}[p] for p in self.stages)
+        return DiffAugFn.apply(inputs, self.sample(inputs), flags)

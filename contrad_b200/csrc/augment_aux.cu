@@ -8,7 +8,14 @@
 //   noise_clamp  Gaussian (augment/__init__.py:40-49): clamp(x + noise * sigma, 0, 1) and its gradient mask; the noise
 //                itself stays torch.randn_like so that the Philox stream is the reference's.
 //
-// Both are HBM-bound: 8 B/element (shift_flip fwd), 12 B/element (noise fwd: x, noise in, y out).
+//   diffaug      DiffAugment(policy = color / translation / cutout subsets, third_party/diffaug.py) of the `diffaug`
+//                baselines (EXPERIMENTS.md: --mode=aug_both --aug=diffaug): brightness, saturation, contrast, integer
+//                translation with zero fill and a square cutout, all per sample.  The chain is affine in x for fixed
+//                draws, with one per-image reduction (the contrast mean; the mean of the gradient in the backward pass):
+//                a reduction launch writes [B] scalars, a pointwise launch does the rest.
+//
+// All are HBM-bound: 8 B/element (shift_flip fwd), 12 B/element (noise fwd: x, noise in, y out), 12 B/element (diffaug:
+// x read twice, y written).
 #include "common.cuh"
 
 namespace {
@@ -124,6 +131,142 @@ inline dim3 image_grid(int B, long long work_items_per_image) {
     return dim3((unsigned)blocks, (unsigned)B);
 }
 
+// ---- DiffAugment ---------------------------------------------------------------------------------------------------
+// [host-testable: diffaug]  (tests/test_host_logic.py runs these four kernels single-threaded under a g++ shim)
+// params [7, B]: r_brightness, r_saturation, r_contrast (the raw U[0,1) draws), translation along H, along W (integers),
+// cutout offset along H, along W (integers).  flags: 1 color, 2 translation, 4 cutout (applied in this order).
+struct DiffAugParams {
+    float bright, sat, con;     // additive brightness (r - 0.5), saturation factor 2 r, contrast factor r + 0.5
+    int th, tw;                 // out[i][j] = in[i + th][j + tw] (zero outside)
+    int ch_lo, ch_hi, cw_lo, cw_hi;   // cutout rows / columns (inclusive); empty when lo > hi
+};
+
+__device__ __forceinline__ DiffAugParams load_diffaug(const float* __restrict__ p, int B, int b, int H, int W, int flags) {
+    DiffAugParams d;
+    const bool color = flags & 1;
+    d.bright = color ? __ldg(p + b) - 0.5f : 0.f;
+    d.sat = color ? __ldg(p + B + b) * 2.f : 1.f;
+    d.con = color ? __ldg(p + 2 * B + b) + 0.5f : 1.f;
+    d.th = (flags & 2) ? (int)__ldg(p + 3 * B + b) : 0;
+    d.tw = (flags & 2) ? (int)__ldg(p + 4 * B + b) : 0;
+    d.ch_lo = 0; d.ch_hi = -1; d.cw_lo = 0; d.cw_hi = -1;
+    if (flags & 4) {            // rand_cutout, third_party/diffaug.py:61-76: size = int(dim * 0.5 + 0.5), clamped index range
+        const int sh = (int)((float)H * 0.5f + 0.5f), sw = (int)((float)W * 0.5f + 0.5f);
+        const int lo_h = (int)__ldg(p + 5 * B + b) - sh / 2, lo_w = (int)__ldg(p + 6 * B + b) - sw / 2;
+        d.ch_lo = max(lo_h, 0); d.ch_hi = min(lo_h + sh - 1, H - 1);
+        d.cw_lo = max(lo_w, 0); d.cw_hi = min(lo_w + sw - 1, W - 1);
+    }
+    return d;
+}
+
+// brightness + saturation of one pixel in [-1, 1] space (rand_brightness / rand_saturation, diffaug.py:24-33)
+__device__ __forceinline__ void diffaug_color_pre(float (&v)[3], const DiffAugParams& d) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (2.f * v[c] - 1.f) + d.bright;
+    const float m = (v[0] + v[1] + v[2]) / 3.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (v[c] - m) * d.sat + m;
+}
+
+// sums[b] += sum over the image of the post-saturation values (the contrast mean is sums / (3 H W))
+__global__ void __launch_bounds__(kT) diffaug_mean_kernel(const float* __restrict__ x, const float* __restrict__ params,
+                                                          float* __restrict__ sums, int B, int H, int W, int flags) {
+    __shared__ float red[32];
+    const int b = blockIdx.y, HW = H * W;
+    const DiffAugParams d = load_diffaug(params, B, b, H, W, flags);
+    const float* xb = x + (size_t)b * 3 * HW;
+    float acc[1] = {0.f};
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float v[3] = {__ldg(xb + pix), __ldg(xb + HW + pix), __ldg(xb + 2 * HW + pix)};
+        diffaug_color_pre(v, d);
+        acc[0] += (v[0] + v[1]) + v[2];
+    }
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(sums + b, acc[0]);
+}
+
+__global__ void __launch_bounds__(kT) diffaug_apply_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const float* __restrict__ params, const float* __restrict__ sums,
+                                                           int B, int H, int W, int flags) {
+    const int b = blockIdx.y, HW = H * W;
+    const DiffAugParams d = load_diffaug(params, B, b, H, W, flags);
+    const float mean = (flags & 1) ? __ldg(sums + b) / (float)(3 * HW) : 0.f;
+    const float* xb = x + (size_t)b * 3 * HW;
+    float* yb = y + (size_t)b * 3 * HW;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        const int i = pix / W, j = pix % W;
+        const int si = i + d.th, sj = j + d.tw;
+        float v[3] = {0.f, 0.f, 0.f};                             // zero fill in [-1, 1] space (diffaug.py:56)
+        const bool cut = i >= d.ch_lo && i <= d.ch_hi && j >= d.cw_lo && j <= d.cw_hi;
+        if (!cut && si >= 0 && si < H && sj >= 0 && sj < W) {
+            const int sp = si * W + sj;
+            v[0] = __ldg(xb + sp); v[1] = __ldg(xb + HW + sp); v[2] = __ldg(xb + 2 * HW + sp);
+            if (flags & 1) {
+                diffaug_color_pre(v, d);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = (v[c] - mean) * d.con + mean;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = 2.f * v[c] - 1.f;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + pix, 0.5f * v[c] + 0.5f);
+    }
+}
+
+// Gradient of the chain.  At source pixel (s, t): g = 0.5 * dy[s - th][t - tw] when that output exists and is not cut.
+__device__ __forceinline__ void diffaug_grad_in(const float* __restrict__ dyb, int HW, int H, int W, int s, int t,
+                                                const DiffAugParams& d, float (&g)[3]) {
+    const int i = s - d.th, j = t - d.tw;
+    g[0] = g[1] = g[2] = 0.f;
+    if (i < 0 || i >= H || j < 0 || j >= W) return;
+    if (i >= d.ch_lo && i <= d.ch_hi && j >= d.cw_lo && j <= d.cw_hi) return;
+    const int op = i * W + j;
+    g[0] = 0.5f * __ldg(dyb + op); g[1] = 0.5f * __ldg(dyb + HW + op); g[2] = 0.5f * __ldg(dyb + 2 * HW + op);
+}
+
+__global__ void __launch_bounds__(kT) diffaug_bwd_sum_kernel(const float* __restrict__ dy, const float* __restrict__ params,
+                                                             float* __restrict__ gsums, int B, int H, int W, int flags) {
+    __shared__ float red[32];
+    const int b = blockIdx.y, HW = H * W;
+    const DiffAugParams d = load_diffaug(params, B, b, H, W, flags);
+    const float* dyb = dy + (size_t)b * 3 * HW;
+    float acc[1] = {0.f};
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float g[3];
+        diffaug_grad_in(dyb, HW, H, W, pix / W, pix % W, d, g);
+        acc[0] += (g[0] + g[1]) + g[2];
+    }
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) atomicAdd(gsums + b, acc[0]);
+}
+
+__global__ void __launch_bounds__(kT) diffaug_bwd_apply_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                                               const float* __restrict__ params, const float* __restrict__ gsums,
+                                                               int B, int H, int W, int flags) {
+    const int b = blockIdx.y, HW = H * W;
+    const DiffAugParams d = load_diffaug(params, B, b, H, W, flags);
+    const float gmean = (flags & 1) ? __ldg(gsums + b) / (float)(3 * HW) : 0.f;
+    const float* dyb = dy + (size_t)b * 3 * HW;
+    float* dxb = dx + (size_t)b * 3 * HW;
+    for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < HW; pix += gridDim.x * blockDim.x) {
+        float g[3];
+        diffaug_grad_in(dyb, HW, H, W, pix / W, pix % W, d, g);
+        if (flags & 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] = d.con * g[c] + (1.f - d.con) * gmean;         // contrast adjoint
+            const float m = (g[0] + g[1] + g[2]) / 3.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] = d.sat * g[c] + (1.f - d.sat) * m;             // saturation adjoint
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) __stcs(dxb + c * HW + pix, 2.f * g[c]);                 // x -> 2 x - 1
+    }
+}
+
+// [host-testable: end diffaug]
+
 __global__ void __launch_bounds__(kT) noise_clamp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ noise,
                                                              float* __restrict__ y, float sigma, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -215,5 +358,43 @@ extern "C" int cb200_noise_clamp_bwd(const float* x, const float* noise, const f
     noise_clamp_bwd_kernel<<<flat_grid(n), kT, 0, static_cast<cudaStream_t>(stream)>>>(x, noise, dy, dx, sigma, n);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("noise_clamp_bwd");
+    return CB200_OK;
+}
+
+// DiffAugment forward / backward (third_party/diffaug.py:8-21 with AUGMENT_FNS 'color', 'translation', 'cutout' in that
+// order; flags = 1 | 2 | 4).  x, y, dy, dx [B,3,H,W]; params [7,B] (see load_diffaug); sums / gsums [B] scratch.
+extern "C" int cb200_diffaug_fwd(const float* x, float* y, const float* params, float* sums, int B, int H, int W, int flags,
+                                 void* stream) {
+    CB200_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && flags >= 0 && flags <= 7, "diffaug_fwd: bad shape / flags");
+    if (B == 0) return CB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid = image_grid(B, (long long)H * W);
+    if (flags & 1) {
+        cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * (size_t)B, st);
+        if (e != cudaSuccess) { cb200_set_error("diffaug_fwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+        diffaug_mean_kernel<<<grid, kT, 0, st>>>(x, params, sums, B, H, W, flags);
+        CB200_COUNT_LAUNCH();
+    }
+    diffaug_apply_kernel<<<grid, kT, 0, st>>>(x, y, params, sums, B, H, W, flags);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("diffaug_fwd");
+    return CB200_OK;
+}
+
+extern "C" int cb200_diffaug_bwd(const float* dy, float* dx, const float* params, float* gsums, int B, int H, int W,
+                                 int flags, void* stream) {
+    CB200_CHECK_ARG(B >= 0 && B <= 65535 && H > 0 && W > 0 && flags >= 0 && flags <= 7, "diffaug_bwd: bad shape / flags");
+    if (B == 0) return CB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid = image_grid(B, (long long)H * W);
+    if (flags & 1) {
+        cudaError_t e = cudaMemsetAsync(gsums, 0, sizeof(float) * (size_t)B, st);
+        if (e != cudaSuccess) { cb200_set_error("diffaug_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
+        diffaug_bwd_sum_kernel<<<grid, kT, 0, st>>>(dy, params, gsums, B, H, W, flags);
+        CB200_COUNT_LAUNCH();
+    }
+    diffaug_bwd_apply_kernel<<<grid, kT, 0, st>>>(dy, dx, params, gsums, B, H, W, flags);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("diffaug_bwd");
     return CB200_OK;
 }

@@ -128,6 +128,21 @@ class ShiftFlipFn(Function):
         return K.shift_flip(_c(dy), params, ctx.padding_mode, adjoint=True), None, None
 
 
+class DiffAugFn(Function):
+    """DiffAugment (third_party/diffaug.py:8-21) on explicit draws: affine in x, so the backward needs only the draws."""
+
+    @staticmethod
+    def forward(ctx, x, params, flags):
+        ctx.save_for_backward(params)
+        ctx.flags = flags
+        return K.diffaug(_c(x), params, flags)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (params,) = ctx.saved_tensors
+        return K.diffaug(_c(dy), params, ctx.flags, adjoint=True), None, None
+
+
 class NoiseClampFn(Function):
     """Gaussian (augment/__init__.py:40-49): clamp(x + noise * sigma, 0, 1)."""
 

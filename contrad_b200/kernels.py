@@ -184,6 +184,23 @@ def noise_clamp_bwd(x, noise, dy, sigma):
     return dx
 
 
+DIFFAUG_FLAGS = {"color": 1, "translation": 2, "cutout": 4}
+
+
+def diffaug(x, params, flags, adjoint=False):
+    """DiffAugment on explicit draws: x [B,3,H,W], params [7,B] (include/contrad_b200.h).  adjoint=True: x = dy -> dx."""
+    x = _f32c(x, "x")
+    params = _f32c(params, "params")
+    B, C, H, W = x.shape
+    assert C == 3 and params.shape == (7, B), (x.shape, params.shape)
+    y = torch.empty_like(x)
+    scratch = torch.empty(B, device=x.device, dtype=torch.float32)
+    fn = lib().cb200_diffaug_bwd if adjoint else lib().cb200_diffaug_fwd
+    _call("diffaug", 0, 12 * x.numel(), fn, ptr(x), ptr(y), ptr(params), ptr(scratch), i32(B), i32(H), i32(W), i32(flags),
+          stream_ptr())
+    return y
+
+
 # ------------------------------------------------------------------ tensor-core GEMM / conv
 def _colsum_buf(colsum, n):
     if colsum is not None:

@@ -97,6 +97,16 @@ int cb200_noise_clamp_fwd(const float* x, const float* noise, float* y, float si
 int cb200_noise_clamp_bwd(const float* x, const float* noise, const float* dy, float* dx, float sigma, long long n,
                           void* stream);
 
+/* DiffAugment (third_party/diffaug.py:8-76; augment/__init__.py:136-145, `--aug diffaug` = policy 'color,cutout'):
+ * x -> 2x-1 -> [color: brightness, saturation, contrast] -> [translation: integer shift, zero fill] -> [cutout: half-size
+ * square zeroed] -> 0.5x+0.5, each stage per sample.  flags = 1 (color) | 2 (translation) | 4 (cutout), applied in that
+ * order.  params [7,B] = {r_brightness, r_saturation, r_contrast (raw U[0,1) draws), shift along H, shift along W, cutout
+ * offset along H, along W (integers stored as floats)}; x, y, dy, dx [B,3,H,W]; sums / gsums [B] caller-allocated scratch. */
+int cb200_diffaug_fwd(const float* x, float* y, const float* params, float* sums, int B, int H, int W, int flags,
+                      void* stream);
+int cb200_diffaug_bwd(const float* dy, float* dx, const float* params, float* gsums, int B, int H, int W, int flags,
+                      void* stream);
+
 /* ---- tcgen05 tensor-core GEMM / implicit-GEMM convolutions (TF32 in, FP32 accumulate) --------
  * Replace F.linear / nn.Conv2d / nn.ConvTranspose2d behind models/gan/sndcgan.py:24-38,91-109 and
  * models/gan/base.py:14-35,92-101 (cuBLAS / cuDNN in the reference).  Activations are NHWC.

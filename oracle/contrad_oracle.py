@@ -376,6 +376,55 @@ def gaussian_noise(x, noise, sigma):
     return (x + noise * sigma).clamp(0, 1)
 
 
+def sample_diffaug(batch, height, width, stages=("color", "cutout"), device="cpu"):
+    """Draws of DiffAugment in the reference's torch RNG order (third_party/diffaug.py:24-76).  [7, B]:
+    r_brightness, r_saturation, r_contrast, shift along H, along W, cutout offset along H, along W."""
+    p = torch.zeros(7, batch, device=device)
+    if "color" in stages:
+        for row in range(3):
+            p[row] = torch.rand(batch, 1, 1, 1, device=device).view(batch)
+    if "translation" in stages:
+        sh, sw = int(height * 0.125 + 0.5), int(width * 0.125 + 0.5)
+        p[3] = torch.randint(-sh, sh + 1, size=[batch, 1, 1], device=device).view(batch).float()
+        p[4] = torch.randint(-sw, sw + 1, size=[batch, 1, 1], device=device).view(batch).float()
+    if "cutout" in stages:
+        ch, cw = int(height * 0.5 + 0.5), int(width * 0.5 + 0.5)
+        p[5] = torch.randint(0, height + (1 - ch % 2), size=[batch, 1, 1], device=device).view(batch).float()
+        p[6] = torch.randint(0, width + (1 - cw % 2), size=[batch, 1, 1], device=device).view(batch).float()
+    return p
+
+
+def diffaug(x, p, stages=("color", "cutout")):
+    """DiffAugment(x, policy) on explicit draws (third_party/diffaug.py:8-76), stages in the order color, translation,
+    cutout.  Plain slicing / masking instead of the reference's meshgrid fancy indexing."""
+    B, C, H, W = x.shape
+    x = 2.0 * x - 1.0
+    if "color" in stages:
+        x = x + (p[0].view(B, 1, 1, 1) - 0.5)                                           # rand_brightness :24-26
+        m = x.mean(dim=1, keepdim=True)
+        x = (x - m) * (p[1].view(B, 1, 1, 1) * 2) + m                                   # rand_saturation :29-32
+        m = x.mean(dim=[1, 2, 3], keepdim=True)
+        x = (x - m) * (p[2].view(B, 1, 1, 1) + 0.5) + m                                 # rand_contrast :35-38
+    if "translation" in stages:                                                         # rand_translation :41-54
+        i = torch.arange(H, device=x.device).view(1, H) + p[3].long().view(B, 1)        # source row of output row
+        j = torch.arange(W, device=x.device).view(1, W) + p[4].long().view(B, 1)
+        vi, vj = (i >= 0) & (i < H), (j >= 0) & (j < W)
+        rows = torch.gather(x, 2, i.clamp(0, H - 1).view(B, 1, H, 1).expand(B, C, H, W))
+        out = torch.gather(rows, 3, j.clamp(0, W - 1).view(B, 1, 1, W).expand(B, C, H, W))
+        x = out * (vi.view(B, 1, H, 1) & vj.view(B, 1, 1, W)).to(x.dtype)
+    if "cutout" in stages:                                                              # rand_cutout :57-72
+        sh, sw = int(H * 0.5 + 0.5), int(W * 0.5 + 0.5)
+        lo_h = p[5].long().view(B, 1) - sh // 2
+        lo_w = p[6].long().view(B, 1) - sw // 2
+        ii = torch.arange(H, device=x.device).view(1, H)
+        jj = torch.arange(W, device=x.device).view(1, W)
+        cut_h = (ii >= lo_h.clamp(min=0)) & (ii <= (lo_h + sh - 1).clamp(max=H - 1))
+        cut_w = (jj >= lo_w.clamp(min=0)) & (jj <= (lo_w + sw - 1).clamp(max=W - 1))
+        mask = 1.0 - (cut_h.view(B, 1, H, 1) & cut_w.view(B, 1, 1, W)).to(x.dtype)
+        x = x * mask
+    return 0.5 * x + 0.5
+
+
 def penalty_cr(sd_d, d_real, images, aug, lbd, training=True):
     """penalty.consistency (penalty.py:47-49) with `aug` = the augmentation on explicit draws."""
     d_aug, _ = d_sndcgan_forward(sd_d, aug(images), training=training)

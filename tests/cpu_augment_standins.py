@@ -58,6 +58,19 @@ def noise_clamp_bwd(x, noise, dy, sigma):
     return dy * ((u >= 0) & (u <= 1)).to(dy.dtype)
 
 
+_DIFFAUG_STAGES = ("color", "translation", "cutout")
+
+
+def diffaug(x, params, flags, adjoint=False):
+    stages = tuple(s for k, s in enumerate(_DIFFAUG_STAGES) if flags & (1 << k))
+    if not adjoint:
+        return O.diffaug(x, params, stages)
+    probe = torch.zeros_like(x, requires_grad=True)
+    with torch.enable_grad():
+        (dx,) = torch.autograd.grad(O.diffaug(probe, params, stages), probe, x)
+    return dx
+
+
 def gan_d_loss(d_real, d_gen, kind):
     dr = d_real.detach().clone().requires_grad_(True)
     dg = d_gen.detach().clone().requires_grad_(True)
@@ -76,7 +89,7 @@ def gan_g_loss(d_gen, kind):
 
 
 NAMES = ("augment_simclr_fwd", "augment_simclr_bwd", "augment_needs_large_path", "augment_simclr_mixed_fwd", "shift_flip",
-         "noise_clamp_fwd", "noise_clamp_bwd", "gan_d_loss", "gan_g_loss")
+         "noise_clamp_fwd", "noise_clamp_bwd", "diffaug", "gan_d_loss", "gan_g_loss")
 
 
 @contextlib.contextmanager

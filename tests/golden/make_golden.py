@@ -338,6 +338,31 @@ def gen_augment_aux(gin):
     torch.save({"shift_flip": cases, "noise": noise_cases, "uint8": u8_cases}, os.path.join(HERE, "augment_aux.pt"))
 
 
+def gen_diffaug(gin):
+    """third_party/diffaug.DiffAugment through the reference for the registry's policy ('color,cutout') and the other
+    canonical-order policies; draws replayed with oracle.sample_diffaug."""
+    from third_party.diffaug import DiffAugment
+    cases = []
+    specs = [("color,cutout", 5, 32, 32), ("color,translation,cutout", 4, 32, 32), ("translation", 3, 16, 24),
+             ("color", 3, 20, 20), ("cutout", 4, 33, 31), ("color,cutout", 2, 64, 64)]
+    for k, (policy, batch, h, w) in enumerate(specs):
+        seed = 500 + k
+        seed_all(seed)
+        x = torch.rand(batch, 3, h, w)
+        dy = torch.randn(batch, 3, h, w)
+        params = O.sample_diffaug(batch, h, w, stages=tuple(policy.split(",")))
+        seed_all(seed)
+        x_ref = torch.rand(batch, 3, h, w)
+        _ = torch.randn(batch, 3, h, w)
+        x_ref.requires_grad_(True)
+        y_ref = DiffAugment(x_ref, policy=policy)
+        (y_ref * dy).sum().backward()
+        cases.append({"policy": policy, "seed": seed, "x": t2l(x), "dy": t2l(dy), "params": t2l(params), "y": t2l(y_ref),
+                      "dx": t2l(x_ref.grad)})
+        print("diffaug case %s B=%d %dx%d" % (policy, batch, h, w))
+    torch.save({"cases": cases}, os.path.join(HERE, "diffaug.pt"))
+
+
 def gen_baselines(gin):
     """training/gan/{std,aug,aug_both}.py with penalty none / cr / bcr and `--aug hfrt`, and simclr_only, through the
     reference modules at reduced width (ndf=4, d_hidden=16): losses, penalty and the D gradient norms."""
@@ -394,7 +419,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gin = ref_import.activate()
     todo = args.only.split(",") if args.only else ["augment", "augment_hq", "contrastive", "sn", "small", "config1", "snresnet18",
-                                                     "augment_aux", "baselines"]
+                                                     "augment_aux", "baselines", "diffaug"]
     if "augment" in todo:
         gen_augment(gin)
     if "augment_hq" in todo:
@@ -413,6 +438,8 @@ def main():
         gen_augment_aux(gin)
     if "baselines" in todo:
         gen_baselines(gin)
+    if "diffaug" in todo:
+        gen_diffaug(gin)
 
 
 if __name__ == "__main__":

@@ -200,3 +200,32 @@ def test_baseline_modes_vs_oracle(gin_defaults, mode, penalty, loss_kind):
     tot_o = O.grad_norm(sd_o)
     tot = float(engine.grad_norm(D))
     assert abs(tot - tot_o) < 5e-3 * tot_o, (tot, tot_o)
+
+
+# ---------------------------------------------------------------------------------------------- diffaug (third_party)
+def test_diffaug_matches_reference_fixtures(golden_dir):
+    """cb200_diffaug_fwd/bwd on the stored draws vs third_party/diffaug.DiffAugment (all canonical policies, odd sizes)."""
+    from contrad_b200.functional import DiffAugFn
+    for case in _load(golden_dir, "diffaug.pt")["cases"]:
+        flags = sum({"color": 1, "translation": 2, "cutout": 4}[s] for s in case["policy"].split(","))
+        x = case["x"].cuda().requires_grad_(True)
+        y = DiffAugFn.apply(x, case["params"].cuda(), flags)
+        assert torch.allclose(y.cpu(), case["y"], atol=2e-6, rtol=0), (case["policy"], float((y.cpu() - case["y"]).abs().max()))
+        (y * case["dy"].cuda()).sum().backward()
+        assert torch.allclose(x.grad.cpu(), case["dx"], atol=5e-6, rtol=1e-5), case["policy"]
+
+
+def test_diffaug_benchmark_batch_vs_oracle(gin_defaults):
+    """get_augment('diffaug') at the D-step batch of mode=aug_both (2 x 512 images): device draws replayed by the oracle."""
+    from contrad_b200.augment import get_augment
+    aug = get_augment("diffaug")
+    x = torch.rand(1024, 3, 32, 32)
+    torch.manual_seed(41)
+    params = O.sample_diffaug(1024, 32, 32, ("color", "cutout"), device="cuda").cpu()
+    torch.manual_seed(41)
+    xc = x.cuda().requires_grad_(True)
+    y = aug(xc)
+    want = O.diffaug(x, params, ("color", "cutout"))
+    assert torch.allclose(y.cpu(), want, atol=3e-6, rtol=0), float((y.cpu() - want).abs().max())
+    y.sum().backward()
+    assert torch.isfinite(xc.grad).all()

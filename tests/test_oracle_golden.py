@@ -242,3 +242,19 @@ def test_baseline_modes_match_reference(golden_dir):
             assert abs(got - ref) <= 1e-4 * max(ref, 1e-6) + 1e-9, (case["mode"], k, got, ref)
         seen.add((case["mode"], case["penalty"]))
     assert {m for m, _ in seen} == {"std", "aug", "aug_both"} and {p for _, p in seen} == {"none", "cr", "bcr"}
+
+
+def test_diffaug_matches_reference(golden_dir):
+    """third_party/diffaug.DiffAugment vs the oracle's slicing / masking restatement on replayed draws."""
+    fx = _load(golden_dir, "diffaug.pt")
+    for case in fx["cases"]:
+        stages = tuple(case["policy"].split(","))
+        b, _, h, w = case["x"].shape
+        np.random.seed(case["seed"]); torch.manual_seed(case["seed"])
+        _ = torch.rand_like(case["x"]); _ = torch.randn_like(case["x"])
+        assert torch.equal(O.sample_diffaug(b, h, w, stages), case["params"])
+        x = case["x"].clone().requires_grad_(True)
+        y = O.diffaug(x, case["params"], stages)
+        (y * case["dy"]).sum().backward()
+        assert torch.allclose(y, case["y"], atol=1e-6, rtol=0), (case["policy"], (y - case["y"]).abs().max())
+        assert torch.allclose(x.grad, case["dx"], atol=2e-6, rtol=1e-5), case["policy"]
