@@ -229,3 +229,73 @@ def test_diffaug_benchmark_batch_vs_oracle(gin_defaults):
     assert torch.allclose(y.cpu(), want, atol=3e-6, rtol=0), float((y.cpu() - want).abs().max())
     y.sum().backward()
     assert torch.isfinite(xc.grad).all()
+
+
+# ------------------------------------------------------------------------- BASELINE config 2 at its full size vs oracle
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: first hardware run pending "
+                                        "(the b64 reference-scalar test and the small-batch oracle tests are the verified ones)")
+def test_config2_full_batch_step_vs_oracle(gin_defaults):
+    """SNDCGAN + ContraD, N = 512 (D-step batch 1536), one complete step incl. Adam on identical
+    weights, latents and augmentation draws - every reported scalar against the fp32 CPU oracle at north_star's 1e-3
+    (the generator's gradient norm at initialisation: 2e-2, see tests/test_gpu_model.py), and the updated weights."""
+    from contrad_b200 import engine
+    from contrad_b200.functional import AugmentSimCLRFn
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import contrad
+    n = 512
+    gen_w = torch.Generator().manual_seed(77)
+    sd_d, sd_g = O.make_d_state(generator=gen_w), O.make_g_state(generator=gen_w)
+    G, D = get_architecture("sndcgan", (32, 32, 3))
+    D.load_state_dict(sd_d); G.load_state_dict(sd_g)
+    G.cuda().train(); D.cuda().train()
+    np.random.seed(5); torch.manual_seed(5)
+    images = torch.rand(n, 3, 32, 32)
+    z_d = O.sample_latent(n); aug_d = O.sample_simclr_params(3 * n, 32, 32)
+    z_g = O.sample_latent(n); aug_g = O.sample_simclr_params(n, 32, 32)
+
+    class Aug(torch.nn.Module):
+        def __init__(self, blocks):
+            super().__init__(); self.blocks = list(blocks)
+        def forward(self, x):
+            packed, order = self.blocks.pop(0)
+            return AugmentSimCLRFn.apply(x, packed.to(x.device), order)
+
+    class Gw(torch.nn.Module):
+        def __init__(self, g, zs):
+            super().__init__(); self.g, self.zs = g, list(zs)
+        def sample_latent(self, k):
+            return self.zs.pop(0).cuda()
+        def forward(self, z):
+            return self.g(z)
+        def parameters(self, recurse=True):
+            return self.g.parameters(recurse)
+        def train(self, mode=True):
+            self.g.train(mode); return self
+
+    P = SimpleNamespace(augment_fn=Aug([(O.pack_params(aug_d[0]), aug_d[1]), (O.pack_params(aug_g[0]), aug_g[1])]),
+                        temp=0.1, lbd_a=1.0, distributed=False)
+    opts = {"loss": "nonsat", "warmup": 3000, "lr": 2e-4}
+    opt_G = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    opt_D = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    got = engine.train_step(P, opts, {"D": contrad.loss_D_fn, "G": contrad.loss_G_fn}, (Gw(G, [z_d, z_g]), D),
+                            (opt_G, opt_D), images.cuda(), 1, record_grad_norms=True)
+    got = {k: float(v) for k, v in got.items()}
+
+    sd_d_o = {k: v.clone() for k, v in sd_d.items()}
+    sd_g_o = {k: v.clone() for k, v in sd_g.items()}
+    opt_g_o, opt_d_o = O.Adam(O.trainable(sd_g_o).values(), 2e-4), O.Adam(O.trainable(sd_d_o).values(), 2e-4)
+    ref = O.train_step(sd_g_o, sd_d_o, opt_g_o, opt_d_o, images, z_d, z_g, aug_d, aug_g, step=1)
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-12)
+    print("config 2 @ N=512:", {k: got.get(k) for k in ("d_loss", "d_penalty", "g_loss", "d_grad_norm", "g_grad_norm")}, ref)
+    assert rel(got["d_loss"], ref["l_con_pos"] + ref["l_con_neg"]) < 1e-3
+    assert rel(got["d_penalty"], ref["l_dis"]) < 1e-3 and rel(got["g_loss"], ref["l_gen"]) < 1e-3
+    assert abs(got["d_real"] - ref["d_real"]) < 1e-3 and abs(got["d_gen"] - ref["d_gen"]) < 1e-3
+    assert rel(got["d_grad_norm"], ref["d_grad_norm"]) < 1e-3, (got["d_grad_norm"], ref["d_grad_norm"])
+    assert rel(got["g_grad_norm"], ref["g_grad_norm"]) < 2e-2, (got["g_grad_norm"], ref["g_grad_norm"])
+    # after Adam (lr = warm-up 2/3000 * 2e-4): the first update moves every weight by ~lr * sign(grad); compare directions
+    sd_now = D.state_dict()
+    for key in ("main.0.weight_orig", "main.12.weight_orig", "projection.0.weight_orig"):
+        step_mine = (sd_now[key].cpu() - sd_d[key]).flatten().double()
+        step_ref = (sd_d_o[key].detach() - sd_d[key]).flatten().double()
+        cos = float((step_mine * step_ref).sum() / (step_mine.norm() * step_ref.norm()).clamp_min(1e-30))
+        assert cos > 0.97, (key, cos)       # Adam's first update is ~lr * sign(grad): sign agreement of 98.5 %
