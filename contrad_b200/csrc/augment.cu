@@ -195,32 +195,7 @@ __device__ __forceinline__ void gather_quad(const float* xs, int H, int W, int i
     }
 }
 
-// ---- async staging: one cp.async.bulk (TMA bulk copy) moves a whole [3,H,W] image into shared memory ----
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; spin < (1u << 26) && !ok; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_addr(bar)), "r"(parity)
-            : "memory");
-    }
-    if (!ok) __trap();
-}
+// (async staging helpers - bar_init / bar_expect_tx / bulk_load / bar_wait - live in common.cuh)
 
 // Forward: PERSISTENT CTAs (grid = resident CTAs) walk the batch with a two-deep prefetch ring: while image i is
 // being processed, image i + gridDim.x is already in flight into the other shared-memory buffer (cp.async.bulk +
@@ -241,7 +216,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
     if (threadIdx.x == 0) {
         bar_init(&bars[0], 1);
         bar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_barrier_init();
     }
     __syncthreads();
     int b = blockIdx.x;
@@ -410,7 +385,7 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
     if (threadIdx.x == 0) {
         bar_init(&bars[0], 1);
         bar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_barrier_init();
     }
     __syncthreads();
     int b = blockIdx.x;
@@ -474,7 +449,7 @@ augment_simclr_fwd_mixed_cols_kernel(const uint8_t* __restrict__ xu, int n_u8, i
     if (threadIdx.x == 0) {
         bar_init(&bars[0], 1);
         bar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_barrier_init();
     }
     __syncthreads();
     auto prefetch = [&](int view, int slot) {                     // thread 0 only
@@ -538,7 +513,7 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
     const float hshift = (sp.fh * 255.f) / 360.f;
     if (sp.cj_on != 0.f && threadIdx.x == 0) {     // x only feeds the clamp mask; one async bulk copy stages it
         bar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_barrier_init();
         bar_expect_tx(bar, (uint32_t)(3 * HW * sizeof(float)));
         bulk_load(xs, x + (size_t)b * 3 * HW, (uint32_t)(3 * HW * sizeof(float)), bar);
     }

@@ -3,6 +3,10 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#if !defined(__CUDACC__)
+#include <sched.h>
+#include <string.h>
+#endif
 
 #define CB200_OK 0
 #define CB200_ERR_ARG 1000        // bad argument (shape / alignment / unsupported size)
@@ -89,6 +93,9 @@ __device__ __forceinline__ void fold_row_lanes(float (&v)[NV], float* scratch /*
     }
 }
 
+// The three PTX helpers below have plain-C equivalents so that the asm-free kernel files can also be compiled by a host
+// compiler against a CUDA emulation header (tests/emu: CPU-side checks of the SIMT kernels; never part of the product).
+#if defined(__CUDACC__)
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -110,3 +117,59 @@ __device__ __forceinline__ float round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+#else
+inline float4 ldg_stream4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+inline void stg_stream4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+inline float round_tf32(float x) {          // cvt.rna.tf32.f32: add half an ulp of the 10-bit mantissa, truncate
+    uint32_t u = __float_as_uint(x);
+    if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+    return __uint_as_float(u);
+}
+#endif
+
+// ---- async staging: cp.async.bulk (TMA bulk copy) of a contiguous block into shared memory, completion on an mbarrier ----
+// Usage: one thread does bar_init(bar, 1) + fence_barrier_init() once, then per phase bar_expect_tx(bar, total_bytes)
+// followed by one or more bulk_load(...) whose sizes add up to total_bytes; every consumer thread calls
+// bar_wait(bar, phase_parity).  (The host versions in the #else branch give the same protocol a synchronous copy and a
+// {phase count, bytes in flight} word, for the CPU-side kernel checks of tests/emu.)
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; spin < (1u << 26) && !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+    if (!ok) __trap();
+}
+#else
+inline void bar_init(uint64_t* bar, uint32_t) { __atomic_store_n(bar, (uint64_t)0, __ATOMIC_RELEASE); }
+inline void fence_barrier_init() {}
+inline void bar_expect_tx(uint64_t* bar, uint32_t bytes) { __atomic_fetch_add(bar, (uint64_t)bytes, __ATOMIC_RELAXED); }
+inline void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    memcpy(dst, src, bytes);
+    const uint64_t v = __atomic_load_n(bar, __ATOMIC_RELAXED);
+    const uint64_t left = (v & 0xffffffffull) - bytes;                      // bytes of this phase still in flight
+    __atomic_store_n(bar, left ? ((v & ~0xffffffffull) | left) : (((v >> 32) + 1) << 32), __ATOMIC_RELEASE);
+}
+inline void bar_wait(uint64_t* bar, uint32_t parity) {
+    while (((__atomic_load_n(bar, __ATOMIC_ACQUIRE) >> 32) & 1u) == parity) sched_yield();
+}
+#endif

@@ -89,33 +89,7 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
 }
 
 // dW_hat[co][ci*9+kh*3+kw] += sum_pixels dY[pix][co] * (2x-1)[ci][h+kh-1][w+kw-1];   db[co] += sum dY
-// ---- async staging helpers (cp.async.bulk + mbarrier, as in augment.cu) ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; spin < (1u << 26) && !ok; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-    if (!ok) __trap();
-}
-
+// (async staging helpers: common.cuh)
 constexpr int kXsElems = 3 * (kRows + 2) * (kCols + 2);            // 612 image values (+halo) per tile
 constexpr int kXsPerThread = (kXsElems + kThreads - 1) / kThreads;  // 3
 constexpr int kDyTileFloats = kRows * kCols * kCo;                  // 8192 floats = 32 KB
@@ -199,7 +173,7 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
     if (threadIdx.x == 0) {
         bar_init(&bars[0], 1);
         bar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_barrier_init();
     }
     __syncthreads();
     int tile = blockIdx.x;

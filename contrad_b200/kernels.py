@@ -330,7 +330,8 @@ class _SnBwdJob(ctypes.Structure):
 
 
 def _p(t):
-    return 0 if t is None else t.data_ptr()
+    """Raw device address for the ctypes structs of the batched launches (ptr() refuses CPU tensors; None -> 0)."""
+    return ptr(t).value or 0
 
 
 def sn_power_iter_batched(layers, training=True, eps=1e-12):
@@ -344,7 +345,7 @@ def sn_power_iter_batched(layers, training=True, eps=1e-12):
     arr = (_SnLayer * len(layers))()
     to, so = 0, 0
     for i, (w, u, v, sigma) in enumerate(layers):
-        assert w.is_cuda and w.is_contiguous()
+        assert w.is_contiguous()
         arr[i] = _SnLayer(w.data_ptr(), u.data_ptr(), v.data_ptr(), sigma.data_ptr(),
                           t_all.data_ptr() + 4 * to if training else 0, s_all.data_ptr() + 4 * so, couts[i], fs[i])
         to += pad4(fs[i])
@@ -570,8 +571,8 @@ def adam_step(entries, lr, beta1, beta2, eps, step):
     arr = (_AdamTensor * len(entries))()
     nbytes = 0
     for i, (p, g, m, v) in enumerate(entries):
-        assert p.is_cuda and p.is_contiguous() and g.is_contiguous()
-        arr[i] = _AdamTensor(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel())
+        assert p.is_contiguous() and g.is_contiguous()
+        arr[i] = _AdamTensor(ptr(p).value, ptr(g).value, ptr(m).value, ptr(v).value, p.numel())      # ptr() refuses CPU tensors
         nbytes += 28 * p.numel()
     if isinstance(lr, torch.Tensor):
         # device-resident {lr, 1-b1^t, sqrt(1-b2^t)} (CUDA-graph replay); `step` is ignored

@@ -279,8 +279,8 @@ def ema_lerp(pairs, decay):
     arr = (_EmaTensor * len(pairs))()
     nbytes = 0
     for i, (d, s) in enumerate(pairs):
-        assert d.is_cuda and s.is_cuda and d.is_contiguous() and s.is_contiguous() and d.numel() == s.numel()
+        assert d.is_contiguous() and s.is_contiguous() and d.numel() == s.numel()
         assert d.dtype == torch.float32 and s.dtype == torch.float32
-        arr[i] = _EmaTensor(d.data_ptr(), s.data_ptr(), d.numel())
+        arr[i] = _EmaTensor(ptr(d).value, ptr(s).value, d.numel())             # ptr() refuses CPU tensors
         nbytes += 12 * d.numel()
     _call("ema_lerp", 0, nbytes, lib().cb200_ema_lerp, arr, i32(len(pairs)), f32(decay), stream_ptr())

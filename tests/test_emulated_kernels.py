@@ -1,0 +1,440 @@
+"""CPU execution of the product's SIMT kernels: the asm-free files of contrad_b200/csrc are compiled for the host against
+a CUDA emulation header (tests/emu) and driven through the product's own bindings, so kernel source, launch configuration
+and Python glue are checked without a GPU.  The first tests replay kernels that ARE verified on the B200 against the same
+fixtures (they validate the emulator); the others extend CPU coverage to the remaining SIMT kernel families."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import contrad_oracle as O
+from tests.emu import emulated
+
+pytestmark = pytest.mark.timeout(600)
+
+_COMPAT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat")
+if _COMPAT not in __import__("sys").path:
+    __import__("sys").path.append(_COMPAT)          # `gin` shim for contrad_b200.augment
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+# ------------------------------------------------------------------ emulator validation on hardware-verified kernels
+def test_emulated_light_augmentations_match_reference_fixtures(golden_dir):
+    from contrad_b200 import kernels as K
+    fx = _load(golden_dir, "augment_aux.pt")
+    with emulated():
+        for case in fx["shift_flip"]:
+            y = K.shift_flip(case["x"], case["params"], case["padding_mode"])
+            assert torch.equal(y, case["y"]), (case["kind"], case["padding_mode"])
+            dx = K.shift_flip(case["dy"], case["params"], case["padding_mode"], adjoint=True)
+            assert torch.allclose(dx, case["dx"], atol=1e-6, rtol=1e-6)
+        for case in fx["noise"]:
+            assert torch.equal(K.noise_clamp_fwd(case["x"], case["noise"], case["sigma"]), case["y"])
+            assert torch.equal(K.noise_clamp_bwd(case["x"], case["noise"], case["dy"], case["sigma"]), case["dx"])
+        for case in _load(golden_dir, "diffaug.pt")["cases"]:
+            flags = sum({"color": 1, "translation": 2, "cutout": 4}[s] for s in case["policy"].split(","))
+            assert torch.allclose(K.diffaug(case["x"], case["params"], flags), case["y"], atol=2e-6, rtol=0)
+            assert torch.allclose(K.diffaug(case["dy"], case["params"], flags, adjoint=True), case["dx"], atol=5e-6, rtol=1e-5)
+
+
+def _rel(a, b):
+    a, b = a.detach().double(), torch.as_tensor(b).detach().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def test_emulated_blur_and_cutout_vs_oracle():
+    """csrc/augment_hq.cu (GPU-verified): separable reflect-padded Gaussian + adjoint, CutOut, at odd small shapes."""
+    from contrad_b200 import kernels as K
+    from contrad_b200.augment.layers import GaussianBlur, gaussian_taps
+    with emulated():
+        for B, H, W, seed in ((3, 40, 36, 1), (4, 32, 32, 2)):
+            torch.manual_seed(seed)
+            x, dy = torch.rand(B, 3, H, W), torch.randn(B, 3, H, W)
+            sigma = 0.1 + 1.9 * float(torch.rand(()))
+            on = (torch.rand(B) > 0.4).float()
+            on[0] = 1.0
+            xr = x.clone().requires_grad_(True)
+            ref = O._blend(xr, O.gaussian_blur(xr, sigma), on)
+            (ref * dy).sum().backward()
+            taps = gaussian_taps(GaussianBlur.kernel_size(H), sigma)
+            assert torch.allclose(K.gaussian_blur(x, taps, on), ref.detach(), atol=3e-6, rtol=0)
+            assert torch.allclose(K.gaussian_blur(dy, taps, on, adjoint=True), xr.grad, atol=2e-5, rtol=1e-5)
+            hc, wc = torch.randint(H, (B,)), torch.randint(W, (B,))
+            params = torch.stack([on, hc.float(), wc.float()])
+            assert torch.equal(K.cutout(x, params, 15), O._blend(x, O.cutout(x, hc, wc, 15), on))
+
+
+# ------------------------------------------------------------------ kernel families beyond the ones above
+def test_emulated_spectral_norm_matches_reference_golden(golden_dir):
+    """csrc/sn_weights.cu: power iteration, packing and backward against the torch.nn.utils.spectral_norm fixture."""
+    from contrad_b200 import kernels as K
+    fx = _load(golden_dir, "spectral_norm.pt")
+    with emulated():
+        for name, rec in fx.items():
+            w = rec["weight_orig"].clone()
+            u, v = rec["u0"].clone(), rec["v0"].clone()
+            sigma = torch.zeros(2)
+            K.sn_power_iter(w, u, v, sigma, training=True)
+            assert torch.allclose(u, rec["u1"], atol=1e-5) and torch.allclose(v, rec["v1"], atol=1e-5)
+            w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
+            Cout, Cin, KH, KW = w4.shape
+            fwd = torch.zeros(Cout, KH * KW * Cin)
+            K.sn_pack_weights(w4, sigma, fwd=fwd, ld_fwd=fwd.shape[1], round_out=False)
+            w_hat = fwd.view(Cout, KH, KW, Cin).permute(0, 3, 1, 2).reshape(rec["w_hat"].shape)
+            assert torch.allclose(w_hat, rec["w_hat"], atol=1e-6, rtol=1e-5)
+            wh = rec["w_hat"].clone().requires_grad_(True)
+            y = F.conv2d(rec["x"], wh, rec["bias"], padding=1) if name == "conv" else F.linear(rec["x"], wh, rec["bias"])
+            y.pow(2).sum().backward()
+            g4 = wh.grad if wh.grad.dim() == 4 else wh.grad.view(Cout, Cin, 1, 1)
+            g_packed = g4.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous()
+            dw = torch.empty_like(w4)
+            K.sn_weight_bwd(g_packed, g_packed.shape[1], w4, u, v, sigma, dw)
+            assert torch.allclose(dw.view(rec["grad_weight_orig"].shape), rec["grad_weight_orig"], atol=1e-4, rtol=1e-3)
+
+
+def test_emulated_sn_pack_layouts_and_batched_launches():
+    from contrad_b200 import kernels as K
+    torch.manual_seed(0)
+    with emulated():
+        w = torch.randn(64, 32, 4, 4)
+        dg = torch.zeros(4 * 32, 4 * 64)
+        K.sn_pack_weights(w, None, dgrad=dg, dgrad_mode=2, round_out=False)
+        assert torch.equal(dg, K.pack_dgrad_weight(w, 2))
+        w3 = torch.randn(64, 32, 3, 3)
+        dg, fw = torch.zeros(32, 9 * 64), torch.zeros(64, 9 * 32)
+        K.sn_pack_weights(w3, None, fwd=fw, ld_fwd=9 * 32, dgrad=dg, dgrad_mode=1, round_out=False)
+        assert torch.equal(dg, K.pack_dgrad_weight(w3, 1)) and torch.equal(fw, K.pack_fwd_weight(w3))
+        wl = torch.randn(48, 32 * 4 * 4)
+        t = torch.zeros(4 * 4 * 32, 100)
+        K.sn_pack_weights(wl.view(48, 32, 4, 4), None, dgrad=t, dgrad_mode=3, ldt=100, col0=20, round_out=False)
+        assert torch.equal(t[:, 20:68], wl.view(48, 32, 4, 4).permute(2, 3, 1, 0).reshape(512, 48)) and not t[:, :20].any()
+        # batched == single (power iteration, eval-mode sigma, pack, backward)
+        shapes = [(64, 3, 3, 3), (32, 16, 4, 4), (48, 640), (1, 96)]
+        ws = [torch.randn(*s) * 0.05 for s in shapes]
+        us = [F.normalize(torch.randn(s[0]), dim=0) for s in shapes]
+        vs = [F.normalize(torch.randn(w.numel() // w.shape[0]), dim=0) for w in ws]
+        u1, v1, u2, v2 = [u.clone() for u in us], [v.clone() for v in vs], [u.clone() for u in us], [v.clone() for v in vs]
+        s1, s2, s3 = ([torch.zeros(2) for _ in ws] for _ in range(3))
+        for w, u, v, s in zip(ws, u1, v1, s1):
+            K.sn_power_iter(w, u, v, s, training=True)
+        K.sn_power_iter_batched(list(zip(ws, u2, v2, s2)), training=True)
+        for a, b in zip(u1 + v1 + s1, u2 + v2 + s2):
+            assert torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+        for i, (w, u, v, s) in enumerate(zip(ws, u1, v1, s1)):     # against the oracle's restatement of torch's hook
+            uu, vv = us[i].clone(), vs[i].clone()
+            w_hat = O.spectral_normalize(w, uu, vv, training=True)
+            assert torch.allclose(u, uu, atol=1e-5) and torch.allclose(v, vv, atol=1e-5)
+            assert torch.allclose(w / s[0], w_hat, atol=1e-5, rtol=1e-4) and abs(float(s[0] * s[1]) - 1.0) < 1e-5
+        K.sn_power_iter_batched(list(zip(ws, u2, v2, s3)), training=False)
+        for a, b in zip(s2, s3):
+            assert torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+        w = ws[1]
+        fwd_a, dg_a = torch.empty(32, 16 * 16), torch.empty(4 * 16, 4 * 32)
+        fwd_b, dg_b = torch.empty_like(fwd_a), torch.empty_like(dg_a)
+        K.sn_pack_weights(w, s1[1], fwd=fwd_a, ld_fwd=256, dgrad=dg_a, dgrad_mode=2)
+        K.sn_pack_batched([dict(w4=w, sigma=s1[1], fwd=fwd_b, ld_fwd=256, dgrad=dg_b, dgrad_mode=2)])
+        assert torch.equal(fwd_a, fwd_b) and torch.equal(dg_a, dg_b)
+        g = torch.randn_like(fwd_a)
+        dw_a, dw_b = torch.empty_like(w), torch.empty_like(w)
+        K.sn_weight_bwd(g, 256, w, u1[1], v1[1], s1[1], dw_a)
+        K.sn_weight_bwd_batched([dict(dw_hat_packed=g, ld_fwd=256, w4=w, u=u1[1], v=v1[1], sigma=s1[1], dw=dw_b)])
+        assert torch.allclose(dw_a, dw_b, atol=1e-6, rtol=1e-4)
+
+
+def test_emulated_contrastive_losses(golden_dir):
+    """csrc/losses.cu: NT-Xent / supcon-fake forward + backward against the reference fixtures and, at a batch that spans
+    several column tiles, against the oracle."""
+    from contrad_b200 import kernels as K
+    fx = _load(golden_dir, "contrastive.pt")
+    one = torch.ones(1)
+    with emulated():
+        for case in fx["cases"]:
+            n, a, b, c = case["n"], case["a"], case["b"], case["c"]
+            z = torch.cat([a, b], 0)
+            loss, lse = K.contrastive_fwd(z, n, 0, 0.1)
+            assert abs(float(loss) - case["nt_xent"]) < 2e-5 * abs(case["nt_xent"])
+            assert torch.allclose(K.contrastive_bwd(z, n, 0, 0.1, lse, one), torch.cat(case["nt_xent_grads"], 0), atol=2e-6, rtol=2e-4)
+            z3 = torch.cat([a, b, c], 0)
+            loss, lse = K.contrastive_fwd(z3, n, 1, 0.1)
+            assert abs(float(loss) - case["supcon"]) < 2e-5 * abs(case["supcon"])
+            assert torch.allclose(K.contrastive_bwd(z3, n, 1, 0.1, lse, one * 0.5), torch.cat(case["supcon_grads"], 0) * 0.5,
+                                  atol=2e-6, rtol=2e-4)
+            loss, _ = K.contrastive_fwd(z, n, 0, 0.5)
+            assert abs(float(loss) - case["nt_xent_t05"]) < 2e-5
+        n = 44
+        torch.manual_seed(n)
+        a, b, c = (F.normalize(torch.randn(n, 128)).requires_grad_(True) for _ in range(3))
+        l1 = O.nt_xent(a, b, 0.1); g1 = torch.autograd.grad(l1, [a, b])
+        l2 = O.supcon_fake(a, b, c, 0.1); g2 = torch.autograd.grad(l2, [a, b, c])
+        z = torch.cat([a, b], 0).detach()
+        loss, lse = K.contrastive_fwd(z, n, 0, 0.1)
+        assert abs(float(loss) - float(l1)) < 1e-5 * abs(float(l1))
+        assert torch.allclose(K.contrastive_bwd(z, n, 0, 0.1, lse, one), torch.cat(g1, 0), atol=1e-7, rtol=1e-3)
+        z3 = torch.cat([a, b, c], 0).detach()
+        loss, lse = K.contrastive_fwd(z3, n, 1, 0.1)
+        assert abs(float(loss) - float(l2)) < 1e-5 * abs(float(l2))
+        assert torch.allclose(K.contrastive_bwd(z3, n, 1, 0.1, lse, one), torch.cat(g2, 0), atol=1e-7, rtol=1e-3)
+
+
+def test_emulated_rownorm_gan_losses_colsum_lrelu():
+    from contrad_b200 import kernels as K
+    torch.manual_seed(0)
+    with emulated():
+        big = torch.randn(70, 384)
+        x = big[:, 128:256]
+        xr = x.clone().requires_grad_(True)
+        yr = F.normalize(xr)
+        dy = torch.randn(70, 128)
+        (yr * dy).sum().backward()
+        y, inv = K.rownorm_fwd(x)
+        assert torch.allclose(y, yr.detach(), atol=1e-6)
+        assert torch.allclose(K.rownorm_bwd(dy, y, inv), xr.grad, atol=1e-5, rtol=1e-4)
+        for kind in ("nonsat", "hinge", "wgan", "lsgan"):
+            d = torch.randn(3 * 40, 1)
+            dr = d.clone().requires_grad_(True)
+            ref = O.gan_d_loss(dr[:40], dr[80:], kind)
+            ref.backward()
+            out, g_r, g_g = K.gan_d_loss(d[:40, 0], d[80:, 0], kind)
+            assert abs(float(out[0]) - float(ref)) < 1e-5
+            assert torch.allclose(g_r, dr.grad[:40, 0], atol=1e-6) and torch.allclose(g_g, dr.grad[80:, 0], atol=1e-6)
+            assert abs(float(out[1]) - float(d[:40].mean())) < 1e-6 and abs(float(out[2]) - float(d[80:].mean())) < 1e-6
+            dr = d[:40].clone().requires_grad_(True)
+            ref = O.gan_g_loss(dr, kind); ref.backward()
+            out, g = K.gan_g_loss(d[:40, 0], kind)
+            assert abs(float(out[0]) - float(ref)) < 1e-5 and torch.allclose(g, dr.grad[:, 0], atol=1e-6)
+        for M, N in ((500, 192), (64, 1024), (37, 12), (300, 1), (1, 256), (2000, 8)):
+            x = torch.randn(M, N)
+            assert torch.allclose(K.colsum(x), x.double().sum(0).float(), atol=2e-3, rtol=1e-4), (M, N)
+        act, g = torch.randn(33, 64), torch.randn(33, 64)
+        assert torch.equal(K.lrelu_bwd(g, act, 0.1), torch.where(act > 0, g, 0.1 * g))
+
+
+def test_emulated_batchnorm_and_generator_tail():
+    """csrc/gen_ops.cu: train-mode BatchNorm + ReLU forward / backward (plain NHWC and the (c,h,w)->(h,w,c) remapped
+    first layer), running statistics, the tanh stage - against torch autograd."""
+    from contrad_b200 import kernels as K
+    torch.manual_seed(3)
+    with emulated():
+        for M, C, remap in ((96, 64, 0), (50, 40, 0), (24, 128, 4), (7, 8192, 16)):
+            x = torch.randn(M, C) * 2 + 0.5
+            gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+            rm, rv = torch.zeros(C), torch.ones(C)
+            sums = K.bn_stats(x)
+            stats = K.bn_finalize(sums, M, rm, rv)
+            y = K.bn_apply_relu(x, stats, gamma, beta, remap_s=remap, round_out=False)
+            xr = x.clone().requires_grad_(True)
+            bn = torch.nn.BatchNorm1d(C)
+            bn.weight.data.copy_(gamma); bn.bias.data.copy_(beta)
+            ref = F.relu(bn(xr))
+            dy = torch.randn(M, C)
+            if remap:                                           # output columns are (s, c) instead of (c, s)
+                perm = torch.arange(C).view(C // remap, remap).t().reshape(-1)
+                ref_out, dy_ref = ref[:, perm], None
+            else:
+                perm, ref_out = None, ref
+            assert torch.allclose(y, ref_out.detach(), atol=2e-5, rtol=1e-5), (M, C, remap)
+            assert torch.allclose(rm, bn.running_mean, atol=1e-6) and torch.allclose(rv, bn.running_var, atol=1e-5, rtol=1e-5)
+            (ref_out * dy).sum().backward()
+            bsums = K.bn_bwd_reduce(dy, y, x, stats, remap_s=remap)
+            dx = K.bn_bwd_apply(dy, y, x, stats, gamma, bsums, M, remap_s=remap, round_out=False)
+            assert torch.allclose(dx, xr.grad, atol=5e-5, rtol=1e-4), (M, C, remap, float((dx - xr.grad).abs().max()))
+        pre = torch.randn(3, 8, 8, 32)
+        bias = torch.randn(3)
+        pr = pre.clone().requires_grad_(True)
+        br = bias.clone().requires_grad_(True)
+        ref = 0.5 * torch.tanh(pr[..., :3].permute(0, 3, 1, 2) + br.view(1, 3, 1, 1)) + 0.5       # sndcgan.py:46-48,52
+        out = K.g_final_fwd(pre, bias)
+        assert torch.allclose(out, ref.detach(), atol=1e-6)
+        dout = torch.randn_like(out)
+        (ref * dout).sum().backward()
+        dpre, dbias = K.g_final_bwd(dout, out)
+        assert torch.allclose(dpre, pr.grad[..., :3].permute(0, 3, 1, 2), atol=1e-6)
+        assert torch.allclose(dbias, br.grad, atol=1e-4, rtol=1e-4)
+        t = torch.randn(1000)
+        assert torch.equal(K.round_tf32_(t), K.round_tf32(t))     # kernel (cvt.rna / its C equivalent) vs the torch bit trick
+
+
+def test_emulated_fused_adam_matches_torch_adam():
+    from contrad_b200 import kernels as K
+    torch.manual_seed(0)
+    shapes = [(40, 96), (64, 3, 3, 3), (1, 512), (77,), (16, 8, 4, 4)]
+    pa = [torch.randn(*s) for s in shapes]
+    pb = [torch.nn.Parameter(p.clone()) for p in pa]
+    ma, va = [torch.zeros_like(p) for p in pa], [torch.zeros_like(p) for p in pa]
+    ob = torch.optim.Adam(pb, lr=2e-4, betas=(0.5, 0.999))
+    with emulated():
+        for step in range(1, 4):
+            grads = [torch.randn_like(p) * step for p in pa]
+            for b, g in zip(pb, grads):
+                b.grad = g.clone()
+            lr = 2e-4 * step / 3
+            for grp in ob.param_groups:
+                grp["lr"] = lr
+            ob.step()
+            K.adam_step(list(zip(pa, grads, ma, va)), lr, 0.5, 0.999, 1e-8, step)
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b.detach(), atol=1e-7, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ StyleGAN2-side SIMT kernels (csrc/sg2_ops.cu)
+@pytest.mark.parametrize("nhwc", [True, False])
+@pytest.mark.parametrize("H,W,k,up,down,pad", [(9, 7, (1, 3, 3, 1), 1, 1, (2, 2, 2, 2)), (8, 8, (1, 3, 3, 1), 1, 2, (1, 1, 1, 1)),
+                                               (5, 6, (1, 3, 3, 1), 2, 1, (2, 1, 2, 1)), (6, 5, (1, 2, 1), 2, 3, (0, 3, 0, 3)),
+                                               (8, 8, (1, 3, 3, 1), 1, 1, (-1, 2, -1, 2))])
+def test_emulated_upfirdn2d(nhwc, H, W, k, up, down, pad):
+    from contrad_b200 import sg2_kernels as S
+    from tests import cpu_kernels as CK
+    torch.manual_seed(H * 100 + W + up + down)
+    C = 5 if not nhwc else 36
+    x = torch.randn(2, H, W, C) if nhwc else torch.randn(2, C, H, W)
+    fir = torch.tensor(k, dtype=torch.float32)
+    fir = fir[None] * fir[:, None]
+    fir = fir / fir.sum() * up * up
+    fir[0, 1] += 0.01                                       # break the symmetry so that flipping is observable
+    with emulated():
+        for flip in (False, True):
+            got = S.upfirdn2d(x, fir, up, down, pad, nhwc=nhwc, flip=flip, gain=1.5)
+            want = CK.upfirdn2d(x, fir, up, down, pad, nhwc=nhwc, flip=flip, gain=1.5)
+            assert got.shape == want.shape and _rel(got, want) < 1e-5
+        oh = (H * up + pad[2] + pad[3] - fir.shape[0]) // down + 2
+        assert _rel(S.upfirdn2d(x, fir, up, down, pad, out_hw=(oh, oh), nhwc=nhwc),
+                    CK.upfirdn2d(x, fir, up, down, pad, out_hw=(oh, oh), nhwc=nhwc)) < 1e-5
+
+
+def test_emulated_sg2_elementwise_and_reduction_kernels():
+    from contrad_b200 import sg2_kernels as S
+    from tests import cpu_kernels as CK
+    torch.manual_seed(0)
+    with emulated():
+        for B, Ho, C in ((2, 4, 32), (3, 1, 8)):
+            x = torch.randn(B, 2 * Ho + 1, 2 * Ho + 1, C)
+            assert torch.equal(S.patch_s2_gather(x), CK.patch_s2_gather(x))
+            u = torch.randn(B, Ho, Ho, 9, C)
+            assert _rel(S.patch_s2_scatter(u), CK.patch_s2_scatter(u)) < 1e-6
+        B, H, C = 4, 8, 48
+        x, res, bias, g = torch.randn(B, H, H, C), torch.randn(B, H, H, C), torch.randn(C), torch.randn(B, H, H, C)
+        assert _rel(S.bias_act(x, bias, 0.2, 1.4, res=res), CK.bias_act(x, bias, 0.2, 1.4, res=res)) < 1e-6
+        assert _rel(S.bias_act(x, None, 0.1, 1.0), CK.bias_act(x, None, 0.1, 1.0)) < 1e-6
+        assert _rel(S.bias_act_grad(g, x, bias, 0.2, 1.4), CK.bias_act_grad(g, x, bias, 0.2, 1.4)) < 1e-6
+        assert _rel(S.bias_act(x, bias, 0.2, 1.4, round_out=True), CK.bias_act(x, bias, 0.2, 1.4)) < 6e-4
+        s = torch.randn(B, C)
+        const = torch.randn(1, H, H, C)
+        assert _rel(S.modulate(x, s), CK.modulate(x, s)) < 1e-6 and _rel(S.modulate(const, s), CK.modulate(const, s)) < 1e-6
+        assert _rel(S.mul_reduce(x, res), CK.mul_reduce(x, res)) < 1e-5
+        assert _rel(S.mul_reduce(x, const), CK.mul_reduce(x, const.expand(B, -1, -1, -1))) < 1e-5
+        noise, nw, d = torch.randn(B, 1, H, H), torch.randn(1), torch.rand(B, C) + 0.5
+        assert _rel(S.mod_epilogue(x, d, noise, nw, bias), CK.mod_epilogue(x, d, noise, nw, bias)) < 1e-6
+        assert _rel(S.mod_epilogue(x, None, noise, nw, bias), CK.mod_epilogue(x, None, noise, nw, bias)) < 1e-6
+        assert _rel(S.noise_grad(g, noise), CK.noise_grad(g, noise)) < 1e-4
+        big, big2 = torch.randn(2, 32, 32, 40), torch.randn(2, 32, 32, 40)       # P > 512: the split-P path of mul_reduce
+        assert _rel(S.mul_reduce(big, big2), CK.mul_reduce(big, big2)) < 1e-4
+        for Bs in (4, 3, 12):                                                   # minibatch stddev incl. second order
+            Cs, Hs = 40, 4
+            xs = torch.randn(Bs, Hs, Hs, Cs)
+            std = CK.stddev_fwd(xs)
+            assert _rel(S.stddev_fwd(xs), std) < 1e-5
+            dstd, gg = torch.randn_like(std), torch.randn_like(xs)
+            assert _rel(S.stddev_bwd(dstd, xs), CK.stddev_bwd(dstd, xs)) < 1e-5
+            got, want = S.stddev_bwd_bwd(gg, dstd, xs), CK.stddev_bwd_bwd(gg, dstd, xs)
+            assert _rel(got[0], want[0]) < 1e-4 and _rel(got[1], want[1]) < 1e-4
+            assert torch.equal(S.stddev_concat(xs, std, 64), CK.stddev_concat(xs, std, 64))
+            dy = torch.randn(Bs, Hs, Hs, 64)
+            got, want = S.stddev_split(dy, Cs), CK.stddev_split(dy, Cs)
+            assert torch.equal(got[0], want[0]) and _rel(got[1], want[1]) < 1e-5
+        xi = torch.rand(3, 3, 16, 16)
+        assert _rel(S.rgb_to_nhwc(xi, 32, 2.0, -1.0), CK.rgb_to_nhwc(xi, 32, 2.0, -1.0)) < 1e-6
+        src, resi = torch.randn(3, 16, 16, 32), torch.randn(3, 3, 16, 16)
+        assert _rel(S.nhwc_to_rgb(src, resi, 0.5), CK.nhwc_to_rgb(src, resi, 0.5)) < 1e-6
+        assert _rel(S.nhwc_to_rgb(src, None, 2.0), CK.nhwc_to_rgb(src, None, 2.0)) < 1e-6
+        z = torch.randn(7, 512)
+        assert _rel(S.pixelnorm(z), CK.pixelnorm(z)) < 1e-5
+        gr = torch.randn(6, 3, 32, 32)
+        assert _rel(S.row_sqsum(gr), CK.row_sqsum(gr)) < 1e-5
+        sc = torch.randn(6)
+        assert _rel(S.row_scale(gr, sc, 2.0), CK.row_scale(gr, sc, 2.0)) < 1e-6
+        a, b = torch.randn(1000), torch.randn(1000)
+        assert _rel(S.axpby(a, b, 0.5, -2.0, 0.25), CK.axpby(a, b, 0.5, -2.0, 0.25)) < 1e-6
+        assert _rel(S.axpby(a, None, 0.5, 0.0, 0.5), CK.axpby(a, None, 0.5, 0.0, 0.5)) < 1e-6
+        dst = [torch.randn(n) for n in (5, 4096, 7001) * 25]                     # 75 tensors: two launches
+        src_ = [torch.randn_like(t) for t in dst]
+        mine = [t.clone() for t in dst]
+        S.ema_lerp(list(zip(mine, src_)), 0.75)
+        CK.ema_lerp(list(zip(dst, src_)), 0.75)
+        assert max(_rel(a_, b_) for a_, b_ in zip(mine, dst)) < 1e-6
+
+
+# ------------------------------------------------------------------ the fused SimCLR chain and the first D layer
+def test_emulated_fused_augment_matches_reference_golden(golden_dir):
+    """csrc/augment.cu, the headline augmentation kernels (persistent CTAs, bulk-copy ring, column mapping) and their
+    backward, on the fixtures produced by the unmodified reference chain; the any-size kernels and the uint8 / mixed-
+    source launch on the same data."""
+    from contrad_b200 import kernels as K
+    fx = _load(golden_dir, "augment_simclr.pt")
+    with emulated():
+        for case in fx["cases"]:
+            x, dy, params = case["x"], case["dy"], case["params"]
+            y = K.augment_simclr_fwd(x, params, case["order"])
+            dx = K.augment_simclr_bwd(x, dy, params, case["order"])
+            assert torch.allclose(y, case["y"], atol=2e-5, rtol=0), float((y - case["y"]).abs().max())
+            assert torch.allclose(dx, case["dx"], atol=1e-4, rtol=1e-4), float((dx - case["dx"]).abs().max())
+            y2, means = K.augment_simclr_large_fwd(x, params, case["order"])
+            dx2 = K.augment_simclr_large_bwd(x, dy, params, case["order"], means)
+            assert torch.allclose(y2, case["y"], atol=2e-5, rtol=0) and torch.allclose(dx2, case["dx"], atol=1e-4, rtol=1e-4)
+        for case in _load(golden_dir, "augment_aux.pt")["uint8"]:
+            n = case["x_u8"].shape[0]
+            y, _ = K.augment_simclr_mixed_fwd(case["x_u8"], 2 * n, case["fakes"], case["params"], case["order"])
+            assert torch.allclose(y, case["y"], atol=2e-5, rtol=0), float((y - case["y"]).abs().max())
+
+
+def test_emulated_fused_augment_persistent_ring_vs_oracle():
+    """More images than the (emulated 4-SM) grid has CTAs: every CTA walks several images through the two-slot prefetch
+    ring; per-image jitter order from row 11 (order = -1, the CUDA-graph mode)."""
+    from contrad_b200 import kernels as K
+    np.random.seed(0); torch.manual_seed(0)
+    B, size = 70, 32
+    x, dy = torch.rand(B, 3, size, size), torch.randn(B, 3, size, size)
+    params, order = O.sample_simclr_params(B, size, size)
+    xr = x.clone().requires_grad_(True)
+    yr = O.augment_simclr(xr, params, order)
+    (yr * dy).sum().backward()
+    packed = O.pack_params(params)
+    with emulated():
+        y = K.augment_simclr_fwd(x, packed, order)
+        assert torch.allclose(y, yr.detach(), atol=2e-5, rtol=0)
+        dx = K.augment_simclr_bwd(x, dy, packed, order)
+        bad = ((dx - xr.grad).abs() > 1e-4 + 1e-4 * xr.grad.abs()).float().mean()
+        assert bad < 2e-3, bad                       # a pixel within rounding of the clamp boundary may flip its mask
+        with_row = torch.cat([packed, torch.full((1, B), float(order))])
+        assert torch.equal(K.augment_simclr_fwd(x, with_row, -1), y)
+        x_u8 = (x[:20] * 255).round().to(torch.uint8)
+        y_mixed, _ = K.augment_simclr_mixed_fwd(x_u8, 40, x[40:], packed, order)
+        y_cat = K.augment_simclr_fwd(torch.cat([O.to_tensor_u8(x_u8)] * 2 + [x[40:]]), packed, order)
+        assert torch.equal(y_mixed, y_cat)           # bit-equal, as on the B200
+
+
+@pytest.mark.parametrize("B,H", [(3, 32), (2, 16)])
+def test_emulated_conv_first_layer(B, H):
+    """csrc/conv_first.cu: Conv2d(3 -> 64) with the x*2-1 input affine, its weight / bias gradient (persistent CTAs,
+    bulk-copied dY tiles) and the channel extraction of the data gradient."""
+    from contrad_b200 import kernels as K
+    torch.manual_seed(B)
+    x = torch.rand(B, 3, H, H)
+    w, bias = torch.randn(64, 3, 3, 3) * 0.1, torch.randn(64) * 0.1
+    sigma = torch.tensor([2.0, 0.5])
+    with emulated():
+        y = K.conv_first_fwd(x, w, sigma, bias, slope=0.1, round_out=False)
+        ref = F.leaky_relu(F.conv2d(x.double() * 2 - 1, w.double() * 0.5, bias.double(), padding=1), 0.1)
+        assert torch.allclose(y, ref.permute(0, 2, 3, 1).float(), atol=1e-5, rtol=1e-5)
+        dy = torch.randn(B, H, H, 64)
+        dw, db = K.conv_first_wgrad(x, dy)
+        ref_dw = torch.nn.grad.conv2d_weight(x.double() * 2 - 1, (64, 3, 3, 3), dy.permute(0, 3, 1, 2).double(), padding=1)
+        assert torch.allclose(dw.view(64, 3, 3, 3), ref_dw.float(), atol=1e-3, rtol=1e-4)
+        assert torch.allclose(db, dy.sum(dim=(0, 1, 2)), atol=1e-3, rtol=1e-4)
+        dpad = torch.randn(B, H, H, 32)
+        dx = K.conv_first_dgrad_finish(dpad)
+        assert torch.allclose(dx, 2 * dpad[..., :3].permute(0, 3, 1, 2), atol=1e-6)
