@@ -102,30 +102,38 @@ struct Cfg {
 };
 inline Cfg cfg(dim3 g, dim3 b, size_t smem = 0, cudaStream_t = nullptr) { return Cfg{g, b, smem}; }
 
+// The threads of a block are host threads created ONCE per launch; they walk the grid block by block in lockstep (a
+// fresh Block context - barriers, dynamic shared memory - is installed between two blocks by the completion step of the
+// `next` barrier, while every thread is parked in it).
 template <class F>
 void launch(const Cfg& c, F&& body) {
     const int nthreads = (int)(c.block.x * c.block.y * c.block.z);
-    for (unsigned bz = 0; bz < c.grid.z; ++bz)
-        for (unsigned by = 0; by < c.grid.y; ++by)
-            for (unsigned bx = 0; bx < c.grid.x; ++bx) {
-                Block b(nthreads, c.smem);
-                std::vector<std::thread> threads;
-                threads.reserve(nthreads);
-                for (int t = 0; t < nthreads; ++t) {
-                    threads.emplace_back([&, t]() {
-                        blk = &b;
-                        tid = t;
-                        threadIdx = uint3{t % c.block.x, (t / c.block.x) % c.block.y, t / (c.block.x * c.block.y)};
-                        blockIdx = uint3{bx, by, bz};
-                        blockDim = c.block;
-                        gridDim = c.grid;
-                        body();
-                        b.warps[t / 32]->bar.arrive_and_drop();     // an exited thread no longer takes part in barriers
-                        b.bar.arrive_and_drop();
-                    });
-                }
-                for (auto& th : threads) th.join();
+    const long long nblocks = (long long)c.grid.x * c.grid.y * c.grid.z;
+    if (nthreads <= 0 || nblocks <= 0) return;
+    std::unique_ptr<Block> cur(new Block(nthreads, c.smem));
+    auto install_next = [&]() noexcept { cur.reset(new Block(nthreads, c.smem)); };
+    std::barrier<decltype(install_next)> next(nthreads, install_next);
+    std::vector<std::thread> threads;
+    threads.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        threads.emplace_back([&, t]() {
+            tid = t;
+            threadIdx = uint3{t % c.block.x, (t / c.block.x) % c.block.y, t / (c.block.x * c.block.y)};
+            blockDim = c.block;
+            gridDim = c.grid;
+            for (long long i = 0; i < nblocks; ++i) {
+                Block* b = cur.get();
+                blk = b;
+                blockIdx = uint3{(unsigned)(i % c.grid.x), (unsigned)((i / c.grid.x) % c.grid.y),
+                                 (unsigned)(i / ((long long)c.grid.x * c.grid.y))};
+                body();
+                b->warps[t / 32]->bar.arrive_and_drop();         // an exited thread no longer takes part in barriers
+                b->bar.arrive_and_drop();
+                next.arrive_and_wait();
             }
+        });
+    }
+    for (auto& th : threads) th.join();
 }
 
 template <class T> inline uint64_t to_bits(T v) { uint64_t u = 0; memcpy(&u, &v, sizeof(T)); return u; }

@@ -438,3 +438,84 @@ def test_emulated_conv_first_layer(B, H):
         dpad = torch.randn(B, H, H, 32)
         dx = K.conv_first_dgrad_finish(dpad)
         assert torch.allclose(dx, 2 * dpad[..., :3].permute(0, 3, 1, 2), atol=1e-6)
+
+
+# ------------------------------------------------------------------ the product's train step on the CPU
+def test_product_train_step_on_cpu_vs_oracle():
+    """BASELINE configs[0] in spirit ("SNDCGAN+ContraD on CPU, one step, synthetic 32x32: plumbing, no GPU"): the PRODUCT's
+    own modules, autograd Functions, engine.train_step and every SIMT kernel (emulated) run one complete D+G step incl.
+    spectral norm and the optimiser on CPU tensors; only the tcgen05 entry points are torch stand-ins
+    (tests/cpu_tc_standins.py).  Scalars, gradient norms and updated buffers against the fp32 oracle on identical weights,
+    latents and augmentation draws.  Heads / generator at reduced width to keep the emulation short."""
+    from types import SimpleNamespace
+    import tests.cpu_tc_standins as TC
+    from contrad_b200 import engine
+    from contrad_b200.functional import AugmentSimCLRFn
+    from contrad_b200.models.gan.sndcgan import D_SNDCGAN, G_SNDCGAN
+    from contrad_b200.training.gan import contrad
+    n, ngf, nz, d_hidden = 6, 64, 16, 16          # ngf = 64: the last generator layer reuses the 64-channel first-layer kernels
+    gen_w = torch.Generator().manual_seed(5)
+    sd_d = O.make_d_state(d_hidden=d_hidden, generator=gen_w)
+    sd_g = O.make_g_state(ngf=ngf, nz=nz, generator=gen_w)
+    np.random.seed(11); torch.manual_seed(11)
+    images = torch.rand(n, 3, 32, 32)
+    z_d = O.sample_latent(n, nz); aug_d = O.sample_simclr_params(3 * n, 32, 32)
+    z_g = O.sample_latent(n, nz); aug_g = O.sample_simclr_params(n, 32, 32)
+
+    # ---- oracle
+    sd_d_o = {k: v.clone() for k, v in sd_d.items()}
+    sd_g_o = {k: v.clone() for k, v in sd_g.items()}
+    opt_g_o, opt_d_o = O.Adam(O.trainable(sd_g_o).values(), 2e-4), O.Adam(O.trainable(sd_d_o).values(), 2e-4)
+    orig_g = O.g_sndcgan_forward
+    O.g_sndcgan_forward = lambda sd, z, **kw: orig_g(sd, z, ngf=ngf)
+    try:
+        ref = O.train_step(sd_g_o, sd_d_o, opt_g_o, opt_d_o, images, z_d, z_g, aug_d, aug_g, step=1)
+    finally:
+        O.g_sndcgan_forward = orig_g
+
+    # ---- product on CPU tensors
+    class Aug(torch.nn.Module):
+        def __init__(self, blocks):
+            super().__init__(); self.blocks = list(blocks)
+        def forward(self, x):
+            packed, order = self.blocks.pop(0)
+            return AugmentSimCLRFn.apply(x, packed, order)
+
+    class Gw(torch.nn.Module):
+        def __init__(self, g, zs):
+            super().__init__(); self.g, self.zs = g, list(zs)
+        def sample_latent(self, k):
+            return self.zs.pop(0)
+        def forward(self, z):
+            return self.g(z)
+        def parameters(self, recurse=True):
+            return self.g.parameters(recurse)
+        def train(self, mode=True):
+            self.g.train(mode); return self
+
+    with emulated(), TC.patched():
+        D = D_SNDCGAN((32, 32, 3), mlp_linear=True, d_hidden=d_hidden)
+        G = G_SNDCGAN((32, 32, 3), ngf=ngf, nz=nz)
+        D.load_state_dict(sd_d); G.load_state_dict(sd_g)
+        P = SimpleNamespace(augment_fn=Aug([(O.pack_params(aug_d[0]), aug_d[1]), (O.pack_params(aug_g[0]), aug_g[1])]),
+                            temp=0.1, lbd_a=1.0, distributed=False)
+        opts = {"loss": "nonsat", "warmup": 3000, "lr": 2e-4}
+        opt_G = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        opt_D = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        got = engine.train_step(P, opts, {"D": contrad.loss_D_fn, "G": contrad.loss_G_fn}, (Gw(G, [z_d, z_g]), D),
+                                (opt_G, opt_D), images, 1, record_grad_norms=True)
+    got = {k: float(v) for k, v in got.items()}
+    rel = lambda a, b: abs(a - b) / max(abs(b), 1e-12)
+    # TF32 rounding of the GEMM operands is part of the product's arithmetic (done by the producing kernels): 1e-3 bars
+    assert rel(got["d_loss"], ref["l_con_pos"] + ref["l_con_neg"]) < 1e-3, (got, ref)
+    assert rel(got["d_penalty"], ref["l_dis"]) < 1e-3 and rel(got["g_loss"], ref["l_gen"]) < 1e-3, (got, ref)
+    assert abs(got["d_real"] - ref["d_real"]) < 1e-3 and abs(got["d_gen"] - ref["d_gen"]) < 1e-3
+    assert rel(got["d_grad_norm"], ref["d_grad_norm"]) < 5e-3, (got["d_grad_norm"], ref["d_grad_norm"])
+    assert rel(got["g_grad_norm"], ref["g_grad_norm"]) < 3e-2, (got["g_grad_norm"], ref["g_grad_norm"])
+    sd_now = D.state_dict()
+    for k, v in sd_d_o.items():
+        if k.endswith(("weight_u", "weight_v")):                      # two power iterations (D step + G step)
+            assert torch.allclose(sd_now[k], v, atol=2e-4), k
+    g_now = G.state_dict()
+    for k in ("norm_init.running_mean", "main.1.running_var", "main.7.running_mean"):
+        assert torch.allclose(g_now[k], sd_g_o[k], atol=1e-4, rtol=1e-3), k
