@@ -221,18 +221,19 @@ g_final_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ bias
 }
 
 // dpre[n,c,h,w] = dout * 0.5 * (1 - t^2), t = 2*out - 1;  dbias[c] += sum dpre
+// Grid-stride: a CTA folds many elements before its three atomics (one element per thread meant 3 same-address
+// atomics per 256 elements - 18 k serialised atomics at b512, 35 us for a 6 MB tensor).
 __global__ void __launch_bounds__(kT)
 g_final_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dpre,
                    float* __restrict__ dbias, int HW, long long total) {
     __shared__ float red[3 * 32];
-    const long long i = (long long)blockIdx.x * kT + threadIdx.x;
     float s[3] = {0.f, 0.f, 0.f};
-    if (i < total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
         const float t = 2.f * out[i] - 1.f;
         const float g = dout[i] * 0.5f * (1.f - t * t);
         dpre[i] = g;
         const int c = (int)((i / HW) % 3);
-        s[0] = c == 0 ? g : 0.f; s[1] = c == 1 ? g : 0.f; s[2] = c == 2 ? g : 0.f;
+        s[0] += c == 0 ? g : 0.f; s[1] += c == 1 ? g : 0.f; s[2] += c == 2 ? g : 0.f;
     }
     block_sum<3>(s, red);
     if (threadIdx.x == 0 && dbias) { atomicAdd(dbias + 0, s[0]); atomicAdd(dbias + 1, s[1]); atomicAdd(dbias + 2, s[2]); }
@@ -254,9 +255,17 @@ round_tf32_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, long
     }
 }
 
-int row_chunks(int M, int* rows_per_cta) {
+// Row chunks of the column-reduction grids: about 128 rows per chunk, but never fewer CTAs than ~8 per SM over the whole
+// (column blocks x chunks) grid - [512, 8192] used to run on 128 CTAs, [32768, 256] on 256 (0.8 - 2 TB/s, ncu launch
+// list of round 1) - and at least 4 rows per row lane so that the unrolled loop body is used.
+int row_chunks(int M, int col_blocks, int lanes, int* rows_per_cta) {
     int chunks = (M + 127) / 128;
+    const int want = (148 * 8 + col_blocks - 1) / col_blocks;
+    if (chunks < want) chunks = want;
+    const int most = M / (4 * lanes);
+    if (chunks > most) chunks = most;
     if (chunks > 1024) chunks = 1024;
+    if (chunks < 1) chunks = 1;
     *rows_per_cta = (M + chunks - 1) / chunks;
     return (M + *rows_per_cta - 1) / *rows_per_cta;
 }
@@ -276,8 +285,8 @@ extern "C" int cb200_bn_stats(const float* x, int M, int C, float* sums, void* s
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
     if (e != cudaSuccess) { cb200_set_error("bn_stats: memset: %s", cudaGetErrorString(e)); return (int)e; }
     int rpc;
-    const int chunks = row_chunks(M, &rpc);
     const int cc = col_lanes(C);
+    const int chunks = row_chunks(M, (C + cc - 1) / cc, kT / cc, &rpc);
     bn_stats_kernel<<<dim3((C + cc - 1) / cc, chunks), kT, 0, st>>>(x, M, C, cc, rpc, sums);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("bn_stats");
@@ -321,8 +330,8 @@ extern "C" int cb200_bn_bwd_reduce(const float* dy, const float* y, const float*
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
     if (e != cudaSuccess) { cb200_set_error("bn_bwd_reduce: memset: %s", cudaGetErrorString(e)); return (int)e; }
     int rpc;
-    const int chunks = row_chunks(M, &rpc);
     const int cc = col_lanes(C);
+    const int chunks = row_chunks(M, (C + cc - 1) / cc, kT / cc, &rpc);
     bn_bwd_reduce_kernel<<<dim3((C + cc - 1) / cc, chunks), kT, 0, st>>>(dy, y, x, stats, M, C, remap_s, cc, rpc, sums);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("bn_bwd_reduce");
@@ -371,7 +380,9 @@ extern "C" int cb200_g_final_bwd(const float* dout, const float* out, float* dpr
         if (e != cudaSuccess) { cb200_set_error("g_final_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
     const long long total = (long long)B * 3 * H * W;
-    g_final_bwd_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, st>>>(dout, out, dpre, dbias, H * W, total);
+    long long grid = (total + kT - 1) / kT;
+    if (grid > 148 * 4) grid = 148 * 4;
+    g_final_bwd_kernel<<<(unsigned)grid, kT, 0, st>>>(dout, out, dpre, dbias, H * W, total);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("g_final_bwd");
     return CB200_OK;

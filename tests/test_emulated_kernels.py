@@ -220,7 +220,7 @@ def test_emulated_batchnorm_and_generator_tail():
     from contrad_b200 import kernels as K
     torch.manual_seed(3)
     with emulated():
-        for M, C, remap in ((96, 64, 0), (50, 40, 0), (24, 128, 4), (7, 8192, 16)):
+        for M, C, remap in ((96, 64, 0), (50, 40, 0), (24, 128, 4), (7, 8192, 16), (3000, 64, 0), (700, 256, 0), (64, 1024, 4)):
             x = torch.randn(M, C) * 2 + 0.5
             gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.1
             rm, rv = torch.zeros(C), torch.ones(C)
@@ -243,7 +243,7 @@ def test_emulated_batchnorm_and_generator_tail():
             bsums = K.bn_bwd_reduce(dy, y, x, stats, remap_s=remap)
             dx = K.bn_bwd_apply(dy, y, x, stats, gamma, bsums, M, remap_s=remap, round_out=False)
             assert torch.allclose(dx, xr.grad, atol=5e-5, rtol=1e-4), (M, C, remap, float((dx - xr.grad).abs().max()))
-        pre = torch.randn(3, 8, 8, 32)
+        pre = torch.randn(6, 96, 96, 32)                          # 165 888 outputs > 592 CTAs x 256: the grid-stride loop iterates
         bias = torch.randn(3)
         pr = pre.clone().requires_grad_(True)
         br = bias.clone().requires_grad_(True)
