@@ -444,9 +444,26 @@ __device__ __forceinline__ void pack_tile_body(const SnPackBatch& p, int l, cons
     const float* __restrict__ w = p.w[l];
     const int ncols = g.n_ci * KK;
     const bool rnd = p.do_round[l] != 0;
+    // Full tiles with a compile-time tap count issue ALL loads of a row (KK per lane) before the first shared-memory
+    // store: with 4 in flight (the unroll of the generic loop) three resident CTAs kept ~12 KB per SM in flight, a
+    // third of what the HBM latency-bandwidth product needs (1.9 TB/s in the round-1 launch list).
+    const bool full = KKc > 1 && g.n_ci == 32 && g.CT == 32;
     for (int r = warp; r < g.n_co; r += kT / 32) {
         const float* src = w + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
         float* row = tile + r * g.RS;
+        if (full) {
+            float val[KKc ? KKc : 1];
+#pragma unroll
+            for (int i = 0; i < KKc; ++i) val[i] = __ldg(src + lane + 32 * i);
+#pragma unroll
+            for (int i = 0; i < KKc; ++i) {
+                const int t = lane + 32 * i;
+                float o = val[i] * inv;
+                if (rnd) o = round_tf32(o);
+                row[(t % KKc) * 33 + t / KKc] = o;
+            }
+            continue;
+        }
 #pragma unroll 4
         for (int t = lane; t < ncols; t += 32) {
             float val = __ldg(src + t) * inv;
@@ -501,13 +518,24 @@ __global__ void __launch_bounds__(kT) sn_pack_tiled_kernel(const __grid_constant
     else pack_tile_body<0>(p, l, g, tile);
 }
 
-// Stage dW_hat (forward-pack order) of one tile into shared memory: coalesced along ci.
+// Stage dW_hat (forward-pack order) of one tile into shared memory: coalesced along ci.  KKc > 1 on a full tile: the KK
+// loads of a row are issued back to back (the generic loop has one load in flight per lane).
+template <int KKc>
 __device__ __forceinline__ void load_dwp_tile(const float* __restrict__ dwp, long long ld, int Cin, const TileGeom& g,
                                               float* tile) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool full = KKc > 1 && g.n_ci == 32 && g.CT == 32;
     for (int r = warp; r < g.n_co; r += kT / 32) {
         const float* src = dwp + (long long)(g.co0 + r) * ld + g.ci0;
         float* row = tile + r * g.RS;
+        if (full) {
+            float val[KKc ? KKc : 1];
+#pragma unroll
+            for (int kk = 0; kk < KKc; ++kk) val[kk] = __ldg(src + (long long)kk * Cin + lane);
+#pragma unroll
+            for (int kk = 0; kk < KKc; ++kk) row[kk * 33 + lane] = val[kk];
+            continue;
+        }
         for (int kk = 0; kk < g.KK; ++kk)
 #pragma unroll 4
             for (int ci = lane; ci < g.n_ci; ci += 32) row[kk * (g.CT + 1) + ci] = __ldg(src + (long long)kk * Cin + ci);
@@ -522,9 +550,21 @@ __device__ __forceinline__ float dot_tile_body(const SnBwdBatch& p, int l, const
     const long long F = (long long)p.cin[l] * KK;
     const int ncols = g.n_ci * KK;
     float a = 0.f;
+    const bool full = KKc > 1 && g.n_ci == 32 && g.CT == 32;
     for (int r = warp; r < g.n_co; r += kT / 32) {
         const float* src = p.w[l] + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
         const float* row = tile + r * g.RS;
+        if (full) {
+            float val[KKc ? KKc : 1];
+#pragma unroll
+            for (int i = 0; i < KKc; ++i) val[i] = __ldg(src + lane + 32 * i);
+#pragma unroll
+            for (int i = 0; i < KKc; ++i) {
+                const int t = lane + 32 * i;
+                a += val[i] * row[(t % KKc) * 33 + t / KKc];
+            }
+            continue;
+        }
 #pragma unroll 4
         for (int t = lane; t < ncols; t += 32) a += __ldg(src + t) * row[(t % KK) * (g.CT + 1) + t / KK];
     }
@@ -537,7 +577,9 @@ __global__ void __launch_bounds__(kT) sn_bwd_dot_tiled_kernel(const __grid_const
     const int l = find_layer(p.cta_begin, p.n, blockIdx.x);
     const int Cin = p.cin[l], KK = p.kh[l] * p.kw[l];
     const TileGeom g = tile_geom(blockIdx.x - p.cta_begin[l], p.cout[l], Cin, KK);
-    load_dwp_tile(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    if (KK == 9) load_dwp_tile<9>(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    else if (KK == 16) load_dwp_tile<16>(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    else load_dwp_tile<0>(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
     float a[1];
     if (KK == 1) a[0] = dot_tile_body<1>(p, l, g, tile);
     else if (KK == 9) a[0] = dot_tile_body<9>(p, l, g, tile);
@@ -560,6 +602,17 @@ __device__ __forceinline__ void apply_tile_body(const SnBwdBatch& p, int l, cons
         const float su = scale * p.u[l][g.co0 + r];
         float* dst = p.dw[l] + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
         const float* row = tile + r * g.RS;
+        if (KKc > 1 && g.n_ci == 32 && g.CT == 32) {
+            float vv[KKc ? KKc : 1];
+#pragma unroll
+            for (int i = 0; i < KKc; ++i) vv[i] = __ldg(v + lane + 32 * i);
+#pragma unroll
+            for (int i = 0; i < KKc; ++i) {
+                const int t = lane + 32 * i;
+                dst[t] = (row[(t % KKc) * 33 + t / KKc] - su * vv[i]) * inv;
+            }
+            continue;
+        }
 #pragma unroll 4
         for (int t = lane; t < ncols; t += 32) dst[t] = (row[(t % KK) * (g.CT + 1) + t / KK] - su * __ldg(v + t)) * inv;
     }
@@ -570,7 +623,9 @@ __global__ void __launch_bounds__(kT) sn_bwd_apply_tiled_kernel(const __grid_con
     const int l = find_layer(p.cta_begin, p.n, blockIdx.x);
     const int Cin = p.cin[l], KK = p.kh[l] * p.kw[l];
     const TileGeom g = tile_geom(blockIdx.x - p.cta_begin[l], p.cout[l], Cin, KK);
-    load_dwp_tile(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    if (KK == 9) load_dwp_tile<9>(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    else if (KK == 16) load_dwp_tile<16>(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
+    else load_dwp_tile<0>(p.dwp[l], p.ld_fwd[l], Cin, g, tile);
     if (KK == 1) apply_tile_body<1>(p, l, g, tile);
     else if (KK == 9) apply_tile_body<9>(p, l, g, tile);
     else if (KK == 16) apply_tile_body<16>(p, l, g, tile);
