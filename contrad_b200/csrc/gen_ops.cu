@@ -8,6 +8,7 @@
 // `0.5 * y + 0.5`).  Under DDP the reference converts BN to SyncBatchNorm (train_gan.py:268): the two-phase
 // split here (partial sums -> finalize) lets the host all-reduce the [2, C] sums between the phases.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -207,6 +208,53 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, c
     dx[src] = round_out ? round_tf32(v) : v;
 }
 
+// Row-tiled variants of the two remapped kernels (the generator's first BatchNorm: features in the reference's (c,h,w)
+// order on the input side, NHWC on the output side).  One CTA moves one sample row through shared memory so that BOTH
+// layouts are read / written along their contiguous index; the element-indexed kernels above read the input side with a
+// stride of S floats (0.8 - 1.1 TB/s in the round-1 launch list).  tile[c * (S + 1) + s]: the odd stride keeps the
+// (s-major) and the (c-major) accesses conflict-free.  Dynamic shared memory: (F / S) * (S + 1) floats.
+__global__ void __launch_bounds__(kT)
+bn_apply_relu_rows_kernel(const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ y, int F, int S, int round_out) {
+    extern __shared__ float tile[];
+    const int ch = F / S;
+    const float* xr = x + (long long)blockIdx.x * F;
+    float* yr = y + (long long)blockIdx.x * F;
+    for (int f = threadIdx.x; f < F; f += kT) {                       // input side: f = c * S + s
+        float v = (xr[f] - stats[f]) * stats[F + f] * gamma[f] + beta[f];
+        v = fmaxf(v, 0.f);
+        const int c = f / S, sp = f - c * S;
+        tile[c * (S + 1) + sp] = round_out ? round_tf32(v) : v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < F; r += kT) {                       // output side: r = s * ch + c
+        const int sp = r / ch, c = r - sp * ch;
+        yr[r] = tile[c * (S + 1) + sp];
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_rows_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ x,
+                         const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ sums,
+                         float count, float* __restrict__ dx, int F, int S, int round_out) {
+    extern __shared__ float tile[];
+    const int ch = F / S;
+    const long long row = (long long)blockIdx.x * F;
+    for (int r = threadIdx.x; r < F; r += kT) {                       // output side: masked gradient
+        const int sp = r / ch, c = r - sp * ch;
+        tile[c * (S + 1) + sp] = (y[row + r] > 0.f) ? dy[row + r] : 0.f;
+    }
+    __syncthreads();
+    const float inv = 1.f / count;
+    for (int f = threadIdx.x; f < F; f += kT) {                       // input side
+        const int c = f / S, sp = f - c * S;
+        const float rstd = stats[F + f];
+        const float xh = (x[row + f] - stats[f]) * rstd;
+        const float v = gamma[f] * rstd * (tile[c * (S + 1) + sp] - sums[f] * inv - xh * sums[F + f] * inv);
+        dx[row + f] = round_out ? round_tf32(v) : v;
+    }
+}
+
 // out[n,c,h,w] = 0.5 * tanh(pre[n,h,w,c] + bias[c]) + 0.5     (pre: NHWC with `cpad` channels, c < 3)
 __global__ void __launch_bounds__(kT)
 g_final_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ bias, float* __restrict__ out, int HW,
@@ -270,6 +318,14 @@ int row_chunks(int M, int col_blocks, int lanes, int* rows_per_cta) {
     return (M + *rows_per_cta - 1) / *rows_per_cta;
 }
 
+constexpr size_t kRowsSmemMax = 96 * 1024;       // row-tiled remap kernels: one sample row (+ padding) per CTA
+
+// CB200_BN_ROWS=0 selects the element-indexed remap kernels again (A/B measurements).
+bool rows_kernels_enabled() {
+    static const bool on = []() { const char* e = getenv("CB200_BN_ROWS"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int col_lanes(int C) {          // columns per CTA: smallest power of two >= C, between 32 and 256
     int cc = 256;
     while (cc > 32 && cc / 2 >= C) cc /= 2;
@@ -311,10 +367,15 @@ extern "C" int cb200_bn_apply_relu(const float* x, const float* stats, const flo
     const bool vec = remap_s == 0 && C % 4 == 0 &&
                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(stats) |
                        reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+    const size_t rows_smem = remap_s > 0 ? (size_t)(C / remap_s) * (remap_s + 1) * sizeof(float) : 0;
     if (vec)
         bn_apply_relu_vec4_kernel<<<(unsigned)((total / 4 + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const float4*>(x), stats, gamma, beta, reinterpret_cast<float4*>(y), total / 4, C, round_out);
-    else
+    else if (remap_s > 1 && rows_smem <= kRowsSmemMax && rows_kernels_enabled()) {
+        cudaFuncSetAttribute(bn_apply_relu_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemMax);
+        bn_apply_relu_rows_kernel<<<M, kT, rows_smem, static_cast<cudaStream_t>(stream)>>>(x, stats, gamma, beta, y, C, remap_s,
+                                                                                          round_out);
+    } else
         bn_apply_relu_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
             x, stats, gamma, beta, y, total, C, remap_s, round_out);
     CB200_COUNT_LAUNCH();
@@ -347,11 +408,16 @@ extern "C" int cb200_bn_bwd_apply(const float* dy, const float* y, const float* 
                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) |
                        reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(stats) | reinterpret_cast<uintptr_t>(gamma) |
                        reinterpret_cast<uintptr_t>(sums)) & 15) == 0;
+    const size_t rows_smem = remap_s > 0 ? (size_t)(C / remap_s) * (remap_s + 1) * sizeof(float) : 0;
     if (vec)
         bn_bwd_apply_vec4_kernel<<<(unsigned)((total / 4 + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
             reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(x),
             stats, gamma, sums, 1.f / count, reinterpret_cast<float4*>(dx), total / 4, C, round_out);
-    else
+    else if (remap_s > 1 && rows_smem <= kRowsSmemMax && rows_kernels_enabled()) {
+        cudaFuncSetAttribute(bn_bwd_apply_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRowsSmemMax);
+        bn_bwd_apply_rows_kernel<<<M, kT, rows_smem, static_cast<cudaStream_t>(stream)>>>(dy, y, x, stats, gamma, sums, count, dx,
+                                                                                         C, remap_s, round_out);
+    } else
         bn_bwd_apply_kernel<<<(unsigned)((total + kT - 1) / kT), kT, 0, static_cast<cudaStream_t>(stream)>>>(
             dy, y, x, stats, gamma, sums, count, dx, total, C, remap_s, round_out);
     CB200_COUNT_LAUNCH();
