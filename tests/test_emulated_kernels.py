@@ -519,3 +519,94 @@ def test_product_train_step_on_cpu_vs_oracle():
     g_now = G.state_dict()
     for k in ("norm_init.running_mean", "main.1.running_var", "main.7.running_mean"):
         assert torch.allclose(g_now[k], sd_g_o[k], atol=1e-4, rtol=1e-3), k
+
+
+# ------------------------------------------------------------------ the data-parallel path on two CPU ranks (gloo)
+def _dp_worker(rank, world, port, payload, results):
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    import tests.cpu_tc_standins as TC
+    from contrad_b200.functional import AugmentSimCLRFn
+    from contrad_b200.models.gan.sndcgan import D_SNDCGAN, G_SNDCGAN
+    from contrad_b200.training.gan import contrad
+    from contrad_b200 import engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = payload["images"].shape[0] // world
+        rows = slice(rank * n, (rank + 1) * n)
+        with emulated(), TC.patched():
+            D = D_SNDCGAN((32, 32, 3), mlp_linear=True, d_hidden=payload["d_hidden"])
+            G = torch.nn.SyncBatchNorm.convert_sync_batchnorm(G_SNDCGAN((32, 32, 3), ngf=64, nz=payload["nz"]))
+            D.load_state_dict(payload["sd_d"]); G.load_state_dict(payload["sd_g"])
+            D.train(); G.train()
+            engine.set_grad(G, False); engine.set_grad(D, True)
+            with torch.no_grad():
+                gen = G(payload["z"][rows])                          # SyncBN: batch statistics over BOTH ranks
+            # the rank's columns of the full-batch draws: views [x | x | G(z)] of its own samples
+            N = payload["images"].shape[0]
+            cols = torch.cat([torch.arange(N)[rows] + k * N for k in range(3)])
+            packed = payload["aug"][:, cols].contiguous()
+
+            class Aug(torch.nn.Module):
+                def forward(self, x):
+                    return AugmentSimCLRFn.apply(x, packed, payload["order"])
+
+            P = SimpleNamespace(augment_fn=Aug(), temp=0.1, lbd_a=1.0, distributed=True)
+            d_loss, aux = contrad.loss_D_fn(P, D, {"loss": "nonsat"}, payload["images"][rows], gen)
+            (d_loss + aux["penalty"]).backward()
+            engine.allreduce_gradients(D)                            # train_gan.py:311-313 (DDP averages)
+            gn = float(engine.grad_norm(D))
+        results[rank] = {"gen": gen.clone(), "l_con": float(d_loss), "l_dis": float(aux["penalty"]), "grad_norm": gn,
+                         "g_main0": D.main[0].weight_orig.grad.clone()}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_d_step_on_two_cpu_ranks_vs_single_process_oracle():
+    """SURVEY 8e on the CPU: two gloo ranks run the PRODUCT's distributed D step (SyncBatchNorm in G, one packed all-gather
+    of the embeddings, replicated full-batch contrastive losses, gradient averaging) on their halves of a batch; the
+    generated images, the contrastive loss and the averaged gradient equal the single-process oracle on the whole batch
+    (the reference's semantics: identical full-batch L_con on every rank, L_dis a local mean, DDP's 1/W averaging)."""
+    import torch.multiprocessing as mp
+    world, n_all, nz, d_hidden = 2, 6, 16, 16
+    gen_w = torch.Generator().manual_seed(9)
+    sd_d = O.make_d_state(d_hidden=d_hidden, generator=gen_w)
+    sd_g = O.make_g_state(ngf=64, nz=nz, generator=gen_w)
+    np.random.seed(3); torch.manual_seed(3)
+    images = torch.rand(n_all, 3, 32, 32)
+    z = O.sample_latent(n_all, nz)
+    params, order = O.sample_simclr_params(3 * n_all, 32, 32)
+    payload = {"sd_d": sd_d, "sd_g": sd_g, "images": images, "z": z, "aug": O.pack_params(params), "order": order,
+               "nz": nz, "d_hidden": d_hidden}
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, 29731, payload, results), nprocs=world, join=True)
+    assert set(results.keys()) == {0, 1}
+
+    # single-process oracle on the full batch
+    sd_d_o = {k: v.clone() for k, v in sd_d.items()}
+    O.set_requires_grad(sd_d_o, True)
+    with torch.no_grad():
+        gen_o = O.g_sndcgan_forward({k: v.clone() for k, v in sd_g.items()}, z)
+    l_con_o, l_dis_o, ex = O.loss_d(sd_d_o, images, gen_o, params, order)
+    n = n_all // world
+    for r in range(world):
+        res = results[r]
+        assert torch.allclose(res["gen"], gen_o[r * n:(r + 1) * n], atol=2e-3), r         # 4 TF32 layers + tanh
+        assert abs(res["l_con"] - float(l_con_o)) < 1e-3 * abs(float(l_con_o)), (res["l_con"], float(l_con_o))
+    # L_dis is a mean over the rank's own samples; the two local means average to the full-batch value
+    assert abs(0.5 * (results[0]["l_dis"] + results[1]["l_dis"]) - float(l_dis_o)) < 1e-3 * abs(float(l_dis_o))
+    # DDP semantics (SURVEY 8e): every rank back-propagates the full-batch L_con through ITS rows, then gradients are
+    # averaged: backbone gradient = (1/W) * d L_con / d theta  +  d L_dis(full batch) / d theta
+    (l_con_o / world + l_dis_o).backward()
+    assert torch.equal(results[0]["g_main0"], results[1]["g_main0"])
+    ref_g = sd_d_o["main.0.weight_orig"].grad
+    err = float((results[0]["g_main0"] - ref_g).norm() / ref_g.norm())
+    assert err < 0.12, err          # per-tensor bar of tests/test_gpu_model.py (LeakyReLU kinks within TF32 rounding at a tiny batch)
+    cos = float((results[0]["g_main0"] * ref_g).sum() / (results[0]["g_main0"].norm() * ref_g.norm()))
+    assert cos > 0.995, cos
+    tot_o = O.grad_norm(sd_d_o)
+    assert abs(results[0]["grad_norm"] - tot_o) < 5e-3 * tot_o, (results[0]["grad_norm"], tot_o)
