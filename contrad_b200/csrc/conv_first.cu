@@ -25,7 +25,10 @@ __global__ void __launch_bounds__(kThreads)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ sigma,
                       const float* __restrict__ bias, float* __restrict__ y, int H, int W, float slope,
                       int round_out, float in_scale, float in_shift) {
-    __shared__ float xs[3][kRows + 2][kCols + 2];
+    // row stride 36 floats (144 B): the 10 input values of a thread start at a 16-byte boundary (seg = 0, 8, 16, 24), so
+    // they are two LDS.128 + one LDS.64 instead of ten LDS.32 - the shared-memory pipe, not the FMA pipe, was the
+    // busier one (22 wavefronts per 96 FMAs per warp and (ci, kh) step; now 15)
+    __shared__ __align__(16) float xs[3][kRows + 2][kCols + 4];
     __shared__ __align__(16) float ws[27][kCo];
     const int b = blockIdx.z;
     const int h0 = blockIdx.y * kRows;
@@ -57,9 +60,10 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
     for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-            float in[10];
-#pragma unroll
-            for (int j = 0; j < 10; ++j) in[j] = xs[ci][row + kh][seg + j];
+            const float* src = &xs[ci][row + kh][seg];
+            const float4 i0 = *reinterpret_cast<const float4*>(src), i1 = *reinterpret_cast<const float4*>(src + 4);
+            const float2 i2 = *reinterpret_cast<const float2*>(src + 8);
+            const float in[10] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y};
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
                 const float4 wv = *reinterpret_cast<const float4*>(&ws[ci * 9 + kh * 3 + kw][cg * 4]);
