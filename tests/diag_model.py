@@ -1,4 +1,5 @@
-"""Diagnostic: product D (kernels) vs oracle on cuda fp32 (TF32 off) at the module-output level."""
+"""Diagnostic (test infrastructure, run by hand on a GPU box: python tests/diag_model.py): product D (kernels) vs the oracle on
+cuda fp32 (TF32 off) at the module-output level."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.append(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contrad_b200", "compat"))

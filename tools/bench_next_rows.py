@@ -10,8 +10,9 @@ import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tools"))
 from contrad_b200 import kernels as K          # noqa: E402
-from oracle import contrad_oracle as O         # noqa: E402  (parameter sampler only)
+from _params import random_shift_flip_params, random_simclr_params      # noqa: E402
 
 
 def timeit(fn, sets, reps=6):
@@ -44,8 +45,7 @@ def main():
     # ---- mixed-source augmentation: n uint8 images x 2 views + n fp32 images (the D-step batch of contrad), 32x32
     for n, size in ((16384, 32), (512, 32), (4096, 64)):
         total = 3 * n
-        params, order = O.sample_simclr_params(total, size, size)
-        packed = O.pack_params(params).cuda()
+        packed, order = random_simclr_params(total)
         sets = [(torch.randint(0, 256, (n, 3, size, size), dtype=torch.uint8, device="cuda"),
                  torch.rand(n, 3, size, size, device="cuda")) for _ in range(3)]
         ms = timeit(lambda u, f: K.augment_simclr_mixed_fwd(u, 2 * n, f, packed, order), sets)
@@ -58,7 +58,7 @@ def main():
     # ---- hfrt gather
     for shape in ((16384, 3, 32, 32), (1536, 3, 32, 32), (48, 3, 512, 512)):
         b, _, h, w = shape
-        prm = O.sample_shift_flip(b, 4, w, flip=True).cuda()
+        prm = random_shift_flip_params(b, 4, w)
         sets = [(torch.rand(*shape, device="cuda"),) for _ in range(3)]
         nel = int(np.prod(shape))
         add("shift_flip_fwd", list(shape), timeit(lambda x: K.shift_flip(x, prm, "reflection"), sets), 8 * nel)
