@@ -34,7 +34,7 @@ void cb200_set_error(const char* fmt, ...);
 // Every kernel launch of this library goes through this counter so that bench.py can report
 // `gpu_launches` from the library itself (not a Python-side guess).
 extern unsigned long long g_cb200_launches;
-#define CB200_COUNT_LAUNCH() (++g_cb200_launches)
+#define CB200_COUNT_LAUNCH() ((void)__atomic_fetch_add(&g_cb200_launches, 1ULL, __ATOMIC_RELAXED))   // one host thread per GPU under nn.DataParallel
 
 // Once-per-device flags for cudaFuncSetAttribute (nn.DataParallel drives several devices from one process).
 inline bool& cb200_device_flag(bool (&flags)[64]) {

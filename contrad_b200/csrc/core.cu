@@ -19,11 +19,13 @@ extern "C" const char* cb200_last_error(void) { return t_last_error; }
 
 extern "C" int cb200_version(void) { return 100; }   // round 1, revision 00
 
-extern "C" unsigned long long cb200_launch_count(void) { return g_cb200_launches; }
+extern "C" unsigned long long cb200_launch_count(void) { return __atomic_load_n(&g_cb200_launches, __ATOMIC_RELAXED); }
 
-extern "C" void cb200_reset_launch_count(void) { g_cb200_launches = 0; }
+extern "C" void cb200_reset_launch_count(void) { __atomic_store_n(&g_cb200_launches, 0ULL, __ATOMIC_RELAXED); }
 
-extern "C" void cb200_add_launch_count(long long n) { g_cb200_launches += (unsigned long long)n; }
+extern "C" void cb200_add_launch_count(long long n) {
+    (void)__atomic_fetch_add(&g_cb200_launches, (unsigned long long)n, __ATOMIC_RELAXED);
+}
 
 extern "C" int cb200_device_arch(int device, int* major, int* minor) {
     cudaDeviceProp prop;
