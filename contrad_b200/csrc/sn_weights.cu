@@ -448,6 +448,7 @@ __device__ __forceinline__ void pack_tile_body(const SnPackBatch& p, int l, cons
     // store: with 4 in flight (the unroll of the generic loop) three resident CTAs kept ~12 KB per SM in flight, a
     // third of what the HBM latency-bandwidth product needs (1.9 TB/s in the round-1 launch list).
     const bool full = KKc > 1 && g.n_ci == 32 && g.CT == 32;
+    constexpr int KKd = KKc > 1 ? KKc : 2;          // divisor on the full-tile path (never executed for KKc <= 1)
     for (int r = warp; r < g.n_co; r += kT / 32) {
         const float* src = w + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
         float* row = tile + r * g.RS;
@@ -460,7 +461,7 @@ __device__ __forceinline__ void pack_tile_body(const SnPackBatch& p, int l, cons
                 const int t = lane + 32 * i;
                 float o = val[i] * inv;
                 if (rnd) o = round_tf32(o);
-                row[(t % KKc) * 33 + t / KKc] = o;
+                row[(t % KKd) * 33 + t / KKd] = o;
             }
             continue;
         }
@@ -551,6 +552,7 @@ __device__ __forceinline__ float dot_tile_body(const SnBwdBatch& p, int l, const
     const int ncols = g.n_ci * KK;
     float a = 0.f;
     const bool full = KKc > 1 && g.n_ci == 32 && g.CT == 32;
+    constexpr int KKd = KKc > 1 ? KKc : 2;          // divisor on the full-tile path (never executed for KKc <= 1)
     for (int r = warp; r < g.n_co; r += kT / 32) {
         const float* src = p.w[l] + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
         const float* row = tile + r * g.RS;
@@ -561,7 +563,7 @@ __device__ __forceinline__ float dot_tile_body(const SnBwdBatch& p, int l, const
 #pragma unroll
             for (int i = 0; i < KKc; ++i) {
                 const int t = lane + 32 * i;
-                a += val[i] * row[(t % KKc) * 33 + t / KKc];
+                a += val[i] * row[(t % KKd) * 33 + t / KKd];
             }
             continue;
         }
@@ -598,6 +600,7 @@ __device__ __forceinline__ void apply_tile_body(const SnBwdBatch& p, int l, cons
     const float inv = p.sigma[l][1];
     const float scale = p.acc[l][0] * inv;
     const float* __restrict__ v = p.v[l] + (long long)g.ci0 * KK;
+    constexpr int KKd = KKc > 1 ? KKc : 2;
     for (int r = warp; r < g.n_co; r += kT / 32) {
         const float su = scale * p.u[l][g.co0 + r];
         float* dst = p.dw[l] + (long long)(g.co0 + r) * F + (long long)g.ci0 * KK;
@@ -609,7 +612,7 @@ __device__ __forceinline__ void apply_tile_body(const SnBwdBatch& p, int l, cons
 #pragma unroll
             for (int i = 0; i < KKc; ++i) {
                 const int t = lane + 32 * i;
-                dst[t] = (row[(t % KKc) * 33 + t / KKc] - su * vv[i]) * inv;
+                dst[t] = (row[(t % KKd) * 33 + t / KKd] - su * vv[i]) * inv;
             }
             continue;
         }
