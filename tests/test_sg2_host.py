@@ -247,3 +247,41 @@ def test_dstep16_oracle_and_product(fx, states):
         _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 2e-3, "product D-step n=16")
         total = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in D.parameters()))
         assert abs(total - c["total_grad_norm"]) < 1e-3 * c["total_grad_norm"]
+
+
+# ------------------------------------------------------------------------------------------------ 3. real SIMT kernels on CPU
+def test_product_stylegan2_on_emulated_kernels(fx, states):
+    """The same fixtures with the REAL csrc/sg2_ops.cu kernels (upfirdn2d, patch gather / scatter, bias_act, modulation,
+    minibatch stddev incl. its double backward, layout kernels ...) executed on the CPU by the CUDA emulator (tests/emu);
+    only the tcgen05 entry points are torch stand-ins (tests/cpu_tc_standins.py, TF32 rounding of the outputs included).
+    Tolerances are the TF32 bars of tests/test_gpu_sg2.py: D forward, the R1 double backward, G forward / backward."""
+    import tests.cpu_tc_standins as TC
+    from tests.emu import emulated
+    from contrad_b200.training.gan import stylegan2 as T
+    with emulated(), TC.patched():
+        G, D = _product_models(states, fx["size"])
+        c = fx["d_case"]
+        x = c["x"].clone().requires_grad_(True)
+        d, aux = D(x, projection=True, projection2=True, penultimate=True)
+        _close(d, c["d"], 1e-2, "d"); _close(aux["projection"], c["projection"], 1e-2, "projection")
+        _close(aux["penultimate"], c["penultimate"], 1e-2, "penultimate")
+        ((d * c["c_d"]).sum() + (aux["projection"] * c["c1"]).sum() + (aux["projection2"] * c["c2"]).sum()).backward()
+        l2 = float((x.grad - c["dx"]).norm() / c["dx"].norm())      # a few LeakyReLU kinks flip under TF32 rounding: L2 bar
+        assert l2 < 5e-2, l2
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 2e-2, "product D (emulated kernels)")
+        D.zero_grad()
+        c = fx["r1_case"]
+        per_sample = T.r1_per_sample(D, c["x"], lambda t: t)
+        _close(per_sample, c["per_sample"], 2e-2, "r1 per sample")
+        per_sample.mean().backward()
+        total = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in D.parameters() if p.grad is not None))
+        want = math.sqrt(sum(n * n for n in c["grad_norms"].values()))
+        assert abs(total - want) < 2e-2 * want, (total, want)
+        c = fx["g_case"]
+        torch.manual_seed(c["mix_seed"])
+        img, latents = G(c["z"], return_latents=True, style_mix=0.9, noise=c["noises"])
+        _close(latents, c["latents"], 5e-3, "latents"); _close(img, c["image"], 1e-2, "image")
+        (img * c["c_img"]).sum().backward()
+        total = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in G.parameters() if p.grad is not None))
+        want = math.sqrt(sum(n * n for n in c["grad_norms"].values()))
+        assert abs(total - want) < 2e-2 * want, (total, want)
