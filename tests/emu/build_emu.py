@@ -6,6 +6,7 @@ import ctypes
 import hashlib
 import os
 import re
+import shutil
 import subprocess
 import tempfile
 
@@ -61,8 +62,9 @@ def build(cache_dir=None):
     if os.path.exists(so):
         return so
     objs, procs = [], []
+    work = tempfile.mkdtemp(prefix="build_%d_" % os.getpid(), dir=cache_dir)     # private intermediates: concurrent builds
     for name, text in zip(EMULATED, srcs):
-        cpp = os.path.join(cache_dir, "%s_%s.cpp" % (name[:-3], tag))
+        cpp = os.path.join(work, "%s.cpp" % name[:-3])
         with open(cpp, "w") as f:
             f.write(transform(text))
         obj = cpp[:-4] + ".o"
@@ -74,10 +76,12 @@ def build(cache_dir=None):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError("g++ failed for the emulated %s:\n%s" % (name, out.decode()[-4000:]))
-    r = subprocess.run(["g++", "-shared", "-pthread", "-o", so + ".tmp"] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    tmp_so = os.path.join(work, "lib.so")
+    r = subprocess.run(["g++", "-shared", "-pthread", "-o", tmp_so] + objs, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout.decode())
-    os.replace(so + ".tmp", so)
+    os.replace(tmp_so, so)                                  # atomic publish into the shared cache
+    shutil.rmtree(work, ignore_errors=True)
     return so
 
 
