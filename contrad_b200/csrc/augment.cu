@@ -94,38 +94,45 @@ __device__ __forceinline__ Tap axis_tap(int o, int n, float s, float b) {
     return t;
 }
 
-// atan2(y, x) / (2 pi) folded into [0, 1): 8-term minimax odd polynomial on [0,1] (max abs error 1.2e-7 rad)
-// + octant fix-ups; the division is the fast reciprocal (2 ulp) - the result feeds a piecewise-linear
-// colour wheel with slope <= 6, so 1e-7 in the turn fraction is far below the fp32 noise of the chain.
+// atan2(y, x) / (2 pi) folded into [0, 1): 8-term minimax odd polynomial on [0,1] (max abs error 1.2e-7 rad), its
+// coefficients pre-multiplied by 1 / (2 pi) so that the result is in turns without a final multiply, + octant fix-ups;
+// the division is the fast reciprocal (2 ulp) - the result feeds a piecewise-linear colour wheel with slope <= 6, so
+// 1e-7 in the turn fraction is far below the fp32 noise of the chain.  mx == 0 (a gray pixel) gives t = 0 -> hue 0 like
+// atan2(0, 0).
 __device__ __forceinline__ float hue_turns(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float t = __fdividef(mn, fmaxf(mx, 1e-30f));
     const float u = t * t;
-    float p = -0.004054375924170017f;
-    p = fmaf(p, u, 0.021862227469682693f);
-    p = fmaf(p, u, -0.05591120570898056f);
-    p = fmaf(p, u, 0.09642109274864197f);
-    p = fmaf(p, u, -0.13908591866493225f);
-    p = fmaf(p, u, 0.1994655728340149f);
-    p = fmaf(p, u, -0.33329859375953674f);
-    p = fmaf(p, u, 0.9999993443489075f);
-    float a = p * t;                                   // atan(mn/mx) in [0, pi/4]
-    if (ay > ax) a = 1.5707963267948966f - a;           // first quadrant
-    if (x < 0.f) a = 3.141592653589793f - a;            // upper half plane
-    if (y < 0.f) a = 6.283185307179586f - a;            // == (atan2 < 0 ? atan2 + 2 pi : atan2)
-    return a * 0.15915494309189535f;
+    float p = -0.00064527396948442972f;
+    p = fmaf(p, u, 0.0034794815687994203f);
+    p = fmaf(p, u, -0.0088985447628120544f);
+    p = fmaf(p, u, 0.015345893529268476f);
+    p = fmaf(p, u, -0.022136211470001277f);
+    p = fmaf(p, u, 0.031745931893189944f);
+    p = fmaf(p, u, -0.053046118722407817f);
+    p = fmaf(p, u, 0.15915483874178302f);
+    float a = p * t;                                   // atan(mn/mx) / (2 pi) in [0, 1/8]
+    if (ay > ax) a = 0.25f - a;                        // first quadrant
+    if (x < 0.f) a = 0.5f - a;                         // upper half plane
+    if (y < 0.f) a = 1.f - a;                          // == (atan2 < 0 ? atan2 + 2 pi : atan2)
+    return a;
 }
 
 // RandomHSVFunction.forward on one pixel (augment/color_jitter.py:83-95, augment/utils.py:27-38,55-63).
 // `hshift` = (f_h * 255) / 360 is hoisted per image.
+// hsv -> rgb (utils.py:55-63: k = (n + 6 h) mod 6, t = clamp(min(k, 4 - k), 0, 1), out = v - c t for n = 5, 3, 1) is
+// evaluated as t = sat(2 - d) with d the CIRCULAR distance (period 6) of 6 h to the channel's centre 3, 5, 1:
+// min(k, 4 - k) = 2 - |k - 2| and |k - 2| is that distance; for the centre 3 it never wraps.  Same function, 10 instead of
+// 18 instructions for the three channels (the chain is issue-bound, profiles/prof_r1_augment.md).
 __device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float hshift, float fs, float fv) {
     float cmax = fmaxf(r, fmaxf(g, b));
     float cmin = fminf(r, fminf(g, b));
     float hue = hue_turns(1.7320508075688772f * (g - b), 2.f * r - g - b);     // finite for finite inputs
-    float sat = 1.f - __fdividef(cmin, cmax + 1e-8f);
-    if (!isfinite(sat)) sat = 0.f;           // the reference zeroes non-finite hsv entries (utils.py:37)
-    float val = isfinite(cmax) ? cmax : 0.f;
+    // the reference zeroes non-finite hsv entries (utils.py:37): a NaN saturation is mapped to 0 by the __saturatef below
+    // (it cannot be +-inf: cmin / (cmax + 1e-8) is finite or NaN), the value needs the explicit test (+inf -> 0)
+    const float sat = 1.f - __fdividef(cmin, cmax + 1e-8f);
+    const float val = isfinite(cmax) ? cmax : 0.f;
     float h = hue + hshift;
     h = h - floorf(h);
     const float s = __saturatef(sat * fs);
@@ -133,10 +140,12 @@ __device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float h
     h = __saturatef(h);
     const float c = v * s;
     const float h6 = h * 6.f;
-    float k, t;
-    k = 5.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = __saturatef(fminf(k, 4.f - k)); r = fmaf(-c, t, v);
-    k = 3.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = __saturatef(fminf(k, 4.f - k)); g = fmaf(-c, t, v);
-    k = 1.f + h6; k = (k >= 6.f) ? k - 6.f : k; t = __saturatef(fminf(k, 4.f - k)); b = fmaf(-c, t, v);
+    const float dr = fabsf(h6 - 3.f);
+    const float ag = fabsf(h6 - 5.f), ab = fabsf(h6 - 1.f);
+    const float dg = fminf(ag, 6.f - ag), db = fminf(ab, 6.f - ab);
+    r = fmaf(-c, __saturatef(2.f - dr), v);
+    g = fmaf(-c, __saturatef(2.f - dg), v);
+    b = fmaf(-c, __saturatef(2.f - db), v);
 }
 
 __device__ __forceinline__ float clamp01(float x) { return __saturatef(x); }   // one FADD.SAT; NaN -> 0 like fmin(fmax())
