@@ -242,7 +242,7 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
         }
         const SampleParams sp = load_params(params, B, b);
         const int ord = resolve_order(params, B, b, order);
-        const float hshift = (sp.fh * 255.f) / 360.f;
+        const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
         fill_taps(taps, H, W, sp);
         bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
         __syncthreads();
@@ -315,6 +315,37 @@ augment_simclr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, co
     }
 }
 
+// Sum of three per-thread values over a 256-thread CTA (8 warps), result in every thread.  The generic block_sum<3>
+// spends 30 shuffles + 30 adds per thread (three independent 5-step butterflies, twice); here the three values share ONE
+// butterfly: after the xor-16 and xor-8 exchanges every lane carries a single value (lanes 0-7: v0, 8-15: v1, 16-23: v2,
+// 24-31: zero), three more steps finish the warp sums, and the 3 x 8 warp partials are folded by one 3-step butterfly and
+// three broadcasts: 12 shuffles.  `scratch` holds 24 floats; the CALLER must synchronise the CTA before reusing it (the
+// image loop does, at the end of every iteration).
+__device__ __forceinline__ void block_sum3_256(float (&v)[3], float* scratch) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool hi = (lane & 16) != 0;
+    // lower half-warp keeps (v0, v1) and hands v2 to its partner; upper half keeps v2 and hands (v0, v1) over
+    const float r0 = __shfl_xor_sync(full, hi ? v[0] : v[2], 16);
+    const float r1 = __shfl_xor_sync(full, hi ? v[1] : 0.f, 16);
+    float a = (hi ? v[2] : v[0]) + r0;
+    const float b = (hi ? 0.f : v[1]) + r1;
+    const bool q = (lane & 8) != 0;
+    a = (q ? b : a) + __shfl_xor_sync(full, q ? a : b, 8);
+    a += __shfl_xor_sync(full, a, 4);
+    a += __shfl_xor_sync(full, a, 2);
+    a += __shfl_xor_sync(full, a, 1);
+    if ((lane & 7) == 0 && lane < 24) scratch[(lane >> 3) * 8 + warp] = a;      // [value][warp]
+    __syncthreads();
+    float t = (lane < 24) ? scratch[lane] : 0.f;
+    t += __shfl_xor_sync(full, t, 4);
+    t += __shfl_xor_sync(full, t, 2);
+    t += __shfl_xor_sync(full, t, 1);
+    v[0] = __shfl_sync(full, t, 0);
+    v[1] = __shfl_sync(full, t, 8);
+    v[2] = __shfl_sync(full, t, 16);
+}
+
 // Per-image arithmetic of the column-mapped forward kernels: thread = output column j, rows i_first .. i_first+NPX-1.
 // `xs` is the fp32 [3,S,S] source image in shared memory, `yb` points at this thread's first output element.
 template <int S>
@@ -348,7 +379,7 @@ __device__ __forceinline__ void cols_process(const float* xs, const float4* xtap
         for (int m = 0; m < NPX; ++m)
 #pragma unroll
             for (int c = 0; c < 3; ++c) sums[c] += v[m][c];
-        block_sum<3>(sums, red);
+        block_sum3_256(sums, red);          // blockDim.x == 256; `red` is not touched again before the CTA-wide sync
         constexpr float inv = 1.f / (float)HW;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -411,7 +442,7 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
         }
         const SampleParams sp = load_params(params, B, b);
         const int ord = resolve_order(params, B, b, order);
-        const float hshift = (sp.fh * 255.f) / 360.f;
+        const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
         if (threadIdx.x < 2 * S) {
             const int e = threadIdx.x;
             if (e < S) {
@@ -477,7 +508,7 @@ augment_simclr_fwd_mixed_cols_kernel(const uint8_t* __restrict__ xu, int n_u8, i
         if (threadIdx.x == 0 && nb < B) prefetch(nb, buf ^ 1);
         const SampleParams sp = load_params(params, B, b);
         const int ord = resolve_order(params, B, b, order);
-        const float hshift = (sp.fh * 255.f) / 360.f;
+        const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
         if (threadIdx.x < 2 * S) {
             const int e = threadIdx.x;
             if (e < S) {
@@ -519,7 +550,7 @@ augment_simclr_bwd_kernel(const float* __restrict__ x, const float* __restrict__
     const int b = blockIdx.x;
     const SampleParams sp = load_params(params, B, b);
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     if (sp.cj_on != 0.f && threadIdx.x == 0) {     // x only feeds the clamp mask; one async bulk copy stages it
         bar_init(bar, 1);
         fence_barrier_init();
@@ -682,7 +713,7 @@ augment_large_mean_kernel(const float* __restrict__ x, const float* __restrict__
     const SampleParams sp = load_params(params, B, b);
     if (sp.cj_on == 0.f) return;                                   // uniform per CTA
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     const int HW = H * W;
     const float* xb = x + (size_t)b * 3 * HW;
     float sums[3] = {0.f, 0.f, 0.f};
@@ -706,7 +737,7 @@ augment_large_apply_kernel(const float* __restrict__ x, float* __restrict__ y, c
     const int b = blockIdx.y;
     const SampleParams sp = load_params(params, B, b);
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     const int HW = H * W;
     const float* xb = x + (size_t)b * 3 * HW;
     float* yb = y + (size_t)b * 3 * HW;
@@ -743,7 +774,7 @@ augment_large_mean_mixed_kernel(const uint8_t* __restrict__ xu, int n_u8, int n_
     lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.f);       // blockDim.x == 256
     __syncthreads();
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     const int HW = H * W;
     const bool bytes_src = b < n_u8_views;
     const uint8_t* xub = xu + (size_t)(bytes_src ? b % n_u8 : 0) * 3 * HW;
@@ -774,7 +805,7 @@ augment_large_apply_mixed_kernel(const uint8_t* __restrict__ xu, int n_u8, int n
     const int b = blockIdx.y;
     const SampleParams sp = load_params(params, B, b);
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     const int HW = H * W;
     const bool bytes_src = b < n_u8_views;
     const uint8_t* xub = xu + (size_t)(bytes_src ? b % n_u8 : 0) * 3 * HW;
@@ -833,7 +864,7 @@ augment_large_bwd_reduce_kernel(const float* __restrict__ x, const float* __rest
     const SampleParams sp = load_params(params, B, b);
     if (sp.cj_on == 0.f) return;
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     const int HW = H * W;
     const float* xb = x + (size_t)b * 3 * HW;
     const float* dyb = dy + (size_t)b * 3 * HW;
@@ -859,7 +890,7 @@ augment_large_bwd_scatter_kernel(const float* __restrict__ x, const float* __res
     const int b = blockIdx.y;
     const SampleParams sp = load_params(params, B, b);
     const int ord = resolve_order(params, B, b, order);
-    const float hshift = (sp.fh * 255.f) / 360.f;
+    const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
     const int HW = H * W;
     const float* xb = x + (size_t)b * 3 * HW;
     const float* dyb = dy + (size_t)b * 3 * HW;
