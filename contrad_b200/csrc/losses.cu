@@ -20,8 +20,9 @@ namespace {
 
 constexpr int kD = 128;            // embedding width (d_project)
 constexpr int kWarps = 8;
-constexpr int kRowsPerWarp = 2;
-constexpr int kRowsPerCta = kWarps * kRowsPerWarp;   // 16
+constexpr int kRowsPerWarp = 4;     // rows per warp: each broadcast of a row vector feeds 4 FMAs per lane; the dot phase is
+                                    // shared-memory bound (4 + R wavefronts per 4 R FMAs and k-step), R = 2 -> 4 cuts that by a third
+constexpr int kRowsPerCta = kWarps * kRowsPerWarp;   // 32
 constexpr int kJT = 32;            // columns per tile = one per lane
 constexpr int kZStride = kD + 4;   // padded smem row (float4-aligned, conflict-free 128-bit reads)
 constexpr int kMaxSplits = 16;
