@@ -12,6 +12,7 @@
 //             channels padded 3 -> 32; `conv_first_dgrad_finish` extracts the 3 real channels,
 //             applies the factor 2 of the input affine and transposes NHWC -> NCHW.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -234,6 +235,135 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ d
     }
 }
 
+// ---- weight gradient, second mapping (CB200_CONV_FIRST_WGRAD=2; written without GPU access, to be timed) ----
+// The kernel above spends, per pixel and thread, one LDS.128 (dY) + seven LDS.32 (image) on 28 FMAs: ~11 shared-memory
+// wavefronts per warp against 28 FMA issue slots, and with 8 warps per CTA sharing one shared-memory pipe that pipe
+// (88 cycles per 4-pixel step) - not the FMA pipes (56) - bounds it.  Here a thread owns ALL nine taps of one input
+// channel (3 tap groups = the 3 input channels, 192 threads): the three image rows it needs slide along the row in
+// registers, so a pixel costs one LDS.128 + three LDS.32 for 36 FMAs (7 wavefronts; 42 vs 54 cycles per step).
+constexpr int kThreadsV2 = 192;
+constexpr int kXsPerThreadV2 = (kXsElems + kThreadsV2 - 1) / kThreadsV2;      // 4
+
+__global__ void __launch_bounds__(kThreadsV2, 3)
+conv_first_wgrad_v2_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                           float* __restrict__ db, int B, int H, int W, float in_scale, float in_shift) {
+    extern __shared__ __align__(128) float wsm[];
+    float* dys = wsm;                                   // [2][kRows][kCols][kCo]
+    float* xsb = wsm + 2 * kDyTileFloats;               // [2][3][kRows+2][kCols+2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xsb + 2 * kXsElems);
+    const int tiles_w = (W + kCols - 1) / kCols, tiles_h = (H + kRows - 1) / kRows;
+    const int ntiles = tiles_w * tiles_h * B;
+    const int cg = threadIdx.x & 15;          // channels 4 cg .. 4 cg + 3
+    const int ci = (threadIdx.x >> 4) % 3;    // input channel = tap group (taps ci*9 .. ci*9 + 8)
+    const int ps = threadIdx.x / 48;          // output row within the tile
+
+    auto tile_origin = [&](int tile, int& b, int& h0, int& w0) {
+        b = tile / (tiles_w * tiles_h);
+        const int rem = tile - b * tiles_w * tiles_h;
+        h0 = (rem / tiles_w) * kRows;
+        w0 = (rem % tiles_w) * kCols;
+    };
+    auto load_x = [&](int tile, float (&v)[kXsPerThreadV2]) {
+        int b, h0, w0;
+        tile_origin(tile, b, h0, w0);
+#pragma unroll
+        for (int k = 0; k < kXsPerThreadV2; ++k) {
+            const int i = threadIdx.x + k * kThreadsV2;
+            const int c = i / ((kRows + 2) * (kCols + 2)), r = (i / (kCols + 2)) % (kRows + 2), cc = i % (kCols + 2);
+            const int hh = h0 + r - 1, ww = w0 + cc - 1;
+            v[k] = 0.f;
+            if (i < kXsElems && hh >= 0 && hh < H && ww >= 0 && ww < W)
+                v[k] = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * in_scale + in_shift;
+        }
+    };
+    auto park_x = [&](int buf, const float (&v)[kXsPerThreadV2]) {
+#pragma unroll
+        for (int k = 0; k < kXsPerThreadV2; ++k)
+            if (threadIdx.x + k * kThreadsV2 < kXsElems) xsb[buf * kXsElems + threadIdx.x + k * kThreadsV2] = v[k];
+    };
+    auto fetch_dy = [&](int tile, int buf) {              // one elected thread
+        int b, h0, w0;
+        tile_origin(tile, b, h0, w0);
+        const int rows = min(kRows, H - h0), ncols = min(kCols, W - w0);
+        const uint32_t row_bytes = (uint32_t)ncols * kCo * sizeof(float);
+        bar_expect_tx(&bars[buf], row_bytes * rows);
+        for (int r = 0; r < rows; ++r)
+            bulk_load(dys + buf * kDyTileFloats + r * kCols * kCo, dy + (((size_t)b * H + h0 + r) * W + w0) * kCo, row_bytes,
+                      &bars[buf]);
+    };
+
+    float acc[9][4];
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+
+    if (threadIdx.x == 0) {
+        bar_init(&bars[0], 1);
+        bar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tile < ntiles) {
+        if (threadIdx.x == 0) fetch_dy(tile, 0);
+        float v[kXsPerThreadV2];
+        load_x(tile, v);
+        park_x(0, v);
+    }
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int next = tile + gridDim.x;
+        float vnext[kXsPerThreadV2];
+        if (next < ntiles) {
+            if (threadIdx.x == 0) fetch_dy(next, buf ^ 1);
+            load_x(next, vnext);                      // in flight during the FMA loop below
+        }
+        bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
+        __syncthreads();                               // halo tile `buf` parked by everybody
+        int b, h0, w0;
+        tile_origin(tile, b, h0, w0);
+        if (h0 + ps < H) {
+            const float* grow = dys + buf * kDyTileFloats + (ps * kCols) * kCo + cg * 4;
+            const float* xr0 = xsb + buf * kXsElems + (ci * (kRows + 2) + ps) * (kCols + 2);      // image row ps-1+kh, kh = 0
+            const float* xr1 = xr0 + (kCols + 2), *xr2 = xr1 + (kCols + 2);
+            const int ncols = min(kCols, W - w0);
+            float a0 = xr0[0], b0 = xr0[1], a1 = xr1[0], b1 = xr1[1], a2 = xr2[0], b2 = xr2[1];   // columns c, c+1 of the window
+#pragma unroll 4
+            for (int c = 0; c < ncols; ++c) {
+                const float4 g = *reinterpret_cast<const float4*>(grow + c * kCo);
+                const float c0 = xr0[c + 2], c1 = xr1[c + 2], c2 = xr2[c + 2];                     // column c+2 enters the window
+                if (ci == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
+                const float xv[9] = {a0, b0, c0, a1, b1, c1, a2, b2, c2};                          // tap = kh * 3 + kw
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    acc[t][0] += g.x * xv[t]; acc[t][1] += g.y * xv[t]; acc[t][2] += g.z * xv[t]; acc[t][3] += g.w * xv[t];
+                }
+                a0 = b0; b0 = c0; a1 = b1; b1 = c1; a2 = b2; b2 = c2;
+            }
+        }
+        if (next < ntiles) park_x(buf ^ 1, vnext);
+        __syncthreads();                               // buffer `buf` is free for the prefetch of iteration it+1
+    }
+    // reduce the four pixel slices through shared memory (the dY ring is dead now), then one atomic per element
+    float (*part)[28][kCo] = reinterpret_cast<float (*)[28][kCo]>(dys);
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+        *reinterpret_cast<float4*>(&part[ps][ci * 9 + t][cg * 4]) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    if (ci == 0) *reinterpret_cast<float4*>(&part[ps][27][cg * 4]) = make_float4(bacc[0], bacc[1], bacc[2], bacc[3]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 28 * kCo; i += kThreadsV2) {
+        const int tap = i / kCo, co = i % kCo;
+        const float sum = (part[0][tap][co] + part[1][tap][co]) + (part[2][tap][co] + part[3][tap][co]);
+        if (tap < 27) atomicAdd(dw + co * 27 + tap, sum);
+        else if (db) atomicAdd(db + co, sum);
+    }
+}
+
+int wgrad_variant() {
+    static const int v = []() { const char* e = getenv("CB200_CONV_FIRST_WGRAD"); return (e && e[0] == '2') ? 2 : 1; }();
+    return v;
+}
+
 // dx[b,c,h,w] = 2 * dpad[b,h,w,c]   (c < 3 of the 32 padded channels)
 __global__ void __launch_bounds__(kThreads)
 conv_first_dgrad_finish_kernel(const float* __restrict__ dpad, float* __restrict__ dx, int HW, int cpad,
@@ -270,9 +400,15 @@ extern "C" int cb200_conv_first_wgrad(const float* x, const float* dy, float* dw
     const long long ntiles = (long long)((W + kCols - 1) / kCols) * ((H + kRows - 1) / kRows) * B;
     CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "conv_first_wgrad: dy must be 16-byte aligned");
     const int grid = (int)(ntiles < 3 * 148 ? ntiles : 3 * 148);           // 3 resident CTAs per SM (69 KB smem each)
-    cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes);
-    conv_first_wgrad_kernel<<<grid, kThreads, kWgradSmemBytes, static_cast<cudaStream_t>(stream)>>>(
-        x, dy, dw_hat, db, B, H, W, in_scale, in_shift);
+    if (wgrad_variant() == 2) {
+        cudaFuncSetAttribute(conv_first_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes);
+        conv_first_wgrad_v2_kernel<<<grid, kThreadsV2, kWgradSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+            x, dy, dw_hat, db, B, H, W, in_scale, in_shift);
+    } else {
+        cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes);
+        conv_first_wgrad_kernel<<<grid, kThreads, kWgradSmemBytes, static_cast<cudaStream_t>(stream)>>>(
+            x, dy, dw_hat, db, B, H, W, in_scale, in_shift);
+    }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("conv_first_wgrad");
     return CB200_OK;

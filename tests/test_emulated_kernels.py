@@ -610,3 +610,29 @@ def test_data_parallel_d_step_on_two_cpu_ranks_vs_single_process_oracle():
     assert cos > 0.995, cos
     tot_o = O.grad_norm(sd_d_o)
     assert abs(results[0]["grad_norm"] - tot_o) < 5e-3 * tot_o, (results[0]["grad_norm"], tot_o)
+
+
+def test_emulated_conv_first_wgrad_second_mapping():
+    """The opt-in weight-gradient mapping of csrc/conv_first.cu (CB200_CONV_FIRST_WGRAD=2: one input channel's nine taps per
+    thread, sliding register window) against torch - in a subprocess, because the variant is read from the environment
+    once per process.  Several tiles per CTA (B = 40 on the emulated 4-SM device) exercise the persistent loop."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+from tests.emu import emulated
+from contrad_b200 import kernels as K
+with emulated():
+    for B, H in ((40, 32), (3, 16), (2, 20)):
+        torch.manual_seed(B)
+        x, dy = torch.rand(B, 3, H, H), torch.randn(B, H, H, 64)
+        dw, db = K.conv_first_wgrad(x, dy)
+        ref = torch.nn.grad.conv2d_weight(x.double() * 2 - 1, (64, 3, 3, 3), dy.permute(0, 3, 1, 2).double(), padding=1)
+        assert torch.allclose(dw.view(64, 3, 3, 3), ref.float(), atol=2e-3, rtol=1e-4), (B, H, float((dw.view(64, 3, 3, 3) - ref.float()).abs().max()))
+        assert torch.allclose(db, dy.sum(dim=(0, 1, 2)), atol=2e-3, rtol=1e-4), (B, H)
+print("wgrad v2 ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CB200_CONV_FIRST_WGRAD="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert r.returncode == 0 and b"wgrad v2 ok" in r.stdout, r.stdout.decode()[-3000:]
