@@ -299,3 +299,49 @@ def test_config2_full_batch_step_vs_oracle(gin_defaults):
         step_ref = (sd_d_o[key].detach() - sd_d[key]).flatten().double()
         cos = float((step_mine * step_ref).sum() / (step_mine.norm() * step_ref.norm()).clamp_min(1e-30))
         assert cos > 0.97, (key, cos)       # Adam's first update is ~lr * sign(grad): sign agreement of 98.5 %
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written without GPU access (verified on the CPU emulator only); "
+                                        "first hardware run pending")
+def test_conv_first_wgrad_second_mapping():
+    """CB200_CONV_FIRST_WGRAD=2 (csrc/conv_first.cu, opt-in): parity with torch and with the default mapping, plus a timing
+    of both at the benchmark batch written to gpurun_out/conv_first_wgrad_ab.json.  Subprocesses: the variant is read once
+    per process."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import json, sys, torch
+sys.path.insert(0, %r)
+from contrad_b200 import kernels as K
+out = {}
+for B, H in ((8, 32), (3, 16), (2, 64)):
+    torch.manual_seed(B)
+    x, dy = torch.rand(B, 3, H, H, device="cuda"), torch.randn(B, H, H, 64, device="cuda")
+    dw, db = K.conv_first_wgrad(x, dy)
+    ref = torch.nn.grad.conv2d_weight(x.double() * 2 - 1, (64, 3, 3, 3), dy.permute(0, 3, 1, 2).double(), padding=1)
+    assert torch.allclose(dw.view(64, 3, 3, 3), ref.float(), atol=1e-3, rtol=1e-4), (B, H)
+    assert torch.allclose(db, dy.sum(dim=(0, 1, 2)), atol=1e-3, rtol=1e-4), (B, H)
+xs = [torch.rand(1536, 3, 32, 32, device="cuda") for _ in range(3)]
+dys = [torch.randn(1536, 32, 32, 64, device="cuda") for _ in range(3)]
+for i in range(3):
+    K.conv_first_wgrad(xs[i], dys[i])
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(6):
+    K.conv_first_wgrad(xs[i %% 3], dys[i %% 3])
+e1.record(); torch.cuda.synchronize()
+print(json.dumps({"ms": e0.elapsed_time(e1) / 6}))
+''' % repo
+    res = {}
+    for variant in ("1", "2"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CB200_CONV_FIRST_WGRAD=variant),
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=280)
+        assert r.returncode == 0, (variant, r.stdout.decode()[-2000:])
+        res["variant_%s_ms" % variant] = json.loads(r.stdout.decode().strip().splitlines()[-1])["ms"]
+    os.makedirs(os.path.join(repo, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(repo, "gpurun_out", "conv_first_wgrad_ab.json"), "w") as f:
+        json.dump(res, f)
+    print("conv_first_wgrad B=1536: default %.3f ms, second mapping %.3f ms" % (res["variant_1_ms"], res["variant_2_ms"]))
