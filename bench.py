@@ -126,15 +126,42 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
+def reference_available():
+    from oracle import ref_import
+    return os.path.isdir(os.path.join(ref_import._VENDORED, "augment")) or ref_import.reference_available()
+
+
 def run_reference(args):
-    """CPU restatement of the reference path (oracle/contrad_oracle.py, kind "port": the reference is
-    Python and cannot travel to the GPU box) on all host cores.  Each step = a bounded SAMPLE of the
-    workload: one full D+G step at batch 64 (1/8 of the b512 batch; BASELINE config 1 shape)."""
+    """The UNMODIFIED reference (oracle/_ref, copied from /root/reference by oracle/make_ref.py) on all host cores:
+    its own `get_architecture('sndcgan')`, `training.gan.contrad`, `get_augment('simclr')` modules and torch.optim.Adam
+    driven through the loop body of train_gan.py:141-179 at the benchmark's batch 512 (kind "reference"; each timed
+    step is one FULL b512 D+G step = the workload itself).  Falls back to the oracle port (kind "port") only when
+    oracle/_ref was never built."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import contrad_oracle as O
     cores = usable_cores()
+    if reference_available():
+        from oracle import ref_runner
+        r = ref_runner.run_cpu(args.steps, args.warmup, batch=GLOBAL_BATCH, threads=cores)
+        value, ms, kind = r["images_per_s"], r["ms_per_step"], "reference"
+        sample = "one full D+G step at batch 512 (the whole b512 workload) per timed step; " + r["what"]
+        threads = r["threads"]
+    else:
+        value, ms, threads = _port_cpu(args.steps, args.warmup, cores)
+        kind, sample = "port", "full D+G step at batch 64 (1/8 of the b512 workload) per timed step, oracle port"
+    line = {"impl": "reference", "metric": "train_step_images_per_sec", "value": value, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def _port_cpu(steps, warmup, cores):
+    from oracle import contrad_oracle as O
     torch.set_num_threads(cores)
     n = 64
     gen_w = torch.Generator().manual_seed(0)
@@ -149,55 +176,31 @@ def run_reference(args):
         z_g = O.sample_latent(n); aug_g = O.sample_simclr_params(n, 32, 32)
         return O.train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=step)
 
-    for w in range(args.warmup):
+    for w in range(warmup):
         one(w + 1)
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        one(args.warmup + s + 1)
+    for s in range(steps):
+        one(warmup + s + 1)
     dt = time.perf_counter() - t0
-    value = n * args.steps / dt
-    sample = "full D+G step at batch 64 (1/8 of the b512 workload) per timed step"
-    line = {"impl": "reference", "metric": "train_step_images_per_sec", "value": value, "unit": "images/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
-    return 0
+    return n * steps / dt, 1e3 * dt / steps, torch.get_num_threads()
 
 
-def cpu_baseline_leg(seconds_budget=25.0):
-    from oracle import contrad_oracle as O
+def cpu_baseline_leg(seconds_budget=20.0):
+    """Bounded sample for the native line: 1 warm-up + at least 2 full b512 steps of the unmodified reference on the host
+    cores (stops once `seconds_budget` is used)."""
     cores = usable_cores()
-    prev = torch.get_num_threads()
-    torch.set_num_threads(cores)
-    n = 64
-    gen_w = torch.Generator().manual_seed(0)
-    sd_d, sd_g = O.make_d_state(generator=gen_w), O.make_g_state(generator=gen_w)
-    opt_g = O.Adam(O.trainable(sd_g).values(), 2e-4)
-    opt_d = O.Adam(O.trainable(sd_d).values(), 2e-4)
+    if reference_available():
+        from oracle import ref_runner
+        r = ref_runner.run_cpu(12, 1, batch=GLOBAL_BATCH, threads=cores, seconds_budget=seconds_budget)
+        return {"value": r["images_per_s"], "unit": "images/s", "cores": r["threads"], "kind": "reference",
+                "sample": "%d full D+G steps at batch 512 of the unmodified reference (oracle/_ref) on the host CPU, "
+                          "torch fp32, after 1 warm-up step" % r["steps"]}
     st_np, st_t = np.random.get_state(), torch.get_rng_state()
-    np.random.seed(0); torch.manual_seed(0)
-
-    def one(step):
-        images = torch.rand(n, 3, 32, 32)
-        z_d = O.sample_latent(n); aug_d = O.sample_simclr_params(3 * n, 32, 32)
-        z_g = O.sample_latent(n); aug_g = O.sample_simclr_params(n, 32, 32)
-        O.train_step(sd_g, sd_d, opt_g, opt_d, images, z_d, z_g, aug_d, aug_g, step=step)
-
-    one(1)
-    t0 = time.perf_counter()
-    steps = 0
-    while steps < 3 or (time.perf_counter() - t0 < seconds_budget and steps < 12):
-        one(steps + 2)
-        steps += 1
-    dt = time.perf_counter() - t0
-    np.random.set_state(st_np); torch.set_rng_state(st_t)
-    torch.set_num_threads(prev)
-    return {"value": n * steps / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": "%d full D+G steps at batch 64 (1/8 of the b512 workload) on the host CPU, torch fp32" % steps}
+    prev = torch.get_num_threads()
+    value, ms, threads = _port_cpu(6, 1, cores)
+    np.random.set_state(st_np); torch.set_rng_state(st_t); torch.set_num_threads(prev)
+    return {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "6 full D+G steps at batch 64 (1/8 of the b512 workload), oracle port, torch fp32"}
 
 
 # ----------------------------------------------------------------------------------------------- this repo's arm
@@ -301,6 +304,14 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    # ---- W > 1: the distributed D step against the single-process full-batch step on the same seeded batch
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import parity_multi
+        parity = parity_multi.check(W.P, W.G, W.D, OPTIONS, GLOBAL_BATCH, dev)
+        _log("parity check done: %s" % (parity,))
+
     # ---- device-resident arm
     _log("world built; set-up steps")
     if not args.no_graph:                         # untimed set-up: eager allocator warm-up steps + the capture
@@ -364,6 +375,17 @@ def run_native(args):
                 graphed_u8.release()
         except Exception as e:                                # noqa: BLE001 - optional leg: report, do not lose the line
             e2e_u8 = {"error": "%s: %s" % (type(e).__name__, e)}
+    # ---- the north_star denominator: the UNMODIFIED reference (oracle/_ref) on the same GPU(s), PyTorch eager
+    eager = None
+    if not args.no_eager_baseline and reference_available():
+        if not args.no_graph:
+            graphed.release()                      # free the graph's pool (and its NCCL kernels) before DDP starts
+        try:
+            eager = eager_gpu_baseline_leg(world, W.local_rank if world > 1 else 0, dev)
+            _log("eager reference leg done: %.3f ms/step" % eager["ms_per_step"])
+        except Exception as e:                                # noqa: BLE001 - report, do not lose the line
+            eager = {"error": "%s: %s" % (type(e).__name__, e)}
+            _log("eager reference leg failed: %s" % eager["error"])
     faulthandler.cancel_dump_traceback_later()
     line = None
     if rank == 0:
@@ -387,6 +409,14 @@ def run_native(args):
         }
         if e2e_u8 is not None:
             line["e2e_uint8_input"] = e2e_u8
+        if parity is not None:
+            line["parity_check"] = parity
+        if eager is not None:
+            if "value" in eager:
+                eager["ratio"] = value / eager["value"]            # device-resident value / reference eager
+                eager["ratio_e2e"] = e2e_value / eager["value"]    # like for like: both include H2D + 5 read-backs
+                eager["target"] = ">= 10x at 1 GPU, >= 6x at 8 GPUs (north_star)"
+            line["eager_gpu_baseline"] = eager
         if roof:
             line.update(roof)
         if cpu:
@@ -405,6 +435,22 @@ def run_native(args):
         dist.destroy_process_group()
     _log("done")
     return 0
+
+
+def eager_gpu_baseline_leg(world, local_rank, dev, steps=50, warmup=10):
+    """`oracle/_ref/train_gan.py`'s own `train()` loop on unmodified reference modules, `.cuda()`, PyTorch default
+    flags, DDP + SyncBatchNorm wrapping exactly as `worker()` does (train_gan.py:268-271,311-313), 50 steps after 10
+    warm-up steps, per-rank batch 512 // N.  Runs on every rank; the step time is the max over ranks."""
+    from oracle import ref_runner
+    r = ref_runner.run_gpu(steps, warmup, global_batch=GLOBAL_BATCH, local_rank=local_rank)
+    ms = torch.tensor([r["ms_per_step"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    return {"value": GLOBAL_BATCH / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "per_gpu_batch": r["per_gpu_batch"], "flags": r["flags"],
+            "kind": "reference", "what": r["what"]}
 
 
 def side_workloads():
@@ -528,6 +574,9 @@ def main():
     ap.add_argument("--no-u8-input", dest="u8_input", action="store_false",
                     help="skip the extra end-to-end leg fed with uint8 host images (row f3; N=1 only, e2e_uint8_input)")
     ap.add_argument("--u8-input", dest="u8_input", action="store_true", help=argparse.SUPPRESS)      # default on
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the reference-PyTorch-eager-on-this-GPU leg (eager_gpu_baseline)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the W > 1 parity check before the timed region")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (and DDP wrappers for N > 1) instead of the CUDA-graph step")
     ap.set_defaults(u8_input=True)
     args = ap.parse_args()

@@ -66,6 +66,30 @@ def install(shims=True):
     return installed
 
 
+def _wrap_reference_accumulate():
+    """The reference's `utils.accumulate` (utils.py:130-143) writes the EMA generator through `.data` in-place ops that
+    no version counter records; wrap it so that derived-weight memos (sg2_functional.weight_memo) are dropped after
+    every call.  (No-grad forwards already bypass the memo; this also covers a g_ema evaluated with grad enabled.)"""
+    try:
+        utils = importlib.import_module("utils")
+    except Exception:                                            # noqa: BLE001 - no reference `utils` on the path
+        return False
+    fn = getattr(utils, "accumulate", None)
+    if fn is None or getattr(fn, "_cb200_wrapped", False):
+        return False
+    from . import sg2_functional
+
+    def accumulate(*args, **kwargs):
+        out = fn(*args, **kwargs)
+        sg2_functional.bump_weight_epoch()
+        return out
+
+    accumulate._cb200_wrapped = True
+    accumulate.__doc__ = fn.__doc__
+    utils.accumulate = accumulate
+    return True
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
@@ -75,6 +99,7 @@ def main(argv=None):
     sys.argv = [script] + argv[1:]
     sys.path.insert(0, os.path.dirname(script))
     os.chdir(os.path.dirname(script))
+    _wrap_reference_accumulate()
     runpy.run_path(script, run_name="__main__")
 
 

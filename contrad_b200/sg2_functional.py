@@ -58,7 +58,14 @@ def weight_memo(param, key, make):
     tensors - and, through `_cached`, their GEMM re-layouts - are then built once per optimiser step instead of once per
     forward.  The entries keep their autograd history, so gradients of all the forwards flow into the parameter; only
     results of scale / pad / permute / reshape chains may be stored (their backward nodes hold no tensors, so they can
-    be back-propagated through any number of times, e.g. under gradient accumulation)."""
+    be back-propagated through any number of times, e.g. under gradient accumulation).
+
+    Forwards under `torch.no_grad()` are NEVER served from the memo: the EMA generator is only ever evaluated that way
+    (evaluate/gan.py:57-58, FID), and the reference's `utils.accumulate` (utils.py:130-143) updates it through
+    `param.data.mul_().add_()`, which neither torch's version counter nor `bump_weight_epoch` sees - a memo entry
+    would freeze g_ema at its first evaluation."""
+    if not torch.is_grad_enabled():
+        return make()
     tag = (param._version, _WEIGHT_EPOCH[0], param.requires_grad, torch.is_grad_enabled())
     memo = getattr(param, "_cb200_wmemo", None)
     if memo is None or memo[0] != tag:

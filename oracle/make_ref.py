@@ -1,0 +1,71 @@
+"""Recipe that materialises the UNMODIFIED reference under ``oracle/_ref/`` (TEST / MEASUREMENT INFRASTRUCTURE).
+
+    python oracle/make_ref.py            # copies /root/reference -> oracle/_ref (git-ignored, travels with gpurun)
+
+The reference is pure Python (+ two JIT-built CUDA ops that only the StyleGAN2 configs touch), so "building" it is a
+byte-for-byte copy of its sources and gin configs from where they lie under ``/root/reference``; nothing is edited
+and nothing is committed (``oracle/_ref/`` is listed in ``.gitignore``, not in ``.gpurunignore``: it has to reach the
+GPU box, where ``/root/reference`` does not exist).  ``bench.py --impl reference`` and the ``eager_gpu_baseline`` leg
+import these files through ``oracle/ref_import.py`` + the ``contrad_b200/compat`` shims for the four packages the
+image lacks (gin, tensorboardX, imageio, kornia).  ``__graft_entry__.build()`` runs this recipe whenever
+``/root/reference`` is present.  A manifest with the sha256 of every copied file is written next to the copy so that
+a reader can check that nothing was modified.
+"""
+import hashlib
+import json
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.environ.get("CONTRAD_REFERENCE_SRC", "/root/reference")
+DST = os.path.join(HERE, "_ref")
+
+# resources/ = README images (5 MB); third_party/tf = TensorFlow FID (needs tensorflow, out of scope)
+SKIP_DIRS = {".git", "resources", "__pycache__", "logs", "data"}
+SKIP_REL = {os.path.join("third_party", "tf")}
+KEEP_EXT = {".py", ".gin", ".cpp", ".cu", ".h", ".txt", ".yml", ".md"}
+
+
+def make(src=SRC, dst=DST, quiet=False):
+    if not os.path.isdir(os.path.join(src, "augment")):
+        raise RuntimeError("reference sources not found at %s" % src)
+    tmp = dst + ".tmp"
+    shutil.rmtree(tmp, ignore_errors=True)
+    manifest = {}
+    for root, dirs, files in os.walk(src):
+        rel_root = os.path.relpath(root, src)
+        dirs[:] = sorted(d for d in dirs if d not in SKIP_DIRS
+                         and os.path.normpath(os.path.join(rel_root, d)) not in SKIP_REL)
+        for name in sorted(files):
+            if os.path.splitext(name)[1] not in KEEP_EXT and name != "LICENSE":
+                continue
+            rel = os.path.normpath(os.path.join(rel_root, name))
+            out = os.path.join(tmp, rel)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            shutil.copyfile(os.path.join(root, name), out)
+            with open(out, "rb") as f:
+                manifest[rel] = hashlib.sha256(f.read()).hexdigest()
+    with open(os.path.join(tmp, "MANIFEST.json"), "w") as f:
+        json.dump({"source": src, "files": manifest}, f, indent=1, sort_keys=True)
+    shutil.rmtree(dst, ignore_errors=True)
+    os.rename(tmp, dst)
+    if not quiet:
+        print("oracle/_ref: %d files copied unmodified from %s" % (len(manifest), src))
+    return dst
+
+
+def verify(dst=DST):
+    """True when every file under oracle/_ref still has the sha256 recorded at copy time."""
+    with open(os.path.join(dst, "MANIFEST.json")) as f:
+        files = json.load(f)["files"]
+    for rel, digest in files.items():
+        with open(os.path.join(dst, rel), "rb") as f:
+            if hashlib.sha256(f.read()).hexdigest() != digest:
+                return False
+    return True
+
+
+if __name__ == "__main__":
+    make()
+    sys.exit(0 if verify() else 1)

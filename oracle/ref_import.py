@@ -12,8 +12,21 @@ import importlib
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("CONTRAD_REFERENCE_ROOT", "/root/reference")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_VENDORED = os.path.join(_REPO, "oracle", "_ref")        # unmodified copy made by oracle/make_ref.py (travels to the GPU box)
+
+
+def _find_root():
+    env = os.environ.get("CONTRAD_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _VENDORED):
+        if os.path.isdir(os.path.join(cand, "augment")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _COMPAT = os.path.join(_REPO, "contrad_b200", "compat")
 
 _REF_TOP_LEVEL = ("augment", "training", "third_party", "models", "penalty", "utils", "datasets", "evaluate")

@@ -205,6 +205,38 @@ def test_product_generator_host_logic(fx, states):
         _close(G(c["z"], style_mix=0.0, noise=c["noises"]), c["image_nomix"], 1e-4, "image (no mixing)")
 
 
+def test_ema_generator_is_not_served_stale_weights(fx, states):
+    """the reference's `utils.accumulate` (utils.py:130-143) updates g_ema through
+    `param.data.mul_().add_()`, which leaves `param._version` untouched; a no-grad forward of g_ema after such an
+    update must see the new weights (FixedSampleGeneration / FID, evaluate/gan.py:57-58)."""
+    import copy
+
+    def ref_accumulate(model_dst, model_src, decay=0.999):          # utils.py:130-143, restated
+        params_dst, params_src = dict(model_dst.named_parameters()), dict(model_src.named_parameters())
+        for k in params_dst:
+            params_dst[k].data.mul_(decay).add_(params_src[k].data, alpha=1 - decay)
+
+    with CK.patched():
+        G, _ = _product_models(states, fx["size"])
+        g_ema = copy.deepcopy(G).eval()
+        for p in g_ema.parameters():
+            p.requires_grad_(False)
+        c = fx["g_case"]
+        with torch.no_grad():
+            img0 = g_ema(c["z"], style_mix=0.0, noise=c["noises"]).clone()
+            versions = [p._version for p in g_ema.parameters()]
+            src = copy.deepcopy(G)
+            for p in src.parameters():
+                p.data.add_(0.05 * torch.randn_like(p))
+            ref_accumulate(g_ema, src, decay=0.5)
+            assert versions == [p._version for p in g_ema.parameters()]        # the update is invisible to torch
+            img1 = g_ema(c["z"], style_mix=0.0, noise=c["noises"])
+            fresh = copy.deepcopy(g_ema)
+            want = fresh(c["z"], style_mix=0.0, noise=c["noises"])
+        assert float((img1 - img0).abs().max()) > 1e-3, "g_ema output did not move after accumulate()"
+        _close(img1, want, 1e-6, "g_ema after accumulate vs a fresh copy of the same weights")
+
+
 def test_product_dstep_losses(fx, states):
     from contrad_b200.training.gan import stylegan2 as T
     import tests.cpu_loss_standins as LS
