@@ -9,6 +9,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import kernels as K
 from .. import staging
 from ..functional import (AugmentSimCLRFn, AugmentSimCLRMixedFn, CutOutFn, DiffAugFn, GaussianBlurFn, NoiseClampFn,
                           ShiftFlipFn)
@@ -260,24 +261,37 @@ class FusedSimCLR(nn.Sequential):
     The child modules hold the gin-configured hyper-parameters and draw the random numbers (in the
     reference order); the arithmetic is cb200_augment_simclr_fwd/bwd."""
 
+    def _draw_cfg(self):
+        """{p_flip, p_jitter, p_gray, contrast, hue, saturation, value ranges} of the child modules (gin-configured)."""
+        apply_cj, apply_gray = self[2], self[3]
+        cj = apply_cj.fn
+        rng = lambda r, centre: (centre, centre) if r is None else (r[0], r[1])
+        return ((0.5, apply_cj.p, apply_gray.p) + rng(cj.contrast, 1.0) + rng(cj.hue, 0.0) + rng(cj.saturation, 1.0)
+                + rng(cj.brightness, 1.0))
+
     def sample_params(self, inputs):
+        """The parameter block of one call.
+
+        Eager calls draw every factor with the reference's own torch / numpy calls in the reference's order (a given
+        seed consumes the RNG streams exactly like `augment.simclr()` does: tests/test_host_logic.py replays the
+        fixtures' seeds).  Under `staging.Recorder` (the step is being turned into a CUDA graph) the ~20 small ATen ops
+        of that sequence would each become a graph node, so the block is built by ONE device draw of [7, n] uniforms
+        mapped by cb200_augment_simclr_params (bernoulli(p) = u < p, uniform_(lo, hi) = lo + (hi - lo) u: the same
+        distributions; seed parity with the eager sequence is given up there - DESIGN 6) plus the host-staged crop
+        boxes and jitter order (row 11, kernel order = -1)."""
         rrc, flip, apply_cj, apply_gray = self[0], self[1], self[2], self[3]
         n, dev = inputs.shape[0], inputs.device
         shape = _ShapeOnly(inputs.shape)
-        recording = staging.recording()
-        p = torch.empty(_N_FIELDS + (1 if recording else 0), n, device=dev)
+        if staging.recording():
+            boxes = staging.stage(lambda: rrc.sample(shape), dev, shape=(4, n))
+            order_src = staging.stage(lambda: torch.tensor([float(apply_cj.fn.draw_order())]), dev, shape=(1,))
+            u = torch.rand(7, n, device=dev)
+            return K.augment_simclr_params(boxes, u, order_src, _N_FIELDS + 1, self._draw_cfg()), -1
+        p = torch.empty(_N_FIELDS, n, device=dev)
         p[0:4] = staging.stage(lambda: rrc.sample(shape), dev, shape=(4, n))
         p[4] = flip.sample(inputs)
         p[5] = apply_cj.sample(inputs)
-        if recording:
-            # CUDA-graph capture: the jitter order must not be baked into the launch.  It is staged as a device
-            # scalar (row 11, kernel order = -1); the device draws keep the sequence of order 0 (i.i.d. draws, so
-            # the distribution is the reference's; only the pairing of draws to factors differs when order = 1).
-            p[11] = staging.stage(lambda: torch.tensor([float(apply_cj.fn.draw_order())]), dev, shape=(1,))
-            _, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs, order=0)
-            order = -1
-        else:
-            order, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs)
+        order, p[6], p[7], p[8], p[9] = apply_cj.fn.sample(inputs)
         p[10] = apply_gray.sample(inputs)
         return p, order
 

@@ -304,6 +304,37 @@ inline int flat_grid(long long n) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Parameter block of the fused SimCLR chain from raw draws (one launch instead of ~20 ATen ops per call):
+//   boxes [4,B]  sx, sy, bx, by  - numpy draws of RandomResizeCropLayer.sample (augment/spatial.py:119-143), host-staged
+//   u     [7,B]  i.i.d. U[0,1)   - device draws: flip, apply-jitter, contrast, hue, saturation, value, apply-gray
+//   order_src    device scalar (0 / 1) or NULL -> params row 11 is written only when rows == 12
+// Mapping = the reference's own: bernoulli(p) = (u < p) (HorizontalFlipLayer: sign = 2*b - 1, spatial.py:86-88;
+// RandomApply mask, augment/__init__.py:100-103), uniform_(lo, hi) = lo + (hi - lo) * u (color_jitter.py:44-63).
+// ------------------------------------------------------------------------------------------------
+struct SimclrDrawCfg {
+    float p_flip, p_jitter, p_gray;
+    float c_lo, c_hi, h_lo, h_hi, s_lo, s_hi, v_lo, v_hi;
+};
+
+__global__ void __launch_bounds__(256)
+simclr_params_kernel(const float* __restrict__ boxes, const float* __restrict__ u, const float* __restrict__ order_src,
+                     float* __restrict__ params, int B, int rows, SimclrDrawCfg c) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B) return;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) params[(size_t)r * B + i] = boxes[(size_t)r * B + i];
+    params[(size_t)4 * B + i] = (u[i] < c.p_flip) ? 1.f : -1.f;
+    params[(size_t)5 * B + i] = (u[(size_t)B + i] < c.p_jitter) ? 1.f : 0.f;
+    params[(size_t)6 * B + i] = c.c_lo + (c.c_hi - c.c_lo) * u[(size_t)2 * B + i];
+    params[(size_t)7 * B + i] = c.h_lo + (c.h_hi - c.h_lo) * u[(size_t)3 * B + i];
+    params[(size_t)8 * B + i] = c.s_lo + (c.s_hi - c.s_lo) * u[(size_t)4 * B + i];
+    params[(size_t)9 * B + i] = c.v_lo + (c.v_hi - c.v_lo) * u[(size_t)5 * B + i];
+    params[(size_t)10 * B + i] = (u[(size_t)6 * B + i] < c.p_gray) ? 1.f : 0.f;
+    if (rows > 11) params[(size_t)11 * B + i] = order_src ? order_src[0] : 0.f;
+}
+
 }  // namespace
 
 extern "C" int cb200_shift_flip_fwd(const float* x, float* y, const float* params, int B, int P, int H, int W,
@@ -396,5 +427,21 @@ extern "C" int cb200_diffaug_bwd(const float* dy, float* dx, const float* params
     diffaug_bwd_apply_kernel<<<grid, kT, 0, st>>>(dy, dx, params, gsums, B, H, W, flags);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("diffaug_bwd");
+    return CB200_OK;
+}
+
+// params[rows,B] (rows = 11, or 12 with the per-image jitter order in row 11) from host-staged crop boxes [4,B] and
+// device uniforms u[7,B]; cfg = {p_flip, p_jitter, p_gray, contrast lo/hi, hue lo/hi, saturation lo/hi, value lo/hi}.
+extern "C" int cb200_augment_simclr_params(const float* boxes, const float* u, const float* order_src, float* params,
+                                           int B, int rows, const float* cfg11, void* stream) {
+    CB200_CHECK_ARG(B > 0 && (rows == 11 || rows == 12), "augment_simclr_params: B=%d rows=%d", B, rows);
+    SimclrDrawCfg c;
+    c.p_flip = cfg11[0]; c.p_jitter = cfg11[1]; c.p_gray = cfg11[2];
+    c.c_lo = cfg11[3]; c.c_hi = cfg11[4]; c.h_lo = cfg11[5]; c.h_hi = cfg11[6];
+    c.s_lo = cfg11[7]; c.s_hi = cfg11[8]; c.v_lo = cfg11[9]; c.v_hi = cfg11[10];
+    simclr_params_kernel<<<(B + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(boxes, u, order_src, params, B,
+                                                                                          rows, c);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("augment_simclr_params");
     return CB200_OK;
 }

@@ -303,6 +303,36 @@ round_tf32_vec_kernel(const float4* __restrict__ x, float4* __restrict__ y, long
     }
 }
 
+
+// Error-compensated TF32 operands ("3xTF32" without touching the GEMM kernels): x = hi + lo with hi = rn_tf32(x),
+// lo = rn_tf32(x - hi) (x - hi is exact in fp32).  A product (a_hi + a_lo)(b_hi + b_lo) ~ a_hi b_hi + a_lo b_hi + a_hi b_lo
+// is a plain GEMM / convolution over a CONCATENATED reduction axis, so the split operands are written in the layouts
+// the existing kernels reduce over:
+//   mode 0: out[rows, 3C] = [hi | lo | hi]      (channel concat: pairs with weights [w_hi | w_hi | w_lo] along Cin)
+//   mode 1: out[rows, 2C] = [hi | hi]           (pairs with weights [w_hi | w_lo]: only the weight is compensated)
+//   mode 2: out[2, rows, C] = hi rows, lo rows  (batch concat for weight-gradient GEMMs, paired with [g ; g])
+__global__ void __launch_bounds__(kT)
+split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ out, long long rows, int c4, int mode) {
+    const long long n4 = rows * c4;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n4; i += (long long)gridDim.x * kT) {
+        const float4 v = x[i];
+        float4 hi, lo;
+        hi.x = round_tf32(v.x); hi.y = round_tf32(v.y); hi.z = round_tf32(v.z); hi.w = round_tf32(v.w);
+        lo.x = round_tf32(v.x - hi.x); lo.y = round_tf32(v.y - hi.y); lo.z = round_tf32(v.z - hi.z); lo.w = round_tf32(v.w - hi.w);
+        const long long r = i / c4;
+        const int c = (int)(i - r * c4);
+        if (mode == 0) {
+            float4* o = out + r * 3 * c4 + c;
+            o[0] = hi; o[c4] = lo; o[2 * c4] = hi;
+        } else if (mode == 1) {
+            float4* o = out + r * 2 * c4 + c;
+            o[0] = hi; o[c4] = hi;
+        } else {
+            out[i] = hi; out[n4 + i] = lo;
+        }
+    }
+}
+
 // Row chunks of the column-reduction grids: about 128 rows per chunk, but never fewer CTAs than ~8 per SM over the whole
 // (column blocks x chunks) grid - [512, 8192] used to run on 128 CTAs, [32768, 256] on 256 (0.8 - 2 TB/s, ncu launch
 // list of round 1) - and at least 4 rows per row lane so that the unrolled loop body is used.
@@ -467,5 +497,20 @@ extern "C" int cb200_round_tf32(const float* x, float* y, long long n, void* str
     }
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("round_tf32");
+    return CB200_OK;
+}
+
+// x[rows, C] (C % 4 == 0, 16-byte aligned) -> split TF32 operands, see split_tf32_kernel (mode 0: [rows, 3C] hi|lo|hi,
+// mode 1: [rows, 2C] hi|hi, mode 2: [2, rows, C] hi ; lo).
+extern "C" int cb200_split_tf32(const float* x, float* out, long long rows, int C, int mode, void* stream) {
+    CB200_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && mode >= 0 && mode <= 2, "split_tf32: rows=%lld C=%d mode=%d", rows, C, mode);
+    CB200_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "split_tf32: alignment");
+    const long long n4 = rows * (C / 4);
+    long long grid = (n4 + kT - 1) / kT;
+    if (grid > 148 * 16) grid = 148 * 16;
+    split_tf32_kernel<<<(unsigned)grid, kT, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), rows, C / 4, mode);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("split_tf32");
     return CB200_OK;
 }

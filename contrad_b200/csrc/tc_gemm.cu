@@ -57,6 +57,12 @@ struct TapGemmParams {
     int round_out;        // round outputs to TF32 (they feed another tensor-core GEMM)
     float* colsum;        // [N] or null: += column sums of the stored outputs (bias gradient of the producing layer)
     int n_total;          // N (columns of the whole problem)
+    // split-K (single-CTA kernel only): gridDim.z = classes * splits; split s accumulates k-blocks
+    // [s * kb_per_split, (s+1) * kb_per_split) and parks its raw 128 x BN partial in `ws`; the LAST split to arrive at a
+    // tile (per-tile arrival counter) adds the partials in split order and runs the ordinary epilogue.
+    int splits, kb_per_split, classes;
+    float* ws;            // [splits][units][128 * BN] fp32, units = gridDim.x * gridDim.y * classes
+    int* counters;        // [units], zero between launches (the finishing CTA resets its counter)
     int debug;            // profiling experiments only (env CB200_TAPGEMM_DEBUG): 1 no stores, 2 no MMA, 4 no A loads, 8 no B loads
 };
 
@@ -76,10 +82,13 @@ struct SmemLayout {
 constexpr int kEpiStride = 36;                        // floats per staged row: 16-byte aligned, conflict-free float4
 constexpr int kEpiWarpFloats = 32 * kEpiStride;       // 4.5 KB per epilogue warp
 
-template <int BN>
+// MODE 0: accumulators from TMEM -> epilogue -> global.  MODE 1 (split-K): raw accumulators -> `ws_tile` (row-major
+// 128 x BN, coalesced).  MODE 2 (split-K finisher): sum of `ws_splits` partials (stride `ws_stride` floats) -> epilogue.
+template <int BN, int MODE = 0>
 __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
                                                      uint32_t tmem_base, int warp, int lane, float* stage_buf,
-                                                     float* cs_smem = nullptr) {
+                                                     float* cs_smem = nullptr, float* ws_tile = nullptr,
+                                                     int ws_splits = 0, size_t ws_stride = 0) {
     const int q = warp & 3;
     float* st = stage_buf + q * kEpiWarpFloats;
     int r = q * 32 + lane;
@@ -98,15 +107,27 @@ __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, con
     const int col4 = (lane & 7) * 4;                            // first of this lane's 4 columns within the chunk
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-        tc::tmem_ld_wait();
-        if (p.debug & 1) continue;
+        if constexpr (MODE != 2) {
+            uint32_t v[32];
+            tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+            tc::tmem_ld_wait();
+            if (p.debug & 1) continue;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(st + lane * kEpiStride + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        __syncwarp();
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(st + lane * kEpiStride + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            __syncwarp();
+        }
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int row = it * 4 + sub;
+                *reinterpret_cast<float4*>(ws_tile + (size_t)(q * 32 + row) * BN + c0 + col4) =
+                    *reinterpret_cast<const float4*>(st + row * kEpiStride + col4);
+            }
+            __syncwarp();
+            continue;
+        }
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + col4));
         long long offs[8];
@@ -123,7 +144,30 @@ __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, con
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int row = it * 4 + sub;
-            float4 o = *reinterpret_cast<const float4*>(st + row * kEpiStride + col4);
+            float4 o;
+            if constexpr (MODE == 2) {
+                o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (offs[it] >= 0) {
+                    const float* src = ws_tile + (size_t)(q * 32 + row) * BN + c0 + col4;
+                    int sp = 0;
+                    for (; sp + 4 <= ws_splits; sp += 4) {          // four independent loads in flight, fixed summation order
+                        const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * ws_stride));
+                        const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 1) * ws_stride));
+                        const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 2) * ws_stride));
+                        const float4 t3 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(sp + 3) * ws_stride));
+                        o.x += t0.x; o.y += t0.y; o.z += t0.z; o.w += t0.w;
+                        o.x += t1.x; o.y += t1.y; o.z += t1.z; o.w += t1.w;
+                        o.x += t2.x; o.y += t2.y; o.z += t2.z; o.w += t2.w;
+                        o.x += t3.x; o.y += t3.y; o.z += t3.z; o.w += t3.w;
+                    }
+                    for (; sp < ws_splits; ++sp) {
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sp * ws_stride));
+                        o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                    }
+                }
+            } else {
+                o = *reinterpret_cast<const float4*>(st + row * kEpiStride + col4);
+            }
             if (offs[it] >= 0) {
                 o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                 if (p.dact) {
@@ -161,6 +205,37 @@ __device__ __forceinline__ void epilogue_rows_nowait(const TapGemmParams& p, con
     }
 }
 
+
+// Split-K tail of one CTA (the four epilogue warps): park the raw 128 x BN partial, count the arrival, and let the LAST
+// split of this output tile add all partials in split order and run the fused epilogue (deterministic).  `flag` = one
+// shared-memory word of the CTA.
+template <int BN>
+__device__ __forceinline__ void splitk_epilogue(const TapGemmParams& p, const int (&base)[4], int cls, int n0, int split,
+                                                uint32_t tmem_base, uint64_t* tmem_full_bar, int warp, int lane,
+                                                float* stage_buf, uint32_t* flag) {
+    const int units = (int)(gridDim.x * gridDim.y) * p.classes;
+    const int unit = (cls * (int)gridDim.y + (int)blockIdx.y) * (int)gridDim.x + (int)blockIdx.x;
+    const size_t tile_floats = (size_t)kBlockM * BN;
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::fence_after_sync();
+    epilogue_rows_nowait<BN, 1>(p, base, cls, n0, tmem_base, warp, lane, stage_buf, nullptr,
+                                p.ws + ((size_t)split * units + unit) * tile_floats);
+    __threadfence();                                       // partial visible device-wide before the arrival
+    asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps
+    if (threadIdx.x == 128) {
+        const int old = atomicAdd(p.counters + unit, 1);
+        const int last = (old == p.splits - 1) ? 1 : 0;
+        if (last) p.counters[unit] = 0;                    // every split has arrived: re-arm for the next launch
+        *flag = (uint32_t)last;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (*flag) {
+        __threadfence();
+        epilogue_rows_nowait<BN, 2>(p, base, cls, n0, tmem_base, warp, lane, stage_buf, nullptr,
+                                    p.ws + (size_t)unit * tile_floats, p.splits, (size_t)units * tile_floats);
+    }
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const TapGemmParams& p, const int (&base)[4], int cls, int n0,
                                               uint32_t tmem_base, uint64_t* tmem_full_bar, int warp, int lane,
@@ -171,7 +246,7 @@ __device__ __forceinline__ void epilogue_rows(const TapGemmParams& p, const int 
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)    // 2 CTAs per SM (<= 128 registers): the split-K grid is sized for it
 tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -183,9 +258,11 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int cls = blockIdx.z;
+    const int cls = (int)blockIdx.z % p.classes;
+    const int split = (int)blockIdx.z / p.classes;
     const int n0 = blockIdx.y * BN;
-    const int num_kb = p.ntaps * p.cblocks;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(p.ntaps * p.cblocks, kb_begin + p.kb_per_split);
 
     // tile -> base coordinates along the 4 spatial dims
     int base[4];
@@ -220,7 +297,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         if (tc::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
                 const int t = kb / p.cblocks;
                 const int cb = kb - t * p.cblocks;
                 tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -240,7 +317,7 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
         constexpr uint32_t idesc = tc::idesc_tf32(kBlockM, BN, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
             tc::mbar_wait(&full_bar[stage], phase);
             tc::fence_after_sync();
             if (tc::elect_one()) {
@@ -251,20 +328,25 @@ tap_gemm_kernel(const __grid_constant__ TapGemmParams p) {
                     for (int k = 0; k < kBlockK / 8; ++k) {
                         const uint64_t adesc = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-                        tc::mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                        tc::mma_tf32(tmem_base, adesc, bdesc, idesc, (kb > kb_begin || k) ? 1u : 0u);
                     }
                     tc::mma_commit(&empty_bar[stage]);
-                    if (kb == num_kb - 1) tc::mma_commit(tmem_full_bar);
+                    if (kb == kb_end - 1) tc::mma_commit(tmem_full_bar);
                 } else {
                     tc::mbar_arrive(&empty_bar[stage]);
-                    if (kb == num_kb - 1) tc::mbar_arrive(tmem_full_bar);
+                    if (kb == kb_end - 1) tc::mbar_arrive(tmem_full_bar);
                 }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
-        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem));
+        if (p.splits <= 1) {
+            epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem));
+        } else {
+            splitk_epilogue<BN>(p, base, cls, n0, split, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem),
+                                tmem_slot + 1);
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -305,9 +387,11 @@ tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const bool leader = rank == 0;
-    const int cls = blockIdx.z;
+    const int cls = (int)blockIdx.z % p.classes;
+    const int split = (int)blockIdx.z / p.classes;
     const int n0 = blockIdx.y * BN;
-    const int num_kb = p.ntaps * p.cblocks;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(p.ntaps * p.cblocks, kb_begin + p.kb_per_split);
 
     int base[4];
     {
@@ -342,7 +426,7 @@ tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
         if (tc::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
                 const int t = kb / p.cblocks;
                 const int cb = kb - t * p.cblocks;
                 tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -361,7 +445,7 @@ tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
         constexpr uint32_t idesc = tc::idesc_tf32(256, BN, 0, 0);
         int stage = 0;
         uint32_t phase = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
             tc::mbar_wait(&full_bar[stage], phase);
             tc::fence_after_sync();
             if (tc::elect_one()) {
@@ -371,16 +455,21 @@ tap_gemm2_kernel(const __grid_constant__ TapGemmParams p) {
                 for (int k = 0; k < kBlockK / 8; ++k) {
                     const uint64_t adesc = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
                     const uint64_t bdesc = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-                    tc::mma2_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+                    tc::mma2_tf32(tmem_base, adesc, bdesc, idesc, (kb > kb_begin || k) ? 1u : 0u);
                 }
                 tc::mma2_commit_multicast(&empty_bar[stage]);
-                if (kb == num_kb - 1) tc::mma2_commit_multicast(tmem_full_bar);
+                if (kb == kb_end - 1) tc::mma2_commit_multicast(tmem_full_bar);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
-        epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem));
+        if (p.splits <= 1) {
+            epilogue_rows<BN>(p, base, cls, n0, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem));
+        } else {
+            splitk_epilogue<BN>(p, base, cls, n0, split, tmem_base, tmem_full_bar, warp, lane, reinterpret_cast<float*>(smem),
+                                tmem_slot + 1);
+        }
     }
     tc::fence_before_sync();
     tc::cluster_sync_all();
@@ -642,6 +731,50 @@ void pick_spatial_box(int Wo, int Ho, int* wt, int* ht, int* bt) {
     *bt = rest / *ht;
 }
 
+// One-shot split-K workspace handed over by the caller right before a tap-GEMM call (cb200_tapgemm_workspace):
+// thread-local, consumed by the next dispatch() of this thread.
+struct SplitWs {
+    float* ws = nullptr;
+    long long bytes = 0;
+    int* counters = nullptr;
+    int n_counters = 0;
+};
+thread_local SplitWs g_split_ws;
+
+// 0 = never split K, 1 = split when the tile list cannot fill the GPU (default); env CB200_TAPGEMM_SPLITK overrides.
+int splitk_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CB200_TAPGEMM_SPLITK");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+// CTA-pair tiles + split-K for small tile lists: OFF by default - measured 1.5-2x SLOWER than the single-CTA kernel on
+// every small shape (tools/bench_small_gemm.py: 4x4x512 at 64 images 54 -> 103 us); env CB200_TAPGEMM_SMALL_PAIR=1 enables
+// it for A/B runs.
+int small_pair_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CB200_TAPGEMM_SMALL_PAIR");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
+// 1 (default) = deep shared-memory ring for grids of at most one CTA per SM; env CB200_TAPGEMM_DEEP=0 disables.
+int deep_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("CB200_TAPGEMM_DEEP");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+int plan_splits(const SplitWs& w, int units, int num_kb, int bn);
+
 struct Epilogue {
     const float* bias;
     const float* dact;
@@ -650,8 +783,26 @@ struct Epilogue {
     float* colsum = nullptr;
 };
 
+// Split-K plan for a tile list that cannot fill the GPU: one CTA per SM (the deep-pipeline variant below), every split
+// keeps >= 8 k-blocks.  Returns the number of splits (>= 1).  Measured on the per-rank shapes of the 8-GPU run
+// (tools/bench_small_gemm.py, profiles/small_gemm_r2.md): splitting pays only for SHORT tile lists with a LONG reduction
+// (heads forward 8192 -> 1536 at 64 / 192 rows: 85 -> 54 us; 4x4x512 layers at 64 images: 54 -> 42 us); with more tiles or
+// a shorter K the partial-tile traffic and the serial finisher cost more than the extra SMs bring.
+int plan_splits(const SplitWs& w, int units, int num_kb, int bn) {
+    int splits = 1;
+    if (w.ws && w.counters && splitk_mode() && units <= 48 && num_kb >= 96 && units <= w.n_counters) {
+        splits = 148 / units;
+        if (splits > num_kb / 8) splits = num_kb / 8;
+        if (splits > 16) splits = 16;
+        const long long per_split = (long long)units * kBlockM * bn * 4;
+        if ((long long)splits * per_split > w.bytes) splits = (int)(w.bytes / per_split);
+        if (splits < 1) splits = 1;
+    }
+    return splits;
+}
+
 template <int BN, int STAGES>
-int launch(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
+int launch_cfg(TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
     using L = SmemLayout<BN, STAGES>;
     static bool configured_dev[64] = {};          // per device: the attribute belongs to the device's context
     bool& configured = cb200_device_flag(configured_dev);
@@ -664,15 +815,40 @@ int launch(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaSt
         }
         configured = true;
     }
-    dim3 grid(m_tiles, n_tiles, classes);
+    dim3 grid(m_tiles, n_tiles, classes * p.splits);
     tap_gemm_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, st>>>(p);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH(name);
     return CB200_OK;
 }
 
+// STAGES = ring depth when the grid is large (2 CTAs per SM), DEEP = ring depth when the whole grid is at most one CTA per
+// SM: a lone CTA needs ~1 us of TMA latency covered by loads in flight (measured: 3 x 32 KB stages sustain one k-block
+// per 0.36 us against 0.19 us of MMA time), so the small-grid variant spends the SM's whole shared memory on the ring.
+template <int BN, int STAGES, int DEEP>
+int launch(const TapGemmParams& p_in, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name,
+           const SplitWs& w) {
+    TapGemmParams p = p_in;
+    const int units = m_tiles * n_tiles * classes;
+    const int num_kb = p.ntaps * p.cblocks;
+    const int splits = plan_splits(w, units, num_kb, BN);
+    p.kb_per_split = (num_kb + splits - 1) / splits;
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.classes = classes;
+    p.ws = w.ws;
+    p.counters = w.counters;
+    const bool deep = units * p.splits <= 148 && deep_mode();
+    static const bool verbose = getenv("CB200_TAPGEMM_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "[tapgemm] %s BN=%d m_tiles=%d n_tiles=%d classes=%d k-blocks=%d -> splits=%d (%d CTAs, %d stages)\n",
+                name, BN, m_tiles, n_tiles, classes, num_kb, p.splits, units * p.splits, deep ? DEEP : STAGES);
+    if (deep) return launch_cfg<BN, DEEP>(p, m_tiles, n_tiles, classes, st, name);
+    return launch_cfg<BN, STAGES>(p, m_tiles, n_tiles, classes, st, name);
+}
+
 template <int BN, int STAGES>
-int launch2(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name) {
+int launch2(const TapGemmParams& p_in, int m_tiles, int n_tiles, int classes, cudaStream_t st, const char* name,
+            const SplitWs& w = SplitWs()) {
     using L = SmemLayout2<BN, STAGES>;
     static bool configured_dev[64] = {};          // per device: the attribute belongs to the device's context
     bool& configured = cb200_device_flag(configured_dev);
@@ -685,9 +861,23 @@ int launch2(const TapGemmParams& p, int m_tiles, int n_tiles, int classes, cudaS
         }
         configured = true;
     }
+    TapGemmParams p = p_in;
+    const int m_pad = (m_tiles + 1) & ~1;
+    const int units = m_pad * n_tiles * classes;             // CTAs per split (partials / counters are per CTA)
+    const int num_kb = p.ntaps * p.cblocks;
+    const int splits = plan_splits(w, units, num_kb, BN);
+    p.kb_per_split = (num_kb + splits - 1) / splits;
+    p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.classes = classes;
+    p.ws = w.ws;
+    p.counters = w.counters;
+    static const bool verbose = getenv("CB200_TAPGEMM_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "[tapgemm] %s pair BN=%d m_tiles=%d n_tiles=%d classes=%d k-blocks=%d -> splits=%d (%d CTAs)\n", name,
+                BN, m_tiles, n_tiles, classes, num_kb, p.splits, units * p.splits);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((m_tiles + 1) & ~1, n_tiles, classes);
+    cfg.gridDim = dim3(m_pad, n_tiles, classes * p.splits);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = st;
@@ -784,6 +974,10 @@ int b_box_rows(int N, int m_tiles) {
         if (N % 256 == 0) return 128;      // pair, BN = 256: half per CTA
         if (N % 128 == 0) return 64;       // pair, BN = 128
     }
+    if (small_pair_mode() && m_tiles >= 2 && g_split_ws.ws) {        // the split-K CTA-pair path of dispatch()
+        if (N % 256 == 0) return 128;
+        if (N % 128 == 0 && m_tiles >= 4) return 64;
+    }
     return (N % 128 == 0) ? 128 : (N % 64 == 0 ? 64 : 32);
 }
 
@@ -798,8 +992,11 @@ int debug_flags() {
 
 int dispatch(const TapGemmParams& p_in, int N, int m_tiles, int classes, cudaStream_t st, const char* name) {
     TapGemmParams p = p_in;
+    const SplitWs w = g_split_ws;
+    g_split_ws = SplitWs();                 // one-shot
     p.debug = debug_flags();
     p.n_total = N;
+    p.splits = 1; p.kb_per_split = p.ntaps * p.cblocks; p.classes = classes;
     if (p.colsum) {
         cudaError_t e = cudaMemsetAsync(p.colsum, 0, sizeof(float) * (size_t)N, st);
         if (e != cudaSuccess) { cb200_set_error("%s: colsum memset: %s", name, cudaGetErrorString(e)); return (int)e; }
@@ -816,9 +1013,16 @@ int dispatch(const TapGemmParams& p_in, int N, int m_tiles, int classes, cudaStr
         if (N % 256 == 0) return launch2<256, 4>(p, m_tiles, N / 256, classes, st, name);     // 32 KB / stage / CTA
         if (N % 128 == 0) return launch2<128, 4>(p, m_tiles, N / 128, classes, st, name);     // 24 KB / stage / CTA
     }
-    if (N % 128 == 0) return launch<128, 3>(p, m_tiles, N / 128, classes, st, name);
-    if (N % 64 == 0) return launch<64, 4>(p, m_tiles, N / 64, classes, st, name);     // 96 KB -> 2 CTAs / SM
-    if (N % 32 == 0) return launch<32, 4>(p, m_tiles, N / 32, classes, st, name);     // 80 KB -> 2 CTAs / SM
+    // small tile lists (deep layers / heads at a small per-GPU batch): these GEMMs are bound by L2 -> SM operand traffic
+    // (measured: the 128 x 128 tile tops out at 260-380 TFLOP/s however many CTAs run), so take the 256 x 256 CTA-pair
+    // tile (half the operand bytes per FLOP) and fill the GPU by splitting K
+    if (small_pair_mode() && m_tiles >= 2 && w.ws) {
+        if (N % 256 == 0) return launch2<256, 4>(p, m_tiles, N / 256, classes, st, name, w);
+        if (N % 128 == 0 && m_tiles >= 4) return launch2<128, 4>(p, m_tiles, N / 128, classes, st, name, w);
+    }
+    if (N % 128 == 0) return launch<128, 3, 6>(p, m_tiles, N / 128, classes, st, name, w);   // 96 KB (2 CTAs / SM) | 192 KB
+    if (N % 64 == 0) return launch<64, 4, 8>(p, m_tiles, N / 64, classes, st, name, w);      // 96 KB | 192 KB
+    if (N % 32 == 0) return launch<32, 4, 8>(p, m_tiles, N / 32, classes, st, name, w);      // 80 KB | 160 KB
     cb200_set_error("%s: N=%d must be a multiple of 32", name, N);
     return CB200_ERR_ARG;
 }
@@ -887,6 +1091,19 @@ int conv_like(const float* src, int Bn, int Hs, int Ws, int C,           // A te
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
+
+// Optional split-K workspace for the NEXT cb200_gemm_nt_tf32 / cb200_conv2d_nhwc_fwd / cb200_conv2d_nhwc_dgrad call made
+// by this host thread (one-shot).  ws: device scratch of `bytes` bytes (any contents); counters: `n_counters` int32 that
+// are ZERO and stay zero between launches (the kernel re-arms them) - one persistent buffer per (device, stream).
+// Without it (or when the tile list already fills the GPU) the kernels run unsplit.  The caller keeps `ws` alive until
+// the launch has been enqueued on its stream (stream-ordered reuse afterwards is fine).
+extern "C" int cb200_tapgemm_workspace(void* ws, long long bytes, int* counters, int n_counters) {
+    g_split_ws.ws = static_cast<float*>(ws);
+    g_split_ws.bytes = ws ? bytes : 0;
+    g_split_ws.counters = counters;
+    g_split_ws.n_counters = counters ? n_counters : 0;
+    return CB200_OK;
+}
 
 // out[M, N] (row stride ldo) = epi( A[M, K] (row stride lda) * Bw[N, K]^T (row stride ldb) + bias ), TF32 tensor cores.
 // epi = LeakyReLU(slope) when dact == NULL, else multiply by lrelu'(dact[M,N]) (dact shares ldo with out).

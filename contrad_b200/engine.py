@@ -50,21 +50,94 @@ def broadcast_parameters(model, src=0):
             dist.broadcast(t, src)
 
 
-def allreduce_gradients(model):
-    """DDP's gradient averaging as ONE flat all-reduce (capturable in a CUDA graph, no bucket hooks): used when
-    `P.distributed` and the model is not DDP-wrapped."""
+def allreduce_gradients(model, params=None, group=None):
+    """DDP's gradient averaging for a bare module (capturable in a CUDA graph, no bucket hooks): used when
+    `P.distributed` and the model is not DDP-wrapped.  NCCL: ONE grouped launch that all-reduces every gradient tensor
+    in place with ReduceOp.AVG (ncclGroupStart/End through c10d's coalescing manager) - no flattening copy, no divide,
+    no copy back.  Other backends (gloo in the CPU tests): one flat SUM all-reduce and a divide."""
     import torch.distributed as dist
-    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    params = list(model.parameters()) if params is None else params
+    grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
+    if dist.get_backend(group) == "nccl":
+        with dist._coalescing_manager(group=group):
+            for g in grads:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=group)
+        return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
-    flat.div_(dist.get_world_size())
+    dist.all_reduce(flat, group=group)
+    flat.div_(dist.get_world_size(group))
     views, off = [], 0
     for g in grads:
         views.append(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
     torch._foreach_copy_(grads, views)
+
+
+class GradSync(object):
+    """Overlapped gradient averaging for a bare (non-DDP) module under `P.distributed` (train_gan.py:311-313 semantics).
+
+    * `early` parameters (for D_SNDCGAN: the six head layers, 50 of the 74 MB, whose gradients are complete right after
+      the heads' backward) are all-reduced on a side stream as soon as the last of them has accumulated its gradient -
+      the transfer then runs under the backbone's backward;
+    * `finish()` reduces the remaining gradients on the same side stream and makes the current stream wait for it;
+    * the collectives use their OWN process group (own NCCL communicator), so they do not queue behind - or delay - the
+      latency-bound SyncBatchNorm / embedding collectives of the default group;
+    * everything is stream-ordered (fork = side.wait_stream(current), join = current.wait_stream(side)), so the whole
+      thing is capturable inside the CUDA graph of the step, where it becomes a parallel branch.
+    Without NCCL (gloo CPU tests) it degrades to one flat all-reduce in `finish()`."""
+
+    def __init__(self, model, early=()):
+        import torch.distributed as dist
+        self.model = model
+        self.nccl = dist.get_backend() == "nccl"
+        self.early = [p for p in early]
+        early_ids = {id(p) for p in self.early}
+        self.rest = [p for p in model.parameters() if id(p) not in early_ids]
+        self.armed, self.seen, self.fired = False, 0, False
+        self.group, self.stream = None, None
+        if self.nccl:
+            self.group = dist.new_group(backend="nccl")
+            self.stream = torch.cuda.Stream()
+            for p in self.early:
+                p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def arm(self):
+        """Call right before the backward pass whose gradients are to be averaged."""
+        self.armed, self.seen, self.fired = True, 0, False
+
+    def _on_grad(self, p):
+        if not self.armed:
+            return
+        self.seen += 1
+        if self.seen == len(self.early):
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                allreduce_gradients(self.model, self.early, group=self.group)
+            self.fired = True
+
+    def finish(self):
+        """After backward(): reduce what the hooks did not, then join the side stream."""
+        self.armed = False
+        if not self.nccl:
+            allreduce_gradients(self.model)
+            return
+        todo = self.rest if self.fired else self.early + self.rest
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            allreduce_gradients(self.model, todo, group=self.group)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def _grad_sync(model):
+    """The GradSync of a bare module (created on first use; every rank creates them in the same order)."""
+    gs = getattr(model, "_cb200_grad_sync", None)
+    if gs is None:
+        early = list(model.early_gradient_parameters()) if hasattr(model, "early_gradient_parameters") else []
+        gs = GradSync(model, early)
+        object.__setattr__(model, "_cb200_grad_sync", gs)
+    return gs
 
 
 def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=True, record_grad_norms=False):
@@ -85,9 +158,11 @@ def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=Tr
     d_loss, aux = train_fn["D"](P, discriminator, opt, images, gen_images)
     loss = d_loss + aux["penalty"]
     opt_D.zero_grad()
+    if sync_d:
+        _grad_sync(discriminator).arm()
     loss.backward()
     if sync_d:
-        allreduce_gradients(discriminator)
+        _grad_sync(discriminator).finish()
     if record_grad_norms:
         out["d_grad_norm"] = grad_norm(discriminator)
     opt_D.step()
@@ -99,9 +174,11 @@ def train_step(P, opt, train_fn, models, optimizers, images, step, use_warmup=Tr
     gen_images = sample_generator(generator, images.size(0))
     g_loss = train_fn["G"](P, discriminator, opt, images, gen_images)
     opt_G.zero_grad()
+    if sync_g:
+        _grad_sync(generator).arm()
     g_loss.backward()
     if sync_g:
-        allreduce_gradients(generator)
+        _grad_sync(generator).finish()
     if record_grad_norms:
         out["g_grad_norm"] = grad_norm(generator)
     opt_G.step()

@@ -10,6 +10,7 @@ import torch
 from torch.autograd import Function
 
 from . import kernels as K
+from . import precision
 
 
 # bias gradients as column sums fused into the producing GEMM epilogue (CB200_FUSED_COLSUM=0: separate kernel)
@@ -18,6 +19,28 @@ _FUSE_COLSUM = os.environ.get("CB200_FUSED_COLSUM", "1") != "0"
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- strict precision ("3xTF32", contrad_b200/precision.py): weight-side helpers.  Activations are split by
+# cb200_split_tf32 (K.split_tf32); weights are small, so their hi / lo parts are built with torch ops on the packed
+# matrices.  `groups` = how the reduction axis of the pack is organised: [rows, taps, C] with the split applied to C.
+def _hi_lo(t):
+    hi = K.round_tf32(t)
+    return hi, K.round_tf32(t - hi)
+
+
+def _split_weight_fwd(pack, taps):
+    """[rows, taps*C] -> [rows, taps*3C] = per tap [w_hi | w_hi | w_lo]: pairs with activations split as hi | lo | hi."""
+    rows = pack.shape[0]
+    hi, lo = _hi_lo(pack.reshape(rows, taps, -1))
+    return torch.cat([hi, hi, lo], dim=2).reshape(rows, -1).contiguous()
+
+
+def _split_weight_bwd(pack, taps):
+    """[rows, taps*C] -> [rows, taps*2C] = per tap [w_hi | w_lo]: pairs with a gradient duplicated as g | g."""
+    rows = pack.shape[0]
+    hi, lo = _hi_lo(pack.reshape(rows, taps, -1))
+    return torch.cat([hi, lo], dim=2).reshape(rows, -1).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -181,24 +204,56 @@ class SNPackFn(Function):
         specs = holder["specs"]
         dev = weights[0].device
         weights = [_c(w) for w in weights]
+        # strict precision applies to passes through FROZEN weights (the generator step): no weight gradient is asked for
+        strict = holder["strict"] = (precision.strict_enabled() and bool(holder.get("allow_strict"))
+                                     and not any(ctx.needs_input_grad[2:]))
+        rnd = not strict
         side = {"dgrad": {}, "sigma": {}}
         sig_all = torch.empty(len(specs), 2, device=dev, dtype=torch.float32)
         sig = [sig_all[i] for i in range(len(specs))]
         layers = [(w, s.module.weight_u, s.module.weight_v, sg) for s, w, sg in zip(specs, weights, sig)]
         for i in range(0, len(layers), 16):                      # the batched kernels take up to 16 layers per launch
             K.sn_power_iter_batched(layers[i:i + 16], training=training)
-        saved_uv = [(s.module.weight_u.clone(), s.module.weight_v.clone()) for s in specs]
+        # u / v of THIS forward (the backward of sigma needs them; the module buffers move on at the next forward):
+        # one flat snapshot filled by a single batched copy, and only when some weight will receive a gradient
+        if any(ctx.needs_input_grad[2:]):
+            srcs = [t for s in specs for t in (s.module.weight_u, s.module.weight_v)]
+            flat = torch.empty(sum(t.numel() for t in srcs), device=dev, dtype=torch.float32)
+            views, off = [], 0
+            for t in srcs:
+                views.append(flat[off:off + t.numel()])
+                off += t.numel()
+            torch._foreach_copy_(views, srcs)
+            saved_uv = [(views[2 * i], views[2 * i + 1]) for i in range(len(specs))]
+        else:
+            saved_uv = None
         head1 = [s for s in specs if s.kind == "head1"]
         outs, jobs = [], []
         wcat = wcat_t = None
+        # zero-padded packs (3 -> 32 input channels of the first layer's data-gradient pack, 1 -> 32 rows of `linear.l2`)
+        # come out of ONE zero-filled allocation
+        pad_sizes = []
+        for s, w in zip(specs, weights):
+            if s.kind == "conv_first":
+                pad_sizes.append(32 * 9 * w.shape[0])
+            elif s.kind == "head2" and w.shape[0] % 32:
+                pad_sizes.append(2 * 32 * w.shape[1])
+        pad_pool = torch.zeros(sum(pad_sizes), device=dev) if pad_sizes else None
+        pad_off = [0]
+
+        def padded(rows, cols):
+            t = pad_pool[pad_off[0]:pad_off[0] + rows * cols].view(rows, cols)
+            pad_off[0] += rows * cols
+            return t
+
         for s, w, sigma in zip(specs, weights, sig):
             side["sigma"][s.name] = sigma
             cout = w.shape[0]
             if s.kind == "conv_first":
                 fwd = torch.empty(cout, 27, device=dev)
-                dg = torch.zeros(32, 9 * cout, device=dev)
+                dg = padded(32, 9 * cout)
                 jobs.append(dict(w4=w.view(cout, 27, 1, 1), sigma=sigma, fwd=fwd, ld_fwd=27, round_out=False))
-                jobs.append(dict(w4=w, sigma=sigma, dgrad=dg, dgrad_mode=1, round_out=True))
+                jobs.append(dict(w4=w, sigma=sigma, dgrad=dg, dgrad_mode=1, round_out=rnd))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
             elif s.kind == "conv":
@@ -206,16 +261,16 @@ class SNPackFn(Function):
                 fwd = torch.empty(cout, s.ks * s.ks * cin, device=dev)
                 if s.stride == 1:
                     dg = torch.empty(cin, s.ks * s.ks * cout, device=dev)
-                    jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=1))
+                    jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=1, round_out=rnd))
                 else:
                     dg = torch.empty(4 * cin, 4 * cout, device=dev)
-                    jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=2))
+                    jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], dgrad=dg, dgrad_mode=2, round_out=rnd))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
             elif s.kind == "conv_plain":         # any kernel size / stride: forward GEMM matrix only (SNResNet18)
                 cin = w.shape[1]
                 fwd = torch.empty(cout, s.ks * s.ks * cin, device=dev)
-                jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1]))
+                jobs.append(dict(w4=w, sigma=sigma, fwd=fwd, ld_fwd=fwd.shape[1], round_out=rnd))
                 outs.append(fwd)
             elif s.kind == "head1":
                 nfeat = w.shape[1]
@@ -225,21 +280,34 @@ class SNPackFn(Function):
                     wcat_t = torch.empty(nfeat, len(head1) * cout, device=dev)
                 idx = head1.index(s)
                 jobs.append(dict(w4=w.view(cout, c_last, sh, sw), sigma=sigma, fwd=wcat[idx * cout:], ld_fwd=nfeat,
-                                 dgrad=wcat_t, dgrad_mode=3, ldt=wcat_t.shape[1], col0=idx * cout))
+                                 dgrad=wcat_t, dgrad_mode=3, ldt=wcat_t.shape[1], col0=idx * cout, round_out=rnd))
                 if idx == len(head1) - 1:
                     outs.append(wcat)
                     side["dgrad"]["wcat"] = wcat_t
             else:   # head2: [cout, hidden]; the 1-output `linear.l2` is padded to 32 rows
                 hid = w.shape[1]
                 rows = cout if cout % 32 == 0 else 32
-                fwd = torch.zeros(rows, hid, device=dev) if rows != cout else torch.empty(rows, hid, device=dev)
-                dg = torch.zeros(hid, rows, device=dev) if rows != cout else torch.empty(hid, rows, device=dev)
+                fwd = padded(rows, hid) if rows != cout else torch.empty(rows, hid, device=dev)
+                dg = padded(hid, rows) if rows != cout else torch.empty(hid, rows, device=dev)
                 jobs.append(dict(w4=w.view(cout, hid, 1, 1), sigma=sigma, fwd=fwd, ld_fwd=hid, dgrad=dg, dgrad_mode=3,
-                                 ldt=rows, col0=0))
+                                 ldt=rows, col0=0, round_out=rnd))
                 outs.append(fwd)
                 side["dgrad"][s.name] = dg
         for i in range(0, len(jobs), 16):
             K.sn_pack_batched(jobs[i:i + 16])
+        if strict:
+            # error-compensated weights: forward packs become [w_hi | w_hi | w_lo] per tap (3x the reduction length),
+            # data-gradient packs [w_hi | w_lo] (2x).  The head packs are split where they are used (HeadsFn).
+            k = 0
+            for s, w in zip(specs, weights):
+                if s.kind == "conv_first":
+                    side["dgrad"][s.name] = _split_weight_bwd(side["dgrad"][s.name], 9)
+                    k += 1
+                elif s.kind in ("conv", "conv_plain"):
+                    outs[k] = _split_weight_fwd(outs[k], s.ks * s.ks)
+                    if s.name in side["dgrad"]:
+                        side["dgrad"][s.name] = _split_weight_bwd(side["dgrad"][s.name], 9 if s.stride == 1 else 4)
+                    k += 1
         holder["side"] = side
         ctx.holder = holder
         ctx.saved_uv = saved_uv
@@ -300,10 +368,14 @@ class SNDCGANBackboneFn(Function):
     def forward(ctx, holder, x, *wb):
         specs = [s for s in holder["specs"] if s.kind in ("conv_first", "conv")]
         x = _c(x)
-        acts = [K.conv_first_fwd(x, wb[0].view(-1, 3, 3, 3), None, wb[1], slope=SNDCGANBackboneFn.SLOPE, round_out=True)]
+        strict = ctx.strict = bool(holder.get("strict"))
+        acts = [K.conv_first_fwd(x, wb[0].view(-1, 3, 3, 3), None, wb[1], slope=SNDCGANBackboneFn.SLOPE,
+                                 round_out=not strict)]
         for li, s in enumerate(specs[1:], start=1):
-            acts.append(K.conv2d_nhwc_fwd(acts[-1], wb[2 * li], wb[2 * li + 1], s.ks, s.stride,
-                                          slope=SNDCGANBackboneFn.SLOPE, round_out=True))
+            # strict: activations stay fp32 and enter the GEMM as hi | lo | hi against [w_hi | w_hi | w_lo]
+            a_in = K.split_tf32(acts[-1], 0) if strict else acts[-1]
+            acts.append(K.conv2d_nhwc_fwd(a_in, wb[2 * li], wb[2 * li + 1], s.ks, s.stride,
+                                          slope=SNDCGANBackboneFn.SLOPE, round_out=not strict))
         ctx.specs = specs
         ctx.dgrad = [holder["side"]["dgrad"][s.name] for s in specs]
         ctx.save_for_backward(x, *acts, *[wb[2 * i] for i in range(len(specs))])
@@ -335,8 +407,8 @@ class SNDCGANBackboneFn(Function):
                 db_prev = None
                 if li > 1 and need_b[li - 1] and _FUSE_COLSUM:
                     db_prev = torch.empty(a_in.shape[-1], device=a_in.device, dtype=torch.float32)
-                g = K.conv2d_nhwc_dgrad(g, ctx.dgrad[li], tuple(a_in.shape), s.ks, s.stride, act_in=a_in,
-                                        slope=SNDCGANBackboneFn.SLOPE, round_out=True, colsum=db_prev)
+                g = K.conv2d_nhwc_dgrad(K.split_tf32(g, 1) if ctx.strict else g, ctx.dgrad[li], tuple(a_in.shape), s.ks,
+                                        s.stride, act_in=a_in, slope=SNDCGANBackboneFn.SLOPE, round_out=True, colsum=db_prev)
                 if li > 1 and need_b[li - 1] and db_prev is None:
                     db_prev = K.colsum(g.view(-1, g.shape[-1]))
                 grads_b[li - 1] = db_prev
@@ -350,7 +422,7 @@ class SNDCGANBackboneFn(Function):
                 grads_b[0] = db0 if need_b[0] else None
             if need_x:
                 B, H, W, _ = g.shape
-                dpad = K.conv2d_nhwc_dgrad(g, ctx.dgrad[0], (B, H, W, 32), 3, 1)
+                dpad = K.conv2d_nhwc_dgrad(K.split_tf32(g, 1) if ctx.strict else g, ctx.dgrad[0], (B, H, W, 32), 3, 1)
                 dx = K.conv_first_dgrad_finish(dpad)
         out = [None, dx]
         for i in range(L):
@@ -414,7 +486,7 @@ class ConvPackedFn(Function):
 # ------------------------------------------------------------------------------------------------
 # generator  (models/gan/sndcgan.py:13-52)
 # ------------------------------------------------------------------------------------------------
-def _bn_forward(K_, x2d, bn_state, gamma, beta, remap_s, training, sync):
+def _bn_forward(K_, x2d, bn_state, gamma, beta, remap_s, training, sync, round_out=True):
     """Train-mode BN(+ReLU): returns (y, stats, count).  bn_state = (running_mean, running_var) or None."""
     M = x2d.shape[0]
     if training:
@@ -430,17 +502,20 @@ def _bn_forward(K_, x2d, bn_state, gamma, beta, remap_s, training, sync):
         rm, rv = bn_state
         stats = torch.stack([rm, torch.rsqrt(rv + 1e-5)])
         count = float(M)
-    return K.bn_apply_relu(x2d, stats, gamma, beta, remap_s=remap_s), stats, count
+    return K.bn_apply_relu(x2d, stats, gamma, beta, remap_s=remap_s, round_out=round_out), stats, count
 
 
 def _bn_backward(dy2d, y2d, x2d, stats, gamma, count, remap_s, sync):
     """Returns (dx, dgamma, dbeta); under SyncBN the sums are all-reduced for dx, the affine grads stay local
     (DDP averages them afterwards, as torch's SyncBatchNorm does)."""
     sums = K.bn_bwd_reduce(dy2d, y2d, x2d, stats, remap_s=remap_s)
-    dbeta, dgamma = sums[0].clone(), sums[1].clone()
     if sync:
         import torch.distributed as dist
+        local = sums.clone()
+        dbeta, dgamma = local[0], local[1]
         dist.all_reduce(sums)
+    else:
+        dbeta, dgamma = sums[0], sums[1]
     dx = K.bn_bwd_apply(dy2d, y2d, x2d, stats, gamma, sums, count, remap_s=remap_s)
     return dx, dgamma, dbeta
 
@@ -463,34 +538,60 @@ class GSNDCGANFn(Function):
         convs = [_c(w1), _c(w2), _c(w3)]
         w4 = _c(w4)
         w_lin = _c(w_lin)
-        # ---- packs (TF32-rounded): linear as-is; convT weights as OIHW of the underlying conv
-        wl = torch.empty_like(w_lin)
-        jobs = [dict(w4=w_lin.view(w_lin.shape[0], w_lin.shape[1], 1, 1), fwd=wl, ld_fwd=w_lin.shape[1])]
-        tpacks, fpacks = [], []
-        for w in convs:
-            o, i = w.shape[0], w.shape[1]
-            fp = torch.empty(o, 16 * i, device=dev)
-            tp = torch.empty(4 * i, 4 * o, device=dev)
-            jobs.append(dict(w4=w, fwd=fp, ld_fwd=16 * i, dgrad=tp, dgrad_mode=2))
-            tpacks.append(tp); fpacks.append(fp)
-        t4 = torch.zeros(32, 9 * w4.shape[0], device=dev)
-        jobs.append(dict(w4=w4, dgrad=t4, dgrad_mode=1))
-        K.sn_pack_batched(jobs)
-        zr = K.round_tf32_(z)
-        h0 = K.gemm_nt(zr, wl, b_lin)
-        a, st0, cnt0 = _bn_forward(K, h0, bn_states[0], g0, be0, sh * sw, training, sync)
+        # strict precision (contrad_b200/precision.py): the generator step, i.e. whenever a generator weight wants a gradient
+        strict = precision.strict_enabled() and any(ctx.needs_input_grad[2:])
+        if strict:
+            # forward operands: activation hi | lo | hi against weights [w_hi | w_hi | w_lo] along the reduction axis (the
+            # INPUT channels `o` of a transposed convolution = dim 0 of its weight); data-gradient packs [w_hi | w_lo]
+            hi, lo = _hi_lo(w_lin)
+            wl = torch.cat([hi, hi, lo], dim=1).contiguous()
+            jobs, tpacks, fpacks = [], [], []
+            for w in convs:
+                o, i = w.shape[0], w.shape[1]
+                hi, lo = _hi_lo(w)
+                fp = torch.empty(o, 16 * 2 * i, device=dev)
+                tp = torch.empty(4 * i, 4 * 3 * o, device=dev)
+                jobs.append(dict(w4=torch.cat([hi, hi, lo], dim=0).contiguous(), dgrad=tp, dgrad_mode=2))
+                jobs.append(dict(w4=torch.cat([hi, lo], dim=1).contiguous(), fwd=fp, ld_fwd=16 * 2 * i))
+                tpacks.append(tp); fpacks.append(fp)
+            hi, lo = _hi_lo(w4)
+            t4 = torch.zeros(32, 9 * 3 * w4.shape[0], device=dev)
+            jobs.append(dict(w4=torch.cat([hi, hi, lo], dim=0).contiguous(), dgrad=t4, dgrad_mode=1))
+            K.sn_pack_batched(jobs)
+            sp = lambda t: K.split_tf32(t, 0)
+            zr = _c(z)
+        else:
+            # ---- packs (TF32-rounded): linear as-is; convT weights as OIHW of the underlying conv
+            wl = torch.empty_like(w_lin)
+            jobs = [dict(w4=w_lin.view(w_lin.shape[0], w_lin.shape[1], 1, 1), fwd=wl, ld_fwd=w_lin.shape[1])]
+            tpacks, fpacks = [], []
+            for w in convs:
+                o, i = w.shape[0], w.shape[1]
+                fp = torch.empty(o, 16 * i, device=dev)
+                tp = torch.empty(4 * i, 4 * o, device=dev)
+                jobs.append(dict(w4=w, fwd=fp, ld_fwd=16 * i, dgrad=tp, dgrad_mode=2))
+                tpacks.append(tp); fpacks.append(fp)
+            t4 = torch.zeros(32, 9 * w4.shape[0], device=dev)
+            jobs.append(dict(w4=w4, dgrad=t4, dgrad_mode=1))
+            K.sn_pack_batched(jobs)
+            sp = lambda t: t
+            zr = K.round_tf32_(z)
+        rnd = not strict
+        h0 = K.gemm_nt(sp(zr), wl, b_lin)
+        a, st0, cnt0 = _bn_forward(K, h0, bn_states[0], g0, be0, sh * sw, training, sync, round_out=rnd)
         xs, acts, stats, counts = [h0], [a], [st0], [cnt0]
         hw = (sh, sw)
         for li, (w, b, g, be) in enumerate(((convs[0], b1, g1, be1), (convs[1], b2, g2, be2), (convs[2], b3, g3, be3))):
             o, i = w.shape[0], w.shape[1]
             x_in = acts[-1].view(N, hw[0], hw[1], o)
             hw = (hw[0] * 2, hw[1] * 2)
-            x = K.conv2d_nhwc_dgrad(x_in, tpacks[li], (N, hw[0], hw[1], i), 4, 2, bias_out=b, slope=1.0)
-            y, st, cnt = _bn_forward(K, x.view(-1, i), bn_states[li + 1], g, be, 0, training, sync)
+            x = K.conv2d_nhwc_dgrad(sp(x_in), tpacks[li], (N, hw[0], hw[1], i), 4, 2, bias_out=b, slope=1.0)
+            y, st, cnt = _bn_forward(K, x.view(-1, i), bn_states[li + 1], g, be, 0, training, sync, round_out=rnd)
             xs.append(x); acts.append(y); stats.append(st); counts.append(cnt)
         c_last = convs[2].shape[1]
-        pre = K.conv2d_nhwc_dgrad(acts[-1].view(N, hw[0], hw[1], c_last), t4, (N, hw[0], hw[1], 32), 3, 1)
+        pre = K.conv2d_nhwc_dgrad(sp(acts[-1].view(N, hw[0], hw[1], c_last)), t4, (N, hw[0], hw[1], 32), 3, 1)
         out = K.g_final_fwd(pre, b4)
+        ctx.strict = strict
         ctx.meta = (sh, sw, sync, counts, [tuple(w.shape) for w in convs])
         ctx.save_for_backward(zr, w4, g0, g1, g2, g3, out, *xs, *acts, *stats, *fpacks)
         return out
@@ -519,15 +620,23 @@ class GSNDCGANFn(Function):
             grads[base + 2], grads[base + 3] = dgam, dbet
             dx4 = dx.view(N, hw[0], hw[1], i)
             a_in = acts[li].view(N, hw[0] // 2, hw[1] // 2, o)
-            dwp = K.conv2d_nhwc_wgrad(dx4, a_in, 4, 2)                        # [o, 16*i] forward-pack layout
+            if ctx.strict:      # activation compensated over the (pixel) reduction axis: [a_hi ; a_lo] against [dx ; dx]
+                dwp = K.conv2d_nhwc_wgrad(torch.cat([dx4, dx4], dim=0),
+                                          K.split_tf32(a_in, 2).view(2 * N, hw[0] // 2, hw[1] // 2, o), 4, 2)
+            else:
+                dwp = K.conv2d_nhwc_wgrad(dx4, a_in, 4, 2)                    # [o, 16*i] forward-pack layout
             dw = torch.empty(o, i, 4, 4, device=dx.device)
             K.sn_weight_bwd(dwp, dwp.shape[1], dw, None, None, None, dw)
             grads[base], grads[base + 1] = dw, K.colsum(dx)
-            da = K.conv2d_nhwc_fwd(dx4, fpacks[li], None, 4, 2, slope=1.0, round_out=False)
+            da = K.conv2d_nhwc_fwd(K.split_tf32(dx4, 1) if ctx.strict else dx4, fpacks[li], None, 4, 2, slope=1.0,
+                                   round_out=False)
             hw = (hw[0] // 2, hw[1] // 2)
         dh0, dgam, dbet = _bn_backward(da.view(N, -1), acts[0], xs[0], stats[0], gammas[0], counts[0], sh * sw, sync)
         grads[4], grads[5] = dgam, dbet
-        grads[2] = K.gemm_tn_wgrad(dh0, zr)
+        if ctx.strict:
+            grads[2] = K.gemm_tn_wgrad(torch.cat([dh0, dh0], dim=0), K.split_tf32(zr, 2).view(2 * N, -1))
+        else:
+            grads[2] = K.gemm_tn_wgrad(dh0, zr)
         grads[3] = K.colsum(dh0)
         return tuple(grads)
 
@@ -535,6 +644,21 @@ class GSNDCGANFn(Function):
 # ------------------------------------------------------------------------------------------------
 # heads: linear (TinyDiscriminator), projection, projection2  (models/gan/base.py:14-35,92-101,123-133)
 # ------------------------------------------------------------------------------------------------
+_UNIT_ROWS = {}
+
+
+def _unit_row(width, ones, device):
+    """[1, width] row with `ones` leading ones (cached per device): `g * row` zero-extends a [B, ones] gradient."""
+    key = (width, ones, device)
+    row = _UNIT_ROWS.get(key)
+    if row is None:
+        row = torch.zeros(1, width, device=device)
+        row[:, :ones] = 1.0
+        if not (device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            _UNIT_ROWS[key] = row          # (a tensor born inside a capture belongs to the graph's pool: not cached)
+    return row
+
+
 class HeadsFn(Function):
     """features [B,F] -> (d [B,1], projection [B,P], projection2 [B,P]).
 
@@ -547,17 +671,25 @@ class HeadsFn(Function):
     def forward(ctx, holder, sg_linear, feat, wcat, bcat, w_l2, b_l2, w_p1, b_p1, w_p2, b_p2):
         feat = _c(feat)
         hid = wcat.shape[0] // 3
-        H = K.gemm_nt(feat, wcat, bcat, slope=HeadsFn.SLOPE, round_out=True)
-        b_l2p = torch.zeros(w_l2.shape[0], device=feat.device)
-        b_l2p[:b_l2.numel()] = b_l2
-        d32 = K.gemm_nt(H[:, :hid], w_l2, b_l2p)
-        p1 = K.gemm_nt(H[:, hid:2 * hid], w_p1, b_p1)
-        p2 = K.gemm_nt(H[:, 2 * hid:], w_p2, b_p2)
+        ctx.set_materialize_grads(False)          # heads the loss does not use arrive as None (G step: only `d`)
+        strict = ctx.strict = bool(holder.get("strict"))
+        if strict:
+            # error-compensated operands: A = hi | lo | hi, B = [w_hi | w_hi | w_lo] along the reduction axis
+            H = K.gemm_nt(K.split_tf32(feat, 0), _split_weight_fwd(wcat, 1), bcat, slope=HeadsFn.SLOPE, round_out=False)
+            sp = lambda t: K.split_tf32(t, 0)
+            d32 = K.gemm_nt(sp(H[:, :hid]), _split_weight_fwd(w_l2, 1), None)
+            p1 = K.gemm_nt(sp(H[:, hid:2 * hid]), _split_weight_fwd(w_p1, 1), b_p1)
+            p2 = K.gemm_nt(sp(H[:, 2 * hid:]), _split_weight_fwd(w_p2, 1), b_p2)
+        else:
+            H = K.gemm_nt(feat, wcat, bcat, slope=HeadsFn.SLOPE, round_out=True)
+            d32 = K.gemm_nt(H[:, :hid], w_l2, None)                 # 1 output row padded to 32; bias added on the slice
+            p1 = K.gemm_nt(H[:, hid:2 * hid], w_p1, b_p1)
+            p2 = K.gemm_nt(H[:, 2 * hid:], w_p2, b_p2)
         side = holder["side"]["dgrad"]
         ctx.t_cat, ctx.t_l2, ctx.t_p1, ctx.t_p2 = side["wcat"], side["linear.l2"], side["projection.2"], side["projection2.2"]
         ctx.sg_linear, ctx.hid, ctx.n_out = sg_linear, hid, b_l2.numel()
         ctx.save_for_backward(feat, H)
-        return d32[:, :ctx.n_out].contiguous(), p1, p2
+        return d32[:, :ctx.n_out] + b_l2, p1, p2
 
     @staticmethod
     def backward(ctx, dd, dp1, dp2):
@@ -570,22 +702,28 @@ class HeadsFn(Function):
         parts = ((dd, ctx.t_l2, 0, 32), (dp1, ctx.t_p1, 1, None), (dp2, ctx.t_p2, 2, None))
         used = [False, False, False]
         padded = [None, None, None]
+        present = [i for i, (g, _, _, _) in enumerate(parts) if g is not None]
+        need_full = ng[3] or ng[4]                 # first-layer weight / bias gradients read every column of dH
         for g, wt, idx, pad in parts:
             sl = slice(idx * hid, (idx + 1) * hid)
             if g is None:
-                dH[:, sl].zero_()
+                # columns of a head without gradient: zero them only where somebody reads them
+                if need_full or (present and present[0] < idx < present[-1]):
+                    dH[:, sl].zero_()
                 if db_cat is not None:
                     db_cat[sl].zero_()
                 continue
             used[idx] = True
             g = _c(g)
             if pad is not None and g.shape[1] != pad:
-                gp = torch.zeros(B, 128, device=dev)          # 128 columns: also reused by the wgrad below
-                gp[:, :g.shape[1]] = g
+                # zero-extend [B, 1] to 128 columns (also reused by the wgrad below) with ONE broadcast multiply
+                gp = g * _unit_row(128, g.shape[1], dev)
                 padded[idx] = gp
                 g = gp[:, :pad]
             else:
                 padded[idx] = g
+            if ctx.strict:            # weights compensated: A = g | g, B = [w_hi | w_lo]
+                g, wt = K.split_tf32(g, 1), _split_weight_bwd(wt, 1)
             K.gemm_nt(g, wt, None, slope=HeadsFn.SLOPE, round_out=True, out=dH[:, sl], dact=H[:, sl],
                       colsum=None if db_cat is None else db_cat[sl])
         grads = [None] * 11
@@ -606,9 +744,18 @@ class HeadsFn(Function):
         if ng[4]:
             grads[4] = db_cat if db_cat is not None else K.colsum(dH)
         if ng[2]:
-            lo = hid if ctx.sg_linear else 0
-            # only heads that actually received a gradient contribute (dH of the others is zero)
-            grads[2] = K.gemm_nt(dH[:, lo:], ctx.t_cat[:, lo:], None, slope=1.0, round_out=False)
+            # only heads that actually received a gradient contribute (dH of the others is zero): contract over the
+            # smallest contiguous range of hidden columns that covers them (G step: the `linear` head alone, K = hid)
+            live = [i for i in range(3) if used[i] and not (i == 0 and ctx.sg_linear)]
+            if live:
+                lo, hi = live[0] * hid, (live[-1] + 1) * hid
+                if ctx.strict:
+                    grads[2] = K.gemm_nt(K.split_tf32(dH[:, lo:hi], 1), _split_weight_bwd(ctx.t_cat[:, lo:hi], 1), None,
+                                         slope=1.0, round_out=False)
+                else:
+                    grads[2] = K.gemm_nt(dH[:, lo:hi], ctx.t_cat[:, lo:hi], None, slope=1.0, round_out=False)
+            else:
+                grads[2] = torch.zeros_like(feat)
         return tuple(grads)
 
 
@@ -658,21 +805,19 @@ class GanDLossFn(Function):
         d_all = _c(d_all)
         flat = d_all.view(-1)
         off = 2 * n if gen_offset is None else int(gen_offset)      # [N real | N real view 2 | N fake] by default
-        out, g_r, g_g = K.gan_d_loss(flat[:n], flat[off:off + n], kind)
-        ctx.save_for_backward(g_r, g_g)
-        ctx.n, ctx.total, ctx.off = n, d_all.shape[0], off
-        means = out[1:].clone()
+        # d L_dis / d d_all as ONE vector: the kernel fills the real and the fake rows, the rest stays zero
+        g_all = torch.zeros(d_all.shape[0], device=d_all.device)
+        out = K.gan_d_loss(flat[:n], flat[off:off + n], kind, g_real=g_all[:n], g_gen=g_all[off:off + n])[0]
+        ctx.save_for_backward(g_all)
+        ctx.shape = tuple(d_all.shape)
+        loss, means = out[0], out[1:]              # views of a fresh buffer (no copies)
         ctx.mark_non_differentiable(means)
-        return out[0].clone(), means
+        return loss, means
 
     @staticmethod
     def backward(ctx, gl, _gm):
-        g_r, g_g = ctx.saved_tensors
-        n = ctx.n
-        gd = torch.zeros(ctx.total, 1, device=g_r.device)
-        gd[:n, 0] = g_r * gl
-        gd[ctx.off:ctx.off + n, 0] = g_g * gl
-        return gd, None, None, None
+        (g_all,) = ctx.saved_tensors
+        return (g_all * gl).view(ctx.shape), None, None, None
 
 
 class GanGLossFn(Function):

@@ -51,6 +51,18 @@ def augment_simclr_fwd(x, params, order):
     return y
 
 
+def augment_simclr_params(boxes, u, order_src, rows, cfg11):
+    """[rows, B] parameter block of the fused chain from the host crop draws `boxes` [4,B], device uniforms `u` [7,B]
+    and (rows == 12) the device scalar `order_src`; cfg11: 11 python floats (see include/contrad_b200.h)."""
+    B = boxes.shape[1]
+    assert boxes.shape == (4, B) and u.shape == (7, B) and boxes.is_contiguous() and u.is_contiguous()
+    params = torch.empty(rows, B, device=u.device, dtype=torch.float32)
+    cfg = (ctypes.c_float * 11)(*[float(v) for v in cfg11])
+    _call("augment_simclr_params", 0, 0, lib().cb200_augment_simclr_params, ptr(boxes), ptr(u), ptr(order_src), ptr(params),
+          i32(B), i32(rows), cfg, stream_ptr())
+    return params
+
+
 def augment_simclr_bwd(x, dy, params, order):
     x = _f32c(x, "x")
     dy = _f32c(dy, "dy")
@@ -208,6 +220,28 @@ def _colsum_buf(colsum, n):
     return colsum
 
 
+_SPLITK_COUNTERS = {}
+_SPLITK_WS_BYTES = 20 << 20            # 296 CTAs x 128 x 128 fp32 partials
+_SPLITK_MAX_UNITS = 256
+
+
+def _offer_splitk_workspace(rows, n, classes, device):
+    """Hand the next tap-GEMM call a split-K scratch when its tile list (128 x {128,64,32} tiles) cannot fill the GPU
+    (include/contrad_b200.h: cb200_tapgemm_workspace).  Returns the scratch tensor (keep it alive across the call)."""
+    if (rows + 127) // 128 >= 64:          # long tile lists take the persistent CTA-pair kernels: nothing to split
+        return None
+    key = (device.index, _capi.stream_ptr().value)
+    counters = _SPLITK_COUNTERS.get(key)
+    if counters is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                  # never allocate persistent state inside a capture: run unsplit
+        counters = _SPLITK_COUNTERS[key] = torch.zeros(_SPLITK_MAX_UNITS, dtype=torch.int32, device=device)
+    ws = torch.empty(_SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
+    check(lib().cb200_tapgemm_workspace(ptr(ws), i64(_SPLITK_WS_BYTES), ptr(counters), i32(_SPLITK_MAX_UNITS)),
+          "tapgemm_workspace")
+    return ws
+
+
 def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None, colsum=None):
     """out[M,N] = lrelu_slope(a[M,K] @ bw[N,K]^T + bias), or (...) * lrelu'(dact) when dact is given.
     `a`, `bw`, `out`, `dact` may be row-strided 2-D views (dact must share out's row stride).
@@ -221,6 +255,7 @@ def gemm_nt(a, bw, bias=None, slope=1.0, round_out=False, out=None, dact=None, c
     assert out.shape == (M, N) and out.stride(1) == 1
     if dact is not None:
         assert dact.shape == (M, N) and dact.stride(1) == 1 and dact.stride(0) == out.stride(0)
+    ws = _offer_splitk_workspace(M, N, 1, a.device)      # noqa: F841 - kept alive until the launch is enqueued
     _call("gemm_nt_tf32", 2.0 * M * N * K, 4 * (M * K + N * K + M * N), lib().cb200_gemm_nt_tf32, ptr(a), i64(a.stride(0)), ptr(bw), i64(bw.stride(0)), ptr(bias), ptr(dact), ptr(out),
                                    i64(out.stride(0)), i32(M), i32(N), i32(K), f32(slope), i32(1 if round_out else 0),
                                    ptr(_colsum_buf(colsum, N)), stream_ptr())
@@ -235,6 +270,7 @@ def conv2d_nhwc_fwd(x, wmat, bias, ks, stride, slope=1.0, round_out=False):
     assert wmat.shape[1] == ks * ks * Cin and wmat.is_contiguous()
     Ho, Wo = H // stride, W // stride
     y = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=torch.float32)
+    ws = _offer_splitk_workspace(B * Ho * Wo, Cout, 1, x.device)      # noqa: F841
     _call("conv2d_nhwc_fwd", 2.0 * B * Ho * Wo * Cout * Cin * ks * ks, 4 * (x.numel() + wmat.numel() + y.numel()), lib().cb200_conv2d_nhwc_fwd, ptr(x), ptr(wmat), ptr(bias), ptr(y), i32(B), i32(H), i32(W), i32(Cin),
                                       i32(Cout), i32(ks), i32(stride), f32(slope), i32(1 if round_out else 0),
                                       stream_ptr())
@@ -250,6 +286,7 @@ def conv2d_nhwc_dgrad(dy, wmat_t, in_shape, ks, stride, act_in=None, bias_out=No
     B, H, W, Cin = in_shape
     Cout = dy.shape[3]
     dx = torch.empty(B, H, W, Cin, device=dy.device, dtype=torch.float32)
+    ws = _offer_splitk_workspace(B * (H // stride) * (W // stride), Cin, stride * stride, dy.device)      # noqa: F841
     _call("conv2d_nhwc_dgrad", 2.0 * B * (H // stride) * (W // stride) * Cout * Cin * ks * ks, 4 * (dy.numel() + wmat_t.numel() + dx.numel()), lib().cb200_conv2d_nhwc_dgrad, ptr(dy), ptr(wmat_t), ptr(act_in), ptr(bias_out), ptr(dx), i32(B), i32(H),
                                         i32(W), i32(Cin), i32(Cout), i32(ks), i32(stride), f32(slope),
                                         i32(1 if round_out else 0), ptr(_colsum_buf(colsum, Cin)), stream_ptr())
@@ -455,13 +492,15 @@ def contrastive_bwd(z, n, mode, temperature, lse, gscale):
     return dz
 
 
-def gan_d_loss(d_real, d_gen, kind):
-    """d_real, d_gen: 1-D views (any element stride, equal).  Returns (out3, g_real, g_gen)."""
+def gan_d_loss(d_real, d_gen, kind, g_real=None, g_gen=None):
+    """d_real, d_gen: 1-D views (any element stride, equal).  Returns (out3, g_real, g_gen); g_real / g_gen may be
+    given as contiguous [n] destinations (e.g. slices of one gradient vector)."""
     n = d_real.numel()
     assert d_real.dim() == 1 and d_gen.dim() == 1 and d_real.stride(0) == d_gen.stride(0)
     out = torch.empty(3, device=d_real.device, dtype=torch.float32)
-    g_r = torch.empty(n, device=d_real.device, dtype=torch.float32)
-    g_g = torch.empty(n, device=d_real.device, dtype=torch.float32)
+    g_r = torch.empty(n, device=d_real.device, dtype=torch.float32) if g_real is None else g_real
+    g_g = torch.empty(n, device=d_real.device, dtype=torch.float32) if g_gen is None else g_gen
+    assert g_r.numel() == n and g_g.numel() == n and g_r.is_contiguous() and g_g.is_contiguous()
     _call("gan_d_loss", 0, 0, lib().cb200_gan_d_loss, ptr(d_real), ptr(d_gen), i64(d_real.stride(0)), i32(n), i32(LOSS_KINDS[kind]),
                                  ptr(out), ptr(g_r), ptr(g_g), stream_ptr())
     return out, g_r, g_g
@@ -558,6 +597,21 @@ def round_tf32_(x):
     y = torch.empty_like(x)
     _call("round_tf32", 0, 0, lib().cb200_round_tf32, ptr(x), ptr(y), i64(x.numel()), stream_ptr())
     return y
+
+
+def split_tf32(x, mode):
+    """x [..., C] -> error-compensated TF32 operands (include/contrad_b200.h: cb200_split_tf32).
+    mode 0: [..., 3C] = hi | lo | hi;  mode 1: [..., 2C] = hi | hi;  mode 2: [2, ..., C] = hi ; lo."""
+    x = _f32c(x, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if mode == 2:
+        out = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.float32)
+    else:
+        out = torch.empty(tuple(x.shape[:-1]) + ((3 if mode == 0 else 2) * C,), device=x.device, dtype=torch.float32)
+    _call("split_tf32", 0, 4 * x.numel() * (4 if mode == 0 else 3), lib().cb200_split_tf32, ptr(x), ptr(out), i64(rows),
+          i32(C), i32(mode), stream_ptr())
+    return out
 
 
 # ------------------------------------------------------------------ fused Adam

@@ -117,14 +117,27 @@ class BaseDiscriminator(nn.Module, metaclass=ABCMeta):
                 SNLayerSpec("projection.2", self.projection[2], "head2"),
                 SNLayerSpec("projection2.2", self.projection2[2], "head2")]
 
-    def _packs(self):
+    def _packs(self, which="all"):
+        """Packed W/sigma matrices of the spectrally-normalised layers.  which = "conv" | "heads" | "all": the forward
+        packs the backbone and the heads as TWO autograd nodes, the heads' node created AFTER the backbone's forward, so
+        that in the backward pass the head layers' weight gradients are final right after the heads' backward (autograd
+        runs the later-created node first) and their all-reduce can overlap the backbone's backward (engine.GradSync)."""
         specs = self._sn_specs()
-        holder = {"specs": specs, "feat_chw": self._feat_chw}
+        if which != "all":
+            is_head = lambda s: s.kind in ("head1", "head2")
+            specs = [s for s in specs if is_head(s) == (which == "heads")]
+        holder = {"specs": specs, "feat_chw": self._feat_chw, "allow_strict": getattr(self, "_strict_capable", False)}
         packs = SNPackFn.apply(holder, self.training, *[s.module.weight_orig for s in specs])
         return holder, packs
 
+    def early_gradient_parameters(self):
+        """Parameters whose gradients are complete before the backbone's backward starts (see `_packs`)."""
+        for m in (self.linear, self.projection, self.projection2):
+            for p in m.parameters():
+                yield p
+
     def penultimate(self, inputs):
-        holder, packs = self._packs()
+        holder, packs = self._packs("conv")
         return self._to_reference_order(self._backbone(holder, inputs, packs))
 
     def forward(self, inputs, y=None, penultimate=False, projection=False, projection2=False,
@@ -132,19 +145,20 @@ class BaseDiscriminator(nn.Module, metaclass=ABCMeta):
         """models/gan/base.py:107-150."""
         if y is not None:
             raise NotImplementedError("class-conditional discriminators are not on the ContraD hot path")
-        holder, packs = self._packs()
-        n_conv = sum(1 for s in holder["specs"] if s.kind in ("conv_first", "conv", "conv_plain"))
         if finetuning:
+            # models/gan/base.py:112-118: the backbone runs in eval mode (no power iteration on its layers, ADVICE r1)
             is_train = self.training
             self.eval()
             with torch.no_grad():
-                features = self._backbone(holder, inputs, packs)
+                holder_c, packs_c = self._packs("conv")
+                features = self._backbone(holder_c, inputs, packs_c)
             features = features.detach()
             self.train(is_train)
         else:
-            features = self._backbone(holder, inputs, packs)
-
-        wcat, w_l2, w_p1, w_p2 = packs[n_conv:n_conv + 4]
+            holder_c, packs_c = self._packs("conv")
+            features = self._backbone(holder_c, inputs, packs_c)
+        holder, packs = self._packs("heads")
+        wcat, w_l2, w_p1, w_p2 = packs[0:4]
         bcat = torch.cat([self.linear.l1.bias, self.projection[0].bias, self.projection2[0].bias])
         output, project, project2 = HeadsFn.apply(holder, bool(sg_linear), features, wcat, bcat,
                                                   w_l2, self.linear.l2.bias, w_p1, self.projection[2].bias,

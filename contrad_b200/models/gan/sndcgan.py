@@ -47,8 +47,7 @@ class G_SNDCGAN(nn.Module):
                   "bn_states": [(b.running_mean, b.running_var) for b in bns],
                   "s_hb": self.s_hb, "s_wb": self.s_wb}
         if self.training:
-            for b in bns:
-                b.num_batches_tracked += 1
+            torch._foreach_add_([b.num_batches_tracked for b in bns], 1)       # one launch for the four counters
         c = self.main
         return GSNDCGANFn.apply(holder, z, self.linear.weight, self.linear.bias, bns[0].weight, bns[0].bias,
                                 c[0].weight, c[0].bias, bns[1].weight, bns[1].bias,
@@ -75,6 +74,8 @@ class G_SNDCGAN(nn.Module):
 
 
 class D_SNDCGAN(BaseDiscriminator):
+    _strict_capable = True        # the strict-precision ("3xTF32") generator step is wired through this backbone and heads
+
     def __init__(self, image_size, ndf=64, n_classes=1, normalize=False, disable_sn=False, mlp_linear=False,
                  d_hidden=128):
         if normalize or disable_sn:

@@ -51,6 +51,15 @@ int cb200_augment_simclr_fwd(const float* x, float* y, const float* params, int 
 int cb200_augment_simclr_bwd(const float* x, const float* dy, float* dx, const float* params,
                              int B, int H, int W, int order, void* stream);
 
+/* The [11|12, B] parameter block from raw draws in one launch: boxes [4,B] = the host (numpy) crop draws of
+ * RandomResizeCropLayer (augment/spatial.py:119-143), u [7,B] = device U[0,1) draws for flip, apply-jitter, contrast,
+ * hue, saturation, value, apply-gray, mapped like the reference (bernoulli(p) = u < p: spatial.py:86-88,
+ * augment/__init__.py:100-103; uniform_(lo,hi) = lo + (hi-lo) u: color_jitter.py:44-63).  cfg11 (HOST pointer) =
+ * {p_flip, p_jitter, p_gray, contrast lo,hi, hue lo,hi, saturation lo,hi, value lo,hi}; order_src = device scalar
+ * written to row 11 when rows == 12 (may be NULL). */
+int cb200_augment_simclr_params(const float* boxes, const float* u, const float* order_src, float* params,
+                                int B, int rows, const float* cfg11, void* stream);
+
 /* Same chain for images of any size (the entry points above keep one image per CTA in shared memory: H*W <= 4096;
  * these run from global memory and are what the 512x512 StyleGAN2 configs use).  means [B,3] (per-channel mean at the
  * contrast input, written by fwd, read by bwd) and gsums [B,3] (bwd scratch) are caller-allocated. */
@@ -132,6 +141,24 @@ int cb200_conv2d_nhwc_fwd(const float* x, const float* wmat, const float* bias, 
 int cb200_conv2d_nhwc_dgrad(const float* dy, const float* wmat_t, const float* act_in,
                             const float* bias_out, float* dx, int B, int H, int W, int Cin, int Cout,
                             int ks, int stride, float slope, int round_out, float* colsum, void* stream);
+
+/* Split-K for small tile lists (the deep layers and the heads at a small per-GPU batch: DDP b512 over 8 GPUs leaves 64
+ * images per rank, train_gan.py:247): the three calls above split the reduction over up to 32 CTAs per output tile when
+ * the tile list cannot fill the GPU; partials are parked in a caller-provided scratch and the last CTA to arrive at a
+ * tile adds them in split order and runs the fused epilogue (deterministic, one launch).  cb200_tapgemm_workspace hands
+ * that scratch to the NEXT of those calls made by this host thread (one-shot, thread-local): `ws` = `bytes` bytes of
+ * device scratch, `counters` = `n_counters` int32 that are zero and are left zero (one persistent buffer per device and
+ * stream).  Without it the calls run unsplit. */
+int cb200_tapgemm_workspace(void* ws, long long bytes, int* counters, int n_counters);
+
+/* Error-compensated TF32 ("3xTF32") operands for the strict-parity mode: x = hi + lo, hi = rn_tf32(x),
+ * lo = rn_tf32(x - hi).  (a_hi + a_lo)(b_hi + b_lo) ~ a_hi b_hi + a_lo b_hi + a_hi b_lo is an ordinary GEMM / convolution
+ * over a concatenated reduction axis, so the unchanged tcgen05 kernels above evaluate it on operands written as
+ * mode 0: out[rows, 3C] = [hi | lo | hi]; mode 1: out[rows, 2C] = [hi | hi]; mode 2: out[2, rows, C] = hi ; lo.
+ * Where the reference computes in fp32 (cuBLAS SGEMM for nn.Linear, models/gan/base.py:14-35) or TF32 (cuDNN default
+ * for nn.Conv2d) the product's default is single-pass TF32; this mode is what holds the generator's gradient norm to
+ * 1e-3 of the fp32 CPU reference at initialisation (tools/tf32_sensitivity.py). */
+int cb200_split_tf32(const float* x, float* out, long long rows, int C, int mode, void* stream);
 
 /* wgrad: dw_hat[Cout, ks*ks*Cin] (forward-pack layout) = sum over pixels dy (x) shifted x; both operands are
  * MN-major tcgen05 tiles, split-K over pixels with fp32 atomics (buffer is zeroed inside).

@@ -71,12 +71,16 @@ def diffaug(x, params, flags, adjoint=False):
     return dx
 
 
-def gan_d_loss(d_real, d_gen, kind):
+def gan_d_loss(d_real, d_gen, kind, g_real=None, g_gen=None):
     dr = d_real.detach().clone().requires_grad_(True)
     dg = d_gen.detach().clone().requires_grad_(True)
     with torch.enable_grad():
         loss = O.gan_d_loss(dr, dg, kind)
         g_r, g_g = torch.autograd.grad(loss, [dr, dg])
+    if g_real is not None:
+        g_r = g_real.copy_(g_r)
+    if g_gen is not None:
+        g_g = g_gen.copy_(g_g)
     return torch.stack([loss.detach(), d_real.mean(), d_gen.mean()]), g_r, g_g
 
 

@@ -42,13 +42,17 @@ def contrastive_bwd(z, n, mode, temperature, lse, gscale):
     return dz * gscale.reshape(())
 
 
-def gan_d_loss(d_real, d_gen, kind):
+def gan_d_loss(d_real, d_gen, kind, g_real=None, g_gen=None):
     assert kind == "nonsat"
     dr = d_real.detach().clone().requires_grad_(True)
     dg = d_gen.detach().clone().requires_grad_(True)
     with torch.enable_grad():
         loss = F.softplus(dg).mean() + F.softplus(-dr).mean()
         g_r, g_g = torch.autograd.grad(loss, [dr, dg])
+    if g_real is not None:
+        g_r = g_real.copy_(g_r)
+    if g_gen is not None:
+        g_g = g_gen.copy_(g_g)
     return torch.stack([loss.detach(), d_real.mean(), d_gen.mean()]), g_r, g_g
 
 

@@ -441,15 +441,20 @@ def test_emulated_conv_first_layer(B, H):
 
 
 # ------------------------------------------------------------------ the product's train step on the CPU
-def test_product_train_step_on_cpu_vs_oracle():
+@pytest.mark.parametrize("strict", [False, True])
+def test_product_train_step_on_cpu_vs_oracle(strict):
     """BASELINE configs[0] in spirit ("SNDCGAN+ContraD on CPU, one step, synthetic 32x32: plumbing, no GPU"): the PRODUCT's
     own modules, autograd Functions, engine.train_step and every SIMT kernel (emulated) run one complete D+G step incl.
     spectral norm and the optimiser on CPU tensors; only the tcgen05 entry points are torch stand-ins
     (tests/cpu_tc_standins.py).  Scalars, gradient norms and updated buffers against the fp32 oracle on identical weights,
-    latents and augmentation draws.  Heads / generator at reduced width to keep the emulation short."""
+    latents and augmentation draws.  Heads / generator at reduced width to keep the emulation short.
+
+    strict = True runs the generator step in the strict precision mode (contrad_b200/precision.py: error-compensated
+    "3xTF32" operands through the same GEMM entry points): the generator's gradient norm - which single-pass TF32 only
+    holds to ~1e-2 at initialisation (tools/tf32_sensitivity.py) - must then meet north_star's 1e-3."""
     from types import SimpleNamespace
     import tests.cpu_tc_standins as TC
-    from contrad_b200 import engine
+    from contrad_b200 import engine, precision
     from contrad_b200.functional import AugmentSimCLRFn
     from contrad_b200.models.gan.sndcgan import D_SNDCGAN, G_SNDCGAN
     from contrad_b200.training.gan import contrad
@@ -493,7 +498,7 @@ def test_product_train_step_on_cpu_vs_oracle():
         def train(self, mode=True):
             self.g.train(mode); return self
 
-    with emulated(), TC.patched():
+    with emulated(), TC.patched(), precision.strict(strict):
         D = D_SNDCGAN((32, 32, 3), mlp_linear=True, d_hidden=d_hidden)
         G = G_SNDCGAN((32, 32, 3), ngf=ngf, nz=nz)
         D.load_state_dict(sd_d); G.load_state_dict(sd_g)
@@ -511,7 +516,7 @@ def test_product_train_step_on_cpu_vs_oracle():
     assert rel(got["d_penalty"], ref["l_dis"]) < 1e-3 and rel(got["g_loss"], ref["l_gen"]) < 1e-3, (got, ref)
     assert abs(got["d_real"] - ref["d_real"]) < 1e-3 and abs(got["d_gen"] - ref["d_gen"]) < 1e-3
     assert rel(got["d_grad_norm"], ref["d_grad_norm"]) < 5e-3, (got["d_grad_norm"], ref["d_grad_norm"])
-    assert rel(got["g_grad_norm"], ref["g_grad_norm"]) < 3e-2, (got["g_grad_norm"], ref["g_grad_norm"])
+    assert rel(got["g_grad_norm"], ref["g_grad_norm"]) < (1e-3 if strict else 3e-2), (got["g_grad_norm"], ref["g_grad_norm"])
     sd_now = D.state_dict()
     for k, v in sd_d_o.items():
         if k.endswith(("weight_u", "weight_v")):                      # two power iterations (D step + G step)

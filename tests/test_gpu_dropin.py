@@ -1,0 +1,99 @@
+"""GPU: the UNMODIFIED `train_gan.py` (oracle/_ref copy of the reference) runs its own `worker()` -> `train()` for three
+steps on the B200 path after `contrad_b200.dropin.install()` - NCCL process group of one rank, DistributedDataParallel +
+SyncBatchNorm wrapping, DataLoader / DistributedSampler, torch.optim.Adam, the five `.item()` reads and `dist.barrier()`
+per step, exactly as train_gan.py:230-318 does.  Only `get_dataset` is replaced (no network for CIFAR-10): a synthetic
+TensorDataset of 32x32 images.  Checks that the steps were executed by this library's kernels and left finite, changed
+parameters; plus a `--resume`-style state_dict round trip through the reference's own checkpoint format."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_CODE = r'''
+import json, os, runpy, sys, tempfile
+repo, root = sys.argv[1], sys.argv[2]
+sys.path.insert(0, repo)
+import torch
+from contrad_b200 import _capi, dropin
+dropin.install()
+sys.path.insert(0, root)
+work = tempfile.mkdtemp(prefix="cb200_dropin_")
+os.symlink(os.path.join(root, "configs"), os.path.join(work, "configs"))
+os.chdir(work)                                     # train_gan.py uses relative paths (configs/, logs/)
+sys.argv = ["train_gan.py", "configs/gan/cifar10/c10_b512.gin", "sndcgan", "--mode=contrad", "--aug=simclr",
+            "--use_warmup", "--no_fid", "--no_gif", "--port", "29777"]
+ns = runpy.run_path(os.path.join(root, "train_gan.py"), run_name="train_gan_under_test")
+import gin
+from pathlib import Path
+
+def synthetic_dataset(dataset):                    # stands in for datasets.get_dataset (datasets.py:10-21)
+    g = torch.Generator().manual_seed(0)
+    data = torch.utils.data.TensorDataset(torch.rand(256, 3, 32, 32, generator=g), torch.zeros(256, dtype=torch.long))
+    return data, None, (32, 32, 3)
+
+stash = {}
+orig_train = ns["train"]
+def train_and_keep(P, opt, train_fn, models, optimizers, train_loader, logger):
+    stash["before"] = [p.detach().clone() for m in models for p in m.parameters()]
+    orig_train(P, opt, train_fn, models, optimizers, train_loader, logger)
+    stash["models"], stash["optimizers"], stash["logdir"] = models, optimizers, getattr(logger, "logdir", None)
+
+ns["get_dataset"] = synthetic_dataset
+ns["train"] = train_and_keep
+P = ns["parse_args"]()
+P.gin_stem = Path(P.gin_config).stem
+P = ns["setup"](P)
+P.n_gpus_per_node, P.world_size, P.distributed = 1, 1, True
+gin.bind_parameter("options.max_steps", 3)
+gin.bind_parameter("options.batch_size", 64)
+before = _capi.launch_count()
+ns["worker"](0, P)                                 # train_gan.py:230-318, unmodified
+torch.cuda.synchronize()
+launches = _capi.launch_count() - before
+G, D = stash["models"]
+params = [p for m in (G, D) for p in m.parameters()]
+moved = sum(1 for a, b in zip(stash["before"], params) if not torch.equal(a, b.detach()))
+# the reference's checkpoint format (train_gan.py:208-222) and its --resume path (train_gan.py:256-262)
+sd_g, sd_d = G.module.state_dict(), D.module.state_dict()
+torch.save(sd_g, os.path.join(work, "gen.pt")); torch.save(sd_d, os.path.join(work, "dis.pt"))
+G2, D2 = ns["get_architecture"]("sndcgan", (32, 32, 3), P=P)
+G2.load_state_dict(torch.load(os.path.join(work, "gen.pt"))); D2.load_state_dict(torch.load(os.path.join(work, "dis.pt")))
+same = all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(G2.state_dict().values(), sd_g.values()))
+same = same and all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(D2.state_dict().values(), sd_d.values()))
+print("RESULT " + json.dumps({
+    "launches": int(launches), "finite": bool(all(torch.isfinite(p).all() for p in params)), "moved": moved,
+    "n_tensors": len(params), "D_type": type(D).__name__, "D_inner": type(D.module).__module__,
+    "G_inner": type(G.module).__module__, "resume_roundtrip": bool(same),
+    "D_keys": sorted(sd_d.keys())[:4], "logdir": stash["logdir"]}))
+torch.distributed.destroy_process_group()
+'''
+
+
+def _reference_root():
+    for cand in (os.path.join(REPO, "oracle", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(cand, "train_gan.py")):
+            return cand
+    return None
+
+
+@pytest.mark.timeout(600)
+def test_unmodified_worker_runs_three_steps_on_the_b200_path():
+    root = _reference_root()
+    if root is None:
+        pytest.skip("reference sources not available (oracle/_ref is made by oracle/make_ref.py in the build container)")
+    r = subprocess.run([sys.executable, "-c", _CODE, REPO, root], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=560)
+    text = r.stdout.decode()
+    assert r.returncode == 0, text[-4000:]
+    res = json.loads([ln for ln in text.splitlines() if ln.startswith("RESULT ")][-1][7:])
+    print(res)
+    assert res["D_type"] == "DistributedDataParallel"
+    assert res["D_inner"].startswith("contrad_b200.") and res["G_inner"].startswith("contrad_b200.")
+    assert res["launches"] > 300, res            # three D+G steps through libcontrad_b200.so (~150 launches per step)
+    assert res["finite"] and res["moved"] >= res["n_tensors"] - 2, res
+    assert res["resume_roundtrip"]

@@ -223,7 +223,9 @@ def test_augment_full_size_properties(K):
 
 # ---------------------------------------------------------------------------------- tensor-core GEMM
 @pytest.mark.parametrize("M,N,K_", [(128, 128, 32), (256, 128, 64), (384, 64, 96), (1000, 32, 512),
-                                    (1536, 1536, 8192), (77, 128, 128), (40000, 256, 64), (37900, 128, 96)])
+                                    (1536, 1536, 8192), (77, 128, 128), (40000, 256, 64), (37900, 128, 96),
+                                    # split-K shapes (heads at 64 images per rank: D step 192 rows, G step 64 rows)
+                                    (192, 1536, 8192), (64, 1536, 8192), (192, 512, 1536), (64, 32, 512), (192, 8192, 1024)])
 def test_gemm_nt_tf32(K, M, N, K_):
     torch.manual_seed(M + N + K_)
     a = K.round_tf32(torch.randn(M, K_, device="cuda"))
@@ -236,6 +238,23 @@ def test_gemm_nt_tf32(K, M, N, K_):
     assert err < 5e-5, err
     want = out.double().sum(0)
     assert ((colsum.double() - want).abs().max() / out.double().abs().sum(0).max()) < 1e-6
+
+
+def test_split_k_is_deterministic_and_rearms(K):
+    """The split-K path (tile list < GPU): bit-identical results call after call (partials are added in split order by
+    the last CTA to arrive; the per-tile arrival counters are left at zero)."""
+    torch.manual_seed(9)
+    a = K.round_tf32(torch.randn(192, 8192, device="cuda"))
+    b = K.round_tf32(torch.randn(1536, 8192, device="cuda") * 0.05)
+    outs = [K.gemm_nt(a, b, None, slope=0.1, round_out=True).clone() for _ in range(4)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = K.round_tf32(F.leaky_relu(a.double() @ b.double().t(), 0.1).float())
+    assert ((outs[0] - ref).abs().max() / ref.abs().max()) < 1e-3          # TF32 rounding of the output included
+    x = K.round_tf32(torch.randn(64, 4, 4, 512, device="cuda"))
+    w = K.round_tf32(torch.randn(512, 512, 3, 3, device="cuda") * 0.05)
+    ys = [K.conv2d_nhwc_fwd(x, K.pack_fwd_weight(w), None, 3, 1).clone() for _ in range(3)]
+    assert torch.equal(ys[0], ys[1]) and torch.equal(ys[0], ys[2])
 
 
 def test_gemm_nt_strided_views(K):
@@ -257,6 +276,9 @@ CONV_CASES = [
     (301, 16, 128, 128, 3, 1), (600, 16, 128, 256, 4, 2), (1201, 8, 256, 256, 3, 1), (1200, 32, 64, 128, 4, 2),
     # thin data gradients (N = Cin = 32: the 3 image channels padded to 32) on the persistent BN = 32 variant
     (700, 16, 32, 64, 3, 1), (300, 32, 32, 64, 4, 2),
+    # split-K shapes: the deep layers at 64 images per rank (D step B = 192, G step B = 64)
+    (192, 4, 512, 512, 3, 1), (192, 8, 256, 512, 4, 2), (64, 8, 256, 256, 3, 1), (64, 16, 128, 256, 4, 2),
+    (64, 4, 512, 512, 3, 1), (64, 8, 256, 512, 4, 2),
 ]
 
 

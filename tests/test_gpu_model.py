@@ -211,9 +211,25 @@ def test_generator_forward_backward_vs_oracle(env, n):
     assert _rel(gn, gn_o) < 5e-3, (gn, gn_o)
 
 
-def test_config1_two_steps_vs_reference_scalars(env, golden_dir):
+@pytest.mark.parametrize("strict", [False, True])
+def test_config1_two_steps_vs_reference_scalars(env, golden_dir, strict):
     """BASELINE config 1 shape (b64, c10_b512.gin hyper-parameters): two complete train steps (Adam incl.) on
-    the B200 path reproduce the UNMODIFIED reference's scalars (tests/golden/config1_scalars.json) to 1e-3."""
+    the B200 path reproduce the UNMODIFIED reference's scalars (tests/golden/config1_scalars.json) to 1e-3.
+
+    strict = True: the strict precision mode (contrad_b200/precision.py, error-compensated "3xTF32" operands in the
+    generator step) - EVERY scalar incl. the generator's gradient norm within north_star's 1e-3.  strict = False (the
+    default single-pass TF32): losses and the discriminator's gradient norm within 1e-3; the generator's gradient norm at
+    initialisation is a small residual that any single TF32 rounding moves by 1e-3 .. 1e-2 (tools/tf32_sensitivity.py,
+    profiles/tf32_sensitivity_r2.json) - bounded at 2e-2 here and stated as such in DESIGN.md."""
+    from contrad_b200 import precision
+    precision.set_strict(strict)
+    try:
+        _config1_two_steps(env, golden_dir, strict)
+    finally:
+        precision.set_strict(False)
+
+
+def _config1_two_steps(env, golden_dir, strict):
     with open(os.path.join(golden_dir, "config1_scalars.json")) as f:
         fx = json.load(f)
     n = fx["batch"]
@@ -258,9 +274,9 @@ def test_config1_two_steps_vs_reference_scalars(env, golden_dir):
         for key, mine in (("l_con", "d_loss"), ("l_dis", "d_penalty"), ("l_gen", "g_loss"),
                           ("d_grad_norm", "d_grad_norm")):
             assert _rel(float(got[mine]), ref[key]) < 1e-3, (ref["step"], key, float(got[mine]), ref[key])
-        # G grad-norm at init: a near-cancelling sum through the TF32 dgrad chain (see the test above); observed
-        # 1e-3 .. 1.1e-2 run to run (fp32 atomics in split-K wgrad reorder the sums): 2e-2
-        assert _rel(float(got["g_grad_norm"]), ref["g_grad_norm"]) < 2e-2, (ref["step"], float(got["g_grad_norm"]))
+        g_tol = 1e-3 if strict else 2e-2
+        assert _rel(float(got["g_grad_norm"]), ref["g_grad_norm"]) < g_tol, (ref["step"], strict, float(got["g_grad_norm"]),
+                                                                            ref["g_grad_norm"])
 
 
 def test_full_batch_step_runs_and_is_finite(env):

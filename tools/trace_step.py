@@ -68,7 +68,14 @@ def summarise(trace_path, steps):
     wall = t1 - t0
     big_gaps = sorted(gaps, reverse=True)[:max(steps - 1, 0)]      # the gaps between replays (host side), excluded below
     inner_gap = sum(gaps) - sum(big_gaps)
+    # per-launch list of the LAST replay (name, grid, duration): the launch list of one step
+    last_start = evs[-1]["ts"]
+    big = sorted(((evs[i + 1]["ts"] - (evs[i]["ts"] + evs[i]["dur"]), i) for i in range(len(evs) - 1)), reverse=True)[:max(steps - 1, 0)]
+    cut = max([i for _, i in big], default=-1) + 1
+    launches = [{"name": short(e["name"]), "us": e["dur"], "grid": e.get("args", {}).get("grid"),
+                 "stream": e.get("args", {}).get("stream"), "t_us": e["ts"] - evs[cut]["ts"]} for e in evs[cut:]]
     out = {
+        "launches_last_step": launches,
         "steps": steps, "wall_us_per_step": (wall - sum(big_gaps)) / steps, "busy_us_per_step": busy / steps,
         "idle_inside_step_us": inner_gap / steps, "n_device_events_per_step": len(evs) / steps,
         "nccl_us_per_step": sum(v["us"] for v in nccl.values()) / steps,
@@ -149,7 +156,7 @@ def main():
         with open(args.out + ".md", "w") as f:
             f.write(to_md(res, "Kernel timeline of one train step, N=%d GPUs, %d images per rank (%s)"
                           % (world, n_local, "eager" if args.no_graph else "CUDA-graph replay")))
-        print(json.dumps({k: v for k, v in res.items() if k != "kernels"}))
+        print(json.dumps({k: v for k, v in res.items() if k not in ("kernels", "launches_last_step")}))
     if graphed is not None:
         graphed.release()
     torch.cuda.synchronize()
