@@ -381,8 +381,9 @@ def run_native(args):
         if not args.no_graph:
             graphed.release()                      # free the graph's pool (and its NCCL kernels) before DDP starts
         try:
-            eager = eager_gpu_baseline_leg(world, W.local_rank if world > 1 else 0, dev)
-            _log("eager reference leg done: %.3f ms/step" % eager["ms_per_step"])
+            eager = (eager_gpu_baseline_leg(world, W.local_rank, dev, steps=30, warmup=8) if world > 1
+                     else eager_gpu_baseline_leg(world, 0, dev))
+            _log("eager reference leg done: %s" % (eager.get("ms_per_step", eager.get("error")),))
         except Exception as e:                                # noqa: BLE001 - report, do not lose the line
             eager = {"error": "%s: %s" % (type(e).__name__, e)}
             _log("eager reference leg failed: %s" % eager["error"])
@@ -437,20 +438,59 @@ def run_native(args):
     return 0
 
 
-def eager_gpu_baseline_leg(world, local_rank, dev, steps=50, warmup=10):
+def eager_gpu_baseline_leg(world, local_rank, dev, steps=50, warmup=10, budget_s=240):
     """`oracle/_ref/train_gan.py`'s own `train()` loop on unmodified reference modules, `.cuda()`, PyTorch default
-    flags, DDP + SyncBatchNorm wrapping exactly as `worker()` does (train_gan.py:268-271,311-313), 50 steps after 10
-    warm-up steps, per-rank batch 512 // N.  Runs on every rank; the step time is the max over ranks."""
-    from oracle import ref_runner
-    r = ref_runner.run_gpu(steps, warmup, global_batch=GLOBAL_BATCH, local_rank=local_rank)
-    ms = torch.tensor([r["ms_per_step"]], device=dev, dtype=torch.float64)
+    flags, DDP + SyncBatchNorm wrapping exactly as `worker()` does (train_gan.py:268-271,311-313), `steps` steps after
+    `warmup` warm-up steps, per-rank batch 512 // N.  Every rank runs it in a CHILD process with its own NCCL
+    rendezvous (MASTER_PORT + 23): the reference leg can neither inherit communicator / graph state from the native arm
+    nor take the native line down - a child that exceeds `budget_s` is killed and the leg reports the failure.  The step
+    time is the max over ranks."""
+    env = dict(os.environ)
+    env.setdefault("MASTER_ADDR", "127.0.0.1")
+    env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 23)
+    env.setdefault("RANK", "0"); env.setdefault("WORLD_SIZE", "1"); env.setdefault("LOCAL_RANK", str(local_rank))
+    for k in [k for k in env if k.startswith("TORCHELASTIC_")]:      # rank 0 of the children hosts its own TCP store
+        env.pop(k)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "eager-child", "--steps", str(steps), "--warmup", str(warmup)]
+    ms, info, err = float("inf"), {}, None
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=budget_s)
+        lines = [ln for ln in r.stdout.decode().splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and lines:
+            info = json.loads(lines[-1])
+            ms = float(info["ms_per_step"])
+        else:
+            err = "child exit %d: %s" % (r.returncode, r.stderr.decode()[-400:].replace("\n", " | "))
+    except subprocess.TimeoutExpired:
+        err = "reference leg exceeded %d s and was killed" % budget_s
+    t = torch.tensor([ms if ms != float("inf") else 1e30], device=dev, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    if ms >= 1e29:
+        return {"error": err or "the reference leg failed on another rank", "n_gpus": world, "kind": "reference"}
     return {"value": GLOBAL_BATCH / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "n_gpus": world,
-            "steps": steps, "warmup": warmup, "per_gpu_batch": r["per_gpu_batch"], "flags": r["flags"],
-            "kind": "reference", "what": r["what"]}
+            "steps": steps, "warmup": warmup, "per_gpu_batch": info.get("per_gpu_batch"), "flags": info.get("flags"),
+            "kind": "reference", "what": info.get("what")}
+
+
+def run_eager_child(args):
+    """Child of eager_gpu_baseline_leg: one rank of the unmodified reference's training loop on its GPU."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from oracle import ref_runner
+    r = ref_runner.run_gpu(args.steps, args.warmup, global_batch=GLOBAL_BATCH, local_rank=local_rank)
+    print(json.dumps(r), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 
 def side_workloads():
@@ -568,7 +608,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "eager-child"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-workloads", action="store_true", help="skip the StyleGAN2 config-4 side measurement")
     ap.add_argument("--no-u8-input", dest="u8_input", action="store_false",
@@ -588,6 +628,8 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager-child":
+        return run_eager_child(args)
     args.warmup = max(args.warmup, 3)
     return run_native(args)
 

@@ -403,24 +403,76 @@ __device__ __forceinline__ void cols_process(const float* xs, const float4* xtap
     }
 }
 
+// The two halves of block_sum3_256 around ONE CTA barrier that the caller places (and shares with its other hand-offs):
+// `partial` leaves 3 x 8 warp sums in `scratch` (24 floats), `total` folds them after the barrier.
+__device__ __forceinline__ void block_sum3_partial(const float (&v)[3], float* scratch) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool hi = (lane & 16) != 0;
+    const float r0 = __shfl_xor_sync(full, hi ? v[0] : v[2], 16);
+    const float r1 = __shfl_xor_sync(full, hi ? v[1] : 0.f, 16);
+    float a = (hi ? v[2] : v[0]) + r0;
+    const float b = (hi ? 0.f : v[1]) + r1;
+    const bool q = (lane & 8) != 0;
+    a = (q ? b : a) + __shfl_xor_sync(full, q ? a : b, 8);
+    a += __shfl_xor_sync(full, a, 4);
+    a += __shfl_xor_sync(full, a, 2);
+    a += __shfl_xor_sync(full, a, 1);
+    if ((lane & 7) == 0 && lane < 24) scratch[(lane >> 3) * 8 + warp] = a;      // [value][warp]
+}
+
+__device__ __forceinline__ void block_sum3_total(float (&v)[3], const float* scratch) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float t = (lane < 24) ? scratch[lane] : 0.f;
+    t += __shfl_xor_sync(full, t, 4);
+    t += __shfl_xor_sync(full, t, 2);
+    t += __shfl_xor_sync(full, t, 1);
+    v[0] = __shfl_sync(full, t, 0);
+    v[1] = __shfl_sync(full, t, 8);
+    v[2] = __shfl_sync(full, t, 16);
+}
+
 // Forward, square S x S images with S a multiple of 32 (the CIFAR / 64x64 cases): COLUMN mapping.  Lane = output
 // column, each thread walks NPX = S*S/256 consecutive output rows.  The bilinear gather then reads, per warp
 // instruction, 32 (almost always distinct) columns of ONE source row: no shared-memory bank conflicts, where the
 // quad mapping above put four source rows - all hitting the same banks, row stride S floats = 0 mod 32 - into
 // each warp instruction (4-way conflicts on every gather; profiles/prof_r1_augment.md: l1tex 81 %, mio_throttle).
 // Column taps are loaded once per thread, row taps are one broadcast LDS.128 per row; stores are 128 B per warp.
-template <int S>
-__global__ void __launch_bounds__(kMaxThreads)
+//
+// Software pipeline with ONE CTA barrier per image (round 1 had four: tap tables, image arrival, the contrast mean's
+// block reduction, end of iteration - ncu: 1.3 barrier stalls per issued instruction at 50 % warp occupancy):
+//   * tap tables, reduction scratch and image buffers are double-buffered by iteration parity;
+//   * while image `it` is gathered, the tap tables of image `it + 1` are computed (the five parameters they need were
+//     requested at the top of the iteration) and the warp partials of the contrast sums are written;
+//   * the single __syncthreads then publishes the next tap tables and the partial sums AND certifies that nobody reads
+//     the current image buffer any more, so thread 0 refills it with image `it + 2` right behind the barrier (two bulk
+//     copies stay in flight);
+//   * the per-image parameters of the current image are requested at the top and first needed after the gather.
+template <int S, int OCC>          // OCC = resident CTAs per SM the register allocation is held to (32x32: 6 -> 40 registers)
+__global__ void __launch_bounds__(kMaxThreads, OCC)
 augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
                                int B, int order) {
     extern __shared__ __align__(128) float smem[];
     constexpr int HW = S * S, NPX = HW / kMaxThreads;
-    float* red = smem + 6 * HW;                                   // [3*32]
-    float4* xtap = reinterpret_cast<float4*>(red + 96);           // [S] {i0, i1 (int bits), w0, w1}, flip folded in
-    float4* ytap = xtap + S;                                      // [S] {i0*S, i1*S (int bits), w0, w1}
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ytap + S);
+    float* red = smem + 6 * HW;                                   // [2][32]
+    float4* xtap = reinterpret_cast<float4*>(red + 96);           // [2][S] {i0, i1 (int bits), w0, w1}, flip folded in
+    float4* ytap = xtap + 2 * S;                                  // [2][S] {i0*S, i1*S (int bits), w0, w1}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ytap + 2 * S);
     constexpr uint32_t img_bytes = (uint32_t)(3 * HW * sizeof(float));
     const int j = threadIdx.x % S, i_first = (threadIdx.x / S) * NPX;
+    const int G = gridDim.x;
+
+    auto write_taps = [&](int par, float sx, float sy, float bx, float by, float flip) {
+        const int e = threadIdx.x;
+        if (e < S) {
+            const Tap a = axis_tap((flip < 0.f) ? (S - 1 - e) : e, S, sx, bx);
+            xtap[par * S + e] = make_float4(__int_as_float(a.i0), __int_as_float(a.i1), a.w0, a.w1);
+        } else if (e < 2 * S) {
+            const Tap a = axis_tap(e - S, S, sy, by);
+            ytap[par * S + e - S] = make_float4(__int_as_float(a.i0 * S), __int_as_float(a.i1 * S), a.w0, a.w1);
+        }
+    };
 
     if (threadIdx.x == 0) {
         bar_init(&bars[0], 1);
@@ -429,36 +481,96 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
     }
     __syncthreads();
     int b = blockIdx.x;
-    if (threadIdx.x == 0 && b < B) {
+    if (b >= B) return;
+    if (threadIdx.x == 0) {
         bar_expect_tx(&bars[0], img_bytes);
         bulk_load(smem, x + (size_t)b * 3 * HW, img_bytes, &bars[0]);
-    }
-    for (int it = 0; b < B; b += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int nb = b + gridDim.x;
-        if (threadIdx.x == 0 && nb < B) {
-            bar_expect_tx(&bars[buf ^ 1], img_bytes);
-            bulk_load(smem + (buf ^ 1) * 3 * HW, x + (size_t)nb * 3 * HW, img_bytes, &bars[buf ^ 1]);
+        if (b + G < B) {
+            bar_expect_tx(&bars[1], img_bytes);
+            bulk_load(smem + 3 * HW, x + (size_t)(b + G) * 3 * HW, img_bytes, &bars[1]);
         }
-        const SampleParams sp = load_params(params, B, b);
+    }
+    if (threadIdx.x < 2 * S)
+        write_taps(0, __ldg(params + 0 * B + b), __ldg(params + 1 * B + b), __ldg(params + 2 * B + b),
+                   __ldg(params + 3 * B + b), __ldg(params + 4 * B + b));
+    __syncthreads();
+
+    for (int it = 0; b < B; b += G, ++it) {
+        const int par = it & 1;
+        const int nb = b + G;
+        // requests first: this image's colour parameters, and (tap writers) the crop parameters of the next image
+        const float cj_on = __ldg(params + 5 * B + b), fc = __ldg(params + 6 * B + b), fh = __ldg(params + 7 * B + b);
+        const float fs = __ldg(params + 8 * B + b), fv = __ldg(params + 9 * B + b), gray_on = __ldg(params + 10 * B + b);
         const int ord = resolve_order(params, B, b, order);
-        const float hshift = sp.fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
-        if (threadIdx.x < 2 * S) {
-            const int e = threadIdx.x;
-            if (e < S) {
-                const Tap a = axis_tap((sp.flip < 0.f) ? (S - 1 - e) : e, S, sp.sx, sp.bx);
-                xtap[e] = make_float4(__int_as_float(a.i0), __int_as_float(a.i1), a.w0, a.w1);
-            } else {
-                const Tap a = axis_tap(e - S, S, sp.sy, sp.by);
-                ytap[e - S] = make_float4(__int_as_float(a.i0 * S), __int_as_float(a.i1 * S), a.w0, a.w1);
+        float nsx = 1.f, nsy = 1.f, nbx = 0.f, nby = 0.f, nflip = 1.f;
+        const bool next_taps = nb < B && threadIdx.x < 2 * S;
+        if (next_taps) {
+            nsx = __ldg(params + 0 * B + nb); nsy = __ldg(params + 1 * B + nb); nbx = __ldg(params + 2 * B + nb);
+            nby = __ldg(params + 3 * B + nb); nflip = __ldg(params + 4 * B + nb);
+        }
+        bar_wait(&bars[par], (uint32_t)(it >> 1) & 1u);
+        const float* xs = smem + par * 3 * HW;
+
+        // ---- gather (crop + flip) into registers
+        float v[NPX][3];
+        {
+            const float4 tx = xtap[par * S + j];
+            const int x0 = __float_as_int(tx.x), x1 = __float_as_int(tx.y);
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float4 ty = ytap[par * S + i_first + m];
+                const float* r0 = xs + __float_as_int(ty.x);
+                const float* r1 = xs + __float_as_int(ty.y);
+                const float w00 = tx.z * ty.z, w01 = tx.w * ty.z, w10 = tx.z * ty.w, w11 = tx.w * ty.w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v[m][c] = r0[c * HW + x0] * w00 + r0[c * HW + x1] * w01 + r1[c * HW + x0] * w10 +
+                              r1[c * HW + x1] * w11;
             }
         }
-        bar_wait(&bars[buf], (uint32_t)(it >> 1) & 1u);
-        __syncthreads();
-        const float* xs = smem + buf * 3 * HW;
-
-        cols_process<S>(xs, xtap, ytap, red, sp, ord, hshift, y + (size_t)b * 3 * HW + i_first * S + j, j, i_first);
-        __syncthreads();      // tap tables / reduction scratch / this image buffer are reused by the next iteration
+        const float hshift = fh * (255.f / 360.f);     // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
+        float sums[3] = {0.f, 0.f, 0.f};
+        if (cj_on != 0.f) {          // uniform across the CTA
+            if (ord == 1) {
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, fs, fv);
+            }
+#pragma unroll
+            for (int m = 0; m < NPX; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sums[c] += v[m][c];
+            block_sum3_partial(sums, red + par * 32);
+        }
+        if (next_taps) write_taps(par ^ 1, nsx, nsy, nbx, nby, nflip);
+        __syncthreads();          // the only CTA barrier of the iteration (see the header comment)
+        if (threadIdx.x == 0 && nb + G < B) {
+            bar_expect_tx(&bars[par], img_bytes);
+            bulk_load(smem + par * 3 * HW, x + (size_t)(nb + G) * 3 * HW, img_bytes, &bars[par]);
+        }
+        if (cj_on != 0.f) {
+            block_sum3_total(sums, red + par * 32);
+            constexpr float inv = 1.f / (float)HW;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float mean = sums[c] * inv;
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) v[m][c] = clamp01((v[m][c] - mean) * fc + mean);
+            }
+            if (ord == 0) {
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) hsv_jitter(v[m][0], v[m][1], v[m][2], hshift, fs, fv);
+            }
+        }
+        float* yb = y + (size_t)b * 3 * HW + i_first * S + j;
+#pragma unroll
+        for (int m = 0; m < NPX; ++m) {
+            if (gray_on != 0.f) {
+                const float l = 0.299f * v[m][0] + 0.587f * v[m][1] + 0.114f * v[m][2];
+                v[m][0] = l; v[m][1] = l; v[m][2] = l;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, v[m][c]);
+        }
     }
 }
 
@@ -950,7 +1062,7 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
     LaunchShape ls;
     CB200_CHECK_ARG(pick_shape(H, W, &ls),
                     "augment_fwd: images larger than 64x64 (%dx%d) need the tiled path (not built yet)", H, W);
-    size_t smem = (size_t)(6 * H * W + 96 + 4 * W + 4 * H) * sizeof(float) + 2 * sizeof(uint64_t);
+    size_t smem = (size_t)(6 * H * W + 96 + 8 * W + 8 * H) * sizeof(float) + 2 * sizeof(uint64_t);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static int sm_count = 0;
     if (!sm_count) {
@@ -970,12 +1082,20 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
     } while (0)
     static const bool cols_ok = []() { const char* e = getenv("CB200_AUGMENT_COLS"); return !(e && e[0] == '0'); }();
     if (cols_ok && H == W && (H == 32 || H == 64)) {
-        if (H == 32) {
-            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            augment_simclr_fwd_cols_kernel<32><<<grid, kMaxThreads, smem, st>>>(x, y, params, B, order);
+        // 32x32: ncu showed the kernel occupancy-limited at 5 CTAs / SM by registers; the default build holds it to 40
+        // registers (6 CTAs / SM, 4 bytes of spill); CB200_AUGMENT_OCC=5 selects the unconstrained build (A/B runs)
+        static const int occ = []() { const char* e = getenv("CB200_AUGMENT_OCC"); return e ? atoi(e) : 6; }();
+        if (H == 32 && occ >= 6) {
+            const int g6 = B < sm_count * 6 ? B : sm_count * 6;
+            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_cols_kernel<32, 6><<<g6, kMaxThreads, smem, st>>>(x, y, params, B, order);
+        } else if (H == 32) {
+            const int g5 = B < sm_count * 5 ? B : sm_count * 5;
+            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_cols_kernel<32, 1><<<g5, kMaxThreads, smem, st>>>(x, y, params, B, order);
         } else {
-            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            augment_simclr_fwd_cols_kernel<64><<<grid, kMaxThreads, smem, st>>>(x, y, params, B, order);
+            cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            augment_simclr_fwd_cols_kernel<64, 1><<<grid, kMaxThreads, smem, st>>>(x, y, params, B, order);
         }
     } else if (H == 32 && W == 32) LAUNCH_FWD(1, 32);
     else if (ls.qpt == 1) LAUNCH_FWD(1, 0); else if (ls.qpt == 2) LAUNCH_FWD(2, 0); else LAUNCH_FWD(4, 0);

@@ -389,6 +389,70 @@ lrelu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ act, 
     out[i] = g;
 }
 
+
+// ------------------------------------------------------------------------------------------ tensor-core similarity path
+// north_star's formulation of the two contrastive losses: the pairwise-cosine similarity matrix is ONE tcgen05 GEMM
+// (cb200_gemm_nt_tf32 on error-compensated operands, see contrad_b200/functional.py ContrastiveTCFn), the
+// temperature-softmax / cross-entropy below are warp-shuffle row reductions over that matrix.
+//   S [Ra, lds]  dot products <z_i, z_j> of the loss rows i (global row index row0 + i) against all R rows (columns >= R
+//                are padding), mode 0: NT-Xent (Ra = R = 2N), mode 1: supcon-fake (R = 3N, loss rows 2N .. 3N-1)
+// fwd: lse[i] = logsumexp_j!=i(S_ij / tau);  rowloss[i] = -(c) * sum_j w_ij (S_ij / tau - lse_i)  with the reference's
+//      weights (criterion.py:35-45: positive j = (i + N) mod 2N, c = 1/2N; contrad.py:13-32: the other fakes, 1/(N-1), c = 1/N)
+// bwd: G_ij = gscale * c * (softmax_ij - w_ij) / tau, G_ii = 0   (d loss / d S_ij; padding columns zero)
+__global__ void __launch_bounds__(256)
+sim_rows_fwd_kernel(const float* __restrict__ S, long long lds, int Ra, int R, int N, int mode, int row0, float inv_tau,
+                    float* __restrict__ lse, float* __restrict__ rowloss) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= Ra) return;
+    const int gi = row0 + r;
+    const float* s = S + (long long)r * lds;
+    float m = -3.0e38f;
+    for (int j = lane; j < R; j += 32) if (j != gi) m = fmaxf(m, s[j] * inv_tau);
+    m = warp_max(m);
+    float se = 0.f, pos = 0.f;
+    const int pj = (gi + N) % (2 * N);
+    for (int j = lane; j < R; j += 32) {
+        if (j == gi) continue;
+        const float l = s[j] * inv_tau;
+        se += __expf(l - m);
+        if (mode == 0) { if (j == pj) pos += l; }
+        else if (j >= 2 * N) pos += l;
+    }
+    se = warp_sum(se);
+    pos = warp_sum(pos);
+    if (lane == 0) {
+        const float L = m + logf(se);
+        lse[r] = L;
+        rowloss[r] = (mode == 0) ? -(pos - L) / (float)(2 * N) : -(pos / (float)(N - 1) - L) / (float)N;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sim_rows_bwd_kernel(const float* __restrict__ S, long long lds, int Ra, int R, int N, int mode, int row0, float inv_tau,
+                    const float* __restrict__ lse, const float* __restrict__ gscale, float* __restrict__ G, long long ldg,
+                    int cols) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= Ra) return;
+    const int gi = row0 + r;
+    const float* s = S + (long long)r * lds;
+    float* g = G + (long long)r * ldg;
+    const float L = lse[r];
+    const float c = gscale[0] * inv_tau / (float)(mode == 0 ? 2 * N : N);
+    const int pj = (gi + N) % (2 * N);
+    const float wpos = (mode == 0) ? 1.f : 1.f / (float)(N - 1);
+    for (int j = lane; j < cols; j += 32) {
+        float v = 0.f;
+        if (j < R && j != gi) {
+            const float p = __expf(s[j] * inv_tau - L);
+            const bool is_pos = (mode == 0) ? (j == pj) : (j >= 2 * N);
+            v = c * (p - (is_pos ? wpos : 0.f));
+        }
+        g[j] = v;
+    }
+}
+
 }  // namespace
 
 extern "C" int cb200_lrelu_bwd(const float* dy, const float* act, float* out, long long n, float slope, int round_out,
@@ -510,5 +574,29 @@ extern "C" int cb200_colsum(const float* x, long long ld, int M, int N, float* o
     else colsum_kernel<1><<<grid, 256, 0, st>>>(x, ld, M, N, cc, rows_per_cta, out);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("colsum");
+    return CB200_OK;
+}
+
+// Row reductions of the tensor-core similarity path (see sim_rows_fwd_kernel): S [Ra, lds] dot products of the loss rows
+// (global indices row0 ..) against R columns -> lse [Ra], rowloss [Ra] (their sum is the loss).
+extern "C" int cb200_sim_rows_fwd(const float* S, long long lds, int Ra, int R, int N, int mode, int row0, float temperature,
+                                  float* lse, float* rowloss, void* stream) {
+    CB200_CHECK_ARG(Ra > 0 && R > 0 && N > 0 && (mode == 0 || mode == 1) && lds >= R, "sim_rows_fwd: bad shape");
+    sim_rows_fwd_kernel<<<(Ra + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, Ra, R, N, mode, row0,
+                                                                                     1.f / temperature, lse, rowloss);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("sim_rows_fwd");
+    return CB200_OK;
+}
+
+// G [Ra, ldg] (columns 0 .. cols-1 written, zeros beyond R) = gscale[0] * d loss / d S.
+extern "C" int cb200_sim_rows_bwd(const float* S, long long lds, int Ra, int R, int N, int mode, int row0, float temperature,
+                                  const float* lse, const float* gscale, float* G, long long ldg, int cols, void* stream) {
+    CB200_CHECK_ARG(Ra > 0 && R > 0 && N > 0 && (mode == 0 || mode == 1) && lds >= R && ldg >= cols && cols >= R,
+                    "sim_rows_bwd: bad shape");
+    sim_rows_bwd_kernel<<<(Ra + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(S, lds, Ra, R, N, mode, row0,
+                                                                                     1.f / temperature, lse, gscale, G, ldg, cols);
+    CB200_COUNT_LAUNCH();
+    CB200_CHECK_LAUNCH("sim_rows_bwd");
     return CB200_OK;
 }

@@ -50,29 +50,36 @@ def broadcast_parameters(model, src=0):
             dist.broadcast(t, src)
 
 
-def allreduce_gradients(model, params=None, group=None):
+def allreduce_gradients(model, params=None, group=None, flat=None):
     """DDP's gradient averaging for a bare module (capturable in a CUDA graph, no bucket hooks): used when
-    `P.distributed` and the model is not DDP-wrapped.  NCCL: ONE grouped launch that all-reduces every gradient tensor
-    in place with ReduceOp.AVG (ncclGroupStart/End through c10d's coalescing manager) - no flattening copy, no divide,
-    no copy back.  Other backends (gloo in the CPU tests): one flat SUM all-reduce and a divide."""
+    `P.distributed` and the model is not DDP-wrapped.
+
+    The gradients are packed into ONE contiguous buffer by a multi-tensor copy, all-reduced with ReduceOp.AVG in a
+    single NCCL call (a contiguous message lets NCCL use its bandwidth protocols; a grouped launch over the 26 separate
+    tensors ran in the latency protocol: 15 MB took 350 us on 8 GPUs, profiles/launches_r2_n8.md), and the parameters'
+    `.grad` are re-pointed at views of that buffer - no copy back, no divide.  `flat` (optional) is a persistent buffer of
+    the right size (engine.GradSync keeps one per bucket).  Backends without AVG (gloo in the CPU tests): SUM + divide."""
     import torch.distributed as dist
-    params = list(model.parameters()) if params is None else params
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
+    params = [p for p in (list(model.parameters()) if params is None else params) if p.grad is not None]
+    if not params:
         return
-    if dist.get_backend(group) == "nccl":
-        with dist._coalescing_manager(group=group):
-            for g in grads:
-                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=group)
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
-    flat.div_(dist.get_world_size(group))
+    grads = [p.grad for p in params]
+    total = sum(g.numel() for g in grads)
+    if flat is None or flat.numel() != total or flat.device != grads[0].device:
+        flat = torch.empty(total, device=grads[0].device, dtype=grads[0].dtype)
     views, off = [], 0
     for g in grads:
         views.append(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
-    torch._foreach_copy_(grads, views)
+    torch._foreach_copy_(views, grads)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, group=group)
+        flat.div_(dist.get_world_size(group))
+    for p, v in zip(params, views):
+        p.grad = v
+    return flat
 
 
 class GradSync(object):
@@ -97,6 +104,7 @@ class GradSync(object):
         self.rest = [p for p in model.parameters() if id(p) not in early_ids]
         self.armed, self.seen, self.fired = False, 0, False
         self.group, self.stream = None, None
+        self.flat_early, self.flat_rest = None, None          # persistent contiguous all-reduce buffers
         if self.nccl:
             self.group = dist.new_group(backend="nccl")
             self.stream = torch.cuda.Stream()
@@ -114,7 +122,7 @@ class GradSync(object):
         if self.seen == len(self.early):
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                allreduce_gradients(self.model, self.early, group=self.group)
+                self.flat_early = allreduce_gradients(self.model, self.early, group=self.group, flat=self.flat_early)
             self.fired = True
 
     def finish(self):
@@ -123,10 +131,11 @@ class GradSync(object):
         if not self.nccl:
             allreduce_gradients(self.model)
             return
-        todo = self.rest if self.fired else self.early + self.rest
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
-            allreduce_gradients(self.model, todo, group=self.group)
+            if not self.fired and self.early:
+                self.flat_early = allreduce_gradients(self.model, self.early, group=self.group, flat=self.flat_early)
+            self.flat_rest = allreduce_gradients(self.model, self.rest, group=self.group, flat=self.flat_rest)
         torch.cuda.current_stream().wait_stream(self.stream)
 
 

@@ -205,8 +205,9 @@ class SNPackFn(Function):
         dev = weights[0].device
         weights = [_c(w) for w in weights]
         # strict precision applies to passes through FROZEN weights (the generator step): no weight gradient is asked for
-        strict = holder["strict"] = (precision.strict_enabled() and bool(holder.get("allow_strict"))
-                                     and not any(ctx.needs_input_grad[2:]))
+        strict = holder["strict"] = (bool(holder.get("allow_strict")) and
+                                     (precision.strict_full() or
+                                      (precision.strict_enabled() and not any(ctx.needs_input_grad[2:]))))
         rnd = not strict
         side = {"dgrad": {}, "sigma": {}}
         sig_all = torch.empty(len(specs), 2, device=dev, dtype=torch.float32)
@@ -296,15 +297,18 @@ class SNPackFn(Function):
         for i in range(0, len(jobs), 16):
             K.sn_pack_batched(jobs[i:i + 16])
         if strict:
-            # error-compensated weights: forward packs become [w_hi | w_hi | w_lo] per tap (3x the reduction length),
-            # data-gradient packs [w_hi | w_lo] (2x).  The head packs are split where they are used (HeadsFn).
+            # error-compensated weights (the packs above are unrounded fp32): the forward GEMMs read [w_hi | w_hi | w_lo]
+            # per tap (3x the reduction length, side["fwd3"]), the data-gradient GEMMs [w_hi | w_lo] (2x).  The
+            # differentiable outputs stay the ordinary packs - they carry the weight gradients back to SNPackFn.backward.
+            # The head packs are split where they are used (HeadsFn).
+            side["fwd3"] = {}
             k = 0
             for s, w in zip(specs, weights):
                 if s.kind == "conv_first":
                     side["dgrad"][s.name] = _split_weight_bwd(side["dgrad"][s.name], 9)
                     k += 1
                 elif s.kind in ("conv", "conv_plain"):
-                    outs[k] = _split_weight_fwd(outs[k], s.ks * s.ks)
+                    side["fwd3"][s.name] = _split_weight_fwd(outs[k], s.ks * s.ks)
                     if s.name in side["dgrad"]:
                         side["dgrad"][s.name] = _split_weight_bwd(side["dgrad"][s.name], 9 if s.stride == 1 else 4)
                     k += 1
@@ -374,7 +378,8 @@ class SNDCGANBackboneFn(Function):
         for li, s in enumerate(specs[1:], start=1):
             # strict: activations stay fp32 and enter the GEMM as hi | lo | hi against [w_hi | w_hi | w_lo]
             a_in = K.split_tf32(acts[-1], 0) if strict else acts[-1]
-            acts.append(K.conv2d_nhwc_fwd(a_in, wb[2 * li], wb[2 * li + 1], s.ks, s.stride,
+            wpack = holder["side"]["fwd3"][s.name] if strict else wb[2 * li]
+            acts.append(K.conv2d_nhwc_fwd(a_in, wpack, wb[2 * li + 1], s.ks, s.stride,
                                           slope=SNDCGANBackboneFn.SLOPE, round_out=not strict))
         ctx.specs = specs
         ctx.dgrad = [holder["side"]["dgrad"][s.name] for s in specs]
@@ -400,7 +405,11 @@ class SNDCGANBackboneFn(Function):
             s = specs[li]
             a_in = acts[li - 1]
             if need_w[li]:
-                grads_w[li] = K.conv2d_nhwc_wgrad(a_in, g, s.ks, s.stride)
+                if ctx.strict:      # activation compensated along the (pixel) reduction axis: [a_hi ; a_lo] against [g ; g]
+                    grads_w[li] = K.conv2d_nhwc_wgrad(K.split_tf32(a_in, 2).view((2 * a_in.shape[0],) + tuple(a_in.shape[1:])),
+                                                      torch.cat([g, g], dim=0), s.ks, s.stride)
+                else:
+                    grads_w[li] = K.conv2d_nhwc_wgrad(a_in, g, s.ks, s.stride)
             if li > 1 or need_x or need_w[0] or need_b[0]:
                 # the data gradient (x lrelu') IS dL/d(pre-activation) of layer li-1: its column sum, fused into the
                 # GEMM epilogue, is that layer's bias gradient (layer 0 gets its own from conv_first_wgrad)
@@ -539,7 +548,7 @@ class GSNDCGANFn(Function):
         w4 = _c(w4)
         w_lin = _c(w_lin)
         # strict precision (contrad_b200/precision.py): the generator step, i.e. whenever a generator weight wants a gradient
-        strict = precision.strict_enabled() and any(ctx.needs_input_grad[2:])
+        strict = precision.strict_full() or (precision.strict_enabled() and any(ctx.needs_input_grad[2:]))
         if strict:
             # forward operands: activation hi | lo | hi against weights [w_hi | w_hi | w_lo] along the reduction axis (the
             # INPUT channels `o` of a transposed convolution = dim 0 of its weight); data-gradient packs [w_hi | w_lo]
@@ -734,13 +743,19 @@ class HeadsFn(Function):
             sl = slice(idx * hid, (idx + 1) * hid)
             gfull = padded[idx]
             if ng[wpos]:
-                dw = K.gemm_tn_wgrad(gfull if gfull.shape[1] % 128 == 0 else gfull, H[:, sl])
+                if ctx.strict:
+                    dw = K.gemm_tn_wgrad(torch.cat([gfull, gfull], dim=0), K.split_tf32(H[:, sl], 2).view(2 * B, hid))
+                else:
+                    dw = K.gemm_tn_wgrad(gfull if gfull.shape[1] % 128 == 0 else gfull, H[:, sl])
                 rows = 32 if pad is not None else dw.shape[0]
                 grads[wpos] = dw[:rows].contiguous() if rows != dw.shape[0] else dw
             if ng[bpos]:
                 grads[bpos] = K.colsum(_c(g))
         if ng[3]:
-            grads[3] = K.gemm_tn_wgrad(dH, feat)
+            if ctx.strict:
+                grads[3] = K.gemm_tn_wgrad(torch.cat([dH, dH], dim=0), K.split_tf32(feat, 2).view(2 * B, -1))
+            else:
+                grads[3] = K.gemm_tn_wgrad(dH, feat)
         if ng[4]:
             grads[4] = db_cat if db_cat is not None else K.colsum(dH)
         if ng[2]:
@@ -794,6 +809,56 @@ class ContrastiveFn(Function):
         z, lse = ctx.saved_tensors
         n, mode, temperature = ctx.cfg
         return K.contrastive_bwd(z, n, mode, temperature, lse, _c(gout).float()), None, None, None
+
+
+class ContrastiveTCFn(Function):
+    """The same two losses in north_star's tensor-core formulation: the similarity matrix of the loss rows against all
+    rows is ONE tcgen05 GEMM (cb200_gemm_nt_tf32, operands error-compensated - the logits are sim / tau with tau = 0.1),
+    softmax / cross-entropy are warp-shuffle row reductions over it (cb200_sim_rows_fwd / _bwd), and the embedding
+    gradient is two more GEMMs: dZ_A += G Z, dZ += G^T Z_A.  Rows are zero-padded to the GEMM tile (128); padding
+    columns are masked by the row kernels.  Memory: Ra x R fp32 twice (S and G): 9 MB at N = 512, 0.5 GB at N = 4096."""
+
+    @staticmethod
+    def forward(ctx, z, n, mode, temperature):
+        z = _c(z)
+        R, d = z.shape
+        row0 = 2 * n if mode else 0
+        Ra = R - row0
+        Rp, Rap = (R + 127) // 128 * 128, (Ra + 127) // 128 * 128
+        zp = z if Rp == R else torch.cat([z, z.new_zeros(Rp - R, d)])
+        za = zp[row0:row0 + Rap] if row0 + Rap <= Rp and Rap == Ra else torch.cat([z[row0:], z.new_zeros(Rap - Ra, d)])
+        hi, lo = _hi_lo(zp)
+        S = K.gemm_nt(K.split_tf32(za, 0), torch.cat([hi, hi, lo], dim=1).contiguous())           # [Rap, Rp]
+        lse, rowloss = K.sim_rows_fwd(S, Ra, R, n, mode, row0, temperature)
+        ctx.save_for_backward(zp, za, S, lse)
+        ctx.cfg = (n, mode, temperature, R, Ra, row0)
+        return rowloss.sum()
+
+    @staticmethod
+    def backward(ctx, gout):
+        zp, za, S, lse = ctx.saved_tensors
+        n, mode, temperature, R, Ra, row0 = ctx.cfg
+        Rap, Rp = S.shape
+        G = K.sim_rows_bwd(S, Ra, R, n, mode, row0, temperature, lse, _c(gout).float(), Rap, Rp)      # [Rap, Rp]
+        hi, lo = _hi_lo(zp.t().contiguous())
+        t1 = K.gemm_nt(K.split_tf32(G, 0), torch.cat([hi, hi, lo], dim=1).contiguous())                # G Z      [Rap, d]
+        gs, zs = K.split_tf32(G, 2), K.split_tf32(za, 2)
+        t2 = K.gemm_tn_wgrad(torch.cat([gs[0], gs[1], gs[0]]), torch.cat([zs[0], zs[0], zs[1]]))       # G^T Z_A  [Rp, d]
+        dz = t2[:R].clone() if Rp != R else t2
+        dz[row0:row0 + Ra] += t1[:Ra]
+        return dz, None, None, None
+
+
+_CONTRASTIVE_PATH = os.environ.get("CB200_CONTRASTIVE", "auto").strip().lower()      # simt | tc | auto
+
+
+def contrastive_loss(z, n, mode, temperature):
+    """NT-Xent (mode 0) / supcon-fake (mode 1) of the stacked embeddings z.  Two implementations of the same function:
+    the fused fp32 SIMT kernels (no similarity matrix in memory; fastest at the benchmark's R = 1-1.5 k rows, where the
+    tensor-core path is ~15 launches against 2) and the tensor-core formulation (ContrastiveTCFn; its GEMMs win once the
+    R^2 x 128 FLOPs dominate).  CB200_CONTRASTIVE = simt | tc | auto (default: tc from R >= 4096)."""
+    use_tc = _CONTRASTIVE_PATH == "tc" or (_CONTRASTIVE_PATH == "auto" and z.shape[0] >= 4096)
+    return (ContrastiveTCFn if use_tc else ContrastiveFn).apply(z, n, mode, temperature)
 
 
 class GanDLossFn(Function):

@@ -492,6 +492,25 @@ def contrastive_bwd(z, n, mode, temperature, lse, gscale):
     return dz
 
 
+def sim_rows_fwd(S, Ra, R, n, mode, row0, temperature):
+    """S [>=Ra, lds] similarity rows -> (lse [Ra], rowloss [Ra]); include/contrad_b200.h cb200_sim_rows_fwd."""
+    lse = torch.empty(Ra, device=S.device, dtype=torch.float32)
+    rowloss = torch.empty(Ra, device=S.device, dtype=torch.float32)
+    _call("sim_rows_fwd", 0, 4 * Ra * R, lib().cb200_sim_rows_fwd, ptr(S), i64(S.stride(0)), i32(Ra), i32(R), i32(n), i32(mode),
+          i32(row0), f32(temperature), ptr(lse), ptr(rowloss), stream_ptr())
+    return lse, rowloss
+
+
+def sim_rows_bwd(S, Ra, R, n, mode, row0, temperature, lse, gscale, rows_pad, cols_pad):
+    """-> G [rows_pad, cols_pad] (rows >= Ra zero) = gscale * dLoss/dS."""
+    G = torch.zeros(rows_pad, cols_pad, device=S.device, dtype=torch.float32) if rows_pad != Ra else \
+        torch.empty(rows_pad, cols_pad, device=S.device, dtype=torch.float32)
+    gscale = _f32c(gscale.reshape(1), "gscale")
+    _call("sim_rows_bwd", 0, 8 * Ra * R, lib().cb200_sim_rows_bwd, ptr(S), i64(S.stride(0)), i32(Ra), i32(R), i32(n), i32(mode),
+          i32(row0), f32(temperature), ptr(lse), ptr(gscale), ptr(G), i64(cols_pad), i32(cols_pad), stream_ptr())
+    return G
+
+
 def gan_d_loss(d_real, d_gen, kind, g_real=None, g_gen=None):
     """d_real, d_gen: 1-D views (any element stride, equal).  Returns (out3, g_real, g_gen); g_real / g_gen may be
     given as contiguous [n] destinations (e.g. slices of one gradient vector)."""

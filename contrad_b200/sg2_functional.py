@@ -19,6 +19,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import kernels as K
+from . import precision
 from . import sg2_kernels as S
 
 
@@ -100,12 +101,46 @@ def _rw_t(w):
     return _cached(w, "rw_t", lambda: K.round_tf32(_c(w.detach().t())))
 
 
+# ---- strict precision ("3xTF32", contrad_b200/precision.py level "full"): every GEMM Function below evaluates
+# (a_hi + a_lo)(b_hi + b_lo) ~ a_hi b_hi + a_lo b_hi + a_hi b_lo through the SAME tcgen05 entry points on operands
+# concatenated along the reduction axis; producers stop rounding (sg2_kernels._ro, RoundTF32).  Because the Function
+# families are closed under differentiation, the R1 double backward is compensated as well.
+def _strict():
+    return precision.strict_full()
+
+
+def _hi_lo(t):
+    hi = K.round_tf32(t)
+    return hi, K.round_tf32(t - hi)
+
+
+def _w3_cols(w2d, key):
+    """[N, K] weight -> [N, 3K] = w_hi | w_hi | w_lo (pairs with an activation split as hi | lo | hi along K)."""
+    def make():
+        hi, lo = _hi_lo(_c(w2d.detach()))
+        return torch.cat([hi, hi, lo], dim=1).contiguous()
+    return _cached(w2d, key, make)
+
+
+def _rows3(t, first):
+    """Three row-stacked copies for reductions over the ROW axis: first=True -> [hi ; lo ; hi], else [hi ; hi ; lo]."""
+    parts = K.split_tf32(_c(t), 2)
+    hi, lo = parts[0], parts[1]
+    return torch.cat([hi, lo, hi] if first else [hi, hi, lo], dim=0)
+
+
 def _pack_fwd(w):
     return _cached(w, "pack_fwd", lambda: K.pack_fwd_weight(_rw(w)))
 
 
 def _pack_dgrad(w):
     return _cached(w, "pack_dgrad", lambda: K.pack_dgrad_weight(_rw(w), 1))
+
+
+def _round_operand(x):
+    """Cotangent about to enter a GEMM: rounded to TF32 (straight-through) - or left alone in the strict precision mode,
+    where the consuming GEMM Function splits it into hi + lo itself."""
+    return x if _strict() else RoundTF32.apply(x)
 
 
 class RoundTF32(Function):
@@ -132,12 +167,14 @@ class MmNT(Function):
         a = _c(a)
         ctx.save_for_backward(a, w)
         ctx.has_bias = bias is not None
+        if _strict():
+            return K.gemm_nt(K.split_tf32(a, 0), _w3_cols(w, "w3"), None if bias is None else _c(bias.detach()))
         return K.gemm_nt(a, _rw(w), None if bias is None else _c(bias.detach()))
 
     @staticmethod
     def backward(ctx, dy):
         a, w = ctx.saved_tensors
-        dy = RoundTF32.apply(dy)
+        dy = _round_operand(dy)
         da = MmNN.apply(dy, w) if ctx.needs_input_grad[0] else None
         dw = MmTN.apply(dy, a) if ctx.needs_input_grad[1] else None
         db = ColSum.apply(dy) if ctx.has_bias and ctx.needs_input_grad[2] else None
@@ -151,12 +188,15 @@ class MmNN(Function):
     def forward(ctx, g, w):
         g = _c(g)
         ctx.save_for_backward(g, w)
+        if _strict():
+            wt3 = _cached(w, "wt3", lambda: (lambda hi, lo: torch.cat([hi, hi, lo], dim=1).contiguous())(*_hi_lo(_c(w.detach().t()))))
+            return K.gemm_nt(K.split_tf32(g, 0), wt3)
         return K.gemm_nt(g, _rw_t(w))
 
     @staticmethod
     def backward(ctx, gg):
         g, w = ctx.saved_tensors
-        gg = RoundTF32.apply(gg)
+        gg = _round_operand(gg)
         d_g = MmNT.apply(gg, w) if ctx.needs_input_grad[0] else None
         d_w = MmTN.apply(g, gg) if ctx.needs_input_grad[1] else None
         return d_g, d_w
@@ -170,6 +210,8 @@ class MmTN(Function):
         g, a = _c(g), _c(a)
         ctx.save_for_backward(g, a)
         n, k = g.shape[1], a.shape[1]
+        if _strict():                                  # reduction over the rows: stack [g_hi; g_lo; g_hi] against [a_hi; a_hi; a_lo]
+            g, a = _rows3(g, True), _rows3(a, False)
         if n % 128 == 0:
             return K.gemm_tn_wgrad(g, a)
         if k % 128 == 0:                               # the kernel wants 128 | rows of the result: compute the transpose
@@ -207,12 +249,17 @@ class Conv3x3(Function):
     def forward(ctx, x, w):
         x = _c(x)
         ctx.save_for_backward(x, w)
+        if _strict():                                  # input channels concatenated: x_hi | x_lo | x_hi against w_hi | w_hi | w_lo
+            def pack3():
+                hi, lo = _hi_lo(_c(w.detach()))
+                return K.pack_fwd_weight(torch.cat([hi, hi, lo], dim=1).contiguous())
+            return K.conv2d_nhwc_fwd(K.split_tf32(x, 0), _cached(w, "pack_fwd3", pack3), None, 3, 1)
         return K.conv2d_nhwc_fwd(x, _pack_fwd(w), None, 3, 1)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        dy = RoundTF32.apply(dy)
+        dy = _round_operand(dy)
         dx = Conv3x3Dgrad.apply(dy, w) if ctx.needs_input_grad[0] else None
         dw = Conv3x3Wgrad.apply(x, dy) if ctx.needs_input_grad[1] else None
         return dx, dw
@@ -226,12 +273,17 @@ class Conv3x3Dgrad(Function):
         dy = _c(dy)
         ctx.save_for_backward(dy, w)
         B, H, W, _ = dy.shape
+        if _strict():                                  # output channels (the reduction axis here) concatenated
+            def pack3():
+                hi, lo = _hi_lo(_c(w.detach()))
+                return K.pack_dgrad_weight(torch.cat([hi, hi, lo], dim=0).contiguous(), 1)
+            return K.conv2d_nhwc_dgrad(K.split_tf32(dy, 0), _cached(w, "pack_dgrad3", pack3), (B, H, W, w.shape[1]), 3, 1)
         return K.conv2d_nhwc_dgrad(dy, _pack_dgrad(w), (B, H, W, w.shape[1]), 3, 1)
 
     @staticmethod
     def backward(ctx, g):
         dy, w = ctx.saved_tensors
-        g = RoundTF32.apply(g)
+        g = _round_operand(g)
         d_dy = Conv3x3.apply(g, w) if ctx.needs_input_grad[0] else None
         d_w = Conv3x3Wgrad.apply(g, dy) if ctx.needs_input_grad[1] else None
         return d_dy, d_w
@@ -245,6 +297,8 @@ class Conv3x3Wgrad(Function):
         x, dy = _c(x), _c(dy)
         ctx.save_for_backward(x, dy)
         cout, cin = dy.shape[3], x.shape[3]
+        if _strict():                                  # reduction over pixels: stack the batch, [x_hi; x_hi; x_lo] vs [dy_hi; dy_lo; dy_hi]
+            x, dy = _rows3(x, False), _rows3(dy, True)
         if cout % 128:          # the kernel tiles Cout by 128: 32- / 64-channel layers present dY zero-extended
             dwp = K.conv2d_nhwc_wgrad(x, S.pad_channels(dy, (cout + 127) // 128 * 128), 3, 1)[:cout]
         else:

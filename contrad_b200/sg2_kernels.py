@@ -5,8 +5,15 @@ import ctypes
 
 import torch
 
+from . import precision
 from ._capi import f32, i32, i64, lib, ptr, stream_ptr
 from .kernels import _call, _f32c
+
+
+def _ro(round_out):
+    """TF32 rounding of a producer's output: off in the full strict precision mode (contrad_b200/precision.py), where
+    activations stay fp32 and the GEMM Functions split them into hi + lo operands at consumption."""
+    return 1 if (round_out and not precision.strict_full()) else 0
 
 
 def _strides4(t, nhwc):
@@ -38,7 +45,7 @@ def upfirdn2d(x, fir, up, down, pad, out_hw=None, nhwc=True, flip=False, gain=1.
     y = torch.empty((N, Ho, Wo, C) if nhwc else (N, C, Ho, Wo), device=x.device, dtype=torch.float32)
     _call("upfirdn2d", 0, 4 * (x.numel() + y.numel()), lib().cb200_upfirdn2d, ptr(x), _strides4(x, nhwc), ptr(y),
           _strides4(y, nhwc), ptr(fir), i32(N), i32(C), i32(Hi), i32(Wi), i32(Ho), i32(Wo), i32(up), i32(down), i32(px0),
-          i32(py0), i32(kh), i32(kw), i32(1 if flip else 0), f32(gain), i32(1 if nhwc else 0), i32(1 if round_out else 0),
+          i32(py0), i32(kh), i32(kw), i32(1 if flip else 0), f32(gain), i32(1 if nhwc else 0), i32(_ro(round_out)),
           stream_ptr())
     return y
 
@@ -51,7 +58,7 @@ def patch_s2_gather(x, round_out=False):
     Ho, Wo = (Hi - 1) // 2, (Wi - 1) // 2
     u = torch.empty(B, Ho, Wo, 9, C, device=x.device, dtype=torch.float32)
     _call("patch_s2_gather", 0, 4 * (x.numel() + u.numel()), lib().cb200_patch_s2_gather, ptr(x), ptr(u), i32(B), i32(Ho), i32(Wo),
-          i32(C), i32(1 if round_out else 0), stream_ptr())
+          i32(C), i32(_ro(round_out)), stream_ptr())
     return u
 
 
@@ -62,7 +69,7 @@ def patch_s2_scatter(u, round_out=False):
     assert nine == 9
     x = torch.empty(B, 2 * Ho + 1, 2 * Wo + 1, C, device=u.device, dtype=torch.float32)
     _call("patch_s2_scatter", 0, 4 * (x.numel() + u.numel()), lib().cb200_patch_s2_scatter, ptr(u), ptr(x), i32(B), i32(Ho),
-          i32(Wo), i32(C), i32(1 if round_out else 0), stream_ptr())
+          i32(Wo), i32(C), i32(_ro(round_out)), stream_ptr())
     return x
 
 
@@ -75,7 +82,7 @@ def bias_act(x, bias, slope, gain, res=None, round_out=False):
         assert res.shape == x.shape
     y = torch.empty_like(x)
     _call("bias_act", 0, 8 * x.numel(), lib().cb200_bias_act, ptr(x), ptr(bias), ptr(None), ptr(res), ptr(y), i64(x.numel()),
-          i32(C), i32(0), f32(slope), f32(gain), i32(1 if round_out else 0), stream_ptr())
+          i32(C), i32(0), f32(slope), f32(gain), i32(_ro(round_out)), stream_ptr())
     return y
 
 
@@ -86,7 +93,7 @@ def bias_act_grad(g, ref, bias, slope, gain, round_out=False):
     assert g.shape == ref.shape, (g.shape, ref.shape)
     y = torch.empty_like(g)
     _call("bias_act", 0, 12 * g.numel(), lib().cb200_bias_act, ptr(g), ptr(bias), ptr(ref), ptr(None), ptr(y), i64(g.numel()),
-          i32(g.shape[-1]), i32(1), f32(slope), f32(gain), i32(1 if round_out else 0), stream_ptr())
+          i32(g.shape[-1]), i32(1), f32(slope), f32(gain), i32(_ro(round_out)), stream_ptr())
     return y
 
 
@@ -99,7 +106,7 @@ def modulate(x, s, batch=None, alpha=1.0, round_out=False):
     P = x[0].numel() // C
     y = torch.empty((B,) + tuple(x.shape[1:]), device=x.device, dtype=torch.float32)
     _call("modulate", 0, 8 * y.numel(), lib().cb200_modulate, ptr(x), i64(0 if x.shape[0] == 1 and B > 1 else P * C), ptr(s),
-          ptr(y), i32(B), i64(P), i32(C), f32(alpha), i32(1 if round_out else 0), stream_ptr())
+          ptr(y), i32(B), i64(P), i32(C), f32(alpha), i32(_ro(round_out)), stream_ptr())
     return y
 
 
@@ -126,7 +133,7 @@ def mod_epilogue(x, demod, noise, noise_weight, bias, slope=0.2, gain=2 ** 0.5, 
         assert noise.numel() == B * P, (noise.shape, x.shape)
     y = torch.empty_like(x)
     _call("mod_epilogue", 0, 8 * x.numel(), lib().cb200_mod_epilogue, ptr(x), ptr(demod), ptr(noise), ptr(noise_weight), ptr(bias),
-          ptr(y), i32(B), i64(P), i32(C), f32(slope), f32(gain), i32(1 if round_out else 0), stream_ptr())
+          ptr(y), i32(B), i64(P), i32(C), f32(slope), f32(gain), i32(_ro(round_out)), stream_ptr())
     return y
 
 
@@ -183,7 +190,7 @@ def stddev_concat(x, std, cpad, round_out=False):
     B, H, W, C = x.shape
     y = torch.empty(B, H, W, cpad, device=x.device, dtype=torch.float32)
     _call("stddev_concat", 0, 4 * (x.numel() + y.numel()), lib().cb200_stddev_concat, ptr(x), ptr(std), ptr(y), i32(B), i64(H * W),
-          i32(C), i32(cpad), i32(1 if round_out else 0), stream_ptr())
+          i32(C), i32(cpad), i32(_ro(round_out)), stream_ptr())
     return y
 
 
@@ -205,7 +212,7 @@ def rgb_to_nhwc(x, cpad=32, scale=1.0, shift=0.0, round_out=False):
     assert C == 3
     y = torch.empty(B, H, W, cpad, device=x.device, dtype=torch.float32)
     _call("rgb_to_nhwc", 0, 4 * (x.numel() + y.numel()), lib().cb200_rgb_to_nhwc, ptr(x), ptr(y), i32(B), i32(H), i32(W), i32(cpad),
-          f32(scale), f32(shift), i32(1 if round_out else 0), stream_ptr())
+          f32(scale), f32(shift), i32(_ro(round_out)), stream_ptr())
     return y
 
 
@@ -225,7 +232,7 @@ def pixelnorm(x, round_out=False):
     x = _f32c(x, "x")
     rows, d = x.shape
     y = torch.empty_like(x)
-    _call("pixelnorm", 0, 8 * x.numel(), lib().cb200_pixelnorm, ptr(x), ptr(y), i32(rows), i32(d), i32(1 if round_out else 0),
+    _call("pixelnorm", 0, 8 * x.numel(), lib().cb200_pixelnorm, ptr(x), ptr(y), i32(rows), i32(d), i32(_ro(round_out)),
           stream_ptr())
     return y
 
@@ -254,7 +261,7 @@ def axpby(a, b=None, alpha=1.0, beta=1.0, gamma=0.0, round_out=False):
         assert b.shape == a.shape
     out = torch.empty_like(a)
     _call("axpby", 0, 8 * a.numel(), lib().cb200_axpby, ptr(a), ptr(b), ptr(out), i64(a.numel()), f32(alpha), f32(beta), f32(gamma),
-          i32(1 if round_out else 0), stream_ptr())
+          i32(_ro(round_out)), stream_ptr())
     return out
 
 

@@ -1,7 +1,7 @@
 """Mirror of training/criterion.py: ``nt_xent`` on the fused sm_100a kernels."""
 import torch
 
-from ..functional import ContrastiveFn, RowNormalizeFn
+from ..functional import contrastive_loss, RowNormalizeFn
 from ..third_party.gather_layer import GatherLayer
 
 
@@ -15,7 +15,7 @@ def nt_xent(out1, out2, temperature=0.1, distributed=False, normalize=False):
         out1 = torch.cat(GatherLayer.apply(out1), dim=0)
         out2 = torch.cat(GatherLayer.apply(out2), dim=0)
     n = out1.size(0)
-    return ContrastiveFn.apply(torch.cat([out1, out2], dim=0), n, 0, float(temperature))
+    return contrastive_loss(torch.cat([out1, out2], dim=0), n, 0, float(temperature))
 
 
 def target_nll_loss(inputs, targets, reduction="none"):

@@ -3,7 +3,7 @@ signatures; the arithmetic runs on the sm_100a kernels (one fused contrastive ke
 fused GAN-loss kernel) and, when ``P.distributed``, on ONE packed all-gather of the embeddings."""
 import torch
 
-from ...functional import ContrastiveFn, GanDLossFn, GanGLossFn, RowNormalizeFn
+from ...functional import contrastive_loss, GanDLossFn, GanGLossFn, RowNormalizeFn
 from ...third_party.gather_layer import GatherLayer, gather_rows
 
 _D_LOSSES = ("nonsat", "wgan", "hinge", "lsgan")
@@ -16,7 +16,7 @@ def supcon_fake(out1, out2, others, temperature, distributed=False):
         out2 = torch.cat(GatherLayer.apply(out2), dim=0)
         others = torch.cat(GatherLayer.apply(others), dim=0)
     n = out1.size(0)
-    return ContrastiveFn.apply(torch.cat([out1, out2, others], dim=0), n, 1, float(temperature))
+    return contrastive_loss(torch.cat([out1, out2, others], dim=0), n, 1, float(temperature))
 
 
 def _rank_major(blocks, n):
@@ -51,11 +51,11 @@ def loss_D_fn(P, D, options, images, gen_images):
         views_all = _rank_major(both[:, :, :d].contiguous(), n)
         reals_all = _rank_major(both[:, :, d:].contiguous(), n)
         n_all = n * both.shape[0]
-        simclr_loss = ContrastiveFn.apply(views_all[:2 * n_all], n_all, 0, float(P.temp))
-        sup_loss = ContrastiveFn.apply(reals_all, n_all, 1, float(P.temp))
+        simclr_loss = contrastive_loss(views_all[:2 * n_all], n_all, 0, float(P.temp))
+        sup_loss = contrastive_loss(reals_all, n_all, 1, float(P.temp))
     else:
-        simclr_loss = ContrastiveFn.apply(views[:2 * n], n, 0, float(P.temp))
-        sup_loss = ContrastiveFn.apply(reals, n, 1, float(P.temp))
+        simclr_loss = contrastive_loss(views[:2 * n], n, 0, float(P.temp))
+        sup_loss = contrastive_loss(reals, n, 1, float(P.temp))
 
     d_loss, means = GanDLossFn.apply(d_all, n, options["loss"])
     return simclr_loss + P.lbd_a * sup_loss, {

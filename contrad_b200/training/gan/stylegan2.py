@@ -10,7 +10,7 @@ from torch import autograd, nn
 
 from ... import sg2_functional as SF
 from ... import sg2_kernels as S
-from ...functional import ContrastiveFn, GanDLossFn, GanGLossFn, RowNormalizeFn
+from ...functional import GanDLossFn, GanGLossFn, RowNormalizeFn, contrastive_loss
 from ..criterion import nt_xent
 from .contrad import supcon_fake
 

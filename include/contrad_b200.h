@@ -234,6 +234,19 @@ int cb200_contrastive_fwd(const float* z, int N, int d, int mode, float temperat
                           float* scratch /* 48 floats per loss row */, float* loss, void* stream);
 int cb200_contrastive_bwd(const float* z, int N, int d, int mode, float temperature, const float* lse,
                           const float* gscale, float* dz, void* stream);
+
+/* Tensor-core formulation of the same two losses (north_star: "the NT-Xent pairwise-cosine similarity matrix uses
+ * tcgen05 MMA fed by TMA; the temperature-softmax / CE are warp-shuffle reductions"): the caller forms S = Z_A Z^T with
+ * cb200_gemm_nt_tf32 on error-compensated operands (cb200_split_tf32: the logits are S / tau with tau = 0.1, so
+ * single-pass TF32 would be amplified 10x) and these two kernels do the row reductions of training/criterion.py:35-45 /
+ * training/gan/contrad.py:13-32 on it: S [Ra, lds] = dot products of the loss rows (global row indices row0 .. row0+Ra-1)
+ * against all R rows, mode 0 NT-Xent (R = 2N), mode 1 supcon-fake (R = 3N, row0 = 2N).  fwd: lse [Ra] and rowloss [Ra]
+ * (loss = sum).  bwd: G [Ra, ldg] = gscale[0] * dLoss/dS (columns >= R and the diagonal are zero); the embedding
+ * gradient is then two more GEMMs, dZ_A += G Z and dZ += G^T Z_A. */
+int cb200_sim_rows_fwd(const float* S, long long lds, int Ra, int R, int N, int mode, int row0, float temperature,
+                       float* lse, float* rowloss, void* stream);
+int cb200_sim_rows_bwd(const float* S, long long lds, int Ra, int R, int N, int mode, int row0, float temperature,
+                       const float* lse, const float* gscale, float* G, long long ldg, int cols, void* stream);
 int cb200_gan_d_loss(const float* d_real, const float* d_gen, long long stride, int N, int kind, float* out3,
                      float* g_real, float* g_gen, void* stream);
 int cb200_gan_g_loss(const float* d_gen, long long stride, int N, int kind, float* out1, float* g_gen,

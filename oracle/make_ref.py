@@ -27,9 +27,27 @@ SKIP_REL = {os.path.join("third_party", "tf")}
 KEEP_EXT = {".py", ".gin", ".cpp", ".cu", ".h", ".txt", ".yml", ".md"}
 
 
-def make(src=SRC, dst=DST, quiet=False):
+def _up_to_date(src, dst):
+    """True when oracle/_ref already holds an unmodified copy of every file the recipe would copy."""
+    try:
+        with open(os.path.join(dst, "MANIFEST.json")) as f:
+            files = json.load(f)["files"]
+        for rel, digest in files.items():
+            with open(os.path.join(src, rel), "rb") as f:
+                if hashlib.sha256(f.read()).hexdigest() != digest:
+                    return False
+        return verify(dst)
+    except (OSError, KeyError, ValueError):
+        return False
+
+
+def make(src=SRC, dst=DST, quiet=False, force=False):
     if not os.path.isdir(os.path.join(src, "augment")):
         raise RuntimeError("reference sources not found at %s" % src)
+    if not force and _up_to_date(src, dst):
+        if not quiet:
+            print("oracle/_ref: up to date")
+        return dst
     tmp = dst + ".tmp"
     shutil.rmtree(tmp, ignore_errors=True)
     manifest = {}
@@ -66,6 +84,27 @@ def verify(dst=DST):
     return True
 
 
+EXT_DIR = os.path.join(DST, "_torch_ext")
+
+
+def build_extensions(dst=DST, quiet=False):
+    """JIT-build the reference's two CUDA ops (models/gan/stylegan2/op: upfirdn2d, fused bias-act) for sm_100 with the
+    reference's OWN `torch.utils.cpp_extension.load` calls, into oracle/_ref/_torch_ext, so that the StyleGAN2 reference
+    legs find them pre-built on the GPU box (no compiler run inside a timed GPU lease).  ~90 s on first use, cached."""
+    import subprocess
+    env = dict(os.environ, TORCH_CUDA_ARCH_LIST="10.0", TORCH_EXTENSIONS_DIR=EXT_DIR, MAX_JOBS="4")
+    code = ("import sys; sys.path.insert(0, %r); from oracle import ref_import; ref_import.REFERENCE_ROOT = %r; "
+            "ref_import.activate(); import models.gan.stylegan2.op as op; print('reference ops:', op.upfirdn2d.__name__)"
+            % (os.path.dirname(HERE), dst))
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if not quiet:
+        print(r.stdout.decode()[-300:])
+    return r.returncode == 0
+
+
 if __name__ == "__main__":
-    make()
-    sys.exit(0 if verify() else 1)
+    make(force="--force" in sys.argv)
+    ok = verify()
+    if "--ext" in sys.argv:
+        ok = build_extensions() and ok
+    sys.exit(0 if ok else 1)

@@ -143,6 +143,74 @@ def run_gpu(steps, warmup, global_batch=512, architecture="sndcgan", gin_config=
         ref_import.deactivate()
 
 
+def run_gpu_stylegan2(steps, warmup, architecture="stylegan2", size=32, batch=64,
+                      gin_config="configs/gan/stylegan2/c10_style64.gin", lbd_r1=0.1, no_lazy=True, halflife_k=1000,
+                      device_ids=None):
+    """BASELINE configs 4 / 5 through the reference's own `train_stylegan2_contraD.train()` (:166-296) on unmodified
+    reference modules with its own CUDA ops (pre-built by oracle/make_ref.py --ext), the set-up of `worker()`
+    (:298-378: G_D, g_ema, torch.optim.Adam, `nn.DataParallel(GD)`), synthetic pinned-host batches.  One process;
+    `device_ids` = the GPUs DataParallel replicates over (None = all visible, as the script does)."""
+    import importlib
+    import torch.nn as nn
+    import torch.optim as optim
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    ext = os.path.join(ref_import._VENDORED, "_torch_ext")
+    if os.path.isdir(ext):
+        os.environ["TORCH_EXTENSIONS_DIR"] = ext
+    gin, root = _activate(gin_config)
+    cwd = os.getcwd()
+    try:
+        os.chdir(root)
+        if "train_stylegan2_contraD" in sys.modules:
+            del sys.modules["train_stylegan2_contraD"]
+        ts = importlib.import_module("train_stylegan2_contraD")
+        from augment import get_augment
+        from models.gan import get_architecture
+        from training.gan import setup
+        torch.cuda.set_device(0)
+        P = SimpleNamespace(mode="contrad", aug="simclr", penalty="none", temp=0.1, lbd_a=1.0, use_warmup=True,
+                            architecture=architecture, distributed=False, no_lazy=no_lazy, d_reg_every=1 if no_lazy else 16,
+                            lbd_r1=lbd_r1, style_mix=0.9, halflife_k=halflife_k, ema_start_k=halflife_k, halflife_lr=0,
+                            no_fid=True, no_gif=True, n_eval_avg=1, print_every=10 ** 9, evaluate_every=10 ** 9,
+                            save_every=10 ** 9, starting_step=1, eval_seed=0, rank=0)
+        P = setup(P)
+        options = ts.get_options_dict()
+        assert options["batch_size"] == batch, (options["batch_size"], batch)
+        P.accum = 0.5 ** (options["batch_size"] / (P.halflife_k * 1000))
+        torch.manual_seed(1234); np.random.seed(1234)
+        image_size = (size, size, 3)
+        generator, discriminator = get_architecture(architecture, image_size, P=P)
+        g_ema, _ = get_architecture(architecture, image_size, P=P)
+        generator, discriminator = generator.cuda(), discriminator.cuda()
+        P.augment_fn = get_augment(mode=P.aug).cuda()
+        GD = ts.G_D(generator, discriminator, P.augment_fn).cuda()
+        g_ema = g_ema.cuda(); g_ema.eval()
+        G_opt = optim.Adam(generator.parameters(), lr=options["lr"], betas=options["beta"])
+        D_opt = optim.Adam(discriminator.parameters(), lr=options["lr_d"], betas=options["beta"])
+        GD = nn.DataParallel(GD, device_ids=device_ids)
+
+        class _Quiet(object):
+            logdir = None
+            def log(self, s): pass
+            def log_dirname(self, s): pass
+            def scalar_summary(self, *a): pass
+
+        loader = _SyntheticLoader(batch, size=size, pool=2)
+        options["max_steps"] = warmup + steps
+        ts.train(P, options, models=(generator, discriminator, GD, g_ema), optimizers=(G_opt, D_opt),
+                 train_loader=loader, logger=_Quiet())
+        for d in range(torch.cuda.device_count() if device_ids is None else len(device_ids)):
+            torch.cuda.synchronize(d)
+        dt = time.perf_counter() - loader.stamps[warmup]
+        return {"ms_per_step": 1e3 * dt / steps, "images_per_s": batch * steps / dt, "steps": steps, "warmup": warmup,
+                "n_gpus": torch.cuda.device_count() if device_ids is None else len(device_ids),
+                "what": "oracle/_ref train_stylegan2_contraD.train() (:166-296) on unmodified reference modules and CUDA ops, "
+                        "nn.DataParallel(G_D), torch.optim.Adam, PyTorch default flags, R1 every %d step(s)" % P.d_reg_every}
+    finally:
+        os.chdir(cwd)
+        ref_import.deactivate()
+
+
 def run_cpu(steps, warmup, batch=512, threads=None, architecture="sndcgan",
             gin_config="configs/gan/cifar10/c10_b512.gin", seconds_budget=None):
     """The reference modules on the host CPU (all `threads` torch threads): loop body of train_gan.py:141-179.

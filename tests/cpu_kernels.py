@@ -233,7 +233,20 @@ def ema_lerp(pairs, decay):
         d.mul_(decay).add_(s, alpha=1 - decay)
 
 
-K_NAMES = ("gemm_nt", "gemm_tn_wgrad", "conv2d_nhwc_fwd", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "colsum", "round_tf32_")
+def split_tf32(x, mode):
+    """include/contrad_b200.h cb200_split_tf32: hi = rn_tf32(x), lo = rn_tf32(x - hi); mode 0 hi|lo|hi, 1 hi|hi, 2 [hi ; lo]."""
+    from contrad_b200 import kernels as K
+    hi = K.round_tf32(x)
+    lo = K.round_tf32(x - hi)
+    if mode == 0:
+        return torch.cat([hi, lo, hi], dim=-1).contiguous()
+    if mode == 1:
+        return torch.cat([hi, hi], dim=-1).contiguous()
+    return torch.stack([hi, lo], dim=0).contiguous()
+
+
+K_NAMES = ("gemm_nt", "gemm_tn_wgrad", "conv2d_nhwc_fwd", "conv2d_nhwc_dgrad", "conv2d_nhwc_wgrad", "colsum", "round_tf32_",
+           "split_tf32")
 S_NAMES = ("upfirdn2d", "patch_s2_gather", "patch_s2_scatter", "bias_act", "bias_act_grad", "modulate", "mul_reduce",
            "mod_epilogue", "noise_grad", "stddev_fwd", "stddev_bwd", "stddev_bwd_bwd", "stddev_concat", "stddev_split",
            "rgb_to_nhwc", "nhwc_to_rgb", "pixelnorm", "row_sqsum", "row_scale", "axpby", "ema_lerp", "pad_channels")

@@ -441,7 +441,7 @@ def test_emulated_conv_first_layer(B, H):
 
 
 # ------------------------------------------------------------------ the product's train step on the CPU
-@pytest.mark.parametrize("strict", [False, True])
+@pytest.mark.parametrize("strict", [False, True, "full"])
 def test_product_train_step_on_cpu_vs_oracle(strict):
     """BASELINE configs[0] in spirit ("SNDCGAN+ContraD on CPU, one step, synthetic 32x32: plumbing, no GPU"): the PRODUCT's
     own modules, autograd Functions, engine.train_step and every SIMT kernel (emulated) run one complete D+G step incl.
@@ -515,7 +515,7 @@ def test_product_train_step_on_cpu_vs_oracle(strict):
     assert rel(got["d_loss"], ref["l_con_pos"] + ref["l_con_neg"]) < 1e-3, (got, ref)
     assert rel(got["d_penalty"], ref["l_dis"]) < 1e-3 and rel(got["g_loss"], ref["l_gen"]) < 1e-3, (got, ref)
     assert abs(got["d_real"] - ref["d_real"]) < 1e-3 and abs(got["d_gen"] - ref["d_gen"]) < 1e-3
-    assert rel(got["d_grad_norm"], ref["d_grad_norm"]) < 5e-3, (got["d_grad_norm"], ref["d_grad_norm"])
+    assert rel(got["d_grad_norm"], ref["d_grad_norm"]) < (1e-3 if strict == "full" else 5e-3), (got["d_grad_norm"], ref["d_grad_norm"])
     assert rel(got["g_grad_norm"], ref["g_grad_norm"]) < (1e-3 if strict else 3e-2), (got["g_grad_norm"], ref["g_grad_norm"])
     sd_now = D.state_dict()
     for k, v in sd_d_o.items():
@@ -641,3 +641,28 @@ print("wgrad v2 ok")
     env = dict(os.environ, CB200_CONV_FIRST_WGRAD="2")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
     assert r.returncode == 0 and b"wgrad v2 ok" in r.stdout, r.stdout.decode()[-3000:]
+
+
+def test_tensor_core_contrastive_formulation_matches_reference_fixtures(golden_dir):
+    """functional.ContrastiveTCFn (north_star: similarity matrix as a tcgen05 GEMM, softmax / CE as warp-shuffle row
+    reductions): the row kernels run emulated, the GEMMs on the torch stand-ins, against the reference's own nt_xent /
+    supcon_fake values and gradients (tests/golden/contrastive.pt) at the fixtures' 2e-5."""
+    import tests.cpu_tc_standins as TC
+    from contrad_b200.functional import ContrastiveTCFn
+    fx = _load(golden_dir, "contrastive.pt")
+    with emulated(), TC.patched():
+        for case in fx["cases"]:
+            n = case["n"]
+            a, b, c = (case[k].clone().requires_grad_(True) for k in ("a", "b", "c"))
+            l1 = ContrastiveTCFn.apply(torch.cat([a, b]), n, 0, 0.1)
+            g1 = torch.autograd.grad(l1, [a, b])
+            assert abs(float(l1) - case["nt_xent"]) < 2e-5 * abs(case["nt_xent"]), (n, float(l1), case["nt_xent"])
+            for g, w in zip(g1, case["nt_xent_grads"]):
+                assert torch.allclose(g, w, atol=2e-5 * float(w.abs().max()) + 1e-7, rtol=1e-4), n
+            l2 = ContrastiveTCFn.apply(torch.cat([a, b, c]), n, 1, 0.1)
+            g2 = torch.autograd.grad(l2, [a, b, c])
+            assert abs(float(l2) - case["supcon"]) < 2e-5 * abs(case["supcon"]), (n, float(l2), case["supcon"])
+            for g, w in zip(g2, case["supcon_grads"]):
+                assert torch.allclose(g, w, atol=2e-5 * float(w.abs().max()) + 1e-7, rtol=1e-4), n
+            l3 = ContrastiveTCFn.apply(torch.cat([a, b]), n, 0, 0.5)
+            assert abs(float(l3) - case["nt_xent_t05"]) < 2e-5 * abs(case["nt_xent_t05"])

@@ -532,3 +532,50 @@ def test_fused_adam_matches_torch_adam(K):
     sa, sb = oa.state_dict(), ob.state_dict()
     assert set(sa["state"][0].keys()) == set(sb["state"][0].keys())
     ob.load_state_dict(sa)          # checkpoints interchange
+
+
+def test_tensor_core_contrastive_path(K, golden_dir):
+    """functional.ContrastiveTCFn - similarity matrix on tcgen05 (error-compensated operands), softmax / CE as warp-shuffle
+    row reductions - against the reference fixtures (2e-5) and against the fused SIMT kernels at the benchmark size
+    (N = 512: R = 1024 / 1536 rows) and at N = 4096 (R = 8192 / 12288); timings of both paths go to gpurun_out."""
+    import json
+    from contrad_b200.functional import ContrastiveFn, ContrastiveTCFn
+    fx = _load(golden_dir, "contrastive.pt")
+    for case in fx["cases"]:
+        n = case["n"]
+        a, b, c = (case[k].cuda().requires_grad_(True) for k in ("a", "b", "c"))
+        l1 = ContrastiveTCFn.apply(torch.cat([a, b]), n, 0, 0.1)
+        g1 = torch.autograd.grad(l1, [a, b])
+        assert abs(float(l1) - case["nt_xent"]) < 2e-5 * abs(case["nt_xent"])
+        for g, w in zip(g1, case["nt_xent_grads"]):
+            assert torch.allclose(g.cpu(), w, atol=2e-5 * float(w.abs().max()) + 1e-7, rtol=1e-4)
+        l2 = ContrastiveTCFn.apply(torch.cat([a, b, c]), n, 1, 0.1)
+        g2 = torch.autograd.grad(l2, [a, b, c])
+        assert abs(float(l2) - case["supcon"]) < 2e-5 * abs(case["supcon"])
+        for g, w in zip(g2, case["supcon_grads"]):
+            assert torch.allclose(g.cpu(), w, atol=2e-5 * float(w.abs().max()) + 1e-7, rtol=1e-4)
+    report = {}
+    for n in (512, 4096):
+        torch.manual_seed(n)
+        for mode, rows in ((0, 2 * n), (1, 3 * n)):
+            z = F.normalize(torch.randn(rows, 128, device="cuda")).requires_grad_(True)
+            res = {}
+            for name, fn in (("simt", ContrastiveFn), ("tc", ContrastiveTCFn)):
+                loss = fn.apply(z, n, mode, 0.1)
+                (g,) = torch.autograd.grad(loss, z)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    l = fn.apply(z, n, mode, 0.1)
+                    torch.autograd.grad(l, z)
+                e1.record(); torch.cuda.synchronize()
+                res[name] = (float(loss), g.detach(), e0.elapsed_time(e1) / 5)
+            assert abs(res["tc"][0] - res["simt"][0]) < 2e-5 * abs(res["simt"][0]), (n, mode, res["tc"][0], res["simt"][0])
+            gerr = float((res["tc"][1] - res["simt"][1]).norm() / res["simt"][1].norm())
+            assert gerr < 1e-4, (n, mode, gerr)
+            report["N%d_mode%d" % (n, mode)] = {"simt_ms_fwd_bwd": res["simt"][2], "tc_ms_fwd_bwd": res["tc"][2], "grad_rel_l2": gerr}
+    print(report)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "contrastive_paths.json"), "w") as f:
+        json.dump(report, f, indent=1)

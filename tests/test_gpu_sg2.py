@@ -463,6 +463,66 @@ def test_dstep16_objective_matches_reference(fx, models, tf32_oracle):
     ck.finish()
 
 
+def test_strict_precision_meets_fixed_tolerances(fx, models):
+    """The full strict precision mode (contrad_b200/precision.py: every GEMM Function of sg2_functional evaluates hi/lo-split
+    "3xTF32" operands, producers stop rounding) against the reference fixtures with FIXED bars - no yardstick: outputs, R1
+    per sample, loss scalars and the total D gradient norm of the n = 16 objective 1e-3 (north_star), worst per-parameter
+    gradient norm 2e-3 (4e-3 for the R1 double backward)."""
+    from contrad_b200 import precision
+    from contrad_b200.training.gan import stylegan2 as T
+    G, D = models
+    ck = _Checks("strict")
+    with precision.strict("full"):
+        c = fx["d_case"]
+        D.zero_grad()
+        x = c["x"].cuda().requires_grad_(True)
+        d, aux = D(x, projection=True, projection2=True, penultimate=True)
+        ck.add("D.d", _rel(d, c["d"]), 1e-3)
+        ck.add("D.projection", _rel(aux["projection"], c["projection"]), 1e-3)
+        ck.add("D.penultimate", _rel(aux["penultimate"], c["penultimate"]), 1e-3)
+        ((d * c["c_d"].cuda()).sum() + (aux["projection"] * c["c1"].cuda()).sum() + (aux["projection2"] * c["c2"].cuda()).sum()).backward()
+        ck.add("D.dx_l2", _l2(x.grad, c["dx"]), 2e-3)
+        ck.add("D.norms", _norm_errs({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], "strict.D"), 2e-3)
+
+        c = fx["r1_case"]
+        D.zero_grad()
+        per_sample = T.r1_per_sample(D, c["x"].cuda(), lambda t: t)
+        ck.add("R1.per_sample", _rel(per_sample, c["per_sample"]), 1e-3)
+        per_sample.mean().backward()
+        ck.add("R1.norms", _norm_errs({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], "strict.R1"), 4e-3)
+
+        c = fx["dstep16_case"]
+        real2, fake = c["real_aug2"].float().cuda(), c["fake_aug"].float().cuda()
+        n = fake.shape[0]
+        D.zero_grad()
+        d_all, view_r, view_f = T.discriminate(D, real2, fake)
+        P = SimpleNamespace(temp=0.1, lbd_a=1.0, distributed=False)
+        d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+        r1 = T.r1_loss(D, real2[:n], lambda t: t)
+        ck.add("dstep16.d_loss", abs(float(d_loss.detach()) - c["d_loss"]) / abs(c["d_loss"]), 1e-3)
+        ck.add("dstep16.r1", abs(float(r1.detach()) - c["r1"]) / abs(c["r1"]), 1e-3)
+        (d_loss + aux["penalty"] + 0.05 * r1).backward()
+        grads = {k: p.grad for k, p in D.named_parameters()}
+        ck.add("dstep16.norms", _norm_errs(grads, c["grad_norms"], "strict.dstep16"), 2e-3)
+        ck.add("dstep16.total_norm", abs(_total_norm(grads.values()) - c["total_grad_norm"]) / c["total_grad_norm"], 1e-3)
+
+        c = fx["g_case"]
+        G.zero_grad()
+        noises = [t.cuda() for t in c["noises"]]
+        z_mix = c["z_mix"].cuda()
+        orig = G.sample_latent
+        G.sample_latent = lambda k: z_mix
+        try:
+            torch.set_rng_state(c["rng_state_after_zmix"])
+            img = G(c["z"].cuda(), style_mix=0.9, noise=noises)
+        finally:
+            G.sample_latent = orig
+        ck.add("G.image", _rel(img, c["image"]), 1e-3)
+        (img * c["c_img"].cuda()).sum().backward()
+        ck.add("G.norms", _norm_errs({k: p.grad for k, p in G.named_parameters()}, _no_noise(c["grad_norms"]), "strict.G"), 2e-3)
+    ck.finish()
+
+
 def test_eager_gpu_yardstick_timing(models):
     """Not a parity check: times the D-step objective (n = 64, contrastive + L_dis + R1, forward + double backward)
     through this library and through the oracle's torch ops on the same GPU (cuDNN / cuBLAS, TF32 allowed = what the

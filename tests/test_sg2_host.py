@@ -205,6 +205,41 @@ def test_product_generator_host_logic(fx, states):
         _close(G(c["z"], style_mix=0.0, noise=c["noises"]), c["image_nomix"], 1e-4, "image (no mixing)")
 
 
+@pytest.mark.parametrize("exact_weights", [True, False])
+def test_product_strict_precision_host_logic(fx, states, exact_weights):
+    """The full strict precision mode (contrad_b200/precision.py): every GEMM Function evaluates hi/lo-split operands over
+    a concatenated reduction axis.  With the kernel stand-ins (fp32 torch) the discriminator, the R1 double backward and the
+    generator must reproduce the reference fixtures as in the default mode; exact_weights=False keeps the real TF32
+    rounding inside the split (hi + lo of genuinely rounded parts), i.e. the arithmetic the tensor core will see."""
+    from contrad_b200 import precision
+    from contrad_b200.training.gan import stylegan2 as T
+    with CK.patched(exact_weights=exact_weights), precision.strict("full"):
+        G, D = _product_models(states, fx["size"])
+        c = fx["d_case"]
+        x = c["x"].clone().requires_grad_(True)
+        d, aux = D(x, projection=True, projection2=True, penultimate=True)
+        _close(d, c["d"], 1e-4, "strict d"); _close(aux["projection"], c["projection"], 1e-4, "strict projection")
+        ((d * c["c_d"]).sum() + (aux["projection"] * c["c1"]).sum() + (aux["projection2"] * c["c2"]).sum()).backward()
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, c["grad_norms"], 1e-3, "strict D")
+        D.zero_grad()
+        c = fx["r1_case"]
+        per_sample = T.r1_per_sample(D, c["x"].clone(), lambda t: t)
+        _close(per_sample, c["per_sample"], 1e-3, "strict R1 per sample")
+        per_sample.mean().backward()
+        _check_norms({k: p.grad for k, p in D.named_parameters()}, {k: n for k, n in c["grad_norms"].items() if n > 0},
+                     2e-3, "strict R1")
+        c = fx["g_case"]
+        torch.manual_seed(c["mix_seed"])
+        img = G(c["z"], style_mix=0.9, noise=c["noises"])
+        _close(img, c["image"], 1e-4, "strict image")
+        (img * c["c_img"]).sum().backward()
+        # NoiseInjection weights are left out: d/d(noise weight) = sum(dpre * noise) is a sum of ~1e5 signed terms in which
+        # single LeakyReLU sign flips show (a 1e-6 perturbation of one layer's output moves these norms by +-30 %), so they
+        # are only comparable between bit-identical forward passes - the GPU tests exclude them for the same reason
+        want = {k: n for k, n in c["grad_norms"].items() if not k.endswith("noise.weight")}
+        _check_norms({k: p.grad for k, p in G.named_parameters()}, want, 1e-3, "strict G")
+
+
 def test_ema_generator_is_not_served_stale_weights(fx, states):
     """the reference's `utils.accumulate` (utils.py:130-143) updates g_ema through
     `param.data.mul_().add_()`, which leaves `param._version` untouched; a no-grad forward of g_ema after such an
