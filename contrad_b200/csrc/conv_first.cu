@@ -22,74 +22,124 @@ constexpr int kRows = 4;        // output rows per CTA
 constexpr int kCols = 32;       // output columns per CTA
 
 // wmat: [64][27] with column ci*9 + kh*3 + kw (the OIHW weight / sigma), bias [64]
+//
+// PERSISTENT CTAs (round 2): the grid is a few CTAs per SM, each walking a strided list of (image, 4-row x 32-column)
+// tiles.  The 27 x 64 weight block is transposed into shared memory ONCE per CTA (round 1 re-read it with a 108-byte
+// stride in every one of the 12 288 CTAs of a B = 1536 launch), the halo tile of the NEXT iteration is fetched into
+// registers before the FMA loop and parked in the other half of a shared-memory double buffer after it, so the global
+// loads of tile i+1 overlap the arithmetic and the stores of tile i, with one CTA barrier per tile.
+constexpr int kFwdXsElems = 3 * (kRows + 2) * (kCols + 2);                  // 612 image values (+halo) per tile
+constexpr int kFwdXsPerThread = (kFwdXsElems + kThreads - 1) / kThreads;     // 3
+
 __global__ void __launch_bounds__(kThreads)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ sigma,
-                      const float* __restrict__ bias, float* __restrict__ y, int H, int W, float slope,
+                      const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W, float slope,
                       int round_out, float in_scale, float in_shift) {
     // row stride 36 floats (144 B): the 10 input values of a thread start at a 16-byte boundary (seg = 0, 8, 16, 24), so
     // they are two LDS.128 + one LDS.64 instead of ten LDS.32 - the shared-memory pipe, not the FMA pipe, was the
     // busier one (22 wavefronts per 96 FMAs per warp and (ci, kh) step; now 15)
-    __shared__ __align__(16) float xs[3][kRows + 2][kCols + 4];
+    __shared__ __align__(16) float xs[2][3][kRows + 2][kCols + 4];
     __shared__ __align__(16) float ws[27][kCo];
-    const int b = blockIdx.z;
-    const int h0 = blockIdx.y * kRows;
-    const int w0 = blockIdx.x * kCols;
+    const int tiles_w = (W + kCols - 1) / kCols, tiles_h = (H + kRows - 1) / kRows;
+    const int ntiles = tiles_w * tiles_h * B;
     const float inv_sigma = sigma ? sigma[1] : 1.f;
     for (int i = threadIdx.x; i < 27 * kCo; i += kThreads) {        // lanes along co: conflict-free shared stores
         int t = i / kCo, co = i % kCo;
         ws[t][co] = __ldg(w + co * 27 + t) * inv_sigma;
     }
-    for (int i = threadIdx.x; i < 3 * (kRows + 2) * (kCols + 2); i += kThreads) {
-        int c = i / ((kRows + 2) * (kCols + 2));
-        int r = (i / (kCols + 2)) % (kRows + 2);
-        int cc = i % (kCols + 2);
-        int hh = h0 + r - 1, ww = w0 + cc - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-            v = __ldg(x + ((size_t)(b * 3 + c) * H + hh) * W + ww) * in_scale + in_shift;
-        xs[c][r][cc] = v;
+    // this thread's slots of the halo tile (tile independent)
+    int sc[kFwdXsPerThread], sr[kFwdXsPerThread], scc[kFwdXsPerThread];
+#pragma unroll
+    for (int k = 0; k < kFwdXsPerThread; ++k) {
+        const int i = threadIdx.x + k * kThreads;
+        sc[k] = i / ((kRows + 2) * (kCols + 2));
+        sr[k] = (i / (kCols + 2)) % (kRows + 2);
+        scc[k] = i % (kCols + 2);
     }
-    __syncthreads();
+    auto origin = [&](int tile, int& b, int& h0, int& w0) {
+        w0 = (tile % tiles_w) * kCols;
+        const int rest = tile / tiles_w;
+        h0 = (rest % tiles_h) * kRows;
+        b = rest / tiles_h;
+    };
+    auto fetch = [&](int tile, float (&v)[kFwdXsPerThread]) {
+        int b, h0, w0;
+        origin(tile, b, h0, w0);
+#pragma unroll
+        for (int k = 0; k < kFwdXsPerThread; ++k) {
+            v[k] = 0.f;
+            if (threadIdx.x + k * kThreads < kFwdXsElems) {
+                const int hh = h0 + sr[k] - 1, ww = w0 + scc[k] - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                    v[k] = __ldg(x + ((size_t)(b * 3 + sc[k]) * H + hh) * W + ww) * in_scale + in_shift;
+            }
+        }
+    };
+    auto park = [&](int buf, const float (&v)[kFwdXsPerThread]) {
+#pragma unroll
+        for (int k = 0; k < kFwdXsPerThread; ++k)
+            if (threadIdx.x + k * kThreads < kFwdXsElems) xs[buf][sc[k]][sr[k]][scc[k]] = v[k];
+    };
     const int cg = threadIdx.x & 15;          // channels 4cg .. 4cg+3
     const int pg = threadIdx.x >> 4;          // 16 pixel groups: row = pg/4, 8-column segment = pg%4
     const int row = pg >> 2, seg = (pg & 3) * 8;
-    float acc[8][4];
     const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cg) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    {
+        float v[kFwdXsPerThread];
+        fetch(tile, v);
+        park(0, v);
+    }
+    __syncthreads();
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int next = tile + gridDim.x;
+        float nv[kFwdXsPerThread];
+        if (next < ntiles) fetch(next, nv);                        // in flight during the FMA loop below
+        float acc[8][4];
 #pragma unroll
-    for (int p = 0; p < 8; ++p) { acc[p][0] = bv.x; acc[p][1] = bv.y; acc[p][2] = bv.z; acc[p][3] = bv.w; }
+        for (int p = 0; p < 8; ++p) { acc[p][0] = bv.x; acc[p][1] = bv.y; acc[p][2] = bv.z; acc[p][3] = bv.w; }
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
+        for (int ci = 0; ci < 3; ++ci) {
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const float* src = &xs[ci][row + kh][seg];
-            const float4 i0 = *reinterpret_cast<const float4*>(src), i1 = *reinterpret_cast<const float4*>(src + 4);
-            const float2 i2 = *reinterpret_cast<const float2*>(src + 8);
-            const float in[10] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y};
+            for (int kh = 0; kh < 3; ++kh) {
+                const float* src = &xs[buf][ci][row + kh][seg];
+                const float4 i0 = *reinterpret_cast<const float4*>(src), i1 = *reinterpret_cast<const float4*>(src + 4);
+                const float2 i2 = *reinterpret_cast<const float2*>(src + 8);
+                const float in[10] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y};
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float4 wv = *reinterpret_cast<const float4*>(&ws[ci * 9 + kh * 3 + kw][cg * 4]);
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&ws[ci * 9 + kh * 3 + kw][cg * 4]);
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    acc[p][0] += in[p + kw] * wv.x; acc[p][1] += in[p + kw] * wv.y;
-                    acc[p][2] += in[p + kw] * wv.z; acc[p][3] += in[p + kw] * wv.w;
+                    for (int p = 0; p < 8; ++p) {
+                        acc[p][0] += in[p + kw] * wv.x; acc[p][1] += in[p + kw] * wv.y;
+                        acc[p][2] += in[p + kw] * wv.z; acc[p][3] += in[p + kw] * wv.w;
+                    }
                 }
             }
         }
-    }
-    const int hh = h0 + row;
-    if (hh >= H) return;
+        int b, h0, w0;
+        origin(tile, b, h0, w0);
+        const int hh = h0 + row;
+        if (hh < H) {
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        const int ww = w0 + seg + p;
-        if (ww >= W) continue;
-        float o[4];
+            for (int p = 0; p < 8; ++p) {
+                const int ww = w0 + seg + p;
+                if (ww >= W) continue;
+                float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float v = acc[p][e];
-            v = v > 0.f ? v : v * slope;
-            o[e] = round_out ? round_tf32(v) : v;
+                for (int e = 0; e < 4; ++e) {
+                    float v = acc[p][e];
+                    v = v > 0.f ? v : v * slope;
+                    o[e] = round_out ? round_tf32(v) : v;
+                }
+                *reinterpret_cast<float4*>(y + (((size_t)b * H + hh) * W + ww) * kCo + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            }
         }
-        *reinterpret_cast<float4*>(y + (((size_t)b * H + hh) * W + ww) * kCo + cg * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        if (next < ntiles) park(buf ^ 1, nv);
+        __syncthreads();      // next tile visible; everybody is done reading xs[buf] (refilled two iterations from now)
     }
 }
 
@@ -360,7 +410,10 @@ conv_first_wgrad_v2_kernel(const float* __restrict__ x, const float* __restrict_
 }
 
 int wgrad_variant() {
-    static const int v = []() { const char* e = getenv("CB200_CONV_FIRST_WGRAD"); return (e && e[0] == '2') ? 2 : 1; }();
+    // default = the second mapping (nine taps of one input channel per thread, sliding register window): measured 3-8 %
+    // faster than the first at B = 192 / 512 / 1536 (tools/bench_conv_first.py, round 2); CB200_CONV_FIRST_WGRAD=1 selects
+    // the first one for A/B runs
+    static const int v = []() { const char* e = getenv("CB200_CONV_FIRST_WGRAD"); return (e && e[0] == '1') ? 1 : 2; }();
     return v;
 }
 
@@ -385,8 +438,19 @@ extern "C" int cb200_conv_first_fwd(const float* x, const float* w, const float*
                                     void* stream) {
     CB200_CHECK_ARG(B > 0 && H > 0 && W > 0, "conv_first_fwd: empty input");
     CB200_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0, "conv_first_fwd: y must be 16-byte aligned");
-    dim3 grid((W + kCols - 1) / kCols, (H + kRows - 1) / kRows, B);
-    conv_first_fwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, sigma, bias, y, H, W, slope,
+    const long long ntiles = (long long)((W + kCols - 1) / kCols) * ((H + kRows - 1) / kRows) * B;
+    CB200_CHECK_ARG(ntiles < (1LL << 31), "conv_first_fwd: too many tiles");
+    static const int per_sm = []() {          // resident CTAs per SM (80 registers x 256 threads -> 3); env override for A/B runs
+        const char* e = getenv("CB200_CONV_FIRST_FWD_CTAS");
+        if (e) return atoi(e);
+        int n = 3;
+#if defined(__CUDACC__)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_first_fwd_kernel, kThreads, 0) != cudaSuccess || n < 1) n = 3;
+#endif
+        return n;
+    }();
+    const int grid = (int)(ntiles < (long long)per_sm * 148 ? ntiles : (long long)per_sm * 148);
+    conv_first_fwd_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, sigma, bias, y, B, H, W, slope,
                                                                                     round_out, in_scale, in_shift);
     CB200_COUNT_LAUNCH();
     CB200_CHECK_LAUNCH("conv_first_fwd");

@@ -24,6 +24,11 @@ _COMPAT = os.path.join(_HERE, "compat")
 _ALIASES = {
     "augment": "contrad_b200.augment",
     "augment.layers": "contrad_b200.augment.layers",
+    # the reference's augment submodules: their classes live in one module here (`from augment.spatial import CutOut`,
+    # `from augment.color_jitter import ColorJitterLayer` keep working; `augment.utils.rgb2hsv / hsv2rgb` are not mirrored -
+    # the colour-space round trip only exists inside the fused kernel)
+    "augment.spatial": "contrad_b200.augment.layers",
+    "augment.color_jitter": "contrad_b200.augment.layers",
     "training": "contrad_b200.training",
     "training.criterion": "contrad_b200.training.criterion",
     "training.gan": "contrad_b200.training.gan",

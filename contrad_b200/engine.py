@@ -64,13 +64,14 @@ def allreduce_gradients(model, params=None, group=None, flat=None):
     if not params:
         return
     grads = [p.grad for p in params]
-    total = sum(g.numel() for g in grads)
+    pad = lambda n: (n + 31) // 32 * 32                  # every view starts on a 128-byte boundary (the fused Adam kernel
+    total = sum(pad(g.numel()) for g in grads)           # reads gradients as float4); the padding stays zero for ever
     if flat is None or flat.numel() != total or flat.device != grads[0].device:
-        flat = torch.empty(total, device=grads[0].device, dtype=grads[0].dtype)
+        flat = torch.zeros(total, device=grads[0].device, dtype=grads[0].dtype)
     views, off = [], 0
     for g in grads:
         views.append(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+        off += pad(g.numel())
     torch._foreach_copy_(views, grads)
     if dist.get_backend(group) == "nccl":
         dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)

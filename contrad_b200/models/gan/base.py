@@ -77,6 +77,38 @@ class TinyDiscriminator(nn.Module):
         self.l2 = SNLinear(d_hidden, 1, init=init)
 
 
+class LinearDiscriminator(nn.Module):
+    """models/gan/base.py:36-51 (linear evaluation / fine-tuning scripts; a plain nn.Linear head, no kernel of this
+    library is involved)."""
+
+    def __init__(self, n_features, n_classes=1):
+        super().__init__()
+        self.n_features, self.n_classes = n_features, n_classes
+        self.linear = nn.Linear(n_features, 1)
+        if n_classes > 1:
+            self.linear_y = nn.Embedding(n_classes, n_features)
+
+    def forward(self, inputs, y=None):
+        d = self.linear(inputs)
+        if y is not None:
+            d = d + (inputs * self.linear_y(y)).sum(1, keepdim=True)
+        return d
+
+
+class LinearWrapper(nn.Linear):
+    """models/gan/base.py:54-59 (`test_lineval.py`)."""
+
+    def forward(self, inputs, y=None):
+        return super().forward(inputs)
+
+
+class NullDiscriminator(nn.Module):
+    """models/gan/base.py:62-68."""
+
+    def forward(self, inputs, y=None):
+        return inputs.sum(1, keepdim=True)
+
+
 def projection(D, inputs):
     """models/gan/base.py:73-76 (used by training/gan/simclr_only.py): the projection head's output; `d.mean() * 0`
     keeps the unused linear head in the graph so that DDP finds a gradient for every parameter."""
