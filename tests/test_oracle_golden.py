@@ -258,3 +258,22 @@ def test_diffaug_matches_reference(golden_dir):
         (y * case["dy"]).sum().backward()
         assert torch.allclose(y, case["y"], atol=1e-6, rtol=0), (case["policy"], (y - case["y"]).abs().max())
         assert torch.allclose(x.grad, case["dx"], atol=2e-6, rtol=1e-5), case["policy"]
+
+
+def test_reference_copy_is_unmodified_and_runs_one_cpu_step():
+    """oracle/_ref (the copy of the reference that bench.py's `--impl reference`, `cpu_baseline` and `eager_gpu_baseline`
+    legs execute; made by oracle/make_ref.py) must be byte-identical to its manifest, and the CPU driver must complete a
+    step of the unmodified modules with finite losses.  Skipped when neither the copy nor /root/reference exists."""
+    import os
+    import numpy as np
+    import pytest
+    from oracle import make_ref, ref_import, ref_runner
+    if not os.path.isdir(os.path.join(make_ref.DST, "augment")):
+        if not os.path.isdir(os.path.join(make_ref.SRC, "augment")):
+            pytest.skip("reference sources not available")
+        make_ref.make(quiet=True)
+    assert make_ref.verify()
+    r = ref_runner.run_cpu(1, 0, batch=8, threads=2)
+    assert r["steps"] == 1 and r["batch"] == 8 and all(np.isfinite(v) for v in r["last_losses"]), r
+    assert abs(r["last_losses"][1] - 2 * np.log(2)) < 0.05          # L_dis at initialisation
+    ref_import.deactivate()
