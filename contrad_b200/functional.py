@@ -602,6 +602,7 @@ class GSNDCGANFn(Function):
         out = K.g_final_fwd(pre, b4)
         ctx.strict = strict
         ctx.meta = (sh, sw, sync, counts, [tuple(w.shape) for w in convs])
+        ctx.w_lin = w_lin if ctx.needs_input_grad[1] else None      # only a latent that asks for a gradient needs it (below)
         ctx.save_for_backward(zr, w4, g0, g1, g2, g3, out, *xs, *acts, *stats, *fpacks)
         return out
 
@@ -647,6 +648,15 @@ class GSNDCGANFn(Function):
         else:
             grads[2] = K.gemm_tn_wgrad(dh0, zr)
         grads[3] = K.colsum(dh0)
+        if ctx.needs_input_grad[1]:
+            # dL/dz = dh0 @ W_lin (latent optimisation / projection into the latent space; the training loop never asks: z
+            # is sampled without grad, models/gan/sndcgan.py:50-52)
+            wt = ctx.w_lin.detach().t().contiguous()                                   # [nz, 8192]
+            if ctx.strict:
+                hi, lo = _hi_lo(wt)
+                grads[1] = K.gemm_nt(K.split_tf32(dh0, 0), torch.cat([hi, hi, lo], dim=1).contiguous())
+            else:
+                grads[1] = K.gemm_nt(K.round_tf32_(dh0), K.round_tf32(wt))
         return tuple(grads)
 
 

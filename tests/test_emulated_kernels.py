@@ -666,3 +666,22 @@ def test_tensor_core_contrastive_formulation_matches_reference_fixtures(golden_d
                 assert torch.allclose(g, w, atol=2e-5 * float(w.abs().max()) + 1e-7, rtol=1e-4), n
             l3 = ContrastiveTCFn.apply(torch.cat([a, b]), n, 0, 0.5)
             assert abs(float(l3) - case["nt_xent_t05"]) < 2e-5 * abs(case["nt_xent_t05"])
+
+
+def test_generator_latent_gradient_vs_oracle():
+    """GSNDCGANFn.backward returns d loss / d z when the latent asks for it (latent optimisation); checked in
+    the full strict precision mode, where the batch-of-4 BatchNorm statistics do not amplify TF32 rounding."""
+    import tests.cpu_tc_standins as TC
+    from contrad_b200 import precision
+    from contrad_b200.models.gan.sndcgan import G_SNDCGAN
+    sd_g = O.make_g_state(ngf=64, nz=16, generator=torch.Generator().manual_seed(5))
+    torch.manual_seed(1)
+    z0, c = torch.empty(4, 16).uniform_(-1, 1), torch.randn(4, 3, 32, 32)
+    with emulated(), TC.patched(), precision.strict("full"):
+        G = G_SNDCGAN((32, 32, 3), ngf=64, nz=16)
+        G.load_state_dict(sd_g); G.train()
+        z = z0.clone().requires_grad_(True)
+        (G(z) * c).sum().backward()
+    zo = z0.clone().requires_grad_(True)
+    (O.g_sndcgan_forward({k: v.clone() for k, v in sd_g.items()}, zo, ngf=64) * c).sum().backward()
+    assert float((z.grad - zo.grad).norm() / zo.grad.norm()) < 2e-3

@@ -524,6 +524,99 @@ def test_strict_precision_meets_fixed_tolerances(fx, models):
     ck.finish()
 
 
+def _seeded_states(size, small32, cm, seeds):
+    from oracle import stylegan2_oracle as SO
+    kw = dict(small32=True) if small32 else dict(small32=False, channel_multiplier=cm)
+    sd_d = SO.make_d_state(size, d_hidden=512, generator=torch.Generator().manual_seed(seeds[0]), **kw)
+    sd_g = SO.make_g_state(size, generator=torch.Generator().manual_seed(seeds[1]), **kw)
+    gen = torch.Generator().manual_seed(seeds[2])
+    for sd in (sd_d, sd_g):
+        for k in sd:
+            if k.endswith(".bias") and sd[k].abs().sum() == 0:
+                sd[k] = 0.1 * torch.randn(sd[k].shape, generator=gen)
+            if k.endswith("noise.weight"):
+                sd[k] = 0.1 * torch.randn(1, generator=gen)
+    return sd_d, sd_g
+
+
+@pytest.mark.parametrize("mode", [0, "full"])
+def test_config4_dstep_at_batch_64_vs_oracle(mode):
+    """BASELINE config 4 at its REAL batch (c10_style64.gin: n = 64, D sees 64 fakes and 128 real views, R1 on 64 images,
+    --lbd_r1 0.1 --no_lazy): the D-step objective of train_stylegan2_contraD.py:207-236 on already-augmented inputs against
+    the fp32 CPU oracle (oracle/stylegan2_oracle.py, pinned on the reference fixtures at n = 4 / 16).  Default precision:
+    loss scalars 1e-3 (north_star), R1 and the total D gradient norm 1e-2; full strict mode: all of them 1e-3."""
+    from oracle import stylegan2_oracle as SO
+    from contrad_b200 import precision
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import stylegan2 as T
+    size, n = 32, 64
+    sd_d, _ = _seeded_states(size, True, None, (41, 42, 43))
+    torch.manual_seed(44)
+    real2, fake = torch.rand(2 * n, 3, size, size), torch.rand(n, 3, size, size)
+    leaf = {k: (v.clone().requires_grad_(True) if not k.endswith(".kernel") else v) for k, v in sd_d.items()}
+    d_loss_o, pen_o, _, _ = SO.gd_losses(leaf, size, real2, fake)
+    r1_o = SO.r1_penalty(leaf, real2[:n], size).mean()
+    (d_loss_o + pen_o + 0.05 * r1_o).backward()                       # 0.5 * lbd_r1 * r1 * d_reg_every with lbd_r1 = 0.1
+    want = _total_norm([v.grad for v in leaf.values() if v.requires_grad and v.grad is not None])
+    _, D = get_architecture("stylegan2", (size, size, 3))
+    D.load_state_dict(sd_d, strict=True)
+    D.cuda().train()
+    ck = _Checks("config4_b64.%s" % mode)
+    with precision.strict(mode):
+        d_all, view_r, view_f = T.discriminate(D, real2.cuda(), fake.cuda())
+        P = SimpleNamespace(temp=0.1, lbd_a=1.0, distributed=False)
+        d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+        r1 = T.r1_loss(D, real2[:n].cuda(), lambda t: t)
+        (d_loss + aux["penalty"] + 0.05 * r1).backward()
+    tol = 1e-3 if mode == "full" else 1e-2
+    ck.add("d_loss", abs(float(d_loss.detach()) - float(d_loss_o)) / abs(float(d_loss_o)), 1e-3)
+    ck.add("penalty", abs(float(aux["penalty"].detach()) - float(pen_o)) / abs(float(pen_o)), 1e-3)
+    ck.add("r1", abs(float(r1.detach()) - float(r1_o)) / abs(float(r1_o)), tol)
+    ck.add("total_norm", abs(_total_norm([p.grad for p in D.parameters()]) - want) / want, tol)
+    ck.finish()
+
+
+def test_config5_per_replica_batch_vs_oracle():
+    """BASELINE config 5 per replica (b64 over 8 GPUs = 8 images of 512x512 per replica, `stylegan2_512`): what ONE
+    DataParallel replica evaluates in the D step - D on 8 fakes and on 16 real views (two minibatch-stddev groupings) and
+    the `simclr` augmentation at 512x512 - against the fp32 CPU oracle.  D outputs and embeddings 1e-2 of their scale
+    (single-pass TF32 through 7 ResBlocks), L_dis 1e-3; the augmentation against the oracle chain on the same draws 2e-5."""
+    from oracle import contrad_oracle as CO
+    from oracle import stylegan2_oracle as SO
+    from contrad_b200.functional import AugmentSimCLRFn
+    from contrad_b200.models.gan import get_architecture
+    from contrad_b200.training.gan import stylegan2 as T
+    size, n = 512, 8
+    sd_d, _ = _seeded_states(size, False, 1.0, (51, 52, 53))
+    torch.manual_seed(54); np.random.seed(54)
+    real, fake = torch.rand(n, 3, size, size), torch.rand(n, 3, size, size)
+    # the large-image augmentation on explicit draws (RRC scale (0.08, 1), jitter 0.8 / 0.8 / 0.8 / 0.2: afhq_dog_style64.gin)
+    params, order = CO.sample_simclr_params(n, size, size, scale=(0.08, 1.0), brightness=0.8, contrast=0.8, saturation=0.8,
+                                            hue=0.2)
+    aug_o = CO.augment_simclr(real, params, order)
+    aug = AugmentSimCLRFn.apply(real.cuda(), CO.pack_params(params).cuda(), order)
+    ck = _Checks("config5_replica")
+    ck.add("augment_512", float((aug.cpu() - aug_o).abs().max()), 2e-5)
+    real2 = torch.cat([aug_o, aug_o.flip(3)])
+    with torch.no_grad():
+        d_gen_o, others_o, fakes_o = SO.d_forward(sd_d, fake, size, sg_linear=True)
+        d_rs_o, views_o, reals_o = SO.d_forward(sd_d, real2, size, sg_linear=True)
+    pen_o = F.softplus(d_gen_o).mean() + F.softplus(-d_rs_o[:n]).mean()
+    _, D = get_architecture("stylegan2_512", (size, size, 3))
+    D.load_state_dict(sd_d, strict=True)
+    D.cuda().train()
+    with torch.no_grad():
+        d_all, view_r, view_f = T.discriminate(D, real2.cuda(), fake.cuda())
+    ck.add("d_real", _rel(d_all[0], d_rs_o[:n]), 1e-2)
+    ck.add("d_gen", _rel(d_all[1], d_gen_o), 1e-2)
+    ck.add("views_real", _rel(view_r[0], F.normalize(views_o)[:n]), 1e-2)
+    ck.add("fakes", _rel(view_f[-1], F.normalize(fakes_o)), 1e-2)
+    P = SimpleNamespace(temp=0.1, lbd_a=1.0, distributed=False)
+    _, aux = T.loss_D_fn(P, d_all, view_r, view_f)
+    ck.add("penalty", abs(float(aux["penalty"]) - float(pen_o)) / abs(float(pen_o)), 1e-3)
+    ck.finish()
+
+
 def test_eager_gpu_yardstick_timing(models):
     """Not a parity check: times the D-step objective (n = 64, contrastive + L_dis + R1, forward + double backward)
     through this library and through the oracle's torch ops on the same GPU (cuDNN / cuBLAS, TF32 allowed = what the
