@@ -13,6 +13,16 @@ from . import kernels as K
 from . import staging
 
 
+def _grad_operand(p):
+    """The gradient as the kernel wants it: contiguous and 16-byte aligned (float4 loads).  nn.DataParallel hands the
+    master parameters gradients that are views into its coalesced reduce buffers at arbitrary offsets - those are
+    copied once; everything the library itself produces is already aligned."""
+    g = p.grad
+    if not g.is_contiguous() or g.data_ptr() % 16:
+        g = g.contiguous() if not g.is_contiguous() else g.clone()
+    return g
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1:
@@ -45,8 +55,7 @@ class FusedAdam(torch.optim.Optimizer):
             return torch.tensor([group["lr"], 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t)], dtype=torch.float32)
 
         dev_hyper = staging.stage(hyper, params[0].device, shape=(3,), late=True)
-        entries = [(p, p.grad if p.grad.is_contiguous() else p.grad.contiguous(), s["exp_avg"], s["exp_avg_sq"])
-                   for p, s in zip(params, states)]
+        entries = [(p, _grad_operand(p), s["exp_avg"], s["exp_avg_sq"]) for p, s in zip(params, states)]
         K.adam_step(entries, dev_hyper, group["betas"][0], group["betas"][1], group["eps"], 0)
 
     @torch.no_grad()
@@ -71,11 +80,10 @@ class FusedAdam(torch.optim.Optimizer):
                 if step_no is None:
                     step_no = s
                 if s != step_no:                     # tensors with a different history: separate launch
-                    K.adam_step([(p, p.grad.contiguous(), state["exp_avg"], state["exp_avg_sq"])], group["lr"],
+                    K.adam_step([(p, _grad_operand(p), state["exp_avg"], state["exp_avg_sq"])], group["lr"],
                                 group["betas"][0], group["betas"][1], group["eps"], s)
                     continue
-                entries.append((p, p.grad if p.grad.is_contiguous() else p.grad.contiguous(), state["exp_avg"],
-                                state["exp_avg_sq"]))
+                entries.append((p, _grad_operand(p), state["exp_avg"], state["exp_avg_sq"]))
             if entries:
                 K.adam_step(entries, group["lr"], group["betas"][0], group["betas"][1], group["eps"], step_no)
         return loss
