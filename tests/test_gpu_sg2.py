@@ -16,6 +16,7 @@ from types import SimpleNamespace
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from tests import cpu_kernels as CK
 
@@ -542,7 +543,8 @@ def _seeded_states(size, small32, cm, seeds):
 @pytest.mark.parametrize("mode", [0, "full"])
 def test_config4_dstep_at_batch_64_vs_oracle(mode):
     """BASELINE config 4 at its REAL batch (c10_style64.gin: n = 64, D sees 64 fakes and 128 real views, R1 on 64 images,
-    --lbd_r1 0.1 --no_lazy): the D-step objective of train_stylegan2_contraD.py:207-236 on already-augmented inputs against
+    --lbd_r1 0.1 --no_lazy): the D-step objective of train_stylegan2_contraD.py:207-236 on SimCLR views (oracle chain) of
+    diverse synthetic images against
     the fp32 CPU oracle (oracle/stylegan2_oracle.py, pinned on the reference fixtures at n = 4 / 16).  Default precision:
     loss scalars 1e-3 (north_star), R1 and the total D gradient norm 1e-2; full strict mode: all of them 1e-3."""
     from oracle import stylegan2_oracle as SO
@@ -551,8 +553,18 @@ def test_config4_dstep_at_batch_64_vs_oracle(mode):
     from contrad_b200.training.gan import stylegan2 as T
     size, n = 32, 64
     sd_d, _ = _seeded_states(size, True, None, (41, 42, 43))
-    torch.manual_seed(44)
-    real2, fake = torch.rand(2 * n, 3, size, size), torch.rand(n, 3, size, size)
+    from oracle import contrad_oracle as CO
+    torch.manual_seed(44); np.random.seed(44)
+
+    def fields(m):          # diverse low-frequency images (white noise collapses every embedding onto one point: the
+        base = F.interpolate(torch.rand(m, 3, 4, 4), size=(size, size), mode="bilinear", align_corners=False)   # contrastive
+        return (0.15 + 0.7 * base + 0.1 * torch.rand(m, 3, size, size)).clamp(0, 1)      # gradient is then a 70x smaller residual)
+
+    imgs = fields(n)
+    p_r, o_r = CO.sample_simclr_params(2 * n, size, size)
+    real2 = CO.augment_simclr(torch.cat([imgs, imgs]), p_r, o_r)          # two SimCLR views of every real image
+    p_f, o_f = CO.sample_simclr_params(n, size, size)
+    fake = CO.augment_simclr(fields(n), p_f, o_f)
     leaf = {k: (v.clone().requires_grad_(True) if not k.endswith(".kernel") else v) for k, v in sd_d.items()}
     d_loss_o, pen_o, _, _ = SO.gd_losses(leaf, size, real2, fake)
     r1_o = SO.r1_penalty(leaf, real2[:n], size).mean()
