@@ -545,8 +545,8 @@ def test_config4_dstep_at_batch_64_vs_oracle(mode):
     """BASELINE config 4 at its REAL batch (c10_style64.gin: n = 64, D sees 64 fakes and 128 real views, R1 on 64 images,
     --lbd_r1 0.1 --no_lazy): the D-step objective of train_stylegan2_contraD.py:207-236 on SimCLR views (oracle chain) of
     diverse synthetic images against
-    the fp32 CPU oracle (oracle/stylegan2_oracle.py, pinned on the reference fixtures at n = 4 / 16).  Default precision:
-    loss scalars 1e-3 (north_star), R1 and the total D gradient norm 1e-2; full strict mode: all of them 1e-3."""
+    the fp32 CPU oracle (oracle/stylegan2_oracle.py, pinned on the reference fixtures at n = 4 / 16).  Loss scalars
+    1e-3 (north_star) in both modes; total D gradient norm 2e-3 (default) / 1e-3 (full); R1 1e-2 / 2e-3."""
     from oracle import stylegan2_oracle as SO
     from contrad_b200 import precision
     from contrad_b200.models.gan import get_architecture
@@ -580,11 +580,12 @@ def test_config4_dstep_at_batch_64_vs_oracle(mode):
         d_loss, aux = T.loss_D_fn(P, d_all, view_r, view_f)
         r1 = T.r1_loss(D, real2[:n].cuda(), lambda t: t)
         (d_loss + aux["penalty"] + 0.05 * r1).backward()
-    tol = 1e-3 if mode == "full" else 1e-2
+    # measured on the B200 (profiles/sg2_parity_r2.json): d_loss 3e-6 / 1e-6, penalty 4e-6 / 3e-7, r1 1e-4 / 6e-4, total
+    # gradient norm 7e-5 / 2e-5 (default / full); R1 is a ~1e-3-sized double-backward quantity, hence its wider bar
     ck.add("d_loss", abs(float(d_loss.detach()) - float(d_loss_o)) / abs(float(d_loss_o)), 1e-3)
     ck.add("penalty", abs(float(aux["penalty"].detach()) - float(pen_o)) / abs(float(pen_o)), 1e-3)
-    ck.add("r1", abs(float(r1.detach()) - float(r1_o)) / abs(float(r1_o)), tol)
-    ck.add("total_norm", abs(_total_norm([p.grad for p in D.parameters()]) - want) / want, tol)
+    ck.add("r1", abs(float(r1.detach()) - float(r1_o)) / abs(float(r1_o)), 2e-3 if mode == "full" else 1e-2)
+    ck.add("total_norm", abs(_total_norm([p.grad for p in D.parameters()]) - want) / want, 1e-3 if mode == "full" else 2e-3)
     ck.finish()
 
 
