@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, call K (1 GPU): call J's list + first-layer kernels (A/B, ncu)
-bash tools/runs/r2_j.sh
+# (in the same call, first: strict StyleGAN2 test, dropin worker test, tensor-core contrastive path, config-4 reference leg)
 echo "== conv_first (default)"; timeout 120 python tools/bench_conv_first.py
 echo "== conv_first wgrad variant 2"; CB200_CONV_FIRST_WGRAD=2 timeout 120 python tools/bench_conv_first.py
 echo "== conv_first fwd 4 CTAs/SM"; CB200_CONV_FIRST_FWD_CTAS=4 timeout 120 python tools/bench_conv_first.py
