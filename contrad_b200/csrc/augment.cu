@@ -99,10 +99,11 @@ __device__ __forceinline__ Tap axis_tap(int o, int n, float s, float b) {
 // the division is the fast reciprocal (2 ulp) - the result feeds a piecewise-linear colour wheel with slope <= 6, so
 // 1e-7 in the turn fraction is far below the fp32 noise of the chain.  mx == 0 (a gray pixel) gives t = 0 -> hue 0 like
 // atan2(0, 0).
+template <int HV>
 __device__ __forceinline__ float hue_turns(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float t = __fdividef(mn, fmaxf(mx, 1e-30f));
+    const float t = HV >= 2 ? fast_div(mn, fmaxf(mx, 1e-30f)) : __fdividef(mn, fmaxf(mx, 1e-30f));
     const float u = t * t;
     float p = -0.00064527396948442972f;
     p = fmaf(p, u, 0.0034794815687994203f);
@@ -125,13 +126,16 @@ __device__ __forceinline__ float hue_turns(float y, float x) {
 // evaluated as t = sat(2 - d) with d the CIRCULAR distance (period 6) of 6 h to the channel's centre 3, 5, 1:
 // min(k, 4 - k) = 2 - |k - 2| and |k - 2| is that distance; for the centre 3 it never wraps.  Same function, 10 instead of
 // 18 instructions for the three channels (the chain is issue-bound, profiles/prof_r1_augment.md).
+// HV selects the build: 1 = first (all other kernels), 2 = guard-free reciprocals (bit-identical for inputs in range:
+// cmax + 1e-8 >= 1e-30; 8 instructions per pixel fewer incl. the predicate parking the guards caused).
+template <int HV = 1>
 __device__ __forceinline__ void hsv_jitter(float& r, float& g, float& b, float hshift, float fs, float fv) {
     float cmax = fmaxf(r, fmaxf(g, b));
     float cmin = fminf(r, fminf(g, b));
-    float hue = hue_turns(1.7320508075688772f * (g - b), 2.f * r - g - b);     // finite for finite inputs
+    float hue = hue_turns<HV>(1.7320508075688772f * (g - b), 2.f * r - g - b);     // finite for finite inputs
     // the reference zeroes non-finite hsv entries (utils.py:37): a NaN saturation is mapped to 0 by the __saturatef below
     // (it cannot be +-inf: cmin / (cmax + 1e-8) is finite or NaN), the value needs the explicit test (+inf -> 0)
-    const float sat = 1.f - __fdividef(cmin, cmax + 1e-8f);
+    const float sat = 1.f - (HV >= 2 ? fast_div(cmin, cmax + 1e-8f) : __fdividef(cmin, cmax + 1e-8f));
     const float val = isfinite(cmax) ? cmax : 0.f;
     float h = hue + hshift;
     h = h - floorf(h);
@@ -570,6 +574,167 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, v[m][c]);
+        }
+    }
+}
+
+// Second build of the same pipeline (CB200_AUGMENT_V=2).  SASS of the kernel above (profiles/prof_r2_augment.md: issue-
+// bound, 4 893 warp instructions per image) spends ~100 of its ~625 instructions per thread and image on the per-image
+// parameters: every thread forms eleven 64-bit addresses `params + k*B + b` and loads the same eleven values, and ~24 on
+// turning tap indices into shared-memory addresses (buffer parity * 3HW + row + column, then scale + base).  Here
+//   * twelve lanes of the last warp fetch the parameter column of image `it + 2` (one LDG each) and park it in a
+//     4-slot shared-memory ring before the iteration's barrier; everybody else reads its colour parameters with two
+//     broadcast LDS.128, the tap writers their crop parameters with two more;
+//   * the tap tables hold BYTE offsets, and the row entries already contain the offset of the ring buffer the image
+//     will arrive in, so a bilinear tap address is one three-input add (row + column + shared window base).
+// The arithmetic on the pixels is instruction for instruction the one above: outputs are bit-identical (test).  HV picks
+// the build of the HSV stage (see hsv_jitter; 2 is still bit-identical); the grayscale branch (taken by 20 % of the
+// images) is a real branch around its own store sequence instead of 20 predicated instructions for everybody.
+template <int S, int OCC, int HV>
+__global__ void __launch_bounds__(kMaxThreads, OCC)
+augment_simclr_fwd_cols2_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ params,
+                                int B, int order) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int HW = S * S, NPX = HW / kMaxThreads;
+    constexpr int kLoader0 = kMaxThreads - 32;                   // first lane of the parameter-loading warp
+    float* red = smem + 6 * HW;                                   // [2][32]
+    float4* xtap = reinterpret_cast<float4*>(red + 96);           // [2][S] {4*i0, 4*i1 (int bits), w0, w1}, flip folded in
+    float4* ytap = xtap + 2 * S;                                  // [2][S] {buffer + 4*S*i0, buffer + 4*S*i1 (bytes), w0, w1}
+    float* pslot = reinterpret_cast<float*>(ytap + 2 * S);        // [4][16] parameter columns: sx sy bx by | flip cj fc fh | fs fv gray order
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pslot + 64);
+    constexpr uint32_t img_bytes = (uint32_t)(3 * HW * sizeof(float));
+    const int j = threadIdx.x % S, i_first = (threadIdx.x / S) * NPX;
+    const int G = gridDim.x;
+    const int pl = (int)threadIdx.x - kLoader0;                   // parameter row this thread fetches (0..11), else none
+    const bool loader = pl >= 0 && pl < 12;
+
+    auto fetch_param = [&](int img) -> float {                    // loader lanes only
+        if (pl == 11) return order >= 0 ? (float)order : (__ldg(params + (size_t)11 * B + img) != 0.f ? 1.f : 0.f);
+        return __ldg(params + (size_t)pl * B + img);
+    };
+    auto write_taps = [&](int par, const float4 crop, float flip) {      // crop = {sx, sy, bx, by}
+        const int e = threadIdx.x;
+        if (e < S) {
+            const Tap a = axis_tap((flip < 0.f) ? (S - 1 - e) : e, S, crop.x, crop.z);
+            xtap[par * S + e] = make_float4(__int_as_float(a.i0 * 4), __int_as_float(a.i1 * 4), a.w0, a.w1);
+        } else if (e < 2 * S) {
+            const Tap a = axis_tap(e - S, S, crop.y, crop.w);
+            const int buf = par * (int)img_bytes;
+            ytap[par * S + e - S] = make_float4(__int_as_float(buf + a.i0 * (S * 4)), __int_as_float(buf + a.i1 * (S * 4)),
+                                                a.w0, a.w1);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        bar_init(&bars[0], 1);
+        bar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    int b = blockIdx.x;
+    if (loader && b < B) {
+        pslot[pl] = fetch_param(b);
+        if (b + G < B) pslot[16 + pl] = fetch_param(b + G);
+    }
+    __syncthreads();
+    if (b >= B) return;
+    if (threadIdx.x == 0) {
+        bar_expect_tx(&bars[0], img_bytes);
+        bulk_load(smem, x + (size_t)b * 3 * HW, img_bytes, &bars[0]);
+        if (b + G < B) {
+            bar_expect_tx(&bars[1], img_bytes);
+            bulk_load(smem + 3 * HW, x + (size_t)(b + G) * 3 * HW, img_bytes, &bars[1]);
+        }
+    }
+    if (threadIdx.x < 2 * S) write_taps(0, *reinterpret_cast<const float4*>(pslot), pslot[4]);
+    __syncthreads();
+
+    const char* sbytes = reinterpret_cast<const char*>(smem);
+    float* yb = y + (size_t)b * 3 * HW + i_first * S + j;
+    for (int it = 0; b < B; b += G, ++it, yb += (size_t)G * 3 * HW) {
+        const int par = it & 1;
+        const int nb = b + G;
+        // requests first: (loader lanes) the parameter column of image it + 2
+        float pv = 0.f;
+        const bool fetch = loader && nb + G < B;
+        if (fetch) pv = fetch_param(nb + G);
+        // this image's colour parameters, (tap writers) the crop parameters of the next image: shared-memory broadcasts
+        const float* ps = pslot + (it & 3) * 16;
+        const float4 c0 = *reinterpret_cast<const float4*>(ps + 4);      // flip cj_on fc fh
+        const float4 c1 = *reinterpret_cast<const float4*>(ps + 8);      // fs fv gray_on order
+        const float cj_on = c0.y, fc = c0.z, fs = c1.x, fv = c1.y, gray_on = c1.z;
+        const int ord = c1.w != 0.f ? 1 : 0;
+        const float hshift = c0.w * (255.f / 360.f);   // color_jitter.py:88, to 1 ulp (a true division costs ~8 issue slots)
+        const bool next_taps = nb < B && threadIdx.x < 2 * S;
+        bar_wait(&bars[par], (uint32_t)(it >> 1) & 1u);
+
+        // ---- gather (crop + flip) into registers
+        float v[NPX][3];
+        {
+            const float4 tx = xtap[par * S + j];
+            const int x0 = __float_as_int(tx.x), x1 = __float_as_int(tx.y);
+            const float4* yt = ytap + par * S + i_first;
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float4 ty = yt[m];
+                const int y0 = __float_as_int(ty.x), y1 = __float_as_int(ty.y);
+                const float* p00 = reinterpret_cast<const float*>(sbytes + (y0 + x0));
+                const float* p01 = reinterpret_cast<const float*>(sbytes + (y0 + x1));
+                const float* p10 = reinterpret_cast<const float*>(sbytes + (y1 + x0));
+                const float* p11 = reinterpret_cast<const float*>(sbytes + (y1 + x1));
+                const float w00 = tx.z * ty.z, w01 = tx.w * ty.z, w10 = tx.z * ty.w, w11 = tx.w * ty.w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    v[m][c] = p00[c * HW] * w00 + p01[c * HW] * w01 + p10[c * HW] * w10 + p11[c * HW] * w11;
+            }
+        }
+        float sums[3] = {0.f, 0.f, 0.f};
+        if (cj_on != 0.f) {          // uniform across the CTA
+            if (ord == 1) {
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) hsv_jitter<HV>(v[m][0], v[m][1], v[m][2], hshift, fs, fv);
+            }
+#pragma unroll
+            for (int m = 0; m < NPX; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) sums[c] += v[m][c];
+            block_sum3_partial(sums, red + par * 32);
+        }
+        if (next_taps) {
+            const float* pn = pslot + ((it + 1) & 3) * 16;
+            write_taps(par ^ 1, *reinterpret_cast<const float4*>(pn), pn[4]);
+        }
+        if (fetch) pslot[((it + 2) & 3) * 16 + pl] = pv;
+        __syncthreads();          // the only CTA barrier of the iteration (see the header comment of the kernel above)
+        if (threadIdx.x == 0 && nb + G < B) {
+            bar_expect_tx(&bars[par], img_bytes);
+            bulk_load(smem + par * 3 * HW, x + (size_t)(nb + G) * 3 * HW, img_bytes, &bars[par]);
+        }
+        if (cj_on != 0.f) {
+            block_sum3_total(sums, red + par * 32);
+            constexpr float inv = 1.f / (float)HW;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float mean = sums[c] * inv;
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) v[m][c] = clamp01((v[m][c] - mean) * fc + mean);
+            }
+            if (ord == 0) {
+#pragma unroll
+                for (int m = 0; m < NPX; ++m) hsv_jitter<HV>(v[m][0], v[m][1], v[m][2], hshift, fs, fv);
+            }
+        }
+        if (gray_on != 0.f) {        // uniform across the CTA
+#pragma unroll
+            for (int m = 0; m < NPX; ++m) {
+                const float l = 0.299f * v[m][0] + 0.587f * v[m][1] + 0.114f * v[m][2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, l);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < NPX; ++m)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) __stcs(yb + c * HW + m * S, v[m][c]);
         }
     }
 }
@@ -1085,7 +1250,23 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
         // 32x32: ncu showed the kernel occupancy-limited at 5 CTAs / SM by registers; the default build holds it to 40
         // registers (6 CTAs / SM, 4 bytes of spill); CB200_AUGMENT_OCC=5 selects the unconstrained build (A/B runs)
         static const int occ = []() { const char* e = getenv("CB200_AUGMENT_OCC"); return e ? atoi(e) : 6; }();
-        if (H == 32 && occ >= 6) {
+        // CB200_AUGMENT_V=2: parameters staged through shared memory + byte-offset tap tables (bit-identical outputs)
+        // (read per call - one getenv - so that one process can compare the two builds)
+        const char* ev = getenv("CB200_AUGMENT_V");
+        const int variant = ev ? atoi(ev) : 1;
+        if (variant == 2) {
+            const size_t smem2 = smem + 64 * sizeof(float);
+#define LAUNCH_COLS2(SZ, OC, HV, GRID)                                                                                   \
+    do {                                                                                                                 \
+        cudaFuncSetAttribute(augment_simclr_fwd_cols2_kernel<SZ, OC, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                             (int)smem2);                                                                                \
+        augment_simclr_fwd_cols2_kernel<SZ, OC, HV><<<GRID, kMaxThreads, smem2, st>>>(x, y, params, B, order);           \
+    } while (0)
+            const int g6 = B < sm_count * 6 ? B : sm_count * 6;
+            if (H == 32) LAUNCH_COLS2(32, 6, 2, g6);
+            else LAUNCH_COLS2(64, 1, 2, grid);
+#undef LAUNCH_COLS2
+        } else if (H == 32 && occ >= 6) {
             const int g6 = B < sm_count * 6 ? B : sm_count * 6;
             cudaFuncSetAttribute(augment_simclr_fwd_cols_kernel<32, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             augment_simclr_fwd_cols_kernel<32, 6><<<g6, kMaxThreads, smem, st>>>(x, y, params, B, order);

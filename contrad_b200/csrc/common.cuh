@@ -117,7 +117,17 @@ __device__ __forceinline__ float round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+
+// a / b through ONE MUFU.RCP + one multiply.  `__fdividef` is the same product in the normal range but brackets it
+// with a denormal guard (FSETP + two predicated FMUL by 2^24 per quotient); callers of this helper guarantee
+// |b| >= 1e-30, where the two are bit-identical.
+__device__ __forceinline__ float fast_div(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
+}
 #else
+inline float fast_div(float a, float b) { return __fdividef(a, b); }
 inline float4 ldg_stream4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 inline void stg_stream4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 inline float round_tf32(float x) {          // cvt.rna.tf32.f32: add half an ulp of the 10-bit mantissa, truncate

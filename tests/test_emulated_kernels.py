@@ -417,6 +417,38 @@ def test_emulated_fused_augment_persistent_ring_vs_oracle():
         assert torch.equal(y_mixed, y_cat)           # bit-equal, as on the B200
 
 
+def test_emulated_fused_augment_second_build_is_bit_identical(golden_dir, monkeypatch):
+    """CB200_AUGMENT_V=2 (parameters staged through a 4-slot shared-memory ring by twelve loader lanes, byte-offset tap
+    tables): same pixel arithmetic, so the outputs must be BIT-equal to the first build - on the reference fixtures, with
+    CTAs that walk up to six images (slot wrap-around, both ring buffers, the tail without a successor), per-image
+    jitter order from row 11, and at 64 x 64."""
+    from contrad_b200 import kernels as K
+    np.random.seed(1); torch.manual_seed(1)
+
+    def both(x, packed, order):
+        monkeypatch.setenv("CB200_AUGMENT_V", "1")
+        y1 = K.augment_simclr_fwd(x, packed, order)
+        monkeypatch.setenv("CB200_AUGMENT_V", "2")
+        y2 = K.augment_simclr_fwd(x, packed, order)
+        monkeypatch.delenv("CB200_AUGMENT_V")
+        return y1, y2
+
+    with emulated():
+        for case in _load(golden_dir, "augment_simclr.pt")["cases"]:
+            y1, y2 = both(case["x"], case["params"], case["order"])
+            assert torch.equal(y1, y2)
+            assert torch.allclose(y2, case["y"], atol=2e-5, rtol=0)
+        for B, size in ((1, 32), (25, 32), (131, 32), (14, 64)):
+            x = torch.rand(B, 3, size, size)
+            params, order = O.sample_simclr_params(B, size, size)
+            packed = O.pack_params(params)
+            y1, y2 = both(x, packed, order)
+            assert torch.equal(y1, y2), (B, size, float((y1 - y2).abs().max()))
+            per_image = torch.cat([packed, (torch.rand(1, B) < 0.5).float()])
+            y1, y2 = both(x, per_image, -1)
+            assert torch.equal(y1, y2), (B, size, "row 11")
+
+
 @pytest.mark.parametrize("B,H", [(3, 32), (2, 16)])
 def test_emulated_conv_first_layer(B, H):
     """csrc/conv_first.cu: Conv2d(3 -> 64) with the x*2-1 input affine, its weight / bias gradient (persistent CTAs,

@@ -62,6 +62,37 @@ def test_augment_matches_oracle_random(K, B, size, seed):
     assert bad < 2e-3, bad
 
 
+def test_augment_builds_are_bit_identical(K, golden_dir, monkeypatch):
+    """CB200_AUGMENT_V=1 | 2 (csrc/augment.cu: per-thread parameter loads / index tap tables vs parameters staged through a
+    shared-memory ring by twelve loader lanes / byte-offset tap tables / guard-free reciprocals): same pixel arithmetic, so
+    the outputs must be bit-equal - on the reference fixtures, on grids where every CTA walks many images (with the
+    per-image jitter order of the graph-replay mode), and at 64 x 64; whichever build is the default is thereby tied to
+    the fixtures through the other one as well."""
+    def both(x, p, order):
+        monkeypatch.setenv("CB200_AUGMENT_V", "1")
+        y1 = K.augment_simclr_fwd(x, p, order)
+        monkeypatch.setenv("CB200_AUGMENT_V", "2")
+        y2 = K.augment_simclr_fwd(x, p, order)
+        monkeypatch.delenv("CB200_AUGMENT_V")
+        return y1, y2
+
+    for case in _load(golden_dir, "augment_simclr.pt")["cases"]:
+        y1, y2 = both(case["x"].cuda(), case["params"].cuda(), case["order"])
+        assert torch.equal(y1, y2)
+        assert torch.allclose(y2.cpu(), case["y"], atol=2e-5, rtol=0)
+    import numpy as np
+    for B, size in ((1, 32), (889, 32), (1536, 32), (20000, 32), (700, 64)):
+        np.random.seed(B); torch.manual_seed(B)
+        x = torch.rand(B, 3, size, size, device="cuda")
+        params, order = O.sample_simclr_params(B, size, size)
+        packed = O.pack_params(params).cuda()
+        y1, y2 = both(x, packed, order)
+        assert torch.equal(y1, y2), (B, size, float((y1 - y2).abs().max()))
+        row = torch.cat([packed, (torch.rand(1, B, device="cuda") < 0.5).float()])
+        y1, y2 = both(x, row, -1)
+        assert torch.equal(y1, y2), (B, size, "row 11")
+
+
 def test_augment_large_path_matches_reference_golden(K, golden_dir):
     """The global-memory kernels (images > 64x64) forced onto the reference-generated small fixtures."""
     fx = _load(golden_dir, "augment_simclr.pt")
