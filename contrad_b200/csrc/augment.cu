@@ -578,8 +578,9 @@ augment_simclr_fwd_cols_kernel(const float* __restrict__ x, float* __restrict__ 
     }
 }
 
-// Second build of the same pipeline (CB200_AUGMENT_V=2).  SASS of the kernel above (profiles/prof_r2_augment.md: issue-
-// bound, 4 893 warp instructions per image) spends ~100 of its ~625 instructions per thread and image on the per-image
+// Second build of the same pipeline - the default since it was timed on the B200 (0.81 against 0.65 of the copy
+// bandwidth at 32 x 32, 0.71 against 0.60 at 64 x 64: profiles/augment_ab_r2.json); CB200_AUGMENT_V=1 selects the first.
+// SASS of the kernel above (profiles/prof_r2_augment.md: issue-bound, 4 893 warp instructions per image) spends ~100 of its ~625 instructions per thread and image on the per-image
 // parameters: every thread forms eleven 64-bit addresses `params + k*B + b` and loads the same eleven values, and ~24 on
 // turning tap indices into shared-memory addresses (buffer parity * 3HW + row + column, then scale + base).  Here
 //   * twelve lanes of the last warp fetch the parameter column of image `it + 2` (one LDG each) and park it in a
@@ -1250,10 +1251,10 @@ extern "C" int cb200_augment_simclr_fwd(const float* x, float* y, const float* p
         // 32x32: ncu showed the kernel occupancy-limited at 5 CTAs / SM by registers; the default build holds it to 40
         // registers (6 CTAs / SM, 4 bytes of spill); CB200_AUGMENT_OCC=5 selects the unconstrained build (A/B runs)
         static const int occ = []() { const char* e = getenv("CB200_AUGMENT_OCC"); return e ? atoi(e) : 6; }();
-        // CB200_AUGMENT_V=2: parameters staged through shared memory + byte-offset tap tables (bit-identical outputs)
+        // default build 2: parameters staged through shared memory + byte-offset tap tables (bit-identical outputs to build 1)
         // (read per call - one getenv - so that one process can compare the two builds)
         const char* ev = getenv("CB200_AUGMENT_V");
-        const int variant = ev ? atoi(ev) : 1;
+        const int variant = ev ? atoi(ev) : 2;
         if (variant == 2) {
             const size_t smem2 = smem + 64 * sizeof(float);
 #define LAUNCH_COLS2(SZ, OC, HV, GRID)                                                                                   \
