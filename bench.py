@@ -590,7 +590,8 @@ def roofline_legs(K, engine, W, one_step, pool, peaks):
     ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
     gbs = 8.0 * x.numel() / (ms * 1e-3) / 1e9
     out["roofline_augment"] = {"kernel": "augment_simclr_fwd", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": load_traffic("augment"),
+                               "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                               "traffic": load_traffic("augment_v2") or load_traffic("augment"),
                                "size": "B=65536 x 3x32x32 fp32 (805 MB in, 805 MB out), 8 algorithmic B/element",
                                "peak_note": "%s copy bandwidth" % peaks["source"]}
     return out
