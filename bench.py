@@ -594,6 +594,32 @@ def roofline_legs(K, engine, W, one_step, pool, peaks):
                                "traffic": load_traffic("augment_v2") or load_traffic("augment"),
                                "size": "B=65536 x 3x32x32 fp32 (805 MB in, 805 MB out), 8 algorithmic B/element",
                                "peak_note": "%s copy bandwidth" % peaks["source"]}
+    # the any-size path of the same chain at config 5's image size (two launches: per-image means, then apply), reported
+    # next to the small-image kernel; optional leg - a failure is recorded, it cannot take the line down
+    try:
+        Bl = 48
+        imgs = [torch.rand(Bl, 3, 512, 512, device="cuda") for _ in range(3)]      # 151 MB each: rotated, > L2
+        prm = torch.zeros(11, Bl, device="cuda")
+        prm[0] = 0.7; prm[1] = 0.8; prm[2] = 0.1; prm[3] = -0.1; prm[4] = 1.0; prm[5] = 1.0; prm[6] = 1.2; prm[7] = 0.05
+        prm[8] = 1.1; prm[9] = 0.9
+        prm[4, ::2] = -1.0; prm[10, ::5] = 1.0
+        for i in range(3):
+            K.augment_simclr_large_fwd(imgs[i], prm, 0)
+        evs = []
+        for i in range(9):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); K.augment_simclr_large_fwd(imgs[i % 3], prm, 0); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        ms_l = float(np.median([a.elapsed_time(b) for a, b in evs]))
+        gbs_l = 8.0 * imgs[0].numel() / (ms_l * 1e-3) / 1e9
+        out["roofline_augment_large"] = {"kernel": "augment_large_mean + augment_large_apply", "bound": "hbm", "achieved": gbs_l,
+                                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs_l / peaks["hbm_gbs"],
+                                         "traffic": load_traffic("augment_large"), "ms": ms_l,
+                                         "size": "B=48 x 3x512x512 fp32, 8 algorithmic B/element, colour jitter on every image"}
+        del imgs
+    except Exception as e:                                    # noqa: BLE001
+        out["roofline_augment_large"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return out
 
 
