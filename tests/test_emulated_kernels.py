@@ -449,6 +449,38 @@ def test_emulated_fused_augment_second_build_is_bit_identical(golden_dir, monkey
             assert torch.equal(y1, y2), (B, size, "row 11")
 
 
+def test_emulated_empty_and_malformed_inputs_are_noops_or_loud_errors():
+    """Edge cases at the C ABI: an empty batch is a no-op for the augmentation entry points (torch returns empty tensors
+    for them too) and a CB200Error with a message for the convolution / reduction / optimiser entry points (the
+    reference's step has no meaning on an empty batch: its losses are means over zero rows); malformed parameter blocks
+    and unsupported shapes are refused before any launch.  Never a crash, never a silent wrong answer."""
+    from contrad_b200 import kernels as K
+    from contrad_b200._capi import CB200Error
+    with emulated():
+        p0 = torch.zeros(11, 0)
+        e = torch.zeros(0, 3, 32, 32)
+        assert K.augment_simclr_fwd(e, p0, 0).shape == (0, 3, 32, 32)
+        assert K.augment_simclr_bwd(e, e, p0, 0).shape == (0, 3, 32, 32)
+        y, means = K.augment_simclr_large_fwd(torch.zeros(0, 3, 40, 40), p0, 0)
+        assert y.shape == (0, 3, 40, 40) and means.shape == (0, 3)
+        for bad in (lambda: K.conv_first_fwd(e, torch.randn(64, 3, 3, 3), None, torch.zeros(64)),
+                    lambda: K.conv_first_wgrad(e, torch.zeros(0, 32, 32, 64)),
+                    lambda: K.colsum(torch.zeros(0, 64)),
+                    lambda: K.adam_step([], 1e-3, 0.5, 0.999, 1e-8, 1),
+                    lambda: K.split_tf32(torch.zeros(0, 32), 0)):
+            with pytest.raises(CB200Error):
+                bad()
+        x = torch.rand(2, 3, 32, 32)
+        with pytest.raises(AssertionError):                 # parameter block with the wrong number of rows / samples
+            K.augment_simclr_fwd(x, torch.zeros(11, 3), 0)
+        with pytest.raises(AssertionError):
+            K.augment_simclr_fwd(x, torch.zeros(11, 2), -1)  # per-image order needs row 11
+        with pytest.raises(CB200Error):                     # the fused small-image kernels stop at 64 x 64
+            K.augment_simclr_fwd(torch.rand(1, 3, 128, 128), torch.zeros(11, 1), 0)
+        with pytest.raises(CB200Error):                     # width must be a multiple of 4 (float4 rows)
+            K.augment_simclr_fwd(torch.rand(1, 3, 30, 30), torch.zeros(11, 1), 0)
+
+
 @pytest.mark.parametrize("B,H", [(3, 32), (2, 16)])
 def test_emulated_conv_first_layer(B, H):
     """csrc/conv_first.cu: Conv2d(3 -> 64) with the x*2-1 input affine, its weight / bias gradient (persistent CTAs,
