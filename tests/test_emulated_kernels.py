@@ -181,6 +181,45 @@ def test_emulated_contrastive_losses(golden_dir):
         assert torch.allclose(K.contrastive_bwd(z3, n, 1, 0.1, lse, one), torch.cat(g2, 0), atol=1e-7, rtol=1e-3)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 33])
+def test_emulated_contrastive_edge_cases(n):
+    """Collisions and degenerate batches of the contrastive losses (training/criterion.py:24-45, training/gan/contrad.py:8-32)
+    against the oracle: a single pair (NT-Xent's softmax row then has exactly one entry besides the masked diagonal),
+    duplicated embeddings (every off-diagonal similarity 1: the positives are indistinguishable from the negatives),
+    antipodal views (similarity -1 at the positive), and a temperature small enough that the largest logit is +-100 - the
+    log-sum-exp must stay finite.  supcon_fake with ONE fake has no positive: NaN in the reference, NaN here."""
+    from contrad_b200 import kernels as K
+    one = torch.ones(1)
+    torch.manual_seed(100 + n)
+    base = F.normalize(torch.randn(n, 128))
+    cases = {"random": tuple(F.normalize(torch.randn(n, 128)) for _ in range(3)),
+             "duplicates": (base[:1].expand(n, 128).contiguous(),) * 3,
+             "identical views": (base, base.clone(), F.normalize(torch.randn(n, 128))),
+             "antipodal views": (base, -base, F.normalize(torch.randn(n, 128)))}
+    with emulated():
+        for name, (a, b, c) in cases.items():
+            for temp in (0.1, 0.01):
+                ar, br, cr = (t.clone().requires_grad_(True) for t in (a, b, c))
+                l1 = O.nt_xent(ar, br, temp); g1 = torch.autograd.grad(l1, [ar, br])
+                z = torch.cat([a, b], 0)
+                loss, lse = K.contrastive_fwd(z, n, 0, temp)
+                assert torch.isfinite(loss) and torch.isfinite(lse).all(), (name, temp)
+                assert abs(float(loss) - float(l1)) < 2e-5 * max(1.0, abs(float(l1))), (name, temp, float(loss), float(l1))
+                g = K.contrastive_bwd(z, n, 0, temp, lse, one)
+                assert torch.allclose(g, torch.cat(g1, 0), atol=2e-5 / temp * 0.1, rtol=1e-3), (name, temp)
+                ar, br, cr = (t.clone().requires_grad_(True) for t in (a, b, c))
+                l2 = O.supcon_fake(ar, br, cr, temp); g2 = torch.autograd.grad(l2, [ar, br, cr])
+                z3 = torch.cat([a, b, c], 0)
+                loss, lse = K.contrastive_fwd(z3, n, 1, temp)
+                if n == 1:      # a single fake has no positive: the reference divides its mask row by 0 (contrad.py:26) -> NaN
+                    assert torch.isnan(l2) and torch.isnan(loss).all(), (name, temp, float(loss), float(l2))
+                    continue
+                assert torch.isfinite(loss) and torch.isfinite(lse).all(), (name, temp)
+                assert abs(float(loss) - float(l2)) < 2e-5 * max(1.0, abs(float(l2))), (name, temp, float(loss), float(l2))
+                g = K.contrastive_bwd(z3, n, 1, temp, lse, one)
+                assert torch.allclose(g, torch.cat(g2, 0), atol=2e-5 / temp * 0.1, rtol=1e-3), (name, temp)
+
+
 def test_emulated_rownorm_gan_losses_colsum_lrelu():
     from contrad_b200 import kernels as K
     torch.manual_seed(0)
