@@ -63,6 +63,38 @@ def test_contrastive_losses_match_reference(golden_dir):
         assert abs(float(O.nt_xent(a, b, 0.5)) - case["nt_xent_t05"]) < 1e-5
 
 
+@pytest.mark.parametrize("n", [1, 2, 33])
+def test_contrastive_oracle_equals_reference_on_degenerate_batches(n):
+    """The oracle against the UNMODIFIED reference functions (training/criterion.py:24-45, training/gan/contrad.py:8-32;
+    oracle/_ref or /root/reference, skipped when neither exists) where the fixtures do not reach: a single pair, duplicated
+    and antipodal embeddings, tau = 0.01.  supcon_fake with one fake row is NaN in the reference (its mask row sums to
+    zero) - the oracle must say the same.  tests/test_emulated_kernels.py holds the kernels to the oracle on these inputs."""
+    from oracle import ref_import
+    if not ref_import.reference_available():
+        pytest.skip("reference sources not available")
+    ref_import.activate()
+    try:
+        from training.criterion import nt_xent as ref_nt_xent
+        from training.gan.contrad import supcon_fake as ref_supcon
+        torch.manual_seed(100 + n)
+        base = F.normalize(torch.randn(n, 128))
+        cases = [tuple(F.normalize(torch.randn(n, 128)) for _ in range(3)),
+                 (base[:1].expand(n, 128).contiguous(),) * 3,
+                 (base, base.clone(), F.normalize(torch.randn(n, 128))),
+                 (base, -base, F.normalize(torch.randn(n, 128)))]
+        for a, b, c in cases:
+            for temp in (0.1, 0.01):
+                r1, o1 = ref_nt_xent(a, b, temperature=temp), O.nt_xent(a, b, temp)
+                assert torch.allclose(o1, r1, atol=1e-6, rtol=1e-5), (n, temp, float(o1), float(r1))
+                r2, o2 = ref_supcon(a, b, c, temp), O.supcon_fake(a, b, c, temp)
+                if n == 1:
+                    assert torch.isnan(r2) and torch.isnan(o2)
+                else:
+                    assert torch.allclose(o2, r2, atol=1e-6, rtol=1e-5), (n, temp, float(o2), float(r2))
+    finally:
+        ref_import.deactivate()
+
+
 def test_spectral_norm_matches_torch_hook(golden_dir):
     fx = _load(golden_dir, "spectral_norm.pt")
     for name, rec in fx.items():
