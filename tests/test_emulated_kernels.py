@@ -488,6 +488,41 @@ def test_emulated_fused_augment_second_build_is_bit_identical(golden_dir, monkey
             assert torch.equal(y1, y2), (B, size, "row 11")
 
 
+def test_emulated_fused_augment_on_degenerate_images(monkeypatch):
+    """tests/edge_inputs.py (colour-cube corners = breakpoints of the colour wheel, saturation-0 images whose hue is
+    undefined, a 0/1 checkerboard, stripes): both builds of the fused forward kernel, the backward, the any-size path and
+    the uint8 / mixed-source launch against the oracle, which tests/test_oracle_golden.py pins on the unmodified reference
+    chain for the very same images."""
+    from contrad_b200 import kernels as K
+    from tests.edge_inputs import degenerate_images
+    x = degenerate_images()
+    B, size = x.shape[0], x.shape[-1]
+    with emulated():
+        for seed in (1, 2):
+            np.random.seed(seed); torch.manual_seed(seed)
+            params, order = O.sample_simclr_params(B, size, size)
+            packed = O.pack_params(params)
+            xr = x.clone().requires_grad_(True)
+            yr = O.augment_simclr(xr, params, order)
+            dy = torch.randn(yr.shape)
+            (yr * dy).sum().backward()
+            for build in ("1", "2"):
+                monkeypatch.setenv("CB200_AUGMENT_V", build)
+                y = K.augment_simclr_fwd(x, packed, order)
+                assert torch.allclose(y, yr.detach(), atol=2e-5, rtol=0), (build, float((y - yr).abs().max()))
+            monkeypatch.delenv("CB200_AUGMENT_V")
+            dx = K.augment_simclr_bwd(x, dy, packed, order)
+            bad = ((dx - xr.grad).abs() > 1e-4 + 1e-4 * xr.grad.abs()).float().mean()
+            assert bad < 5e-3, float(bad)                # pixels exactly ON the clamp boundary (0 / 1 images) may flip their mask
+            y2, _ = K.augment_simclr_large_fwd(x, packed, order)
+            assert torch.allclose(y2, yr.detach(), atol=2e-5, rtol=0)
+            exact = (x == 0) | (x == 1)                  # images that ToTensor can produce from bytes
+            keep = exact.flatten(1).all(1).nonzero().flatten()
+            x_u8 = (x[keep] * 255).to(torch.uint8)
+            y_u8, _ = K.augment_simclr_mixed_fwd(x_u8, len(keep), x[:0], packed[:, keep].contiguous(), order)
+            assert torch.allclose(y_u8, yr.detach()[keep], atol=2e-5, rtol=0)
+
+
 def test_emulated_empty_and_malformed_inputs_are_noops_or_loud_errors():
     """Edge cases at the C ABI: an empty batch is a no-op for the augmentation entry points (torch returns empty tensors
     for them too) and a CB200Error with a message for the convolution / reduction / optimiser entry points (the

@@ -95,6 +95,36 @@ def test_contrastive_oracle_equals_reference_on_degenerate_batches(n):
         ref_import.deactivate()
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_augment_oracle_equals_reference_on_degenerate_images(seed):
+    """The oracle's SimCLR chain against the UNMODIFIED reference's `get_augment('simclr')` (augment/__init__.py:95-112,
+    skipped when the reference is absent) on images the random fixtures never contain (tests/edge_inputs.py).  The
+    oracle's sampler replays the reference's draws after the same seed (as in tests/golden/make_golden.py)."""
+    from oracle import ref_import
+    if not ref_import.reference_available():
+        pytest.skip("reference sources not available")
+    from tests.edge_inputs import degenerate_images
+    x = degenerate_images()
+    B, size = x.shape[0], x.shape[-1]
+    ref_import.activate()
+    try:
+        from augment import get_augment
+        aug = get_augment(mode="simclr")
+        np.random.seed(seed); torch.manual_seed(seed)
+        params, order = O.sample_simclr_params(B, size, size)
+        np.random.seed(seed); torch.manual_seed(seed)
+        xr = x.clone().requires_grad_(True)
+        y_ref = aug(xr)
+        xo = x.clone().requires_grad_(True)
+        y = O.augment_simclr(xo, params, order)
+        assert torch.allclose(y, y_ref, atol=5e-6, rtol=0), float((y - y_ref).abs().max())
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(seed))
+        (y_ref * dy).sum().backward(); (y * dy).sum().backward()
+        assert torch.allclose(xo.grad, xr.grad, atol=1e-4, rtol=1e-4), float((xo.grad - xr.grad).abs().max())
+    finally:
+        ref_import.deactivate()
+
+
 def test_spectral_norm_matches_torch_hook(golden_dir):
     fx = _load(golden_dir, "spectral_norm.pt")
     for name, rec in fx.items():
