@@ -523,6 +523,31 @@ def test_emulated_fused_augment_on_degenerate_images(monkeypatch):
             assert torch.allclose(y_u8, yr.detach()[keep], atol=2e-5, rtol=0)
 
 
+@pytest.mark.parametrize("kind", ["nonsat", "hinge", "wgan", "lsgan"])
+def test_emulated_gan_losses_at_extreme_logits(kind):
+    """L_dis / L_gen (training/gan/contrad.py:52-64,73-81) where torch's softplus switches branches (|x| = 20), where
+    exp() overflows in fp32 (|x| > 88.7) and far beyond: values and logit gradients against torch, no inf / NaN."""
+    from contrad_b200 import kernels as K
+    v = torch.tensor([-1e4, -100., -88.8, -20.0001, -19.9999, -1., -1e-8, 0., 1e-8, 1., 19.9999, 20.0001, 88.8, 100., 1e4])
+    scale = float(v.abs().sum()) if kind != "lsgan" else float((v ** 2).sum())
+    with emulated():
+        dr, dg = v.clone().requires_grad_(True), v.flip(0).clone().requires_grad_(True)
+        ref = {"nonsat": lambda: F.softplus(dg).mean() + F.softplus(-dr).mean(),
+               "wgan": lambda: dg.mean() - dr.mean(),
+               "hinge": lambda: F.relu(1. + dg).mean() + F.relu(1. - dr).mean(),
+               "lsgan": lambda: 0.5 * (((dr - 1.0) ** 2).mean() + (dg ** 2).mean())}[kind]()
+        ref.backward()
+        out, g_r, g_g = K.gan_d_loss(v.clone(), v.flip(0).clone(), kind)
+        assert torch.isfinite(out).all() and abs(float(out[0]) - float(ref.detach())) < 1e-6 * scale
+        assert torch.allclose(g_r, dr.grad, atol=1e-7, rtol=1e-6) and torch.allclose(g_g, dg.grad, atol=1e-7, rtol=1e-6)
+        d = v.clone().requires_grad_(True)
+        rg = {"nonsat": lambda: F.softplus(-d).mean(), "lsgan": lambda: 0.5 * ((d - 1.0) ** 2).mean()}.get(kind, lambda: -d.mean())()
+        rg.backward()
+        out, g = K.gan_g_loss(v.clone(), kind)
+        assert torch.isfinite(out).all() and abs(float(out[0]) - float(rg.detach())) < 1e-6 * scale
+        assert torch.allclose(g, d.grad, atol=1e-7, rtol=1e-6)
+
+
 def test_emulated_empty_and_malformed_inputs_are_noops_or_loud_errors():
     """Edge cases at the C ABI: an empty batch is a no-op for the augmentation entry points (torch returns empty tensors
     for them too) and a CB200Error with a message for the convolution / reduction / optimiser entry points (the
