@@ -352,3 +352,46 @@ def test_product_stylegan2_on_emulated_kernels(fx, states):
         total = math.sqrt(sum(float(p.grad.double().pow(2).sum()) for p in G.parameters() if p.grad is not None))
         want = math.sqrt(sum(n * n for n in c["grad_norms"].values()))
         assert abs(total - want) < 2e-2 * want, (total, want)
+
+
+# ------------------------------------------------------------------ the stand-ins themselves against the reference's native ops
+def _reference_function(rel_path, name):
+    """Compile ONE pure-Python function of the unmodified reference without importing its module (importing
+    models/gan/stylegan2/op JIT-builds two CUDA extensions).  Test infrastructure; skipped without the reference."""
+    import ast
+    from oracle import ref_import
+    path = os.path.join(ref_import.REFERENCE_ROOT, rel_path)
+    if not os.path.exists(path):
+        pytest.skip("reference sources not available")
+    tree = ast.parse(open(path).read())
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "F": F}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def test_standins_equal_reference_native_ops():
+    """The kernel-level GPU tests of csrc/sg2_ops.cu compare with tests/cpu_kernels.py; this ties those stand-ins to the
+    reference's own CPU code: `upfirdn2d_native` (models/gan/stylegan2/op/upfirdn2d.py:159-200: zero-stuffing, signed
+    padding, flipped-kernel correlation, decimation) for every (up, down, pad) the two networks use and a few they do
+    not, and `fused_leaky_relu` (op/fused_act.py:86-92)."""
+    native = _reference_function("models/gan/stylegan2/op/upfirdn2d.py", "upfirdn2d_native")
+    flr = _reference_function("models/gan/stylegan2/op/fused_act.py", "fused_leaky_relu")
+    torch.manual_seed(0)
+    k1 = torch.tensor([1., 3., 3., 1.])
+    k2 = k1[None] * k1[:, None]
+    k2 = k2 / k2.sum()
+    asym = torch.randn(3, 4)                                    # not symmetric: catches a missing kernel flip
+    for H, W in ((9, 11), (8, 8)):
+        x = torch.randn(2, 5, H, W)
+        for fir in (k2, asym):
+            for up, down, pad in ((1, 1, (2, 1)), (1, 1, (2, 2)), (1, 1, (1, 1)), (2, 1, (2, 1)), (1, 2, (1, 1)), (1, 2, (2, 2)),
+                                  (2, 2, (0, 3)), (1, 1, (-1, 2)), (3, 2, (1, -1))):
+                ref = native(x, fir, up, up, down, down, pad[0], pad[1], pad[0], pad[1])          # NCHW in, NCHW out
+                got = CK.upfirdn2d(x.permute(0, 2, 3, 1).contiguous(), fir, up, down, (pad[0], pad[1], pad[0], pad[1]))
+                assert got.shape[1:3] == ref.shape[2:], (up, down, pad)
+                assert torch.allclose(got.permute(0, 3, 1, 2), ref, atol=1e-6, rtol=1e-6), (up, down, pad)
+    x, bias = torch.randn(3, 7, 6, 6), torch.randn(7)
+    ref = flr(x, bias, 0.2, 2 ** 0.5)
+    got = CK.bias_act(x.permute(0, 2, 3, 1).contiguous(), bias, 0.2, 2 ** 0.5)
+    assert torch.allclose(got.permute(0, 3, 1, 2), ref, atol=1e-6, rtol=1e-6)
